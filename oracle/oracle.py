@@ -1,0 +1,162 @@
+"""ctypes binding of the CPU oracle (oracle/tm_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/tm_oracle.h.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module.  PARITY UNPINNED (the
+reference holds no golden vectors for this path; upstream QUDA is not vendored).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libtm_oracle.so")
+
+# UKQCD gamma matrices, mu = x,y,z,t  (reference lib/code_pieces/gammas_tm_base.h:21-32)
+def gamma_ukqcd():
+    g = np.zeros((4, 4, 4), dtype=np.complex128)
+    i = 1j
+    g[0][0][3] = i; g[0][1][2] = i; g[0][2][1] = -i; g[0][3][0] = -i
+    g[1][0][3] = 1; g[1][1][2] = -1; g[1][2][1] = -1; g[1][3][0] = 1
+    g[2][0][2] = i; g[2][1][3] = -i; g[2][2][0] = -i; g[2][3][1] = i
+    g[3][0][0] = 1; g[3][1][1] = 1; g[3][2][2] = -1; g[3][3][3] = -1
+    return g
+
+# DeGrand-Rossi gamma matrices (chiral; gamma5 diagonal) -- used only for the change-of-basis check
+def gamma_degrand_rossi():
+    g = np.zeros((4, 4, 4), dtype=np.complex128)
+    i = 1j
+    g[0] = [[0, 0, 0, i], [0, 0, i, 0], [0, -i, 0, 0], [-i, 0, 0, 0]]
+    g[1] = [[0, 0, 0, -1], [0, 0, 1, 0], [0, 1, 0, 0], [-1, 0, 0, 0]]
+    g[2] = [[0, 0, i, 0], [0, 0, 0, -i], [-i, 0, 0, 0], [0, i, 0, 0]]
+    g[3] = [[0, 0, 1, 0], [0, 0, 0, 1], [1, 0, 0, 0], [0, 1, 0, 0]]
+    return g
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("tm_oracle.c", "tm_oracle.h", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        dp = C.POINTER(C.c_double)
+        dpp = C.POINTER(dp)
+        L.orc_set_lattice.argtypes = [C.POINTER(C.c_int)]
+        L.orc_full_lattice_index.argtypes = [C.c_int, C.c_int]
+        L.orc_neighbor_index.argtypes = [C.c_int] * 6
+        L.orc_set_gamma.argtypes = [dp]
+        L.orc_get_gamma5.argtypes = [dp]
+        L.orc_apply_t_boundary.argtypes = [dpp, C.c_int]
+        L.orc_su3_reconstruct12.argtypes = [dp, C.c_double]
+        L.orc_plaquette.argtypes = [dpp]; L.orc_plaquette.restype = C.c_double
+        L.orc_dslash.argtypes = [dp, dpp, dp, C.c_int, C.c_int]
+        L.orc_twist_gamma5.argtypes = [dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.orc_tm_dslash.argtypes = [dp, dpp, dp, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.orc_tm_matpc.argtypes = [dp, dpp, dp, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.orc_tm_mdagm.argtypes = [dp, dpp, dp, C.c_double, C.c_double, C.c_int]
+        L.orc_tm_mat.argtypes = [dp, dpp, dp, C.c_double, C.c_double, C.c_int]
+        L.orc_prepare.argtypes = [dp, dpp, dp, C.c_double, C.c_double, C.c_int]
+        L.orc_reconstruct.argtypes = [dp, dpp, dp, C.c_double, C.c_double, C.c_int]
+        L.orc_norm2.argtypes = [dp, C.c_long]; L.orc_norm2.restype = C.c_double
+        L.orc_redot.argtypes = [dp, dp, C.c_long]; L.orc_redot.restype = C.c_double
+        L.orc_cdot.argtypes = [dp, dp, C.c_long, dp]
+        L.orc_cg_mdagm.argtypes = [dp, dpp, dp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int,
+                                   C.c_int, dp, dp]
+        L.orc_cg_mdagm.restype = C.c_int
+        L.orc_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _gpp(gauge):
+    """gauge: float64 array [4][V][3][3][2] in QDP even-odd order -> double*[4]"""
+    assert gauge.dtype == np.float64 and gauge.flags["C_CONTIGUOUS"] and gauge.shape[0] == 4
+    arr = (C.POINTER(C.c_double) * 4)()
+    for mu in range(4):
+        arr[mu] = gauge[mu].ctypes.data_as(C.POINTER(C.c_double))
+    return arr
+
+
+class Oracle:
+    """Stateful wrapper: one lattice + one gamma basis at a time (the C side uses globals, like
+    the reference's Z[]/V/Vh in qkxtm/QKXTM_util.cpp:28-44)."""
+
+    def __init__(self, X, gamma=None):
+        self.L = lib()
+        self.X = tuple(int(x) for x in X)
+        self.V = int(np.prod(self.X)); self.Vh = self.V // 2
+        self.L.orc_set_lattice((C.c_int * 4)(*self.X))
+        self.set_gamma(gamma_ukqcd() if gamma is None else gamma)
+
+    def set_gamma(self, g):
+        a = np.ascontiguousarray(np.stack([g.real, g.imag], axis=-1), dtype=np.float64)
+        self.L.orc_set_gamma(_dp(a))
+
+    def gamma5(self):
+        a = np.zeros((4, 4, 2)); self.L.orc_get_gamma5(_dp(a)); return a[..., 0] + 1j * a[..., 1]
+
+    def full_index(self, i, odd): return self.L.orc_full_lattice_index(i, odd)
+    def neighbor_index(self, i, odd, dx4, dx3, dx2, dx1): return self.L.orc_neighbor_index(i, odd, dx4, dx3, dx2, dx1)
+
+    def apply_t_boundary(self, gauge, sign=-1): self.L.orc_apply_t_boundary(_gpp(gauge), sign)
+    def plaquette(self, gauge): return self.L.orc_plaquette(_gpp(gauge))
+
+    def reconstruct12(self, mat18, u0=1.0):
+        m = np.array(mat18, dtype=np.float64).reshape(18).copy(); self.L.orc_su3_reconstruct12(_dp(m), u0); return m
+
+    def _par(self): return np.empty((self.Vh, 4, 3, 2), dtype=np.float64)
+    def _full(self): return np.empty((2 * self.Vh, 4, 3, 2), dtype=np.float64)
+
+    def dslash(self, gauge, psi, odd_bit, dagger=0):
+        out = self._par(); self.L.orc_dslash(_dp(out), _gpp(gauge), _dp(psi), odd_bit, dagger); return out
+
+    def twist(self, psi, kappa, mu, dagger=0, inverse=0):
+        out = np.empty_like(psi); n = psi.size // 24
+        self.L.orc_twist_gamma5(_dp(out), _dp(psi), dagger, kappa, mu, inverse, n); return out
+
+    def tm_dslash(self, gauge, psi, kappa, mu, odd_bit, dagger=0):
+        out = self._par(); self.L.orc_tm_dslash(_dp(out), _gpp(gauge), _dp(psi), kappa, mu, odd_bit, dagger); return out
+
+    def matpc(self, gauge, psi, kappa, mu, matpc=0, dagger=0):
+        out = self._par(); self.L.orc_tm_matpc(_dp(out), _gpp(gauge), _dp(psi), kappa, mu, matpc, dagger); return out
+
+    def mdagm(self, gauge, psi, kappa, mu, matpc=0):
+        out = self._par(); self.L.orc_tm_mdagm(_dp(out), _gpp(gauge), _dp(psi), kappa, mu, matpc); return out
+
+    def mat(self, gauge, psi, kappa, mu, dagger=0):
+        out = self._full(); self.L.orc_tm_mat(_dp(out), _gpp(gauge), _dp(psi), kappa, mu, dagger); return out
+
+    def prepare(self, gauge, b, kappa, mu, matpc=0):
+        out = self._par(); self.L.orc_prepare(_dp(out), _gpp(gauge), _dp(b), kappa, mu, matpc); return out
+
+    def reconstruct(self, gauge, x_full, b, kappa, mu, matpc=0):
+        self.L.orc_reconstruct(_dp(x_full), _gpp(gauge), _dp(b), kappa, mu, matpc); return x_full
+
+    def norm2(self, x): return self.L.orc_norm2(_dp(x), x.size)
+    def redot(self, x, y): return self.L.orc_redot(_dp(x), _dp(y), x.size)
+    def cdot(self, x, y):
+        o = np.zeros(2); self.L.orc_cdot(_dp(x), _dp(y), x.size, _dp(o)); return complex(o[0], o[1])
+
+    def cg_mdagm(self, gauge, b, kappa, mu, matpc=0, tol=1e-7, maxiter=10000, pr_beta=0):
+        x = self._par(); tr = C.c_double(0.0)
+        hist = np.zeros(maxiter + 2)
+        it = self.L.orc_cg_mdagm(_dp(x), _gpp(gauge), _dp(b), kappa, mu, matpc, tol, maxiter, pr_beta,
+                                 C.byref(tr), _dp(hist))
+        return x, it, tr.value, hist[: it + 1]
+
+    def num_threads(self): return self.L.orc_num_threads()
