@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- the even-odd twisted-mass Dslash inside CG on M^dag M, 48^3x96 fp64 (BASELINE.json metric).
+
+One JSON line on stdout (rank 0).  Definitions (DESIGN.md section "Measurement"):
+  step     one CG iteration on M_pc^dag M_pc = 4 even-odd TM Dslash launches (fused twists / xpay /
+           reductions) + 1 fused update launch, on a resident 48^3x96 (global) lattice, no host sync
+  value    GFLOP/s over the K timed steps, QUDA flop model 5904 flop per parity site per iteration
+           (SURVEY.md 8d), CUDA events on the launching stream, max over ranks
+  e2e      the same metric through the host-facing call: pinned host source -> H2D -> prepare -> M^dag ->
+           CG to tol (real iteration count) -> reconstruct -> D2H of the solution; copies inside the timed
+           region; flops = 5904 x Vh x iterations
+  roofline the hop + A^-1 Dslash kernel (EPI_TW, half of all Dslash launches) timed alone with CUDA events:
+           algorithmic bytes (24 + 24 + 8*12) * 8 = 1152 B per output parity site (fp64, recon 12)
+  cpu_baseline / --impl reference: the CPU oracle (oracle/, a port: the reference's own host code cannot be
+           built here) running CG iterations on the box's host cores
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "quda-qkxtm-multigrid-plugin_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+KAPPA = 1.0 / (2.0 * (4.0 + 0.1))
+MU = 0.1
+FLOPS_ITER = 5904.0           # per parity site per CG iteration (M^dag M 5664 + blas 240)
+FLOPS_K = {0: 1320.0, 1: 1392.0, 2: 1440.0}
+KNAME = {0: "K1 hop", 1: "K2 hop+A^-1", 2: "K3 hop+A^-1+xpay"}
+
+
+def bytes_per_site(kind, prec, recon):
+    spinors = {0: 2, 1: 2, 2: 3}[kind]
+    return (24 * spinors + 8 * recon) * prec
+
+
+def step_bytes_per_site(prec, recon):
+    # K1 (in,out) + K2 (in,x,out) + K3 (in,out) + K4 (in,x,r read,r write) + update (x,p r/w, r read) + 4 gauge sweeps
+    return (24 * (2 + 3 + 2 + 4 + 5) + 4 * 8 * recon) * prec
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples drawing more than half of the maximum observed power
+        pmax = max(power)
+        load = [s for s, p in zip(sm, power) if p >= 0.5 * pmax] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(smax)), "power_w_max": pmax,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def choose_grid(n):
+    """T first, then Z (BASELINE.json: 'sharded along T, then Z')."""
+    return {1: (1, 1, 1, 1), 2: (1, 1, 1, 2), 4: (1, 1, 1, 4), 8: (1, 1, 1, 8)}[n]
+
+
+def dist_setup(n):
+    if n == 1:
+        return None, 0
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group(backend="gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    assert dist.get_world_size() == n, "launch with torchrun --nproc-per-node %d" % n
+    return dist, dist.get_rank()
+
+
+def dist_max(dist, v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([float(v)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def dist_sum(dist, v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([float(v)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_cg_sample(X, budget_s, gauge=None, rhs=None, iters=None):
+    """the CPU oracle (port) timed on this box: `iters` CG iterations (or as many as fit in budget_s)."""
+    from oracle.oracle import Oracle
+    import tmq
+    o = Oracle(X)
+    if gauge is None:
+        gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1)
+    if rhs is None:
+        rhs = np.ascontiguousarray(tmq.gen_spinor(X, "z4", seed=100)[: o.Vh])
+    t0 = time.perf_counter()
+    o.mdagm(gauge, rhs, KAPPA, MU, 0)                      # calibration (and page-in)
+    t1 = time.perf_counter() - t0
+    if iters is None:
+        iters = int(max(2, min(50, budget_s / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    _, it, _, _ = o.cg_mdagm(gauge, rhs, KAPPA, MU, 0, tol=1e-30, maxiter=iters)
+    dt = time.perf_counter() - t0
+    gf = FLOPS_ITER * o.Vh * it / dt * 1e-9
+    return {"value": gf, "unit": "GFLOP/s", "cores": o.num_threads(), "kind": "port",
+            "sample": "%dx%dx%dx%d fp64, %d CG iterations on MdagM (%.2f s)" % (X + (it, dt)), "ms_per_iter": dt / it * 1e3}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  Its own host Dslash/CG is upstream QUDA
+    (tests/wilson_dslash_reference.cpp), absent from /root/reference and not buildable here, so the timed code
+    is the oracle port with all host threads.  Each step = one CPU CG iteration on a bounded sample lattice."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    from oracle.oracle import Oracle
+    import tmq
+    # choose the largest sample lattice whose (steps + warmup) iterations fit in ~150 s
+    ladder = [(48, 48, 48, 96), (32, 32, 32, 64), (24, 24, 24, 48), (16, 16, 16, 32), (8, 8, 8, 16)]
+    Xc = (16, 16, 16, 32)
+    o = Oracle(Xc)
+    g = tmq.gen_gauge(Xc); r = np.ascontiguousarray(tmq.gen_spinor(Xc, "z4")[: o.Vh])
+    o.mdagm(g, r, KAPPA, MU, 0)
+    t0 = time.perf_counter(); o.mdagm(g, r, KAPPA, MU, 0); per_site = (time.perf_counter() - t0) / o.Vh
+    X = ladder[-1]
+    for cand in ladder:
+        if per_site * (np.prod(cand) / 2) * (steps + warm + 2) * 1.3 < 150.0:
+            X = cand
+            break
+    o = Oracle(X)
+    gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1)
+    rhs = np.ascontiguousarray(tmq.gen_spinor(X, "z4", seed=100)[: o.Vh])
+    if warm > 0:
+        o.cg_mdagm(gauge, rhs, KAPPA, MU, 0, tol=1e-30, maxiter=warm)
+    t0 = time.perf_counter()
+    _, it, _, _ = o.cg_mdagm(gauge, rhs, KAPPA, MU, 0, tol=1e-30, maxiter=steps)
+    dt = time.perf_counter() - t0
+    gf = FLOPS_ITER * o.Vh * it / dt * 1e-9
+    sample = "%dx%dx%dx%d fp64 sample of the 48x48x48x96 workload, %d CG iterations on MdagM per run" % (X + (it,))
+    line = {"impl": "reference", "metric": "tm_dslash_cg_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt / max(it, 1) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "48x48x48x96 even-odd twisted-mass Dslash in CG on MdagM, fp64 (CPU sample: %dx%dx%dx%d)" % X,
+                       "kappa": KAPPA, "mu": MU, "matpc": "even-even"},
+            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": o.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import tmq
+    n = args.gpus
+    dist, rank = dist_setup(n)
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    GX = tuple(args.lattice)
+    grid = tuple(args.grid) if args.grid else choose_grid(n)
+    assert int(np.prod(grid)) == n
+    if args.scaling == "weak":
+        X = GX
+        GX = tuple(GX[d] * grid[d] for d in range(4))
+    else:
+        assert all(GX[d] % grid[d] == 0 for d in range(4))
+        X = tuple(GX[d] // grid[d] for d in range(4))
+    coord = (0, 0, (rank // grid[3]) % grid[2], rank % grid[3])
+    prec, recon = args.prec, args.recon
+    Vh_loc = int(np.prod(X)) // 2
+    Vh_glob = int(np.prod(GX)) // 2
+
+    ctx = tmq.Context(X, grid=grid, coord=coord, device=local_rank)
+    if n > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(tmq.comm_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(uid, src=0)
+        ctx.comm_init(bytes(uid.numpy().tobytes()), n, rank)
+    if args.tile:
+        ctx.set_tile(*args.tile)
+    gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1, grid=grid, coord=coord)
+    ctx.load_gauge(gauge, t_boundary=-1, recon=recon)
+    ctx.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
+    src_full = tmq.gen_spinor(X, "z4", seed=100, grid=grid, coord=coord)
+    b_par = ctx.spinor(8); b_par.set(src_full[:Vh_loc])
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- value: K fused CG iterations, device resident, CUDA events inside libtmq on its own stream
+    sampler = ClockSampler(local_rank)
+    ctx.time_kernel(4, prec, max(args.warmup, 3), b_par)          # untimed warm-up steps
+    barrier()
+    l0 = ctx.launch_count()
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    ms_step, launches_per_step = ctx.time_kernel(4, prec, args.steps, b_par)
+    barrier()
+    wall = time.perf_counter() - wall0
+    # per-kernel timings (same stream, CUDA events), used for the roofline
+    kern = {}
+    for kind in (0, 1, 2):
+        ms, _ = ctx.time_kernel(kind, prec, max(args.steps, 10), b_par)
+        kern[kind] = dist_max(dist, ms)
+    clocks = sampler.stop() if rank == 0 else None
+    l1 = ctx.launch_count()
+    ms_step = dist_max(dist, ms_step)
+    value = FLOPS_ITER * Vh_glob / (ms_step * 1e-3) * 1e-9
+
+    peak, peak_src = measured_peak()
+    bps = bytes_per_site(1, prec, recon)
+    ach = bps * Vh_loc / (kern[1] * 1e-3) * 1e-9
+    roofline = {"bound": "hbm", "kernel": "dslash_kernel<%s,%d,EPI_TW> (hop + A^-1)" % ("double" if prec == 8 else "float", recon),
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_site": bps, "sites_per_launch": Vh_loc, "ms_per_launch": kern[1],
+                "traffic": args.ncu_traffic}
+    kernels = {}
+    for kind in (0, 1, 2):
+        b = bytes_per_site(kind, prec, recon)
+        kernels[KNAME[kind]] = {"ms": kern[kind], "GB/s": b * Vh_loc / (kern[kind] * 1e-3) * 1e-9,
+                                "GFLOP/s": FLOPS_K[kind] * Vh_loc / (kern[kind] * 1e-3) * 1e-9,
+                                "frac_of_hbm_peak": b * Vh_loc / (kern[kind] * 1e-3) * 1e-9 / peak}
+    step_gbs = step_bytes_per_site(prec, recon) * Vh_loc / (ms_step * 1e-3) * 1e-9
+
+    # ---- e2e: the host-facing solve with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    cg_info = None
+    if not args.no_e2e:
+        import torch
+        host_b = torch.from_numpy(src_full.reshape(-1)).pin_memory() if torch.cuda.is_available() else None
+        hb = host_b.numpy().reshape(src_full.shape) if host_b is not None else src_full
+        host_x_t = torch.empty(src_full.size, dtype=torch.float64).pin_memory() if torch.cuda.is_available() else None
+        hx = host_x_t.numpy().reshape(src_full.shape) if host_x_t is not None else np.empty_like(src_full)
+        b = ctx.spinor(8, tmq.FULL); x = ctx.spinor(8, tmq.FULL)
+        spc, rhs, xpc = ctx.spinor(8), ctx.spinor(8), ctx.spinor(8)
+
+        def solve():
+            b.set(hb)                                   # H2D
+            ctx.prepare(spc, b)
+            ctx.matpc(rhs, spc, 1)                      # in <- M^dag in (lib/qudaQKXTM_interface.cpp:2034)
+            info = ctx.cg_mdagm(xpc, rhs, tol=args.tol, maxiter=args.maxiter,
+                                sloppy_prec=args.sloppy_prec, reliable_delta=args.delta)
+            ctx.reconstruct(x, xpc, b)
+            ctx.L.tmq_spinor_to_host(hx.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), x.h)   # D2H
+            return info
+
+        solve()                                          # warm-up solve
+        barrier()
+        t0 = time.perf_counter()
+        reps = args.e2e_solves
+        for _ in range(reps):
+            cg_info = solve()
+        barrier()
+        dt = dist_max(dist, (time.perf_counter() - t0) / reps)
+        iters = cg_info["iter"]
+        e2e = {"value": FLOPS_ITER * Vh_glob * iters / dt * 1e-9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": int(src_full.nbytes * n / max(iters, 1)), "d2h_bytes_per_step": int(src_full.nbytes * n / max(iters, 1)),
+               "what": "host source -> H2D -> prepare -> Mdag -> CG(tol=%g) -> reconstruct -> D2H, per solve; bytes amortised per CG iteration" % args.tol,
+               "solve_secs": dt, "iterations": iters, "true_res": cg_info["true_res"],
+               "h2d_bytes_per_solve": int(src_full.nbytes * n), "d2h_bytes_per_solve": int(src_full.nbytes * n)}
+
+    # ---- CPU baseline on rank 0, N=1 only (bounded sample of the same workload)
+    cpu = None
+    if n == 1 and not args.no_cpu:
+        del src_full
+        rhs_np = np.ascontiguousarray(b_par.get())
+        cpu = cpu_cg_sample(X, args.cpu_budget, gauge=gauge, rhs=rhs_np)
+
+    if rank == 0:
+        line = {"metric": "tm_dslash_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": n, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "f64" if prec == 8 else "f32", "data": "synthetic",
+                "config": {"workload": "%dx%dx%dx%d even-odd twisted-mass Dslash in CG on MdagM" % GX,
+                           "local_lattice": list(X), "grid": list(grid), "recon": recon, "kappa": KAPPA, "mu": MU,
+                           "matpc": "even-even", "step": "1 CG iteration = 4 Dslash launches + 1 fused update launch",
+                           "l2_policy": "inputs larger than L2 (parity spinor %.0f MB, gauge %.0f MB per sweep vs 126 MB L2)"
+                                        % (Vh_loc * 24 * prec / 1e6, Vh_loc * 8 * recon * prec / 1e6),
+                           "timing": "CUDA events on libtmq's compute stream, max over ranks; wall %.3f s" % wall},
+                "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
+                "gpu_launches_total": int(l1 - l0),
+                "step_hbm_gbs": step_gbs, "step_frac_of_hbm_peak": step_gbs / peak,
+                "kernels": kernels, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--lattice", type=int, nargs=4, default=[48, 48, 48, 96], help="global lattice (strong) / local (weak)")
+    ap.add_argument("--grid", type=int, nargs=4, default=None)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--prec", type=int, default=8, choices=[8, 4])
+    ap.add_argument("--recon", type=int, default=12, choices=[12, 18])
+    ap.add_argument("--tile", type=int, nargs=3, default=None)
+    ap.add_argument("--tol", type=float, default=1e-9)
+    ap.add_argument("--maxiter", type=int, default=5000)
+    ap.add_argument("--sloppy-prec", type=int, default=8, choices=[8, 4])
+    ap.add_argument("--delta", type=float, default=1e-1)
+    ap.add_argument("--e2e-solves", type=int, default=2)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ncu-traffic", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

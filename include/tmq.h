@@ -1,0 +1,165 @@
+/*
+ * tmq.h -- C ABI of libtmq.so: the B200-native even-odd twisted-mass Wilson Dslash + CG on M^dag M.
+ *
+ * This is the drop-in boundary for ONE hot path of ETMC-QUDA/quda-QKXTM-Multigrid-PlugIn.  The plug-in
+ * reaches that path through upstream-QUDA C++ internals (lib/qudaQKXTM_interface.cpp:1 textually
+ * includes interface_quda.cpp); each entry point below names the reference call site(s) it replaces.
+ * The C++ QKXTM shim in quda-qkxtm-multigrid-plugin_b200/host/ (QKXTM_Vector/Gauge/Propagator,
+ * init_qudaQKXTM, loadGaugeQuda, the calc_loops / MG_bench solve skeletons) is the only intended caller.
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on error; tmq_last_error() gives the text.
+ *     The shim converts non-zero into the reference's errorQuda() abort behaviour.
+ *   - plain pointers and sizes only; handles are opaque; one context per GPU / per process.
+ *   - calls on one context are serialised by the caller (the reference is single-threaded per rank).
+ *   - device work is enqueued on the context's stream; a call returns after the result it promises is
+ *     complete (host-visible) unless documented otherwise.
+ *   - there is no CPU fallback: every compute entry point fails if no CUDA device is usable.
+ *   - operator: kappa normalisation, M_full = A - kappa D, A = 1 + i (2 kappa mu) gamma5, UKQCD basis
+ *     (the only basis the plug-in accepts: lib/qudaQKXTM_interface.cpp:64-67).
+ */
+#ifndef TMQ_H
+#define TMQ_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tmq_ctx tmq_ctx;
+typedef struct tmq_spinor tmq_spinor;
+
+enum { TMQ_PREC_SINGLE = 4, TMQ_PREC_DOUBLE = 8 };          /* bytes, as QKXTM_Field::Precision() (include/qudaQKXTM.h:150) */
+enum { TMQ_SUBSET_PARITY = 1, TMQ_SUBSET_FULL = 2 };          /* QUDA_PARITY_SITE_SUBSET / QUDA_FULL_SITE_SUBSET            */
+enum { TMQ_MATPC_EVEN_EVEN = 0, TMQ_MATPC_ODD_ODD = 1,        /* qkxtm/Calc_Loops.cpp:443-450                               */
+       TMQ_MATPC_EVEN_EVEN_ASYM = 2, TMQ_MATPC_ODD_ODD_ASYM = 3 };
+enum { TMQ_RECON_12 = 12, TMQ_RECON_18 = 18 };                /* --recon 12 / 18 (qkxtm/misc.cpp:661-683)                   */
+enum { TMQ_SOLUTION_MAT = 0, TMQ_SOLUTION_MATPC = 1 };        /* QUDA_MAT_SOLUTION / QUDA_MATPC_SOLUTION                    */
+
+const char *tmq_last_error(void);
+int tmq_version(void);
+int tmq_device_count(void);
+
+/* ---- context: replaces initQuda(device) + initCommsGridQuda + init_qudaQKXTM geometry
+ *      (qkxtm/Calc_Loops.cpp:554,753-755; lib/qudaQKXTM_kernels.cu:118-297) ------------------------------
+ * localX: local lattice extents (x,y,z,t), all even.  grid/coord: process grid and this rank's
+ * coordinate; only z and t may be partitioned (grid[0] = grid[1] = 1).                                   */
+tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const int coord[4]);
+int tmq_destroy(tmq_ctx *);
+int tmq_sync(tmq_ctx *);
+/* NCCL bootstrap for the halo exchange and the CG all-reduces: rank 0 fills a 128-byte unique id, the
+ * caller broadcasts it (MPI / torch.distributed / file), every rank then joins.  Replaces the MPI/QMP
+ * communicator QUDA builds in initCommsGridQuda (qkxtm/QKXTM_util.cpp:48-68).                             */
+int tmq_comm_unique_id(char id128[128]);
+int tmq_comm_init(tmq_ctx *, const char id128[128], int nranks, int rank);
+/* force the ghost-zone (pack -> exchange -> interior/boundary) path in dimension d even when grid[d] = 1,
+ * where the exchange wraps onto this rank: the reference's --partition mask (qkxtm/QKXTM_util.cpp:1717-1720).
+ * Only z (part[2]) and t (part[3]) may be set.  Must be called before any field is created.              */
+int tmq_force_partition(tmq_ctx *, const int part[4]);
+/* tuning knobs (tile of the thread->site map); 0 keeps the default                                        */
+int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
+
+/* ---- gauge: replaces loadGaugeQuda / freeGaugeQuda (qkxtm/Calc_Loops.cpp:759,806) ----------------------
+ * qdp_eo_gauge[mu]: host, double, [even Vh | odd Vh] x 3x3 complex row-major (QDP order,
+ * qkxtm/QKXTM_util.cpp:840-857), with the T boundary condition ALREADY folded into U_t on the last
+ * global time slice when t_boundary = -1 (applyGaugeFieldScaling, qkxtm/QKXTM_util.cpp:698-705).
+ * Creates resident fp64 and fp32 copies with the requested reconstruct.                                   */
+int tmq_gauge_load(tmq_ctx *, const void *const qdp_eo_gauge[4], int t_boundary, int recon);
+int tmq_gauge_free(tmq_ctx *);
+/* sum Re tr P / (V_global * 3 * 6): QKXTM_Gauge::calculatePlaq (lib/qudaQKXTM_Gauge.cpp:376-386,
+ * lib/qudaQKXTM_kernels.cu:941-957).  Single rank only.                                                    */
+int tmq_plaquette(tmq_ctx *, double *plaq);
+
+/* ---- spinor fields: replace cudaColorSpinorField (lib/qudaQKXTM_interface.cpp:1923-1937) --------------- */
+tmq_spinor *tmq_spinor_alloc(tmq_ctx *, int prec, int subset);
+int tmq_spinor_free(tmq_spinor *);
+size_t tmq_spinor_bytes(const tmq_spinor *);
+/* QKXTM device layout <-> native: d_qkxtm[(s*3+c)*V*2 + x_lex*2 + ri] (lib/qudaQKXTM_Vector.cpp:72-81).
+ * Replaces run_UploadToCuda / run_DownloadFromCuda / run_ScaleVector
+ * (lib/qudaQKXTM_kernels.cu:1024-1124).  For a PARITY field `parity` selects the parity it holds
+ * (isEven -> 0); download zero-fills the absent parity (downloadFromCuda_core.h) and multiplies by `scale`
+ * (the 2*kappa rescale of lib/qudaQKXTM_interface.cpp:200-203 fused in).                                   */
+int tmq_spinor_from_qkxtm(tmq_spinor *dst, const void *d_qkxtm, int qkxtm_prec, int parity);
+int tmq_spinor_to_qkxtm(void *d_qkxtm, int qkxtm_prec, const tmq_spinor *src, int parity, double scale);
+/* host even-odd order [cb][spin][colour][re,im], double (QUDA_DIRAC_ORDER host spinor; a FULL field is
+ * [even Vh | odd Vh], include/QKXTM_mapping_parity.h:67-110).  Used by dslash_test-style drivers.          */
+int tmq_spinor_from_host(tmq_spinor *dst, const double *h_eo);
+int tmq_spinor_to_host(double *h_eo, const tmq_spinor *src);
+/* views of the two parities of a FULL field (qudaVec.Even()/Odd(), lib/qudaQKXTM_kernels.cu:1055)          */
+tmq_spinor *tmq_spinor_even(tmq_spinor *full);
+tmq_spinor *tmq_spinor_odd(tmq_spinor *full);
+
+/* ---- operator: replaces createDirac + Dirac::{Dslash,M,Mdag,MdagM,prepare,reconstruct}
+ *      (lib/qudaQKXTM_interface.cpp:1886-1889,2020-2041; lib/qudaQKXTM_Deflation.cpp:153-155,217) -------- */
+int tmq_op_set(tmq_ctx *, double kappa, double mu, int matpc);
+/* out(parity) = D in or D^dag in : the bare hop (a4)                                                      */
+int tmq_dslash(tmq_spinor *out, const tmq_spinor *in, int out_parity, int dagger);
+/* out = A^-1 D in (dagger = 0) / A^-dag D^dag in (dagger = 1); with x != NULL: out = x + k * (that)         */
+int tmq_dslash_twist_xpay(tmq_spinor *out, const tmq_spinor *in, int out_parity, int dagger,
+                          const tmq_spinor *x, double k);
+int tmq_matpc(tmq_spinor *out, const tmq_spinor *in, int dagger);       /* M_pc, sym or asym per tmq_op_set */
+int tmq_mdagm(tmq_spinor *out, const tmq_spinor *in);                   /* M_pc^dag M_pc (DiracMdagM)        */
+int tmq_mat_full(tmq_spinor *out, const tmq_spinor *in, int dagger);    /* A - kappa D on FULL fields        */
+int tmq_prepare(tmq_spinor *src_pc, const tmq_spinor *b_full);          /* Dirac::prepare, MAT solution      */
+int tmq_reconstruct(tmq_spinor *x_full, const tmq_spinor *x_pc, const tmq_spinor *b_full); /* Dirac::reconstruct */
+
+/* ---- solver: replaces Solver::create(CG) + (*solve)(out,in) on DiracMdagM
+ *      (lib/qudaQKXTM_interface.cpp:2031-2037).  Solves M^dag M x = b for PARITY fields, x0 = 0.
+ * sloppy_prec = 8: pure fp64; 4: fp32 inner iterations with reliable updates (delta), fp64 true residual.
+ * Outputs mirror QudaInvertParam::{iter,true_res,secs,gflops} (updateInvertParam).                         */
+int tmq_cg_mdagm(tmq_spinor *x, const tmq_spinor *b, double tol, int maxiter, double reliable_delta,
+                 int sloppy_prec, int *iters, double *true_res, double *secs, double *gflops);
+/* optional residual history of the last solve (|r|^2 per iteration), up to n entries                       */
+int tmq_cg_history(tmq_ctx *, double *r2, int n);
+
+/* ---- blas: replaces blas::* used by the plug-in (lib/qudaQKXTM_interface.cpp:135-136,
+ *      lib/qudaQKXTM_Deflation.cpp:1015-1056,1431-1435) and by CG ----------------------------------------- */
+int tmq_zero(tmq_spinor *x);
+int tmq_copy(tmq_spinor *dst, const tmq_spinor *src);                                  /* converts precision */
+int tmq_ax(double a, tmq_spinor *x);
+int tmq_axpy(double a, const tmq_spinor *x, tmq_spinor *y);                             /* y += a x           */
+int tmq_axpby(double a, const tmq_spinor *x, double b, tmq_spinor *y);                  /* y = a x + b y      */
+int tmq_xpay(const tmq_spinor *x, double a, tmq_spinor *y);                             /* y = x + a y        */
+int tmq_caxpy(const double a[2], const tmq_spinor *x, tmq_spinor *y);                   /* y += a x (complex) */
+int tmq_cxpaypbz(const tmq_spinor *x, const double a[2], const tmq_spinor *y, const double b[2], tmq_spinor *z);
+                                                                                        /* z = x + a y + b z  */
+int tmq_norm2(const tmq_spinor *x, double *out);
+int tmq_redot(const tmq_spinor *x, const tmq_spinor *y, double *out);
+int tmq_cdot(const tmq_spinor *x, const tmq_spinor *y, double out[2]);                  /* sum conj(x) y      */
+int tmq_axpy_norm(double a, const tmq_spinor *x, tmq_spinor *y, double *norm2_y);
+int tmq_xmy_norm(const tmq_spinor *x, tmq_spinor *y, double *norm2_y);                  /* y = x - y          */
+int tmq_axpy_zpbx(double a, tmq_spinor *x, tmq_spinor *y, const tmq_spinor *z, double b);
+                                                                                        /* y += a x; x = z + b x */
+int tmq_gamma5(tmq_spinor *x);                                                          /* apply_gamma5_vector */
+
+/* ---- QKXTM container kernels on the QKXTM device layout (lib/qudaQKXTM_kernels.cu:1110-1124,1353-1365,
+ *      lib/code_pieces/apply_gamma5_vector_core.h, lib/qudaQKXTM_Propagator.cpp:90-106) ------------------- */
+int tmq_qkxtm_scale(tmq_ctx *, void *d_qkxtm, int prec, double a);
+int tmq_qkxtm_cast(tmq_ctx *, void *d_dst, int dst_prec, const void *d_src, int src_prec);
+int tmq_qkxtm_gamma5(tmq_ctx *, void *d_qkxtm, int prec);
+int tmq_qkxtm_absorb(tmq_ctx *, void *d_prop, const void *d_vec, int prec, int nu, int c2);
+
+/* ---- raw device memory for the containers (QKXTM_Field::create_device, lib/qudaQKXTM_Field.cpp:172) ----- */
+int tmq_dev_malloc(tmq_ctx *, void **ptr, size_t bytes);
+int tmq_dev_free(tmq_ctx *, void *ptr);
+int tmq_dev_memset(tmq_ctx *, void *ptr, int value, size_t bytes);
+int tmq_h2d(tmq_ctx *, void *dst, const void *src, size_t bytes);
+int tmq_d2h(tmq_ctx *, void *dst, const void *src, size_t bytes);
+
+/* ---- measurement helpers (CUDA events on the context's stream) ------------------------------------------ */
+/* run `reps` back-to-back applications of one kernel flavour on (a copy of) the PARITY field `in` and return
+ * the average device time per application in milliseconds (CUDA events on the launching stream).
+ * kind: 0 = K1 hop, 1 = K2 hop+A^-1, 2 = K3 hop+A^-1+xpay, 3 = M^dag M (4 kernels), 4 = one fused CG
+ * iteration (4 Dslash kernels + update, no host sync).  prec selects fp64/fp32 arithmetic.  When
+ * flush_l2 != 0 a buffer larger than L2 is rewritten before every application and each application is
+ * timed separately.                                                                                          */
+int tmq_time_kernel(tmq_ctx *, int kind, int prec, int reps, const tmq_spinor *in, int flush_l2,
+                    double *ms_per_app, long long *launches);
+/* number of kernels this library has launched on the context since creation                                 */
+long long tmq_launch_count(tmq_ctx *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

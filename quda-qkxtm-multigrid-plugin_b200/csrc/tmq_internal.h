@@ -1,0 +1,148 @@
+// tmq_internal.h -- library-internal declarations (context, field handles, kernel launchers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "tmq_types.h"
+#include "tmq_reduce.cuh"
+
+struct tmq_ctx;
+
+struct tmq_spinor {
+  tmq_ctx *ctx;
+  int prec;      // 8 | 4
+  int subset;    // 1 parity | 2 full
+  void *d;       // device pointer (parity block 0, then block 1 for FULL)
+  size_t bytes;
+  bool owns;     // false for Even()/Odd() views
+  tmq_spinor *view[2];
+};
+
+namespace tmq {
+
+struct Comm;   // NCCL state (tmq_comm.cpp)
+
+struct GaugeStore {
+  void *d = nullptr;     // [2][4][3 or 9][Vh] in vec / cplx units
+  size_t bytes = 0;
+};
+
+// per-precision scratch used by the operator (temporaries of M, M^dag M, CG)
+constexpr int NSCRATCH = 6;
+struct Scratch {
+  void *tmp[NSCRATCH] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // parity fields
+};
+
+}  // namespace tmq
+
+struct tmq_ctx {
+  int device;
+  cudaStream_t stream;       // compute stream
+  cudaStream_t comm_stream;  // halo exchange stream
+  cudaEvent_t ev_a, ev_b, ev_pack, ev_halo, ev_r2;
+  tmq::Geom g;
+  int grid[4], coord[4];
+  int nranks, rank;
+  long long Vglobal;
+  int tile[3];
+  bool multi;                // any dimension partitioned
+  // gauge
+  int recon;                 // 12 | 18
+  int t_boundary;
+  tmq::GaugeStore gauge_d, gauge_s;
+  // operator
+  double kappa, mu;
+  int matpc;
+  bool op_set;
+  // scratch parity fields per precision
+  tmq::Scratch scr_d, scr_s;
+  // reductions
+  double *partials;          // device
+  size_t partials_len;
+  unsigned int *ticket;      // device
+  double *scal;              // device scalar block [SC_COUNT]
+  double *h_scal;            // pinned host mirror [SC_COUNT]
+  // halo buffers per precision: [dim][dir] send / recv, vec[3][face]
+  void *halo_send[2][4][2];
+  void *halo_recv[2][4][2];
+  tmq::Comm *comm;
+  long long launches;
+  std::vector<double> cg_hist;
+  // grow-only device staging buffer for host <-> native conversions
+  void *stage;
+  size_t stage_bytes;
+  // timing-kernel scratch (tmq_time_kernel)
+  int sms;
+};
+
+namespace tmq {
+
+void set_error(const char *fmt, ...);
+#define TMQ_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      tmq::set_error("%s:%d CUDA error: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(e__), #call); \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+
+inline size_t vec_bytes(int prec) { return prec == 8 ? 32 : 16; }
+inline size_t parity_bytes(const tmq_ctx *c, int prec) { return (size_t)6 * c->g.Vh * vec_bytes(prec); }
+
+Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_pref[3]);
+
+// dslash launchers (one TU per precision x recon)
+cudaError_t launch_dslash_d12(int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st);
+cudaError_t launch_dslash_d18(int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st);
+cudaError_t launch_dslash_s12(int epi, bool multi, const DslashArgs<float> &A, cudaStream_t st);
+cudaError_t launch_dslash_s18(int epi, bool multi, const DslashArgs<float> &A, cudaStream_t st);
+
+// blas launchers (tmq_blas.cu).  n = number of vectors (6*Vh per parity block).  prec = 8 | 4.
+struct BlasRed { double *partials; unsigned int *ticket; double *scal; int slot; };
+cudaError_t blas_zero(void *x, size_t bytes, cudaStream_t st);
+cudaError_t blas_copy(void *dst, int dprec, const void *src, int sprec, size_t n, cudaStream_t st);
+cudaError_t blas_axpby(int prec, double a, const void *x, double b, void *y, size_t n, cudaStream_t st);   // y = a x + b y
+cudaError_t blas_ax(int prec, double a, void *x, size_t n, cudaStream_t st);
+cudaError_t blas_caxpy(int prec, double ar, double ai, const void *x, void *y, size_t n, cudaStream_t st);
+cudaError_t blas_cxpaypbz(int prec, const void *x, double ar, double ai, const void *y, double br, double bi, void *z,
+                          size_t n, cudaStream_t st);
+cudaError_t blas_norm2(int prec, const void *x, size_t n, const BlasRed &r, cudaStream_t st);
+cudaError_t blas_redot(int prec, const void *x, const void *y, size_t n, const BlasRed &r, cudaStream_t st);
+cudaError_t blas_cdot(int prec, const void *x, const void *y, size_t n, const BlasRed &r, cudaStream_t st);  // slot, slot+1
+cudaError_t blas_axpy_norm(int prec, double a, const void *x, void *y, size_t n, const BlasRed &r, cudaStream_t st);
+cudaError_t blas_xmy_norm(int prec, const void *x, void *y, size_t n, const BlasRed &r, cudaStream_t st);
+cudaError_t blas_axpy_zpbx(int prec, double a, void *x, void *y, const void *z, double b, size_t n, cudaStream_t st);
+// CG update with device-resident scalars: alpha = s[an]/s[ad], beta = s[bn]/s[bd];  x += alpha p ; p = r + beta p
+cudaError_t blas_cg_update(int prec, void *x, void *p, const void *r, size_t n, const double *scal, int an, int ad,
+                           int bn, int bd, cudaStream_t st);
+// mixed precision accumulate: y(double) += x(float)
+cudaError_t blas_xpy_mixed(void *y_d, const void *x_s, size_t n, cudaStream_t st);
+// site-local twist / gamma5 on a parity block: out = c (in + i a g5 in)
+cudaError_t blas_twist(int prec, void *out, const void *in, double c, double a, int Vh, cudaStream_t st);
+int blas_grid();
+
+// field kernels (tmq_fields.cu)
+cudaError_t gauge_reorder(int prec, int recon, void *dst, const double *src_mu, int mu, int Vh, cudaStream_t st);
+cudaError_t spinor_from_qkxtm(int prec, void *even, void *odd, const void *qk, int qprec, const Geom &g, cudaStream_t st);
+cudaError_t spinor_to_qkxtm(void *qk, int qprec, int prec, const void *even, const void *odd, double scale,
+                            const Geom &g, cudaStream_t st);
+cudaError_t spinor_from_host_eo(int prec, void *dst, const double *d_aos, int Vh, cudaStream_t st);
+cudaError_t spinor_to_host_eo(double *d_aos, int prec, const void *src, int Vh, cudaStream_t st);
+cudaError_t plaquette_launch(int recon, const void *gauge_d, const Geom &g, const BlasRed &r, cudaStream_t st);
+cudaError_t qkxtm_scale(void *d, int prec, double a, size_t ncplx, cudaStream_t st);
+cudaError_t qkxtm_cast(void *dst, int dprec, const void *src, int sprec, size_t ncplx, cudaStream_t st);
+cudaError_t qkxtm_gamma5(void *d, int prec, int V, cudaStream_t st);
+// halo pack: project (and for the forward-going face multiply by U^dag) the boundary slices of `in`
+cudaError_t halo_pack(int prec, int recon, const DslashArgs<double> *Ad, const DslashArgs<float> *As, int dim,
+                      void *send_bwd, void *send_fwd, cudaStream_t st);
+
+// comm layer (tmq_comm.cpp)
+int comm_unique_id(char id128[128]);
+int comm_init(tmq_ctx *c, const char id128[128], int nranks, int rank);
+void comm_destroy(tmq_ctx *c);
+int comm_exchange(tmq_ctx *c, int pi, int prec, cudaStream_t st);
+int comm_allreduce(tmq_ctx *c, double *d_ptr, int n, cudaStream_t st);
+
+}  // namespace tmq

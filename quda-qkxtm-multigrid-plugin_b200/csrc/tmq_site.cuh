@@ -1,0 +1,446 @@
+// tmq_site.cuh -- the per-site body of the twisted-mass Dslash family.
+//
+// One function, dslash_site<F, RECON, EPI, MULTI>(), computes for one output parity site
+//     h(x) = sum_mu [ (1 - s g_mu) U_mu(x) in(x+mu) + (1 + s g_mu) U_mu(x-mu)^dag in(x-mu) ]      (s = +1: D, -1: D^dag)
+// in the UKQCD basis and applies the fused epilogue (tmq_types.h).  Hop convention:
+// reference lib/code_pieces/fixSinkContractions_noether_core.h:117-137; gamma matrices:
+// lib/code_pieces/gammas_tm_base.h:21-32,148-171; gamma5 = spin swap (apply_gamma5_vector_core.h);
+// checkerboard geometry: qkxtm/QKXTM_util.cpp:405-470; recon-12 third row and its boundary sign:
+// qkxtm/QKXTM_util.cpp:281-295.  Written from the maths, not from QUDA's dslash_core.
+//
+// The body is __host__ __device__ so that the CPU test-suite can run the identical index / projector
+// / epilogue code on host arrays (tests/hostemu, test infrastructure only) before GPU time is spent.
+// The product never calls it on the host.
+#pragma once
+#include "tmq_types.h"
+
+namespace tmq {
+
+// ---- loads / stores with cache policy ---------------------------------------------------------------
+// spinor neighbours: read-only path, allocate in L1 (each input site is used by 8 outputs, most of them
+// in the same CTA tile).  gauge links: used exactly once per application -> no L1 allocation, L2
+// evict-first so they do not push the spinor working set out of L2.
+TMQ_HD VecT<double> ld_spinor(const VecT<double> *p) {
+#if defined(__CUDA_ARCH__)
+  VecT<double> r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+TMQ_HD VecT<float> ld_spinor(const VecT<float> *p) {
+#if defined(__CUDA_ARCH__)
+  VecT<float> r;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.a), "=f"(r.b), "=f"(r.c), "=f"(r.d) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+TMQ_HD VecT<double> ld_stream(const VecT<double> *p) {
+#if defined(__CUDA_ARCH__)
+  VecT<double> r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+TMQ_HD VecT<float> ld_stream(const VecT<float> *p) {
+#if defined(__CUDA_ARCH__)
+  VecT<float> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.a), "=f"(r.b), "=f"(r.c), "=f"(r.d) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+TMQ_HD CplxT<double> ld_stream(const CplxT<double> *p) {
+#if defined(__CUDA_ARCH__)
+  CplxT<double> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.re), "=d"(r.im) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+TMQ_HD CplxT<float> ld_stream(const CplxT<float> *p) {
+#if defined(__CUDA_ARCH__)
+  CplxT<float> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.re), "=f"(r.im) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+
+// ---- site enumeration -----------------------------------------------------------------------------------
+struct SiteCoord {
+  int xh, y, z, t;   // local coordinates (xh = x/2)
+  int xodd;          // x & 1
+  int idx;           // cb-lexicographic index inside the parity block
+};
+
+TMQ_HD SiteCoord decode_site(const Geom &g, const Enum &en, int parity, uint32_t e) {
+  SiteCoord c;
+  uint32_t r = fd_div(e, en.dXh);
+  c.xh = (int)(e - r * en.dXh.d);
+  uint32_t q = fd_div(r, en.dTy); int ly = (int)(r - q * en.dTy.d); r = q;
+  q = fd_div(r, en.dTz); int lz = (int)(r - q * en.dTz.d); r = q;
+  q = fd_div(r, en.dTt); int lt = (int)(r - q * en.dTt.d); r = q;
+  q = fd_div(r, en.dNy); int ty = (int)(r - q * en.dNy.d); r = q;
+  q = fd_div(r, en.dNz); int tz = (int)(r - q * en.dNz.d); int tt = (int)q;
+  c.y = en.lo[0] + ty * (int)en.dTy.d + ly;
+  c.z = en.lo[1] + tz * (int)en.dTz.d + lz;
+  c.t = en.lo[2] + tt * (int)en.dTt.d + lt;
+  c.xodd = (c.y + c.z + c.t + parity) & 1;
+  c.idx = ((c.t * g.X[2] + c.z) * g.X[1] + c.y) * g.Xh + c.xh;
+  return c;
+}
+
+// ---- small complex helpers on explicit re/im scalars ---------------------------------------------------
+// acc += a*b
+#define TMQ_CMAC(accr, acci, ar, ai, br, bi) \
+  { accr += (ar) * (br); accr -= (ai) * (bi); acci += (ar) * (bi); acci += (ai) * (br); }
+// acc += conj(a)*b
+#define TMQ_CMAC_CONJ(accr, acci, ar, ai, br, bi) \
+  { accr += (ar) * (br); accr += (ai) * (bi); acci += (ar) * (bi); acci -= (ai) * (br); }
+
+template <typename F> struct Link { F u[3][3][2]; };
+
+// rows 0,1 stored; row 2 = conj(row0 x row1) * sign  (qkxtm/QKXTM_util.cpp:281-295, u0 = t_boundary)
+template <typename F> TMQ_HD void reconstruct_row2(Link<F> &L, F sign) {
+#define U(r, c, p) L.u[r][c][p]
+  F ar, ai;
+  // U20 = conj(U01 U12 - U02 U11)
+  ar = U(0, 1, 0) * U(1, 2, 0) - U(0, 1, 1) * U(1, 2, 1) - U(0, 2, 0) * U(1, 1, 0) + U(0, 2, 1) * U(1, 1, 1);
+  ai = U(0, 1, 0) * U(1, 2, 1) + U(0, 1, 1) * U(1, 2, 0) - U(0, 2, 0) * U(1, 1, 1) - U(0, 2, 1) * U(1, 1, 0);
+  U(2, 0, 0) = sign * ar; U(2, 0, 1) = -sign * ai;
+  // U21 = conj(U02 U10 - U00 U12)
+  ar = U(0, 2, 0) * U(1, 0, 0) - U(0, 2, 1) * U(1, 0, 1) - U(0, 0, 0) * U(1, 2, 0) + U(0, 0, 1) * U(1, 2, 1);
+  ai = U(0, 2, 0) * U(1, 0, 1) + U(0, 2, 1) * U(1, 0, 0) - U(0, 0, 0) * U(1, 2, 1) - U(0, 0, 1) * U(1, 2, 0);
+  U(2, 1, 0) = sign * ar; U(2, 1, 1) = -sign * ai;
+  // U22 = conj(U00 U11 - U01 U10)
+  ar = U(0, 0, 0) * U(1, 1, 0) - U(0, 0, 1) * U(1, 1, 1) - U(0, 1, 0) * U(1, 0, 0) + U(0, 1, 1) * U(1, 0, 1);
+  ai = U(0, 0, 0) * U(1, 1, 1) + U(0, 0, 1) * U(1, 1, 0) - U(0, 1, 0) * U(1, 0, 1) - U(0, 1, 1) * U(1, 0, 0);
+  U(2, 2, 0) = sign * ar; U(2, 2, 1) = -sign * ai;
+#undef U
+}
+
+template <typename F, int RECON>
+TMQ_HD void load_link(Link<F> &L, const void *gauge, int parity, int mu, int idx, int stride, F sign12) {
+  if (RECON == 12) {
+    const VecT<F> *b = (const VecT<F> *)gauge + (size_t)((parity * 4 + mu) * 3) * (size_t)stride + idx;
+    VecT<F> v0 = ld_stream(b), v1 = ld_stream(b + stride), v2 = ld_stream(b + 2 * (size_t)stride);
+    L.u[0][0][0] = v0.a; L.u[0][0][1] = v0.b; L.u[0][1][0] = v0.c; L.u[0][1][1] = v0.d;
+    L.u[0][2][0] = v1.a; L.u[0][2][1] = v1.b; L.u[1][0][0] = v1.c; L.u[1][0][1] = v1.d;
+    L.u[1][1][0] = v2.a; L.u[1][1][1] = v2.b; L.u[1][2][0] = v2.c; L.u[1][2][1] = v2.d;
+    reconstruct_row2(L, sign12);
+  } else {
+    const CplxT<F> *b = (const CplxT<F> *)gauge + (size_t)((parity * 4 + mu) * 9) * (size_t)stride + idx;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      CplxT<F> c = ld_stream(b + (size_t)k * stride);
+      L.u[k / 3][k % 3][0] = c.re; L.u[k / 3][k % 3][1] = c.im;
+    }
+  }
+}
+
+// half spinor: 2 spin x 3 colour complex
+template <typename F> struct Half { F h[2][3][2]; };
+
+// uh = U h (forward) or U^dag h (backward)
+template <typename F, bool DAG> TMQ_HD void su3_apply(Half<F> &o, const Link<F> &L, const Half<F> &h) {
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      F re = 0, im = 0;
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        if (!DAG) { TMQ_CMAC(re, im, L.u[a][b][0], L.u[a][b][1], h.h[s][b][0], h.h[s][b][1]); }
+        else      { TMQ_CMAC_CONJ(re, im, L.u[b][a][0], L.u[b][a][1], h.h[s][b][0], h.h[s][b][1]); }
+      }
+      o.h[s][a][0] = re; o.h[s][a][1] = im;
+    }
+}
+
+// full spinor in registers: o[spin][colour][re/im]
+template <typename F> struct Spinor { F v[4][3][2]; };
+
+template <typename F> TMQ_HD void unpack_vec(Spinor<F> &p, int j, const VecT<F> &v) {
+  // vector j holds complex k = 2j, 2j+1 with k = 3*spin + colour
+  const int k0 = 2 * j, k1 = 2 * j + 1;
+  p.v[k0 / 3][k0 % 3][0] = v.a; p.v[k0 / 3][k0 % 3][1] = v.b;
+  p.v[k1 / 3][k1 % 3][0] = v.c; p.v[k1 / 3][k1 % 3][1] = v.d;
+}
+template <typename F> TMQ_HD VecT<F> pack_vec(const Spinor<F> &p, int j) {
+  const int k0 = 2 * j, k1 = 2 * j + 1;
+  VecT<F> v;
+  v.a = p.v[k0 / 3][k0 % 3][0]; v.b = p.v[k0 / 3][k0 % 3][1];
+  v.c = p.v[k1 / 3][k1 % 3][0]; v.d = p.v[k1 / 3][k1 % 3][1];
+  return v;
+}
+
+template <typename F> TMQ_HD void load_spinor(Spinor<F> &p, const VecT<F> *base, int idx, int stride) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) unpack_vec(p, j, ld_spinor(base + (size_t)j * stride + idx));
+}
+// only spins {2*half, 2*half+1}: vectors 3*half .. 3*half+2
+template <typename F> TMQ_HD void load_spinor_half(Spinor<F> &p, const VecT<F> *base, int idx, int stride, int half) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    VecT<F> v = ld_spinor(base + (size_t)(3 * half + j) * stride + idx);
+    // unpack with compile-time register indices for both cases
+    if (half) unpack_vec(p, 3 + j, v); else unpack_vec(p, j, v);
+  }
+}
+template <typename F> TMQ_HD void load_half_ghost(Half<F> &h, const VecT<F> *base, int fidx, int fstride) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    VecT<F> v = ld_stream(base + (size_t)j * fstride + fidx);
+    const int k0 = 2 * j, k1 = 2 * j + 1;
+    h.h[k0 / 3][k0 % 3][0] = v.a; h.h[k0 / 3][k0 % 3][1] = v.b;
+    h.h[k1 / 3][k1 % 3][0] = v.c; h.h[k1 / 3][k1 % 3][1] = v.d;
+  }
+}
+
+// ---- spin projection / reconstruction in the UKQCD basis, P = 1 - sg * gamma_mu --------------------
+//   mu=0 (x): h0 = p0 - sg i p3, h1 = p1 - sg i p2 ; rows 2,3 = sg i h1, sg i h0
+//   mu=1 (y): h0 = p0 - sg p3,   h1 = p1 + sg p2   ; rows 2,3 = sg h1,  -sg h0
+//   mu=2 (z): h0 = p0 - sg i p2, h1 = p1 + sg i p3 ; rows 2,3 = sg i h0, -sg i h1
+//   mu=3 (t): sg=+1: h = 2 p2, 2 p3 -> rows 2,3 ; sg=-1: h = 2 p0, 2 p1 -> rows 0,1
+template <typename F, int MU> TMQ_HD void project(Half<F> &h, const Spinor<F> &p, F sg) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    if constexpr (MU == 0) {
+      h.h[0][c][0] = p.v[0][c][0] + sg * p.v[3][c][1]; h.h[0][c][1] = p.v[0][c][1] - sg * p.v[3][c][0];
+      h.h[1][c][0] = p.v[1][c][0] + sg * p.v[2][c][1]; h.h[1][c][1] = p.v[1][c][1] - sg * p.v[2][c][0];
+    } else if constexpr (MU == 1) {
+      h.h[0][c][0] = p.v[0][c][0] - sg * p.v[3][c][0]; h.h[0][c][1] = p.v[0][c][1] - sg * p.v[3][c][1];
+      h.h[1][c][0] = p.v[1][c][0] + sg * p.v[2][c][0]; h.h[1][c][1] = p.v[1][c][1] + sg * p.v[2][c][1];
+    } else if constexpr (MU == 2) {
+      h.h[0][c][0] = p.v[0][c][0] + sg * p.v[2][c][1]; h.h[0][c][1] = p.v[0][c][1] - sg * p.v[2][c][0];
+      h.h[1][c][0] = p.v[1][c][0] - sg * p.v[3][c][1]; h.h[1][c][1] = p.v[1][c][1] + sg * p.v[3][c][0];
+    }
+  }
+}
+template <typename F, int MU> TMQ_HD void accumulate(Spinor<F> &o, const Half<F> &u, F sg) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    o.v[0][c][0] += u.h[0][c][0]; o.v[0][c][1] += u.h[0][c][1];
+    o.v[1][c][0] += u.h[1][c][0]; o.v[1][c][1] += u.h[1][c][1];
+    if constexpr (MU == 0) {        // row2 += sg i u1 ; row3 += sg i u0
+      o.v[2][c][0] -= sg * u.h[1][c][1]; o.v[2][c][1] += sg * u.h[1][c][0];
+      o.v[3][c][0] -= sg * u.h[0][c][1]; o.v[3][c][1] += sg * u.h[0][c][0];
+    } else if constexpr (MU == 1) { // row2 += sg u1 ; row3 -= sg u0
+      o.v[2][c][0] += sg * u.h[1][c][0]; o.v[2][c][1] += sg * u.h[1][c][1];
+      o.v[3][c][0] -= sg * u.h[0][c][0]; o.v[3][c][1] -= sg * u.h[0][c][1];
+    } else if constexpr (MU == 2) { // row2 += sg i u0 ; row3 -= sg i u1
+      o.v[2][c][0] -= sg * u.h[0][c][1]; o.v[2][c][1] += sg * u.h[0][c][0];
+      o.v[3][c][0] += sg * u.h[1][c][1]; o.v[3][c][1] -= sg * u.h[1][c][0];
+    }
+  }
+}
+
+// one of the 8 hop terms.  FWD: (1 - s g_mu) U_mu(x) in(x+mu) ; !FWD: (1 + s g_mu) U_mu(x-mu)^dag in(x-mu)
+// nidx = neighbour cb index (other parity); cross = the neighbour lies across a partitioned boundary
+template <typename F, int RECON, int MU, bool FWD, bool MULTI>
+TMQ_HD void hop_term(Spinor<F> &o, const DslashArgs<F> &A, const SiteCoord &c, int nidx, bool cross, int fidx,
+                     F sign12) {
+  const int stride = A.g.Vh;
+  const F sg = FWD ? A.dsign : -A.dsign;
+  Half<F> h, u;
+  if constexpr (MU < 3) {
+    if (MULTI && cross) {
+      // ghost faces hold projected half spinors; the one arriving from the backward neighbour is
+      // already multiplied by U^dag on the sender (the link lives there)
+      if (FWD) {
+        load_half_ghost(h, A.ghost[MU][1], fidx, A.g.face[MU]);
+        Link<F> L; load_link<F, RECON>(L, A.gauge, A.parity, MU, c.idx, stride, (F)1);
+        su3_apply<F, false>(u, L, h);
+      } else {
+        load_half_ghost(u, A.ghost[MU][0], fidx, A.g.face[MU]);
+      }
+    } else {
+      Spinor<F> p; load_spinor(p, A.in, nidx, stride);
+      project<F, MU>(h, p, sg);
+      Link<F> L;
+      if (FWD) { load_link<F, RECON>(L, A.gauge, A.parity, MU, c.idx, stride, (F)1); su3_apply<F, false>(u, L, h); }
+      else     { load_link<F, RECON>(L, A.gauge, 1 - A.parity, MU, nidx, stride, (F)1); su3_apply<F, true>(u, L, h); }
+    }
+    accumulate<F, MU>(o, u, sg);
+  } else {
+    // t direction: P = diag(1-sg,1-sg,1+sg,1+sg): only two spin components are read
+    const bool lower = sg > (F)0;   // sg=+1 -> spins 2,3
+    if (MULTI && cross) {
+      if (FWD) {
+        load_half_ghost(h, A.ghost[3][1], fidx, A.g.face[3]);
+        Link<F> L; load_link<F, RECON>(L, A.gauge, A.parity, 3, c.idx, stride, sign12);
+        su3_apply<F, false>(u, L, h);
+      } else {
+        load_half_ghost(u, A.ghost[3][0], fidx, A.g.face[3]);
+      }
+    } else {
+      Spinor<F> p;
+      if (lower) {
+        load_spinor_half(p, A.in, nidx, stride, 1);
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          h.h[0][cc][0] = 2 * p.v[2][cc][0]; h.h[0][cc][1] = 2 * p.v[2][cc][1];
+          h.h[1][cc][0] = 2 * p.v[3][cc][0]; h.h[1][cc][1] = 2 * p.v[3][cc][1];
+        }
+      } else {
+        load_spinor_half(p, A.in, nidx, stride, 0);
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          h.h[0][cc][0] = 2 * p.v[0][cc][0]; h.h[0][cc][1] = 2 * p.v[0][cc][1];
+          h.h[1][cc][0] = 2 * p.v[1][cc][0]; h.h[1][cc][1] = 2 * p.v[1][cc][1];
+        }
+      }
+      Link<F> L;
+      if (FWD) { load_link<F, RECON>(L, A.gauge, A.parity, 3, c.idx, stride, sign12); su3_apply<F, false>(u, L, h); }
+      else     { load_link<F, RECON>(L, A.gauge, 1 - A.parity, 3, nidx, stride, sign12); su3_apply<F, true>(u, L, h); }
+    }
+    if (lower) {
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) {
+        o.v[2][cc][0] += u.h[0][cc][0]; o.v[2][cc][1] += u.h[0][cc][1];
+        o.v[3][cc][0] += u.h[1][cc][0]; o.v[3][cc][1] += u.h[1][cc][1];
+      }
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) {
+        o.v[0][cc][0] += u.h[0][cc][0]; o.v[0][cc][1] += u.h[0][cc][1];
+        o.v[1][cc][0] += u.h[1][cc][0]; o.v[1][cc][1] += u.h[1][cc][1];
+      }
+    }
+  }
+}
+
+// y = c (x + i a g5 x), g5 = spin swap 0<->2, 1<->3
+template <typename F> TMQ_HD void twist(Spinor<F> &y, const Spinor<F> &x, F c, F a) {
+#pragma unroll
+  for (int s = 0; s < 4; s++)
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) {
+      y.v[s][cc][0] = c * (x.v[s][cc][0] - a * x.v[s ^ 2][cc][1]);
+      y.v[s][cc][1] = c * (x.v[s][cc][1] + a * x.v[s ^ 2][cc][0]);
+    }
+}
+
+template <int EPI> struct EpiTraits {
+  static constexpr bool TW1 = (EPI == EPI_TW || EPI == EPI_TW_XPAY || EPI == EPI_MDAGM2);
+  static constexpr bool XTERM = (EPI >= EPI_TW_XPAY);
+  static constexpr bool TWX = (EPI == EPI_TWX_XPAY || EPI == EPI_CG4);
+  static constexpr bool TW3 = (EPI == EPI_XPAY_TW3 || EPI == EPI_MDAGM2);
+  static constexpr int RED = (EPI == EPI_MDAGM2) ? 1 : (EPI == EPI_CG4 ? 2 : 0);
+};
+
+// Computes one output site; returns this site's contribution to the fused reduction (0 if none).
+template <typename F, int RECON, int EPI, bool MULTI>
+TMQ_HD double dslash_site(const DslashArgs<F> &A, uint32_t e, F alpha) {
+  typedef EpiTraits<EPI> T;
+  const Geom &g = A.g;
+  const SiteCoord c = decode_site(g, A.en, A.parity, e);
+  const int Xh = g.Xh, stride = g.Vh;
+  Spinor<F> o;
+#pragma unroll
+  for (int s = 0; s < 4; s++)
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) { o.v[s][cc][0] = 0; o.v[s][cc][1] = 0; }
+
+  // recon-12 boundary sign: the links U_t(T-1) carry the anti-periodic -1 (QKXTM_util.cpp:698-705),
+  // so their reconstructed third row needs the same factor (QKXTM_util.cpp:292-294)
+  const F s12_f = (g.tb_last && c.t == g.X[3] - 1) ? (F)g.tb_sign : (F)1;
+  // backward t link U_t(x-t): a boundary link iff this site sits at global t = 0 (unused on the ghost
+  // path, where the sender applied its own U^dag)
+  const F s12_b = (g.tb_first && c.t == 0) ? (F)g.tb_sign : (F)1;
+
+  // +x / -x : xh' = xh + xodd (fwd), xh - (1 - xodd) (bwd), periodic or ghost
+  {
+    int nx = c.xh + c.xodd; bool cross = false; int fidx = 0;
+    if (nx == Xh) { nx = 0; if (MULTI && g.part[0]) { cross = true; fidx = (c.t * g.X[2] + c.z) * g.X[1] + c.y; fidx >>= 1; } }
+    hop_term<F, RECON, 0, true, MULTI>(o, A, c, c.idx - c.xh + nx, cross, fidx, (F)1);
+    nx = c.xh - (1 - c.xodd); cross = false;
+    if (nx < 0) { nx = Xh - 1; if (MULTI && g.part[0]) { cross = true; fidx = ((c.t * g.X[2] + c.z) * g.X[1] + c.y) >> 1; } }
+    hop_term<F, RECON, 0, false, MULTI>(o, A, c, c.idx - c.xh + nx, cross, fidx, (F)1);
+  }
+  // +-y
+  {
+    bool cross = false; int fidx = 0;
+    int n = c.idx + Xh;
+    if (c.y == g.X[1] - 1) { n = c.idx - (g.X[1] - 1) * Xh; if (MULTI && g.part[1]) { cross = true; fidx = (c.t * g.X[2] + c.z) * Xh + c.xh; } }
+    hop_term<F, RECON, 1, true, MULTI>(o, A, c, n, cross, fidx, (F)1);
+    cross = false; n = c.idx - Xh;
+    if (c.y == 0) { n = c.idx + (g.X[1] - 1) * Xh; if (MULTI && g.part[1]) { cross = true; fidx = (c.t * g.X[2] + c.z) * Xh + c.xh; } }
+    hop_term<F, RECON, 1, false, MULTI>(o, A, c, n, cross, fidx, (F)1);
+  }
+  // +-z
+  {
+    const int sz = g.X[1] * Xh;
+    bool cross = false; int fidx = 0;
+    int n = c.idx + sz;
+    if (c.z == g.X[2] - 1) { n = c.idx - (g.X[2] - 1) * sz; if (MULTI && g.part[2]) { cross = true; fidx = (c.t * g.X[1] + c.y) * Xh + c.xh; } }
+    hop_term<F, RECON, 2, true, MULTI>(o, A, c, n, cross, fidx, (F)1);
+    cross = false; n = c.idx - sz;
+    if (c.z == 0) { n = c.idx + (g.X[2] - 1) * sz; if (MULTI && g.part[2]) { cross = true; fidx = (c.t * g.X[1] + c.y) * Xh + c.xh; } }
+    hop_term<F, RECON, 2, false, MULTI>(o, A, c, n, cross, fidx, (F)1);
+  }
+  // +-t
+  {
+    const int st = g.X[2] * g.X[1] * Xh;
+    bool cross = false; int fidx = 0;
+    int n = c.idx + st;
+    if (c.t == g.X[3] - 1) { n = c.idx - (g.X[3] - 1) * st; if (MULTI && g.part[3]) { cross = true; fidx = c.idx - (g.X[3] - 1) * st; } }
+    hop_term<F, RECON, 3, true, MULTI>(o, A, c, n, cross, fidx, s12_f);
+    cross = false; n = c.idx - st;
+    if (c.t == 0) { n = c.idx + (g.X[3] - 1) * st; if (MULTI && g.part[3]) { cross = true; fidx = c.idx; } }
+    hop_term<F, RECON, 3, false, MULTI>(o, A, c, n, cross, fidx, s12_b);
+  }
+
+  // ---- epilogue ----
+  double red = 0.0;
+  if (T::TW1) { Spinor<F> t; twist(t, o, A.e.c1, A.e.a1); o = t; }
+  if (T::XTERM) {
+    Spinor<F> x;
+#pragma unroll
+    for (int j = 0; j < 6; j++) unpack_vec(x, j, A.x[(size_t)j * stride + c.idx]);
+    if (T::TWX) { Spinor<F> xt; twist(xt, x, A.e.cx, A.e.ax); x = xt; }
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) {
+        o.v[s][cc][0] = x.v[s][cc][0] + A.e.k * o.v[s][cc][0];
+        o.v[s][cc][1] = x.v[s][cc][1] + A.e.k * o.v[s][cc][1];
+      }
+  }
+  if (T::RED == 1) {
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++)
+        red += (double)o.v[s][cc][0] * (double)o.v[s][cc][0] + (double)o.v[s][cc][1] * (double)o.v[s][cc][1];
+  }
+  if (T::TW3) { Spinor<F> t; twist(t, o, A.e.c3, A.e.a3); o = t; }
+  if (T::RED == 2) {
+    // r <- r - alpha z ; |r|^2
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      VecT<F> rv = A.r[(size_t)j * stride + c.idx];
+      VecT<F> zv = pack_vec(o, j);
+      rv.a -= alpha * zv.a; rv.b -= alpha * zv.b; rv.c -= alpha * zv.c; rv.d -= alpha * zv.d;
+      red += (double)rv.a * rv.a + (double)rv.b * rv.b + (double)rv.c * rv.c + (double)rv.d * rv.d;
+      A.r[(size_t)j * stride + c.idx] = rv;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; j++) A.out[(size_t)j * stride + c.idx] = pack_vec(o, j);
+  }
+  return red;
+}
+
+}  // namespace tmq

@@ -1,0 +1,318 @@
+"""ctypes binding of libtmq.so (include/tmq.h) -- the thin Python host layer used by the parity tests and
+bench.py.  The product's reference-facing host layer is the C++ QKXTM shim in ../host/; this module only
+mirrors the C ABI one-to-one (same names, same argument meaning) so that tests read like upstream's
+dslash_test / invert_test drivers.
+
+There is NO fallback: if libtmq.so is missing or no CUDA device is usable, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtmq.so")
+
+PREC_SINGLE, PREC_DOUBLE = 4, 8
+PARITY, FULL = 1, 2
+MATPC_EVEN_EVEN, MATPC_ODD_ODD, MATPC_EVEN_EVEN_ASYM, MATPC_ODD_ODD_ASYM = 0, 1, 2, 3
+
+# every symbol include/tmq.h declares (checked against the header by tests/test_abi.py)
+SYMBOLS = """tmq_last_error tmq_version tmq_device_count tmq_create tmq_destroy tmq_sync tmq_comm_unique_id
+tmq_comm_init tmq_force_partition tmq_set_tile tmq_gauge_load tmq_gauge_free tmq_plaquette tmq_spinor_alloc
+tmq_spinor_free tmq_spinor_bytes tmq_spinor_from_qkxtm tmq_spinor_to_qkxtm tmq_spinor_from_host tmq_spinor_to_host
+tmq_spinor_even tmq_spinor_odd tmq_op_set tmq_dslash tmq_dslash_twist_xpay tmq_matpc tmq_mdagm tmq_mat_full
+tmq_prepare tmq_reconstruct tmq_cg_mdagm tmq_cg_history tmq_zero tmq_copy tmq_ax tmq_axpy tmq_axpby tmq_xpay
+tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm tmq_axpy_zpbx tmq_gamma5
+tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
+tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count""".split()
+
+
+class TmqError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen libtmq.so; raises (never falls back) when the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TmqError("libtmq.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
+    L.tmq_last_error.restype = C.c_char_p
+    L.tmq_create.restype = vp; L.tmq_create.argtypes = [C.c_int, ip, ip, ip]
+    L.tmq_destroy.argtypes = [vp]; L.tmq_sync.argtypes = [vp]
+    L.tmq_comm_unique_id.argtypes = [C.c_char_p]
+    L.tmq_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+    L.tmq_force_partition.argtypes = [vp, ip]
+    L.tmq_set_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.tmq_gauge_load.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int]
+    L.tmq_gauge_free.argtypes = [vp]
+    L.tmq_plaquette.argtypes = [vp, dp]
+    L.tmq_spinor_alloc.restype = vp; L.tmq_spinor_alloc.argtypes = [vp, C.c_int, C.c_int]
+    L.tmq_spinor_free.argtypes = [vp]
+    L.tmq_spinor_bytes.restype = C.c_size_t; L.tmq_spinor_bytes.argtypes = [vp]
+    L.tmq_spinor_from_qkxtm.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.tmq_spinor_to_qkxtm.argtypes = [vp, C.c_int, vp, C.c_int, C.c_double]
+    L.tmq_spinor_from_host.argtypes = [vp, dp]; L.tmq_spinor_to_host.argtypes = [dp, vp]
+    L.tmq_spinor_even.restype = vp; L.tmq_spinor_even.argtypes = [vp]
+    L.tmq_spinor_odd.restype = vp; L.tmq_spinor_odd.argtypes = [vp]
+    L.tmq_op_set.argtypes = [vp, C.c_double, C.c_double, C.c_int]
+    L.tmq_dslash.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.tmq_dslash_twist_xpay.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_double]
+    L.tmq_matpc.argtypes = [vp, vp, C.c_int]; L.tmq_mdagm.argtypes = [vp, vp]
+    L.tmq_mat_full.argtypes = [vp, vp, C.c_int]
+    L.tmq_prepare.argtypes = [vp, vp]; L.tmq_reconstruct.argtypes = [vp, vp, vp]
+    L.tmq_cg_mdagm.argtypes = [vp, vp, C.c_double, C.c_int, C.c_double, C.c_int, ip, dp, dp, dp]
+    L.tmq_cg_history.argtypes = [vp, dp, C.c_int]
+    L.tmq_zero.argtypes = [vp]; L.tmq_copy.argtypes = [vp, vp]
+    L.tmq_ax.argtypes = [C.c_double, vp]
+    L.tmq_axpy.argtypes = [C.c_double, vp, vp]
+    L.tmq_axpby.argtypes = [C.c_double, vp, C.c_double, vp]
+    L.tmq_xpay.argtypes = [vp, C.c_double, vp]
+    L.tmq_caxpy.argtypes = [dp, vp, vp]
+    L.tmq_cxpaypbz.argtypes = [vp, dp, vp, dp, vp]
+    L.tmq_norm2.argtypes = [vp, dp]; L.tmq_redot.argtypes = [vp, vp, dp]; L.tmq_cdot.argtypes = [vp, vp, dp]
+    L.tmq_axpy_norm.argtypes = [C.c_double, vp, vp, dp]; L.tmq_xmy_norm.argtypes = [vp, vp, dp]
+    L.tmq_axpy_zpbx.argtypes = [C.c_double, vp, vp, vp, C.c_double]
+    L.tmq_gamma5.argtypes = [vp]
+    L.tmq_qkxtm_scale.argtypes = [vp, vp, C.c_int, C.c_double]
+    L.tmq_qkxtm_cast.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.tmq_qkxtm_gamma5.argtypes = [vp, vp, C.c_int]
+    L.tmq_qkxtm_absorb.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    L.tmq_dev_malloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]; L.tmq_dev_free.argtypes = [vp, vp]
+    L.tmq_dev_memset.argtypes = [vp, vp, C.c_int, C.c_size_t]
+    L.tmq_h2d.argtypes = [vp, vp, vp, C.c_size_t]; L.tmq_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.tmq_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, dp, C.POINTER(C.c_longlong)]
+    L.tmq_launch_count.restype = C.c_longlong; L.tmq_launch_count.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _ck(rc):
+    if rc != 0:
+        raise TmqError(load().tmq_last_error().decode())
+
+
+def _i4(v):
+    return (C.c_int * 4)(*[int(x) for x in v])
+
+
+def _dp(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    _ck(load().tmq_comm_unique_id(buf))
+    return buf.raw
+
+
+class Spinor:
+    def __init__(self, ctx, prec=PREC_DOUBLE, subset=PARITY, _handle=None):
+        self.ctx, self.prec, self.subset = ctx, prec, subset
+        self._owner = _handle is None
+        self.h = _handle if _handle is not None else ctx.L.tmq_spinor_alloc(ctx.h, prec, subset)
+        if not self.h:
+            raise TmqError(ctx.L.tmq_last_error().decode())
+
+    def free(self):
+        if self.h and self._owner:
+            self.ctx.L.tmq_spinor_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    @property
+    def nsites(self):
+        return self.ctx.Vh * self.subset
+
+    def set(self, host_eo):
+        """host even-odd order [cb][4][3][2] float64 (FULL: [even Vh | odd Vh])"""
+        a = np.ascontiguousarray(host_eo, dtype=np.float64)
+        assert a.size == self.nsites * 24, (a.shape, self.nsites)
+        _ck(self.ctx.L.tmq_spinor_from_host(self.h, _dp(a)))
+        return self
+
+    def get(self):
+        out = np.empty((self.nsites, 4, 3, 2), dtype=np.float64)
+        _ck(self.ctx.L.tmq_spinor_to_host(_dp(out), self.h))
+        return out
+
+    def even(self):
+        return Spinor(self.ctx, self.prec, PARITY, _handle=self.ctx.L.tmq_spinor_even(self.h))
+
+    def odd(self):
+        return Spinor(self.ctx, self.prec, PARITY, _handle=self.ctx.L.tmq_spinor_odd(self.h))
+
+
+class Context:
+    """One GPU / one rank.  Mirrors initQuda + init_qudaQKXTM + loadGaugeQuda + createDirac."""
+
+    def __init__(self, localX, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0), device=0):
+        self.L = load()
+        self.X = tuple(int(x) for x in localX)
+        self.grid, self.coord = tuple(grid), tuple(coord)
+        self.V = int(np.prod(self.X)); self.Vh = self.V // 2
+        self.h = self.L.tmq_create(device, _i4(localX), _i4(grid), _i4(coord))
+        if not self.h:
+            raise TmqError(self.L.tmq_last_error().decode())
+        self._gauge_keep = None
+
+    def close(self):
+        if self.h:
+            self.L.tmq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup
+    def force_partition(self, part): _ck(self.L.tmq_force_partition(self.h, _i4(part)))
+    def set_tile(self, ty, tz, tt): _ck(self.L.tmq_set_tile(self.h, ty, tz, tt))
+    def comm_init(self, uid, nranks, rank): _ck(self.L.tmq_comm_init(self.h, uid, nranks, rank))
+    def sync(self): _ck(self.L.tmq_sync(self.h))
+
+    def load_gauge(self, gauge_qdp, t_boundary=-1, recon=12):
+        """gauge_qdp: float64 [4][V][3][3][2], QDP even-odd order, boundary sign already folded in"""
+        g = np.ascontiguousarray(gauge_qdp, dtype=np.float64)
+        assert g.shape[0] == 4 and g[0].size == self.V * 18
+        ptrs = (C.c_void_p * 4)(*[g[mu].ctypes.data for mu in range(4)])
+        _ck(self.L.tmq_gauge_load(self.h, ptrs, int(t_boundary), int(recon)))
+
+    def plaquette(self):
+        p = C.c_double(0)
+        _ck(self.L.tmq_plaquette(self.h, C.byref(p)))
+        return p.value
+
+    def set_op(self, kappa, mu, matpc=MATPC_EVEN_EVEN): _ck(self.L.tmq_op_set(self.h, kappa, mu, matpc))
+
+    def spinor(self, prec=PREC_DOUBLE, subset=PARITY): return Spinor(self, prec, subset)
+
+    # -- operator
+    def dslash(self, out, inp, out_parity, dagger=0): _ck(self.L.tmq_dslash(out.h, inp.h, out_parity, dagger))
+    def dslash_twist_xpay(self, out, inp, out_parity, dagger=0, x=None, k=0.0):
+        _ck(self.L.tmq_dslash_twist_xpay(out.h, inp.h, out_parity, dagger, x.h if x is not None else None, k))
+    def matpc(self, out, inp, dagger=0): _ck(self.L.tmq_matpc(out.h, inp.h, dagger))
+    def mdagm(self, out, inp): _ck(self.L.tmq_mdagm(out.h, inp.h))
+    def mat_full(self, out, inp, dagger=0): _ck(self.L.tmq_mat_full(out.h, inp.h, dagger))
+    def prepare(self, src_pc, b_full): _ck(self.L.tmq_prepare(src_pc.h, b_full.h))
+    def reconstruct(self, x_full, x_pc, b_full): _ck(self.L.tmq_reconstruct(x_full.h, x_pc.h, b_full.h))
+
+    def cg_mdagm(self, x, b, tol=1e-7, maxiter=10000, reliable_delta=1e-1, sloppy_prec=PREC_DOUBLE):
+        it = C.c_int(0); tr = C.c_double(0); secs = C.c_double(0); gf = C.c_double(0)
+        _ck(self.L.tmq_cg_mdagm(x.h, b.h, tol, maxiter, reliable_delta, sloppy_prec, C.byref(it), C.byref(tr),
+                                C.byref(secs), C.byref(gf)))
+        return dict(iter=it.value, true_res=tr.value, secs=secs.value, gflops=gf.value)
+
+    def cg_history(self, n):
+        h = np.zeros(n)
+        _ck(self.L.tmq_cg_history(self.h, _dp(h), n))
+        return h
+
+    # -- blas
+    def zero(self, x): _ck(self.L.tmq_zero(x.h))
+    def copy(self, dst, src): _ck(self.L.tmq_copy(dst.h, src.h))
+    def ax(self, a, x): _ck(self.L.tmq_ax(a, x.h))
+    def axpy(self, a, x, y): _ck(self.L.tmq_axpy(a, x.h, y.h))
+    def axpby(self, a, x, b, y): _ck(self.L.tmq_axpby(a, x.h, b, y.h))
+    def xpay(self, x, a, y): _ck(self.L.tmq_xpay(x.h, a, y.h))
+    def caxpy(self, a, x, y): _ck(self.L.tmq_caxpy((C.c_double * 2)(a.real, a.imag), x.h, y.h))
+    def cxpaypbz(self, x, a, y, b, z):
+        _ck(self.L.tmq_cxpaypbz(x.h, (C.c_double * 2)(a.real, a.imag), y.h, (C.c_double * 2)(b.real, b.imag), z.h))
+    def norm2(self, x):
+        o = C.c_double(0); _ck(self.L.tmq_norm2(x.h, C.byref(o))); return o.value
+    def redot(self, x, y):
+        o = C.c_double(0); _ck(self.L.tmq_redot(x.h, y.h, C.byref(o))); return o.value
+    def cdot(self, x, y):
+        o = (C.c_double * 2)(); _ck(self.L.tmq_cdot(x.h, y.h, o)); return complex(o[0], o[1])
+    def axpy_norm(self, a, x, y):
+        o = C.c_double(0); _ck(self.L.tmq_axpy_norm(a, x.h, y.h, C.byref(o))); return o.value
+    def xmy_norm(self, x, y):
+        o = C.c_double(0); _ck(self.L.tmq_xmy_norm(x.h, y.h, C.byref(o))); return o.value
+    def axpy_zpbx(self, a, x, y, z, b): _ck(self.L.tmq_axpy_zpbx(a, x.h, y.h, z.h, b))
+    def gamma5(self, x): _ck(self.L.tmq_gamma5(x.h))
+
+    # -- raw device memory + QKXTM-layout kernels
+    def dev_malloc(self, nbytes):
+        p = C.c_void_p(0); _ck(self.L.tmq_dev_malloc(self.h, C.byref(p), nbytes)); return p.value
+    def dev_free(self, p): _ck(self.L.tmq_dev_free(self.h, p))
+    def h2d(self, dptr, arr):
+        a = np.ascontiguousarray(arr); _ck(self.L.tmq_h2d(self.h, dptr, a.ctypes.data, a.nbytes))
+    def d2h(self, arr, dptr):
+        assert arr.flags["C_CONTIGUOUS"]; _ck(self.L.tmq_d2h(self.h, arr.ctypes.data, dptr, arr.nbytes))
+    def from_qkxtm(self, dst, dptr, qprec=PREC_DOUBLE, parity=-1): _ck(self.L.tmq_spinor_from_qkxtm(dst.h, dptr, qprec, parity))
+    def to_qkxtm(self, dptr, src, qprec=PREC_DOUBLE, parity=-1, scale=1.0):
+        _ck(self.L.tmq_spinor_to_qkxtm(dptr, qprec, src.h, parity, scale))
+    def qkxtm_scale(self, dptr, prec, a): _ck(self.L.tmq_qkxtm_scale(self.h, dptr, prec, a))
+    def qkxtm_cast(self, dst, dprec, src, sprec): _ck(self.L.tmq_qkxtm_cast(self.h, dst, dprec, src, sprec))
+    def qkxtm_gamma5(self, dptr, prec): _ck(self.L.tmq_qkxtm_gamma5(self.h, dptr, prec))
+    def qkxtm_absorb(self, dprop, dvec, prec, nu, c2): _ck(self.L.tmq_qkxtm_absorb(self.h, dprop, dvec, prec, nu, c2))
+
+    # -- measurement
+    def time_kernel(self, kind, prec, reps, inp, flush_l2=0):
+        ms = C.c_double(0); nl = C.c_longlong(0)
+        _ck(self.L.tmq_time_kernel(self.h, kind, prec, reps, inp.h, flush_l2, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def launch_count(self): return int(self.L.tmq_launch_count(self.h))
+
+
+# ---- host-side field generators (libqkxtm_tmq.so, include/tmq_host.h) ------------------------------------------
+HOST_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libqkxtm_tmq.so")
+_hostlib = None
+
+
+def load_host():
+    global _hostlib
+    if _hostlib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise TmqError("libqkxtm_tmq.so not built (%s)" % HOST_LIB_PATH)
+        load()   # libtmq.so first (the shim links against it)
+        H = C.CDLL(HOST_LIB_PATH)
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        H.tmq_fieldgen_gauge_qdp.argtypes = [C.POINTER(dp), ip, ip, ip, C.c_ulonglong, C.c_int]
+        H.tmq_fieldgen_unit_gauge_qdp.argtypes = [C.POINTER(dp), ip, ip, ip, C.c_int]
+        H.tmq_fieldgen_spinor_gaussian.argtypes = [dp, ip, ip, ip, C.c_ulonglong, C.c_int]
+        H.tmq_fieldgen_spinor_z4.argtypes = [dp, ip, ip, ip, C.c_ulonglong, C.c_int]
+        _hostlib = H
+    return _hostlib
+
+
+def gen_gauge(localX, seed=137, t_boundary=-1, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0), unit=False):
+    """float64 [4][V][3][3][2], QDP even-odd order, boundary sign folded in"""
+    H = load_host()
+    V = int(np.prod(localX))
+    g = np.empty((4, V, 3, 3, 2), dtype=np.float64)
+    ptrs = (C.POINTER(C.c_double) * 4)(*[g[mu].ctypes.data_as(C.POINTER(C.c_double)) for mu in range(4)])
+    if unit:
+        H.tmq_fieldgen_unit_gauge_qdp(ptrs, _i4(localX), _i4(grid), _i4(coord), t_boundary)
+    else:
+        H.tmq_fieldgen_gauge_qdp(ptrs, _i4(localX), _i4(grid), _i4(coord), seed, t_boundary)
+    return g
+
+
+def gen_spinor(localX, kind="gaussian", seed=None, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0), eo_order=True):
+    H = load_host()
+    V = int(np.prod(localX))
+    out = np.empty((V, 4, 3, 2), dtype=np.float64)
+    if kind == "gaussian":
+        H.tmq_fieldgen_spinor_gaussian(_dp(out), _i4(localX), _i4(grid), _i4(coord), 101 if seed is None else seed, int(eo_order))
+    elif kind == "z4":
+        H.tmq_fieldgen_spinor_z4(_dp(out), _i4(localX), _i4(grid), _i4(coord), 100 if seed is None else seed, int(eo_order))
+    else:
+        raise ValueError(kind)
+    return out
