@@ -400,6 +400,7 @@ int tmq_destroy(tmq_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  while (!c->spinors.empty()) tmq_spinor_free(*c->spinors.begin());
   comm_destroy(c);
   tmq_gauge_free(c);
   for (int i = 0; i < NSCRATCH; i++) { if (c->scr_d.tmp[i]) cudaFree(c->scr_d.tmp[i]); if (c->scr_s.tmp[i]) cudaFree(c->scr_s.tmp[i]); }
@@ -510,10 +511,13 @@ tmq_spinor *tmq_spinor_alloc(tmq_ctx *c, int prec, int subset) {
     return nullptr;
   }
   cudaMemsetAsync(s->d, 0, s->bytes, c->stream);
+  c->spinors.insert(s);
   return s;
 }
 int tmq_spinor_free(tmq_spinor *s) {
   if (!s) return 0;
+  if (!s->owns) { set_error("Even()/Odd() views are freed with their FULL field"); return 1; }
+  s->ctx->spinors.erase(s);
   for (int i = 0; i < 2; i++) if (s->view[i]) delete s->view[i];
   if (s->owns && s->d) { cudaStreamSynchronize(s->ctx->stream); cudaFree(s->d); }
   delete s;

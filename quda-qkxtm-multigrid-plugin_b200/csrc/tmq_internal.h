@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <set>
 #include <string>
 #include <vector>
 #include "tmq_types.h"
@@ -72,6 +73,8 @@ struct tmq_ctx {
   // grow-only device staging buffer for host <-> native conversions
   void *stage;
   size_t stage_bytes;
+  // live spinor handles allocated on this context (freed by tmq_destroy; their handles die with the context)
+  std::set<tmq_spinor *> spinors;
   // timing-kernel scratch (tmq_time_kernel)
   int sms;
 };

@@ -7,6 +7,7 @@ There is NO fallback: if libtmq.so is missing or no CUDA device is usable, the c
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -121,9 +122,10 @@ class Spinor:
         self.h = _handle if _handle is not None else ctx.L.tmq_spinor_alloc(ctx.h, prec, subset)
         if not self.h:
             raise TmqError(ctx.L.tmq_last_error().decode())
+        ctx._spinors.add(self)
 
     def free(self):
-        if self.h and self._owner:
+        if self.h and self._owner and self.ctx.h:
             self.ctx.L.tmq_spinor_free(self.h)
         self.h = None
 
@@ -164,13 +166,17 @@ class Context:
         self.X = tuple(int(x) for x in localX)
         self.grid, self.coord = tuple(grid), tuple(coord)
         self.V = int(np.prod(self.X)); self.Vh = self.V // 2
+        self._spinors = weakref.WeakSet()
         self.h = self.L.tmq_create(device, _i4(localX), _i4(grid), _i4(coord))
         if not self.h:
             raise TmqError(self.L.tmq_last_error().decode())
         self._gauge_keep = None
 
     def close(self):
+        """tmq_destroy frees every spinor of the context: invalidate their Python handles first"""
         if self.h:
+            for s in list(self._spinors):
+                s.free()
             self.L.tmq_destroy(self.h)
             self.h = None
 
