@@ -47,12 +47,12 @@ static int largest_divisor_le(int n, int pref) {
   return 1;
 }
 
-Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_pref[3]) {
+Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_pref[3], const int step[3]) {
   Enum en;
   const int Ty = largest_divisor_le(ext[0], tile_pref[0]);
   const int Tz = largest_divisor_le(ext[1], tile_pref[1]);
   const int Tt = largest_divisor_le(ext[2], tile_pref[2]);
-  for (int i = 0; i < 3; i++) en.lo[i] = lo[i];
+  for (int i = 0; i < 3; i++) { en.lo[i] = lo[i]; en.step[i] = step ? step[i] : 1; }
   en.nsites = g.Xh * ext[0] * ext[1] * ext[2];
   en.dXh = make_fastdiv((uint32_t)g.Xh);
   en.dTy = make_fastdiv((uint32_t)Ty);
@@ -172,26 +172,22 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   const int zlo = g.part[2] ? 1 : 0, zhi = g.part[2] ? g.X[2] - 1 : g.X[2];   // interior range [lo, hi)
   const int tlo = g.part[3] ? 1 : 0, thi = g.part[3] ? g.X[3] - 1 : g.X[3];
   bool first = true;
-  auto launch_box = [&](int z0, int z1, int t0, int t1) -> int {
-    if (z1 <= z0 || t1 <= t0) return 0;
-    const int lo[3] = {0, z0, t0}, ext[3] = {g.X[1], z1 - z0, t1 - t0};
-    A.en = make_enum(g, lo, ext, c->tile);
+  // a box of the (y,z,t) index space; nz / nt enumerated z / t values spaced by sz / st
+  auto launch_box = [&](int z0, int nz, int sz, int t0, int nt, int st) -> int {
+    if (nz <= 0 || nt <= 0) return 0;
+    const int lo[3] = {0, z0, t0}, ext[3] = {g.X[1], nz, nt}, step[3] = {1, sz, st};
+    A.en = make_enum(g, lo, ext, c->tile, step);
     A.red_accum = (has_red && !first) ? 1 : 0;
     TMQ_CUDA(launch_any<F>(c, s.epi, true, A, c->stream));
     c->launches++;
     first = false;
     return 0;
   };
-  TMQ_TRY(launch_box(zlo, zhi, tlo, thi));                       // interior: no ghost needed
+  TMQ_TRY(launch_box(zlo, zhi - zlo, 1, tlo, thi - tlo, 1));     // interior: no ghost needed
   TMQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-  if (g.part[3]) {
-    TMQ_TRY(launch_box(0, g.X[2], 0, 1));
-    if (g.X[3] > 1) TMQ_TRY(launch_box(0, g.X[2], g.X[3] - 1, g.X[3]));
-  }
-  if (g.part[2]) {
-    TMQ_TRY(launch_box(0, 1, tlo, thi));
-    if (g.X[2] > 1) TMQ_TRY(launch_box(g.X[2] - 1, g.X[2], tlo, thi));
-  }
+  // boundary: the two t slices {0, T-1} in one launch, then the two z slices of the interior t range
+  if (g.part[3]) TMQ_TRY(launch_box(0, g.X[2], 1, 0, 2, g.X[3] - 1));
+  if (g.part[2]) TMQ_TRY(launch_box(0, 2, g.X[2] - 1, tlo, thi - tlo, 1));
   if (has_red) TMQ_TRY(comm_allreduce(c, c->scal + s.red_slot, 1, c->stream));
   return 0;
 }
@@ -343,7 +339,12 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
 
   bool ok = true;
   ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) == cudaSuccess;
+  {
+    // the exchange must not queue behind the interior kernel's CTAs: give its stream the highest priority
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    ok = ok && cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+  }
   ok = ok && cudaEventCreate(&c->ev_a) == cudaSuccess && cudaEventCreate(&c->ev_b) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) == cudaSuccess;

@@ -94,7 +94,7 @@ void set_error(const char *fmt, ...);
 inline size_t vec_bytes(int prec) { return prec == 8 ? 32 : 16; }
 inline size_t parity_bytes(const tmq_ctx *c, int prec) { return (size_t)6 * c->g.Vh * vec_bytes(prec); }
 
-Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_pref[3]);
+Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_pref[3], const int step[3] = nullptr);
 
 // dslash launchers (one TU per precision x recon)
 cudaError_t launch_dslash_d12(int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st);

@@ -93,9 +93,9 @@ TMQ_HD SiteCoord decode_site(const Geom &g, const Enum &en, int parity, uint32_t
   q = fd_div(r, en.dTt); int lt = (int)(r - q * en.dTt.d); r = q;
   q = fd_div(r, en.dNy); int ty = (int)(r - q * en.dNy.d); r = q;
   q = fd_div(r, en.dNz); int tz = (int)(r - q * en.dNz.d); int tt = (int)q;
-  c.y = en.lo[0] + ty * (int)en.dTy.d + ly;
-  c.z = en.lo[1] + tz * (int)en.dTz.d + lz;
-  c.t = en.lo[2] + tt * (int)en.dTt.d + lt;
+  c.y = en.lo[0] + (ty * (int)en.dTy.d + ly) * en.step[0];
+  c.z = en.lo[1] + (tz * (int)en.dTz.d + lz) * en.step[1];
+  c.t = en.lo[2] + (tt * (int)en.dTt.d + lt) * en.step[2];
   c.xodd = (c.y + c.z + c.t + parity) & 1;
   c.idx = ((c.t * g.X[2] + c.z) * g.X[1] + c.y) * g.Xh + c.xh;
   return c;

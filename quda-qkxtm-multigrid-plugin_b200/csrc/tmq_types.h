@@ -73,6 +73,8 @@ struct Geom {
 // interior / boundary slabs of a sharded lattice are further sub-boxes.
 struct Enum {
   int lo[3];                              // y, z, t origin
+  int step[3];                            // coordinate stride per enumerated index (1, or L-1 to visit the two
+                                          // boundary slices 0 and L-1 of a partitioned dimension in one launch)
   int nsites;                             // Xh * ext_y * ext_z * ext_t
   FastDiv dXh, dTy, dTz, dTt, dNy, dNz;   // divisors for the decode chain
 };

@@ -187,3 +187,26 @@ def c2r(z):
 
 def r2c(a):
     return a[..., 0] + 1j * a[..., 1]
+
+
+# ---- sharding helpers (host logic of the multi-GPU path) ---------------------------------------------
+
+def rank_coord(rank, grid):
+    """rank -> process-grid coordinate, t fastest then z (the order libtmq's rank_of() uses)"""
+    ct = rank % grid[3]; cz = (rank // grid[3]) % grid[2]; cy = (rank // (grid[3] * grid[2])) % grid[1]
+    cx = rank // (grid[3] * grid[2] * grid[1])
+    return (cx, cy, cz, ct)
+
+
+def coord_rank(coord, grid):
+    return ((coord[0] * grid[1] + coord[1]) * grid[2] + coord[2]) * grid[3] + coord[3]
+
+
+def local_from_global_eo(field_global_eo, Xloc, grid, coord):
+    """slab of a FULL global even-odd field owned by the rank at `coord`, in the rank's local even-odd order"""
+    G = tuple(Xloc[d] * grid[d] for d in range(4))
+    gl, _ = global_lex(Xloc, grid, coord)                 # global lex index of each local lex site
+    inv = np.empty(int(np.prod(G)), dtype=np.int64)
+    inv[eo_from_lex(G)] = np.arange(len(inv))             # global lex -> global eo position
+    loc_perm = eo_from_lex(Xloc)                          # local eo -> local lex
+    return np.ascontiguousarray(field_global_eo[inv[gl.astype(np.int64)[loc_perm]]])

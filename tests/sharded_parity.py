@@ -1,0 +1,98 @@
+"""Sharded (multi-GPU) parity check, one process per GPU.  Launch:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29517 \
+        tests/sharded_parity.py --lattice 8 8 8 16 --grid 1 1 1 2
+Every rank computes the CPU oracle on the GLOBAL lattice and compares its own slab of the device result
+(hop both parities / daggers, M^dag M, CG iterations, true residual).  Exit code 0 = parity green."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "quda-qkxtm-multigrid-plugin_b200")):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import lattice_util as lu
+import tmq
+from oracle.oracle import Oracle
+
+KAPPA, MU = 1.0 / (2.0 * 4.1), 0.1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lattice", type=int, nargs=4, default=[8, 8, 8, 16])
+    ap.add_argument("--grid", type=int, nargs=4, default=[1, 1, 1, 2])
+    ap.add_argument("--recon", type=int, default=12)
+    a = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    G, grid = tuple(a.lattice), tuple(a.grid)
+    assert int(np.prod(grid)) == world
+    X = tuple(G[d] // grid[d] for d in range(4))
+    coord = lu.rank_coord(rank, grid)
+    ctx = tmq.Context(X, grid=grid, coord=coord, device=int(os.environ.get("LOCAL_RANK", rank)))
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(tmq.comm_unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(uid, src=0)
+    ctx.comm_init(uid.numpy().tobytes(), world, rank)
+    ctx.load_gauge(tmq.gen_gauge(X, grid=grid, coord=coord), t_boundary=-1, recon=a.recon)
+    ctx.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
+
+    o = Oracle(G)
+    gauge_g = tmq.gen_gauge(G)
+    psi_g = tmq.gen_spinor(G)                                   # global, even-odd order
+    Vh_g, Vh = o.Vh, ctx.Vh
+    loc = lu.local_from_global_eo(psi_g, X, grid, coord)        # local FULL field
+    assert np.array_equal(loc, tmq.gen_spinor(X, grid=grid, coord=coord)), "sharded generator != slab of global field"
+    fails = []
+    for prec, tol in ((8, 1e-13), (4, 1e-5)):
+        s_in, s_out = ctx.spinor(prec), ctx.spinor(prec)
+        for out_parity in (0, 1):
+            src_g = np.ascontiguousarray(psi_g[(1 - out_parity) * Vh_g:(2 - out_parity) * Vh_g])
+            s_in.set(loc[(1 - out_parity) * Vh:(2 - out_parity) * Vh])
+            for dagger in (0, 1):
+                ref = np.zeros_like(psi_g)
+                ref[out_parity * Vh_g:(out_parity + 1) * Vh_g] = o.dslash(gauge_g, src_g, out_parity, dagger)
+                ref_loc = lu.local_from_global_eo(ref, X, grid, coord)[out_parity * Vh:(out_parity + 1) * Vh]
+                ctx.dslash(s_out, s_in, out_parity, dagger)
+                e = lu.rel_l2(s_out.get(), ref_loc)
+                if not e < tol:
+                    fails.append(("hop", prec, out_parity, dagger, e))
+        even_g = np.ascontiguousarray(psi_g[:Vh_g])
+        ref = np.zeros_like(psi_g); ref[:Vh_g] = o.mdagm(gauge_g, even_g, KAPPA, MU, 0)
+        s_in.set(loc[:Vh]); ctx.mdagm(s_out, s_in)
+        e = lu.rel_l2(s_out.get(), lu.local_from_global_eo(ref, X, grid, coord)[:Vh])
+        if not e < 2 * tol:
+            fails.append(("mdagm", prec, e))
+    # CG: iteration count and residual against the CPU CG on the global lattice
+    x_ref, it_ref, tr_ref, _ = o.cg_mdagm(gauge_g, even_g, KAPPA, MU, 0, tol=1e-9, maxiter=5000)
+    b, x = ctx.spinor(8), ctx.spinor(8)
+    b.set(loc[:Vh])
+    info = ctx.cg_mdagm(x, b, tol=1e-9, maxiter=5000)
+    xr = np.zeros_like(psi_g); xr[:Vh_g] = x_ref
+    e = lu.rel_l2(x.get(), lu.local_from_global_eo(xr, X, grid, coord)[:Vh])
+    if abs(info["iter"] - it_ref) > 2 or info["true_res"] > 1.05e-9 or e > 1e-8:
+        fails.append(("cg", info, it_ref, e))
+    info4 = ctx.cg_mdagm(x, b, tol=1e-9, maxiter=5000, sloppy_prec=4, reliable_delta=0.1)
+    e4 = lu.rel_l2(x.get(), lu.local_from_global_eo(xr, X, grid, coord)[:Vh])
+    if info4["true_res"] > 1.05e-9 or e4 > 1e-7:
+        fails.append(("cg-mixed", info4, e4))
+    n2 = ctx.norm2(b)
+    if abs(n2 - np.sum(even_g * even_g)) > 1e-12 * n2:
+        fails.append(("norm2-allreduce", n2))
+    print("rank %d/%d coord %s: cg iters %d (cpu %d) true_res %.2e mixed iters %d; failures: %s"
+          % (rank, world, coord, info["iter"], it_ref, info["true_res"], info4["iter"], fails), flush=True)
+    t = torch.tensor([len(fails)], dtype=torch.int64)
+    dist.all_reduce(t)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if int(t[0]) else 0)
+
+
+if __name__ == "__main__":
+    main()
