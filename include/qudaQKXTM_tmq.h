@@ -1,0 +1,221 @@
+// qudaQKXTM_tmq.h -- the C++ host side of the drop-in: the QKXTM containers, parameter structs and solve entry
+// points of ETMC-QUDA/quda-QKXTM-Multigrid-PlugIn for ONE hot path (even-odd twisted-mass Dslash + CG on
+// M^dag M), re-implemented over the libtmq.so C ABI (include/tmq.h).  Same names, argument meaning and
+// error behaviour (errorQuda aborts) as the reference, so that a driver written against
+//   include/qudaQKXTM.h:104-277 (containers), :484-513 (entry points),
+//   include/qudaQKXTM_utils.h:45-75,126-139 (qudaQKXTMinfo, enums, init_qudaQKXTM)
+// and the handful of QUDA C-API calls the drivers make (qkxtm/Calc_Loops.cpp:692-708,753-759,797-806)
+// compiles against this header for that path.  Everything the path does not touch (contractions, smearing,
+// deflation, loops, file I/O, ghost exchange of the containers) is deliberately absent -- see DESIGN.md.
+//
+// Threading / state: like the reference, one host thread per rank and library-global state (one context,
+// one resident gauge field, one-shot init_qudaQKXTM); not re-entrant.
+#ifndef QUDAQKXTM_TMQ_H
+#define QUDAQKXTM_TMQ_H
+
+#include <cstddef>
+#include <typeinfo>
+#include "tmq.h"
+
+#define QUDAQKXTM_DIM 4
+
+// ---- the slice of quda.h / enum_quda.h the path reads ----------------------------------------------
+typedef enum { QUDA_SINGLE_PRECISION = 4, QUDA_DOUBLE_PRECISION = 8 } QudaPrecision;
+typedef enum { QUDA_RECONSTRUCT_NO = 18, QUDA_RECONSTRUCT_12 = 12 } QudaReconstructType;
+typedef enum { QUDA_ANTI_PERIODIC_T = -1, QUDA_PERIODIC_T = 1 } QudaTboundary;
+typedef enum { QUDA_QDP_GAUGE_ORDER = 0 } QudaGaugeFieldOrder;
+typedef enum { QUDA_WILSON_LINKS = 0, QUDA_SMEARED_LINKS = 1 } QudaLinkType;
+typedef enum { QUDA_GAUGE_FIXED_NO = 0 } QudaGaugeFixed;
+typedef enum { QUDA_TWISTED_MASS_DSLASH = 0, QUDA_WILSON_DSLASH = 1, QUDA_TWISTED_CLOVER_DSLASH = 2 } QudaDslashType;
+typedef enum { QUDA_CG_INVERTER = 0, QUDA_GCR_INVERTER = 1, QUDA_BICGSTAB_INVERTER = 2, QUDA_INVALID_INVERTER = -1 } QudaInverterType;
+typedef enum { QUDA_MAT_SOLUTION = 0, QUDA_MATPC_SOLUTION = 1, QUDA_MATPCDAG_MATPC_SOLUTION = 2 } QudaSolutionType;
+typedef enum { QUDA_DIRECT_SOLVE = 0, QUDA_NORMOP_SOLVE = 1, QUDA_DIRECT_PC_SOLVE = 2, QUDA_NORMOP_PC_SOLVE = 3 } QudaSolveType;
+typedef enum { QUDA_MATPC_EVEN_EVEN = 0, QUDA_MATPC_ODD_ODD = 1, QUDA_MATPC_EVEN_EVEN_ASYMMETRIC = 2,
+               QUDA_MATPC_ODD_ODD_ASYMMETRIC = 3 } QudaMatPCType;
+typedef enum { QUDA_KAPPA_NORMALIZATION = 0, QUDA_MASS_NORMALIZATION = 1, QUDA_ASYMMETRIC_MASS_NORMALIZATION = 2 } QudaMassNormalization;
+typedef enum { QUDA_DEGRAND_ROSSI_GAMMA_BASIS = 0, QUDA_UKQCD_GAMMA_BASIS = 1 } QudaGammaBasis;
+typedef enum { QUDA_DIRAC_ORDER = 0 } QudaDiracFieldOrder;
+typedef enum { QUDA_TWIST_SINGLET = 1, QUDA_TWIST_NO = 0 } QudaTwistFlavorType;
+typedef enum { QUDA_DAG_NO = 0, QUDA_DAG_YES = 1 } QudaDagType;
+typedef enum { QUDA_PRESERVE_SOURCE_NO = 0, QUDA_PRESERVE_SOURCE_YES = 1 } QudaPreserveSource;
+typedef enum { QUDA_CPU_FIELD_LOCATION = 1, QUDA_CUDA_FIELD_LOCATION = 2 } QudaFieldLocation;
+typedef enum { QUDA_L2_RELATIVE_RESIDUAL = 1 } QudaResidualType;
+typedef enum { QUDA_SILENT = 0, QUDA_SUMMARIZE = 1, QUDA_VERBOSE = 2 } QudaVerbosity;
+typedef enum { QUDA_PARITY_SITE_SUBSET = 1, QUDA_FULL_SITE_SUBSET = 2 } QudaSiteSubset;
+
+typedef struct QudaGaugeParam_s {       // fields set at qkxtm/Calc_Loops.cpp:189-225
+  int X[4];
+  double anisotropy;
+  QudaLinkType type;
+  QudaGaugeFieldOrder gauge_order;
+  QudaTboundary t_boundary;
+  QudaPrecision cpu_prec, cuda_prec, cuda_prec_sloppy, cuda_prec_precondition;
+  QudaReconstructType reconstruct, reconstruct_sloppy, reconstruct_precondition;
+  QudaGaugeFixed gauge_fix;
+  int ga_pad;
+} QudaGaugeParam;
+
+typedef struct QudaInvertParam_s {      // fields read / written on the path
+  double kappa, mu, mass;
+  QudaDslashType dslash_type;
+  QudaTwistFlavorType twist_flavor;
+  QudaMatPCType matpc_type;
+  QudaSolveType solve_type;
+  QudaSolutionType solution_type;
+  QudaInverterType inv_type, inv_type_precondition;
+  QudaMassNormalization mass_normalization;
+  QudaGammaBasis gamma_basis;
+  QudaDiracFieldOrder dirac_order;
+  QudaPrecision cpu_prec, cuda_prec, cuda_prec_sloppy, cuda_prec_precondition;
+  QudaPreserveSource preserve_source;
+  QudaFieldLocation input_location, output_location;
+  int sp_pad, cl_pad, Ls;
+  QudaDagType dagger;
+  double tol, tol_hq;
+  QudaResidualType residual_type;
+  int maxiter;
+  double reliable_delta;
+  int pipeline, gcrNkrylov;
+  QudaVerbosity verbosity, verbosity_precondition;
+  void *preconditioner;
+  // outputs (zeroed before each solve, lib/qudaQKXTM_interface.cpp:95-97; filled like updateInvertParam)
+  double spinorGiB, secs, gflops, true_res;
+  int iter;
+} QudaInvertParam;
+
+QudaGaugeParam newQudaGaugeParam(void);
+QudaInvertParam newQudaInvertParam(void);
+void initCommsGridQuda(int nDim, const int *dims, void *func, void *fdata);   // qkxtm/QKXTM_util.cpp:66
+void initQuda(int device);                                                     // qkxtm/Calc_Loops.cpp:753
+void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param);                      // qkxtm/Calc_Loops.cpp:759 (void *gauge[4], QDP order)
+void freeGaugeQuda(void);
+void endQuda(void);
+// host spinors: full lattice, even-odd site order [even Vh | odd Vh][spin][colour][re,im], double
+void invertQuda(void *h_x, void *h_b, QudaInvertParam *param);
+void MatQuda(void *h_out, void *h_in, QudaInvertParam *param);                 // full operator (dslash_test-style check)
+void setVerbosityQuda(QudaVerbosity v);
+
+namespace quda {
+
+enum ALLOCATION_FLAG { NONE, HOST, DEVICE, BOTH, BOTH_EXTRA };                 // include/qudaQKXTM_utils.h:126
+enum CLASS_ENUM { FIELD, GAUGE, VECTOR, PROPAGATOR, PROPAGATOR3D, VECTOR3D };  // include/qudaQKXTM_utils.h:127
+
+typedef struct {                       // the hot-path slice of qudaQKXTMinfo (include/qudaQKXTM_utils.h:45-75)
+  int nsmearAPE, nsmearGauss;
+  double alphaAPE, alphaGauss;
+  int lL[QUDAQKXTM_DIM];
+  int Nsources;
+  QudaPrecision Precision;
+  bool isEven;
+  double kappa, mu, csw, inv_tol;
+} qudaQKXTMinfo;
+
+void init_qudaQKXTM(qudaQKXTMinfo *info);      // lib/qudaQKXTM_kernels.cu:118-297 (one-shot; containers need it)
+void printf_qudaQKXTM();
+
+// stand-in for cudaColorSpinorField on this path: a device field in libtmq's native layout
+class ColorSpinorField {
+  tmq_spinor *h_;
+  QudaSiteSubset subset_;
+public:
+  ColorSpinorField(QudaSiteSubset subset, QudaPrecision prec);   // zero-initialised (QUDA_ZERO_FIELD_CREATE)
+  ~ColorSpinorField();
+  tmq_spinor *handle() const { return h_; }
+  QudaSiteSubset SiteSubset() const { return subset_; }
+  tmq_spinor *Even() const;
+  tmq_spinor *Odd() const;
+};
+
+template <typename Float> class QKXTM_Vector;
+template <typename Float> class QKXTM_Propagator;
+
+template <typename Float> class QKXTM_Field {     // include/qudaQKXTM.h:104-160, lib/qudaQKXTM_Field.cpp:81-258
+protected:
+  int field_length;
+  long long total_length;                          // 64-bit: the reference's int overflows at 64^3x128
+  size_t bytes_total_length;
+  Float *h_elem, *h_elem_backup, *d_elem;
+  bool isAllocHost, isAllocDevice, isAllocHostBackup;
+  void create_host();
+  void create_host_backup();
+  void destroy_host();
+  void destroy_host_backup();
+  void create_device();
+  void destroy_device();
+public:
+  QKXTM_Field(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT);
+  virtual ~QKXTM_Field();
+  void zero_host();
+  void zero_host_backup();
+  void zero_device();
+  Float *H_elem() const { return h_elem; }
+  Float *D_elem() const { return d_elem; }
+  size_t Bytes_total() const { return bytes_total_length; }
+  size_t Bytes_ghost() const { return 0; }         // the containers' own ghost exchange is not on this path
+  size_t Bytes_total_plus_ghost() const { return bytes_total_length; }
+  int Precision() const { return (int)sizeof(Float); }
+  void printInfo();
+};
+
+template <typename Float> class QKXTM_Gauge : public QKXTM_Field<Float> {       // include/qudaQKXTM.h:166-183
+public:
+  QKXTM_Gauge(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT);
+  void packGauge(void **gauge);                    // lexicographic host links -> SoA (lib/qudaQKXTM_Gauge.cpp:73-89)
+  void packGaugeToBackup(void **gauge);
+  void loadGaugeFromBackup();
+  void justDownloadGauge();
+  void loadGauge();
+  double calculatePlaq();                          // prints like the reference and also returns the value
+};
+
+template <typename Float> class QKXTM_Vector : public QKXTM_Field<Float> {      // include/qudaQKXTM.h:189-225
+public:
+  QKXTM_Vector(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT);
+  void packVector(Float *vector);                  // AoS [x][s][c][ri] -> SoA (lib/qudaQKXTM_Vector.cpp:72-81)
+  void unpackVector();
+  void unpackVector(Float *vector);
+  void loadVector();
+  void unloadVector();
+  void download();                                 // D2H + SoA -> AoS in h_elem (lib/qudaQKXTM_Vector.cpp:135-156)
+  void uploadToCuda(ColorSpinorField *cudaVector, bool isEv = false);      // lib/qudaQKXTM_Vector.cpp:424-427
+  void downloadFromCuda(ColorSpinorField *cudaVector, bool isEv = false);  // lib/qudaQKXTM_Vector.cpp:430-432
+  void scaleVector(double a);
+  void castDoubleToFloat(QKXTM_Vector<double> &vecIn);
+  void castFloatToDouble(QKXTM_Vector<float> &vecIn);
+  double norm2Host();
+  void apply_gamma5();
+};
+
+template <typename Float> class QKXTM_Propagator : public QKXTM_Field<Float> {  // include/qudaQKXTM.h:244-265
+public:
+  QKXTM_Propagator(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT);
+  void absorbVectorToHost(QKXTM_Vector<Float> &vec, int nu, int c2);
+  void absorbVectorToDevice(QKXTM_Vector<Float> &vec, int nu, int c2);
+};
+
+// accessors for drivers / tests
+tmq_ctx *qkxtm_context();
+typedef void (*qkxtm_error_handler)(const char *msg);
+void qkxtm_set_error_handler(qkxtm_error_handler h);   // default: print and abort, like errorQuda
+
+}  // namespace quda
+
+// ---- solve entry points (include/qudaQKXTM.h:484-513) --------------------------------------------------------------
+// MG_bench: the 12-column point-source propagator skeleton of lib/qudaQKXTM_interface.cpp:19-233 with the
+// solver swapped for CG on M^dag M, as the calc_loops CG branch does (lib/qudaQKXTM_interface.cpp:2031-2038):
+//   point source -> packVector -> loadVector -> uploadToCuda -> prepare -> in <- M^dag in -> CG -> reconstruct
+//   -> downloadFromCuda -> scaleVector(2 kappa) if mass-normalised.
+// gaugeSmeared: lexicographic links for the plaquette print (may be NULL); gauge: unused, as in the reference
+// (the solver uses the field resident since loadGaugeQuda).  prop_out (optional, not in the reference, which
+// discards the columns): 12 x V x 24 doubles, column-major host AoS.
+void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param,
+              quda::qudaQKXTMinfo info, double *prop_out = nullptr);
+// the per-RHS solve of calc_loops' CG branch (lib/qudaQKXTM_interface.cpp:2008-2041,2062) for one host source in
+// the plug-in's AoS order [x_lex][s][c][ri]; the solution comes back in the same order.
+void calc_loops_solve(double *h_solution, double *h_source, QudaInvertParam *param, quda::qudaQKXTMinfo info);
+// QKXTM_Deflation::ApplyMdagM (lib/qudaQKXTM_Deflation.cpp:189-281, preconditioned branch): full-volume host
+// vector in the plug-in's AoS order [x_lex][s][c][ri] -> packVector/loadVector/uploadToCuda(parity isEven) ->
+// M_pc^dag M_pc -> downloadFromCuda/unloadVector/unpackVector; the other parity comes back zero-filled.
+void ApplyMdagM(double *h_out, double *h_in, QudaInvertParam *param, bool isEven);
+
+#endif

@@ -135,6 +135,9 @@ int tmq_gamma5(tmq_spinor *x);                                                  
 
 /* ---- QKXTM container kernels on the QKXTM device layout (lib/qudaQKXTM_kernels.cu:1110-1124,1353-1365,
  *      lib/code_pieces/apply_gamma5_vector_core.h, lib/qudaQKXTM_Propagator.cpp:90-106) ------------------- */
+/* plaquette of a gauge field in the QKXTM device layout d[((dir*3+c1)*3+c2)*V + x_lex] (lib/qudaQKXTM_Gauge.cpp:73-89):
+ * QKXTM_Gauge::calculatePlaq (lib/qudaQKXTM_Gauge.cpp:376-386).  Single rank.                                  */
+int tmq_qkxtm_plaquette(tmq_ctx *, const void *d_gauge_qkxtm, int prec, double *plaq);
 int tmq_qkxtm_scale(tmq_ctx *, void *d_qkxtm, int prec, double a);
 int tmq_qkxtm_cast(tmq_ctx *, void *d_dst, int dst_prec, const void *d_src, int src_prec);
 int tmq_qkxtm_gamma5(tmq_ctx *, void *d_qkxtm, int prec);

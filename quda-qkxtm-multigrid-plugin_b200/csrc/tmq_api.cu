@@ -945,6 +945,17 @@ int tmq_gamma5(tmq_spinor *x) {
 }
 
 // ---- QKXTM container kernels ------------------------------------------------------------------------------------------
+int tmq_qkxtm_plaquette(tmq_ctx *c, const void *d_gauge, int prec, double *plaq) {
+  TMQ_REQUIRE(c && d_gauge && plaq, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(c->nranks == 1, "tmq_qkxtm_plaquette is a single-rank sanity check");
+  TMQ_REQUIRE((size_t)(c->g.Vh / 64 + 1) * 1 <= c->partials_len, "partials too small");
+  TMQ_CUDA(qkxtm_plaquette(d_gauge, prec, c->g, red_at(c, SC_T0), c->stream)); c->launches++;
+  double s;
+  TMQ_TRY(fetch_scal(c, SC_T0, 1, &s));
+  *plaq = s / ((double)c->Vglobal * 3.0 * 6.0);
+  return 0;
+}
 int tmq_qkxtm_scale(tmq_ctx *c, void *d, int prec, double a) {
   TMQ_REQUIRE(c && d, "null argument");
   TMQ_CUDA(qkxtm_scale(d, prec, a, (size_t)24 * c->g.Vh, c->stream)); c->launches++;

@@ -193,6 +193,44 @@ cudaError_t plaquette_launch(int recon, const void *gauge_d, const Geom &g, cons
   return cudaGetLastError();
 }
 
+// ---- plaquette on the QKXTM gauge layout d[((dir*3+c1)*3+c2)*V + x_lex] (lib/qudaQKXTM_Gauge.cpp:73-89):
+//      QKXTM_Gauge::calculatePlaq (lib/qudaQKXTM_Gauge.cpp:376-386, lib/code_pieces/plaquette_core.h).  Single rank.
+template <typename Q>
+__global__ void __launch_bounds__(128) qk_plaquette_kernel(const CplxT<Q> *__restrict__ gq, Geom g, BlasRed r) {
+  const size_t V = (size_t)2 * g.Vh;
+  const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+  double red[1] = {0.0};
+  if (i < V) {
+    int c[4];
+    c[0] = (int)(i % g.X[0]); c[1] = (int)((i / g.X[0]) % g.X[1]);
+    c[2] = (int)((i / ((size_t)g.X[0] * g.X[1])) % g.X[2]); c[3] = (int)(i / ((size_t)g.X[0] * g.X[1] * g.X[2]));
+    auto lex = [&](const int (&x)[4]) { return (size_t)x[0] + (size_t)g.X[0] * (x[1] + (size_t)g.X[1] * (x[2] + (size_t)g.X[2] * x[3])); };
+    auto ld = [&](double (&u)[3][3][2], int mu, size_t x) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) { CplxT<Q> z = gq[((size_t)mu * 9 + k) * V + x]; u[k / 3][k % 3][0] = (double)z.re; u[k / 3][k % 3][1] = (double)z.im; }
+    };
+    for (int mu = 0; mu < 4; mu++)
+      for (int nu = mu + 1; nu < 4; nu++) {
+        int xm[4] = {c[0], c[1], c[2], c[3]}, xn[4] = {c[0], c[1], c[2], c[3]};
+        xm[mu] = (xm[mu] + 1) % g.X[mu]; xn[nu] = (xn[nu] + 1) % g.X[nu];
+        double A[3][3][2], B[3][3][2], C[3][3][2], D[3][3][2], ab[3][3][2], cd[3][3][2];
+        ld(A, mu, i); ld(B, nu, lex(xm)); ld(C, nu, i); ld(D, mu, lex(xn));
+        mm(ab, A, B); mm(cd, C, D);
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) red[0] += ab[a][b][0] * cd[a][b][0] + ab[a][b][1] * cd[a][b][1];
+      }
+  }
+  block_reduce_finalize<1>(red, r.partials, r.ticket, r.scal, r.slot);
+}
+cudaError_t qkxtm_plaquette(const void *gq, int prec, const Geom &g, const BlasRed &r, cudaStream_t st) {
+  const int grid = (2 * g.Vh + 127) / 128;
+  if (prec == 8) qk_plaquette_kernel<double><<<grid, 128, 0, st>>>((const CplxT<double> *)gq, g, r);
+  else qk_plaquette_kernel<float><<<grid, 128, 0, st>>>((const CplxT<float> *)gq, g, r);
+  return cudaGetLastError();
+}
+
 // ---- QKXTM container kernels on the QKXTM layout ---------------------------------------------------------------
 template <typename Q> __global__ void qk_scale_kernel(CplxT<Q> *d, Q a, size_t n) {
   for (size_t i = (size_t)blockIdx.x * FB + threadIdx.x; i < n; i += (size_t)gridDim.x * FB) {

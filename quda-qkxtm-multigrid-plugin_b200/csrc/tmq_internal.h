@@ -134,6 +134,7 @@ cudaError_t spinor_to_qkxtm(void *qk, int qprec, int prec, const void *even, con
 cudaError_t spinor_from_host_eo(int prec, void *dst, const double *d_aos, int Vh, cudaStream_t st);
 cudaError_t spinor_to_host_eo(double *d_aos, int prec, const void *src, int Vh, cudaStream_t st);
 cudaError_t plaquette_launch(int recon, const void *gauge_d, const Geom &g, const BlasRed &r, cudaStream_t st);
+cudaError_t qkxtm_plaquette(const void *gq, int prec, const Geom &g, const BlasRed &r, cudaStream_t st);
 cudaError_t qkxtm_scale(void *d, int prec, double a, size_t ncplx, cudaStream_t st);
 cudaError_t qkxtm_cast(void *dst, int dprec, const void *src, int sprec, size_t ncplx, cudaStream_t st);
 cudaError_t qkxtm_gamma5(void *d, int prec, int V, cudaStream_t st);

@@ -1,0 +1,152 @@
+// qkxtm_invert_test.cpp -- a small driver in the mould of qkxtm/MG_Bench.cpp / qkxtm/Calc_Loops.cpp main():
+// parse the hot-path flags (the ~15 of SURVEY.md section 5 / Appendix D, same names), fill QudaGaugeParam /
+// QudaInvertParam / qudaQKXTMinfo the way the reference drivers do (qkxtm/Calc_Loops.cpp:189-225,380-497),
+// build a synthetic gauge field, then initQuda -> init_qudaQKXTM -> loadGaugeQuda -> one entry point.
+// Results go to a raw binary file so that the parity tests can check them against the CPU oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../../include/qudaQKXTM_tmq.h"
+#include "../../../include/tmq_host.h"
+
+using namespace quda;
+
+static void usage() {
+  printf("qkxtm_invert_test --dim X Y Z T [--kappa k | --mass m] [--mu mu] [--tol t] [--niter n]\n"
+         "   [--prec-sloppy double|single] [--recon 12|18] [--matpc even-even|odd-odd] [--mass-normalization kappa|mass]\n"
+         "   [--test invert|mgbench|loops|mdagm|mat] [--source z4|gaussian] [--seed s] [--verbosity-level silent|summarize|verbose]\n"
+         "   [--out file] [--dump-inputs prefix]\n");
+}
+
+int main(int argc, char **argv) {
+  int dim[4] = {8, 8, 8, 16};
+  double kappa = -1.0, mass = 0.1, mu = 0.1, tol = 1e-7;      // defaults: qkxtm/QKXTM_util.cpp:1594-1600
+  int niter = 5000, recon = 18;
+  std::string prec_sloppy = "double", matpc = "even-even", test = "invert", source = "z4", out, massnorm = "kappa", verb = "summarize";
+  unsigned long long seed = 100;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto need = [&](int n) { if (i + n >= argc) { usage(); exit(2); } };
+    if (a == "--dim") { need(4); for (int d = 0; d < 4; d++) dim[d] = atoi(argv[++i]); }
+    else if (a == "--kappa") { need(1); kappa = atof(argv[++i]); }
+    else if (a == "--mass") { need(1); mass = atof(argv[++i]); }
+    else if (a == "--mu") { need(1); mu = atof(argv[++i]); }
+    else if (a == "--tol") { need(1); tol = atof(argv[++i]); }
+    else if (a == "--niter") { need(1); niter = atoi(argv[++i]); }
+    else if (a == "--prec-sloppy") { need(1); prec_sloppy = argv[++i]; }
+    else if (a == "--recon") { need(1); recon = atoi(argv[++i]); }
+    else if (a == "--matpc") { need(1); matpc = argv[++i]; }
+    else if (a == "--mass-normalization") { need(1); massnorm = argv[++i]; }
+    else if (a == "--test") { need(1); test = argv[++i]; }
+    else if (a == "--source") { need(1); source = argv[++i]; }
+    else if (a == "--seed") { need(1); seed = strtoull(argv[++i], nullptr, 10); }
+    else if (a == "--verbosity-level") { need(1); verb = argv[++i]; }
+    else if (a == "--out") { need(1); out = argv[++i]; }
+    else if (a == "--help") { usage(); return 0; }
+    else { fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
+  }
+  const long long V = (long long)dim[0] * dim[1] * dim[2] * dim[3];
+  const int grid[4] = {1, 1, 1, 1}, coord[4] = {0, 0, 0, 0};
+
+  // setGaugeParam (qkxtm/Calc_Loops.cpp:189-225)
+  QudaGaugeParam gauge_param = newQudaGaugeParam();
+  for (int d = 0; d < 4; d++) gauge_param.X[d] = dim[d];
+  gauge_param.anisotropy = 1.0;
+  gauge_param.type = QUDA_WILSON_LINKS;
+  gauge_param.gauge_order = QUDA_QDP_GAUGE_ORDER;
+  gauge_param.t_boundary = QUDA_ANTI_PERIODIC_T;
+  gauge_param.cpu_prec = QUDA_DOUBLE_PRECISION;
+  gauge_param.cuda_prec = QUDA_DOUBLE_PRECISION;
+  gauge_param.cuda_prec_sloppy = prec_sloppy == "single" ? QUDA_SINGLE_PRECISION : QUDA_DOUBLE_PRECISION;
+  gauge_param.reconstruct = gauge_param.reconstruct_sloppy = recon == 12 ? QUDA_RECONSTRUCT_12 : QUDA_RECONSTRUCT_NO;
+  gauge_param.gauge_fix = QUDA_GAUGE_FIXED_NO;
+  gauge_param.ga_pad = 0;
+
+  // setInvertParam (qkxtm/Calc_Loops.cpp:380-497)
+  QudaInvertParam inv_param = newQudaInvertParam();
+  inv_param.Ls = 1; inv_param.sp_pad = 0; inv_param.cl_pad = 0;
+  inv_param.kappa = kappa < 0 ? 1.0 / (2.0 * (1 + 3 / gauge_param.anisotropy + mass)) : kappa;   // Calc_Loops.cpp:382-388
+  inv_param.mass = 0.5 / inv_param.kappa - (1 + 3 / gauge_param.anisotropy);
+  inv_param.mu = mu;
+  inv_param.dslash_type = QUDA_TWISTED_MASS_DSLASH;
+  inv_param.twist_flavor = QUDA_TWIST_SINGLET;
+  inv_param.cpu_prec = inv_param.cuda_prec = QUDA_DOUBLE_PRECISION;
+  inv_param.cuda_prec_sloppy = inv_param.cuda_prec_precondition = gauge_param.cuda_prec_sloppy;
+  inv_param.preserve_source = QUDA_PRESERVE_SOURCE_NO;
+  inv_param.gamma_basis = QUDA_UKQCD_GAMMA_BASIS;
+  inv_param.dirac_order = QUDA_DIRAC_ORDER;
+  inv_param.input_location = inv_param.output_location = QUDA_CPU_FIELD_LOCATION;
+  inv_param.solution_type = QUDA_MAT_SOLUTION;
+  inv_param.solve_type = QUDA_NORMOP_PC_SOLVE;
+  inv_param.matpc_type = matpc == "odd-odd" ? QUDA_MATPC_ODD_ODD : QUDA_MATPC_EVEN_EVEN;
+  inv_param.inv_type = QUDA_CG_INVERTER;
+  inv_param.mass_normalization = massnorm == "mass" ? QUDA_MASS_NORMALIZATION : QUDA_KAPPA_NORMALIZATION;
+  inv_param.residual_type = QUDA_L2_RELATIVE_RESIDUAL;
+  inv_param.tol = tol; inv_param.maxiter = niter;
+  inv_param.reliable_delta = prec_sloppy == "single" ? 1e-1 : 1e-4;
+  inv_param.verbosity = verb == "silent" ? QUDA_SILENT : (verb == "verbose" ? QUDA_VERBOSE : QUDA_SUMMARIZE);
+  setVerbosityQuda(inv_param.verbosity);
+
+  qudaQKXTMinfo info;
+  memset(&info, 0, sizeof(info));
+  for (int d = 0; d < 4; d++) info.lL[d] = dim[d];
+  info.isEven = inv_param.matpc_type == QUDA_MATPC_EVEN_EVEN;
+  info.kappa = inv_param.kappa; info.mu = mu; info.inv_tol = tol; info.Precision = QUDA_DOUBLE_PRECISION;
+
+  // synthetic configuration: random SU(3), QDP even-odd order, anti-periodic T folded in
+  std::vector<double> gbuf((size_t)4 * V * 18);
+  double *gauge[4] = {gbuf.data(), gbuf.data() + (size_t)V * 18, gbuf.data() + (size_t)2 * V * 18, gbuf.data() + (size_t)3 * V * 18};
+  tmq_fieldgen_gauge_qdp(gauge, dim, grid, coord, 137, -1);
+
+  initCommsGridQuda(4, grid, nullptr, nullptr);
+  initQuda(0);
+  init_qudaQKXTM(&info);
+  printf_qudaQKXTM();
+  loadGaugeQuda((void *)gauge, &gauge_param);
+
+  std::vector<double> result;
+  if (test == "invert" || test == "mat") {
+    std::vector<double> b((size_t)V * 24), x((size_t)V * 24);
+    if (source == "z4") tmq_fieldgen_spinor_z4(b.data(), dim, grid, coord, seed, 1);
+    else tmq_fieldgen_spinor_gaussian(b.data(), dim, grid, coord, seed, 1);
+    if (test == "invert") invertQuda(x.data(), b.data(), &inv_param);
+    else MatQuda(x.data(), b.data(), &inv_param);
+    result = x;
+  } else if (test == "loops" || test == "mdagm") {
+    std::vector<double> b((size_t)V * 24), x((size_t)V * 24);
+    if (source == "z4") tmq_fieldgen_spinor_z4(b.data(), dim, grid, coord, seed, 0);     // plug-in host order [x_lex][s][c]
+    else tmq_fieldgen_spinor_gaussian(b.data(), dim, grid, coord, seed, 0);
+    if (test == "loops") calc_loops_solve(x.data(), b.data(), &inv_param, info);
+    else ApplyMdagM(x.data(), b.data(), &inv_param, info.isEven);
+    result = x;
+  } else if (test == "mgbench") {
+    // lexicographic copy of the links for the plaquette print (gauge_Plaq in the drivers): unit test uses the
+    // same synthetic field reordered even-odd -> lexicographic
+    std::vector<double> lex((size_t)4 * V * 18);
+    double *glex[4];
+    for (int mu_ = 0; mu_ < 4; mu_++) {
+      glex[mu_] = lex.data() + (size_t)mu_ * V * 18;
+      for (long long i = 0; i < V; i++) {
+        const int x0 = i % dim[0], y = (i / dim[0]) % dim[1], z = (i / ((long long)dim[0] * dim[1])) % dim[2], t = i / ((long long)dim[0] * dim[1] * dim[2]);
+        const long long eo = (long long)((x0 + y + z + t) & 1) * (V / 2) + i / 2;
+        memcpy(glex[mu_] + i * 18, gauge[mu_] + eo * 18, 18 * sizeof(double));
+      }
+    }
+    result.resize((size_t)12 * V * 24);
+    MG_bench((void **)glex, (void **)gauge, &gauge_param, &inv_param, info, result.data());
+  } else { usage(); return 2; }
+
+  printf("RESULT test=%s iter=%d true_res=%.6e secs=%.6f gflops=%.3f kappa=%.17g mu=%.17g\n", test.c_str(), inv_param.iter,
+         inv_param.true_res, inv_param.secs, inv_param.gflops, inv_param.kappa, inv_param.mu);
+  if (!out.empty()) {
+    FILE *f = fopen(out.c_str(), "wb");
+    if (!f) { perror("fopen"); return 1; }
+    fwrite(result.data(), sizeof(double), result.size(), f);
+    fclose(f);
+  }
+  freeGaugeQuda();
+  endQuda();
+  return 0;
+}

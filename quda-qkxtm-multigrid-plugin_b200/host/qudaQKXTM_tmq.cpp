@@ -1,0 +1,512 @@
+// qudaQKXTM_tmq.cpp -- the QKXTM host layer (containers + solve skeletons) over the libtmq.so C ABI.
+// See include/qudaQKXTM_tmq.h for the reference interfaces each piece mirrors.  No arithmetic on lattice
+// fields happens here except the reference's own host-side repacking loops (packVector, packGauge, ...),
+// which the reference also runs on the CPU; everything else is a call into the CUDA library.
+#include "../../include/qudaQKXTM_tmq.h"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
+
+using namespace quda;
+
+// ---- library-global state (the reference's GK_* globals + QUDA's gaugePrecise etc.) ----------------------------------
+namespace {
+struct Globals {
+  int device = -1;
+  bool quda_initialized = false;
+  bool qkxtm_initialized = false;     // GK_init_qudaQKXTM_flag (lib/qudaQKXTM_kernels.cu:120)
+  bool gauge_loaded = false;
+  int grid[4] = {1, 1, 1, 1};
+  int coord[4] = {0, 0, 0, 0};
+  int localL[4] = {0, 0, 0, 0};
+  long long localVolume = 0;
+  tmq_ctx *ctx = nullptr;
+  QudaVerbosity verbosity = QUDA_SUMMARIZE;
+  qkxtm_error_handler on_error = nullptr;
+  double op_kappa = 0, op_mu = 0;
+  int op_matpc = -1;
+} G;
+
+void default_error(const char *msg) {
+  fprintf(stderr, "%s\n", msg);
+  fflush(stderr);
+  std::abort();      // errorQuda aborts the job (SURVEY.md 8b "Errors")
+}
+}  // namespace
+
+#define errorQuda(...)                                                                          \
+  do {                                                                                          \
+    char b__[1024];                                                                             \
+    int n__ = snprintf(b__, sizeof(b__), "ERROR: ");                                            \
+    n__ += snprintf(b__ + n__, sizeof(b__) - n__, __VA_ARGS__);                                 \
+    snprintf(b__ + n__, sizeof(b__) - n__, " (%s:%d in %s())", __FILE__, __LINE__, __func__);   \
+    (G.on_error ? G.on_error : default_error)(b__);                                             \
+  } while (0)
+#define printfQuda(...)                                              \
+  do {                                                               \
+    if (G.verbosity > QUDA_SILENT) { printf(__VA_ARGS__); fflush(stdout); } \
+  } while (0)
+#define TMQ_OK(call)                                                        \
+  do {                                                                      \
+    if ((call) != 0) errorQuda("libtmq: %s", tmq_last_error());             \
+  } while (0)
+
+static void ensure_context(const int X[4]) {
+  if (!G.quda_initialized) errorQuda("initQuda must be called first");
+  if (G.ctx) {
+    for (int d = 0; d < 4; d++)
+      if (G.localL[d] != X[d]) errorQuda("local lattice %d %d %d %d does not match the initialised one", X[0], X[1], X[2], X[3]);
+    return;
+  }
+  for (int d = 0; d < 4; d++) G.localL[d] = X[d];
+  G.localVolume = (long long)X[0] * X[1] * X[2] * X[3];
+  G.ctx = tmq_create(G.device, X, G.grid, G.coord);
+  if (!G.ctx) errorQuda("libtmq: %s", tmq_last_error());
+}
+
+// ---- QUDA C API slice ---------------------------------------------------------------------------------------------------
+QudaGaugeParam newQudaGaugeParam(void) {
+  QudaGaugeParam p;
+  memset(&p, 0, sizeof(p));
+  p.anisotropy = 1.0;
+  p.t_boundary = QUDA_ANTI_PERIODIC_T;
+  p.cpu_prec = p.cuda_prec = QUDA_DOUBLE_PRECISION;
+  p.cuda_prec_sloppy = p.cuda_prec_precondition = QUDA_DOUBLE_PRECISION;
+  p.reconstruct = p.reconstruct_sloppy = p.reconstruct_precondition = QUDA_RECONSTRUCT_NO;
+  return p;
+}
+QudaInvertParam newQudaInvertParam(void) {
+  QudaInvertParam p;
+  memset(&p, 0, sizeof(p));
+  p.kappa = -1.0;
+  p.dslash_type = QUDA_TWISTED_MASS_DSLASH;
+  p.twist_flavor = QUDA_TWIST_SINGLET;
+  p.inv_type = QUDA_INVALID_INVERTER;
+  p.inv_type_precondition = QUDA_INVALID_INVERTER;
+  p.solve_type = QUDA_NORMOP_PC_SOLVE;
+  p.solution_type = QUDA_MAT_SOLUTION;
+  p.gamma_basis = QUDA_UKQCD_GAMMA_BASIS;
+  p.cpu_prec = p.cuda_prec = p.cuda_prec_sloppy = p.cuda_prec_precondition = QUDA_DOUBLE_PRECISION;
+  p.input_location = p.output_location = QUDA_CPU_FIELD_LOCATION;
+  p.Ls = 1;
+  p.tol = 1e-7;
+  p.maxiter = 100;
+  p.reliable_delta = 1e-4;
+  p.residual_type = QUDA_L2_RELATIVE_RESIDUAL;
+  p.verbosity = QUDA_SUMMARIZE;
+  return p;
+}
+
+void setVerbosityQuda(QudaVerbosity v) { G.verbosity = v; }
+
+void initCommsGridQuda(int nDim, const int *dims, void *, void *) {
+  if (nDim != 4) errorQuda("Number of communication grid dimensions must be 4");
+  // single-process host layer: multi-rank runs bootstrap NCCL through tmq_comm_init
+  for (int d = 0; d < 4; d++) {
+    if (dims[d] != 1) errorQuda("this host layer drives one rank; use the C ABI (tmq_create + tmq_comm_init) for a process grid");
+    G.grid[d] = dims[d];
+  }
+}
+
+void initQuda(int device) {
+  if (G.quda_initialized) return;
+  if (tmq_device_count() <= 0) errorQuda("no CUDA device (there is no CPU fallback)");
+  G.device = device < 0 ? 0 : device;
+  G.quda_initialized = true;
+}
+
+void endQuda(void) {
+  if (G.ctx) { tmq_destroy(G.ctx); G.ctx = nullptr; }
+  G.quda_initialized = G.qkxtm_initialized = G.gauge_loaded = false;
+  G.op_matpc = -1;
+}
+
+void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param) {
+  if (!param || !h_gauge) errorQuda("null argument");
+  if (param->gauge_order != QUDA_QDP_GAUGE_ORDER) errorQuda("only QUDA_QDP_GAUGE_ORDER host links are accepted (qkxtm/Calc_Loops.cpp:197)");
+  if (param->cpu_prec != QUDA_DOUBLE_PRECISION) errorQuda("host links must be double precision");
+  if (param->anisotropy != 1.0) errorQuda("anisotropy != 1 is not supported");
+  if (param->type == QUDA_SMEARED_LINKS) {
+    // the 2pt/3pt driver loads smeared links first (qkxtm/CalcMG_2pt3pt_EvenOdd.cpp:675-676); they feed the
+    // smearing containers only, which are not on this path
+    printfQuda("loadGaugeQuda: smeared links are not used by the solver path; ignored\n");
+    return;
+  }
+  ensure_context(param->X);
+  const int recon = (int)param->reconstruct;
+  if (recon != 12 && recon != 18) errorQuda("reconstruct must be 12 or 18");
+  TMQ_OK(tmq_gauge_load(G.ctx, (const void *const *)h_gauge, (int)param->t_boundary, recon));
+  G.gauge_loaded = true;
+}
+void freeGaugeQuda(void) {
+  if (G.ctx) tmq_gauge_free(G.ctx);
+  G.gauge_loaded = false;
+}
+
+// checkInvertParam + the drivers' own guards (lib/qudaQKXTM_interface.cpp:64-67, qkxtm/Calc_Loops.cpp:685-689,774-776)
+static int matpc_of(const QudaInvertParam *p) { return (int)p->matpc_type; }
+static void check_param(const QudaInvertParam *p) {
+  if (!G.gauge_loaded) errorQuda("no gauge field resident (loadGaugeQuda)");
+  if (p->dslash_type != QUDA_TWISTED_MASS_DSLASH) errorQuda("This path supports the twisted-mass operator only");
+  if (p->gamma_basis != QUDA_UKQCD_GAMMA_BASIS) errorQuda("This function works only with ukqcd gamma basis");
+  if (p->dirac_order != QUDA_DIRAC_ORDER) errorQuda("This function works only with colors inside the spins");
+  if (p->cuda_prec != QUDA_DOUBLE_PRECISION) errorQuda("cuda_prec must be double (the QKXTM upload kernel writes double2, lib/qudaQKXTM_kernels.cu:1031)");
+  if (p->sp_pad != 0) errorQuda("sp_pad must be 0 (lib/code_pieces/uploadToCuda_core.h:5)");
+  if (p->kappa <= 0) errorQuda("kappa must be set");
+}
+static void check_solver(const QudaInvertParam *p) {
+  check_param(p);
+  if (p->inv_type != QUDA_CG_INVERTER) errorQuda("This path provides the CG inverter only (inv_type)");
+  if (p->solve_type != QUDA_NORMOP_PC_SOLVE) errorQuda("CG requires a normal-operator pc solve (qkxtm/Calc_Loops.cpp:774-776)");
+  if (p->solution_type != QUDA_MAT_SOLUTION) errorQuda("solution_type must be QUDA_MAT_SOLUTION (qkxtm/Calc_Loops.cpp:439)");
+  if (p->tol <= 0 || p->maxiter <= 0) errorQuda("tol and maxiter must be positive");
+}
+// createDirac: the operator parameters live in the context
+static void create_dirac(const QudaInvertParam *p) {
+  const int m = matpc_of(p);
+  if (G.op_kappa != p->kappa || G.op_mu != p->mu || G.op_matpc != m) {
+    TMQ_OK(tmq_op_set(G.ctx, p->kappa, p->mu, m));
+    G.op_kappa = p->kappa; G.op_mu = p->mu; G.op_matpc = m;
+  }
+}
+
+// the solve of lib/qudaQKXTM_interface.cpp:2020-2041 on device fields: x = M_full^-1 b
+static void solve_device(ColorSpinorField &x, ColorSpinorField &b, QudaInvertParam *param) {
+  create_dirac(param);
+  param->secs = 0; param->gflops = 0; param->iter = 0; param->true_res = 0;       // interface.cpp:95-97
+  param->spinorGiB = (double)G.localVolume * 24 * 8 * 5 / (1024.0 * 1024.0 * 1024.0);
+  ColorSpinorField in(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION), out(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION),
+      tmp(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  const auto t0 = std::chrono::steady_clock::now();
+  TMQ_OK(tmq_prepare(tmp.handle(), b.handle()));                                   // dirac.prepare            (:2020)
+  TMQ_OK(tmq_matpc(in.handle(), tmp.handle(), 1));                                 // in <- M^dag in           (:2034)
+  int iters = 0;
+  double true_res = 0, secs = 0, gflops = 0;
+  TMQ_OK(tmq_cg_mdagm(out.handle(), in.handle(), param->tol, param->maxiter, param->reliable_delta,
+                      (int)param->cuda_prec_sloppy, &iters, &true_res, &secs, &gflops));   // (*solve)(*out,*in) (:2036)
+  TMQ_OK(tmq_reconstruct(x.handle(), out.handle(), b.handle()));                   // dirac.reconstruct        (:2040)
+  TMQ_OK(tmq_sync(G.ctx));
+  param->iter = iters; param->true_res = true_res; param->gflops = gflops;         // updateInvertParam
+  param->secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (G.verbosity >= QUDA_SUMMARIZE)
+    printfQuda("CG: Convergence at %d iterations, L2 relative residual: true = %e (tol %e); %.3f secs, %.1f Gflops\n",
+               iters, true_res, param->tol, param->secs, gflops);
+  if (iters >= param->maxiter && G.verbosity > QUDA_SILENT)
+    fprintf(stderr, "WARNING: Exceeded maximum iterations %d\n", param->maxiter);   // warningQuda continues
+}
+
+void invertQuda(void *h_x, void *h_b, QudaInvertParam *param) {
+  if (!h_x || !h_b || !param) errorQuda("null argument");
+  check_solver(param);
+  ColorSpinorField b(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION), x(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  TMQ_OK(tmq_spinor_from_host(b.handle(), (const double *)h_b));
+  solve_device(x, b, param);
+  TMQ_OK(tmq_spinor_to_host((double *)h_x, x.handle()));
+  if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION) {
+    const double s = 2.0 * param->kappa;
+    double *p = (double *)h_x;
+    for (long long i = 0; i < G.localVolume * 24; i++) p[i] *= s;
+  }
+}
+
+void MatQuda(void *h_out, void *h_in, QudaInvertParam *param) {
+  if (!h_out || !h_in || !param) errorQuda("null argument");
+  check_param(param);
+  create_dirac(param);
+  ColorSpinorField in(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION), out(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  TMQ_OK(tmq_spinor_from_host(in.handle(), (const double *)h_in));
+  TMQ_OK(tmq_mat_full(out.handle(), in.handle(), param->dagger == QUDA_DAG_YES ? 1 : 0));
+  TMQ_OK(tmq_spinor_to_host((double *)h_out, out.handle()));
+}
+
+// ---- quda:: ---------------------------------------------------------------------------------------------------------------
+namespace quda {
+
+tmq_ctx *qkxtm_context() { return G.ctx; }
+void qkxtm_set_error_handler(qkxtm_error_handler h) { G.on_error = h; }
+
+void init_qudaQKXTM(qudaQKXTMinfo *info) {
+  if (G.qkxtm_initialized) return;                       // one-shot (lib/qudaQKXTM_kernels.cu:120,288)
+  if (!info) errorQuda("null info");
+  ensure_context(info->lL);
+  G.qkxtm_initialized = true;
+  printfQuda("qudaQKXTM has been initialized\n");
+}
+
+void printf_qudaQKXTM() {
+  printfQuda("Number of colors is %d\nNumber of spins is %d\nNumber of dimensions is %d\n", 3, 4, 4);
+  printfQuda("Number of process in each direction is (x,y,z,t) %d x %d x %d x %d\n", G.grid[0], G.grid[1], G.grid[2], G.grid[3]);
+  printfQuda("Local lattice is (x,y,z,t) %d x %d x %d x %d\n", G.localL[0], G.localL[1], G.localL[2], G.localL[3]);
+  printfQuda("Local volume is %lld\n", G.localVolume);
+}
+
+ColorSpinorField::ColorSpinorField(QudaSiteSubset subset, QudaPrecision prec) : h_(nullptr), subset_(subset) {
+  if (!G.ctx) errorQuda("no context: call loadGaugeQuda / init_qudaQKXTM first");
+  h_ = tmq_spinor_alloc(G.ctx, (int)prec, subset == QUDA_FULL_SITE_SUBSET ? TMQ_SUBSET_FULL : TMQ_SUBSET_PARITY);
+  if (!h_) errorQuda("libtmq: %s", tmq_last_error());
+}
+ColorSpinorField::~ColorSpinorField() { if (h_ && G.ctx) tmq_spinor_free(h_); }
+tmq_spinor *ColorSpinorField::Even() const { return tmq_spinor_even(h_); }
+tmq_spinor *ColorSpinorField::Odd() const { return tmq_spinor_odd(h_); }
+
+// ---- QKXTM_Field ------------------------------------------------------------------------------------------------------------
+template <typename Float>
+QKXTM_Field<Float>::QKXTM_Field(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT)
+    : h_elem(NULL), h_elem_backup(NULL), d_elem(NULL), isAllocHost(false), isAllocDevice(false), isAllocHostBackup(false) {
+  if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
+  switch (classT) {
+    case FIELD: field_length = 1; total_length = G.localVolume; break;
+    case GAUGE: field_length = 4 * 3 * 3; total_length = G.localVolume; break;
+    case VECTOR: field_length = 4 * 3; total_length = G.localVolume; break;
+    case PROPAGATOR: field_length = 4 * 3 * 4 * 3; total_length = G.localVolume; break;
+    case PROPAGATOR3D: field_length = 4 * 3 * 4 * 3; total_length = G.localVolume / G.localL[3]; break;
+    case VECTOR3D: field_length = 4 * 3; total_length = G.localVolume / G.localL[3]; break;
+  }
+  bytes_total_length = (size_t)total_length * field_length * 2 * sizeof(Float);
+  if (alloc_flag == BOTH) { create_host(); create_device(); }
+  else if (alloc_flag == HOST) create_host();
+  else if (alloc_flag == DEVICE) create_device();
+  else if (alloc_flag == BOTH_EXTRA) { create_host(); create_host_backup(); create_device(); }
+}
+template <typename Float> QKXTM_Field<Float>::~QKXTM_Field() {
+  if (h_elem != NULL) destroy_host();
+  if (h_elem_backup != NULL) destroy_host_backup();
+  if (d_elem != NULL) destroy_device();
+}
+template <typename Float> void QKXTM_Field<Float>::create_host() {
+  h_elem = (Float *)malloc(bytes_total_length);
+  if (h_elem == NULL) errorQuda("Error with allocation host memory");
+  isAllocHost = true;
+  zero_host();
+}
+template <typename Float> void QKXTM_Field<Float>::create_host_backup() {
+  h_elem_backup = (Float *)malloc(bytes_total_length);
+  if (h_elem_backup == NULL) errorQuda("Error with allocation host memory");
+  isAllocHostBackup = true;
+  zero_host_backup();
+}
+template <typename Float> void QKXTM_Field<Float>::create_device() {
+  void *p = nullptr;
+  TMQ_OK(tmq_dev_malloc(G.ctx, &p, bytes_total_length));
+  d_elem = (Float *)p;
+  isAllocDevice = true;
+  zero_device();
+}
+template <typename Float> void QKXTM_Field<Float>::destroy_host() { free(h_elem); h_elem = NULL; }
+template <typename Float> void QKXTM_Field<Float>::destroy_host_backup() { free(h_elem_backup); h_elem_backup = NULL; }   // (the reference nulls h_elem here: App. C quirk, not replicated)
+template <typename Float> void QKXTM_Field<Float>::destroy_device() {
+  if (G.ctx) tmq_dev_free(G.ctx, d_elem);
+  d_elem = NULL;
+}
+template <typename Float> void QKXTM_Field<Float>::zero_host() { memset(h_elem, 0, bytes_total_length); }
+template <typename Float> void QKXTM_Field<Float>::zero_host_backup() { memset(h_elem_backup, 0, bytes_total_length); }
+template <typename Float> void QKXTM_Field<Float>::zero_device() { TMQ_OK(tmq_dev_memset(G.ctx, d_elem, 0, bytes_total_length)); }
+template <typename Float> void QKXTM_Field<Float>::printInfo() {
+  printfQuda("GPU memory needed is %f MB \n", bytes_total_length / (1024.0 * 1024.0));
+}
+
+// ---- QKXTM_Gauge --------------------------------------------------------------------------------------------------------------
+template <typename Float> QKXTM_Gauge<Float>::QKXTM_Gauge(ALLOCATION_FLAG a, CLASS_ENUM c) : QKXTM_Field<Float>(a, c) {}
+
+template <typename Float> static void pack_gauge_into(Float *dst, void **gauge, long long V) {
+  double **pg = (double **)gauge;
+  for (int dir = 0; dir < 4; dir++)
+#pragma omp parallel for
+    for (long long iv = 0; iv < V; iv++)
+      for (int c1 = 0; c1 < 3; c1++)
+        for (int c2 = 0; c2 < 3; c2++)
+          for (int part = 0; part < 2; part++)
+            dst[(((size_t)dir * 3 + c1) * 3 + c2) * V * 2 + iv * 2 + part] = (Float)pg[dir][iv * 18 + c1 * 6 + c2 * 2 + part];
+}
+template <typename Float> void QKXTM_Gauge<Float>::packGauge(void **gauge) { pack_gauge_into(this->h_elem, gauge, this->total_length); }
+template <typename Float> void QKXTM_Gauge<Float>::packGaugeToBackup(void **gauge) {
+  if (this->h_elem_backup == NULL) errorQuda("Error you can call this method only if you allocate memory for h_elem_backup");
+  pack_gauge_into(this->h_elem_backup, gauge, this->total_length);
+}
+template <typename Float> void QKXTM_Gauge<Float>::loadGauge() { TMQ_OK(tmq_h2d(G.ctx, this->d_elem, this->h_elem, this->bytes_total_length)); }
+template <typename Float> void QKXTM_Gauge<Float>::loadGaugeFromBackup() {
+  if (this->h_elem_backup == NULL) errorQuda("Error you can call this method only if you allocate memory for h_elem_backup");
+  TMQ_OK(tmq_h2d(G.ctx, this->d_elem, this->h_elem_backup, this->bytes_total_length));
+}
+template <typename Float> void QKXTM_Gauge<Float>::justDownloadGauge() { TMQ_OK(tmq_d2h(G.ctx, this->h_elem, this->d_elem, this->bytes_total_length)); }
+template <typename Float> double QKXTM_Gauge<Float>::calculatePlaq() {
+  double plaq = 0;
+  TMQ_OK(tmq_qkxtm_plaquette(G.ctx, this->d_elem, (int)sizeof(Float), &plaq));
+  if (sizeof(Float) == 4) printfQuda("Calculated plaquette in single precision is %f\n", plaq);
+  else printfQuda("Calculated plaquette in double precision is %lf\n", plaq);
+  return plaq;
+}
+
+// ---- QKXTM_Vector --------------------------------------------------------------------------------------------------------------
+template <typename Float> QKXTM_Vector<Float>::QKXTM_Vector(ALLOCATION_FLAG a, CLASS_ENUM c) : QKXTM_Field<Float>(a, c) {}
+
+template <typename Float> void QKXTM_Vector<Float>::packVector(Float *vector) {
+  const long long V = this->total_length;
+  Float *h = this->h_elem;
+#pragma omp parallel for
+  for (long long iv = 0; iv < V; iv++)
+    for (int sc = 0; sc < 12; sc++)       // always colours inside spins
+      for (int part = 0; part < 2; part++) h[(size_t)sc * V * 2 + iv * 2 + part] = vector[iv * 24 + sc * 2 + part];
+}
+template <typename Float> void QKXTM_Vector<Float>::unpackVector(Float *vector) {
+  const long long V = this->total_length;
+  Float *h = this->h_elem;
+#pragma omp parallel for
+  for (long long iv = 0; iv < V; iv++)
+    for (int sc = 0; sc < 12; sc++)
+      for (int part = 0; part < 2; part++) h[iv * 24 + sc * 2 + part] = vector[(size_t)sc * V * 2 + iv * 2 + part];
+}
+template <typename Float> void QKXTM_Vector<Float>::unpackVector() {
+  Float *tmp = (Float *)malloc(this->bytes_total_length);
+  if (tmp == NULL) errorQuda("Error in allocate memory of tmp vector in unpackVector");
+  memcpy(tmp, this->h_elem, this->bytes_total_length);
+  unpackVector(tmp);
+  free(tmp);
+}
+template <typename Float> void QKXTM_Vector<Float>::loadVector() { TMQ_OK(tmq_h2d(G.ctx, this->d_elem, this->h_elem, this->bytes_total_length)); }
+template <typename Float> void QKXTM_Vector<Float>::unloadVector() { TMQ_OK(tmq_d2h(G.ctx, this->h_elem, this->d_elem, this->bytes_total_length)); }
+template <typename Float> void QKXTM_Vector<Float>::download() { unloadVector(); unpackVector(); }
+
+template <typename Float> void QKXTM_Vector<Float>::uploadToCuda(ColorSpinorField *cv, bool isEv) {
+  if (!cv) errorQuda("null field");
+  const int parity = cv->SiteSubset() == QUDA_FULL_SITE_SUBSET ? -1 : (isEv ? 0 : 1);
+  TMQ_OK(tmq_spinor_from_qkxtm(cv->handle(), this->d_elem, (int)sizeof(Float), parity));
+}
+template <typename Float> void QKXTM_Vector<Float>::downloadFromCuda(ColorSpinorField *cv, bool isEv) {
+  if (!cv) errorQuda("null field");
+  const int parity = cv->SiteSubset() == QUDA_FULL_SITE_SUBSET ? -1 : (isEv ? 0 : 1);
+  TMQ_OK(tmq_spinor_to_qkxtm(this->d_elem, (int)sizeof(Float), cv->handle(), parity, 1.0));
+}
+template <typename Float> void QKXTM_Vector<Float>::scaleVector(double a) { TMQ_OK(tmq_qkxtm_scale(G.ctx, this->d_elem, (int)sizeof(Float), a)); }
+template <typename Float> void QKXTM_Vector<Float>::castDoubleToFloat(QKXTM_Vector<double> &in) {
+  if (sizeof(Float) != 4) errorQuda("castDoubleToFloat needs a float vector");
+  TMQ_OK(tmq_qkxtm_cast(G.ctx, this->d_elem, 4, in.D_elem(), 8));
+}
+template <typename Float> void QKXTM_Vector<Float>::castFloatToDouble(QKXTM_Vector<float> &in) {
+  if (sizeof(Float) != 8) errorQuda("castFloatToDouble needs a double vector");
+  TMQ_OK(tmq_qkxtm_cast(G.ctx, this->d_elem, 8, in.D_elem(), 4));
+}
+template <typename Float> double QKXTM_Vector<Float>::norm2Host() {
+  double res = 0.0;
+  const long long n = this->total_length * 24;
+  for (long long i = 0; i < n; i++) res += (double)this->h_elem[i] * (double)this->h_elem[i];
+  printfQuda("Vector norm2 is %e\n", res);
+  return res;
+}
+template <typename Float> void QKXTM_Vector<Float>::apply_gamma5() { TMQ_OK(tmq_qkxtm_gamma5(G.ctx, this->d_elem, (int)sizeof(Float))); }
+
+// ---- QKXTM_Propagator ------------------------------------------------------------------------------------------------------------
+template <typename Float> QKXTM_Propagator<Float>::QKXTM_Propagator(ALLOCATION_FLAG a, CLASS_ENUM c) : QKXTM_Field<Float>(a, c) {}
+template <typename Float> void QKXTM_Propagator<Float>::absorbVectorToDevice(QKXTM_Vector<Float> &vec, int nu, int c2) {
+  TMQ_OK(tmq_qkxtm_absorb(G.ctx, this->d_elem, vec.D_elem(), (int)sizeof(Float), nu, c2));
+}
+template <typename Float> void QKXTM_Propagator<Float>::absorbVectorToHost(QKXTM_Vector<Float> &vec, int nu, int c2) {
+  const size_t V = (size_t)this->total_length;
+  for (int mu = 0; mu < 4; mu++)
+    for (int c1 = 0; c1 < 3; c1++)
+      TMQ_OK(tmq_d2h(G.ctx, this->h_elem + (((size_t)mu * 4 + nu) * 9 + c1 * 3 + c2) * V * 2, vec.D_elem() + ((size_t)mu * 3 + c1) * V * 2,
+                     V * 2 * sizeof(Float)));
+}
+
+template class QKXTM_Field<double>;
+template class QKXTM_Field<float>;
+template class QKXTM_Gauge<double>;
+template class QKXTM_Gauge<float>;
+template class QKXTM_Vector<double>;
+template class QKXTM_Vector<float>;
+template class QKXTM_Propagator<double>;
+template class QKXTM_Propagator<float>;
+
+}  // namespace quda
+
+// ---- solve entry points ---------------------------------------------------------------------------------------------------------
+void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, qudaQKXTMinfo info,
+              double *prop_out) {
+  (void)gauge;
+  if (!param || !gauge_param) errorQuda("null argument");
+  check_solver(param);
+  if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
+  if (info.nsmearGauss != 0) errorQuda("Gaussian smearing of the source is outside this path (nsmearGauss must be 0)");
+  const bool flag_eo = info.isEven;     // (the reference leaves this unset; b and x are full fields, so it is moot)
+  const auto T0 = std::chrono::steady_clock::now();
+  const long long V = G.localVolume;
+  double *input_vector = (double *)malloc((size_t)V * 24 * sizeof(double));
+  if (!input_vector) errorQuda("Error allocating memory for the host source");
+  QKXTM_Vector<double> *K_vector = new QKXTM_Vector<double>(BOTH, VECTOR);
+  if (gaugeSmeared) {
+    QKXTM_Gauge<double> *K_gaugeSmeared = new QKXTM_Gauge<double>(BOTH, GAUGE);
+    K_gaugeSmeared->packGauge(gaugeSmeared);
+    K_gaugeSmeared->loadGauge();
+    K_gaugeSmeared->calculatePlaq();
+    delete K_gaugeSmeared;
+  }
+  printfQuda("Memory allocation was successfull\n");
+  ColorSpinorField *b = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  ColorSpinorField *x = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  printfQuda("\n ### Calculations for source-position %d - %02d.%02d.%02d.%02d begin now ###\n\nForward Inversions:\n", 0, 0, 0, 0, 0);
+  for (int isc = 0; isc < 12; isc++) {
+    const auto t4 = std::chrono::steady_clock::now();
+    memset(input_vector, 0, (size_t)V * 24 * sizeof(double));
+    if (param->mu < 0) param->mu *= -1.0;                 // "Ensure mu is positive" (interface.cpp:162-163)
+    input_vector[isc * 2] = 1.0;                          // point source at the origin, spin-colour isc
+    K_vector->packVector(input_vector);
+    K_vector->loadVector();
+    K_vector->uploadToCuda(b, flag_eo);
+    printfQuda(" up - %02d: \n", isc);
+    solve_device(*x, *b, param);
+    K_vector->downloadFromCuda(x, flag_eo);
+    if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION)
+      K_vector->scaleVector(2 * param->kappa);
+    if (prop_out) {
+      K_vector->download();
+      memcpy(prop_out + (size_t)isc * V * 24, K_vector->H_elem(), (size_t)V * 24 * sizeof(double));
+    }
+    printfQuda("Inversion up = %d, for source = %d finished in time %f sec\n", isc, 0,
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - t4).count());
+  }
+  free(input_vector);
+  delete K_vector;
+  delete x;
+  delete b;
+  printfQuda("...Done (%f sec)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
+}
+
+void calc_loops_solve(double *h_solution, double *h_source, QudaInvertParam *param, qudaQKXTMinfo info) {
+  if (!h_solution || !h_source || !param) errorQuda("null argument");
+  check_solver(param);
+  if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
+  const bool flag_eo = info.isEven;
+  QKXTM_Vector<double> *K_vector = new QKXTM_Vector<double>(BOTH, VECTOR);
+  ColorSpinorField b(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION), x(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  K_vector->packVector(h_source);                                      // interface.cpp:2008
+  K_vector->loadVector();                                              // :2009
+  K_vector->uploadToCuda(&b, flag_eo);                                 // :2010
+  solve_device(x, b, param);                                           // :2020-2041
+  K_vector->downloadFromCuda(&x, flag_eo);                             // :2062
+  K_vector->download();                                                // :2063
+  memcpy(h_solution, K_vector->H_elem(), (size_t)G.localVolume * 24 * sizeof(double));
+  delete K_vector;
+}
+
+void ApplyMdagM(double *h_out, double *h_in, QudaInvertParam *param, bool isEven) {
+  if (!h_out || !h_in || !param) errorQuda("null argument");
+  check_param(param);
+  if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
+  const int want = isEven ? 0 : 1;
+  if ((matpc_of(param) & 1) != want) errorQuda("matpc_type does not match the requested parity");
+  create_dirac(param);
+  QKXTM_Vector<double> *Kvec = new QKXTM_Vector<double>(BOTH, VECTOR);
+  ColorSpinorField in(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION), out(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  Kvec->packVector(h_in);
+  Kvec->loadVector();
+  Kvec->uploadToCuda(&in, isEven);
+  TMQ_OK(tmq_mdagm(out.handle(), in.handle()));                        // diracOp->MdagM (Deflation.cpp:265)
+  Kvec->downloadFromCuda(&out, isEven);
+  Kvec->unloadVector();
+  Kvec->unpackVector();
+  memcpy(h_out, Kvec->H_elem(), (size_t)G.localVolume * 24 * sizeof(double));
+  delete Kvec;
+}

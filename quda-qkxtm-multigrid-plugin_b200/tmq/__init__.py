@@ -25,7 +25,7 @@ tmq_spinor_free tmq_spinor_bytes tmq_spinor_from_qkxtm tmq_spinor_to_qkxtm tmq_s
 tmq_spinor_even tmq_spinor_odd tmq_op_set tmq_dslash tmq_dslash_twist_xpay tmq_matpc tmq_mdagm tmq_mat_full
 tmq_prepare tmq_reconstruct tmq_cg_mdagm tmq_cg_history tmq_zero tmq_copy tmq_ax tmq_axpy tmq_axpby tmq_xpay
 tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm tmq_axpy_zpbx tmq_gamma5
-tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
+tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count""".split()
 
 
@@ -82,6 +82,7 @@ def load():
     L.tmq_axpy_norm.argtypes = [C.c_double, vp, vp, dp]; L.tmq_xmy_norm.argtypes = [vp, vp, dp]
     L.tmq_axpy_zpbx.argtypes = [C.c_double, vp, vp, vp, C.c_double]
     L.tmq_gamma5.argtypes = [vp]
+    L.tmq_qkxtm_plaquette.argtypes = [vp, vp, C.c_int, dp]
     L.tmq_qkxtm_scale.argtypes = [vp, vp, C.c_int, C.c_double]
     L.tmq_qkxtm_cast.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.tmq_qkxtm_gamma5.argtypes = [vp, vp, C.c_int]
@@ -263,6 +264,8 @@ class Context:
     def from_qkxtm(self, dst, dptr, qprec=PREC_DOUBLE, parity=-1): _ck(self.L.tmq_spinor_from_qkxtm(dst.h, dptr, qprec, parity))
     def to_qkxtm(self, dptr, src, qprec=PREC_DOUBLE, parity=-1, scale=1.0):
         _ck(self.L.tmq_spinor_to_qkxtm(dptr, qprec, src.h, parity, scale))
+    def qkxtm_plaquette(self, dgauge, prec):
+        o = C.c_double(0); _ck(self.L.tmq_qkxtm_plaquette(self.h, dgauge, prec, C.byref(o))); return o.value
     def qkxtm_scale(self, dptr, prec, a): _ck(self.L.tmq_qkxtm_scale(self.h, dptr, prec, a))
     def qkxtm_cast(self, dst, dprec, src, sprec): _ck(self.L.tmq_qkxtm_cast(self.h, dst, dprec, src, sprec))
     def qkxtm_gamma5(self, dptr, prec): _ck(self.L.tmq_qkxtm_gamma5(self.h, dptr, prec))

@@ -1,0 +1,92 @@
+"""GPU tests of the C++ QKXTM host layer (include/qudaQKXTM_tmq.h, host/qudaQKXTM_tmq.cpp) through the
+qkxtm_invert_test driver: the reference-shaped call sequences (initQuda -> init_qudaQKXTM -> loadGaugeQuda ->
+invertQuda / MG_bench / calc_loops solve / ApplyMdagM) checked against the CPU oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import lattice_util as lu
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRV = os.path.join(ROOT, "quda-qkxtm-multigrid-plugin_b200", "lib", "qkxtm_invert_test")
+X = (4, 6, 4, 8)
+KAPPA = 1.0 / (2.0 * 4.1)
+MU = 0.1
+
+
+def run(tmp_path, *flags):
+    out = str(tmp_path / "out.bin")
+    cmd = [DRV, "--dim"] + [str(x) for x in X] + list(flags) + ["--out", out]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    m = re.search(r"RESULT .*iter=(\d+) true_res=(\S+)", p.stdout)
+    return np.fromfile(out, dtype=np.float64), int(m.group(1)), float(m.group(2)), p.stdout
+
+
+@pytest.fixture(scope="module")
+def env():
+    import tmq
+    from oracle.oracle import Oracle
+    o = Oracle(X)
+    return o, tmq.gen_gauge(X, seed=137, t_boundary=-1), tmq
+
+
+@pytest.mark.parametrize("flags", [[], ["--recon", "12"], ["--prec-sloppy", "single", "--recon", "12"], ["--matpc", "odd-odd"]])
+def test_invertQuda_solves_full_system(tmp_path, env, flags):
+    o, gauge, tmq = env
+    x, it, tr, _ = run(tmp_path, "--test", "invert", "--tol", "1e-10", *flags)
+    b = tmq.gen_spinor(X, "z4", seed=100)
+    assert tr <= 1.05e-10 and it > 5
+    assert lu.rel_l2(o.mat(gauge, x.reshape(b.shape), KAPPA, MU, 0), b) < 1e-8
+
+
+def test_mass_normalization_rescales_by_2kappa(tmp_path, env):
+    o, gauge, tmq = env
+    xk, _, _, _ = run(tmp_path, "--test", "invert", "--tol", "1e-10")
+    xm, _, _, _ = run(tmp_path, "--test", "invert", "--tol", "1e-10", "--mass-normalization", "mass")
+    assert lu.rel_l2(xm, 2 * KAPPA * xk) < 1e-12          # lib/qudaQKXTM_interface.cpp:200-203
+
+
+def test_calc_loops_solve_in_plugin_host_order(tmp_path, env):
+    o, gauge, tmq = env
+    x, it, tr, _ = run(tmp_path, "--test", "loops", "--tol", "1e-9", "--mu", "-0.1", "--recon", "12")   # loops use mu < 0 (Calc_Loops.cpp:424)
+    b_lex = tmq.gen_spinor(X, "z4", seed=100, eo_order=False)
+    x_eo = lu.spinor_eo_from_lex(x.reshape(b_lex.shape), X)
+    assert tr <= 1.05e-9
+    assert lu.rel_l2(o.mat(gauge, x_eo, KAPPA, -MU, 0), lu.spinor_eo_from_lex(b_lex, X)) < 1e-7
+
+
+def test_ApplyMdagM_and_MatQuda(tmp_path, env):
+    o, gauge, tmq = env
+    y, _, _, _ = run(tmp_path, "--test", "mdagm", "--source", "gaussian", "--seed", "101")
+    src = lu.spinor_eo_from_lex(tmq.gen_spinor(X, "gaussian", seed=101, eo_order=False), X)
+    y_eo = lu.spinor_eo_from_lex(y.reshape(src.shape), X)
+    assert lu.rel_l2(y_eo[: o.Vh], o.mdagm(gauge, np.ascontiguousarray(src[: o.Vh]), KAPPA, MU, 0)) < 2e-13
+    assert not y_eo[o.Vh:].any()                            # absent parity zero-filled (downloadFromCuda_core.h)
+    m, _, _, _ = run(tmp_path, "--test", "mat", "--source", "gaussian", "--seed", "101")
+    src_eo = tmq.gen_spinor(X, "gaussian", seed=101)
+    assert lu.rel_l2(m.reshape(src_eo.shape), o.mat(gauge, src_eo, KAPPA, MU, 0)) < 1e-13
+
+
+def test_MG_bench_twelve_columns_and_plaquette(tmp_path, env):
+    o, gauge, tmq = env
+    prop, it, tr, log = run(tmp_path, "--test", "mgbench", "--tol", "1e-9", "--recon", "12")
+    V = o.V
+    prop = prop.reshape(12, V, 4, 3, 2)
+    plaq = float(re.search(r"Calculated plaquette in double precision is (\S+)", log).group(1))
+    assert abs(plaq - o.plaquette(gauge)) < 1e-6            # printed with %lf
+    assert log.count("Inversion up =") == 12
+    for isc in (0, 5, 11):
+        b = np.zeros((V, 4, 3, 2)); b.reshape(V, 12, 2)[0, isc, 0] = 1.0
+        x_eo = lu.spinor_eo_from_lex(prop[isc], X)
+        assert lu.rel_l2(o.mat(gauge, x_eo, KAPPA, MU, 0), lu.spinor_eo_from_lex(b, X)) < 1e-7
+
+
+def test_driver_rejects_unsupported_parameters(tmp_path):
+    p = subprocess.run([DRV, "--dim", "5", "4", "4", "4"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "ERROR" in p.stderr      # errorQuda aborts
