@@ -59,6 +59,8 @@ int tmq_comm_init(tmq_ctx *, const char id128[128], int nranks, int rank);
 int tmq_force_partition(tmq_ctx *, const int part[4]);
 /* tuning knobs (tile of the thread->site map); 0 keeps the default                                        */
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
+enum { TMQ_OPT_PREFETCH = 1 };   /* L2 prefetch of the epilogue operands inside the Dslash kernels (default 0: no measurable gain) */
+int tmq_set_option(tmq_ctx *, int option, int value);
 
 /* ---- gauge: replaces loadGaugeQuda / freeGaugeQuda (qkxtm/Calc_Loops.cpp:759,806) ----------------------
  * qdp_eo_gauge[mu]: host, double, [even Vh | odd Vh] x 3x3 complex row-major (QDP order,

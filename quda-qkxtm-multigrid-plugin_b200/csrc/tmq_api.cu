@@ -148,6 +148,7 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   A.partials = c->partials; A.ticket = c->ticket; A.scal = c->scal;
   A.red_slot = s.red_slot; A.red_accum = 0;
   A.alpha_num = s.alpha_num; A.alpha_den = s.alpha_den;
+  A.prefetch = c->opt_prefetch;
 
   const Geom &g = c->g;
   const bool has_red = (s.epi == EPI_MDAGM2 || s.epi == EPI_CG4);
@@ -336,6 +337,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->Vglobal = V * c->nranks;
   c->multi = g.part[2] || g.part[3];
   c->tile[0] = 4; c->tile[1] = 4; c->tile[2] = 2;
+  c->opt_prefetch = 0;
 
   bool ok = true;
   ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -448,6 +450,15 @@ int tmq_set_tile(tmq_ctx *c, int ty, int tz, int tt) {
   if (tz > 0) c->tile[1] = tz;
   if (tt > 0) c->tile[2] = tt;
   return 0;
+}
+
+int tmq_set_option(tmq_ctx *c, int option, int value) {
+  TMQ_REQUIRE(c, "null context");
+  switch (option) {
+    case TMQ_OPT_PREFETCH: c->opt_prefetch = value ? 1 : 0; return 0;
+  }
+  set_error("unknown option %d", option);
+  return 1;
 }
 
 // ---- gauge ----------------------------------------------------------------------------------------------------------

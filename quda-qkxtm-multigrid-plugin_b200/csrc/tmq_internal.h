@@ -77,6 +77,7 @@ struct tmq_ctx {
   std::set<tmq_spinor *> spinors;
   // timing-kernel scratch (tmq_time_kernel)
   int sms;
+  int opt_prefetch;
 };
 
 namespace tmq {

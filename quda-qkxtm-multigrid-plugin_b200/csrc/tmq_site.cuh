@@ -77,6 +77,16 @@ TMQ_HD CplxT<float> ld_stream(const CplxT<float> *p) {
 #endif
 }
 
+// L2 prefetch of a vector this thread will read in its epilogue (x term, residual): issued before the hop
+// so that the late, dependent loads hit L2 instead of paying a second HBM round trip at low occupancy
+template <typename F> TMQ_HD void prefetch_l2(const VecT<F> *p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // ---- site enumeration -----------------------------------------------------------------------------------
 struct SiteCoord {
   int xh, y, z, t;   // local coordinates (xh = x/2)
@@ -352,6 +362,14 @@ TMQ_HD double dslash_site(const DslashArgs<F> &A, uint32_t e, F alpha) {
   for (int s = 0; s < 4; s++)
 #pragma unroll
     for (int cc = 0; cc < 3; cc++) { o.v[s][cc][0] = 0; o.v[s][cc][1] = 0; }
+  if (T::XTERM && A.prefetch) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) prefetch_l2(A.x + (size_t)j * stride + c.idx);
+  }
+  if (T::RED == 2 && A.prefetch) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) prefetch_l2(A.r + (size_t)j * stride + c.idx);
+  }
 
   // recon-12 boundary sign: the links U_t(T-1) carry the anti-periodic -1 (QKXTM_util.cpp:698-705),
   // so their reconstructed third row needs the same factor (QKXTM_util.cpp:292-294)

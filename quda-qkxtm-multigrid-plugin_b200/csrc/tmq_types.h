@@ -120,6 +120,7 @@ template <typename F> struct DslashArgs {
   int red_slot;            // where the finished sum goes
   int red_accum;           // 1: add to the slot (second and later launches of a split application)
   int alpha_num, alpha_den; // EPI_CG4: alpha = scal[alpha_num] / scal[alpha_den]
+  int prefetch;            // 1: L2-prefetch the epilogue operands (x, r) before the hop
 };
 
 }  // namespace tmq
