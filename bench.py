@@ -238,6 +238,10 @@ def run_native(args):
         ctx.comm_init(bytes(uid.numpy().tobytes()), n, rank)
     if args.tile:
         ctx.set_tile(*args.tile)
+    ctx.set_option(tmq.OPT_HALO_P2P, 1 if args.halo == "p2p" else 0)
+    if args.boundary_at is not None:
+        ctx.set_option(3, args.boundary_at)
+    halo_mode = {0: "none", 1: "nccl send/recv", 2: "peer-memory stores + fused launch"}[ctx.halo_mode()]
     gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1, grid=grid, coord=coord)
     ctx.load_gauge(gauge, t_boundary=-1, recon=recon)
     ctx.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
@@ -334,7 +338,7 @@ def run_native(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64" if prec == 8 else "f32", "data": "synthetic",
                 "config": {"workload": "%dx%dx%dx%d even-odd twisted-mass Dslash in CG on MdagM" % GX,
-                           "local_lattice": list(X), "grid": list(grid), "recon": recon, "kappa": KAPPA, "mu": MU,
+                           "local_lattice": list(X), "grid": list(grid), "halo": halo_mode, "recon": recon, "kappa": KAPPA, "mu": MU,
                            "matpc": "even-even", "step": "1 CG iteration = 4 Dslash launches + 1 fused update launch",
                            "l2_policy": "inputs larger than L2 (parity spinor %.0f MB, gauge %.0f MB per sweep vs 126 MB L2)"
                                         % (Vh_loc * 24 * prec / 1e6, Vh_loc * 8 * recon * prec / 1e6),
@@ -362,6 +366,8 @@ def main():
     ap.add_argument("--prec", type=int, default=8, choices=[8, 4])
     ap.add_argument("--recon", type=int, default=12, choices=[12, 18])
     ap.add_argument("--tile", type=int, nargs=3, default=None)
+    ap.add_argument("--boundary-at", type=int, default=None, help="%% of interior CTAs scheduled before the boundary CTAs")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost exchange: peer-memory stores + fused launch, or ncclSend/Recv")
     ap.add_argument("--tol", type=float, default=1e-9)
     ap.add_argument("--maxiter", type=int, default=5000)
     ap.add_argument("--sloppy-prec", type=int, default=8, choices=[8, 4])

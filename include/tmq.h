@@ -59,8 +59,12 @@ int tmq_comm_init(tmq_ctx *, const char id128[128], int nranks, int rank);
 int tmq_force_partition(tmq_ctx *, const int part[4]);
 /* tuning knobs (tile of the thread->site map); 0 keeps the default                                        */
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
-enum { TMQ_OPT_PREFETCH = 1 };   /* L2 prefetch of the epilogue operands inside the Dslash kernels (default 0: no measurable gain) */
+enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3 };   /* L2 prefetch of the epilogue operands inside the Dslash kernels (default 0: no measurable gain) */
 int tmq_set_option(tmq_ctx *, int option, int value);
+/* TMQ_OPT_HALO_P2P (default 1): ghost faces are stored by the pack kernel straight into the neighbours' ghost buffers
+ * over NVLink peer mappings (CUDA IPC, set up by tmq_comm_init) and the Dslash is ONE launch whose boundary CTAs wait
+ * on arrival flags; 0 selects ncclSend/ncclRecv on a separate stream.  tmq_halo_mode: 0 none, 1 NCCL, 2 peer memory. */
+int tmq_halo_mode(tmq_ctx *);
 
 /* ---- gauge: replaces loadGaugeQuda / freeGaugeQuda (qkxtm/Calc_Loops.cpp:759,806) ----------------------
  * qdp_eo_gauge[mu]: host, double, [even Vh | odd Vh] x 3x3 complex row-major (QDP order,

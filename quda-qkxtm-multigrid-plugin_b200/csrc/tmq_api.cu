@@ -65,6 +65,27 @@ Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_
 
 static inline int pidx(int prec) { return prec == 8 ? 0 : 1; }
 
+HaloArena halo_arena_layout(const Geom &g) {
+  HaloArena L;
+  size_t off = 0;
+  for (int buf = 0; buf < 2; buf++)
+    for (int pi = 0; pi < 2; pi++)
+      for (int d = 0; d < 4; d++)
+        for (int dir = 0; dir < 2; dir++) {
+          L.recv[buf][pi][d][dir] = off;
+          if (d >= 2) off += ((size_t)3 * g.face[d] * vec_bytes(pi == 0 ? 8 : 4) + 255) & ~(size_t)255;
+        }
+  L.flag = off;
+  off += 2 * 4 * 2 * sizeof(unsigned int);
+  off = (off + 255) & ~(size_t)255;
+  L.mbox = off;
+  off += (size_t)2 * 4 * TMQ_MAX_RANKS * sizeof(double);
+  L.mflag = off;
+  off += (size_t)2 * TMQ_MAX_RANKS * sizeof(unsigned int);
+  L.bytes = (off + 255) & ~(size_t)255;
+  return L;
+}
+
 static int ensure_scratch(tmq_ctx *c, int prec, int n) {
   Scratch &s = prec == 8 ? c->scr_d : c->scr_s;
   for (int i = 0; i < n && i < NSCRATCH; i++)
@@ -152,14 +173,66 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
 
   const Geom &g = c->g;
   const bool has_red = (s.epi == EPI_MDAGM2 || s.epi == EPI_CG4);
+  auto nblocks = [](const Enum &en) { return (en.nsites + 127) / 128; };
+  A.nblk[0] = A.nblk[1] = A.nblk[2] = 0;
+  A.npre = 0x7fffffff;
+  A.hw.n = 0; A.hw.seq = 0; A.hw.err = c->scal + SC_ERR;
   if (!c->multi) {
     const int lo[3] = {0, 0, 0}, ext[3] = {g.X[1], g.X[2], g.X[3]};
     A.en = make_enum(g, lo, ext, c->tile);
+    A.nblk[0] = nblocks(A.en);
     TMQ_CUDA(launch_any<F>(c, s.epi, false, A, c->stream));
     c->launches++;
     return 0;
   }
-  // sharded: pack faces -> exchange on the comm stream, overlapped with the interior launch
+  const int zlo = g.part[2] ? 1 : 0, zhi = g.part[2] ? g.X[2] - 1 : g.X[2];   // interior range [lo, hi)
+  const int tlo = g.part[3] ? 1 : 0, thi = g.part[3] ? g.X[3] - 1 : g.X[3];
+  // a box of the (y,z,t) index space; nz / nt enumerated z / t values spaced by sz / st
+  auto box = [&](int z0, int nz, int sz, int t0, int nt, int st) -> Enum {
+    const int lo[3] = {0, z0, t0}, ext[3] = {g.X[1], nz > 0 ? nz : 0, nt > 0 ? nt : 0}, step[3] = {1, sz, st};
+    if (nz <= 0 || nt <= 0) { Enum e; memset(&e, 0, sizeof(e)); e.dXh = e.dTy = e.dTz = e.dTt = e.dNy = e.dNz = make_fastdiv(1); return e; }
+    return make_enum(g, lo, ext, c->tile, step);
+  };
+  const Enum en_int = box(zlo, zhi - zlo, 1, tlo, thi - tlo, 1);                      // no ghost needed
+  const Enum en_t = g.part[3] ? box(0, g.X[2], 1, 0, 2, g.X[3] - 1) : box(0, 0, 1, 0, 0, 1);      // t slices {0, T-1}
+  const Enum en_z = g.part[2] ? box(0, 2, g.X[2] - 1, tlo, thi - tlo, 1) : box(0, 0, 1, 0, 0, 1);  // z slices {0, Z-1}, interior t
+
+  if (c->p2p) {
+    // ---- peer-memory path: faces are stored straight into the neighbours' ghost arenas by ONE pack launch;
+    //      ONE Dslash launch computes interior CTAs first and boundary CTAs last, which wait on arrival flags.
+    const unsigned int seq = ++c->halo_seq;
+    const int buf = (int)(seq & 1u);
+    const HaloArena &L = c->arena_layout;
+    PackDst<F> D;
+    memset(&D, 0, sizeof(D));
+    D.seq = seq; D.ticket = c->ticket2;
+    for (int d = 2; d < 4; d++) {
+      if (!g.part[d]) continue;
+      const int sl = D.nslot++;
+      D.dim[sl] = d;
+      // my slice 0 is the "from forward neighbour" ghost (dir 1) of rank-1; my slice L-1 the dir-0 ghost of rank+1
+      D.dst[sl][0] = (VecT<F> *)(c->peer_arena[d][0] + L.recv[buf][pi][d][1]);
+      D.flag[sl][0] = (unsigned int *)(c->peer_arena[d][0] + arena_flag_off(L, buf, d, 1));
+      D.dst[sl][1] = (VecT<F> *)(c->peer_arena[d][1] + L.recv[buf][pi][d][0]);
+      D.flag[sl][1] = (unsigned int *)(c->peer_arena[d][1] + arena_flag_off(L, buf, d, 0));
+      for (int dir = 0; dir < 2; dir++) {
+        A.ghost[d][dir] = (const VecT<F> *)(c->arena + L.recv[buf][pi][d][dir]);
+        A.hw.flag[A.hw.n++] = (const unsigned int *)(c->arena + arena_flag_off(L, buf, d, dir));
+      }
+    }
+    A.hw.seq = seq;
+    TMQ_CUDA(halo_pack_p2p(c->recon, A, D, c->stream));
+    c->launches++;
+    A.en = en_int; A.en_b[0] = en_t; A.en_b[1] = en_z;
+    A.nblk[0] = nblocks(en_int); A.nblk[1] = nblocks(en_t); A.nblk[2] = nblocks(en_z);
+    A.npre = (int)((long long)A.nblk[0] * c->opt_pre_pct / 100);
+    TMQ_CUDA(launch_any<F>(c, s.epi, true, A, c->stream));
+    c->launches++;
+    if (has_red) TMQ_TRY(comm_allreduce(c, c->scal + s.red_slot, 1, c->stream));
+    return 0;
+  }
+
+  // ---- NCCL path: pack faces -> send/recv on the comm stream, overlapped with the interior launch
   for (int d = 2; d < 4; d++)
     if (g.part[d]) {
       TMQ_CUDA(pack_any<F>(c, A, d, c->halo_send[pi][d][0], c->halo_send[pi][d][1], c->stream));
@@ -169,26 +242,23 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   TMQ_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
   TMQ_TRY(comm_exchange(c, pi, prec, c->comm_stream));
   TMQ_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
-
-  const int zlo = g.part[2] ? 1 : 0, zhi = g.part[2] ? g.X[2] - 1 : g.X[2];   // interior range [lo, hi)
-  const int tlo = g.part[3] ? 1 : 0, thi = g.part[3] ? g.X[3] - 1 : g.X[3];
   bool first = true;
-  // a box of the (y,z,t) index space; nz / nt enumerated z / t values spaced by sz / st
-  auto launch_box = [&](int z0, int nz, int sz, int t0, int nt, int st) -> int {
-    if (nz <= 0 || nt <= 0) return 0;
-    const int lo[3] = {0, z0, t0}, ext[3] = {g.X[1], nz, nt}, step[3] = {1, sz, st};
-    A.en = make_enum(g, lo, ext, c->tile, step);
+  auto launch_seg = [&](const Enum &en, int is_boundary) -> int {
+    if (en.nsites <= 0) return 0;
+    A.en = en;
+    A.all_boundary = is_boundary;
+    A.nblk[0] = nblocks(en);
+    A.npre = A.nblk[0];
     A.red_accum = (has_red && !first) ? 1 : 0;
     TMQ_CUDA(launch_any<F>(c, s.epi, true, A, c->stream));
     c->launches++;
     first = false;
     return 0;
   };
-  TMQ_TRY(launch_box(zlo, zhi - zlo, 1, tlo, thi - tlo, 1));     // interior: no ghost needed
+  TMQ_TRY(launch_seg(en_int, 0));
   TMQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-  // boundary: the two t slices {0, T-1} in one launch, then the two z slices of the interior t range
-  if (g.part[3]) TMQ_TRY(launch_box(0, g.X[2], 1, 0, 2, g.X[3] - 1));
-  if (g.part[2]) TMQ_TRY(launch_box(0, 2, g.X[2] - 1, tlo, thi - tlo, 1));
+  TMQ_TRY(launch_seg(en_t, 1));
+  TMQ_TRY(launch_seg(en_z, 1));
   if (has_red) TMQ_TRY(comm_allreduce(c, c->scal + s.red_slot, 1, c->stream));
   return 0;
 }
@@ -209,6 +279,21 @@ static int fetch_scal(tmq_ctx *c, int slot, int n, double *out) {
   TMQ_CUDA(cudaMemcpyAsync(c->h_scal + slot, c->scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; i++) out[i] = c->h_scal[slot + i];
+  return 0;
+}
+
+// the Dslash kernels raise scal[SC_ERR] when a halo wait timed out (a neighbour never delivered its face)
+static int check_device_error(tmq_ctx *c) {
+  if (!c->multi) return 0;
+  double e = 0;
+  TMQ_TRY(fetch_scal(c, SC_ERR, 1, &e));
+  if (e != 0.0) {
+    const double zero = 0.0;
+    cudaMemcpyAsync(c->scal + SC_ERR, &zero, sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    cudaStreamSynchronize(c->stream);
+    set_error("halo exchange timed out: a neighbour rank did not deliver its ghost face");
+    return 1;
+  }
   return 0;
 }
 
@@ -338,6 +423,9 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->multi = g.part[2] || g.part[3];
   c->tile[0] = 4; c->tile[1] = 4; c->tile[2] = 2;
   c->opt_prefetch = 0;
+  c->opt_pre_pct = 50; c->red_seq = 0; memset(c->rank_arena, 0, sizeof(c->rank_arena));
+  c->opt_p2p = 1; c->p2p = false; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
+  memset(c->peer_arena, 0, sizeof(c->peer_arena));
 
   bool ok = true;
   ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -358,6 +446,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->partials_len = nblk * 4;
   ok = ok && cudaMalloc(&c->partials, c->partials_len * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->ticket, sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->ticket2, sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->scal, SC_COUNT * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMallocHost(&c->h_scal, SC_COUNT * sizeof(double)) == cudaSuccess;
   if (ok) {
@@ -365,6 +454,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
     for (int i = 0; i < SC_COUNT; i++) init[i] = 0.0;
     init[SC_ONE] = 1.0;
     ok = ok && cudaMemset(c->ticket, 0, sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMemset(c->ticket2, 0, sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaMemcpy(c->scal, init, sizeof(init), cudaMemcpyHostToDevice) == cudaSuccess;
   }
   if (!ok) {
@@ -395,6 +485,20 @@ int tmq_force_partition(tmq_ctx *c, const int part[4]) {
         TMQ_CUDA(cudaMalloc(&c->halo_send[pi][d][dir], nbytes));
         TMQ_CUDA(cudaMalloc(&c->halo_recv[pi][d][dir], nbytes));
       }
+  // ghost arena of the peer-memory path; a partitioned dimension on a grid of extent 1 wraps onto this rank, so
+  // its "neighbour" arena is our own.  Remote neighbours are mapped by tmq_comm_init (CUDA IPC).
+  if (c->multi && !c->arena) {
+    c->arena_layout = halo_arena_layout(c->g);
+    TMQ_CUDA(cudaMalloc((void **)&c->arena, c->arena_layout.bytes));
+    TMQ_CUDA(cudaMemset(c->arena, 0, c->arena_layout.bytes));
+  }
+  bool all_mapped = c->multi;
+  for (int d = 2; d < 4; d++) {
+    if (!c->g.part[d]) continue;
+    if (c->grid[d] == 1) c->peer_arena[d][0] = c->peer_arena[d][1] = c->arena;
+    all_mapped = all_mapped && c->peer_arena[d][0] && c->peer_arena[d][1];
+  }
+  c->p2p = c->opt_p2p && all_mapped;
   return 0;
 }
 
@@ -413,6 +517,9 @@ int tmq_destroy(tmq_ctx *c) {
         if (c->halo_send[pi][d][dir]) cudaFree(c->halo_send[pi][d][dir]);
         if (c->halo_recv[pi][d][dir]) cudaFree(c->halo_recv[pi][d][dir]);
       }
+  for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (c->arena) cudaFree(c->arena);
+  if (c->ticket2) cudaFree(c->ticket2);
   if (c->stage) cudaFree(c->stage);
   if (c->partials) cudaFree(c->partials);
   if (c->ticket) cudaFree(c->ticket);
@@ -433,7 +540,7 @@ int tmq_sync(tmq_ctx *c) {
   TMQ_REQUIRE(c, "null context");
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   TMQ_CUDA(cudaStreamSynchronize(c->comm_stream));
-  return 0;
+  return check_device_error(c);
 }
 
 int tmq_comm_unique_id(char id128[128]) { return comm_unique_id(id128); }
@@ -441,8 +548,10 @@ int tmq_comm_init(tmq_ctx *c, const char id128[128], int nranks, int rank) {
   TMQ_REQUIRE(c, "null context");
   TMQ_REQUIRE(nranks == c->nranks && rank == c->rank, "communicator (%d of %d) does not match the process grid (%d of %d)",
               rank, nranks, c->rank, c->nranks);
-  return comm_init(c, id128, nranks, rank);
+  TMQ_TRY(comm_init(c, id128, nranks, rank));
+  return comm_setup_p2p(c);     // map the neighbours' ghost arenas (CUDA IPC); falls back to NCCL send/recv
 }
+int tmq_halo_mode(tmq_ctx *c) { return c ? (c->multi ? (c->p2p ? 2 : 1) : 0) : -1; }
 
 int tmq_set_tile(tmq_ctx *c, int ty, int tz, int tt) {
   TMQ_REQUIRE(c, "null context");
@@ -456,6 +565,16 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
   TMQ_REQUIRE(c, "null context");
   switch (option) {
     case TMQ_OPT_PREFETCH: c->opt_prefetch = value ? 1 : 0; return 0;
+    case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
+    case TMQ_OPT_HALO_P2P: {
+      c->opt_p2p = value ? 1 : 0;
+      bool all_mapped = c->multi;
+      for (int d = 2; d < 4; d++)
+        if (c->g.part[d]) all_mapped = all_mapped && c->peer_arena[d][0] && c->peer_arena[d][1];
+      TMQ_CUDA(cudaStreamSynchronize(c->stream));
+      c->p2p = c->opt_p2p && all_mapped;
+      return 0;
+    }
   }
   set_error("unknown option %d", option);
   return 1;
@@ -840,6 +959,7 @@ int tmq_cg_mdagm(tmq_spinor *x, const tmq_spinor *b, double tol, int maxiter, do
   if (sloppy_prec == 8) TMQ_TRY(cg_double(c, x, b, tol, maxiter, &it, &tr));
   else TMQ_TRY(cg_mixed(c, x, b, tol, maxiter, reliable_delta > 0 ? reliable_delta : 1e-1, &it, &tr));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  TMQ_TRY(check_device_error(c));
   const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (iters) *iters = it;
   if (true_res) *true_res = tr;
@@ -1094,6 +1214,7 @@ int tmq_time_kernel(tmq_ctx *c, int kind, int prec, int reps, const tmq_spinor *
     }
   }
   if (flush) cudaFree(flush);
+  TMQ_TRY(check_device_error(c));
   *ms_per_app = total / reps;
   if (launches) *launches = per;
   return 0;

@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
+#include <vector>
 #include "tmq_internal.h"
 
 namespace tmq {
@@ -18,6 +19,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -33,7 +35,7 @@ static int nccl_load() {
   *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, name);                   \
   if (!g_nccl.field) { set_error("NCCL symbol %s missing", name); return 1; }
   SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-  SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(GroupStart, "ncclGroupStart")
+  SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(GroupStart, "ncclGroupStart")
   SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
   return 0;
@@ -115,9 +117,77 @@ int comm_exchange(tmq_ctx *c, int pi, int prec, cudaStream_t st) {
   return 0;
 }
 
+// Peer-memory halo path: expose this rank's ghost arena to its neighbours with CUDA IPC and map theirs.  The
+// 64-byte handles travel through an ncclAllGather; every rank then opens the arenas of its (at most four)
+// neighbours, and an all-reduce makes the decision unanimous: if any mapping failed anywhere, every rank stays
+// on the ncclSend/ncclRecv path.
+int comm_setup_p2p(tmq_ctx *c) {
+  if (!c->multi || !c->arena || !c->comm) return 0;
+  bool remote = false;
+  for (int d = 2; d < 4; d++) remote = remote || (c->g.part[d] && c->grid[d] > 1);
+  if (!remote) return 0;
+  const int n = c->comm->nranks, me = c->comm->rank;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  int ok = cudaIpcGetMemHandle(&mine, c->arena) == cudaSuccess ? 1 : 0;
+  if (!ok) cudaGetLastError();
+  char *d_all = nullptr;
+  TMQ_CUDA(cudaMalloc((void **)&d_all, (size_t)64 * n));
+  TMQ_CUDA(cudaMemcpyAsync(d_all + (size_t)64 * me, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+  TMQ_NCCL(g_nccl.AllGather(d_all + (size_t)64 * me, d_all, 64, ncclChar, c->comm->comm, c->stream));
+  std::vector<cudaIpcMemHandle_t> all(n);
+  TMQ_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)64 * n, cudaMemcpyDeviceToHost, c->stream));
+  TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  TMQ_CUDA(cudaFree(d_all));
+  // map every rank's arena: neighbours carry the ghost faces, all ranks carry the scalar all-reduce mailboxes
+  if (n > TMQ_MAX_RANKS) ok = 0;
+  for (int r = 0; r < n && ok; r++) {
+    if (r == me) { c->rank_arena[r] = c->arena; continue; }
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    c->rank_arena[r] = (char *)p;
+    c->ipc_opened.push_back(p);
+  }
+  for (int d = 2; d < 4 && ok; d++) {
+    if (!c->g.part[d] || c->grid[d] == 1) continue;
+    for (int dir = 0; dir < 2; dir++) c->peer_arena[d][dir] = c->rank_arena[rank_of(c, d, dir ? +1 : -1)];
+  }
+  // unanimous decision
+  const double bad = ok ? 0.0 : 1.0;
+  TMQ_CUDA(cudaMemcpyAsync(c->scal + SC_T3, &bad, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TMQ_NCCL(g_nccl.AllReduce(c->scal + SC_T3, c->scal + SC_T3, 1, ncclDouble, ncclSum, c->comm->comm, c->stream));
+  double total = 0;
+  TMQ_CUDA(cudaMemcpyAsync(&total, c->scal + SC_T3, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  if (total != 0.0) {
+    for (int d = 2; d < 4; d++)
+      if (c->g.part[d] && c->grid[d] > 1) c->peer_arena[d][0] = c->peer_arena[d][1] = nullptr;
+    c->p2p = false;
+  } else {
+    c->p2p = c->opt_p2p != 0;
+  }
+  return 0;
+}
+
 // in-place sum of n doubles of the device scalar block across ranks
 int comm_allreduce(tmq_ctx *c, double *d_ptr, int n, cudaStream_t st) {
   if (!c->comm || c->comm->nranks == 1) return 0;
+  if (c->p2p && n <= 4) {
+    // peer-memory all-reduce: one 32-thread launch, NVLink stores into every rank's mailbox
+    P2PRed R;
+    memset(&R, 0, sizeof(R));
+    R.scal = c->scal; R.slot = (int)(d_ptr - c->scal); R.n = n;
+    R.rank = c->comm->rank; R.nranks = c->comm->nranks; R.seq = ++c->red_seq;
+    R.err = c->scal + SC_ERR;
+    for (int r = 0; r < R.nranks; r++) {
+      R.mbox[r] = (double *)(c->rank_arena[r] + c->arena_layout.mbox);
+      R.mflag[r] = (unsigned int *)(c->rank_arena[r] + c->arena_layout.mflag);
+    }
+    TMQ_CUDA(p2p_allreduce(R, st));
+    c->launches++;
+    return 0;
+  }
   TMQ_NCCL(g_nccl.AllReduce(d_ptr, d_ptr, (size_t)n, ncclDouble, ncclSum, c->comm->comm, st));
   return 0;
 }

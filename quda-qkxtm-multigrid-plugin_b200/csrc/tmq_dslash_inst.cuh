@@ -15,20 +15,62 @@ namespace tmq {
 template <typename F> struct MinBlocks { static constexpr int v = 3; };
 template <> struct MinBlocks<float> { static constexpr int v = 6; };
 
+// Boundary CTAs of a fused sharded launch: wait until every neighbour has published this application's
+// sequence number (its pack kernel has finished storing the faces into our ghost buffers over NVLink).
+// Bounded: after ~1 s the wait gives up and raises the device error scalar instead of hanging the GPU.
+__device__ __forceinline__ void halo_wait(const HaloWait &hw) {
+  if ((int)threadIdx.x < hw.n) {
+    const unsigned int *f = hw.flag[threadIdx.x];
+    unsigned int v = 0;
+    int spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - hw.seq) >= 0) break;
+      if (++spins > (1 << 23)) { *((volatile double *)hw.err) = 1.0; break; }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+}
+
 template <typename F, int RECON, int EPI, bool MULTI>
 __global__ void __launch_bounds__(TMQ_DSLASH_BLOCK, MinBlocks<F>::v)
 dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
-  const uint32_t e = blockIdx.x * TMQ_DSLASH_BLOCK + threadIdx.x;
+  uint32_t blk = blockIdx.x;
+  const Enum *en = &A.en;
+  bool boundary = MULTI && A.all_boundary;
+  if (MULTI && blk >= (uint32_t)A.npre) {
+    // fused sharded launch: the first npre interior CTAs overlap the halo transfer; the boundary CTAs come next
+    // (they wait on the arrival flags, normally already set) and the remaining interior CTAs keep the SMs busy
+    // behind them, so the cold boundary work never forms the tail of the launch
+    const uint32_t nb = (uint32_t)(A.nblk[1] + A.nblk[2]);
+    if (blk < (uint32_t)A.npre + nb) {
+      blk -= (uint32_t)A.npre;
+      if (blk < (uint32_t)A.nblk[1]) en = &A.en_b[0];
+      else { blk -= (uint32_t)A.nblk[1]; en = &A.en_b[1]; }
+      boundary = true;
+      if (A.hw.n > 0) halo_wait(A.hw);
+    } else {
+      blk -= nb;
+    }
+  }
+  const uint32_t e = blk * TMQ_DSLASH_BLOCK + threadIdx.x;
   F alpha = 0;
   if (EpiTraits<EPI>::RED == 2) alpha = (F)(A.scal[A.alpha_num] / A.scal[A.alpha_den]);
   double red[1] = {0.0};
-  if (e < (uint32_t)A.en.nsites) red[0] = dslash_site<F, RECON, EPI, MULTI>(A, e, alpha);
+  if (e < (uint32_t)en->nsites) {
+    // interior sites never touch a ghost zone: they run the branch-free single-GPU body (the ghost-aware body
+    // costs ~8% because its conditional loads cannot be hoisted); only boundary CTAs pay for it
+    if (MULTI && boundary) red[0] = dslash_site<F, RECON, EPI, true>(A, *en, e, alpha);
+    else                   red[0] = dslash_site<F, RECON, EPI, false>(A, *en, e, alpha);
+  }
   if (EpiTraits<EPI>::RED != 0) block_reduce_finalize<1>(red, A.partials, A.ticket, A.scal, A.red_slot, A.red_accum != 0);
 }
 
 template <typename F, int RECON, int EPI>
 static cudaError_t launch_epi(bool multi, const DslashArgs<F> &A, cudaStream_t st) {
-  const int grid = (A.en.nsites + TMQ_DSLASH_BLOCK - 1) / TMQ_DSLASH_BLOCK;
+  // callers fill nblk[] (segment sizes in CTAs); a plain launch has nblk = {ceil(nsites/128), 0, 0}
+  const int grid = A.nblk[0] + A.nblk[1] + A.nblk[2];
   if (grid == 0) return cudaSuccess;
   if (multi) dslash_kernel<F, RECON, EPI, true><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);
   else       dslash_kernel<F, RECON, EPI, false><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);

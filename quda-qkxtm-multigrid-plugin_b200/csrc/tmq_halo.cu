@@ -37,16 +37,12 @@ template <typename F, int MU> __device__ __forceinline__ void project_any(Half<F
   }
 }
 
-// blockIdx.y = 0: backward-going face (slice 0), 1: forward-going face (slice L-1)
+// one face site: project (and for the forward-going face multiply by U^dag) and store into `dst`
 template <typename F, int RECON, int MU>
-__global__ void __launch_bounds__(128) halo_pack_kernel(const __grid_constant__ DslashArgs<F> A, VecT<F> *send_bwd,
-                                                        VecT<F> *send_fwd) {
+__device__ __forceinline__ void pack_site(const DslashArgs<F> &A, int f, bool fwd, VecT<F> *dst) {
   const Geom &g = A.g;
   const int face = g.face[MU];
-  const int f = blockIdx.x * 128 + threadIdx.x;
-  if (f >= face) return;
   const int q = 1 - A.parity;
-  const bool fwd = blockIdx.y == 1;
   const int slice = fwd ? g.X[MU] - 1 : 0;
   int idx;
   if (MU == 3) idx = slice * face + f;
@@ -60,7 +56,7 @@ __global__ void __launch_bounds__(128) halo_pack_kernel(const __grid_constant__ 
   Half<F> h;
   if (!fwd) {
     project_any<F, MU>(h, p, A.dsign);          // receiver's forward hop: 1 - s g
-    store_half(send_bwd, f, face, h);
+    store_half(dst, f, face, h);
   } else {
     project_any<F, MU>(h, p, -A.dsign);         // receiver's backward hop: 1 + s g
     Link<F> L;
@@ -68,7 +64,46 @@ __global__ void __launch_bounds__(128) halo_pack_kernel(const __grid_constant__ 
     load_link<F, RECON>(L, A.gauge, q, MU, idx, g.Vh, s12);
     Half<F> u;
     su3_apply<F, true>(u, L, h);
-    store_half(send_fwd, f, face, u);
+    store_half(dst, f, face, u);
+  }
+}
+
+// NCCL path: pack into local send buffers.  blockIdx.y = 0: backward-going face (slice 0), 1: forward-going (L-1)
+template <typename F, int RECON, int MU>
+__global__ void __launch_bounds__(128) halo_pack_kernel(const __grid_constant__ DslashArgs<F> A, VecT<F> *send_bwd,
+                                                        VecT<F> *send_fwd) {
+  const int f = blockIdx.x * 128 + threadIdx.x;
+  if (f >= A.g.face[MU]) return;
+  const bool fwd = blockIdx.y == 1;
+  pack_site<F, RECON, MU>(A, f, fwd, fwd ? send_fwd : send_bwd);
+}
+
+// Peer-memory path: ONE launch packs every partitioned dimension and stores the faces straight into the
+// neighbours' ghost buffers through NVLink-mapped pointers (no staging copy, no NCCL kernel); the last CTA to
+// finish publishes the application's sequence number in the neighbours' arrival flags (release, system scope).
+// blockIdx.y = direction, blockIdx.z = partitioned-dimension slot.
+template <typename F, int RECON>
+__global__ void __launch_bounds__(128) halo_pack_p2p_kernel(const __grid_constant__ DslashArgs<F> A,
+                                                            const __grid_constant__ PackDst<F> D) {
+  const int slot = blockIdx.z;
+  const int mu = D.dim[slot];
+  const bool fwd = blockIdx.y == 1;
+  const int f = blockIdx.x * 128 + threadIdx.x;
+  if (f < A.g.face[mu]) {
+    if (mu == 3) pack_site<F, RECON, 3>(A, f, fwd, D.dst[slot][fwd ? 1 : 0]);
+    else         pack_site<F, RECON, 2>(A, f, fwd, D.dst[slot][fwd ? 1 : 0]);
+  }
+  __threadfence_system();            // this thread's peer stores are ordered before the ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int t = atomicInc(D.ticket, total - 1);
+    if (t == total - 1) {
+      __threadfence_system();
+      for (int s = 0; s < D.nslot; s++)
+        for (int d = 0; d < 2; d++)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(D.flag[s][d]), "r"(D.seq) : "memory");
+    }
   }
 }
 
@@ -85,6 +120,51 @@ cudaError_t halo_pack(int prec, int recon, const DslashArgs<double> *Ad, const D
                       void *send_bwd, void *send_fwd, cudaStream_t st) {
   if (prec == 8) return recon == 12 ? pack_t<double, 12>(*Ad, dim, send_bwd, send_fwd, st) : pack_t<double, 18>(*Ad, dim, send_bwd, send_fwd, st);
   return recon == 12 ? pack_t<float, 12>(*As, dim, send_bwd, send_fwd, st) : pack_t<float, 18>(*As, dim, send_bwd, send_fwd, st);
+}
+
+template <typename F> static cudaError_t pack_p2p_t(int recon, const DslashArgs<F> &A, const PackDst<F> &D, cudaStream_t st) {
+  int maxface = 0;
+  for (int s = 0; s < D.nslot; s++) maxface = A.g.face[D.dim[s]] > maxface ? A.g.face[D.dim[s]] : maxface;
+  dim3 grid((maxface + 127) / 128, 2, D.nslot);
+  if (recon == 12) halo_pack_p2p_kernel<F, 12><<<grid, 128, 0, st>>>(A, D);
+  else             halo_pack_p2p_kernel<F, 18><<<grid, 128, 0, st>>>(A, D);
+  return cudaGetLastError();
+}
+cudaError_t halo_pack_p2p(int recon, const DslashArgs<double> &A, const PackDst<double> &D, cudaStream_t st) { return pack_p2p_t<double>(recon, A, D, st); }
+cudaError_t halo_pack_p2p(int recon, const DslashArgs<float> &A, const PackDst<float> &D, cudaStream_t st) { return pack_p2p_t<float>(recon, A, D, st); }
+
+
+// ---- scalar all-reduce over peer memory -------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) p2p_allreduce_kernel(const __grid_constant__ P2PRed R) {
+  const int t = threadIdx.x;
+  const int buf = (int)(R.seq & 1u);
+  if (t < R.nranks) {
+    double *dst = R.mbox[t] + (size_t)buf * 4 * TMQ_MAX_RANKS;
+    for (int j = 0; j < R.n; j++) dst[j * TMQ_MAX_RANKS + R.rank] = R.scal[R.slot + j];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(R.mflag[t] + buf * TMQ_MAX_RANKS + R.rank), "r"(R.seq) : "memory");
+    // wait for rank t's contribution to arrive in our own mailbox
+    const unsigned int *f = R.mflag[R.rank] + buf * TMQ_MAX_RANKS + t;
+    unsigned int v = 0;
+    int spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - R.seq) >= 0) break;
+      if (++spins > (1 << 23)) { *((volatile double *)R.err) = 1.0; break; }
+      __nanosleep(50);
+    }
+  }
+  __syncwarp();
+  if (t < R.n) {
+    const volatile double *src = R.mbox[R.rank] + (size_t)buf * 4 * TMQ_MAX_RANKS + t * TMQ_MAX_RANKS;
+    double s = 0.0;
+    for (int r = 0; r < R.nranks; r++) s += src[r];      // fixed rank order: identical bits on every rank
+    R.scal[R.slot + t] = s;
+  }
+}
+cudaError_t p2p_allreduce(const P2PRed &R, cudaStream_t st) {
+  p2p_allreduce_kernel<<<1, 32, 0, st>>>(R);
+  return cudaGetLastError();
 }
 
 }  // namespace tmq

@@ -24,6 +24,15 @@ namespace tmq {
 
 struct Comm;   // NCCL state (tmq_comm.cpp)
 
+// Ghost-zone arena of the peer-memory halo path: one cudaMalloc per context (so that ONE IPC handle exposes it to
+// the neighbours), identical layout on every rank: recv[buf 0..1][prec 0..1][dim 2..3][dir 0..1] + arrival flags.
+struct HaloArena {
+  size_t recv[2][2][4][2];
+  size_t flag;            // byte offset of unsigned int flags[2 buf][4 dim][2 dir]
+  size_t mbox;            // byte offset of double mailbox[2 buf][4][TMQ_MAX_RANKS] (scalar all-reduce)
+  size_t mflag;           // byte offset of unsigned int mflags[2 buf][TMQ_MAX_RANKS]
+  size_t bytes;
+};
 struct GaugeStore {
   void *d = nullptr;     // [2][4][3 or 9][Vh] in vec / cplx units
   size_t bytes = 0;
@@ -78,6 +87,18 @@ struct tmq_ctx {
   // timing-kernel scratch (tmq_time_kernel)
   int sms;
   int opt_prefetch;
+  // peer-memory halo path
+  int opt_p2p;               // requested (default 1)
+  int opt_pre_pct;           // % of the interior CTAs scheduled before the boundary CTAs in a fused launch
+  bool p2p;                  // active: every neighbour's arena is mapped
+  char *arena;               // own ghost arena (cudaMalloc)
+  tmq::HaloArena arena_layout;
+  char *peer_arena[4][2];    // [dim][0 = rank-1, 1 = rank+1]: base of that neighbour's arena in this address space
+  char *rank_arena[tmq::TMQ_MAX_RANKS];   // every rank's arena (own for rank == self); scalar all-reduce mailboxes
+  unsigned int red_seq;
+  std::vector<void *> ipc_opened;
+  unsigned int halo_seq;
+  unsigned int *ticket2;     // pack-kernel ticket
 };
 
 namespace tmq {
@@ -143,7 +164,15 @@ cudaError_t qkxtm_gamma5(void *d, int prec, int V, cudaStream_t st);
 cudaError_t halo_pack(int prec, int recon, const DslashArgs<double> *Ad, const DslashArgs<float> *As, int dim,
                       void *send_bwd, void *send_fwd, cudaStream_t st);
 
+cudaError_t halo_pack_p2p(int recon, const DslashArgs<double> &A, const PackDst<double> &D, cudaStream_t st);
+cudaError_t halo_pack_p2p(int recon, const DslashArgs<float> &A, const PackDst<float> &D, cudaStream_t st);
+cudaError_t p2p_allreduce(const P2PRed &R, cudaStream_t st);
+
+HaloArena halo_arena_layout(const Geom &g);
+inline size_t arena_flag_off(const HaloArena &L, int buf, int d, int dir) { return L.flag + sizeof(unsigned int) * (size_t)((buf * 4 + d) * 2 + dir); }
+
 // comm layer (tmq_comm.cpp)
+int comm_setup_p2p(tmq_ctx *c);
 int comm_unique_id(char id128[128]);
 int comm_init(tmq_ctx *c, const char id128[128], int nranks, int rank);
 void comm_destroy(tmq_ctx *c);

@@ -208,10 +208,30 @@ template <typename F> TMQ_HD void load_spinor_half(Spinor<F> &p, const VecT<F> *
     if (half) unpack_vec(p, 3 + j, v); else unpack_vec(p, j, v);
   }
 }
+// ghost faces may have been written by a peer GPU during this launch (peer-memory halo path): coherent loads,
+// ordered after the acquire of the arrival flag
+TMQ_HD VecT<double> ld_ghost(const VecT<double> *p) {
+#if defined(__CUDA_ARCH__)
+  VecT<double> r;
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p) : "memory");
+  return r;
+#else
+  return *p;
+#endif
+}
+TMQ_HD VecT<float> ld_ghost(const VecT<float> *p) {
+#if defined(__CUDA_ARCH__)
+  VecT<float> r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.a), "=f"(r.b), "=f"(r.c), "=f"(r.d) : "l"(p) : "memory");
+  return r;
+#else
+  return *p;
+#endif
+}
 template <typename F> TMQ_HD void load_half_ghost(Half<F> &h, const VecT<F> *base, int fidx, int fstride) {
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    VecT<F> v = ld_stream(base + (size_t)j * fstride + fidx);
+    VecT<F> v = ld_ghost(base + (size_t)j * fstride + fidx);
     const int k0 = 2 * j, k1 = 2 * j + 1;
     h.h[k0 / 3][k0 % 3][0] = v.a; h.h[k0 / 3][k0 % 3][1] = v.b;
     h.h[k1 / 3][k1 % 3][0] = v.c; h.h[k1 / 3][k1 % 3][1] = v.d;
@@ -352,10 +372,10 @@ template <int EPI> struct EpiTraits {
 
 // Computes one output site; returns this site's contribution to the fused reduction (0 if none).
 template <typename F, int RECON, int EPI, bool MULTI>
-TMQ_HD double dslash_site(const DslashArgs<F> &A, uint32_t e, F alpha) {
+TMQ_HD double dslash_site(const DslashArgs<F> &A, const Enum &en, uint32_t e, F alpha) {
   typedef EpiTraits<EPI> T;
   const Geom &g = A.g;
-  const SiteCoord c = decode_site(g, A.en, A.parity, e);
+  const SiteCoord c = decode_site(g, en, A.parity, e);
   const int Xh = g.Xh, stride = g.Vh;
   Spinor<F> o;
 #pragma unroll

@@ -84,6 +84,29 @@ struct Enum {
 //   y = cx (x + i ax g5 x) + k t           x term (plain or twisted)
 //   z = c3 (y + i a3 g5 y)                 post twist
 // reductions: RED=1 -> sum |y|^2 ; RED=2 -> r -= alpha z, sum |r|^2 (z not stored)
+// destinations of one fused pack launch: per partitioned-dimension slot, the neighbours' ghost buffers and flags
+template <typename F> struct PackDst {
+  VecT<F> *dst[2][2];            // [slot][0 = backward-going face -> rank-1, 1 = forward-going face -> rank+1]
+  unsigned int *flag[2][2];
+  int dim[2];                    // lattice dimension of each slot (2 = z, 3 = t)
+  int nslot;
+  unsigned int seq;
+  unsigned int *ticket;
+};
+
+// scalar all-reduce over peer memory (one tiny launch): every rank stores its partial into every peer's mailbox,
+// publishes a sequence number, waits for all peers and sums in rank order (bit-identical result on every rank)
+enum { TMQ_MAX_RANKS = 16 };
+struct P2PRed {
+  double *scal;                        // own device scalar block
+  int slot, n;                         // scal[slot .. slot+n) is reduced in place (n <= 4)
+  int rank, nranks;
+  unsigned int seq;
+  double *mbox[TMQ_MAX_RANKS];         // mbox[r]: base of rank r's mailbox [2 buf][4][TMQ_MAX_RANKS] (own for r == rank)
+  unsigned int *mflag[TMQ_MAX_RANKS];  // mflag[r]: rank r's flags [2 buf][TMQ_MAX_RANKS]
+  double *err;
+};
+
 template <typename F> struct Epi {
   F c1, a1, k, cx, ax, c3, a3;
 };
@@ -100,9 +123,23 @@ enum {
   EPI_COUNT = 8
 };
 
+// Arrival flags the boundary CTAs of a fused sharded launch wait on (peer-memory halo path): the neighbour's pack
+// kernel stores the face straight into this rank's ghost buffer over NVLink and then publishes `seq` in the flag.
+struct HaloWait {
+  const unsigned int *flag[4];   // up to 2 partitioned dims x 2 directions
+  int n;                         // 0: no waiting (NCCL path / interior-only launch)
+  unsigned int seq;
+  double *err;                   // device scalar set to 1 if a wait times out (never hang the GPU)
+};
+
 template <typename F> struct DslashArgs {
   Geom g;
-  Enum en;
+  Enum en;                 // segment 0: whole lattice, or the interior of a sharded lattice
+  Enum en_b[2];            // fused sharded launch: boundary segments ({0,T-1} slices, {0,Z-1} slices)
+  int nblk[3];             // CTAs per segment; gridDim.x = nblk[0] + nblk[1] + nblk[2]
+  int npre;                // interior CTAs scheduled BEFORE the boundary CTAs (the rest come after them)
+  int all_boundary;        // 1: every CTA of this launch works on boundary sites (separate-launch NCCL path)
+  HaloWait hw;
   VecT<F> *out;
   const VecT<F> *in;
   const VecT<F> *x;        // x term (may alias nothing else)

@@ -15,12 +15,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtmq.so")
 
 PREC_SINGLE, PREC_DOUBLE = 4, 8
+OPT_PREFETCH, OPT_HALO_P2P = 1, 2
 PARITY, FULL = 1, 2
 MATPC_EVEN_EVEN, MATPC_ODD_ODD, MATPC_EVEN_EVEN_ASYM, MATPC_ODD_ODD_ASYM = 0, 1, 2, 3
 
 # every symbol include/tmq.h declares (checked against the header by tests/test_abi.py)
 SYMBOLS = """tmq_last_error tmq_version tmq_device_count tmq_create tmq_destroy tmq_sync tmq_comm_unique_id
-tmq_comm_init tmq_force_partition tmq_set_tile tmq_set_option tmq_gauge_load tmq_gauge_free tmq_plaquette tmq_spinor_alloc
+tmq_comm_init tmq_force_partition tmq_set_tile tmq_set_option tmq_halo_mode tmq_gauge_load tmq_gauge_free tmq_plaquette tmq_spinor_alloc
 tmq_spinor_free tmq_spinor_bytes tmq_spinor_from_qkxtm tmq_spinor_to_qkxtm tmq_spinor_from_host tmq_spinor_to_host
 tmq_spinor_even tmq_spinor_odd tmq_op_set tmq_dslash tmq_dslash_twist_xpay tmq_matpc tmq_mdagm tmq_mat_full
 tmq_prepare tmq_reconstruct tmq_cg_mdagm tmq_cg_history tmq_zero tmq_copy tmq_ax tmq_axpy tmq_axpby tmq_xpay
@@ -53,6 +54,7 @@ def load():
     L.tmq_force_partition.argtypes = [vp, ip]
     L.tmq_set_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.tmq_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.tmq_halo_mode.argtypes = [vp]
     L.tmq_gauge_load.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int]
     L.tmq_gauge_free.argtypes = [vp]
     L.tmq_plaquette.argtypes = [vp, dp]
@@ -192,6 +194,7 @@ class Context:
     def force_partition(self, part): _ck(self.L.tmq_force_partition(self.h, _i4(part)))
     def set_tile(self, ty, tz, tt): _ck(self.L.tmq_set_tile(self.h, ty, tz, tt))
     def set_option(self, opt, val): _ck(self.L.tmq_set_option(self.h, opt, val))
+    def halo_mode(self): return self.L.tmq_halo_mode(self.h)
     def comm_init(self, uid, nranks, rank): _ck(self.L.tmq_comm_init(self.h, uid, nranks, rank))
     def sync(self): _ck(self.L.tmq_sync(self.h))
 

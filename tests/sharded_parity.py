@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--lattice", type=int, nargs=4, default=[8, 8, 8, 16])
     ap.add_argument("--grid", type=int, nargs=4, default=[1, 1, 1, 2])
     ap.add_argument("--recon", type=int, default=12)
+    ap.add_argument("--p2p", type=int, default=1)
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -39,6 +40,8 @@ def main():
         uid = torch.frombuffer(bytearray(tmq.comm_unique_id()), dtype=torch.uint8).clone()
     dist.broadcast(uid, src=0)
     ctx.comm_init(uid.numpy().tobytes(), world, rank)
+    ctx.set_option(tmq.OPT_HALO_P2P, a.p2p)
+    mode = ctx.halo_mode()
     ctx.load_gauge(tmq.gen_gauge(X, grid=grid, coord=coord), t_boundary=-1, recon=a.recon)
     ctx.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
 
@@ -84,8 +87,8 @@ def main():
     n2 = ctx.norm2(b)
     if abs(n2 - np.sum(even_g * even_g)) > 1e-12 * n2:
         fails.append(("norm2-allreduce", n2))
-    print("rank %d/%d coord %s: cg iters %d (cpu %d) true_res %.2e mixed iters %d; failures: %s"
-          % (rank, world, coord, info["iter"], it_ref, info["true_res"], info4["iter"], fails), flush=True)
+    print("halo_mode %d rank %d/%d coord %s: cg iters %d (cpu %d) true_res %.2e mixed iters %d; failures: %s"
+          % (mode, rank, world, coord, info["iter"], it_ref, info["true_res"], info4["iter"], fails), flush=True)
     t = torch.tensor([len(fails)], dtype=torch.int64)
     dist.all_reduce(t)
     ctx.close()
