@@ -61,9 +61,12 @@ int tmq_force_partition(tmq_ctx *, const int part[4]);
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
 enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3 };   /* L2 prefetch of the epilogue operands inside the Dslash kernels (default 0: no measurable gain) */
 int tmq_set_option(tmq_ctx *, int option, int value);
-/* TMQ_OPT_HALO_P2P (default 1): ghost faces are stored by the pack kernel straight into the neighbours' ghost buffers
- * over NVLink peer mappings (CUDA IPC, set up by tmq_comm_init) and the Dslash is ONE launch whose boundary CTAs wait
- * on arrival flags; 0 selects ncclSend/ncclRecv on a separate stream.  tmq_halo_mode: 0 none, 1 NCCL, 2 peer memory. */
+/* TMQ_OPT_HALO_P2P selects the ghost exchange.  0: ncclSend/ncclRecv on a separate stream + interior / boundary
+ * launches.  1: the pack kernel stores the faces straight into the neighbours' ghost arenas over NVLink peer mappings
+ * (CUDA IPC, set up by tmq_comm_init).  2 (default): faces are packed locally and pushed by the copy engines into the
+ * neighbours' arenas, overlapping the Dslash.  In modes 1 and 2 the Dslash is ONE launch whose boundary CTAs wait on
+ * arrival flags and the CG scalars are all-reduced through peer-memory mailboxes.  tmq_halo_mode returns 0 (not
+ * sharded), 1 (NCCL), 2 (peer stores) or 3 (peer copies); modes 2/3 need every rank's arena to be mappable.       */
 int tmq_halo_mode(tmq_ctx *);
 
 /* ---- gauge: replaces loadGaugeQuda / freeGaugeQuda (qkxtm/Calc_Loops.cpp:759,806) ----------------------

@@ -64,6 +64,7 @@ Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_
 }
 
 static inline int pidx(int prec) { return prec == 8 ? 0 : 1; }
+static const unsigned int SEQ_TABLE = 4096;
 
 HaloArena halo_arena_layout(const Geom &g) {
   HaloArena L;
@@ -196,6 +197,46 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   const Enum en_int = box(zlo, zhi - zlo, 1, tlo, thi - tlo, 1);                      // no ghost needed
   const Enum en_t = g.part[3] ? box(0, g.X[2], 1, 0, 2, g.X[3] - 1) : box(0, 0, 1, 0, 0, 1);      // t slices {0, T-1}
   const Enum en_z = g.part[2] ? box(0, 2, g.X[2] - 1, tlo, thi - tlo, 1) : box(0, 0, 1, 0, 0, 1);  // z slices {0, Z-1}, interior t
+
+  if (c->p2p && c->opt_p2p == 2) {
+    // ---- peer-memory path, copy-engine variant: pack into local send buffers (HBM speed), then the DMA engines
+    //      push faces + arrival flags into the neighbours' ghost arenas over NVLink while ONE Dslash launch runs
+    //      (interior CTAs first; boundary CTAs wait on the flags).  No SM is needed for the transfer, so spinning
+    //      boundary CTAs can never starve it.
+    const unsigned int seq = ++c->halo_seq;
+    const int buf = (int)(seq & 1u);
+    const HaloArena &L = c->arena_layout;
+    TMQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));     // our previous outgoing copies have left the send buffers
+    for (int d = 2; d < 4; d++)
+      if (g.part[d]) {
+        TMQ_CUDA(pack_any<F>(c, A, d, c->halo_send[pi][d][0], c->halo_send[pi][d][1], c->stream));
+        c->launches++;
+      }
+    TMQ_CUDA(cudaEventRecord(c->ev_pack, c->stream));
+    TMQ_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+    for (int d = 2; d < 4; d++) {
+      if (!g.part[d]) continue;
+      const size_t nbytes = (size_t)3 * g.face[d] * vec_bytes(prec);
+      for (int dir = 0; dir < 2; dir++) {
+        // send[dir 0] = slice 0 -> rank-1, where it is the "from forward neighbour" ghost (1); send[1] -> rank+1, ghost 0
+        char *peer = c->peer_arena[d][dir];
+        TMQ_CUDA(cudaMemcpyAsync(peer + L.recv[buf][pi][d][1 - dir], c->halo_send[pi][d][dir], nbytes, cudaMemcpyDeviceToDevice, c->comm_stream));
+        TMQ_CUDA(cudaMemcpyAsync(peer + arena_flag_off(L, buf, d, 1 - dir), c->seq_table + (seq & (SEQ_TABLE - 1)), sizeof(unsigned int),
+                                 cudaMemcpyDeviceToDevice, c->comm_stream));
+        A.ghost[d][dir] = (const VecT<F> *)(c->arena + L.recv[buf][pi][d][dir]);
+        A.hw.flag[A.hw.n++] = (const unsigned int *)(c->arena + arena_flag_off(L, buf, d, dir));
+      }
+    }
+    TMQ_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+    A.hw.seq = seq & (SEQ_TABLE - 1); A.hw.exact = 1;
+    A.en = en_int; A.en_b[0] = en_t; A.en_b[1] = en_z;
+    A.nblk[0] = nblocks(en_int); A.nblk[1] = nblocks(en_t); A.nblk[2] = nblocks(en_z);
+    A.npre = (int)((long long)A.nblk[0] * c->opt_pre_pct / 100);
+    TMQ_CUDA(launch_any<F>(c, s.epi, true, A, c->stream));
+    c->launches++;
+    if (has_red) TMQ_TRY(comm_allreduce(c, c->scal + s.red_slot, 1, c->stream));
+    return 0;
+  }
 
   if (c->p2p) {
     // ---- peer-memory path: faces are stored straight into the neighbours' ghost arenas by ONE pack launch;
@@ -424,7 +465,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->tile[0] = 4; c->tile[1] = 4; c->tile[2] = 2;
   c->opt_prefetch = 0;
   c->opt_pre_pct = 50; c->red_seq = 0; memset(c->rank_arena, 0, sizeof(c->rank_arena));
-  c->opt_p2p = 1; c->p2p = false; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
+  c->opt_p2p = 2; c->p2p = false; c->seq_table = nullptr; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
   memset(c->peer_arena, 0, sizeof(c->peer_arena));
 
   bool ok = true;
@@ -447,6 +488,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   ok = ok && cudaMalloc(&c->partials, c->partials_len * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->ticket, sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->ticket2, sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->seq_table, SEQ_TABLE * sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->scal, SC_COUNT * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMallocHost(&c->h_scal, SC_COUNT * sizeof(double)) == cudaSuccess;
   if (ok) {
@@ -455,6 +497,9 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
     init[SC_ONE] = 1.0;
     ok = ok && cudaMemset(c->ticket, 0, sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaMemset(c->ticket2, 0, sizeof(unsigned int)) == cudaSuccess;
+    std::vector<unsigned int> tab(SEQ_TABLE);
+    for (unsigned int i = 0; i < SEQ_TABLE; i++) tab[i] = i;
+    ok = ok && cudaMemcpy(c->seq_table, tab.data(), SEQ_TABLE * sizeof(unsigned int), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(c->scal, init, sizeof(init), cudaMemcpyHostToDevice) == cudaSuccess;
   }
   if (!ok) {
@@ -520,6 +565,7 @@ int tmq_destroy(tmq_ctx *c) {
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   if (c->arena) cudaFree(c->arena);
   if (c->ticket2) cudaFree(c->ticket2);
+  if (c->seq_table) cudaFree(c->seq_table);
   if (c->stage) cudaFree(c->stage);
   if (c->partials) cudaFree(c->partials);
   if (c->ticket) cudaFree(c->ticket);
@@ -551,7 +597,7 @@ int tmq_comm_init(tmq_ctx *c, const char id128[128], int nranks, int rank) {
   TMQ_TRY(comm_init(c, id128, nranks, rank));
   return comm_setup_p2p(c);     // map the neighbours' ghost arenas (CUDA IPC); falls back to NCCL send/recv
 }
-int tmq_halo_mode(tmq_ctx *c) { return c ? (c->multi ? (c->p2p ? 2 : 1) : 0) : -1; }
+int tmq_halo_mode(tmq_ctx *c) { return c ? (c->multi ? (c->p2p ? 1 + c->opt_p2p : 1) : 0) : -1; }
 
 int tmq_set_tile(tmq_ctx *c, int ty, int tz, int tt) {
   TMQ_REQUIRE(c, "null context");
@@ -567,7 +613,7 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
     case TMQ_OPT_PREFETCH: c->opt_prefetch = value ? 1 : 0; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {
-      c->opt_p2p = value ? 1 : 0;
+      c->opt_p2p = value < 0 ? 0 : (value > 2 ? 2 : value);
       bool all_mapped = c->multi;
       for (int d = 2; d < 4; d++)
         if (c->g.part[d]) all_mapped = all_mapped && c->peer_arena[d][0] && c->peer_arena[d][1];

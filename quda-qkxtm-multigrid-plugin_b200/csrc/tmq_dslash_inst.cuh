@@ -25,7 +25,7 @@ __device__ __forceinline__ void halo_wait(const HaloWait &hw) {
     int spins = 0;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if ((int)(v - hw.seq) >= 0) break;
+      if (hw.exact ? (v == hw.seq) : ((int)(v - hw.seq) >= 0)) break;
       if (++spins > (1 << 23)) { *((volatile double *)hw.err) = 1.0; break; }
       __nanosleep(100);
     }

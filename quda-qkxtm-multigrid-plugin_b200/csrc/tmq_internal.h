@@ -88,7 +88,7 @@ struct tmq_ctx {
   int sms;
   int opt_prefetch;
   // peer-memory halo path
-  int opt_p2p;               // requested (default 1)
+  int opt_p2p;               // requested: 0 NCCL send/recv, 1 peer stores from the pack kernel, 2 copy-engine peer copies
   int opt_pre_pct;           // % of the interior CTAs scheduled before the boundary CTAs in a fused launch
   bool p2p;                  // active: every neighbour's arena is mapped
   char *arena;               // own ghost arena (cudaMalloc)
@@ -99,6 +99,7 @@ struct tmq_ctx {
   std::vector<void *> ipc_opened;
   unsigned int halo_seq;
   unsigned int *ticket2;     // pack-kernel ticket
+  unsigned int *seq_table;   // device table seq_table[i] = i: source of the copy-engine flag writes
 };
 
 namespace tmq {

@@ -129,6 +129,7 @@ struct HaloWait {
   const unsigned int *flag[4];   // up to 2 partitioned dims x 2 directions
   int n;                         // 0: no waiting (NCCL path / interior-only launch)
   unsigned int seq;
+  int exact;                     // 1: wait for flag == seq (copy-engine path, sequence numbers modulo the table size)
   double *err;                   // device scalar set to 1 if a wait times out (never hang the GPU)
 };
 

@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--lattice", type=int, nargs=4, default=[8, 8, 8, 16])
     ap.add_argument("--grid", type=int, nargs=4, default=[1, 1, 1, 2])
     ap.add_argument("--recon", type=int, default=12)
-    ap.add_argument("--p2p", type=int, default=1)
+    ap.add_argument("--p2p", type=int, default=2)
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -205,7 +205,7 @@ def test_mixed_precision_cg_reaches_fp64_residual(tmq, recon):
 @pytest.mark.parametrize("part", [(0, 0, 0, 1), (0, 0, 1, 0), (0, 0, 1, 1)])
 @pytest.mark.parametrize("recon", [12, 18])
 @pytest.mark.parametrize("prec", [8, 4])
-@pytest.mark.parametrize("p2p", [1, 0])
+@pytest.mark.parametrize("p2p", [2, 1, 0])
 def test_ghost_zone_path_equals_periodic_path(tmq, part, recon, prec, p2p):
     """--partition style self-exchange (qkxtm/QKXTM_util.cpp:1717-1720): pack -> exchange -> interior +
     boundary launches must reproduce the single-launch result and the oracle."""
@@ -213,10 +213,11 @@ def test_ghost_zone_path_equals_periodic_path(tmq, part, recon, prec, p2p):
     s = get_setup(tmq, X, recon); o = s.oracle()
     c = tmq.Context(X)
     c.force_partition(part)
-    # p2p = 1: peer-memory halo (faces stored straight into the neighbour's ghost arena, one fused launch whose
-    # boundary CTAs wait on arrival flags); 0: pack -> exchange stream -> interior + boundary launches
+    # p2p = 1 / 2: peer-memory halo (faces stored by the pack kernel / pushed by the copy engines into the neighbour's
+    # ghost arena, one fused launch whose boundary CTAs wait on arrival flags); 0: pack -> exchange stream ->
+    # interior + boundary launches
     c.set_option(tmq.OPT_HALO_P2P, p2p)
-    assert c.halo_mode() == (2 if p2p else 1)
+    assert c.halo_mode() == 1 + p2p
     c.load_gauge(s.gauge, t_boundary=-1, recon=recon)
     c.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
     a, b = c.spinor(prec), c.spinor(prec)
