@@ -6,7 +6,7 @@
 //   include/qudaQKXTM_utils.h:45-75,126-139 (qudaQKXTMinfo, enums, init_qudaQKXTM)
 // and the handful of QUDA C-API calls the drivers make (qkxtm/Calc_Loops.cpp:692-708,753-759,797-806)
 // compiles against this header for that path.  Everything the path does not touch (contractions, smearing,
-// deflation, loops, file I/O, ghost exchange of the containers) is deliberately absent -- see DESIGN.md.
+// loops, file I/O, ghost exchange of the containers) is deliberately absent -- see DESIGN.md.
 //
 // Threading / state: like the reference, one host thread per rank and library-global state (one context,
 // one resident gauge field, one-shot init_qudaQKXTM); not re-entrant.
@@ -191,6 +191,59 @@ public:
   QKXTM_Propagator(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT);
   void absorbVectorToHost(QKXTM_Vector<Float> &vec, int nu, int c2);
   void absorbVectorToDevice(QKXTM_Vector<Float> &vec, int nu, int c2);
+};
+
+// ---- exact deflation (include/qudaQKXTM.h:391-475, include/qudaQKXTM_utils.h:76-94) ------------------------------------
+enum WHICHSPECTRUM { SR, LR, SM, LM, SI, LI };
+typedef struct {
+  int PolyDeg;                 // degree of the Chebyshev polynomial
+  int nEv;                     // number of eigenvectors wanted
+  int nKv;                     // size of the Krylov space
+  WHICHSPECTRUM spectrumPart;  // SR or LR (eigenvalues of M^dag M are real and positive: SM = SR, LM = LR)
+  bool isACC;
+  double tolArpack;
+  int maxIterArpack;
+  char arpack_logfile[512];    // unused (no ARPACK)
+  double amin, amax;
+  bool isEven;
+  bool isFullOp;               // must be false: the even-odd operator is the hot path
+  int modeArpack;              // unused
+} qudaQKXTM_arpackInfo;
+
+// QKXTM_Deflation for the even-odd M^dag M: the Krylov basis and the eigenvectors stay resident in HBM (the reference
+// keeps NkV host vectors and stages every ARPACK reverse-communication step through PCIe).  The eigensolver is a
+// thick-restart Lanczos inside libtmq (tmq_eigensolve); eigenvalues/residuals are recomputed with the true operator as
+// the reference does after zneupd.
+template <typename Float> class QKXTM_Deflation {
+  int PolyDeg, NeV, NkV;
+  WHICHSPECTRUM spectrumPart;
+  bool isACC, isEv, isFullOp;
+  double tolArpack, amin, amax, flavor_sign;
+  int maxIterArpack;
+  long long total_length_per_NeV;
+  size_t bytes_total_length_per_NeV;
+  Float *eigenValues;          // [2 * NkV] (re, im) like the reference
+  double *residuals;
+  tmq_eigset *set;
+  QudaInvertParam *invert_param;
+  int nconv, nrestarts, nmatvec;
+public:
+  QKXTM_Deflation(QudaInvertParam *param, qudaQKXTM_arpackInfo arpackInfo);
+  ~QKXTM_Deflation();
+  Float *EigenValues() const { return eigenValues; }
+  const double *Residuals() const { return residuals; }
+  size_t Bytes_Per_NeV() const { return bytes_total_length_per_NeV; }
+  long long Length_Per_NeV() const { return total_length_per_NeV; }
+  int NeVs() const { return NeV; }
+  int Converged() const { return nconv; }
+  int MatVecs() const { return nmatvec; }
+  void printInfo();
+  void eigenSolver();                                                                  // Deflation.cpp:1069-1475
+  void polynomialOperator(ColorSpinorField &out, const ColorSpinorField &in);         // :997-1063
+  void deflateVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in);     // :614-800 (vec_in: host AoS)
+  void ApplyMdagM(Float *vec_out, Float *vec_in, QudaInvertParam *param);             // :189-281
+  void copyEigenVectorToQKXTM_Vector(int eigenVector_id, Float *vec);                 // :449-536 (full volume, AoS)
+  tmq_eigset *EigenSet() const { return set; }
 };
 
 // accessors for drivers / tests

@@ -142,6 +142,33 @@ int tmq_axpy_zpbx(double a, tmq_spinor *x, tmq_spinor *y, const tmq_spinor *z, d
                                                                                         /* y += a x; x = z + b x */
 int tmq_gamma5(tmq_spinor *x);                                                          /* apply_gamma5_vector */
 
+/* ---- eigensolver on M^dag M: replaces QKXTM_Deflation::{polynomialOperator, eigenSolver, deflateVector}
+ *      (lib/qudaQKXTM_Deflation.cpp:997-1063, 1069-1475, 614-800), where the reference drives ARPACK p?naupd by
+ *      reverse communication with host-staged vectors and deflates with a host zgemv ------------------------------- */
+typedef struct tmq_eigset tmq_eigset;
+/* out = p(M^dag M) in: the Chebyshev filter with the reference's recurrence (delta = (amax-amin)/2, theta = (amax+amin)/2,
+ * sigma_1 = -delta/theta; degree 0 copies).  One degree = 4 fused Dslash launches, the recurrence is their epilogue.  */
+int tmq_poly_mdagm(tmq_spinor *out, const tmq_spinor *in, int deg, double amin, double amax);
+/* a set of PARITY vectors resident in HBM (Krylov basis / eigenvectors), replaces the host h_elem array              */
+tmq_eigset *tmq_eigset_alloc(tmq_ctx *, int nvec, int prec);
+int tmq_eigset_free(tmq_eigset *);              /* before tmq_destroy of its context                                  */
+int tmq_eigset_size(const tmq_eigset *);
+tmq_spinor *tmq_eigset_vector(tmq_eigset *, int i);   /* handle of the i-th vector, owned by the set                  */
+/* nev eigenpairs of M_pc^dag M_pc by thick-restart Lanczos in a Krylov space of nkv vectors (set size >= nkv + 1).
+ * which = 0: smallest (the reference's SR; with poly_deg > 0 the filter turns them into the dominant ones, as the
+ * reference's SR <-> LR swap), 1: largest.  tol as ARPACK's: |beta q_m| <= tol max(eps^(2/3), |theta|).
+ * On return vectors 0..nev-1 of the set hold orthonormal eigenvectors sorted by ascending eigenvalue, evals / resid
+ * (nev each; resid may be NULL) the Rayleigh quotients <v, M^dag M v> and |M^dag M v - lambda v| computed with the true
+ * operator (Deflation.cpp:1426-1439).  Handles obtained from tmq_eigset_vector before the call are stale afterwards.  */
+int tmq_eigensolve(tmq_eigset *set, int nev, int nkv, int poly_deg, double amin, double amax, double tol, int max_restarts,
+                   int which, unsigned long long seed, double *evals, double *resid, int *nconv, int *nrestarts,
+                   int *nmatvec);
+/* out = U Lambda^-1 U^dag in over the first nvec vectors of the set (deflateVector)                                  */
+int tmq_deflate(tmq_spinor *out, const tmq_spinor *in, tmq_eigset *set, const double *evals, int nvec);
+/* out = in - U U^dag in over the first nvec vectors (projectVector, lib/qudaQKXTM_Deflation.cpp:1926-2060); out may
+ * alias in                                                                                                         */
+int tmq_project(tmq_spinor *out, const tmq_spinor *in, tmq_eigset *set, int nvec);
+
 /* ---- QKXTM container kernels on the QKXTM device layout (lib/qudaQKXTM_kernels.cu:1110-1124,1353-1365,
  *      lib/code_pieces/apply_gamma5_vector_core.h, lib/qudaQKXTM_Propagator.cpp:90-106) ------------------- */
 /* plaquette of a gauge field in the QKXTM device layout d[((dir*3+c1)*3+c2)*V + x_lex] (lib/qudaQKXTM_Gauge.cpp:73-89):

@@ -160,3 +160,65 @@ class Oracle:
         return x, it, tr.value, hist[: it + 1]
 
     def num_threads(self): return self.L.orc_num_threads()
+
+
+# ---- eigensolver restatements ----------------------------------------------------------------
+def cheb_coefficients(deg, amin, amax):
+    """The scalar recurrence of QKXTM_Deflation::polynomialOperator (reference lib/qudaQKXTM_Deflation.cpp:1003-1057):
+    returns [(d1, d2, d3)] for steps 1..deg, T_1 = d2 T_0 + d1 A T_0, T_i = d1 A T_{i-1} + d2 T_{i-1} + d3 T_{i-2}."""
+    delta, theta = (amax - amin) / 2.0, (amax + amin) / 2.0
+    sigma1 = -delta / theta
+    out = [(sigma1 / delta, 1.0, 0.0)]
+    sigma_old = sigma1
+    for _ in range(2, deg + 1):
+        sigma = 1.0 / (2.0 / sigma1 - sigma_old)
+        d1 = 2.0 * sigma / delta
+        out.append((d1, -d1 * theta, -sigma * sigma_old))
+        sigma_old = sigma
+    return out[:deg]
+
+
+def poly_operator(apply_A, x, deg, amin, amax):
+    """out = p(A) x with the reference's loop structure (copy; MdagM + axpby; then per degree MdagM, ax, cxpaypbz and
+    two copies -- Deflation.cpp:1013-1057), A given as a callable on numpy arrays."""
+    out = x.copy()
+    if deg == 0:
+        return out
+    coef = cheb_coefficients(deg, amin, amax)
+    d1, d2, _ = coef[0]
+    out = d2 * x + d1 * apply_A(x)
+    if deg == 1:
+        return out
+    tm1, tm2 = x.copy(), out.copy()
+    for (d1, d2, d3) in coef[1:]:
+        out = apply_A(tm2)
+        tm1 = d3 * tm1
+        out = tm1 + d2 * tm2 + d1 * out
+        tm1, tm2 = tm2, out.copy()
+    return out
+
+
+def poly_scalar(lam, deg, amin, amax):
+    """p(lambda): the same recurrence on a number (what the filter does to an eigenvalue)."""
+    return poly_operator(lambda v: lam * v, np.ones(1), deg, amin, amax)[0]
+
+
+def eigs_reference(apply_A, n_complex, nev, ncv, which="SR", poly=None, tol=0.0, v0=None):
+    """ARPACK through scipy (the reference drives the same p?naupd / p?neupd by reverse communication,
+    Deflation.cpp:1296-1372): eigenpairs of the hermitian operator A acting on complex vectors of length n_complex.
+    poly = (deg, amin, amax) iterates p(A) and asks ARPACK for the opposite end, as the reference's isACC branch."""
+    import scipy.sparse.linalg as sla
+    def mv(v):
+        return apply_A(np.ascontiguousarray(v, dtype=np.complex128))
+    if poly is not None:
+        deg, amin, amax = poly
+        op = sla.LinearOperator((n_complex, n_complex), dtype=np.complex128,
+                                matvec=lambda v: poly_operator(mv, np.asarray(v, dtype=np.complex128).ravel(), deg, amin, amax))
+        w, U = sla.eigsh(op, k=nev, ncv=ncv, which={"SR": "LA", "LR": "SA"}[which], tol=tol, v0=v0)
+    else:
+        op = sla.LinearOperator((n_complex, n_complex), dtype=np.complex128, matvec=lambda v: mv(np.asarray(v).ravel()))
+        w, U = sla.eigsh(op, k=nev, ncv=ncv, which={"SR": "SA", "LR": "LA"}[which], tol=tol, v0=v0)
+    # eigenvalues of the actual operator by Rayleigh quotient, as Deflation.cpp:1426-1439
+    lam = np.array([np.vdot(U[:, i], mv(U[:, i])).real for i in range(nev)])
+    o = np.argsort(lam)
+    return lam[o], U[:, o]

@@ -30,16 +30,6 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
-#define TMQ_REQUIRE(cond, ...)                 \
-  do {                                         \
-    if (!(cond)) { tmq::set_error(__VA_ARGS__); return 1; } \
-  } while (0)
-#define TMQ_TRY(expr)            \
-  do {                           \
-    int rc__ = (expr);           \
-    if (rc__) return rc__;       \
-  } while (0)
-
 static int largest_divisor_le(int n, int pref) {
   if (pref < 1) pref = 1;
   for (int d = pref < n ? pref : n; d >= 1; d--)
@@ -87,7 +77,7 @@ HaloArena halo_arena_layout(const Geom &g) {
   return L;
 }
 
-static int ensure_scratch(tmq_ctx *c, int prec, int n) {
+int ensure_scratch(tmq_ctx *c, int prec, int n) {
   Scratch &s = prec == 8 ? c->scr_d : c->scr_s;
   for (int i = 0; i < n && i < NSCRATCH; i++)
     if (!s.tmp[i]) {
@@ -96,7 +86,6 @@ static int ensure_scratch(tmq_ctx *c, int prec, int n) {
     }
   return 0;
 }
-static inline void *scr(tmq_ctx *c, int prec, int i) { return (prec == 8 ? c->scr_d : c->scr_s).tmp[i]; }
 
 static int ensure_stage(tmq_ctx *c, size_t bytes) {
   if (c->stage_bytes >= bytes) return 0;
@@ -105,30 +94,6 @@ static int ensure_stage(tmq_ctx *c, size_t bytes) {
   c->stage_bytes = bytes;
   return 0;
 }
-
-// ---- twist coefficient helpers: out = c (1 + i a g5) in ---------------------------------------------------------
-struct Tw { double c, a; };
-static inline double tw_a(const tmq_ctx *c) { return 2.0 * c->kappa * c->mu; }
-static inline Tw tw_A(const tmq_ctx *c, int dag) { return {1.0, dag ? -tw_a(c) : tw_a(c)}; }
-static inline Tw tw_Ainv(const tmq_ctx *c, int dag) {
-  const double a = tw_a(c);
-  return {1.0 / (1.0 + a * a), dag ? a : -a};
-}
-
-// ---- one Dslash-class application (possibly split into interior + boundary launches) ---------------------------
-struct HopSpec {
-  int epi = EPI_PLAIN;
-  int out_parity = 0;
-  int dagger = 0;
-  Tw t1 = {1, 0};      // post-hop twist
-  Tw tx = {1, 0};      // twist on the x term
-  Tw t3 = {1, 0};      // final twist
-  double k = 0;
-  const void *x = nullptr;
-  void *r = nullptr;
-  int red_slot = SC_T3;
-  int alpha_num = SC_ONE, alpha_den = SC_ONE;
-};
 
 template <typename F> static cudaError_t launch_any(tmq_ctx *c, int epi, bool multi, const DslashArgs<F> &A, cudaStream_t st);
 template <> cudaError_t launch_any<double>(tmq_ctx *c, int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st) {
@@ -158,6 +123,8 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   A.in = (const VecT<F> *)in;
   A.x = (const VecT<F> *)s.x;
   A.r = (VecT<F> *)s.r;
+  A.y = (const VecT<F> *)s.y;
+  A.e.d1 = (F)s.d1; A.e.d2 = (F)s.d2; A.e.d3 = (F)s.d3;
   A.gauge = gs.d;
   A.parity = s.out_parity;
   A.dsign = s.dagger ? (F)-1 : (F)1;
@@ -304,7 +271,7 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   return 0;
 }
 
-static int apply_hop(tmq_ctx *c, int prec, void *out, const void *in, const HopSpec &s) {
+int apply_hop(tmq_ctx *c, int prec, void *out, const void *in, const HopSpec &s) {
   return prec == 8 ? apply_hop_t<double>(c, out, in, s) : apply_hop_t<float>(c, out, in, s);
 }
 
@@ -312,11 +279,11 @@ static inline BlasRed red_at(tmq_ctx *c, int slot) { return BlasRed{c->partials,
 static inline size_t nvec(const tmq_ctx *c) { return (size_t)6 * c->g.Vh; }
 
 // reduction helpers: run the blas reduction, all-reduce across ranks, leave the result on the device
-static int reduce_finish(tmq_ctx *c, int slot, int n) {
+int reduce_finish(tmq_ctx *c, int slot, int n) {
   if (c->multi && c->nranks > 1) TMQ_TRY(comm_allreduce(c, c->scal + slot, n, c->stream));
   return 0;
 }
-static int fetch_scal(tmq_ctx *c, int slot, int n, double *out) {
+int fetch_scal(tmq_ctx *c, int slot, int n, double *out) {
   TMQ_CUDA(cudaMemcpyAsync(c->h_scal + slot, c->scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; i++) out[i] = c->h_scal[slot + i];
@@ -324,7 +291,7 @@ static int fetch_scal(tmq_ctx *c, int slot, int n, double *out) {
 }
 
 // the Dslash kernels raise scal[SC_ERR] when a halo wait timed out (a neighbour never delivered its face)
-static int check_device_error(tmq_ctx *c) {
+int check_device_error(tmq_ctx *c) {
   if (!c->multi) return 0;
   double e = 0;
   TMQ_TRY(fetch_scal(c, SC_ERR, 1, &e));
@@ -340,7 +307,7 @@ static int check_device_error(tmq_ctx *c) {
 
 // ---- operator compositions on raw parity blocks -----------------------------------------------------------------
 // p = parity the preconditioned operator acts on; q = 1 - p
-static int op_matpc(tmq_ctx *c, int prec, void *out, const void *in, int dagger) {
+int op_matpc(tmq_ctx *c, int prec, void *out, const void *in, int dagger) {
   TMQ_TRY(ensure_scratch(c, prec, 2));
   const int p = c->matpc & 1, q = 1 - p;
   const bool asym = c->matpc >= 2;
@@ -370,7 +337,7 @@ static int op_matpc(tmq_ctx *c, int prec, void *out, const void *in, int dagger)
 
 // out = M^dag M in.  Symmetric: the four fused launches K1..K4 (without the CG tail); leaves |M in|^2 in
 // pap_slot.  Asymmetric: two op_matpc calls through scratch 2.
-static int op_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int pap_slot) {
+int op_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int pap_slot) {
   const int p = c->matpc & 1, q = 1 - p;
   const double k2 = -c->kappa * c->kappa;
   if (c->matpc >= 2) {
@@ -554,6 +521,7 @@ int tmq_destroy(tmq_ctx *c) {
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   while (!c->spinors.empty()) tmq_spinor_free(*c->spinors.begin());
   comm_destroy(c);
+  eig_release(c);
   tmq_gauge_free(c);
   for (int i = 0; i < NSCRATCH; i++) { if (c->scr_d.tmp[i]) cudaFree(c->scr_d.tmp[i]); if (c->scr_s.tmp[i]) cudaFree(c->scr_s.tmp[i]); }
   for (int pi = 0; pi < 2; pi++)

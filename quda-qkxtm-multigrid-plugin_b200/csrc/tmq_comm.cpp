@@ -173,7 +173,7 @@ int comm_setup_p2p(tmq_ctx *c) {
 // in-place sum of n doubles of the device scalar block across ranks
 int comm_allreduce(tmq_ctx *c, double *d_ptr, int n, cudaStream_t st) {
   if (!c->comm || c->comm->nranks == 1) return 0;
-  if (c->p2p && n <= 4) {
+  if (c->p2p && n <= 4 && d_ptr >= c->scal && d_ptr + n <= c->scal + SC_COUNT) {
     // peer-memory all-reduce: one 32-thread launch, NVLink stores into every rank's mailbox
     P2PRed R;
     memset(&R, 0, sizeof(R));

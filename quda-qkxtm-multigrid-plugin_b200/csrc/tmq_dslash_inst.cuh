@@ -88,6 +88,7 @@ static cudaError_t launch_dslash_t(int epi, bool multi, const DslashArgs<F> &A, 
     case EPI_MDAGM2:   return launch_epi<F, RECON, EPI_MDAGM2>(multi, A, st);
     case EPI_TWX_XPAY: return launch_epi<F, RECON, EPI_TWX_XPAY>(multi, A, st);
     case EPI_CG4:      return launch_epi<F, RECON, EPI_CG4>(multi, A, st);
+    case EPI_CHEB:     return launch_epi<F, RECON, EPI_CHEB>(multi, A, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -114,10 +114,56 @@ void set_error(const char *fmt, ...);
     }                                                                                          \
   } while (0)
 
+#define TMQ_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) { tmq::set_error(__VA_ARGS__); return 1; } \
+  } while (0)
+#define TMQ_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__) return rc__;       \
+  } while (0)
+
 inline size_t vec_bytes(int prec) { return prec == 8 ? 32 : 16; }
 inline size_t parity_bytes(const tmq_ctx *c, int prec) { return (size_t)6 * c->g.Vh * vec_bytes(prec); }
 
 Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_pref[3], const int step[3] = nullptr);
+
+// ---- one Dslash-class application (tmq_api.cu: possibly split into interior + boundary launches) ----------------
+struct Tw { double c, a; };   // out = c (1 + i a g5) in
+struct HopSpec {
+  int epi = EPI_PLAIN;
+  int out_parity = 0;
+  int dagger = 0;
+  Tw t1 = {1, 0};      // post-hop twist
+  Tw tx = {1, 0};      // twist on the x term
+  Tw t3 = {1, 0};      // final twist
+  double k = 0;
+  const void *x = nullptr;
+  void *r = nullptr;
+  const void *y = nullptr;          // EPI_CHEB
+  double d1 = 0, d2 = 0, d3 = 0;    // EPI_CHEB
+  int red_slot = SC_T3;
+  int alpha_num = SC_ONE, alpha_den = SC_ONE;
+};
+inline double tw_a(const tmq_ctx *c) { return 2.0 * c->kappa * c->mu; }
+inline Tw tw_A(const tmq_ctx *c, int dag) { return {1.0, dag ? -tw_a(c) : tw_a(c)}; }
+inline Tw tw_Ainv(const tmq_ctx *c, int dag) {
+  const double a = tw_a(c);
+  return {1.0 / (1.0 + a * a), dag ? a : -a};
+}
+
+int apply_hop(tmq_ctx *c, int prec, void *out, const void *in, const HopSpec &s);
+int ensure_scratch(tmq_ctx *c, int prec, int n);
+inline void *scr(tmq_ctx *c, int prec, int i) { return (prec == 8 ? c->scr_d : c->scr_s).tmp[i]; }
+int reduce_finish(tmq_ctx *c, int slot, int n);
+int fetch_scal(tmq_ctx *c, int slot, int n, double *out);
+int check_device_error(tmq_ctx *c);
+int op_matpc(tmq_ctx *c, int prec, void *out, const void *in, int dagger);
+int op_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int pap_slot);
+// out = p(M^dag M) in, the Chebyshev filter of the eigensolver (tmq_eig.cu)
+int op_poly_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int deg, double amin, double amax);
+void eig_release(tmq_ctx *c);   // frees the eigensolver workspace of a context
 
 // dslash launchers (one TU per precision x recon)
 cudaError_t launch_dslash_d12(int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st);

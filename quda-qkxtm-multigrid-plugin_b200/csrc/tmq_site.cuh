@@ -365,7 +365,8 @@ template <typename F> TMQ_HD void twist(Spinor<F> &y, const Spinor<F> &x, F c, F
 template <int EPI> struct EpiTraits {
   static constexpr bool TW1 = (EPI == EPI_TW || EPI == EPI_TW_XPAY || EPI == EPI_MDAGM2);
   static constexpr bool XTERM = (EPI >= EPI_TW_XPAY);
-  static constexpr bool TWX = (EPI == EPI_TWX_XPAY || EPI == EPI_CG4);
+  static constexpr bool TWX = (EPI == EPI_TWX_XPAY || EPI == EPI_CG4 || EPI == EPI_CHEB);
+  static constexpr bool CHEB = (EPI == EPI_CHEB);
   static constexpr bool TW3 = (EPI == EPI_XPAY_TW3 || EPI == EPI_MDAGM2);
   static constexpr int RED = (EPI == EPI_MDAGM2) ? 1 : (EPI == EPI_CG4 ? 2 : 0);
 };
@@ -473,6 +474,22 @@ TMQ_HD double dslash_site(const DslashArgs<F> &A, const Enum &en, uint32_t e, F 
       rv.a -= alpha * zv.a; rv.b -= alpha * zv.b; rv.c -= alpha * zv.c; rv.d -= alpha * zv.d;
       red += (double)rv.a * rv.a + (double)rv.b * rv.b + (double)rv.c * rv.c + (double)rv.d * rv.d;
       A.r[(size_t)j * stride + c.idx] = rv;
+    }
+  } else if (T::CHEB) {
+    // three-term recurrence of the Chebyshev-accelerated operator (reference lib/qudaQKXTM_Deflation.cpp:1040-1056):
+    // out = d1 (M^dag M y) + d2 y + d3 r, with z = M^dag M y formed above; out may alias r (site-local)
+    const bool has3 = (A.e.d3 != (F)0);
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      VecT<F> zv = pack_vec(o, j);
+      const VecT<F> yv = A.y[(size_t)j * stride + c.idx];
+      zv.a = A.e.d1 * zv.a + A.e.d2 * yv.a; zv.b = A.e.d1 * zv.b + A.e.d2 * yv.b;
+      zv.c = A.e.d1 * zv.c + A.e.d2 * yv.c; zv.d = A.e.d1 * zv.d + A.e.d2 * yv.d;
+      if (has3) {
+        const VecT<F> rv = A.r[(size_t)j * stride + c.idx];
+        zv.a += A.e.d3 * rv.a; zv.b += A.e.d3 * rv.b; zv.c += A.e.d3 * rv.c; zv.d += A.e.d3 * rv.d;
+      }
+      A.out[(size_t)j * stride + c.idx] = zv;
     }
   } else {
 #pragma unroll

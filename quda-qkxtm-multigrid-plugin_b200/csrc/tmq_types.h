@@ -109,6 +109,7 @@ struct P2PRed {
 
 template <typename F> struct Epi {
   F c1, a1, k, cx, ax, c3, a3;
+  F d1, d2, d3;   // EPI_CHEB: out = d1 z + d2 y + d3 r  (three-term Chebyshev recurrence)
 };
 
 enum {
@@ -120,7 +121,8 @@ enum {
   EPI_MDAGM2 = 5,       // out = c3 (1 + i a3 g5)(x + k t), reduce |x + k t|^2
   EPI_TWX_XPAY = 6,     // out = cx (1 + i ax g5) x + k h
   EPI_CG4 = 7,          // z = cx (1 + i ax g5) x + k h ; r -= alpha z ; reduce |r|^2
-  EPI_COUNT = 8
+  EPI_CHEB = 8,         // z = cx (1 + i ax g5) x + k h ; out = d1 z + d2 y + d3 r   (r read-only, out may alias r)
+  EPI_COUNT = 9
 };
 
 // Arrival flags the boundary CTAs of a fused sharded launch wait on (peer-memory halo path): the neighbour's pack
@@ -144,7 +146,8 @@ template <typename F> struct DslashArgs {
   VecT<F> *out;
   const VecT<F> *in;
   const VecT<F> *x;        // x term (may alias nothing else)
-  VecT<F> *r;              // EPI_CG4: residual updated in place
+  VecT<F> *r;              // EPI_CG4: residual updated in place; EPI_CHEB: T_{n-1} term (read only)
+  const VecT<F> *y;        // EPI_CHEB: T_n term
   const void *gauge;       // base of the [2][4][..][stride] array
   int parity;              // parity of the output sites
   F dsign;                 // +1: D, -1: D^dagger (projector signs)

@@ -26,6 +26,8 @@ int main(int argc, char **argv) {
   int niter = 5000, recon = 18;
   std::string prec_sloppy = "double", matpc = "even-even", test = "invert", source = "z4", out, massnorm = "kappa", verb = "summarize";
   unsigned long long seed = 100;
+  int nev = 4, nkv = 16, polydeg = 20;
+  double amin = 0.385, amax = 2.0, eig_tol = 1e-10;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto need = [&](int n) { if (i + n >= argc) { usage(); exit(2); } };
@@ -44,6 +46,12 @@ int main(int argc, char **argv) {
     else if (a == "--seed") { need(1); seed = strtoull(argv[++i], nullptr, 10); }
     else if (a == "--verbosity-level") { need(1); verb = argv[++i]; }
     else if (a == "--out") { need(1); out = argv[++i]; }
+    else if (a == "--PolyDeg") { need(1); polydeg = atoi(argv[++i]); }        // the reference's ARPACK flags (qkxtm/QKXTM_util.cpp)
+    else if (a == "--nEv") { need(1); nev = atoi(argv[++i]); }
+    else if (a == "--nKv") { need(1); nkv = atoi(argv[++i]); }
+    else if (a == "--amin") { need(1); amin = atof(argv[++i]); }
+    else if (a == "--amax") { need(1); amax = atof(argv[++i]); }
+    else if (a == "--tolArpack") { need(1); eig_tol = atof(argv[++i]); }
     else if (a == "--help") { usage(); return 0; }
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
   }
@@ -80,7 +88,8 @@ int main(int argc, char **argv) {
   inv_param.input_location = inv_param.output_location = QUDA_CPU_FIELD_LOCATION;
   inv_param.solution_type = QUDA_MAT_SOLUTION;
   inv_param.solve_type = QUDA_NORMOP_PC_SOLVE;
-  inv_param.matpc_type = matpc == "odd-odd" ? QUDA_MATPC_ODD_ODD : QUDA_MATPC_EVEN_EVEN;
+  inv_param.matpc_type = matpc == "odd-odd" ? QUDA_MATPC_ODD_ODD : (matpc == "even-even-asym" ? QUDA_MATPC_EVEN_EVEN_ASYMMETRIC
+                         : (matpc == "odd-odd-asym" ? QUDA_MATPC_ODD_ODD_ASYMMETRIC : QUDA_MATPC_EVEN_EVEN));
   inv_param.inv_type = QUDA_CG_INVERTER;
   inv_param.mass_normalization = massnorm == "mass" ? QUDA_MASS_NORMALIZATION : QUDA_KAPPA_NORMALIZATION;
   inv_param.residual_type = QUDA_L2_RELATIVE_RESIDUAL;
@@ -92,7 +101,7 @@ int main(int argc, char **argv) {
   qudaQKXTMinfo info;
   memset(&info, 0, sizeof(info));
   for (int d = 0; d < 4; d++) info.lL[d] = dim[d];
-  info.isEven = inv_param.matpc_type == QUDA_MATPC_EVEN_EVEN;
+  info.isEven = ((int)inv_param.matpc_type & 1) == 0;
   info.kappa = inv_param.kappa; info.mu = mu; info.inv_tol = tol; info.Precision = QUDA_DOUBLE_PRECISION;
 
   // synthetic configuration: random SU(3), QDP even-odd order, anti-periodic T folded in
@@ -121,6 +130,29 @@ int main(int argc, char **argv) {
     if (test == "loops") calc_loops_solve(x.data(), b.data(), &inv_param, info);
     else ApplyMdagM(x.data(), b.data(), &inv_param, info.isEven);
     result = x;
+  } else if (test == "eig") {
+    // calcEigenVectors-style flow (lib/qudaQKXTM_interface.cpp:1378-1395): eigenSolver, then deflate a source with it
+    qudaQKXTM_arpackInfo ai;
+    memset(&ai, 0, sizeof(ai));
+    ai.PolyDeg = polydeg; ai.nEv = nev; ai.nKv = nkv; ai.spectrumPart = SR; ai.isACC = polydeg > 0;
+    ai.tolArpack = eig_tol; ai.maxIterArpack = 1000; ai.amin = amin; ai.amax = amax; ai.isEven = info.isEven; ai.isFullOp = false;
+    QKXTM_Deflation<double> *deflation = new QKXTM_Deflation<double>(&inv_param, ai);
+    deflation->printInfo();
+    deflation->eigenSolver();
+    std::vector<double> b((size_t)V * 24), v0((size_t)V * 24);
+    if (source == "z4") tmq_fieldgen_spinor_z4(b.data(), dim, grid, coord, seed, 0);
+    else tmq_fieldgen_spinor_gaussian(b.data(), dim, grid, coord, seed, 0);
+    QKXTM_Vector<double> K_in(BOTH, VECTOR), K_defl(BOTH, VECTOR);
+    memcpy(K_in.H_elem(), b.data(), b.size() * sizeof(double));          // deflateVector reads the host AoS vector
+    deflation->deflateVector(K_defl, K_in);
+    K_defl.download();
+    deflation->copyEigenVectorToQKXTM_Vector(0, v0.data());
+    for (int i = 0; i < nev; i++) result.push_back(deflation->EigenValues()[2 * i]);
+    for (int i = 0; i < nev; i++) result.push_back(deflation->Residuals()[i]);
+    result.insert(result.end(), v0.begin(), v0.end());
+    result.insert(result.end(), K_defl.H_elem(), K_defl.H_elem() + (size_t)V * 24);
+    inv_param.iter = deflation->MatVecs();
+    delete deflation;
   } else if (test == "mgbench") {
     // lexicographic copy of the links for the plaquette print (gauge_Plaq in the drivers): unit test uses the
     // same synthetic field reordered even-odd -> lexicographic

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <vector>
 
 using namespace quda;
 
@@ -410,6 +411,102 @@ template <typename Float> void QKXTM_Propagator<Float>::absorbVectorToHost(QKXTM
       TMQ_OK(tmq_d2h(G.ctx, this->h_elem + (((size_t)mu * 4 + nu) * 9 + c1 * 3 + c2) * V * 2, vec.D_elem() + ((size_t)mu * 3 + c1) * V * 2,
                      V * 2 * sizeof(Float)));
 }
+
+// ---- QKXTM_Deflation ----------------------------------------------------------------------------------------------------
+template <typename Float>
+QKXTM_Deflation<Float>::QKXTM_Deflation(QudaInvertParam *param, qudaQKXTM_arpackInfo ai)
+    : eigenValues(NULL), residuals(NULL), set(NULL), nconv(0), nrestarts(0), nmatvec(0) {
+  if (!G.qkxtm_initialized) errorQuda("You must initialize QKXTM library first");
+  if (typeid(Float) != typeid(double)) errorQuda("Single precision is not implemented in the eigensolver (Deflation.cpp:1001)");
+  PolyDeg = ai.PolyDeg; NeV = ai.nEv; NkV = ai.nKv; spectrumPart = ai.spectrumPart; isACC = ai.isACC;
+  tolArpack = ai.tolArpack; maxIterArpack = ai.maxIterArpack; amin = ai.amin; amax = ai.amax;
+  isEv = ai.isEven; isFullOp = ai.isFullOp; flavor_sign = param->mu; invert_param = param;
+  total_length_per_NeV = 0; bytes_total_length_per_NeV = 0;
+  if (NeV == 0) { printfQuda("######### Got NeV = 0 #########\n"); return; }
+  if (isFullOp) errorQuda("This path provides the even-odd operator only (isFullOp = false)");
+  if (spectrumPart != SR && spectrumPart != LR && spectrumPart != SM && spectrumPart != LM)
+    errorQuda("eigenSolver: Option for spectrumPart is suspicious");
+  check_param(param);
+  if (((int)param->matpc_type & 1) != (isEv ? 0 : 1)) errorQuda("matpc_type does not match arpackInfo.isEven");
+  invert_param->solve_type = QUDA_NORMOP_PC_SOLVE;                                     // Deflation.cpp:133
+  total_length_per_NeV = (G.localVolume / 2) * 4 * 3 * 2;
+  bytes_total_length_per_NeV = (size_t)total_length_per_NeV * sizeof(Float);
+  eigenValues = (Float *)calloc((size_t)2 * NkV, sizeof(Float));
+  residuals = (double *)calloc((size_t)NkV, sizeof(double));
+  if (!eigenValues || !residuals) errorQuda("Error: Out of memory of eigenValues.");
+  set = tmq_eigset_alloc(G.ctx, NkV + 1, (int)sizeof(Float));
+  if (!set) errorQuda("libtmq: %s", tmq_last_error());
+}
+template <typename Float> QKXTM_Deflation<Float>::~QKXTM_Deflation() {
+  if (set) tmq_eigset_free(set);
+  free(eigenValues);
+  free(residuals);
+}
+template <typename Float> void QKXTM_Deflation<Float>::printInfo() {
+  printfQuda("\n======= DEFLATION INFO =======\n");
+  printfQuda(" Will calculate EigenVectors for the %s %smu operator\n", isEv ? "even-even" : "odd-odd", (flavor_sign > 0) ? "+" : "-");
+  printfQuda(" Number of requested EigenVectors is %d in precision %d\n", NeV, (int)sizeof(Float));
+  printfQuda(" The Size of Krylov space is %d\n", NkV);
+  printfQuda(" Device GB for the Krylov space: %lf\n", (NkV + 1) * ((double)bytes_total_length_per_NeV / (1024. * 1024. * 1024.)));
+  printfQuda("==============================\n");
+}
+template <typename Float> void QKXTM_Deflation<Float>::eigenSolver() {
+  if (NeV == 0) { printfQuda("eigenSolver: Got NeV=%d. Returning...\n", NeV); return; }
+  create_dirac(invert_param);
+  printfQuda("\neigenSolver: Input to the Lanczos solver\n========================================\n");
+  printfQuda(" Number of Ritz eigenvalues requested: %d\n Size of Krylov space is: %d\n", NeV, NkV);
+  printfQuda(" Polynomial acceleration: %s\n", isACC ? "yes" : "no");
+  if (isACC) printfQuda(" Chebyshev polynomial paramaters: Degree = %d, amin = %+e, amax = %+e\n", PolyDeg, amin, amax);
+  printfQuda(" The convergence criterion is %+e\n Maximum number of restarts is %d\n========================================\n\n",
+             tolArpack, maxIterArpack);
+  const int which = (spectrumPart == SR || spectrumPart == SM) ? 0 : 1;
+  std::vector<double> ev(NeV), rs(NeV);
+  const auto t0 = std::chrono::steady_clock::now();
+  TMQ_OK(tmq_eigensolve(set, NeV, NkV, isACC ? PolyDeg : 0, amin, amax, tolArpack, maxIterArpack, which, 1234ull, ev.data(),
+                        rs.data(), &nconv, &nrestarts, &nmatvec));
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  printfQuda("eigenSolver: Number of converged eigenvalues: %d (restarts %d, operator applications %d)\n", nconv, nrestarts, nmatvec);
+  printfQuda("eigenSolver: TIME_REPORT - Eigenvalue calculation: %f sec\n", secs);
+  printfQuda("Eigenvalues of the Even-Odd Dirac operator:\n===========\n");
+  for (int i = 0; i < NeV; i++) {
+    eigenValues[2 * i] = (Float)ev[i]; eigenValues[2 * i + 1] = 0;
+    residuals[i] = rs[i];
+    printfQuda("Eval[%04d] = %+e  %+e    Residual: %+e\n", i, ev[i], 0.0, rs[i]);
+  }
+}
+template <typename Float> void QKXTM_Deflation<Float>::polynomialOperator(ColorSpinorField &out, const ColorSpinorField &in) {
+  create_dirac(invert_param);
+  TMQ_OK(tmq_poly_mdagm(out.handle(), in.handle(), PolyDeg, amin, amax));
+}
+template <typename Float> void QKXTM_Deflation<Float>::deflateVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in) {
+  if (NeV == 0) { vec_defl.zero_device(); return; }
+  // vec_in.H_elem() holds the host AoS vector (Deflation.cpp:640-668); the parity block isEv is deflated, the other
+  // parity of the result is zero
+  QKXTM_Vector<Float> stage(BOTH, VECTOR);
+  stage.packVector(vec_in.H_elem());
+  stage.loadVector();
+  ColorSpinorField in(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION), out(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  stage.uploadToCuda(&in, isEv);
+  std::vector<double> ev(NeV);
+  for (int i = 0; i < NeV; i++) ev[i] = (double)eigenValues[2 * i];
+  TMQ_OK(tmq_deflate(out.handle(), in.handle(), set, ev.data(), NeV));
+  vec_defl.downloadFromCuda(&out, isEv);
+  vec_defl.unloadVector();        // keep h_elem (SoA) in step with the device copy, as packVector + loadVector leave it
+}
+template <typename Float> void QKXTM_Deflation<Float>::ApplyMdagM(Float *vec_out, Float *vec_in, QudaInvertParam *param) {
+  ::ApplyMdagM((double *)vec_out, (double *)vec_in, param, isEv);
+}
+template <typename Float> void QKXTM_Deflation<Float>::copyEigenVectorToQKXTM_Vector(int id, Float *vec) {
+  if (NeV == 0) return;
+  if (id < 0 || id >= NeV) errorQuda("eigenvector index %d out of range", id);
+  QKXTM_Vector<Float> stage(BOTH, VECTOR);
+  ColorSpinorField v(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  TMQ_OK(tmq_copy(v.handle(), tmq_eigset_vector(set, id)));
+  stage.downloadFromCuda(&v, isEv);
+  stage.download();
+  memcpy(vec, stage.H_elem(), (size_t)G.localVolume * 24 * sizeof(Float));
+}
+template class QKXTM_Deflation<double>;
 
 template class QKXTM_Field<double>;
 template class QKXTM_Field<float>;

@@ -27,7 +27,8 @@ tmq_spinor_even tmq_spinor_odd tmq_op_set tmq_dslash tmq_dslash_twist_xpay tmq_m
 tmq_prepare tmq_reconstruct tmq_cg_mdagm tmq_cg_history tmq_zero tmq_copy tmq_ax tmq_axpy tmq_axpby tmq_xpay
 tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm tmq_axpy_zpbx tmq_gamma5
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
-tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count""".split()
+tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
+tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project""".split()
 
 
 class TmqError(RuntimeError):
@@ -95,6 +96,14 @@ def load():
     L.tmq_h2d.argtypes = [vp, vp, vp, C.c_size_t]; L.tmq_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     L.tmq_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, dp, C.POINTER(C.c_longlong)]
     L.tmq_launch_count.restype = C.c_longlong; L.tmq_launch_count.argtypes = [vp]
+    L.tmq_poly_mdagm.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double]
+    L.tmq_eigset_alloc.restype = vp; L.tmq_eigset_alloc.argtypes = [vp, C.c_int, C.c_int]
+    L.tmq_eigset_free.argtypes = [vp]; L.tmq_eigset_size.argtypes = [vp]
+    L.tmq_eigset_vector.restype = vp; L.tmq_eigset_vector.argtypes = [vp, C.c_int]
+    L.tmq_eigensolve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                 C.c_ulonglong, dp, dp, ip, ip, ip]
+    L.tmq_deflate.argtypes = [vp, vp, vp, dp, C.c_int]
+    L.tmq_project.argtypes = [vp, vp, vp, C.c_int]
     _lib = L
     return L
 
@@ -162,6 +171,34 @@ class Spinor:
         return Spinor(self.ctx, self.prec, PARITY, _handle=self.ctx.L.tmq_spinor_odd(self.h))
 
 
+class EigSet:
+    """A set of parity vectors resident in HBM (tmq_eigset): Krylov basis / eigenvectors of QKXTM_Deflation."""
+
+    def __init__(self, ctx, nvec, prec=PREC_DOUBLE):
+        self.ctx, self.prec, self.nvec = ctx, prec, nvec
+        self.h = ctx.L.tmq_eigset_alloc(ctx.h, nvec, prec)
+        if not self.h:
+            raise TmqError(ctx.L.tmq_last_error().decode())
+        ctx._eigsets.add(self)
+
+    def vector(self, i):
+        h = self.ctx.L.tmq_eigset_vector(self.h, i)
+        if not h:
+            raise TmqError(self.ctx.L.tmq_last_error().decode())
+        return Spinor(self.ctx, self.prec, PARITY, _handle=h)
+
+    def free(self):
+        if self.h and self.ctx.h:
+            self.ctx.L.tmq_eigset_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU / one rank.  Mirrors initQuda + init_qudaQKXTM + loadGaugeQuda + createDirac."""
 
@@ -171,6 +208,7 @@ class Context:
         self.grid, self.coord = tuple(grid), tuple(coord)
         self.V = int(np.prod(self.X)); self.Vh = self.V // 2
         self._spinors = weakref.WeakSet()
+        self._eigsets = weakref.WeakSet()
         self.h = self.L.tmq_create(device, _i4(localX), _i4(grid), _i4(coord))
         if not self.h:
             raise TmqError(self.L.tmq_last_error().decode())
@@ -179,6 +217,8 @@ class Context:
     def close(self):
         """tmq_destroy frees every spinor of the context: invalidate their Python handles first"""
         if self.h:
+            for e in list(self._eigsets):
+                e.free()
             for s in list(self._spinors):
                 s.free()
             self.L.tmq_destroy(self.h)
@@ -234,6 +274,24 @@ class Context:
         h = np.zeros(n)
         _ck(self.L.tmq_cg_history(self.h, _dp(h), n))
         return h
+
+    # -- eigensolver (QKXTM_Deflation)
+    def poly_mdagm(self, out, inp, deg, amin, amax): _ck(self.L.tmq_poly_mdagm(out.h, inp.h, deg, amin, amax))
+
+    def eigset(self, nvec, prec=PREC_DOUBLE): return EigSet(self, nvec, prec)
+
+    def eigensolve(self, eset, nev, nkv, poly_deg=0, amin=0.0, amax=0.0, tol=1e-10, max_restarts=100, which=0, seed=1):
+        ev = np.zeros(nev); rs = np.zeros(nev)
+        nc = C.c_int(0); nr = C.c_int(0); nm = C.c_int(0)
+        _ck(self.L.tmq_eigensolve(eset.h, nev, nkv, poly_deg, amin, amax, tol, max_restarts, which, seed, _dp(ev), _dp(rs),
+                                  C.byref(nc), C.byref(nr), C.byref(nm)))
+        return dict(evals=ev, resid=rs, nconv=nc.value, restarts=nr.value, matvecs=nm.value)
+
+    def deflate(self, out, inp, eset, evals, nvec=None):
+        ev = np.ascontiguousarray(evals, dtype=np.float64)
+        _ck(self.L.tmq_deflate(out.h, inp.h, eset.h, _dp(ev), len(ev) if nvec is None else nvec))
+
+    def project(self, out, inp, eset, nvec): _ck(self.L.tmq_project(out.h, inp.h, eset.h, nvec))
 
     # -- blas
     def zero(self, x): _ck(self.L.tmq_zero(x.h))

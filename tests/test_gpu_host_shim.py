@@ -90,3 +90,33 @@ def test_MG_bench_twelve_columns_and_plaquette(tmp_path, env):
 def test_driver_rejects_unsupported_parameters(tmp_path):
     p = subprocess.run([DRV, "--dim", "5", "4", "4", "4"], capture_output=True, text=True, timeout=120)
     assert p.returncode != 0 and "ERROR" in p.stderr      # errorQuda aborts
+
+
+def test_deflation_class_eigensolver_and_deflate(tmp_path, env):
+    """QKXTM_Deflation (include/qudaQKXTM.h:391-475): eigenSolver on the even-even asymmetric M^dag M (the operator the
+    reference's eigensolver uses, qkxtm/Calc_Loops.cpp:712-713), copyEigenVectorToQKXTM_Vector and deflateVector"""
+    o, gauge, tmq = env
+    nev = 4
+    r, _, _, out = run(tmp_path, "--test", "eig", "--matpc", "even-even-asym", "--nEv", str(nev), "--nKv", "24", "--PolyDeg", "20",
+                       "--amin", "0.34", "--amax", "2.0", "--tolArpack", "1e-11", "--source", "gaussian")
+    V = int(np.prod(X))
+    ev, rs = r[:nev], r[nev:2 * nev]
+    v0 = lu.spinor_eo_from_lex(r[2 * nev: 2 * nev + V * 24].reshape(V, 4, 3, 2), X)
+    xd = lu.spinor_eo_from_lex(r[2 * nev + V * 24:].reshape(V, 4, 3, 2), X)
+    Vh = V // 2
+    assert np.all(np.diff(ev) >= 0) and np.all(rs < 1e-8), (ev, rs)
+    # eigenvector 0: even parity normalised, odd parity zero, eigen-equation holds with the oracle operator
+    e0 = np.ascontiguousarray(v0[:Vh])
+    assert np.all(v0[Vh:] == 0) and abs(np.sum(e0 * e0) - 1) < 1e-10
+    Ae = o.mdagm(gauge, e0, KAPPA, MU, 2)
+    assert lu.rel_l2(Ae, ev[0] * e0) < 1e-8
+    # smallest eigenvalue agrees with ARPACK on the oracle operator
+    from oracle.oracle import eigs_reference
+    cplx = lambda a: np.ascontiguousarray(a[..., 0] + 1j * a[..., 1]).ravel()
+    real = lambda v: np.ascontiguousarray(np.stack([v.real, v.imag], axis=-1).reshape(Vh, 4, 3, 2))
+    lam, U = eigs_reference(lambda v: cplx(o.mdagm(gauge, real(v), KAPPA, MU, 2)), 12 * Vh, nev, 24, "SR", tol=1e-12)
+    assert np.allclose(ev, lam, rtol=1e-9), (ev, lam)
+    # deflated source = U Lambda^-1 U^dag b_even, odd parity zero
+    b = lu.spinor_eo_from_lex(tmq.gen_spinor(X, "gaussian", seed=100, eo_order=False), X)
+    ref = U @ ((U.conj().T @ cplx(np.ascontiguousarray(b[:Vh]))) / lam)
+    assert np.all(xd[Vh:] == 0) and lu.rel_l2(cplx(np.ascontiguousarray(xd[:Vh])), ref) < 1e-7

@@ -260,3 +260,23 @@ def test_golden_checksums():
         for key in ("plaquette", "sum", "sumsq"):
             assert abs(got[name][key] - gold[name][key]) <= 1e-11 * max(1.0, abs(gold[name][key])), (name, key)
         assert np.allclose(got[name]["samples"], gold[name]["samples"], rtol=1e-12, atol=1e-13)
+
+
+def test_chebyshev_filter_restatement():
+    """the oracle's polynomialOperator restatement (reference lib/qudaQKXTM_Deflation.cpp:997-1063) is a polynomial in A:
+    on a diagonal operator it equals the scalar recurrence applied to each eigenvalue, p(0) = 1, |p| stays below its
+    edge value inside the window [amin, amax] and grows monotonically below amin"""
+    from oracle.oracle import poly_operator, poly_scalar, cheb_coefficients
+    rng = np.random.default_rng(5)
+    lam = np.concatenate([[0.0, 1e-3, 1e-2], rng.uniform(0.05, 4.0, 40)])
+    x = rng.standard_normal(lam.size) + 1j * rng.standard_normal(lam.size)
+    for deg in (0, 1, 2, 7, 40):
+        y = poly_operator(lambda v: lam * v, x, deg, 0.05, 4.0)
+        p = np.array([poly_scalar(l, deg, 0.05, 4.0) for l in lam])
+        assert np.allclose(y, p * x, rtol=1e-12, atol=1e-14)
+        assert abs(p[0] - 1.0) < 1e-12
+        if deg >= 2:
+            edge = abs(poly_scalar(0.05, deg, 0.05, 4.0))
+            assert np.all(np.abs(p[3:]) <= edge * (1 + 1e-9))
+            assert p[0] > p[1] > p[2] > edge
+    assert len(cheb_coefficients(5, 0.05, 4.0)) == 5
