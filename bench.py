@@ -56,6 +56,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def committed_traffic(prec, recon, X):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture (profiles/), if one exists
+    for this exact kernel and local lattice; else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        return t.get("dslash_kernel<%s,%d,EPI_TW>@%dx%dx%dx%d" % (("double" if prec == 8 else "float", recon) + tuple(X)))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -280,7 +291,7 @@ def run_native(args):
     roofline = {"bound": "hbm", "kernel": "dslash_kernel<%s,%d,EPI_TW> (hop + A^-1)" % ("double" if prec == 8 else "float", recon),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_site": bps, "sites_per_launch": Vh_loc, "ms_per_launch": kern[1],
-                "traffic": args.ncu_traffic}
+                "traffic": args.ncu_traffic if args.ncu_traffic is not None else committed_traffic(prec, recon, X)}
     kernels = {}
     for kind in (0, 1, 2):
         b = bytes_per_site(kind, prec, recon)

@@ -5,7 +5,7 @@
 //   include/qudaQKXTM.h:104-277 (containers), :484-513 (entry points),
 //   include/qudaQKXTM_utils.h:45-75,126-139 (qudaQKXTMinfo, enums, init_qudaQKXTM)
 // and the handful of QUDA C-API calls the drivers make (qkxtm/Calc_Loops.cpp:692-708,753-759,797-806)
-// compiles against this header for that path.  Everything the path does not touch (contractions, smearing,
+// compiles against this header for that path.  Everything the path does not touch (contractions,
 // loops, file I/O, ghost exchange of the containers) is deliberately absent -- see DESIGN.md.
 //
 // Threading / state: like the reference, one host thread per rank and library-global state (one context,
@@ -179,6 +179,7 @@ public:
   void download();                                 // D2H + SoA -> AoS in h_elem (lib/qudaQKXTM_Vector.cpp:135-156)
   void uploadToCuda(ColorSpinorField *cudaVector, bool isEv = false);      // lib/qudaQKXTM_Vector.cpp:424-427
   void downloadFromCuda(ColorSpinorField *cudaVector, bool isEv = false);  // lib/qudaQKXTM_Vector.cpp:430-432
+  void gaussianSmearing(QKXTM_Vector<Float> &vecIn, QKXTM_Gauge<Float> &gaugeAPE);   // lib/qudaQKXTM_Vector.cpp:386-421 (vecIn is clobbered, as in the reference)
   void scaleVector(double a);
   void castDoubleToFloat(QKXTM_Vector<double> &vecIn);
   void castFloatToDouble(QKXTM_Vector<float> &vecIn);

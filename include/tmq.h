@@ -59,7 +59,7 @@ int tmq_comm_init(tmq_ctx *, const char id128[128], int nranks, int rank);
 int tmq_force_partition(tmq_ctx *, const int part[4]);
 /* tuning knobs (tile of the thread->site map); 0 keeps the default                                        */
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
-enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3 };   /* L2 prefetch of the epilogue operands inside the Dslash kernels (default 0: no measurable gain) */
+enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3, TMQ_OPT_SMEAR_BLOCK_T = 4 };   /* L2 prefetch of the epilogue operands inside the Dslash kernels (default 0: no measurable gain) */
 int tmq_set_option(tmq_ctx *, int option, int value);
 /* TMQ_OPT_HALO_P2P selects the ghost exchange.  0: ncclSend/ncclRecv on a separate stream + interior / boundary
  * launches.  1: the pack kernel stores the faces straight into the neighbours' ghost arenas over NVLink peer mappings
@@ -178,6 +178,13 @@ int tmq_qkxtm_scale(tmq_ctx *, void *d_qkxtm, int prec, double a);
 int tmq_qkxtm_cast(tmq_ctx *, void *d_dst, int dst_prec, const void *d_src, int src_prec);
 int tmq_qkxtm_gamma5(tmq_ctx *, void *d_qkxtm, int prec);
 int tmq_qkxtm_absorb(tmq_ctx *, void *d_prop, const void *d_vec, int prec, int nu, int c2);
+/* QKXTM_Vector::gaussianSmearing (lib/qudaQKXTM_Vector.cpp:386-421, kernel body lib/code_pieces/Gauss_core.h):
+ * nsmear steps of out = (psi + alpha sum_{mu=x,y,z} [U_mu(x) psi(x+mu) + U_mu(x-mu)^dag psi(x-mu)]) / (1 + 6 alpha) on the
+ * QKXTM device layouts (vector d[(s*3+c)*V + x], gauge d[((dir*3+c1)*3+c2)*V + x]).  Like the reference it ping-pongs
+ * between the two vectors: d_in is CLOBBERED, the result ends in d_out (nsmear = 0 copies).  The time direction does
+ * not hop, so a T-sharded lattice needs no exchange; a z split is refused.  Time slices are swept in L2-resident
+ * blocks (TMQ_OPT_SMEAR_BLOCK_T: slices per block, 0 = derive from the L2 size, >= T = plain streaming order).    */
+int tmq_qkxtm_gauss_smear(tmq_ctx *, void *d_out, void *d_in, const void *d_gauge, int prec, int nsmear, double alpha);
 
 /* ---- raw device memory for the containers (QKXTM_Field::create_device, lib/qudaQKXTM_Field.cpp:172) ----- */
 int tmq_dev_malloc(tmq_ctx *, void **ptr, size_t bytes);
@@ -190,11 +197,16 @@ int tmq_d2h(tmq_ctx *, void *dst, const void *src, size_t bytes);
 /* run `reps` back-to-back applications of one kernel flavour on (a copy of) the PARITY field `in` and return
  * the average device time per application in milliseconds (CUDA events on the launching stream).
  * kind: 0 = K1 hop, 1 = K2 hop+A^-1, 2 = K3 hop+A^-1+xpay, 3 = M^dag M (4 kernels), 4 = one fused CG
- * iteration (4 Dslash kernels + update, no host sync).  prec selects fp64/fp32 arithmetic.  When
+ * iteration (4 Dslash kernels + update, no host sync), 5 = Chebyshev filter of degree `reps` (ms per degree).
+ * prec selects fp64/fp32 arithmetic.  When
  * flush_l2 != 0 a buffer larger than L2 is rewritten before every application and each application is
  * timed separately.                                                                                          */
 int tmq_time_kernel(tmq_ctx *, int kind, int prec, int reps, const tmq_spinor *in, int flush_l2,
                     double *ms_per_app, long long *launches);
+/* CUDA-event stopwatch on the context's stream, for the asynchronous container kernels: start records an event, stop
+ * records a second one, waits for it and returns the device time between them in milliseconds                */
+int tmq_timer_start(tmq_ctx *);
+int tmq_timer_stop(tmq_ctx *, double *ms);
 /* number of kernels this library has launched on the context since creation                                 */
 long long tmq_launch_count(tmq_ctx *);
 

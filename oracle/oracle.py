@@ -222,3 +222,32 @@ def eigs_reference(apply_A, n_complex, nev, ncv, which="SR", poly=None, tol=0.0,
     lam = np.array([np.vdot(U[:, i], mv(U[:, i])).real for i in range(nev)])
     o = np.argsort(lam)
     return lam[o], U[:, o]
+
+
+# ---- Gaussian (Wuppertal) smearing restatement ---------------------------------------------------
+def gauss_smear_step(vec, gauge, X, alpha):
+    """One step of lib/code_pieces/Gauss_core.h in numpy on the plug-in's device layouts:
+    vec  [12][V] complex (component s*3+c, x lexicographic x + X(y + Y(z + Z t)))    (Gauss_core.h:197 READVECTOR)
+    gauge [4][3][3][V] complex (dir, c1, c2)                                          (Gauss_core.h:76 READGAUGE)
+    out = (psi + alpha sum_{mu=0,1,2} [U_mu(x) psi(x+mu) + U_mu(x-mu)^dag psi(x-mu)]) / (1 + 6 alpha)   (:80-215);
+    the time direction does not hop; periodic in x, y, z (single rank)."""
+    Xd, Yd, Zd, Td = X
+    psi = vec.reshape(4, 3, Td, Zd, Yd, Xd)
+    U = gauge.reshape(4, 3, 3, Td, Zd, Yd, Xd)
+    acc = np.zeros_like(psi)
+    for mu, ax in ((0, 5), (1, 4), (2, 3)):
+        fwd = np.roll(psi, -1, axis=ax)                                  # psi(x + mu)
+        acc += np.einsum("ab...,sb...->sa...", U[mu], fwd)               # apply_U_on_S      (core_def.h:498-513)
+        Ub = np.roll(U[mu], 1, axis=ax)                                  # U_mu(x - mu)
+        bwd = np.roll(psi, 1, axis=ax)
+        acc += np.einsum("ba...,sb...->sa...", Ub.conj(), bwd)           # apply_U_DAG_on_S  (core_def.h:515-530)
+    out = (psi + alpha * acc) / (1.0 + 6.0 * alpha)
+    return out.reshape(12, -1)
+
+
+def gauss_smear(vec, gauge, X, alpha, nsmear):
+    """QKXTM_Vector::gaussianSmearing (lib/qudaQKXTM_Vector.cpp:386-421)."""
+    cur = vec
+    for _ in range(nsmear):
+        cur = gauss_smear_step(cur, gauge, X, alpha)
+    return cur.copy()

@@ -431,6 +431,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->multi = g.part[2] || g.part[3];
   c->tile[0] = 4; c->tile[1] = 4; c->tile[2] = 2;
   c->opt_prefetch = 0;
+  c->opt_smear_block_t = 0;
   c->opt_pre_pct = 50; c->red_seq = 0; memset(c->rank_arena, 0, sizeof(c->rank_arena));
   c->opt_p2p = 2; c->p2p = false; c->seq_table = nullptr; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
   memset(c->peer_arena, 0, sizeof(c->peer_arena));
@@ -579,6 +580,7 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
   TMQ_REQUIRE(c, "null context");
   switch (option) {
     case TMQ_OPT_PREFETCH: c->opt_prefetch = value ? 1 : 0; return 0;
+    case TMQ_OPT_SMEAR_BLOCK_T: c->opt_smear_block_t = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {
       c->opt_p2p = value < 0 ? 0 : (value > 2 ? 2 : value);
@@ -1167,8 +1169,8 @@ int tmq_time_kernel(tmq_ctx *c, int kind, int prec, int reps, const tmq_spinor *
   TMQ_REQUIRE(c && ms_per_app, "null argument");
   REQ_PARITY(in); REQ_OP(c);
   TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
-  TMQ_REQUIRE(kind >= 0 && kind <= 4 && reps > 0, "bad kind / reps");
-  TMQ_REQUIRE(c->matpc < 2, "timing kinds are defined for the symmetric preconditioning");
+  TMQ_REQUIRE(kind >= 0 && kind <= 5 && reps > 0, "bad kind / reps");
+  TMQ_REQUIRE(c->matpc < 2 || kind == 5, "timing kinds 0-4 are defined for the symmetric preconditioning");
   TMQ_TRY(ensure_scratch(c, prec, 6));
   const size_t n = nvec(c);
   void *src = scr(c, prec, 4), *dst = scr(c, prec, 5), *r = scr(c, prec, 2), *p = scr(c, prec, 3);
@@ -1181,6 +1183,23 @@ int tmq_time_kernel(tmq_ctx *c, int kind, int prec, int reps, const tmq_spinor *
   const size_t flush_bytes = (size_t)256 << 20;
   if (flush_l2) TMQ_CUDA(cudaMalloc(&flush, flush_bytes));
   const int pq = c->matpc & 1;
+  if (kind == 5) {
+    // Chebyshev filter of degree `reps` (4 Dslash launches per degree, recurrence fused): ms per degree
+    if (flush) { cudaFree(flush); flush = nullptr; }
+    const long long l0 = c->launches;
+    TMQ_TRY(op_poly_mdagm(c, prec, dst, src, 2, 0.1, 4.0));
+    const long long per = (c->launches - l0) / 2;
+    TMQ_CUDA(cudaEventRecord(c->ev_a, c->stream));
+    TMQ_TRY(op_poly_mdagm(c, prec, dst, src, reps, 0.1, 4.0));
+    TMQ_CUDA(cudaEventRecord(c->ev_b, c->stream));
+    TMQ_CUDA(cudaEventSynchronize(c->ev_b));
+    float ms = 0;
+    TMQ_CUDA(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+    TMQ_TRY(check_device_error(c));
+    *ms_per_app = ms / reps;
+    if (launches) *launches = per;
+    return 0;
+  }
   auto one = [&](int it) -> int {
     HopSpec s;
     switch (kind) {

@@ -12,8 +12,18 @@ namespace tmq {
 #define TMQ_DSLASH_BLOCK 128
 #endif
 
-template <typename F> struct MinBlocks { static constexpr int v = 3; };
-template <> struct MinBlocks<float> { static constexpr int v = 6; };
+// CTAs per SM.  fp64: the light epilogues (plain hop, hop + twist: K1 and K3 of the CG iteration) fit 128 registers with
+// a 12-16 byte spill and gain 4% from the fourth resident CTA (16 instead of 12 warps hide the recon-12 / SU(3) fp64
+// latency; measured A/B in profiles/r02_variant_minblocks.log); the heavy epilogues spill 250-400 bytes at 128
+// registers and stay at 3.
+#ifndef TMQ_MINBLOCKS_D
+#define TMQ_MINBLOCKS_D 3
+#endif
+#ifndef TMQ_MINBLOCKS_D_LIGHT
+#define TMQ_MINBLOCKS_D_LIGHT 4
+#endif
+template <typename F, int EPI> struct MinBlocks { static constexpr int v = (EPI == EPI_PLAIN || EPI == EPI_TW) ? TMQ_MINBLOCKS_D_LIGHT : TMQ_MINBLOCKS_D; };
+template <int EPI> struct MinBlocks<float, EPI> { static constexpr int v = 6; };
 
 // Boundary CTAs of a fused sharded launch: wait until every neighbour has published this application's
 // sequence number (its pack kernel has finished storing the faces into our ghost buffers over NVLink).
@@ -34,7 +44,7 @@ __device__ __forceinline__ void halo_wait(const HaloWait &hw) {
 }
 
 template <typename F, int RECON, int EPI, bool MULTI>
-__global__ void __launch_bounds__(TMQ_DSLASH_BLOCK, MinBlocks<F>::v)
+__global__ void __launch_bounds__(TMQ_DSLASH_BLOCK, (MinBlocks<F, EPI>::v))
 dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
   uint32_t blk = blockIdx.x;
   const Enum *en = &A.en;

@@ -28,6 +28,8 @@ struct Globals {
   QudaVerbosity verbosity = QUDA_SUMMARIZE;
   qkxtm_error_handler on_error = nullptr;
   double op_kappa = 0, op_mu = 0;
+  int nsmearGauss = 0;                // GK_nsmearGauss, GK_alphaGauss (lib/qudaQKXTM_kernels.cu:60-64)
+  double alphaGauss = 0;
   int op_matpc = -1;
 } G;
 
@@ -233,6 +235,7 @@ void init_qudaQKXTM(qudaQKXTMinfo *info) {
   if (G.qkxtm_initialized) return;                       // one-shot (lib/qudaQKXTM_kernels.cu:120,288)
   if (!info) errorQuda("null info");
   ensure_context(info->lL);
+  G.nsmearGauss = info->nsmearGauss; G.alphaGauss = info->alphaGauss;      // GK_nsmearGauss, GK_alphaGauss (:125-127)
   G.qkxtm_initialized = true;
   printfQuda("qudaQKXTM has been initialized\n");
 }
@@ -381,6 +384,11 @@ template <typename Float> void QKXTM_Vector<Float>::downloadFromCuda(ColorSpinor
   const int parity = cv->SiteSubset() == QUDA_FULL_SITE_SUBSET ? -1 : (isEv ? 0 : 1);
   TMQ_OK(tmq_spinor_to_qkxtm(this->d_elem, (int)sizeof(Float), cv->handle(), parity, 1.0));
 }
+template <typename Float> void QKXTM_Vector<Float>::gaussianSmearing(QKXTM_Vector<Float> &vecIn, QKXTM_Gauge<Float> &gaugeAPE) {
+  // GK_nsmearGauss / GK_alphaGauss come from init_qudaQKXTM (lib/qudaQKXTM_kernels.cu:125-127); no ghost exchange is
+  // needed: the hop is 3-dimensional and the lattice is sharded along T
+  TMQ_OK(tmq_qkxtm_gauss_smear(G.ctx, this->d_elem, vecIn.D_elem(), gaugeAPE.D_elem(), (int)sizeof(Float), G.nsmearGauss, G.alphaGauss));
+}
 template <typename Float> void QKXTM_Vector<Float>::scaleVector(double a) { TMQ_OK(tmq_qkxtm_scale(G.ctx, this->d_elem, (int)sizeof(Float), a)); }
 template <typename Float> void QKXTM_Vector<Float>::castDoubleToFloat(QKXTM_Vector<double> &in) {
   if (sizeof(Float) != 4) errorQuda("castDoubleToFloat needs a float vector");
@@ -526,19 +534,20 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
   if (!param || !gauge_param) errorQuda("null argument");
   check_solver(param);
   if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
-  if (info.nsmearGauss != 0) errorQuda("Gaussian smearing of the source is outside this path (nsmearGauss must be 0)");
+  if (G.nsmearGauss != 0 && !gaugeSmeared) errorQuda("Gaussian smearing of the source needs the smeared links (gaugeSmeared)");
   const bool flag_eo = info.isEven;     // (the reference leaves this unset; b and x are full fields, so it is moot)
   const auto T0 = std::chrono::steady_clock::now();
   const long long V = G.localVolume;
   double *input_vector = (double *)malloc((size_t)V * 24 * sizeof(double));
   if (!input_vector) errorQuda("Error allocating memory for the host source");
   QKXTM_Vector<double> *K_vector = new QKXTM_Vector<double>(BOTH, VECTOR);
+  QKXTM_Vector<double> *K_guess = new QKXTM_Vector<double>(BOTH, VECTOR);
+  QKXTM_Gauge<double> *K_gaugeSmeared = NULL;
   if (gaugeSmeared) {
-    QKXTM_Gauge<double> *K_gaugeSmeared = new QKXTM_Gauge<double>(BOTH, GAUGE);
+    K_gaugeSmeared = new QKXTM_Gauge<double>(BOTH, GAUGE);              // interface.cpp:72-77
     K_gaugeSmeared->packGauge(gaugeSmeared);
     K_gaugeSmeared->loadGauge();
     K_gaugeSmeared->calculatePlaq();
-    delete K_gaugeSmeared;
   }
   printfQuda("Memory allocation was successfull\n");
   ColorSpinorField *b = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
@@ -551,7 +560,12 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
     input_vector[isc * 2] = 1.0;                          // point source at the origin, spin-colour isc
     K_vector->packVector(input_vector);
     K_vector->loadVector();
-    K_vector->uploadToCuda(b, flag_eo);
+    if (K_gaugeSmeared) {
+      K_guess->gaussianSmearing(*K_vector, *K_gaugeSmeared);            // interface.cpp:184 (nsmearGauss = 0 copies)
+      K_guess->uploadToCuda(b, flag_eo);                                // :185
+    } else {
+      K_vector->uploadToCuda(b, flag_eo);
+    }
     printfQuda(" up - %02d: \n", isc);
     solve_device(*x, *b, param);
     K_vector->downloadFromCuda(x, flag_eo);
@@ -566,6 +580,8 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
   }
   free(input_vector);
   delete K_vector;
+  delete K_guess;
+  if (K_gaugeSmeared) delete K_gaugeSmeared;
   delete x;
   delete b;
   printfQuda("...Done (%f sec)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());

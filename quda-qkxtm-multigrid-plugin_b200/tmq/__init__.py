@@ -12,10 +12,11 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtmq.so")
+# TMQ_LIB_PATH: tuning variants built by `make VARIANT=...` (tools/ only; tests and bench use the product library)
+LIB_PATH = os.environ.get("TMQ_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libtmq.so")
 
 PREC_SINGLE, PREC_DOUBLE = 4, 8
-OPT_PREFETCH, OPT_HALO_P2P = 1, 2
+OPT_PREFETCH, OPT_HALO_P2P, OPT_BOUNDARY_AT_PCT, OPT_SMEAR_BLOCK_T = 1, 2, 3, 4
 PARITY, FULL = 1, 2
 MATPC_EVEN_EVEN, MATPC_ODD_ODD, MATPC_EVEN_EVEN_ASYM, MATPC_ODD_ODD_ASYM = 0, 1, 2, 3
 
@@ -28,7 +29,7 @@ tmq_prepare tmq_reconstruct tmq_cg_mdagm tmq_cg_history tmq_zero tmq_copy tmq_ax
 tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm tmq_axpy_zpbx tmq_gamma5
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
-tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project""".split()
+tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop""".split()
 
 
 class TmqError(RuntimeError):
@@ -104,6 +105,8 @@ def load():
                                  C.c_ulonglong, dp, dp, ip, ip, ip]
     L.tmq_deflate.argtypes = [vp, vp, vp, dp, C.c_int]
     L.tmq_project.argtypes = [vp, vp, vp, C.c_int]
+    L.tmq_qkxtm_gauss_smear.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_double]
+    L.tmq_timer_start.argtypes = [vp]; L.tmq_timer_stop.argtypes = [vp, dp]
     _lib = L
     return L
 
@@ -334,7 +337,14 @@ class Context:
     def qkxtm_gamma5(self, dptr, prec): _ck(self.L.tmq_qkxtm_gamma5(self.h, dptr, prec))
     def qkxtm_absorb(self, dprop, dvec, prec, nu, c2): _ck(self.L.tmq_qkxtm_absorb(self.h, dprop, dvec, prec, nu, c2))
 
+    def qkxtm_gauss_smear(self, dout, din, dgauge, prec, nsmear, alpha):
+        _ck(self.L.tmq_qkxtm_gauss_smear(self.h, dout, din, dgauge, prec, nsmear, alpha))
+
     # -- measurement
+    def timer_start(self): _ck(self.L.tmq_timer_start(self.h))
+    def timer_stop(self):
+        ms = C.c_double(0); _ck(self.L.tmq_timer_stop(self.h, C.byref(ms))); return ms.value
+
     def time_kernel(self, kind, prec, reps, inp, flush_l2=0):
         ms = C.c_double(0); nl = C.c_longlong(0)
         _ck(self.L.tmq_time_kernel(self.h, kind, prec, reps, inp.h, flush_l2, C.byref(ms), C.byref(nl)))

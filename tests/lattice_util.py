@@ -143,7 +143,9 @@ def spinor_lex_from_eo(psi_eo, Xloc):
 
 
 def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64).ravel(); b = np.asarray(b, dtype=np.float64).ravel()
+    a = np.asarray(a); b = np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = a.astype(dt).ravel(); b = b.astype(dt).ravel()
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 

@@ -9,7 +9,7 @@ def P(*a):
     print(*a, file=out)
 
 P("# ncu summary %s\n" % tag)
-P("Command profiled: `python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu` (48^3x96 fp64 recon-12, 1 GPU).")
+P("Command profiled: `%s` (48^3x96, 1 GPU)." % (sys.argv[2] if len(sys.argv) > 2 else "python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu"))
 P("Per-launch times below are cold-cache and serialised under ncu: compare SHARES, not absolutes.\n")
 rows = list(csv.reader(open("gpurun_out/launches_%s.csv" % tag)))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -28,7 +28,7 @@ P("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|"
 for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
     P("| `%s` | %d | %.1f | %.1f | %.1f%% |" % (k, n, t, t / n, 100 * t / tot))
 P("\nEPI codes: 0 plain hop, 1 hop+A^-1 (K1/K3 of the CG iteration), 2 hop+A^-1+xpay, 5 = K2 (M p, fused |Mp|^2, A^-dag), "
-  "7 = K4 (A^dag w - k^2 D^dag u, fused r -= alpha z and |r|^2).\n")
+  "7 = K4 (A^dag w - k^2 D^dag u, fused r -= alpha z and |r|^2), 6 = K2 of the asymmetric operator (A x - k^2 D t), 8 = K4 with the Chebyshev three-term recurrence fused in (EPI_CHEB).\n")
 raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_%s.ncu-rep" % tag, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw)))
 if len(rr) > 2:
