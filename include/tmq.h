@@ -59,7 +59,7 @@ int tmq_comm_init(tmq_ctx *, const char id128[128], int nranks, int rank);
 int tmq_force_partition(tmq_ctx *, const int part[4]);
 /* tuning knobs (tile of the thread->site map); 0 keeps the default                                        */
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
-enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3, TMQ_OPT_SMEAR_BLOCK_T = 4 };   /* L2 prefetch of the epilogue operands inside the Dslash kernels (default 0: no measurable gain) */
+enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3, TMQ_OPT_SMEAR_BLOCK_T = 4 };   /* TMQ_OPT_PREFETCH: accepted and ignored (the L2-prefetch experiment was removed: no gain) */
 int tmq_set_option(tmq_ctx *, int option, int value);
 /* TMQ_OPT_HALO_P2P selects the ghost exchange.  0: ncclSend/ncclRecv on a separate stream + interior / boundary
  * launches.  1: the pack kernel stores the faces straight into the neighbours' ghost arenas over NVLink peer mappings
@@ -182,8 +182,8 @@ int tmq_qkxtm_absorb(tmq_ctx *, void *d_prop, const void *d_vec, int prec, int n
  * nsmear steps of out = (psi + alpha sum_{mu=x,y,z} [U_mu(x) psi(x+mu) + U_mu(x-mu)^dag psi(x-mu)]) / (1 + 6 alpha) on the
  * QKXTM device layouts (vector d[(s*3+c)*V + x], gauge d[((dir*3+c1)*3+c2)*V + x]).  Like the reference it ping-pongs
  * between the two vectors: d_in is CLOBBERED, the result ends in d_out (nsmear = 0 copies).  The time direction does
- * not hop, so a T-sharded lattice needs no exchange; a z split is refused.  Time slices are swept in L2-resident
- * blocks (TMQ_OPT_SMEAR_BLOCK_T: slices per block, 0 = derive from the L2 size, >= T = plain streaming order).    */
+ * not hop, so a T-sharded lattice needs no exchange; a z split is refused.  TMQ_OPT_SMEAR_BLOCK_T > 0 sweeps the
+ * time slices in blocks of that many slices (block outer, step inner: L2-resident); 0 (default) = streaming order. */
 int tmq_qkxtm_gauss_smear(tmq_ctx *, void *d_out, void *d_in, const void *d_gauge, int prec, int nsmear, double alpha);
 
 /* ---- raw device memory for the containers (QKXTM_Field::create_device, lib/qudaQKXTM_Field.cpp:172) ----- */

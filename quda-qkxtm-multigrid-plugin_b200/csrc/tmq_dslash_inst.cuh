@@ -12,12 +12,12 @@ namespace tmq {
 #define TMQ_DSLASH_BLOCK 128
 #endif
 
-// CTAs per SM.  fp64: the light epilogues (plain hop, hop + twist: K1 and K3 of the CG iteration) fit 128 registers with
-// a 12-16 byte spill and gain 4% from the fourth resident CTA (16 instead of 12 warps hide the recon-12 / SU(3) fp64
-// latency; measured A/B in profiles/r02_variant_minblocks.log); the heavy epilogues spill 250-400 bytes at 128
-// registers and stay at 3.
+// CTAs per SM.  fp64: every epilogue fits the 128-register budget of 4 resident CTAs (16 warps) with a 12-36 byte spill;
+// the fourth CTA hides the recon-12 / SU(3) fp64 latency and is worth 4-10% (A/B: profiles/r02_variant_minblocks.log,
+// r03).  What used to push the x-term epilogues to 250-400 bytes of spill was the optional L2-prefetch code path
+// (measured: no gain), now removed; the epilogue itself runs in three (vector j, j+3) pairs to stay small.
 #ifndef TMQ_MINBLOCKS_D
-#define TMQ_MINBLOCKS_D 3
+#define TMQ_MINBLOCKS_D 4
 #endif
 #ifndef TMQ_MINBLOCKS_D_LIGHT
 #define TMQ_MINBLOCKS_D_LIGHT 4

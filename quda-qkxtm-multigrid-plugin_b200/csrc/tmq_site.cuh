@@ -77,16 +77,6 @@ TMQ_HD CplxT<float> ld_stream(const CplxT<float> *p) {
 #endif
 }
 
-// L2 prefetch of a vector this thread will read in its epilogue (x term, residual): issued before the hop
-// so that the late, dependent loads hit L2 instead of paying a second HBM round trip at low occupancy
-template <typename F> TMQ_HD void prefetch_l2(const VecT<F> *p) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
-
 // ---- site enumeration -----------------------------------------------------------------------------------
 struct SiteCoord {
   int xh, y, z, t;   // local coordinates (xh = x/2)
@@ -362,6 +352,17 @@ template <typename F> TMQ_HD void twist(Spinor<F> &y, const Spinor<F> &x, F c, F
     }
 }
 
+// the same twist on one (vector j, vector j+3) pair: u' = c (u + i a l), l' = c (l + i a u)
+template <typename F> TMQ_HD void twist_pair(VecT<F> &u, VecT<F> &l, F c, F a) {
+  VecT<F> ou, ol;
+  ou.a = c * (u.a - a * l.b); ou.b = c * (u.b + a * l.a); ou.c = c * (u.c - a * l.d); ou.d = c * (u.d + a * l.c);
+  ol.a = c * (l.a - a * u.b); ol.b = c * (l.b + a * u.a); ol.c = c * (l.c - a * u.d); ol.d = c * (l.d + a * u.c);
+  u = ou; l = ol;
+}
+template <typename F> TMQ_HD double norm2_vec(const VecT<F> &v) {
+  return (double)v.a * (double)v.a + (double)v.b * (double)v.b + (double)v.c * (double)v.c + (double)v.d * (double)v.d;
+}
+
 template <int EPI> struct EpiTraits {
   static constexpr bool TW1 = (EPI == EPI_TW || EPI == EPI_TW_XPAY || EPI == EPI_MDAGM2);
   static constexpr bool XTERM = (EPI >= EPI_TW_XPAY);
@@ -383,14 +384,6 @@ TMQ_HD double dslash_site(const DslashArgs<F> &A, const Enum &en, uint32_t e, F 
   for (int s = 0; s < 4; s++)
 #pragma unroll
     for (int cc = 0; cc < 3; cc++) { o.v[s][cc][0] = 0; o.v[s][cc][1] = 0; }
-  if (T::XTERM && A.prefetch) {
-#pragma unroll
-    for (int j = 0; j < 6; j++) prefetch_l2(A.x + (size_t)j * stride + c.idx);
-  }
-  if (T::RED == 2 && A.prefetch) {
-#pragma unroll
-    for (int j = 0; j < 6; j++) prefetch_l2(A.r + (size_t)j * stride + c.idx);
-  }
 
   // recon-12 boundary sign: the links U_t(T-1) carry the anti-periodic -1 (QKXTM_util.cpp:698-705),
   // so their reconstructed third row needs the same factor (QKXTM_util.cpp:292-294)
@@ -442,58 +435,49 @@ TMQ_HD double dslash_site(const DslashArgs<F> &A, const Enum &en, uint32_t e, F 
   }
 
   // ---- epilogue ----
+  // Processed in three (vector j, vector j+3) pairs -- gamma5 pairs spin s with s^2, i.e. vector j with j+3 -- so that
+  // only 16 extra values (one pair of x / y / r vectors) are live at a time instead of a whole second spinor; the
+  // compiler fences keep the three pairs from being batched again.
   double red = 0.0;
-  if (T::TW1) { Spinor<F> t; twist(t, o, A.e.c1, A.e.a1); o = t; }
-  if (T::XTERM) {
-    Spinor<F> x;
 #pragma unroll
-    for (int j = 0; j < 6; j++) unpack_vec(x, j, A.x[(size_t)j * stride + c.idx]);
-    if (T::TWX) { Spinor<F> xt; twist(xt, x, A.e.cx, A.e.ax); x = xt; }
-#pragma unroll
-    for (int s = 0; s < 4; s++)
-#pragma unroll
-      for (int cc = 0; cc < 3; cc++) {
-        o.v[s][cc][0] = x.v[s][cc][0] + A.e.k * o.v[s][cc][0];
-        o.v[s][cc][1] = x.v[s][cc][1] + A.e.k * o.v[s][cc][1];
-      }
-  }
-  if (T::RED == 1) {
-#pragma unroll
-    for (int s = 0; s < 4; s++)
-#pragma unroll
-      for (int cc = 0; cc < 3; cc++)
-        red += (double)o.v[s][cc][0] * (double)o.v[s][cc][0] + (double)o.v[s][cc][1] * (double)o.v[s][cc][1];
-  }
-  if (T::TW3) { Spinor<F> t; twist(t, o, A.e.c3, A.e.a3); o = t; }
-  if (T::RED == 2) {
-    // r <- r - alpha z ; |r|^2
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-      VecT<F> rv = A.r[(size_t)j * stride + c.idx];
-      VecT<F> zv = pack_vec(o, j);
-      rv.a -= alpha * zv.a; rv.b -= alpha * zv.b; rv.c -= alpha * zv.c; rv.d -= alpha * zv.d;
-      red += (double)rv.a * rv.a + (double)rv.b * rv.b + (double)rv.c * rv.c + (double)rv.d * rv.d;
-      A.r[(size_t)j * stride + c.idx] = rv;
+  for (int jp = 0; jp < 3; jp++) {
+    VecT<F> ou = pack_vec(o, jp), ol = pack_vec(o, jp + 3);
+    if (T::TW1) twist_pair(ou, ol, A.e.c1, A.e.a1);
+    if (T::XTERM) {
+      VecT<F> xu = A.x[(size_t)jp * stride + c.idx], xl = A.x[(size_t)(jp + 3) * stride + c.idx];
+      if (T::TWX) twist_pair(xu, xl, A.e.cx, A.e.ax);
+      ou.a = xu.a + A.e.k * ou.a; ou.b = xu.b + A.e.k * ou.b; ou.c = xu.c + A.e.k * ou.c; ou.d = xu.d + A.e.k * ou.d;
+      ol.a = xl.a + A.e.k * ol.a; ol.b = xl.b + A.e.k * ol.b; ol.c = xl.c + A.e.k * ol.c; ol.d = xl.d + A.e.k * ol.d;
     }
-  } else if (T::CHEB) {
-    // three-term recurrence of the Chebyshev-accelerated operator (reference lib/qudaQKXTM_Deflation.cpp:1040-1056):
-    // out = d1 (M^dag M y) + d2 y + d3 r, with z = M^dag M y formed above; out may alias r (site-local)
-    const bool has3 = (A.e.d3 != (F)0);
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-      VecT<F> zv = pack_vec(o, j);
-      const VecT<F> yv = A.y[(size_t)j * stride + c.idx];
-      zv.a = A.e.d1 * zv.a + A.e.d2 * yv.a; zv.b = A.e.d1 * zv.b + A.e.d2 * yv.b;
-      zv.c = A.e.d1 * zv.c + A.e.d2 * yv.c; zv.d = A.e.d1 * zv.d + A.e.d2 * yv.d;
-      if (has3) {
-        const VecT<F> rv = A.r[(size_t)j * stride + c.idx];
-        zv.a += A.e.d3 * rv.a; zv.b += A.e.d3 * rv.b; zv.c += A.e.d3 * rv.c; zv.d += A.e.d3 * rv.d;
+    if (T::RED == 1) red += norm2_vec(ou) + norm2_vec(ol);
+    if (T::TW3) twist_pair(ou, ol, A.e.c3, A.e.a3);
+    if (T::RED == 2) {
+      // r <- r - alpha z ; |r|^2
+      VecT<F> ru = A.r[(size_t)jp * stride + c.idx], rl = A.r[(size_t)(jp + 3) * stride + c.idx];
+      ru.a -= alpha * ou.a; ru.b -= alpha * ou.b; ru.c -= alpha * ou.c; ru.d -= alpha * ou.d;
+      rl.a -= alpha * ol.a; rl.b -= alpha * ol.b; rl.c -= alpha * ol.c; rl.d -= alpha * ol.d;
+      red += norm2_vec(ru) + norm2_vec(rl);
+      A.r[(size_t)jp * stride + c.idx] = ru; A.r[(size_t)(jp + 3) * stride + c.idx] = rl;
+    } else if (T::CHEB) {
+      // three-term recurrence of the Chebyshev-accelerated operator (reference lib/qudaQKXTM_Deflation.cpp:1040-1056):
+      // out = d1 (M^dag M y) + d2 y + d3 r, with z = M^dag M y formed above; out may alias r (site-local)
+      const VecT<F> yu = A.y[(size_t)jp * stride + c.idx], yl = A.y[(size_t)(jp + 3) * stride + c.idx];
+      ou.a = A.e.d1 * ou.a + A.e.d2 * yu.a; ou.b = A.e.d1 * ou.b + A.e.d2 * yu.b;
+      ou.c = A.e.d1 * ou.c + A.e.d2 * yu.c; ou.d = A.e.d1 * ou.d + A.e.d2 * yu.d;
+      ol.a = A.e.d1 * ol.a + A.e.d2 * yl.a; ol.b = A.e.d1 * ol.b + A.e.d2 * yl.b;
+      ol.c = A.e.d1 * ol.c + A.e.d2 * yl.c; ol.d = A.e.d1 * ol.d + A.e.d2 * yl.d;
+      if (A.e.d3 != (F)0) {
+        const VecT<F> ru = A.r[(size_t)jp * stride + c.idx], rl = A.r[(size_t)(jp + 3) * stride + c.idx];
+        ou.a += A.e.d3 * ru.a; ou.b += A.e.d3 * ru.b; ou.c += A.e.d3 * ru.c; ou.d += A.e.d3 * ru.d;
+        ol.a += A.e.d3 * rl.a; ol.b += A.e.d3 * rl.b; ol.c += A.e.d3 * rl.c; ol.d += A.e.d3 * rl.d;
       }
-      A.out[(size_t)j * stride + c.idx] = zv;
+      A.out[(size_t)jp * stride + c.idx] = ou; A.out[(size_t)(jp + 3) * stride + c.idx] = ol;
+    } else {
+      A.out[(size_t)jp * stride + c.idx] = ou; A.out[(size_t)(jp + 3) * stride + c.idx] = ol;
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 6; j++) A.out[(size_t)j * stride + c.idx] = pack_vec(o, j);
+#if defined(__CUDA_ARCH__)
+    if (T::XTERM) asm volatile("" ::: "memory");
+#endif
   }
   return red;
 }

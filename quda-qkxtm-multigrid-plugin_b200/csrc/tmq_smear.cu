@@ -8,10 +8,13 @@
 // of the whole vector.  Here:
 //   * the time direction does not hop, so time slices are independent: a T-sharded lattice needs NO exchange at all
 //     (z-sharding is refused for this entry point), and
-//   * the sweep order is (block of time slices) outer, (smearing step) inner: the ping-pong vectors and the three spatial
-//     link directions of a block of slices (90 MB for one 48^3 slice in fp64) stay resident in the 126 MB L2 across
-//     the nsmear steps, so HBM sees the fields once instead of nsmear times.  The block size is chosen from the L2
-//     size; block = all slices gives the plain streaming order.
+//   * optionally (TMQ_OPT_SMEAR_BLOCK_T) the sweep order is (block of time slices) outer, (smearing step) inner, so that
+//     the ping-pong vectors and the three spatial link directions of a block (90 MB for one 48^3 slice in fp64) stay
+//     resident in the 126 MB L2 across the nsmear steps.  MEASURED on B200 at 48^3x96 (profiles/r03_smear_bench.jsonl):
+//     the blocked order is SLOWER (1.95 ms vs 1.67 ms per step in fp64): one slice is only 864 CTAs (1.2 waves) and the
+//     4800 short launches expose launch gaps and tails that outweigh the L2 hit rate.  The default is therefore the
+//     plain streaming order (0.79 of the measured HBM peak); a persistent per-block kernel with grid syncs is the
+//     way to make the L2 residency pay and is left for a later round.
 // HBM-bound streaming stencil: algorithmic bytes per site and step = (24 in + 24 out + 3*18 links) * sizeof(real)
 // = 816 B in fp64; no tensor cores.
 #include <cuda_runtime.h>
@@ -61,7 +64,7 @@ __device__ __forceinline__ void su3_acc(F (&acc)[12][2], const CplxT<F> *__restr
 }
 
 template <typename F>
-__global__ void __launch_bounds__(SMEAR_BLOCK) gauss_smear_kernel(CplxT<F> *__restrict__ out, const CplxT<F> *__restrict__ in,
+__global__ void __launch_bounds__(SMEAR_BLOCK, (sizeof(F) == 8 ? 4 : 8)) gauss_smear_kernel(CplxT<F> *__restrict__ out, const CplxT<F> *__restrict__ in,
                                                                  const CplxT<F> *__restrict__ gauge, SmearGeom g, F alpha, F normalize) {
   const uint32_t e = blockIdx.x * SMEAR_BLOCK + threadIdx.x;
   const uint32_t nsl = (uint32_t)(g.X[0] * g.X[1] * g.X[2]);
@@ -113,14 +116,7 @@ int smear_run(tmq_ctx *c, void *a, void *b, const void *gauge, int prec, int nsm
   g.dX = make_fastdiv((uint32_t)g.X[0]); g.dY = make_fastdiv((uint32_t)g.X[1]); g.dZ = make_fastdiv((uint32_t)g.X[2]);
   g.V = (size_t)2 * c->g.Vh;
   const int T = g.X[3];
-  if (block_t <= 0) {
-    // largest block of slices whose two vectors + three link directions fit in ~70% of L2
-    int l2 = 0;
-    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, c->device);
-    const double per_slice = (double)g.X[0] * g.X[1] * g.X[2] * (24.0 + 24.0 + 54.0) * prec;
-    block_t = (int)(0.7 * (double)l2 / per_slice);
-    if (block_t < 1) block_t = T;        // a slice does not fit: plain streaming order
-  }
+  if (block_t <= 0) block_t = T;        // default: plain streaming order (measured faster, see the header comment)
   if (block_t > T) block_t = T;
   for (int t0 = 0; t0 < T; t0 += block_t) {
     g.t0 = t0; g.nt = (t0 + block_t <= T) ? block_t : T - t0;

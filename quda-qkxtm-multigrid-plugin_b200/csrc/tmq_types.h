@@ -161,7 +161,7 @@ template <typename F> struct DslashArgs {
   int red_slot;            // where the finished sum goes
   int red_accum;           // 1: add to the slot (second and later launches of a split application)
   int alpha_num, alpha_den; // EPI_CG4: alpha = scal[alpha_num] / scal[alpha_den]
-  int prefetch;            // 1: L2-prefetch the epilogue operands (x, r) before the hop
+  int prefetch;            // unused (the L2-prefetch experiment was removed: no gain, and it cost the 4th resident CTA)
 };
 
 }  // namespace tmq
