@@ -181,6 +181,7 @@ public:
   void downloadFromCuda(ColorSpinorField *cudaVector, bool isEv = false);  // lib/qudaQKXTM_Vector.cpp:430-432
   void gaussianSmearing(QKXTM_Vector<Float> &vecIn, QKXTM_Gauge<Float> &gaugeAPE);   // lib/qudaQKXTM_Vector.cpp:386-421 (vecIn is clobbered, as in the reference)
   void scaleVector(double a);
+  void write(char *filename);                      // "DiracFermion_Sink" LIME file from h_elem (AoS), lib/qudaQKXTM_Vector.cpp:510-702
   void castDoubleToFloat(QKXTM_Vector<double> &vecIn);
   void castFloatToDouble(QKXTM_Vector<float> &vecIn);
   double norm2Host();
@@ -271,5 +272,12 @@ void calc_loops_solve(double *h_solution, double *h_source, QudaInvertParam *par
 // vector in the plug-in's AoS order [x_lex][s][c][ri] -> packVector/loadVector/uploadToCuda(parity isEven) ->
 // M_pc^dag M_pc -> downloadFromCuda/unloadVector/unpackVector; the other parity comes back zero-filled.
 void ApplyMdagM(double *h_out, double *h_in, QudaInvertParam *param, bool isEven);
+
+// ---- configuration I/O (include/QKXTM_read_conf.h:816-848) -----------------------------------------------------------
+// reads this rank's sub-block of an ILDG / LIME configuration into the QDP even-odd host order of loadGaugeQuda and sets
+// param->X to the local extents; no boundary condition is applied (call applyBoundaryCondition, as the drivers do)
+void readLimeGauge(void **gauge, char *fname, QudaGaugeParam *param, QudaInvertParam *inv_param, int gridSize[4]);
+void readLimeGaugeSmeared(void **gauge, char *fname, QudaGaugeParam *param, QudaInvertParam *inv_param, int gridSize[4]);
+void applyBoundaryCondition(void **gauge, int Vh, QudaGaugeParam *gauge_param);
 
 #endif

@@ -25,6 +25,24 @@ void tmq_fieldgen_spinor_gaussian(double *out, const int localX[4], const int gr
 void tmq_fieldgen_spinor_z4(double *out, const int localX[4], const int grid[4], const int coord[4],
                             unsigned long long seed, int eo_order);
 
+
+/* ---- on-disk formats (host/tmq_lime.cpp): ILDG / LIME gauge configurations (include/QKXTM_read_conf.h:107-400) and the
+ * "DiracFermion_Sink" propagator files of QKXTM_Vector::write (lib/qudaQKXTM_Vector.cpp:510-702).  Every function returns
+ * 0 on success; tmq_lime_last_error() gives the text.  Each rank reads / writes its own sub-block with pread / pwrite
+ * (no c-lime, no MPI-IO); when writing, the rank at coordinate (0,0,0,0) creates the file and must be called first.   */
+const char *tmq_lime_last_error(void);
+int tmq_lime_gauge_info(const char *fname, int globalX[4], int *precision_bits, double *kappa, double *mu);
+/* gauge[mu]: QDP even-odd host order, 2*Vh*18 doubles; no boundary condition is applied (QKXTM_read_conf.h:395-397)      */
+int tmq_lime_read_gauge(const char *fname, double *const gauge[4], const int localX[4], const int grid[4], const int coord[4]);
+int tmq_lime_write_gauge(const char *fname, const double *const gauge[4], const int localX[4], const int grid[4],
+                         const int coord[4], double kappa, double mu);
+/* h_aos: the plug-in's host vector order [x_lex][spin][colour][re,im] (local sub-lattice), prec = 8 | 4                  */
+int tmq_lime_write_vector(const char *fname, const void *h_aos, int prec, const int localX[4], const int grid[4], const int coord[4]);
+int tmq_lime_read_vector(const char *fname, void *h_aos, int prec, const int localX[4], const int grid[4], const int coord[4]);
+/* applyGaugeFieldScaling restricted to what the path uses (qkxtm/QKXTM_util.cpp:682-725 with anisotropy 1): multiplies
+ * U_t on the last GLOBAL time slice by t_boundary (-1: anti-periodic).  gauge[mu]: QDP even-odd host order.               */
+void tmq_apply_t_boundary(double *const gauge[4], const int localX[4], const int grid[4], const int coord[4], int t_boundary);
+
 #ifdef __cplusplus
 }
 #endif

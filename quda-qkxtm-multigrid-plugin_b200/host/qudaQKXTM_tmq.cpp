@@ -3,6 +3,7 @@
 // fields happens here except the reference's own host-side repacking loops (packVector, packGauge, ...),
 // which the reference also runs on the CPU; everything else is a call into the CUDA library.
 #include "../../include/qudaQKXTM_tmq.h"
+#include "../../include/tmq_host.h"
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -389,6 +390,10 @@ template <typename Float> void QKXTM_Vector<Float>::gaussianSmearing(QKXTM_Vecto
   // needed: the hop is 3-dimensional and the lattice is sharded along T
   TMQ_OK(tmq_qkxtm_gauss_smear(G.ctx, this->d_elem, vecIn.D_elem(), gaugeAPE.D_elem(), (int)sizeof(Float), G.nsmearGauss, G.alphaGauss));
 }
+template <typename Float> void QKXTM_Vector<Float>::write(char *filename) {
+  // h_elem holds the host AoS vector (after download()), as in the reference (lib/qudaQKXTM_Vector.cpp:676-690)
+  if (tmq_lime_write_vector(filename, this->h_elem, (int)sizeof(Float), G.localL, G.grid, G.coord)) errorQuda("%s", tmq_lime_last_error());
+}
 template <typename Float> void QKXTM_Vector<Float>::scaleVector(double a) { TMQ_OK(tmq_qkxtm_scale(G.ctx, this->d_elem, (int)sizeof(Float), a)); }
 template <typename Float> void QKXTM_Vector<Float>::castDoubleToFloat(QKXTM_Vector<double> &in) {
   if (sizeof(Float) != 4) errorQuda("castDoubleToFloat needs a float vector");
@@ -585,6 +590,33 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
   delete x;
   delete b;
   printfQuda("...Done (%f sec)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
+}
+
+void readLimeGauge(void **gauge, char *fname, QudaGaugeParam *param, QudaInvertParam *inv_param, int gridSize[4]) {
+  if (!gauge || !fname || !param || !gridSize) errorQuda("null argument");
+  if (param->cpu_prec != QUDA_DOUBLE_PRECISION) errorQuda("Dont support reading confs lime single precision");
+  int GX[4], prec = 0;
+  double kap = 0, mu = 0;
+  if (tmq_lime_gauge_info(fname, GX, &prec, &kap, &mu)) errorQuda("%s", tmq_lime_last_error());
+  if (inv_param) {
+    printfQuda("Kappa given is : %.8f \t Kappa conf is : %.8f \t check that they agree\n", inv_param->kappa, kap);
+    printfQuda("Mu given is : %f \t Mu conf is : %f \t may disagree for heavy quark\n", inv_param->mu, mu);
+  }
+  printfQuda("Precision:\t%i bit\n", prec);
+  for (int d = 0; d < 4; d++) {
+    if (gridSize[d] < 1 || GX[d] % gridSize[d]) errorQuda("lattice extent %d is not divisible by the process grid in dimension %d", GX[d], d);
+    param->X[d] = GX[d] / gridSize[d];                                                    // QKXTM_read_conf.h:190-207
+  }
+  printfQuda("Volume:   \t%ix%ix%ix%i\nSubvolume:\t%ix%ix%ix%i\n", GX[0], GX[1], GX[2], GX[3], param->X[0], param->X[1], param->X[2], param->X[3]);
+  if (tmq_lime_read_gauge(fname, (double *const *)gauge, param->X, gridSize, G.coord)) errorQuda("%s", tmq_lime_last_error());
+}
+void readLimeGaugeSmeared(void **gauge, char *fname, QudaGaugeParam *param, QudaInvertParam *inv_param, int gridSize[4]) {
+  readLimeGauge(gauge, fname, param, inv_param, gridSize);      // same record layout (QKXTM_read_conf.h:401-675)
+}
+void applyBoundaryCondition(void **gauge, int Vh, QudaGaugeParam *gauge_param) {
+  if (gauge_param->cpu_prec != QUDA_DOUBLE_PRECISION) errorQuda("boundary condition application implement only for double precision");
+  if ((long long)Vh * 2 != (long long)gauge_param->X[0] * gauge_param->X[1] * gauge_param->X[2] * gauge_param->X[3]) errorQuda("Vh does not match the lattice");
+  tmq_apply_t_boundary((double *const *)gauge, gauge_param->X, G.grid, G.coord, (int)gauge_param->t_boundary);
 }
 
 void calc_loops_solve(double *h_solution, double *h_source, QudaInvertParam *param, qudaQKXTMinfo info) {

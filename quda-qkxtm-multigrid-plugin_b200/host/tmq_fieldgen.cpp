@@ -144,4 +144,17 @@ void tmq_fieldgen_spinor_z4(double *out, const int localX[4], const int grid[4],
   }
 }
 
+// applyGaugeFieldScaling with anisotropy 1 (qkxtm/QKXTM_util.cpp:682-725): only the anti-periodic sign on U_t(T-1) remains
+void tmq_apply_t_boundary(double *const gauge[4], const int localX[4], const int grid[4], const int coord[4], int t_boundary) {
+  if (t_boundary != -1 || coord[3] != grid[3] - 1) return;
+  const long long Vh = (long long)localX[0] * localX[1] * localX[2] * localX[3] / 2;
+  const long long slice_h = (long long)localX[0] * localX[1] * localX[2] / 2;
+  // the last local time slice occupies the last slice_h checkerboard sites of each parity block
+  for (int par = 0; par < 2; par++)
+    for (long long i = Vh - slice_h; i < Vh; i++) {
+      double *u = gauge[3] + (par * Vh + i) * 18;
+      for (int k = 0; k < 18; k++) u[k] = -u[k];
+    }
+}
+
 }  // extern "C"

@@ -370,6 +370,13 @@ def load_host():
         H.tmq_fieldgen_unit_gauge_qdp.argtypes = [C.POINTER(dp), ip, ip, ip, C.c_int]
         H.tmq_fieldgen_spinor_gaussian.argtypes = [dp, ip, ip, ip, C.c_ulonglong, C.c_int]
         H.tmq_fieldgen_spinor_z4.argtypes = [dp, ip, ip, ip, C.c_ulonglong, C.c_int]
+        H.tmq_lime_last_error.restype = C.c_char_p
+        H.tmq_lime_gauge_info.argtypes = [C.c_char_p, ip, ip, dp, dp]
+        H.tmq_lime_read_gauge.argtypes = [C.c_char_p, C.POINTER(dp), ip, ip, ip]
+        H.tmq_lime_write_gauge.argtypes = [C.c_char_p, C.POINTER(dp), ip, ip, ip, C.c_double, C.c_double]
+        H.tmq_lime_write_vector.argtypes = [C.c_char_p, C.c_void_p, C.c_int, ip, ip, ip]
+        H.tmq_lime_read_vector.argtypes = [C.c_char_p, C.c_void_p, C.c_int, ip, ip, ip]
+        H.tmq_apply_t_boundary.argtypes = [C.POINTER(dp), ip, ip, ip, C.c_int]
         _hostlib = H
     return _hostlib
 
@@ -398,3 +405,46 @@ def gen_spinor(localX, kind="gaussian", seed=None, grid=(1, 1, 1, 1), coord=(0, 
     else:
         raise ValueError(kind)
     return out
+
+
+# ---- on-disk formats (host/tmq_lime.cpp) ---------------------------------------------------------------------------
+def _hck(rc):
+    if rc != 0:
+        raise TmqError(load_host().tmq_lime_last_error().decode())
+
+
+def _g4(g):
+    return (C.POINTER(C.c_double) * 4)(*[g[mu].ctypes.data_as(C.POINTER(C.c_double)) for mu in range(4)])
+
+
+def lime_gauge_info(fname):
+    X = (C.c_int * 4)(); prec = C.c_int(0); k = C.c_double(0); m = C.c_double(0)
+    _hck(load_host().tmq_lime_gauge_info(fname.encode(), X, C.byref(prec), C.byref(k), C.byref(m)))
+    return dict(X=tuple(X), precision=prec.value, kappa=k.value, mu=m.value)
+
+
+def lime_read_gauge(fname, localX, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0)):
+    g = np.empty((4, int(np.prod(localX)), 3, 3, 2), dtype=np.float64)
+    _hck(load_host().tmq_lime_read_gauge(fname.encode(), _g4(g), _i4(localX), _i4(grid), _i4(coord)))
+    return g
+
+
+def lime_write_gauge(fname, gauge_qdp, localX, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0), kappa=0.0, mu=0.0):
+    g = np.ascontiguousarray(gauge_qdp, dtype=np.float64)
+    _hck(load_host().tmq_lime_write_gauge(fname.encode(), _g4(g), _i4(localX), _i4(grid), _i4(coord), kappa, mu))
+
+
+def lime_write_vector(fname, aos, localX, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0)):
+    a = np.ascontiguousarray(aos)
+    prec = 8 if a.dtype == np.float64 else 4
+    _hck(load_host().tmq_lime_write_vector(fname.encode(), a.ctypes.data, prec, _i4(localX), _i4(grid), _i4(coord)))
+
+
+def lime_read_vector(fname, localX, dtype=np.float64, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0)):
+    out = np.empty((int(np.prod(localX)), 4, 3, 2), dtype=dtype)
+    _hck(load_host().tmq_lime_read_vector(fname.encode(), out.ctypes.data, out.dtype.itemsize, _i4(localX), _i4(grid), _i4(coord)))
+    return out
+
+
+def apply_t_boundary(gauge_qdp, localX, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0), t_boundary=-1):
+    load_host().tmq_apply_t_boundary(_g4(gauge_qdp), _i4(localX), _i4(grid), _i4(coord), t_boundary)

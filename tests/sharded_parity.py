@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--grid", type=int, nargs=4, default=[1, 1, 1, 2])
     ap.add_argument("--recon", type=int, default=12)
     ap.add_argument("--p2p", type=int, default=2)
+    ap.add_argument("--amin", type=float, default=0.2, help="lower edge of the Chebyshev window (just above the wanted eigenvalues)")
+    ap.add_argument("--eig", type=int, default=1, help="also run the (slower) eigensolver / deflation check")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -84,6 +86,31 @@ def main():
     e4 = lu.rel_l2(x.get(), lu.local_from_global_eo(xr, X, grid, coord)[:Vh])
     if info4["true_res"] > 1.05e-9 or e4 > 1e-7:
         fails.append(("cg-mixed", info4, e4))
+    # eigensolver layer on the sharded lattice: Chebyshev filter vs the oracle recurrence, a few eigenpairs vs ARPACK on
+    # the global oracle operator, and the deflation projector built from them (coefficients all-reduced over ranks)
+    from oracle.oracle import poly_operator, eigs_reference
+    cplx = lambda v: np.ascontiguousarray(v[..., 0] + 1j * v[..., 1]).ravel()
+    real = lambda v: np.ascontiguousarray(np.stack([v.real, v.imag], axis=-1).reshape(Vh_g, 4, 3, 2))
+    A = lambda v: cplx(o.mdagm(gauge_g, real(v), KAPPA, MU, 0))
+    slab = lambda v: lu.local_from_global_eo(np.concatenate([real(v), np.zeros((Vh_g, 4, 3, 2))]), X, grid, coord)[:Vh]
+    pin, pout = ctx.spinor(8), ctx.spinor(8)
+    pin.set(loc[:Vh])
+    ctx.poly_mdagm(pout, pin, 12, 0.3, 2.0)
+    e = lu.rel_l2(pout.get(), slab(poly_operator(A, cplx(even_g), 12, 0.3, 2.0)))
+    if not e < 1e-12:
+        fails.append(("cheb", e))
+    if a.eig:
+        nev, nkv = 4, 24
+        lam_ref, U_ref = eigs_reference(A, 12 * Vh_g, nev, nkv, "SR", poly=(20, a.amin, 2.0), tol=1e-12)
+        es = ctx.eigset(nkv + 1)
+        r = ctx.eigensolve(es, nev, nkv, poly_deg=20, amin=a.amin, amax=2.0, tol=1e-11, max_restarts=500, which=0, seed=9)
+        if r["nconv"] != nev or not np.allclose(r["evals"], lam_ref, rtol=1e-9) or r["resid"].max() > 1e-8:
+            fails.append(("eig", r, lam_ref))
+        ctx.deflate(pout, pin, es, r["evals"], nev)
+        want = U_ref @ ((U_ref.conj().T @ cplx(even_g)) / lam_ref)
+        e = lu.rel_l2(pout.get(), slab(want))
+        if not e < 1e-7:
+            fails.append(("deflate", e))
     n2 = ctx.norm2(b)
     if abs(n2 - np.sum(even_g * even_g)) > 1e-12 * n2:
         fails.append(("norm2-allreduce", n2))
