@@ -57,6 +57,7 @@ typedef struct QudaGaugeParam_s {       // fields set at qkxtm/Calc_Loops.cpp:18
 
 typedef struct QudaInvertParam_s {      // fields read / written on the path
   double kappa, mu, mass;
+  double clover_coeff;                 // csw * kappa (qkxtm/MG_Bench.cpp:249), used by loadCloverQuda
   QudaDslashType dslash_type;
   QudaTwistFlavorType twist_flavor;
   QudaMatPCType matpc_type;
@@ -89,6 +90,10 @@ void initCommsGridQuda(int nDim, const int *dims, void *func, void *fdata);   //
 void initQuda(int device);                                                     // qkxtm/Calc_Loops.cpp:753
 void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param);                      // qkxtm/Calc_Loops.cpp:759 (void *gauge[4], QDP order)
 void freeGaugeQuda(void);
+// loadCloverQuda(NULL, NULL, &inv_param) (qkxtm/MG_Bench.cpp:605-608): the clover field is BUILT on the device from the resident
+// gauge field with inv_param->clover_coeff; host clover fields (h_clover / h_clovinv != NULL) are not supported
+void loadCloverQuda(void *h_clover, void *h_clovinv, QudaInvertParam *inv_param);
+void freeCloverQuda(void);
 void endQuda(void);
 // host spinors: full lattice, even-odd site order [even Vh | odd Vh][spin][colour][re,im], double
 void invertQuda(void *h_x, void *h_b, QudaInvertParam *param);

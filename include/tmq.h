@@ -102,6 +102,13 @@ tmq_spinor *tmq_spinor_odd(tmq_spinor *full);
 /* ---- operator: replaces createDirac + Dirac::{Dslash,M,Mdag,MdagM,prepare,reconstruct}
  *      (lib/qudaQKXTM_interface.cpp:1886-1889,2020-2041; lib/qudaQKXTM_Deflation.cpp:153-155,217) -------- */
 int tmq_op_set(tmq_ctx *, double kappa, double mu, int matpc);
+/* twisted-clover (dslash_type = twisted-clover, qkxtm/MG_Bench.cpp:243-251,605-608): replaces loadCloverQuda(NULL, NULL,
+ * &inv_param), which builds the clover field on the device from the resident gauge field with inv_param.clover_coeff =
+ * csw * kappa.  Afterwards every operator entry point uses A = C + i (2 kappa mu) gamma5 with C = 1 + i clover_coeff
+ * sum_{mu<nu} sigma_munu F_munu in place of the constant twist; (C + i a gamma5)^-1 is rebuilt whenever tmq_op_set changes
+ * kappa or mu.  Single rank in this round.  tmq_clover_free returns to plain twisted mass.                            */
+int tmq_clover_load(tmq_ctx *, double clover_coeff);
+int tmq_clover_free(tmq_ctx *);
 /* out(parity) = D in or D^dag in : the bare hop (a4)                                                      */
 int tmq_dslash(tmq_spinor *out, const tmq_spinor *in, int out_parity, int dagger);
 /* out = A^-1 D in (dagger = 0) / A^-dag D^dag in (dagger = 1); with x != NULL: out = x + k * (that)         */

@@ -74,6 +74,9 @@ def lib():
                                    C.c_int, dp, dp]
         L.orc_cg_mdagm.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
+        L.orc_clover_compute.argtypes = [dp, dpp, C.c_double]
+        L.orc_set_clover.argtypes = [dp]
+        L.orc_site_A.argtypes = [dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -101,6 +104,7 @@ class Oracle:
         self.X = tuple(int(x) for x in X)
         self.V = int(np.prod(self.X)); self.Vh = self.V // 2
         self.L.orc_set_lattice((C.c_int * 4)(*self.X))
+        self.L.orc_set_clover(None)           # the C side keeps globals: a new Oracle starts without a clover term
         self.set_gamma(gamma_ukqcd() if gamma is None else gamma)
 
     def set_gamma(self, g):
@@ -160,6 +164,19 @@ class Oracle:
         return x, it, tr.value, hist[: it + 1]
 
     def num_threads(self): return self.L.orc_num_threads()
+
+    # -- twisted-clover: after set_clover every operator above uses A = C + i a g5 (set_clover(None) switches back)
+    def clover_compute(self, gauge, coeff):
+        clov = np.empty((2 * self.Vh, 12, 12, 2), dtype=np.float64)
+        self.L.orc_clover_compute(_dp(clov), _gpp(gauge), float(coeff))
+        return clov
+
+    def set_clover(self, clov):
+        self._clov_keep = clov          # the C side keeps the pointer
+        self.L.orc_set_clover(_dp(clov) if clov is not None else None)
+
+    def site_A(self, psi, kappa, mu, parity, dagger=0, inverse=0):
+        out = self._par(); self.L.orc_site_A(_dp(out), _dp(psi), dagger, kappa, mu, inverse, parity); return out
 
 
 # ---- eigensolver restatements ----------------------------------------------------------------

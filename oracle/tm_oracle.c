@@ -22,6 +22,7 @@ static int V, Vh;
 /* projector table P[2mu + s][row][col][re,im]; 2mu = 1-gamma_mu, 2mu+1 = 1+gamma_mu */
 static double PROJ[8][4][4][2];
 static double G5[4][4][2];
+static double GAM[4][4][4][2];   /* gamma_mu as set by orc_set_gamma (sigma_munu of the clover term) */
 
 int orc_num_threads(void) {
 #ifdef _OPENMP
@@ -89,6 +90,7 @@ static void cmat_mul(double c[4][4][2], double a[4][4][2], double b[4][4][2]) {
 void orc_set_gamma(const double g[4][4][4][2]) {
   double gm[4][4][4][2];
   memcpy(gm, g, sizeof(gm));
+  memcpy(GAM, g, sizeof(GAM));
   for (int mu = 0; mu < 4; mu++)
     for (int i = 0; i < 4; i++)
       for (int j = 0; j < 4; j++) {
@@ -305,17 +307,167 @@ void orc_twist_gamma5(double *out, const double *in, int daggerBit, double kappa
   }
 }
 
+/* ---- twisted-clover: A = C + i a gamma5 with the site-dependent clover matrix
+ * C(x) = 1 + i coeff sum_{mu<nu} sigma_munu (x) F_munu(x), sigma_munu = (i/2)[gamma_mu, gamma_nu],
+ * F_munu = (Q_munu - Q_munu^dag)/8, Q_munu = sum of the four plaquette leaves around x (Sheikholeslami-Wohlert term
+ * D_W + csw (i/4) sigma_munu F_munu divided by 4 + m0; coeff = csw kappa = inv_param.clover_coeff of
+ * qkxtm/MG_Bench.cpp:243-251).  The oracle keeps C as a dense 12x12 complex matrix per site, in whatever gamma basis is
+ * set, [parity][cb][12][12][re,im]; no chiral-basis shortcut, inverse by Gaussian elimination. --------------------- */
+static const double *CLOV = NULL;
+
+void orc_set_clover(const double *clov) { CLOV = clov; }
+
+void orc_clover_compute(double *clov, double *gauge[4], double coeff) {
+  /* sigma_munu for the 6 planes */
+  double sig[6][4][4][2];
+  int plane = 0;
+  for (int mu = 0; mu < 4; mu++)
+    for (int nu = mu + 1; nu < 4; nu++, plane++) {
+      double ab[4][4][2], ba[4][4][2];
+      cmat_mul(ab, GAM[mu], GAM[nu]);
+      cmat_mul(ba, GAM[nu], GAM[mu]);
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+          double re = ab[i][j][0] - ba[i][j][0], im = ab[i][j][1] - ba[i][j][1];
+          sig[plane][i][j][0] = -0.5 * im;   /* (i/2)(re + i im) */
+          sig[plane][i][j][1] = 0.5 * re;
+        }
+    }
+#pragma omp parallel for
+  for (int Y = 0; Y < V; Y++) {
+    double *C = clov + ((long)orc_odd_bit(Y) * Vh + Y / 2) * 288;
+    for (int k = 0; k < 288; k++) C[k] = 0.0;
+    for (int k = 0; k < 12; k++) C[(k * 12 + k) * 2] = 1.0;
+    int pl = 0;
+    for (int mu = 0; mu < 4; mu++)
+      for (int nu = mu + 1; nu < 4; nu++, pl++) {
+        int xpm = shift_lex(Y, mu, 1), xpn = shift_lex(Y, nu, 1), xmm = shift_lex(Y, mu, -1), xmn = shift_lex(Y, nu, -1);
+        int xmm_pn = shift_lex(xmm, nu, 1), xmm_mn = shift_lex(xmm, nu, -1), xpm_mn = shift_lex(xpm, nu, -1);
+        double Q[18], a[18], b[18], t[18], one[18] = {1, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+        /* leaf 1: U_mu(x) U_nu(x+mu) U_mu(x+nu)^dag U_nu(x)^dag */
+        su3_mm(a, link_at(gauge, mu, Y), link_at(gauge, nu, xpm));
+        su3_mmd(a, a, link_at(gauge, mu, xpn));
+        su3_mmd(Q, a, link_at(gauge, nu, Y));
+        /* leaf 2: U_nu(x) U_mu(x-mu+nu)^dag U_nu(x-mu)^dag U_mu(x-mu) */
+        su3_mmd(a, link_at(gauge, nu, Y), link_at(gauge, mu, xmm_pn));
+        su3_mmd(a, a, link_at(gauge, nu, xmm));
+        su3_mm(t, a, link_at(gauge, mu, xmm));
+        for (int k = 0; k < 18; k++) Q[k] += t[k];
+        /* leaf 3: U_mu(x-mu)^dag U_nu(x-mu-nu)^dag U_mu(x-mu-nu) U_nu(x-nu) */
+        su3_mmd(a, one, link_at(gauge, mu, xmm));
+        su3_mmd(a, a, link_at(gauge, nu, xmm_mn));
+        su3_mm(a, a, link_at(gauge, mu, xmm_mn));
+        su3_mm(t, a, link_at(gauge, nu, xmn));
+        for (int k = 0; k < 18; k++) Q[k] += t[k];
+        /* leaf 4: U_nu(x-nu)^dag U_mu(x-nu) U_nu(x+mu-nu) U_mu(x)^dag */
+        su3_mmd(a, one, link_at(gauge, nu, xmn));
+        su3_mm(a, a, link_at(gauge, mu, xmn));
+        su3_mm(a, a, link_at(gauge, nu, xpm_mn));
+        su3_mmd(t, a, link_at(gauge, mu, Y));
+        for (int k = 0; k < 18; k++) Q[k] += t[k];
+        /* F = (Q - Q^dag)/8 */
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) {
+            b[(i * 3 + j) * 2] = 0.125 * (Q[(i * 3 + j) * 2] - Q[(j * 3 + i) * 2]);
+            b[(i * 3 + j) * 2 + 1] = 0.125 * (Q[(i * 3 + j) * 2 + 1] + Q[(j * 3 + i) * 2 + 1]);
+          }
+        /* C += i coeff sigma (x) F */
+        for (int s = 0; s < 4; s++)
+          for (int sp = 0; sp < 4; sp++) {
+            double sr = sig[pl][s][sp][0], si = sig[pl][s][sp][1];
+            if (sr == 0.0 && si == 0.0) continue;
+            for (int i = 0; i < 3; i++)
+              for (int j = 0; j < 3; j++) {
+                double fr = b[(i * 3 + j) * 2], fi = b[(i * 3 + j) * 2 + 1];
+                double pr = sr * fr - si * fi, pi = sr * fi + si * fr;
+                double *e = C + ((s * 3 + i) * 12 + (sp * 3 + j)) * 2;
+                e[0] -= coeff * pi;
+                e[1] += coeff * pr;
+              }
+          }
+      }
+  }
+}
+
+/* out = (C + i a g5) in, its inverse, and their daggers on `nsites` sites of the parity block `parity`
+ * (with CLOV == NULL: the plain twist).  C is hermitian, so the dagger only flips the sign of a. */
+static void site_A(double *out, const double *in, int daggerBit, double kappa, double mu, int inverse, int parity, int nsites) {
+  if (!CLOV) { orc_twist_gamma5(out, in, daggerBit, kappa, mu, inverse, nsites); return; }
+  double a = 2.0 * kappa * mu;
+  if (daggerBit) a = -a;
+#pragma omp parallel for
+  for (int i = 0; i < nsites; i++) {
+    const double *C = CLOV + ((long)parity * Vh + i) * 288;
+    double M[12][13][2];
+    for (int r = 0; r < 12; r++) {
+      for (int c = 0; c < 12; c++) {
+        /* i a g5 : g5[s][s'] delta_cc' */
+        int s = r / 3, sp = c / 3;
+        double gr = (r % 3 == c % 3) ? G5[s][sp][0] : 0.0, gi = (r % 3 == c % 3) ? G5[s][sp][1] : 0.0;
+        M[r][c][0] = C[(r * 12 + c) * 2] - a * gi;
+        M[r][c][1] = C[(r * 12 + c) * 2 + 1] + a * gr;
+      }
+      M[r][12][0] = in[(long)i * SS + 2 * r]; M[r][12][1] = in[(long)i * SS + 2 * r + 1];
+    }
+    double y[12][2];
+    if (!inverse) {
+      for (int r = 0; r < 12; r++) {
+        double re = 0, im = 0;
+        for (int c = 0; c < 12; c++) {
+          re += M[r][c][0] * M[c][12][0] - M[r][c][1] * M[c][12][1];
+          im += M[r][c][0] * M[c][12][1] + M[r][c][1] * M[c][12][0];
+        }
+        y[r][0] = re; y[r][1] = im;
+      }
+    } else {
+      /* Gaussian elimination with partial pivoting on [M | in] */
+      for (int p = 0; p < 12; p++) {
+        int piv = p; double best = M[p][p][0] * M[p][p][0] + M[p][p][1] * M[p][p][1];
+        for (int r = p + 1; r < 12; r++) {
+          double v2 = M[r][p][0] * M[r][p][0] + M[r][p][1] * M[r][p][1];
+          if (v2 > best) { best = v2; piv = r; }
+        }
+        if (piv != p)
+          for (int c = 0; c < 13; c++) {
+            double tr = M[p][c][0], ti = M[p][c][1];
+            M[p][c][0] = M[piv][c][0]; M[p][c][1] = M[piv][c][1]; M[piv][c][0] = tr; M[piv][c][1] = ti;
+          }
+        double ir = M[p][p][0] / best, ii = -M[p][p][1] / best;
+        for (int c = p; c < 13; c++) {
+          double xr = M[p][c][0], xi = M[p][c][1];
+          M[p][c][0] = xr * ir - xi * ii; M[p][c][1] = xr * ii + xi * ir;
+        }
+        for (int r = 0; r < 12; r++) {
+          if (r == p) continue;
+          double fr = M[r][p][0], fi = M[r][p][1];
+          for (int c = p; c < 13; c++) {
+            M[r][c][0] -= fr * M[p][c][0] - fi * M[p][c][1];
+            M[r][c][1] -= fr * M[p][c][1] + fi * M[p][c][0];
+          }
+        }
+      }
+      for (int r = 0; r < 12; r++) { y[r][0] = M[r][12][0]; y[r][1] = M[r][12][1]; }
+    }
+    for (int r = 0; r < 12; r++) { out[(long)i * SS + 2 * r] = y[r][0]; out[(long)i * SS + 2 * r + 1] = y[r][1]; }
+  }
+}
+
+/* public form of the site operator (tests) */
+void orc_site_A(double *out, const double *in, int daggerBit, double kappa, double mu, int inverse, int parity) {
+  site_A(out, in, daggerBit, kappa, mu, inverse, parity, Vh);
+}
+
 /* [upstream-shape: tm_dslash] */
 void orc_tm_dslash(double *res, double *gauge[4], const double *in, double kappa, double mu,
                    int oddBit, int daggerBit) {
   if (daggerBit) {
     double *tmp = (double *)malloc((size_t)Vh * SS * sizeof(double));
-    orc_twist_gamma5(tmp, in, daggerBit, kappa, mu, 1, Vh);
+    site_A(tmp, in, daggerBit, kappa, mu, 1, 1 - oddBit, Vh);
     orc_dslash(res, gauge, tmp, oddBit, daggerBit);
     free(tmp);
   } else {
     orc_dslash(res, gauge, in, oddBit, daggerBit);
-    orc_twist_gamma5(res, res, daggerBit, kappa, mu, 1, Vh);
+    site_A(res, res, daggerBit, kappa, mu, 1, oddBit, Vh);
   }
 }
 
@@ -335,9 +487,9 @@ void orc_tm_matpc(double *out, double *gauge[4], const double *in, double kappa,
   } else {
     /* M = A - k^2 D A^-1 D ;  M^dag = A^dag - k^2 D^dag A^-dag D^dag */
     orc_dslash(tmp, gauge, in, 1 - p, daggerBit);
-    orc_twist_gamma5(tmp, tmp, daggerBit, kappa, mu, 1, Vh);
+    site_A(tmp, tmp, daggerBit, kappa, mu, 1, 1 - p, Vh);
     orc_dslash(out, gauge, tmp, p, daggerBit);
-    orc_twist_gamma5(tmp, in, daggerBit, kappa, mu, 0, Vh);
+    site_A(tmp, in, daggerBit, kappa, mu, 0, p, Vh);
     orc_xpay(tmp, k2, out, (long)n);
   }
   free(tmp);
@@ -359,7 +511,8 @@ void orc_tm_mat(double *out, double *gauge[4], const double *in, double kappa, d
   double *tmp = (double *)malloc(2 * n * sizeof(double));
   orc_dslash(outO, gauge, inE, 1, daggerBit);
   orc_dslash(outE, gauge, inO, 0, daggerBit);
-  orc_twist_gamma5(tmp, in, daggerBit, kappa, mu, 0, V);
+  site_A(tmp, inE, daggerBit, kappa, mu, 0, 0, Vh);
+  site_A(tmp + n, inO, daggerBit, kappa, mu, 0, 1, Vh);
   orc_xpay(tmp, -kappa, out, 2 * (long)n);
   free(tmp);
 }
@@ -372,10 +525,10 @@ void orc_prepare(double *src, double *gauge[4], const double *b, double kappa, d
   int p = matpc & 1, asym = matpc >= 2;
   const double *bp = b + (size_t)p * n, *bq = b + (size_t)(1 - p) * n;
   double *tmp = (double *)malloc(n * sizeof(double));
-  orc_twist_gamma5(tmp, bq, 0, kappa, mu, 1, Vh);
+  site_A(tmp, bq, 0, kappa, mu, 1, 1 - p, Vh);
   orc_dslash(src, gauge, tmp, p, 0);
   orc_xpay(bp, kappa, src, (long)n);
-  if (!asym) orc_twist_gamma5(src, src, 0, kappa, mu, 1, Vh);
+  if (!asym) site_A(src, src, 0, kappa, mu, 1, p, Vh);
   free(tmp);
 }
 
@@ -387,7 +540,7 @@ void orc_reconstruct(double *x, double *gauge[4], const double *b, double kappa,
   double *xp = x + (size_t)p * n, *xq = x + (size_t)(1 - p) * n;
   orc_dslash(xq, gauge, xp, 1 - p, 0);
   orc_xpay(bq, kappa, xq, (long)n);
-  orc_twist_gamma5(xq, xq, 0, kappa, mu, 1, Vh);
+  site_A(xq, xq, 0, kappa, mu, 1, 1 - p, Vh);
 }
 
 /* ---- blas [upstream-shape: tests/blas_reference.cpp] ------------------------------------------ */

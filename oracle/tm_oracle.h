@@ -78,6 +78,13 @@ void orc_tm_mat(double *out, double *gauge[4], const double *in, double kappa, d
 void orc_prepare(double *src, double *gauge[4], const double *b, double kappa, double mu, int matpc);
 void orc_reconstruct(double *x, double *gauge[4], const double *b, double kappa, double mu, int matpc);
 
+/* twisted-clover: dense 12x12 site matrices C(x), [parity][cb][12][12][re,im] = 288 doubles per site, built from the
+ * gauge field with coeff = csw * kappa (see tm_oracle.c).  orc_set_clover(clov) switches EVERY operator above from the
+ * constant twist A = 1 + i a g5 to A = C + i a g5 (NULL switches back); orc_site_A applies A, A^-1 and their daggers. */
+void orc_clover_compute(double *clov, double *gauge[4], double coeff);
+void orc_set_clover(const double *clov);
+void orc_site_A(double *out, const double *in, int daggerBit, double kappa, double mu, int inverse, int parity);
+
 /* blas (upstream tests/blas_reference.cpp shapes) ---------------------------------------------- */
 void   orc_ax(double a, double *x, long n);
 void   orc_axpy(double a, const double *x, double *y, long n);       /* y += a x                  */

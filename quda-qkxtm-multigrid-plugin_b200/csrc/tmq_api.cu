@@ -138,6 +138,13 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   A.red_slot = s.red_slot; A.red_accum = 0;
   A.alpha_num = s.alpha_num; A.alpha_den = s.alpha_den;
   A.prefetch = c->opt_prefetch;
+  if (c->clover_on) {
+    // site matrices of the OUTPUT parity (every site operator of the epilogues acts on the output site)
+    const size_t off = (size_t)s.out_parity * 36 * c->g.Vh;
+    A.cl_inv = (const VecT<F> *)(prec == 8 ? c->clov_inv_d.d : c->clov_inv_s.d) + off;
+    A.cl_c = (const VecT<F> *)(prec == 8 ? c->clov_c_d.d : c->clov_c_s.d) + off;
+    A.cl_dag1 = s.t1.dag; A.cl_dag3 = s.t3.dag;
+  }
 
   const Geom &g = c->g;
   const bool has_red = (s.epi == EPI_MDAGM2 || s.epi == EPI_CG4);
@@ -272,7 +279,21 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
 }
 
 int apply_hop(tmq_ctx *c, int prec, void *out, const void *in, const HopSpec &s) {
+  if (c->clover_on) TMQ_TRY(clover_update_inverse(c));
   return prec == 8 ? apply_hop_t<double>(c, out, in, s) : apply_hop_t<float>(c, out, in, s);
+}
+
+int site_op(tmq_ctx *c, int prec, void *out, const void *in, int parity, const Tw &w) {
+  if (!c->clover_on) {
+    TMQ_CUDA(blas_twist(prec, out, in, w.c, w.a, c->g.Vh, c->stream)); c->launches++;
+    return 0;
+  }
+  TMQ_TRY(clover_update_inverse(c));
+  const size_t off = (size_t)parity * 36 * c->g.Vh * vec_bytes(prec);
+  const char *M = (const char *)(w.inv ? (prec == 8 ? c->clov_inv_d.d : c->clov_inv_s.d) : (prec == 8 ? c->clov_c_d.d : c->clov_c_s.d)) + off;
+  // A = C + i a g5 (w.a carries the dagger sign); A^-1 is stored whole, its conjugate transpose is A^-dag
+  TMQ_CUDA(clover_apply(prec, out, in, M, c->g.Vh, w.inv ? w.dag : 0, w.inv ? 0.0 : w.a, c->stream)); c->launches++;
+  return 0;
 }
 
 static inline BlasRed red_at(tmq_ctx *c, int slot) { return BlasRed{c->partials, c->ticket, c->scal, slot}; }
@@ -321,8 +342,7 @@ int op_matpc(tmq_ctx *c, int prec, void *out, const void *in, int dagger) {
     return apply_hop(c, prec, out, t0, b);
   }
   if (!asym && dagger) {
-    const Tw w = tw_Ainv(c, 1);
-    TMQ_CUDA(blas_twist(prec, t1, in, w.c, w.a, c->g.Vh, c->stream)); c->launches++;
+    TMQ_TRY(site_op(c, prec, t1, in, p, tw_Ainv(c, 1)));
     a.epi = EPI_TW; a.out_parity = q; a.dagger = 1; a.t1 = tw_Ainv(c, 1);
     TMQ_TRY(apply_hop(c, prec, t0, t1, a));
     b.epi = EPI_XPAY; b.out_parity = p; b.dagger = 1; b.k = k2; b.x = in;
@@ -523,6 +543,7 @@ int tmq_destroy(tmq_ctx *c) {
   while (!c->spinors.empty()) tmq_spinor_free(*c->spinors.begin());
   comm_destroy(c);
   eig_release(c);
+  tmq_clover_free(c);
   tmq_gauge_free(c);
   for (int i = 0; i < NSCRATCH; i++) { if (c->scr_d.tmp[i]) cudaFree(c->scr_d.tmp[i]); if (c->scr_s.tmp[i]) cudaFree(c->scr_s.tmp[i]); }
   for (int pi = 0; pi < 2; pi++)
@@ -805,8 +826,7 @@ int tmq_prepare(tmq_spinor *src, const tmq_spinor *b) {
   const bool asym = c->matpc >= 2;
   const size_t pb = parity_bytes(c, prec);
   TMQ_TRY(ensure_scratch(c, prec, 1));
-  const Tw w = tw_Ainv(c, 0);
-  TMQ_CUDA(blas_twist(prec, scr(c, prec, 0), (const char *)b->d + (size_t)q * pb, w.c, w.a, c->g.Vh, c->stream)); c->launches++;
+  TMQ_TRY(site_op(c, prec, scr(c, prec, 0), (const char *)b->d + (size_t)q * pb, q, tw_Ainv(c, 0)));
   HopSpec s; s.epi = asym ? EPI_XPAY : EPI_XPAY_TW3; s.out_parity = p; s.k = c->kappa; s.x = (const char *)b->d + (size_t)p * pb;
   s.t3 = tw_Ainv(c, 0);
   return apply_hop(c, prec, src->d, scr(c, prec, 0), s);

@@ -43,8 +43,13 @@ __device__ __forceinline__ void halo_wait(const HaloWait &hw) {
   __syncthreads();
 }
 
-template <typename F, int RECON, int EPI, bool MULTI>
-__global__ void __launch_bounds__(TMQ_DSLASH_BLOCK, (MinBlocks<F, EPI>::v))
+// twisted-clover variants: the site matrices add 36 vector loads per application and a second spinor in the x-term
+// epilogues; one CTA less per SM keeps them out of local memory
+template <typename F> struct MinBlocksClover { static constexpr int v = 3; };
+template <> struct MinBlocksClover<float> { static constexpr int v = 5; };
+
+template <typename F, int RECON, int EPI, bool MULTI, bool CLOVER = false>
+__global__ void __launch_bounds__(TMQ_DSLASH_BLOCK, (CLOVER ? MinBlocksClover<F>::v : MinBlocks<F, EPI>::v))
 dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
   uint32_t blk = blockIdx.x;
   const Enum *en = &A.en;
@@ -71,8 +76,8 @@ dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
   if (e < (uint32_t)en->nsites) {
     // interior sites never touch a ghost zone: they run the branch-free single-GPU body (the ghost-aware body
     // costs ~8% because its conditional loads cannot be hoisted); only boundary CTAs pay for it
-    if (MULTI && boundary) red[0] = dslash_site<F, RECON, EPI, true>(A, *en, e, alpha);
-    else                   red[0] = dslash_site<F, RECON, EPI, false>(A, *en, e, alpha);
+    if (MULTI && boundary) red[0] = dslash_site<F, RECON, EPI, true, CLOVER>(A, *en, e, alpha);
+    else                   red[0] = dslash_site<F, RECON, EPI, false, CLOVER>(A, *en, e, alpha);
   }
   if (EpiTraits<EPI>::RED != 0) block_reduce_finalize<1>(red, A.partials, A.ticket, A.scal, A.red_slot, A.red_accum != 0);
 }
@@ -82,6 +87,13 @@ static cudaError_t launch_epi(bool multi, const DslashArgs<F> &A, cudaStream_t s
   // callers fill nblk[] (segment sizes in CTAs); a plain launch has nblk = {ceil(nsites/128), 0, 0}
   const int grid = A.nblk[0] + A.nblk[1] + A.nblk[2];
   if (grid == 0) return cudaSuccess;
+  // twisted-clover: only the epilogues that apply a site matrix have a clover variant (single rank this round)
+  constexpr bool HAS_SITE_OP = EpiTraits<EPI>::TW1 || EpiTraits<EPI>::TW3 || EpiTraits<EPI>::TWX;
+  if (A.cl_inv != nullptr && HAS_SITE_OP) {
+    if (multi) return cudaErrorNotSupported;
+    if constexpr (HAS_SITE_OP) dslash_kernel<F, RECON, EPI, false, true><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);
+    return cudaGetLastError();
+  }
   if (multi) dslash_kernel<F, RECON, EPI, true><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);
   else       dslash_kernel<F, RECON, EPI, false><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);
   return cudaGetLastError();

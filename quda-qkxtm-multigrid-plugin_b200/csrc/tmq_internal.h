@@ -61,6 +61,10 @@ struct tmq_ctx {
   int recon;                 // 12 | 18
   int t_boundary;
   tmq::GaugeStore gauge_d, gauge_s;
+  // twisted-clover: C and (C + i a g5)^-1 in the chiral basis, vec[2 parity][36][Vh], fp64 + fp32 copies (tmq_clover.cu)
+  tmq::GaugeStore clov_c_d, clov_inv_d, clov_c_s, clov_inv_s;
+  bool clover_on = false, clov_inv_valid = false;
+  double clover_coeff = 0, clov_inv_a = 0;
   // operator
   double kappa, mu;
   int matpc;
@@ -131,7 +135,7 @@ inline size_t parity_bytes(const tmq_ctx *c, int prec) { return (size_t)6 * c->g
 Enum make_enum(const Geom &g, const int lo[3], const int ext[3], const int tile_pref[3], const int step[3] = nullptr);
 
 // ---- one Dslash-class application (tmq_api.cu: possibly split into interior + boundary launches) ----------------
-struct Tw { double c, a; };   // out = c (1 + i a g5) in
+struct Tw { double c, a; int inv = 0, dag = 0; };   // out = c (1 + i a g5) in; inv / dag say which of A, A^-1, A^dag, A^-dag it is (clover path)
 struct HopSpec {
   int epi = EPI_PLAIN;
   int out_parity = 0;
@@ -148,11 +152,15 @@ struct HopSpec {
   int alpha_num = SC_ONE, alpha_den = SC_ONE;
 };
 inline double tw_a(const tmq_ctx *c) { return 2.0 * c->kappa * c->mu; }
-inline Tw tw_A(const tmq_ctx *c, int dag) { return {1.0, dag ? -tw_a(c) : tw_a(c)}; }
+inline Tw tw_A(const tmq_ctx *c, int dag) { return {1.0, dag ? -tw_a(c) : tw_a(c), 0, dag}; }
 inline Tw tw_Ainv(const tmq_ctx *c, int dag) {
   const double a = tw_a(c);
-  return {1.0 / (1.0 + a * a), dag ? a : -a};
+  return {1.0 / (1.0 + a * a), dag ? a : -a, 1, dag};
 }
+// site-local A / A^-1 / A^dag / A^-dag on the parity block `parity`: the constant twist, or the site's clover blocks
+int site_op(tmq_ctx *c, int prec, void *out, const void *in, int parity, const Tw &w);
+cudaError_t clover_apply(int prec, void *out, const void *in, const void *M, int Vh, int dag, double a, cudaStream_t st);
+int clover_update_inverse(tmq_ctx *c);
 
 int apply_hop(tmq_ctx *c, int prec, void *out, const void *in, const HopSpec &s);
 int ensure_scratch(tmq_ctx *c, int prec, int n);

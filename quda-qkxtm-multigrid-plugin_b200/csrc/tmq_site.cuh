@@ -352,6 +352,47 @@ template <typename F> TMQ_HD void twist(Spinor<F> &y, const Spinor<F> &x, F c, F
     }
 }
 
+// o <- M o (or M^dag o) with M = diag(M+, M-) in the chiral basis chi^(+-)_s = psi_s +- psi_{s+2} (s = 0,1): gamma5 is the
+// spin swap in the UKQCD basis (apply_gamma5_vector_core.h), so its eigenvectors are the sums / differences of the upper
+// and lower spin pairs and sigma_munu -- hence the clover term -- is block diagonal there.  M: vec[36][stride].
+template <typename F> TMQ_HD void clover_mul(Spinor<F> &o, const VecT<F> *M, int idx, int stride, bool dag) {
+  F chi[2][6][2], y[2][6][2];
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        chi[0][s * 3 + c][r] = o.v[s][c][r] + o.v[s + 2][c][r];
+        chi[1][s * 3 + c][r] = o.v[s][c][r] - o.v[s + 2][c][r];
+        y[0][s * 3 + c][r] = 0; y[1][s * 3 + c][r] = 0;
+      }
+#pragma unroll
+  for (int b = 0; b < 2; b++)
+#pragma unroll
+    for (int v = 0; v < 18; v++) {
+      const VecT<F> m = M[(size_t)(b * 18 + v) * stride + idx];
+      const int k0 = 2 * v, k1 = 2 * v + 1;
+      const int r0 = k0 / 6, c0 = k0 % 6, r1 = k1 / 6, c1 = k1 % 6;
+      if (!dag) {
+        TMQ_CMAC(y[b][r0][0], y[b][r0][1], m.a, m.b, chi[b][c0][0], chi[b][c0][1]);
+        TMQ_CMAC(y[b][r1][0], y[b][r1][1], m.c, m.d, chi[b][c1][0], chi[b][c1][1]);
+      } else {
+        TMQ_CMAC_CONJ(y[b][c0][0], y[b][c0][1], m.a, m.b, chi[b][r0][0], chi[b][r0][1]);
+        TMQ_CMAC_CONJ(y[b][c1][0], y[b][c1][1], m.c, m.d, chi[b][r1][0], chi[b][r1][1]);
+      }
+    }
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        o.v[s][c][r] = (F)0.5 * (y[0][s * 3 + c][r] + y[1][s * 3 + c][r]);
+        o.v[s + 2][c][r] = (F)0.5 * (y[0][s * 3 + c][r] - y[1][s * 3 + c][r]);
+      }
+}
+
 // the same twist on one (vector j, vector j+3) pair: u' = c (u + i a l), l' = c (l + i a u)
 template <typename F> TMQ_HD void twist_pair(VecT<F> &u, VecT<F> &l, F c, F a) {
   VecT<F> ou, ol;
@@ -373,7 +414,7 @@ template <int EPI> struct EpiTraits {
 };
 
 // Computes one output site; returns this site's contribution to the fused reduction (0 if none).
-template <typename F, int RECON, int EPI, bool MULTI>
+template <typename F, int RECON, int EPI, bool MULTI, bool CLOVER = false>
 TMQ_HD double dslash_site(const DslashArgs<F> &A, const Enum &en, uint32_t e, F alpha) {
   typedef EpiTraits<EPI> T;
   const Geom &g = A.g;
@@ -432,6 +473,64 @@ TMQ_HD double dslash_site(const DslashArgs<F> &A, const Enum &en, uint32_t e, F 
     cross = false; n = c.idx - st;
     if (c.t == 0) { n = c.idx + (g.X[3] - 1) * st; if (MULTI && g.part[3]) { cross = true; fidx = c.idx; } }
     hop_term<F, RECON, 3, false, MULTI>(o, A, c, n, cross, fidx, s12_b);
+  }
+
+  // ---- twisted-clover epilogue: the site-constant twist matrices become the site's 6x6 chiral blocks ----
+  if constexpr (CLOVER) {
+    double redc = 0.0;
+    if (T::TW1) clover_mul(o, A.cl_inv, c.idx, stride, A.cl_dag1 != 0);
+    if (T::XTERM) {
+      Spinor<F> x;
+#pragma unroll
+      for (int j = 0; j < 6; j++) unpack_vec(x, j, A.x[(size_t)j * stride + c.idx]);
+      if (T::TWX) {
+        // (C + i ax g5) x
+        Spinor<F> cx = x;
+        clover_mul(cx, A.cl_c, c.idx, stride, false);
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            cx.v[s][cc][0] -= A.e.ax * x.v[s ^ 2][cc][1];
+            cx.v[s][cc][1] += A.e.ax * x.v[s ^ 2][cc][0];
+          }
+        x = cx;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          o.v[s][cc][0] = x.v[s][cc][0] + A.e.k * o.v[s][cc][0];
+          o.v[s][cc][1] = x.v[s][cc][1] + A.e.k * o.v[s][cc][1];
+        }
+    }
+    if (T::RED == 1) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) redc += norm2_vec(pack_vec(o, j));
+    }
+    if (T::TW3) clover_mul(o, A.cl_inv, c.idx, stride, A.cl_dag3 != 0);
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      VecT<F> zv = pack_vec(o, j);
+      if (T::RED == 2) {
+        VecT<F> rv = A.r[(size_t)j * stride + c.idx];
+        rv.a -= alpha * zv.a; rv.b -= alpha * zv.b; rv.c -= alpha * zv.c; rv.d -= alpha * zv.d;
+        redc += norm2_vec(rv);
+        A.r[(size_t)j * stride + c.idx] = rv;
+      } else if (T::CHEB) {
+        const VecT<F> yv = A.y[(size_t)j * stride + c.idx];
+        zv.a = A.e.d1 * zv.a + A.e.d2 * yv.a; zv.b = A.e.d1 * zv.b + A.e.d2 * yv.b;
+        zv.c = A.e.d1 * zv.c + A.e.d2 * yv.c; zv.d = A.e.d1 * zv.d + A.e.d2 * yv.d;
+        if (A.e.d3 != (F)0) {
+          const VecT<F> rv = A.r[(size_t)j * stride + c.idx];
+          zv.a += A.e.d3 * rv.a; zv.b += A.e.d3 * rv.b; zv.c += A.e.d3 * rv.c; zv.d += A.e.d3 * rv.d;
+        }
+        A.out[(size_t)j * stride + c.idx] = zv;
+      } else {
+        A.out[(size_t)j * stride + c.idx] = zv;
+      }
+    }
+    return redc;
   }
 
   // ---- epilogue ----

@@ -161,6 +161,11 @@ template <typename F> struct DslashArgs {
   int red_slot;            // where the finished sum goes
   int red_accum;           // 1: add to the slot (second and later launches of a split application)
   int alpha_num, alpha_den; // EPI_CG4: alpha = scal[alpha_num] / scal[alpha_den]
+  // twisted-clover: site matrices of the OUTPUT parity in the chiral basis chi^(+-)_s = psi_s +- psi_{s+2},
+  // two 6x6 complex blocks per site, vec[36][stride] (complex k = block*36 + row*6 + col; vector k/2)
+  const VecT<F> *cl_inv;   // (C + i a g5)^-1 ; its conjugate transpose is (C - i a g5)^-1
+  const VecT<F> *cl_c;     // C = 1 + i csw kappa sum_{mu<nu} sigma_munu F_munu
+  int cl_dag1, cl_dag3;    // apply the conjugate transpose in the post-hop (t1) / final (t3) position
   int prefetch;            // unused (the L2-prefetch experiment was removed: no gain, and it cost the 4th resident CTA)
 };
 

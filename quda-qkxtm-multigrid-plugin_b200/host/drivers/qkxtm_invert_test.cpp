@@ -27,7 +27,8 @@ int main(int argc, char **argv) {
   std::string prec_sloppy = "double", matpc = "even-even", test = "invert", source = "z4", out, massnorm = "kappa", verb = "summarize";
   unsigned long long seed = 100;
   int nev = 4, nkv = 16, polydeg = 20;
-  double amin = 0.385, amax = 2.0, eig_tol = 1e-10;
+  double amin = 0.385, amax = 2.0, eig_tol = 1e-10, csw = 0.0;
+  std::string dslash_type = "twisted-mass";
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto need = [&](int n) { if (i + n >= argc) { usage(); exit(2); } };
@@ -46,6 +47,8 @@ int main(int argc, char **argv) {
     else if (a == "--seed") { need(1); seed = strtoull(argv[++i], nullptr, 10); }
     else if (a == "--verbosity-level") { need(1); verb = argv[++i]; }
     else if (a == "--out") { need(1); out = argv[++i]; }
+    else if (a == "--dslash-type") { need(1); dslash_type = argv[++i]; }      // twisted-mass | twisted-clover (qkxtm/misc.cpp:830-859)
+    else if (a == "--csw") { need(1); csw = atof(argv[++i]); }                 // qkxtm/QKXTM_util.cpp:1642
     else if (a == "--PolyDeg") { need(1); polydeg = atoi(argv[++i]); }        // the reference's ARPACK flags (qkxtm/QKXTM_util.cpp)
     else if (a == "--nEv") { need(1); nev = atoi(argv[++i]); }
     else if (a == "--nKv") { need(1); nkv = atoi(argv[++i]); }
@@ -78,7 +81,8 @@ int main(int argc, char **argv) {
   inv_param.kappa = kappa < 0 ? 1.0 / (2.0 * (1 + 3 / gauge_param.anisotropy + mass)) : kappa;   // Calc_Loops.cpp:382-388
   inv_param.mass = 0.5 / inv_param.kappa - (1 + 3 / gauge_param.anisotropy);
   inv_param.mu = mu;
-  inv_param.dslash_type = QUDA_TWISTED_MASS_DSLASH;
+  inv_param.dslash_type = dslash_type == "twisted-clover" ? QUDA_TWISTED_CLOVER_DSLASH : QUDA_TWISTED_MASS_DSLASH;
+  inv_param.clover_coeff = csw * inv_param.kappa;                              // qkxtm/MG_Bench.cpp:249
   inv_param.twist_flavor = QUDA_TWIST_SINGLET;
   inv_param.cpu_prec = inv_param.cuda_prec = QUDA_DOUBLE_PRECISION;
   inv_param.cuda_prec_sloppy = inv_param.cuda_prec_precondition = gauge_param.cuda_prec_sloppy;
@@ -114,6 +118,11 @@ int main(int argc, char **argv) {
   init_qudaQKXTM(&info);
   printf_qudaQKXTM();
   loadGaugeQuda((void *)gauge, &gauge_param);
+  if (inv_param.dslash_type == QUDA_TWISTED_CLOVER_DSLASH) {                    // qkxtm/MG_Bench.cpp:605-608
+    printf("Constructing clover field\n");
+    loadCloverQuda(NULL, NULL, &inv_param);
+    printf("Clover field done\n");
+  }
 
   std::vector<double> result;
   if (test == "invert" || test == "mat") {

@@ -21,6 +21,7 @@ struct Globals {
   bool quda_initialized = false;
   bool qkxtm_initialized = false;     // GK_init_qudaQKXTM_flag (lib/qudaQKXTM_kernels.cu:120)
   bool gauge_loaded = false;
+  bool clover_loaded = false;
   int grid[4] = {1, 1, 1, 1};
   int coord[4] = {0, 0, 0, 0};
   int localL[4] = {0, 0, 0, 0};
@@ -145,6 +146,18 @@ void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param) {
   TMQ_OK(tmq_gauge_load(G.ctx, (const void *const *)h_gauge, (int)param->t_boundary, recon));
   G.gauge_loaded = true;
 }
+void loadCloverQuda(void *h_clover, void *h_clovinv, QudaInvertParam *inv_param) {
+  if (!G.gauge_loaded) errorQuda("loadCloverQuda needs a resident gauge field (loadGaugeQuda)");
+  if (h_clover || h_clovinv) errorQuda("host clover fields are not supported: pass NULL to have the field built on the device");
+  if (!inv_param) errorQuda("null argument");
+  TMQ_OK(tmq_clover_load(G.ctx, inv_param->clover_coeff));
+  G.clover_loaded = true;
+  G.op_matpc = -1;              // force createDirac to push kappa / mu again (the inverse depends on them)
+}
+void freeCloverQuda(void) {
+  if (G.ctx) tmq_clover_free(G.ctx);
+  G.clover_loaded = false;
+}
 void freeGaugeQuda(void) {
   if (G.ctx) tmq_gauge_free(G.ctx);
   G.gauge_loaded = false;
@@ -154,7 +167,10 @@ void freeGaugeQuda(void) {
 static int matpc_of(const QudaInvertParam *p) { return (int)p->matpc_type; }
 static void check_param(const QudaInvertParam *p) {
   if (!G.gauge_loaded) errorQuda("no gauge field resident (loadGaugeQuda)");
-  if (p->dslash_type != QUDA_TWISTED_MASS_DSLASH) errorQuda("This path supports the twisted-mass operator only");
+  if (p->dslash_type != QUDA_TWISTED_MASS_DSLASH && p->dslash_type != QUDA_TWISTED_CLOVER_DSLASH)
+    errorQuda("This routine is for twisted mass or twisted clover operators only");        // qkxtm/Calc_Loops.cpp:685-689
+  if (p->dslash_type == QUDA_TWISTED_CLOVER_DSLASH && !G.clover_loaded) errorQuda("twisted-clover needs loadCloverQuda first");
+  if (p->dslash_type == QUDA_TWISTED_MASS_DSLASH && G.clover_loaded) errorQuda("a clover field is resident: call freeCloverQuda for plain twisted mass");
   if (p->gamma_basis != QUDA_UKQCD_GAMMA_BASIS) errorQuda("This function works only with ukqcd gamma basis");
   if (p->dirac_order != QUDA_DIRAC_ORDER) errorQuda("This function works only with colors inside the spins");
   if (p->cuda_prec != QUDA_DOUBLE_PRECISION) errorQuda("cuda_prec must be double (the QKXTM upload kernel writes double2, lib/qudaQKXTM_kernels.cu:1031)");

@@ -29,7 +29,7 @@ tmq_prepare tmq_reconstruct tmq_cg_mdagm tmq_cg_history tmq_zero tmq_copy tmq_ax
 tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm tmq_axpy_zpbx tmq_gamma5
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
-tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop""".split()
+tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free""".split()
 
 
 class TmqError(RuntimeError):
@@ -107,6 +107,7 @@ def load():
     L.tmq_project.argtypes = [vp, vp, vp, C.c_int]
     L.tmq_qkxtm_gauss_smear.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_double]
     L.tmq_timer_start.argtypes = [vp]; L.tmq_timer_stop.argtypes = [vp, dp]
+    L.tmq_clover_load.argtypes = [vp, C.c_double]; L.tmq_clover_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -254,6 +255,8 @@ class Context:
         return p.value
 
     def set_op(self, kappa, mu, matpc=MATPC_EVEN_EVEN): _ck(self.L.tmq_op_set(self.h, kappa, mu, matpc))
+    def clover_load(self, clover_coeff): _ck(self.L.tmq_clover_load(self.h, clover_coeff))     # loadCloverQuda(NULL, NULL, &inv_param)
+    def clover_free(self): _ck(self.L.tmq_clover_free(self.h))
 
     def spinor(self, prec=PREC_DOUBLE, subset=PARITY): return Spinor(self, prec, subset)
 

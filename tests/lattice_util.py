@@ -183,6 +183,52 @@ def dense_mat(U_lex, psi_lex, X, gam, kappa, mu_tm, dagger=False):
     return np.einsum("st,xtc->xsc", A, psi_lex) - kappa * dense_hop(U_lex, psi_lex, X, gam, dagger)
 
 
+def dense_clover(U_lex, X, gam, coeff):
+    """C(x) = 1 + i coeff sum_{mu<nu} sigma_munu (x) F_munu(x) as [V][4][3][4][3] complex, sigma_munu = (i/2)[g_mu, g_nu],
+    F = (Q - Q^dag)/8 with Q the sum of the four plaquette leaves around x, all from np.roll on a [t][z][y][x] grid
+    (independent of the C oracle's index code)."""
+    shp = (X[3], X[2], X[1], X[0])
+    U = [U_lex[mu].reshape(shp + (3, 3)) for mu in range(4)]
+    V = int(np.prod(X))
+
+    def sh(A, mu, d):            # field evaluated at x + d mu
+        return np.roll(A, -d, axis=3 - mu)
+
+    def mm(*ms):
+        out = ms[0]
+        for m in ms[1:]:
+            out = np.einsum("...ab,...bc->...ac", out, m)
+        return out
+
+    def dg(A):
+        return np.conj(np.swapaxes(A, -1, -2))
+
+    C = np.zeros((V, 4, 3, 4, 3), dtype=np.complex128)
+    for s in range(4):
+        for c in range(3):
+            C[:, s, c, s, c] = 1.0
+    for mu in range(4):
+        for nu in range(mu + 1, 4):
+            Um, Un = U[mu], U[nu]
+            Q = mm(Um, sh(Un, mu, 1), dg(sh(Um, nu, 1)), dg(Un))
+            Q = Q + mm(Un, dg(sh(sh(Um, mu, -1), nu, 1)), dg(sh(Un, mu, -1)), sh(Um, mu, -1))
+            Q = Q + mm(dg(sh(Um, mu, -1)), dg(sh(sh(Un, mu, -1), nu, -1)), sh(sh(Um, mu, -1), nu, -1), sh(Un, nu, -1))
+            Q = Q + mm(dg(sh(Un, nu, -1)), sh(Um, nu, -1), sh(sh(Un, mu, 1), nu, -1), dg(Um))
+            F = (Q - dg(Q)) / 8.0
+            sig = 0.5j * (gam[mu] @ gam[nu] - gam[nu] @ gam[mu])
+            C += 1j * coeff * np.einsum("st,xab->xsatb", sig, F.reshape(V, 3, 3))
+    return C
+
+
+def dense_mat_clover(U_lex, psi_lex, X, gam, kappa, mu_tm, coeff, dagger=False):
+    """M_full psi = (C + i a g5) psi - kappa D psi"""
+    g5 = gam[0] @ gam[1] @ gam[2] @ gam[3]
+    a = 2.0 * kappa * mu_tm * (-1.0 if dagger else 1.0)
+    C = dense_clover(U_lex, X, gam, coeff)
+    out = np.einsum("xsatb,xtb->xsa", C, psi_lex) + 1j * a * np.einsum("st,xtc->xsc", g5, psi_lex)
+    return out - kappa * dense_hop(U_lex, psi_lex, X, gam, dagger)
+
+
 def c2r(z):
     return np.ascontiguousarray(np.stack([z.real, z.imag], axis=-1))
 

@@ -120,3 +120,19 @@ def test_deflation_class_eigensolver_and_deflate(tmp_path, env):
     b = lu.spinor_eo_from_lex(tmq.gen_spinor(X, "gaussian", seed=100, eo_order=False), X)
     ref = U @ ((U.conj().T @ cplx(np.ascontiguousarray(b[:Vh]))) / lam)
     assert np.all(xd[Vh:] == 0) and lu.rel_l2(cplx(np.ascontiguousarray(xd[:Vh])), ref) < 1e-7
+
+
+def test_twisted_clover_invert_through_the_shim(tmp_path, env):
+    """--dslash-type twisted-clover: loadCloverQuda(NULL, NULL, &inv_param) after loadGaugeQuda, then invertQuda
+    (qkxtm/MG_Bench.cpp:598-608); the solution satisfies the oracle's full twisted-clover operator"""
+    o, gauge, tmq = env
+    csw = 1.57551
+    x, it, tr, _ = run(tmp_path, "--test", "invert", "--tol", "1e-10", "--dslash-type", "twisted-clover", "--csw", str(csw), "--recon", "12")
+    b = tmq.gen_spinor(X, "z4", seed=100)
+    from oracle.oracle import Oracle
+    oc = Oracle(X)
+    oc.set_clover(oc.clover_compute(gauge, csw * KAPPA))
+    r = oc.mat(gauge, x.reshape(b.shape), KAPPA, MU, 0)
+    oc.set_clover(None)
+    assert tr <= 1.05e-10 and it > 5
+    assert lu.rel_l2(r, b) < 1e-8

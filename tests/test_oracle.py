@@ -280,3 +280,111 @@ def test_chebyshev_filter_restatement():
             assert np.all(np.abs(p[3:]) <= edge * (1 + 1e-9))
             assert p[0] > p[1] > p[2] > edge
     assert len(cheb_coefficients(5, 0.05, 4.0)) == 5
+
+
+# ---- twisted-clover --------------------------------------------------------------------------------
+CSW = 1.57551           # the ETMC N_f = 2 clover ensembles' value; coeff = csw * kappa (qkxtm/MG_Bench.cpp:249)
+
+
+def _clover_setup(X, seed=137):
+    o = Oracle(X)
+    U = lu.random_su3_lex(X, seed=seed)
+    gq = lu.gauge_qdp_from_lex(U, X, t_boundary=-1)
+    Ubc = U.copy(); xs, ys, zs, ts = lu.coords_lex(X); Ubc[3, ts == X[3] - 1] *= -1
+    clov = o.clover_compute(gq, CSW * KAPPA)
+    return o, U, Ubc, gq, clov
+
+
+def test_clover_term_matches_dense_numpy_and_is_hermitian():
+    X = XA
+    o, U, Ubc, gq, clov = _clover_setup(X)
+    V = o.V
+    want = lu.dense_clover(Ubc, X, gamma_ukqcd(), CSW * KAPPA).reshape(V, 12, 12)
+    got_eo = lu.r2c(clov)                                    # [even Vh | odd Vh][12][12]
+    got = np.empty_like(got_eo); got[lu.eo_from_lex(X)] = got_eo
+    assert np.abs(got - want).max() < 1e-14
+    assert np.abs(got - np.conj(np.swapaxes(got, 1, 2))).max() < 1e-14      # C is hermitian
+    # the anti-periodic sign on U_t(T-1) cancels in every leaf: same C as for the periodic field
+    assert np.abs(want - lu.dense_clover(U, X, gamma_ukqcd(), CSW * KAPPA).reshape(V, 12, 12)).max() < 1e-14
+    # unit gauge field: F = 0, C = 1
+    unit = np.zeros_like(U); unit[:, :, range(3), range(3)] = 1.0
+    assert np.abs(lu.dense_clover(unit, X, gamma_ukqcd(), 0.3).reshape(V, 12, 12) - np.eye(12)).max() == 0.0
+
+
+@pytest.mark.parametrize("dagger", [0, 1])
+def test_clover_full_operator_matches_dense_numpy(dagger):
+    X = XA
+    o, U, Ubc, gq, clov = _clover_setup(X)
+    o.set_clover(clov)
+    psi = lu.gaussian_spinor_lex(X, seed=101)
+    ref = lu.dense_mat_clover(Ubc, lu.r2c(psi), X, gamma_ukqcd(), KAPPA, MU, CSW * KAPPA, dagger=bool(dagger))
+    got = o.mat(gq, lu.spinor_eo_from_lex(psi, X), KAPPA, MU, dagger)
+    o.set_clover(None)
+    assert lu.rel_l2(full_eo_to_lexc(got, X).view(np.float64), ref.view(np.float64)) < 1e-14
+
+
+def test_clover_site_operator_inverse_and_csw_zero_limit():
+    X = X4
+    o, U, Ubc, gq, clov = _clover_setup(X)
+    psi = np.ascontiguousarray(lu.spinor_eo_from_lex(lu.gaussian_spinor_lex(X, seed=7), X)[: o.Vh])
+    o.set_clover(clov)
+    for parity in (0, 1):
+        for dagger in (0, 1):
+            y = o.site_A(psi, KAPPA, MU, parity, dagger, 0)
+            assert lu.rel_l2(o.site_A(y, KAPPA, MU, parity, dagger, 1), psi) < 1e-14
+    # csw = 0: C = 1, everything reduces to plain twisted mass
+    o.set_clover(o.clover_compute(gq, 0.0))
+    a = o.mdagm(gq, psi, KAPPA, MU, 0)
+    o.set_clover(None)
+    assert lu.rel_l2(a, o.mdagm(gq, psi, KAPPA, MU, 0)) < 1e-15
+
+
+@pytest.mark.parametrize("matpc", [0, 1, 2, 3])
+def test_clover_adjointness_and_schur(matpc):
+    """<x, M y> = <M^dag x, y> for the preconditioned twisted-clover operator, and prepare -> M^dag -> CG -> reconstruct
+    solves the full system"""
+    X = X4
+    o, U, Ubc, gq, clov = _clover_setup(X)
+    o.set_clover(clov)
+    x = np.ascontiguousarray(lu.spinor_eo_from_lex(lu.gaussian_spinor_lex(X, seed=3), X)[: o.Vh])
+    y = np.ascontiguousarray(lu.spinor_eo_from_lex(lu.gaussian_spinor_lex(X, seed=4), X)[: o.Vh])
+    lhs = np.vdot(lu.r2c(x), lu.r2c(o.matpc(gq, y, KAPPA, MU, matpc, 0)))
+    rhs = np.vdot(lu.r2c(o.matpc(gq, x, KAPPA, MU, matpc, 1)), lu.r2c(y))
+    assert abs(lhs - rhs) < 1e-12 * abs(lhs)
+    b = lu.spinor_eo_from_lex(lu.z4_source_lex(X, seed=100), X)
+    src = o.prepare(gq, b, KAPPA, MU, matpc)
+    rhs_v = o.matpc(gq, src, KAPPA, MU, matpc, 1)
+    xp, it, tr, _ = o.cg_mdagm(gq, rhs_v, KAPPA, MU, matpc, tol=1e-12, maxiter=2000)
+    p = matpc & 1
+    xf = np.zeros_like(b); xf[p * o.Vh:(p + 1) * o.Vh] = xp
+    xf = o.reconstruct(gq, xf, b, KAPPA, MU, matpc)
+    res = o.mat(gq, xf, KAPPA, MU, 0) - b
+    o.set_clover(None)
+    assert tr < 1e-11 and np.linalg.norm(res) / np.linalg.norm(b) < 1e-10
+
+
+def test_clover_gamma5_hermiticity_and_gauge_covariance():
+    """g5 M(mu) g5 = M(-mu)^dag for the full twisted-clover operator; gauge covariance of the clover term"""
+    X = X4
+    o, U, Ubc, gq, clov = _clover_setup(X)
+    o.set_clover(clov)
+    psi = lu.spinor_eo_from_lex(lu.gaussian_spinor_lex(X, seed=5), X)
+    g5 = o.gamma5()
+    def G5(v):
+        return lu.c2r(np.einsum("st,xtc->xsc", g5, lu.r2c(v)))
+    a = G5(o.mat(gq, G5(psi), KAPPA, MU, 0))
+    b = o.mat(gq, psi, KAPPA, -MU, 1)
+    assert lu.rel_l2(a, b) < 1e-14
+    o.set_clover(None)
+    G = lu.random_su3_lex(X, seed=12)[0]
+    xs, ys, zs, ts = lu.coords_lex(X)
+    Urot = np.empty_like(Ubc)
+    for mu in range(4):
+        c = [xs.copy(), ys.copy(), zs.copy(), ts.copy()]
+        c[mu] = (c[mu] + 1) % X[mu]
+        nb = c[0] + X[0] * (c[1] + X[1] * (c[2] + X[2] * c[3]))
+        Urot[mu] = np.einsum("xab,xbc,xdc->xad", G, Ubc[mu], np.conj(G[nb]))
+    C0 = lu.dense_clover(Ubc, X, gamma_ukqcd(), 0.2)
+    C1 = lu.dense_clover(Urot, X, gamma_ukqcd(), 0.2)
+    want = np.einsum("xab,xsbtc,xdc->xsatd", G, C0, np.conj(G))
+    assert np.abs(C1 - want).max() < 1e-13
