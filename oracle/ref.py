@@ -85,3 +85,74 @@ class Ref:
 
     def gamma5(self, vec):
         v = vec.copy(); self.L.qref_apply_gamma5_double(_dp(v)); return v
+
+
+# ---- the reference's host utility file qkxtm/QKXTM_util.cpp compiled in place (oracle/_ref/libqkxtm_util_ref.so) ------
+_SO_UTIL = os.path.join(_HERE, "_ref", "libqkxtm_util_ref.so")
+_util = None
+
+
+def util_available():
+    return os.path.exists(_SO_UTIL)
+
+
+def util_lib():
+    global _util
+    if _util is None:
+        L = C.CDLL(_SO_UTIL)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        dpp = C.POINTER(dp)
+        L.qutil_set_dims.argtypes = [ip]
+        L.qutil_full_lattice_index.argtypes = [C.c_int, C.c_int]
+        L.qutil_neighbor_index.argtypes = [C.c_int] * 6
+        L.qutil_get_odd_bit.argtypes = [C.c_int]
+        L.qutil_su3_reconstruct12.argtypes = [dp, C.c_int, C.c_int, C.c_int]
+        L.qutil_apply_gauge_field_scaling.argtypes = [dpp, C.c_int]
+        L.qutil_construct_gauge_field.argtypes = [dpp, C.c_int, C.c_uint, C.c_int]
+        L.qutil_read_lime_gauge.argtypes = [dpp, C.c_char_p, ip, C.c_double, C.c_double]
+        _util = L
+    return _util
+
+
+def _g4(g):
+    arr = (C.POINTER(C.c_double) * 4)()
+    for mu in range(4):
+        arr[mu] = g[mu].ctypes.data_as(C.POINTER(C.c_double))
+    return arr
+
+
+class RefUtil:
+    """fullLatticeIndex / neighborIndex / getOddBit / su3Reconstruct12 / applyGaugeFieldScaling / construct_gauge_field of
+    qkxtm/QKXTM_util.cpp and readLimeGauge of include/QKXTM_read_conf.h, run from the reference's own source."""
+
+    def __init__(self, X):
+        self.L = util_lib()
+        self.X = tuple(int(v) for v in X)
+        self.V = int(np.prod(self.X)); self.Vh = self.V // 2
+        self.L.qutil_set_dims((C.c_int * 4)(*self.X))
+
+    def full_index(self, i, odd): return self.L.qutil_full_lattice_index(i, odd)
+    def neighbor_index(self, i, odd, dx4, dx3, dx2, dx1): return self.L.qutil_neighbor_index(i, odd, dx4, dx3, dx2, dx1)
+    def odd_bit(self, Y): return self.L.qutil_get_odd_bit(Y)
+
+    def reconstruct12(self, mat18, direction, ga_idx, t_boundary):
+        m = np.array(mat18, dtype=np.float64).reshape(18).copy()
+        self.L.qutil_su3_reconstruct12(_dp(m), direction, ga_idx, t_boundary)
+        return m
+
+    def apply_gauge_field_scaling(self, gauge, t_boundary):
+        g = np.ascontiguousarray(gauge, dtype=np.float64).copy()
+        self.L.qutil_apply_gauge_field_scaling(_g4(g), t_boundary)
+        return g
+
+    def construct_gauge_field(self, kind=1, seed=137, t_boundary=-1):
+        """kind 0 = unit, 1 = random SU(3) (libc rand() after srand(seed)), QDP even-odd order [4][V][3][3][2]"""
+        g = np.zeros((4, self.V, 3, 3, 2), dtype=np.float64)
+        self.L.qutil_construct_gauge_field(_g4(g), kind, seed, t_boundary)
+        return g
+
+    def read_lime_gauge(self, fname):
+        g = np.zeros((4, self.V, 3, 3, 2), dtype=np.float64)
+        X = (C.c_int * 4)(*self.X)
+        self.L.qutil_read_lime_gauge(_g4(g), fname.encode(), X, 0.0, 0.0)
+        return g, tuple(X)
