@@ -252,6 +252,8 @@ def run_native(args):
     ctx.set_option(tmq.OPT_HALO_P2P, {"p2p": 2, "store": 1, "nccl": 0}[args.halo])
     if args.boundary_at is not None:
         ctx.set_option(3, args.boundary_at)
+    if args.pack_async is not None:
+        ctx.set_option(5, args.pack_async)
     halo_mode = {0: "none", 1: "nccl send/recv", 2: "peer-memory stores + fused launch", 3: "copy-engine peer copies + fused launch"}[ctx.halo_mode()]
     gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1, grid=grid, coord=coord)
     ctx.load_gauge(gauge, t_boundary=-1, recon=recon)
@@ -389,6 +391,7 @@ def main():
     ap.add_argument("--recon", type=int, default=12, choices=[12, 18])
     ap.add_argument("--tile", type=int, nargs=3, default=None)
     ap.add_argument("--boundary-at", type=int, default=None, help="%% of interior CTAs scheduled before the boundary CTAs")
+    ap.add_argument("--pack-async", type=int, default=None, help="1: launch the face pack on the exchange stream (TMQ_OPT_PACK_ASYNC)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "store", "nccl"],
                     help="ghost exchange: copy-engine peer copies (p2p) or peer stores from the pack kernel (store), both with one fused Dslash launch; or ncclSend/Recv")
     ap.add_argument("--tol", type=float, default=1e-9)

@@ -180,14 +180,27 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
     const unsigned int seq = ++c->halo_seq;
     const int buf = (int)(seq & 1u);
     const HaloArena &L = c->arena_layout;
-    TMQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));     // our previous outgoing copies have left the send buffers
-    for (int d = 2; d < 4; d++)
-      if (g.part[d]) {
-        TMQ_CUDA(pack_any<F>(c, A, d, c->halo_send[pi][d][0], c->halo_send[pi][d][1], c->stream));
-        c->launches++;
-      }
-    TMQ_CUDA(cudaEventRecord(c->ev_pack, c->stream));
-    TMQ_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+    if (c->opt_pack_async) {
+      // pack on the (high-priority) exchange stream as well: it only needs the input field, so the Dslash launch below
+      // no longer queues behind it -- the interior CTAs start at once and the pack + copies run beside them.  In-order
+      // execution on the exchange stream also protects the send buffers from the previous application's copies.
+      TMQ_CUDA(cudaEventRecord(c->ev_pack, c->stream));
+      TMQ_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+      for (int d = 2; d < 4; d++)
+        if (g.part[d]) {
+          TMQ_CUDA(pack_any<F>(c, A, d, c->halo_send[pi][d][0], c->halo_send[pi][d][1], c->comm_stream));
+          c->launches++;
+        }
+    } else {
+      TMQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));     // our previous outgoing copies have left the send buffers
+      for (int d = 2; d < 4; d++)
+        if (g.part[d]) {
+          TMQ_CUDA(pack_any<F>(c, A, d, c->halo_send[pi][d][0], c->halo_send[pi][d][1], c->stream));
+          c->launches++;
+        }
+      TMQ_CUDA(cudaEventRecord(c->ev_pack, c->stream));
+      TMQ_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+    }
     for (int d = 2; d < 4; d++) {
       if (!g.part[d]) continue;
       const size_t nbytes = (size_t)3 * g.face[d] * vec_bytes(prec);
@@ -452,6 +465,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->tile[0] = 4; c->tile[1] = 4; c->tile[2] = 2;
   c->opt_prefetch = 0;
   c->opt_smear_block_t = 0;
+  c->opt_pack_async = 0;
   c->opt_pre_pct = 50; c->red_seq = 0; memset(c->rank_arena, 0, sizeof(c->rank_arena));
   c->opt_p2p = 2; c->p2p = false; c->seq_table = nullptr; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
   memset(c->peer_arena, 0, sizeof(c->peer_arena));
@@ -601,6 +615,7 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
   TMQ_REQUIRE(c, "null context");
   switch (option) {
     case TMQ_OPT_PREFETCH: c->opt_prefetch = value ? 1 : 0; return 0;
+    case TMQ_OPT_PACK_ASYNC: c->opt_pack_async = value ? 1 : 0; return 0;
     case TMQ_OPT_SMEAR_BLOCK_T: c->opt_smear_block_t = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {

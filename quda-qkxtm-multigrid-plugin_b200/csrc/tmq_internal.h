@@ -91,6 +91,7 @@ struct tmq_ctx {
   // timing-kernel scratch (tmq_time_kernel)
   int sms;
   int opt_prefetch;
+  int opt_pack_async;        // copy-engine halo path: launch the face pack on the exchange stream, beside the Dslash
   int opt_smear_block_t;     // time slices per L2-resident block of the Gaussian smearing (0 = from the L2 size)
   // peer-memory halo path
   int opt_p2p;               // requested: 0 NCCL send/recv, 1 peer stores from the pack kernel, 2 copy-engine peer copies

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--grid", type=int, nargs=4, default=[1, 1, 1, 2])
     ap.add_argument("--recon", type=int, default=12)
     ap.add_argument("--p2p", type=int, default=2)
+    ap.add_argument("--pack-async", type=int, default=0)
     ap.add_argument("--amin", type=float, default=0.2, help="lower edge of the Chebyshev window (just above the wanted eigenvalues)")
     ap.add_argument("--eig", type=int, default=1, help="also run the (slower) eigensolver / deflation check")
     a = ap.parse_args()
@@ -43,6 +44,8 @@ def main():
     dist.broadcast(uid, src=0)
     ctx.comm_init(uid.numpy().tobytes(), world, rank)
     ctx.set_option(tmq.OPT_HALO_P2P, a.p2p)
+    if a.pack_async:
+        ctx.set_option(5, 1)
     mode = ctx.halo_mode()
     ctx.load_gauge(tmq.gen_gauge(X, grid=grid, coord=coord), t_boundary=-1, recon=a.recon)
     ctx.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
