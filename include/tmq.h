@@ -106,7 +106,8 @@ int tmq_op_set(tmq_ctx *, double kappa, double mu, int matpc);
  * &inv_param), which builds the clover field on the device from the resident gauge field with inv_param.clover_coeff =
  * csw * kappa.  Afterwards every operator entry point uses A = C + i (2 kappa mu) gamma5 with C = 1 + i clover_coeff
  * sum_{mu<nu} sigma_munu F_munu in place of the constant twist; (C + i a gamma5)^-1 is rebuilt whenever tmq_op_set changes
- * kappa or mu.  Single rank in this round.  tmq_clover_free returns to plain twisted mass.                            */
+ * kappa or mu.  On a sharded lattice the gauge halo the clover leaves need (incl. the z-t corners) is exchanged once,
+ * inside this call.  tmq_clover_free returns to plain twisted mass.                                                  */
 int tmq_clover_load(tmq_ctx *, double clover_coeff);
 int tmq_clover_free(tmq_ctx *);
 /* out(parity) = D in or D^dag in : the bare hop (a4)                                                      */

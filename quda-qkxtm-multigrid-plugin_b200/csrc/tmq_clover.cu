@@ -100,11 +100,35 @@ __device__ __forceinline__ void m3_dag(M3 &c, const M3 &a) {
 }
 
 struct Coord4 { int x[4]; };
+
+// gauge field with a one-site halo in the partitioned dimensions (z, t): the clover leaves reach x +- mu +- nu, i.e. across
+// rank boundaries and their corners.  Plain fp64 links, [site_ext][mu][3][3][re,im], site_ext lexicographic over
+// (x, y, z + hz, t + ht); built once per tmq_clover_load and freed afterwards.
+struct ExtGauge {
+  const double *d;      // nullptr: single rank without forced partition -> periodic wrap on the native field
+  int h[4];             // halo width per dimension (0 | 1)
+  int E[4];             // extended extents
+};
+__device__ __forceinline__ size_t ext_site(const ExtGauge &x, const int c[4]) {
+  return (((size_t)(c[3] + x.h[3]) * x.E[2] + (c[2] + x.h[2])) * x.E[1] + c[1]) * x.E[0] + c[0];
+}
 template <int RECON>
-__device__ __forceinline__ void link_at(M3 &m, const void *gauge, const Geom &g, Coord4 c, int mu) {
-  // periodic wrap on the local lattice (single rank: local = global)
+__device__ __forceinline__ void link_at(M3 &m, const void *gauge, const ExtGauge &ext, const Geom &g, Coord4 c, int mu) {
+  // periodic wrap on the local lattice where the dimension is not partitioned; halo sites otherwise
 #pragma unroll
-  for (int d = 0; d < 4; d++) { if (c.x[d] < 0) c.x[d] += g.X[d]; if (c.x[d] >= g.X[d]) c.x[d] -= g.X[d]; }
+  for (int d = 0; d < 4; d++) {
+    if (ext.d != nullptr && ext.h[d]) continue;
+    if (c.x[d] < 0) c.x[d] += g.X[d];
+    if (c.x[d] >= g.X[d]) c.x[d] -= g.X[d];
+  }
+  if (ext.d != nullptr) {
+    const double *p = ext.d + (ext_site(ext, c.x) * 4 + mu) * 18;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) { m.u[i][j][0] = p[(i * 3 + j) * 2]; m.u[i][j][1] = p[(i * 3 + j) * 2 + 1]; }
+    return;
+  }
   const int parity = (c.x[0] + c.x[1] + c.x[2] + c.x[3]) & 1;
   const int idx = ((c.x[3] * g.X[2] + c.x[2]) * g.X[1] + c.x[1]) * g.Xh + (c.x[0] >> 1);
   const double s12 = (mu == 3 && g.tb_last && c.x[3] == g.X[3] - 1) ? (double)g.tb_sign : 1.0;
@@ -119,7 +143,7 @@ __device__ __forceinline__ Coord4 shifted(Coord4 c, int mu, int d) { c.x[mu] += 
 
 // C(x) for one site: thread = (parity, cb index)
 template <int RECON>
-__global__ void __launch_bounds__(128) clover_compute_kernel(VecT<double> *C, const void *gauge, Geom g, SigmaConst S, double coeff) {
+__global__ void __launch_bounds__(128) clover_compute_kernel(VecT<double> *C, const void *gauge, ExtGauge ext, Geom g, SigmaConst S, double coeff) {
   const int e = blockIdx.x * 128 + threadIdx.x;
   if (e >= 2 * g.Vh) return;
   const int parity = e / g.Vh, idx = e - parity * g.Vh;
@@ -141,32 +165,32 @@ __global__ void __launch_bounds__(128) clover_compute_kernel(VecT<double> *C, co
     for (int nu = mu + 1; nu < 4; nu++, plane++) {
       M3 Q, a, b2, t;
       // leaf 1: U_mu(x) U_nu(x+mu) U_mu(x+nu)^dag U_nu(x)^dag
-      link_at<RECON>(a, gauge, g, c, mu); link_at<RECON>(b2, gauge, g, shifted(c, mu, 1), nu); m3_mul(Q, a, b2);
-      link_at<RECON>(a, gauge, g, shifted(c, nu, 1), mu); m3_dag(a, a); m3_mul(Q, Q, a);
-      link_at<RECON>(a, gauge, g, c, nu); m3_dag(a, a); m3_mul(Q, Q, a);
+      link_at<RECON>(a, gauge, ext, g, c, mu); link_at<RECON>(b2, gauge, ext, g, shifted(c, mu, 1), nu); m3_mul(Q, a, b2);
+      link_at<RECON>(a, gauge, ext, g, shifted(c, nu, 1), mu); m3_dag(a, a); m3_mul(Q, Q, a);
+      link_at<RECON>(a, gauge, ext, g, c, nu); m3_dag(a, a); m3_mul(Q, Q, a);
       // leaf 2: U_nu(x) U_mu(x-mu+nu)^dag U_nu(x-mu)^dag U_mu(x-mu)
-      link_at<RECON>(t, gauge, g, c, nu);
-      link_at<RECON>(a, gauge, g, shifted(shifted(c, mu, -1), nu, 1), mu); m3_dag(a, a); m3_mul(t, t, a);
-      link_at<RECON>(a, gauge, g, shifted(c, mu, -1), nu); m3_dag(a, a); m3_mul(t, t, a);
-      link_at<RECON>(a, gauge, g, shifted(c, mu, -1), mu); m3_mul(t, t, a);
+      link_at<RECON>(t, gauge, ext, g, c, nu);
+      link_at<RECON>(a, gauge, ext, g, shifted(shifted(c, mu, -1), nu, 1), mu); m3_dag(a, a); m3_mul(t, t, a);
+      link_at<RECON>(a, gauge, ext, g, shifted(c, mu, -1), nu); m3_dag(a, a); m3_mul(t, t, a);
+      link_at<RECON>(a, gauge, ext, g, shifted(c, mu, -1), mu); m3_mul(t, t, a);
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) { Q.u[i][j][0] += t.u[i][j][0]; Q.u[i][j][1] += t.u[i][j][1]; }
       // leaf 3: U_mu(x-mu)^dag U_nu(x-mu-nu)^dag U_mu(x-mu-nu) U_nu(x-nu)
-      link_at<RECON>(t, gauge, g, shifted(c, mu, -1), mu); m3_dag(t, t);
-      link_at<RECON>(a, gauge, g, shifted(shifted(c, mu, -1), nu, -1), nu); m3_dag(a, a); m3_mul(t, t, a);
-      link_at<RECON>(a, gauge, g, shifted(shifted(c, mu, -1), nu, -1), mu); m3_mul(t, t, a);
-      link_at<RECON>(a, gauge, g, shifted(c, nu, -1), nu); m3_mul(t, t, a);
+      link_at<RECON>(t, gauge, ext, g, shifted(c, mu, -1), mu); m3_dag(t, t);
+      link_at<RECON>(a, gauge, ext, g, shifted(shifted(c, mu, -1), nu, -1), nu); m3_dag(a, a); m3_mul(t, t, a);
+      link_at<RECON>(a, gauge, ext, g, shifted(shifted(c, mu, -1), nu, -1), mu); m3_mul(t, t, a);
+      link_at<RECON>(a, gauge, ext, g, shifted(c, nu, -1), nu); m3_mul(t, t, a);
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) { Q.u[i][j][0] += t.u[i][j][0]; Q.u[i][j][1] += t.u[i][j][1]; }
       // leaf 4: U_nu(x-nu)^dag U_mu(x-nu) U_nu(x+mu-nu) U_mu(x)^dag
-      link_at<RECON>(t, gauge, g, shifted(c, nu, -1), nu); m3_dag(t, t);
-      link_at<RECON>(a, gauge, g, shifted(c, nu, -1), mu); m3_mul(t, t, a);
-      link_at<RECON>(a, gauge, g, shifted(shifted(c, mu, 1), nu, -1), nu); m3_mul(t, t, a);
-      link_at<RECON>(a, gauge, g, c, mu); m3_dag(a, a); m3_mul(t, t, a);
+      link_at<RECON>(t, gauge, ext, g, shifted(c, nu, -1), nu); m3_dag(t, t);
+      link_at<RECON>(a, gauge, ext, g, shifted(c, nu, -1), mu); m3_mul(t, t, a);
+      link_at<RECON>(a, gauge, ext, g, shifted(shifted(c, mu, 1), nu, -1), nu); m3_mul(t, t, a);
+      link_at<RECON>(a, gauge, ext, g, c, mu); m3_dag(a, a); m3_mul(t, t, a);
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -256,6 +280,48 @@ __global__ void __launch_bounds__(128) clover_invert_kernel(VecT<double> *Ainv, 
   }
 }
 
+// ---- building the extended gauge field --------------------------------------------------------------------------------
+template <int RECON>
+__global__ void __launch_bounds__(128) ext_fill_kernel(double *E, ExtGauge ext, const void *gauge, Geom g) {
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= 2 * g.Vh) return;
+  const int parity = e / g.Vh, idx = e - parity * g.Vh;
+  int c[4];
+  {
+    int r = idx;
+    const int xh = r % g.Xh; r /= g.Xh;
+    c[1] = r % g.X[1]; r /= g.X[1];
+    c[2] = r % g.X[2]; c[3] = r / g.X[2];
+    c[0] = 2 * xh + ((c[1] + c[2] + c[3] + parity) & 1);
+  }
+  double *dst = E + ext_site(ext, c) * 72;
+  for (int mu = 0; mu < 4; mu++) {
+    const double s12 = (mu == 3 && g.tb_last && c[3] == g.X[3] - 1) ? (double)g.tb_sign : 1.0;
+    Link<double> L;
+    load_link<double, RECON>(L, gauge, parity, mu, idx, g.Vh, s12);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) { dst[mu * 18 + (i * 3 + j) * 2] = L.u[i][j][0]; dst[mu * 18 + (i * 3 + j) * 2 + 1] = L.u[i][j][1]; }
+  }
+}
+// z faces are strided in the extended array: gather slices z = 0 and z = Z-1 (interior t) / scatter into z = -1 and z = Z
+__global__ void ext_zface_kernel(double *E, ExtGauge ext, Geom g, double *buf_lo, double *buf_hi, int scatter) {
+  const size_t n = (size_t)g.X[0] * g.X[1] * g.X[3] * 72;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % 72);
+    size_t r = i / 72;
+    int c[4];
+    c[0] = (int)(r % g.X[0]); r /= g.X[0];
+    c[1] = (int)(r % g.X[1]); c[3] = (int)(r / g.X[1]);
+    if (!scatter) {
+      c[2] = 0; buf_lo[i] = E[ext_site(ext, c) * 72 + k];
+      c[2] = g.X[2] - 1; buf_hi[i] = E[ext_site(ext, c) * 72 + k];
+    } else {
+      c[2] = -1; E[ext_site(ext, c) * 72 + k] = buf_lo[i];        // from the backward neighbour's z = Z-1
+      c[2] = g.X[2]; E[ext_site(ext, c) * 72 + k] = buf_hi[i];    // from the forward neighbour's z = 0
+    }
+  }
+}
+
 // site-local application on one parity block: out = M in / M^dag in, plus i a g5 in when `a` != 0 (A = C + i a g5)
 template <typename F>
 __global__ void __launch_bounds__(128) clover_apply_kernel(VecT<F> *out, const VecT<F> *in, const VecT<F> *M, int Vh, int dag, F a) {
@@ -315,7 +381,6 @@ extern "C" {
 int tmq_clover_load(tmq_ctx *c, double clover_coeff) {
   TMQ_REQUIRE(c, "null context");
   TMQ_REQUIRE(c->gauge_d.d != nullptr, "no gauge field loaded (tmq_gauge_load): the clover field is built from it");
-  TMQ_REQUIRE(c->nranks == 1 && !c->multi, "the twisted-clover variant is single-rank in this round (the clover leaves need gauge ghost zones)");
   TMQ_CUDA(cudaSetDevice(c->device));
   const size_t nv = (size_t)72 * c->g.Vh;     // vectors per field: 2 parities x 36
   GaugeStore *st[4] = {&c->clov_c_d, &c->clov_inv_d, &c->clov_c_s, &c->clov_inv_s};
@@ -330,9 +395,45 @@ int tmq_clover_load(tmq_ctx *c, double clover_coeff) {
   SigmaConst S;
   build_sigma(S);
   const unsigned int grid = (unsigned int)((2 * (size_t)c->g.Vh + 127) / 128);
-  if (c->recon == 12) clover_compute_kernel<12><<<grid, 128, 0, c->stream>>>((VecT<double> *)c->clov_c_d.d, c->gauge_d.d, c->g, S, clover_coeff);
-  else clover_compute_kernel<18><<<grid, 128, 0, c->stream>>>((VecT<double> *)c->clov_c_d.d, c->gauge_d.d, c->g, S, clover_coeff);
+  // sharded lattice: the leaves need the neighbours' links (and the z-t corners): build a gauge field with a one-site halo
+  // in the partitioned dimensions -- z faces first (packed), then whole t slices of the extended array, which carry the z
+  // halo rows along and so fill the corners
+  ExtGauge ext;
+  memset(&ext, 0, sizeof(ext));
+  double *E = nullptr, *zbuf = nullptr;
+  if (c->multi) {
+    const Geom &g = c->g;
+    for (int d = 0; d < 4; d++) { ext.h[d] = g.part[d] ? 1 : 0; ext.E[d] = g.X[d] + 2 * ext.h[d]; }
+    const size_t next = (size_t)ext.E[0] * ext.E[1] * ext.E[2] * ext.E[3];
+    TMQ_CUDA(cudaMalloc((void **)&E, next * 72 * sizeof(double)));
+    TMQ_CUDA(cudaMemsetAsync(E, 0, next * 72 * sizeof(double), c->stream));
+    if (c->recon == 12) ext_fill_kernel<12><<<grid, 128, 0, c->stream>>>(E, ext, c->gauge_d.d, g);
+    else ext_fill_kernel<18><<<grid, 128, 0, c->stream>>>(E, ext, c->gauge_d.d, g);
+    TMQ_CUDA(cudaGetLastError()); c->launches++;
+    if (g.part[2]) {
+      const size_t nz = (size_t)g.X[0] * g.X[1] * g.X[3] * 72;
+      TMQ_CUDA(cudaMalloc((void **)&zbuf, 4 * nz * sizeof(double)));
+      double *s_lo = zbuf, *s_hi = zbuf + nz, *r_lo = zbuf + 2 * nz, *r_hi = zbuf + 3 * nz;
+      ext_zface_kernel<<<blas_grid(), 256, 0, c->stream>>>(E, ext, g, s_lo, s_hi, 0);
+      TMQ_CUDA(cudaGetLastError()); c->launches++;
+      // my z = 0 slice goes to the backward neighbour (its z = Z halo), my z = Z-1 slice to the forward neighbour (its z = -1 halo)
+      TMQ_TRY(comm_sendrecv_dim(c, 2, s_lo, s_hi, /*from fwd: its z = 0*/ r_hi, /*from bwd: its z = Z-1*/ r_lo, nz * sizeof(double), c->stream));
+      ext_zface_kernel<<<blas_grid(), 256, 0, c->stream>>>(E, ext, g, r_lo, r_hi, 1);
+      TMQ_CUDA(cudaGetLastError()); c->launches++;
+    }
+    if (g.part[3]) {
+      const size_t slice = (size_t)ext.E[0] * ext.E[1] * ext.E[2] * 72;       // doubles per extended t slice
+      double *t_first = E + slice * 1, *t_last = E + slice * (size_t)g.X[3];     // interior t = 0 and t = T-1 (ext index t + 1)
+      double *halo_lo = E, *halo_hi = E + slice * (size_t)(g.X[3] + 1);
+      TMQ_TRY(comm_sendrecv_dim(c, 3, t_first, t_last, /*from fwd: its t = 0*/ halo_hi, /*from bwd: its t = T-1*/ halo_lo,
+                                slice * sizeof(double), c->stream));
+    }
+    ext.d = E;
+  }
+  if (c->recon == 12) clover_compute_kernel<12><<<grid, 128, 0, c->stream>>>((VecT<double> *)c->clov_c_d.d, c->gauge_d.d, ext, c->g, S, clover_coeff);
+  else clover_compute_kernel<18><<<grid, 128, 0, c->stream>>>((VecT<double> *)c->clov_c_d.d, c->gauge_d.d, ext, c->g, S, clover_coeff);
   TMQ_CUDA(cudaGetLastError()); c->launches++;
+  if (E) { TMQ_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(E); if (zbuf) cudaFree(zbuf); }
   TMQ_CUDA(blas_copy(c->clov_c_s.d, 4, c->clov_c_d.d, 8, nv, c->stream)); c->launches++;
   c->clover_on = true; c->clover_coeff = clover_coeff; c->clov_inv_valid = false;
   if (c->op_set) TMQ_TRY(clover_update_inverse(c));

@@ -117,6 +117,26 @@ int comm_exchange(tmq_ctx *c, int pi, int prec, cudaStream_t st) {
   return 0;
 }
 
+// generic neighbour exchange along one partitioned dimension (one-off set-up traffic such as the gauge halo of the clover
+// term): send_bwd -> rank-1, send_fwd -> rank+1, recv_from_fwd <- rank+1, recv_from_bwd <- rank-1; wraps locally on a grid of 1
+int comm_sendrecv_dim(tmq_ctx *c, int dim, const void *send_bwd, const void *send_fwd, void *recv_from_fwd, void *recv_from_bwd,
+                      size_t nbytes, cudaStream_t st) {
+  if (c->grid[dim] == 1) {
+    TMQ_CUDA(cudaMemcpyAsync(recv_from_fwd, send_bwd, nbytes, cudaMemcpyDeviceToDevice, st));
+    TMQ_CUDA(cudaMemcpyAsync(recv_from_bwd, send_fwd, nbytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (!c->comm) { set_error("lattice is partitioned across ranks but tmq_comm_init was not called"); return 1; }
+  const int rm = rank_of(c, dim, -1), rp = rank_of(c, dim, +1);
+  TMQ_NCCL(g_nccl.GroupStart());
+  TMQ_NCCL(g_nccl.Send(send_bwd, nbytes, ncclChar, rm, c->comm->comm, st));
+  TMQ_NCCL(g_nccl.Send(send_fwd, nbytes, ncclChar, rp, c->comm->comm, st));
+  TMQ_NCCL(g_nccl.Recv(recv_from_fwd, nbytes, ncclChar, rp, c->comm->comm, st));
+  TMQ_NCCL(g_nccl.Recv(recv_from_bwd, nbytes, ncclChar, rm, c->comm->comm, st));
+  TMQ_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
 // Peer-memory halo path: expose this rank's ghost arena to its neighbours with CUDA IPC and map theirs.  The
 // 64-byte handles travel through an ncclAllGather; every rank then opens the arenas of its (at most four)
 // neighbours, and an all-reduce makes the decision unanimous: if any mapping failed anywhere, every rank stays

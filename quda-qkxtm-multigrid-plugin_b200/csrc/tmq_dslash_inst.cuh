@@ -87,11 +87,13 @@ static cudaError_t launch_epi(bool multi, const DslashArgs<F> &A, cudaStream_t s
   // callers fill nblk[] (segment sizes in CTAs); a plain launch has nblk = {ceil(nsites/128), 0, 0}
   const int grid = A.nblk[0] + A.nblk[1] + A.nblk[2];
   if (grid == 0) return cudaSuccess;
-  // twisted-clover: only the epilogues that apply a site matrix have a clover variant (single rank this round)
+  // twisted-clover: only the epilogues that apply a site matrix have a clover variant
   constexpr bool HAS_SITE_OP = EpiTraits<EPI>::TW1 || EpiTraits<EPI>::TW3 || EpiTraits<EPI>::TWX;
   if (A.cl_inv != nullptr && HAS_SITE_OP) {
-    if (multi) return cudaErrorNotSupported;
-    if constexpr (HAS_SITE_OP) dslash_kernel<F, RECON, EPI, false, true><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);
+    if constexpr (HAS_SITE_OP) {
+      if (multi) dslash_kernel<F, RECON, EPI, true, true><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);
+      else       dslash_kernel<F, RECON, EPI, false, true><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);
+    }
     return cudaGetLastError();
   }
   if (multi) dslash_kernel<F, RECON, EPI, true><<<grid, TMQ_DSLASH_BLOCK, 0, st>>>(A);

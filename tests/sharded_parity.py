@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--recon", type=int, default=12)
     ap.add_argument("--p2p", type=int, default=2)
     ap.add_argument("--pack-async", type=int, default=0)
+    ap.add_argument("--clover", type=int, default=1, help="also check the twisted-clover variant")
     ap.add_argument("--amin", type=float, default=0.2, help="lower edge of the Chebyshev window (just above the wanted eigenvalues)")
     ap.add_argument("--eig", type=int, default=1, help="also run the (slower) eigensolver / deflation check")
     a = ap.parse_args()
@@ -114,6 +115,23 @@ def main():
         e = lu.rel_l2(pout.get(), slab(want))
         if not e < 1e-7:
             fails.append(("deflate", e))
+    # twisted-clover on the sharded lattice: the clover term is built from the gauge field with an exchanged halo
+    if a.clover:
+        csw = 1.57551
+        ctx.clover_load(csw * KAPPA)
+        o.set_clover(o.clover_compute(gauge_g, csw * KAPPA))
+        ref = np.zeros_like(psi_g); ref[:Vh_g] = o.mdagm(gauge_g, even_g, KAPPA, MU, 0)
+        s_in, s_out = ctx.spinor(8), ctx.spinor(8)
+        s_in.set(loc[:Vh]); ctx.mdagm(s_out, s_in)
+        e = lu.rel_l2(s_out.get(), lu.local_from_global_eo(ref, X, grid, coord)[:Vh])
+        if not e < 4e-13:
+            fails.append(("clover-mdagm", e))
+        x_ref, it_ref_c, _, _ = o.cg_mdagm(gauge_g, even_g, KAPPA, MU, 0, tol=1e-9, maxiter=5000)
+        info_c = ctx.cg_mdagm(x, b, tol=1e-9, maxiter=5000)
+        if abs(info_c["iter"] - it_ref_c) > 2 or info_c["true_res"] > 1.05e-9:
+            fails.append(("clover-cg", info_c, it_ref_c))
+        o.set_clover(None)
+        ctx.clover_free()
     n2 = ctx.norm2(b)
     if abs(n2 - np.sum(even_g * even_g)) > 1e-12 * n2:
         fails.append(("norm2-allreduce", n2))
