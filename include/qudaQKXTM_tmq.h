@@ -213,11 +213,11 @@ typedef struct {
   char arpack_logfile[512];    // unused (no ARPACK)
   double amin, amax;
   bool isEven;
-  bool isFullOp;               // must be false: the even-odd operator is the hot path
+  bool isFullOp;               // false: even-odd M_pc^dag M_pc; true: the unpreconditioned M^dag M (what calc_loops deflates with)
   int modeArpack;              // unused
 } qudaQKXTM_arpackInfo;
 
-// QKXTM_Deflation for the even-odd M^dag M: the Krylov basis and the eigenvectors stay resident in HBM (the reference
+// QKXTM_Deflation for the even-odd or the full M^dag M: the Krylov basis and the eigenvectors stay resident in HBM (the reference
 // keeps NkV host vectors and stages every ARPACK reverse-communication step through PCIe).  The eigensolver is a
 // thick-restart Lanczos inside libtmq (tmq_eigensolve); eigenvalues/residuals are recomputed with the true operator as
 // the reference does after zneupd.
@@ -248,6 +248,7 @@ public:
   void eigenSolver();                                                                  // Deflation.cpp:1069-1475
   void polynomialOperator(ColorSpinorField &out, const ColorSpinorField &in);         // :997-1063
   void deflateVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in);     // :614-800 (vec_in: host AoS)
+  void projectVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in, int is, int NeV_defl);   // :1926-2060 (isFullOp)
   void ApplyMdagM(Float *vec_out, Float *vec_in, QudaInvertParam *param);             // :189-281
   void copyEigenVectorToQKXTM_Vector(int eigenVector_id, Float *vec);                 // :449-536 (full volume, AoS)
   tmq_eigset *EigenSet() const { return set; }

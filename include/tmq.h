@@ -155,14 +155,17 @@ int tmq_gamma5(tmq_spinor *x);                                                  
  *      reverse communication with host-staged vectors and deflates with a host zgemv ------------------------------- */
 typedef struct tmq_eigset tmq_eigset;
 /* out = p(M^dag M) in: the Chebyshev filter with the reference's recurrence (delta = (amax-amin)/2, theta = (amax+amin)/2,
- * sigma_1 = -delta/theta; degree 0 copies).  One degree = 4 fused Dslash launches, the recurrence is their epilogue.  */
+ * sigma_1 = -delta/theta; degree 0 copies, degree -1 applies the bare M^dag M).  PARITY fields: the even-odd operator,
+ * FULL fields: the unpreconditioned one.  One degree = 4 fused Dslash launches, the recurrence is their epilogue.       */
 int tmq_poly_mdagm(tmq_spinor *out, const tmq_spinor *in, int deg, double amin, double amax);
-/* a set of PARITY vectors resident in HBM (Krylov basis / eigenvectors), replaces the host h_elem array              */
-tmq_eigset *tmq_eigset_alloc(tmq_ctx *, int nvec, int prec);
+/* a set of vectors resident in HBM (Krylov basis / eigenvectors), replaces the host h_elem array.  subset =
+ * TMQ_SUBSET_PARITY: the even-odd operator M_pc^dag M_pc; TMQ_SUBSET_FULL: the unpreconditioned M_full^dag M_full on
+ * [even | odd] fields (the reference's isFullOp, the branch calc_loops uses: lib/qudaQKXTM_interface.cpp:1725-1736)  */
+tmq_eigset *tmq_eigset_alloc(tmq_ctx *, int nvec, int prec, int subset);
 int tmq_eigset_free(tmq_eigset *);              /* before tmq_destroy of its context                                  */
 int tmq_eigset_size(const tmq_eigset *);
 tmq_spinor *tmq_eigset_vector(tmq_eigset *, int i);   /* handle of the i-th vector, owned by the set                  */
-/* nev eigenpairs of M_pc^dag M_pc by thick-restart Lanczos in a Krylov space of nkv vectors (set size >= nkv + 1).
+/* nev eigenpairs of M^dag M (even-odd or full, per the set's subset) by thick-restart Lanczos in a Krylov space of nkv vectors (set size >= nkv + 1).
  * which = 0: smallest (the reference's SR; with poly_deg > 0 the filter turns them into the dominant ones, as the
  * reference's SR <-> LR swap), 1: largest.  tol as ARPACK's: |beta q_m| <= tol max(eps^(2/3), |theta|).
  * On return vectors 0..nev-1 of the set hold orthonormal eigenvectors sorted by ascending eigenvalue, evals / resid

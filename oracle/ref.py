@@ -29,6 +29,7 @@ def lib():
         L.qref_download.argtypes = [dp, dp, dp]
         L.qref_scale_vector.argtypes = [dp, C.c_double]
         L.qref_apply_gamma5_double.argtypes = [dp]
+        L.qref_calculate_plaq.argtypes = [dp]; L.qref_calculate_plaq.restype = C.c_double
         _lib = L
     return _lib
 
@@ -85,6 +86,10 @@ class Ref:
 
     def gamma5(self, vec):
         v = vec.copy(); self.L.qref_apply_gamma5_double(_dp(v)); return v
+
+    def plaquette(self, gauge):
+        """QKXTM_Gauge::calculatePlaq on the QKXTM device layout [4][3][3][V][2]"""
+        return self.L.qref_calculate_plaq(_dp(np.ascontiguousarray(gauge, dtype=np.float64)))
 
 
 # ---- the reference's host utility file qkxtm/QKXTM_util.cpp compiled in place (oracle/_ref/libqkxtm_util_ref.so) ------

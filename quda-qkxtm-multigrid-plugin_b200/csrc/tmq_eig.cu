@@ -53,17 +53,52 @@ static int cheb_step(tmq_ctx *c, int prec, void *out, const void *y, const void 
   return apply_hop(c, prec, out, t0, k4);
 }
 
-int op_poly_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int deg, double amin, double amax) {
+// the same step for the FULL (unpreconditioned) operator M_full = A - kappa D on [even | odd] fields:
+//   w = M y (two launches), out_p = d1 (A^dag w_p - kappa D^dag w_q) + d2 y_p + d3 tm1_p (two launches, recurrence fused)
+static int cheb_step_full(tmq_ctx *c, int prec, void *out, const void *y, const void *tm1, double d1, double d2, double d3, void *w) {
   const size_t pb = parity_bytes(c, prec);
-  if (deg <= 0) { TMQ_CUDA(cudaMemcpyAsync(out, in, pb, cudaMemcpyDeviceToDevice, c->stream)); return 0; }
+  for (int p = 0; p < 2; p++) {
+    HopSpec s; s.epi = EPI_TWX_XPAY; s.out_parity = p; s.dagger = 0; s.tx = tw_A(c, 0); s.k = -c->kappa;
+    s.x = (const char *)y + (size_t)p * pb;
+    TMQ_TRY(apply_hop(c, prec, (char *)w + (size_t)p * pb, (const char *)y + (size_t)(1 - p) * pb, s));
+  }
+  for (int p = 0; p < 2; p++) {
+    HopSpec s; s.epi = EPI_CHEB; s.out_parity = p; s.dagger = 1; s.tx = tw_A(c, 1); s.k = -c->kappa;
+    s.x = (const char *)w + (size_t)p * pb;
+    s.y = (const char *)y + (size_t)p * pb;
+    s.r = tm1 ? (char *)const_cast<void *>(tm1) + (size_t)p * pb : nullptr;
+    s.d1 = d1; s.d2 = d2; s.d3 = d3;
+    TMQ_TRY(apply_hop(c, prec, (char *)out + (size_t)p * pb, (const char *)w + (size_t)(1 - p) * pb, s));
+  }
+  return 0;
+}
+
+static int eig_full_scratch(tmq_ctx *c, int prec, void *buf[3]);
+
+// subset = 1: p(M_pc^dag M_pc) on PARITY fields; 2: p(M_full^dag M_full) on FULL fields (the reference's isFullOp).
+// deg = 0 copies; deg = -1 applies the bare operator M^dag M (no recurrence)
+int op_poly(tmq_ctx *c, int prec, int subset, void *out, const void *in, int deg, double amin, double amax) {
+  const size_t pb = parity_bytes(c, prec) * subset;
+  if (deg == 0) { TMQ_CUDA(cudaMemcpyAsync(out, in, pb, cudaMemcpyDeviceToDevice, c->stream)); return 0; }
   TMQ_REQUIRE(out != in, "polynomial operator: out must not alias in");
-  TMQ_TRY(ensure_scratch(c, prec, 4));
+  void *B[2], *w = nullptr;
+  if (subset == 1) {
+    TMQ_TRY(ensure_scratch(c, prec, 4));
+    B[0] = scr(c, prec, 2); B[1] = scr(c, prec, 3);
+  } else {
+    void *f[3];
+    TMQ_TRY(eig_full_scratch(c, prec, f));
+    B[0] = f[0]; B[1] = f[1]; w = f[2];
+  }
+  auto step = [&](void *o, const void *y, const void *tm1, double d1, double d2, double d3) -> int {
+    return subset == 1 ? cheb_step(c, prec, o, y, tm1, d1, d2, d3) : cheb_step_full(c, prec, o, y, tm1, d1, d2, d3, w);
+  };
+  if (deg < 0) return step(out, in, nullptr, 1.0, 0.0, 0.0);            // M^dag M itself
   const double delta = (amax - amin) / 2.0, theta = (amax + amin) / 2.0;
   const double sigma1 = -delta / theta;
-  void *B[2] = {scr(c, prec, 2), scr(c, prec, 3)};
   // degree 1
   void *dst = (deg == 1) ? out : B[0];
-  TMQ_TRY(cheb_step(c, prec, dst, in, nullptr, sigma1 / delta, 1.0, 0.0));
+  TMQ_TRY(step(dst, in, nullptr, sigma1 / delta, 1.0, 0.0));
   if (deg == 1) return 0;
   const void *tm1 = in;     // T_{i-2}
   void *tm2 = B[0];         // T_{i-1}
@@ -74,11 +109,14 @@ int op_poly_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int deg, doub
     // destination: the user's buffer on the last step, otherwise the buffer holding T_{i-2} (in place) -- except at
     // i = 2, where T_0 is the caller's input and must survive
     void *o = (i == deg) ? out : (i == 2 ? B[1] : const_cast<void *>(tm1));
-    TMQ_TRY(cheb_step(c, prec, o, tm2, tm1, d1, d2, d3));
+    TMQ_TRY(step(o, tm2, tm1, d1, d2, d3));
     tm1 = tm2; tm2 = o;
     sigma_old = sigma;
   }
   return 0;
+}
+int op_poly_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int deg, double amin, double amax) {
+  return op_poly(c, prec, 1, out, in, deg < 0 ? 0 : deg, amin, amax);
 }
 
 // ---- block inner products / block updates -------------------------------------------------------------------------------
@@ -279,6 +317,7 @@ using namespace tmq;
 struct tmq_eigset {
   tmq_ctx *ctx;
   int prec;
+  int subset;      // TMQ_SUBSET_PARITY: even-odd operator; TMQ_SUBSET_FULL: the unpreconditioned operator (isFullOp)
   std::vector<tmq_spinor *> vec;
 };
 
@@ -292,6 +331,7 @@ struct EigWork {
   void **d_ptrs = nullptr;        // device array of basis pointers [cap]
   double *d_Q = nullptr;          // rotation matrix [cap*cap]
   int cap = 0;
+  void *full[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // FULL-field scratch per precision (full-operator filter)
 };
 static std::vector<std::pair<tmq_ctx *, EigWork>> g_work;
 
@@ -315,6 +355,19 @@ static EigWork *eig_work(tmq_ctx *c, int cap) {
   w->cap = cap;
   return w;
 }
+static int eig_full_scratch(tmq_ctx *c, int prec, void *buf[3]) {
+  EigWork *w = eig_work(c, 1);
+  if (!w) return 1;
+  const int pi = prec == 8 ? 0 : 1;
+  for (int i = 0; i < 3; i++) {
+    if (!w->full[pi][i]) {
+      TMQ_CUDA(cudaMalloc(&w->full[pi][i], 2 * parity_bytes(c, prec)));
+      TMQ_CUDA(cudaMemsetAsync(w->full[pi][i], 0, 2 * parity_bytes(c, prec), c->stream));
+    }
+    buf[i] = w->full[pi][i];
+  }
+  return 0;
+}
 void eig_release(tmq_ctx *c) {
   for (size_t i = 0; i < g_work.size(); i++)
     if (g_work[i].first == c) {
@@ -324,6 +377,7 @@ void eig_release(tmq_ctx *c) {
       if (w.h_coef) cudaFreeHost(w.h_coef);
       if (w.d_ptrs) cudaFree(w.d_ptrs);
       if (w.d_Q) cudaFree(w.d_Q);
+      for (int pi = 0; pi < 2; pi++) for (int k = 0; k < 3; k++) if (w.full[pi][k]) cudaFree(w.full[pi][k]);
       g_work.erase(g_work.begin() + i);
       return;
     }
@@ -331,8 +385,7 @@ void eig_release(tmq_ctx *c) {
 
 // coef[0..2nv) = V^H w for the first nv vectors of `vp` (all-reduced over ranks); result left on the device and
 // mirrored into h_coef (host-visible after the returned sync)
-static int basis_cdot(tmq_ctx *c, EigWork *W, int prec, void *const *vp, int nv, const void *w, bool to_host) {
-  const size_t n = (size_t)6 * c->g.Vh;
+static int basis_cdot(tmq_ctx *c, EigWork *W, int prec, size_t n, void *const *vp, int nv, const void *w, bool to_host) {
   for (int j0 = 0; j0 < nv; j0 += EIG_NB) {
     const int nb = std::min(EIG_NB, nv - j0);
     TMQ_CUDA(cdot_block(prec, nb, vp + j0, w, n, W->partials, c->ticket, W->coef + 2 * j0, c->stream));
@@ -346,8 +399,7 @@ static int basis_cdot(tmq_ctx *c, EigWork *W, int prec, void *const *vp, int nv,
   return 0;
 }
 // w += sign * sum_j coef_j v_j
-static int basis_caxpy(tmq_ctx *c, EigWork *W, int prec, void *const *vp, int nv, double sign, void *w) {
-  const size_t n = (size_t)6 * c->g.Vh;
+static int basis_caxpy(tmq_ctx *c, EigWork *W, int prec, size_t n, void *const *vp, int nv, double sign, void *w) {
   for (int j0 = 0; j0 < nv; j0 += EIG_NB) {
     const int nb = std::min(EIG_NB, nv - j0);
     TMQ_CUDA(caxpy_block(prec, nb, vp + j0, W->coef + 2 * j0, sign, w, n, c->stream));
@@ -355,9 +407,8 @@ static int basis_caxpy(tmq_ctx *c, EigWork *W, int prec, void *const *vp, int nv
   }
   return 0;
 }
-static int basis_rotate(tmq_ctx *c, EigWork *W, int prec, void *const *vp, int m, int k, const std::vector<double> &Qmk) {
+static int basis_rotate(tmq_ctx *c, EigWork *W, int prec, size_t n, void *const *vp, int m, int k, const std::vector<double> &Qmk) {
   // Qmk: m x k row-major
-  const size_t n = (size_t)6 * c->g.Vh;
   TMQ_CUDA(cudaMemcpyAsync(W->d_ptrs, vp, (size_t)m * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
   TMQ_CUDA(cudaMemcpyAsync(W->d_Q, Qmk.data(), (size_t)m * k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   const size_t vb = vec_bytes(prec);
@@ -380,8 +431,8 @@ static int basis_rotate(tmq_ctx *c, EigWork *W, int prec, void *const *vp, int m
   return 0;
 }
 
-static int vec_norm2(tmq_ctx *c, int prec, const void *x, double *out) {
-  TMQ_CUDA(blas_norm2(prec, x, (size_t)6 * c->g.Vh, BlasRed{c->partials, c->ticket, c->scal, SC_T0}, c->stream)); c->launches++;
+static int vec_norm2(tmq_ctx *c, int prec, size_t n, const void *x, double *out) {
+  TMQ_CUDA(blas_norm2(prec, x, n, BlasRed{c->partials, c->ticket, c->scal, SC_T0}, c->stream)); c->launches++;
   TMQ_TRY(reduce_finish(c, SC_T0, 1));
   return fetch_scal(c, SC_T0, 1, out);
 }
@@ -392,24 +443,27 @@ extern "C" {
 
 int tmq_poly_mdagm(tmq_spinor *out, const tmq_spinor *in, int deg, double amin, double amax) {
   TMQ_REQUIRE(out && in, "null spinor");
-  TMQ_REQUIRE(out->subset == TMQ_SUBSET_PARITY && in->subset == TMQ_SUBSET_PARITY, "parity fields required");
+  TMQ_REQUIRE(out->subset == in->subset, "out and in must both be PARITY (even-odd operator) or both FULL (full operator)");
   TMQ_REQUIRE(out->ctx == in->ctx && out->prec == in->prec, "fields must share context and precision");
   tmq_ctx *c = out->ctx;
   TMQ_REQUIRE(c->op_set, "operator not set (tmq_op_set)");
-  TMQ_REQUIRE(deg >= 0, "polynomial degree must be >= 0");
-  TMQ_REQUIRE(deg == 0 || (amax > amin && amax + amin != 0.0), "Chebyshev window needs amax > amin");
+  TMQ_REQUIRE(deg >= -1, "polynomial degree must be >= 0 (or -1 for the bare M^dag M)");
+  TMQ_REQUIRE(deg <= 0 || (amax > amin && amax + amin != 0.0), "Chebyshev window needs amax > amin");
   TMQ_CUDA(cudaSetDevice(c->device));
-  TMQ_TRY(op_poly_mdagm(c, out->prec, out->d, in->d, deg, amin, amax));
+  TMQ_TRY(op_poly(c, out->prec, out->subset, out->d, in->d, deg, amin, amax));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   return check_device_error(c);
 }
 
-tmq_eigset *tmq_eigset_alloc(tmq_ctx *c, int nvec, int prec) {
-  if (!c || nvec < 1 || (prec != 8 && prec != 4)) { set_error("tmq_eigset_alloc: bad arguments"); return nullptr; }
+tmq_eigset *tmq_eigset_alloc(tmq_ctx *c, int nvec, int prec, int subset) {
+  if (!c || nvec < 1 || (prec != 8 && prec != 4) || (subset != TMQ_SUBSET_PARITY && subset != TMQ_SUBSET_FULL)) {
+    set_error("tmq_eigset_alloc: bad arguments");
+    return nullptr;
+  }
   tmq_eigset *s = new tmq_eigset();
-  s->ctx = c; s->prec = prec;
+  s->ctx = c; s->prec = prec; s->subset = subset;
   for (int i = 0; i < nvec; i++) {
-    tmq_spinor *v = tmq_spinor_alloc(c, prec, TMQ_SUBSET_PARITY);
+    tmq_spinor *v = tmq_spinor_alloc(c, prec, subset);
     if (!v) { for (tmq_spinor *u : s->vec) tmq_spinor_free(u); delete s; return nullptr; }
     s->vec.push_back(v);
   }
@@ -443,8 +497,9 @@ int tmq_eigensolve(tmq_eigset *set, int nev, int nkv, int poly_deg, double amin,
   TMQ_CUDA(cudaSetDevice(c->device));
   EigWork *W = eig_work(c, m + 1);
   if (!W) return 1;
-  TMQ_TRY(ensure_scratch(c, prec, 5));
-  const size_t n = (size_t)6 * c->g.Vh, pb = parity_bytes(c, prec);
+  const int subset = set->subset;
+  if (subset == TMQ_SUBSET_PARITY) TMQ_TRY(ensure_scratch(c, prec, 5));
+  const size_t n = (size_t)6 * c->g.Vh * subset, pb = parity_bytes(c, prec) * subset;
   std::vector<void *> vp(m + 1);
   for (int j = 0; j <= m; j++) vp[j] = set->vec[j]->d;
   // with the Chebyshev filter the wanted end of the spectrum becomes the dominant one of p(M^dag M), as the
@@ -452,8 +507,8 @@ int tmq_eigensolve(tmq_eigset *set, int nev, int nkv, int poly_deg, double amin,
   const bool acc = poly_deg > 0;
   const bool largest = acc ? (which == 0) : (which == 1);
   auto apply_B = [&](void *out, const void *in) -> int {
-    if (acc) return op_poly_mdagm(c, prec, out, in, poly_deg, amin, amax);
-    return op_mdagm(c, prec, out, in, SC_T3);
+    if (acc) return op_poly(c, prec, subset, out, in, poly_deg, amin, amax);
+    return subset == TMQ_SUBSET_PARITY ? op_mdagm(c, prec, out, in, SC_T3) : op_poly(c, prec, subset, out, in, -1, 0, 0);
   };
   int nmatvec = 0;
 
@@ -464,7 +519,7 @@ int tmq_eigensolve(tmq_eigset *set, int nev, int nkv, int poly_deg, double amin,
     else random_fill_kernel<float><<<blas_grid(), 256, 0, c->stream>>>((VecT<float> *)vp[0], n, key);
     TMQ_CUDA(cudaGetLastError()); c->launches++;
     double nrm;
-    TMQ_TRY(vec_norm2(c, prec, vp[0], &nrm));
+    TMQ_TRY(vec_norm2(c, prec, n, vp[0], &nrm));
     TMQ_CUDA(blas_ax(prec, 1.0 / sqrt(nrm), vp[0], n, c->stream)); c->launches++;
   }
 
@@ -479,14 +534,14 @@ int tmq_eigensolve(tmq_eigset *set, int nev, int nkv, int poly_deg, double amin,
       TMQ_TRY(apply_B(w, vp[j]));
       nmatvec++;
       // full re-orthogonalisation against v_0..v_j, classical Gram-Schmidt twice; alpha_j = Re <v_j, w>
-      TMQ_TRY(basis_cdot(c, W, prec, vp.data(), j + 1, w, true));
+      TMQ_TRY(basis_cdot(c, W, prec, n, vp.data(), j + 1, w, true));
       alpha[j] = W->h_coef[2 * j];
-      TMQ_TRY(basis_caxpy(c, W, prec, vp.data(), j + 1, -1.0, w));
-      TMQ_TRY(basis_cdot(c, W, prec, vp.data(), j + 1, w, true));
+      TMQ_TRY(basis_caxpy(c, W, prec, n, vp.data(), j + 1, -1.0, w));
+      TMQ_TRY(basis_cdot(c, W, prec, n, vp.data(), j + 1, w, true));
       alpha[j] += W->h_coef[2 * j];
-      TMQ_TRY(basis_caxpy(c, W, prec, vp.data(), j + 1, -1.0, w));
+      TMQ_TRY(basis_caxpy(c, W, prec, n, vp.data(), j + 1, -1.0, w));
       double nrm;
-      TMQ_TRY(vec_norm2(c, prec, w, &nrm));
+      TMQ_TRY(vec_norm2(c, prec, n, w, &nrm));
       beta[j] = sqrt(nrm);
       TMQ_REQUIRE(beta[j] > 0.0 && beta[j] == beta[j], "Lanczos breakdown at step %d (invariant subspace or NaN)", j);
       TMQ_CUDA(blas_ax(prec, 1.0 / beta[j], w, n, c->stream)); c->launches++;
@@ -515,7 +570,7 @@ int tmq_eigensolve(tmq_eigset *set, int nev, int nkv, int poly_deg, double amin,
     std::vector<double> Qmk((size_t)m * keep);
     for (int r = 0; r < m; r++)
       for (int i = 0; i < keep; i++) Qmk[(size_t)r * keep + i] = Q[(size_t)r * m + order[i]];
-    TMQ_TRY(basis_rotate(c, W, prec, vp.data(), m, keep, Qmk));
+    TMQ_TRY(basis_rotate(c, W, prec, n, vp.data(), m, keep, Qmk));
     if (done) break;
     for (int i = 0; i < keep; i++) { theta[i] = ritz[order[i]]; s[i] = beta[m - 1] * Q[(size_t)(m - 1) * m + order[i]]; }
     TMQ_CUDA(cudaMemcpyAsync(vp[keep], vp[m], pb, cudaMemcpyDeviceToDevice, c->stream));
@@ -526,14 +581,14 @@ int tmq_eigensolve(tmq_eigset *set, int nev, int nkv, int poly_deg, double amin,
   std::vector<double> lam(nev), res(nev);
   void *t = vp[m];
   for (int i = 0; i < nev; i++) {
-    TMQ_TRY(op_mdagm(c, prec, t, vp[i], SC_T3));
+    TMQ_TRY(subset == TMQ_SUBSET_PARITY ? op_mdagm(c, prec, t, vp[i], SC_T3) : op_poly(c, prec, subset, t, vp[i], -1, 0, 0));
     nmatvec++;
     void *one[1] = {vp[i]};
-    TMQ_TRY(basis_cdot(c, W, prec, one, 1, t, true));
+    TMQ_TRY(basis_cdot(c, W, prec, n, one, 1, t, true));
     lam[i] = W->h_coef[0];
     TMQ_CUDA(blas_axpby(prec, -lam[i], vp[i], 1.0, t, n, c->stream)); c->launches++;
     double nrm;
-    TMQ_TRY(vec_norm2(c, prec, t, &nrm));
+    TMQ_TRY(vec_norm2(c, prec, n, t, &nrm));
     res[i] = sqrt(nrm);
   }
   // ascending eigenvalue order; the set's handles are permuted, no data moves
@@ -554,12 +609,12 @@ int tmq_deflate(tmq_spinor *out, const tmq_spinor *in, tmq_eigset *set, const do
   TMQ_REQUIRE(out && in && set && evals, "null argument");
   tmq_ctx *c = set->ctx;
   TMQ_REQUIRE(out->ctx == c && in->ctx == c, "fields belong to another context");
-  TMQ_REQUIRE(out->subset == TMQ_SUBSET_PARITY && in->subset == TMQ_SUBSET_PARITY, "parity fields required");
+  TMQ_REQUIRE(out->subset == set->subset && in->subset == set->subset, "fields must have the site subset of the eigenvector set");
   TMQ_REQUIRE(out->prec == set->prec && in->prec == set->prec, "fields must have the precision of the eigenvector set");
   TMQ_REQUIRE(nvec >= 0 && nvec <= (int)set->vec.size(), "bad number of eigenvectors");
   TMQ_REQUIRE(out->d != in->d, "out must not alias in");
   TMQ_CUDA(cudaSetDevice(c->device));
-  const size_t pb = parity_bytes(c, set->prec);
+  const size_t pb = parity_bytes(c, set->prec) * set->subset, n = (size_t)6 * c->g.Vh * set->subset;
   TMQ_CUDA(cudaMemsetAsync(out->d, 0, pb, c->stream));
   if (nvec == 0) { TMQ_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
   EigWork *W = eig_work(c, nvec);
@@ -567,13 +622,13 @@ int tmq_deflate(tmq_spinor *out, const tmq_spinor *in, tmq_eigset *set, const do
   std::vector<void *> vp(nvec);
   for (int j = 0; j < nvec; j++) vp[j] = set->vec[j]->d;
   // U^dag in -> Lambda^-1 -> U (.)   (reference: zgemv ConjTrans, MPI_Allreduce, divide, zgemv NoTrans)
-  TMQ_TRY(basis_cdot(c, W, set->prec, vp.data(), nvec, in->d, true));
+  TMQ_TRY(basis_cdot(c, W, set->prec, n, vp.data(), nvec, in->d, true));
   for (int j = 0; j < nvec; j++) {
     TMQ_REQUIRE(evals[j] != 0.0, "zero eigenvalue %d in deflation", j);
     W->h_coef[2 * j] /= evals[j]; W->h_coef[2 * j + 1] /= evals[j];
   }
   TMQ_CUDA(cudaMemcpyAsync(W->coef, W->h_coef, (size_t)2 * nvec * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  TMQ_TRY(basis_caxpy(c, W, set->prec, vp.data(), nvec, 1.0, out->d));
+  TMQ_TRY(basis_caxpy(c, W, set->prec, n, vp.data(), nvec, 1.0, out->d));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -582,11 +637,11 @@ int tmq_project(tmq_spinor *out, const tmq_spinor *in, tmq_eigset *set, int nvec
   TMQ_REQUIRE(out && in && set, "null argument");
   tmq_ctx *c = set->ctx;
   TMQ_REQUIRE(out->ctx == c && in->ctx == c, "fields belong to another context");
-  TMQ_REQUIRE(out->subset == TMQ_SUBSET_PARITY && in->subset == TMQ_SUBSET_PARITY, "parity fields required");
+  TMQ_REQUIRE(out->subset == set->subset && in->subset == set->subset, "fields must have the site subset of the eigenvector set");
   TMQ_REQUIRE(out->prec == set->prec && in->prec == set->prec, "fields must have the precision of the eigenvector set");
   TMQ_REQUIRE(nvec >= 0 && nvec <= (int)set->vec.size(), "bad number of eigenvectors");
   TMQ_CUDA(cudaSetDevice(c->device));
-  const size_t pb = parity_bytes(c, set->prec);
+  const size_t pb = parity_bytes(c, set->prec) * set->subset, n = (size_t)6 * c->g.Vh * set->subset;
   if (out->d != in->d) TMQ_CUDA(cudaMemcpyAsync(out->d, in->d, pb, cudaMemcpyDeviceToDevice, c->stream));
   if (nvec > 0) {
     EigWork *W = eig_work(c, nvec);
@@ -595,8 +650,8 @@ int tmq_project(tmq_spinor *out, const tmq_spinor *in, tmq_eigset *set, int nvec
     for (int j = 0; j < nvec; j++) vp[j] = set->vec[j]->d;
     // vec_in - U (U^dag vec_in): zgemv ConjTrans, all-reduce, zgemv NoTrans, zaxpy in the reference; the coefficients
     // never leave the device here
-    TMQ_TRY(basis_cdot(c, W, set->prec, vp.data(), nvec, in->d, false));
-    TMQ_TRY(basis_caxpy(c, W, set->prec, vp.data(), nvec, -1.0, out->d));
+    TMQ_TRY(basis_cdot(c, W, set->prec, n, vp.data(), nvec, in->d, false));
+    TMQ_TRY(basis_caxpy(c, W, set->prec, n, vp.data(), nvec, -1.0, out->d));
   }
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -452,18 +452,18 @@ QKXTM_Deflation<Float>::QKXTM_Deflation(QudaInvertParam *param, qudaQKXTM_arpack
   isEv = ai.isEven; isFullOp = ai.isFullOp; flavor_sign = param->mu; invert_param = param;
   total_length_per_NeV = 0; bytes_total_length_per_NeV = 0;
   if (NeV == 0) { printfQuda("######### Got NeV = 0 #########\n"); return; }
-  if (isFullOp) errorQuda("This path provides the even-odd operator only (isFullOp = false)");
+
   if (spectrumPart != SR && spectrumPart != LR && spectrumPart != SM && spectrumPart != LM)
     errorQuda("eigenSolver: Option for spectrumPart is suspicious");
   check_param(param);
-  if (((int)param->matpc_type & 1) != (isEv ? 0 : 1)) errorQuda("matpc_type does not match arpackInfo.isEven");
-  invert_param->solve_type = QUDA_NORMOP_PC_SOLVE;                                     // Deflation.cpp:133
-  total_length_per_NeV = (G.localVolume / 2) * 4 * 3 * 2;
+  if (!isFullOp && ((int)param->matpc_type & 1) != (isEv ? 0 : 1)) errorQuda("matpc_type does not match arpackInfo.isEven");
+  invert_param->solve_type = isFullOp ? QUDA_NORMOP_SOLVE : QUDA_NORMOP_PC_SOLVE;     // Deflation.cpp:132-133
+  total_length_per_NeV = (G.localVolume / (isFullOp ? 1 : 2)) * 4 * 3 * 2;
   bytes_total_length_per_NeV = (size_t)total_length_per_NeV * sizeof(Float);
   eigenValues = (Float *)calloc((size_t)2 * NkV, sizeof(Float));
   residuals = (double *)calloc((size_t)NkV, sizeof(double));
   if (!eigenValues || !residuals) errorQuda("Error: Out of memory of eigenValues.");
-  set = tmq_eigset_alloc(G.ctx, NkV + 1, (int)sizeof(Float));
+  set = tmq_eigset_alloc(G.ctx, NkV + 1, (int)sizeof(Float), isFullOp ? TMQ_SUBSET_FULL : TMQ_SUBSET_PARITY);
   if (!set) errorQuda("libtmq: %s", tmq_last_error());
 }
 template <typename Float> QKXTM_Deflation<Float>::~QKXTM_Deflation() {
@@ -473,7 +473,8 @@ template <typename Float> QKXTM_Deflation<Float>::~QKXTM_Deflation() {
 }
 template <typename Float> void QKXTM_Deflation<Float>::printInfo() {
   printfQuda("\n======= DEFLATION INFO =======\n");
-  printfQuda(" Will calculate EigenVectors for the %s %smu operator\n", isEv ? "even-even" : "odd-odd", (flavor_sign > 0) ? "+" : "-");
+  if (isFullOp) printfQuda(" The EigenVectors are for the Full %smu operator\n", (flavor_sign > 0) ? "+" : "-");
+  else printfQuda(" Will calculate EigenVectors for the %s %smu operator\n", isEv ? "even-even" : "odd-odd", (flavor_sign > 0) ? "+" : "-");
   printfQuda(" Number of requested EigenVectors is %d in precision %d\n", NeV, (int)sizeof(Float));
   printfQuda(" The Size of Krylov space is %d\n", NkV);
   printfQuda(" Device GB for the Krylov space: %lf\n", (NkV + 1) * ((double)bytes_total_length_per_NeV / (1024. * 1024. * 1024.)));
@@ -496,7 +497,7 @@ template <typename Float> void QKXTM_Deflation<Float>::eigenSolver() {
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printfQuda("eigenSolver: Number of converged eigenvalues: %d (restarts %d, operator applications %d)\n", nconv, nrestarts, nmatvec);
   printfQuda("eigenSolver: TIME_REPORT - Eigenvalue calculation: %f sec\n", secs);
-  printfQuda("Eigenvalues of the Even-Odd Dirac operator:\n===========\n");
+  printfQuda("Eigenvalues of the %s Dirac operator:\n===========\n", isFullOp ? "Full" : "Even-Odd");
   for (int i = 0; i < NeV; i++) {
     eigenValues[2 * i] = (Float)ev[i]; eigenValues[2 * i + 1] = 0;
     residuals[i] = rs[i];
@@ -514,7 +515,8 @@ template <typename Float> void QKXTM_Deflation<Float>::deflateVector(QKXTM_Vecto
   QKXTM_Vector<Float> stage(BOTH, VECTOR);
   stage.packVector(vec_in.H_elem());
   stage.loadVector();
-  ColorSpinorField in(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION), out(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  const QudaSiteSubset sub = isFullOp ? QUDA_FULL_SITE_SUBSET : QUDA_PARITY_SITE_SUBSET;
+  ColorSpinorField in(sub, QUDA_DOUBLE_PRECISION), out(sub, QUDA_DOUBLE_PRECISION);
   stage.uploadToCuda(&in, isEv);
   std::vector<double> ev(NeV);
   for (int i = 0; i < NeV; i++) ev[i] = (double)eigenValues[2 * i];
@@ -523,13 +525,38 @@ template <typename Float> void QKXTM_Deflation<Float>::deflateVector(QKXTM_Vecto
   vec_defl.unloadVector();        // keep h_elem (SoA) in step with the device copy, as packVector + loadVector leave it
 }
 template <typename Float> void QKXTM_Deflation<Float>::ApplyMdagM(Float *vec_out, Float *vec_in, QudaInvertParam *param) {
-  ::ApplyMdagM((double *)vec_out, (double *)vec_in, param, isEv);
+  if (!isFullOp) { ::ApplyMdagM((double *)vec_out, (double *)vec_in, param, isEv); return; }
+  // full operator branch (Deflation.cpp:194-228)
+  create_dirac(param);
+  QKXTM_Vector<double> Kvec(BOTH, VECTOR);
+  ColorSpinorField in(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION), out(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  Kvec.packVector((double *)vec_in);
+  Kvec.loadVector();
+  Kvec.uploadToCuda(&in, false);
+  TMQ_OK(tmq_poly_mdagm(out.handle(), in.handle(), -1, 0.0, 0.0));      // diracOp->MdagM on the full field (:213)
+  Kvec.downloadFromCuda(&out, false);
+  Kvec.unloadVector();
+  Kvec.unpackVector();
+  memcpy(vec_out, Kvec.H_elem(), (size_t)G.localVolume * 24 * sizeof(double));
+}
+// vec_defl = vec_in - U U^dag vec_in over the first NeV_defl eigenvectors (Deflation.cpp:1926-2060; full operator only)
+template <typename Float> void QKXTM_Deflation<Float>::projectVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in, int is, int NeV_defl) {
+  (void)is;
+  if (!isFullOp) errorQuda("projectVector: This function only works with the Full Operator");
+  QKXTM_Vector<Float> stage(BOTH, VECTOR);
+  stage.packVector(vec_in.H_elem());
+  stage.loadVector();
+  ColorSpinorField in(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  stage.uploadToCuda(&in, false);
+  TMQ_OK(tmq_project(in.handle(), in.handle(), set, NeV_defl < NeV ? NeV_defl : NeV));
+  vec_defl.downloadFromCuda(&in, false);
+  vec_defl.unloadVector();
 }
 template <typename Float> void QKXTM_Deflation<Float>::copyEigenVectorToQKXTM_Vector(int id, Float *vec) {
   if (NeV == 0) return;
   if (id < 0 || id >= NeV) errorQuda("eigenvector index %d out of range", id);
   QKXTM_Vector<Float> stage(BOTH, VECTOR);
-  ColorSpinorField v(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  ColorSpinorField v(isFullOp ? QUDA_FULL_SITE_SUBSET : QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
   TMQ_OK(tmq_copy(v.handle(), tmq_eigset_vector(set, id)));
   stage.downloadFromCuda(&v, isEv);
   stage.download();

@@ -98,7 +98,7 @@ def load():
     L.tmq_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, dp, C.POINTER(C.c_longlong)]
     L.tmq_launch_count.restype = C.c_longlong; L.tmq_launch_count.argtypes = [vp]
     L.tmq_poly_mdagm.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double]
-    L.tmq_eigset_alloc.restype = vp; L.tmq_eigset_alloc.argtypes = [vp, C.c_int, C.c_int]
+    L.tmq_eigset_alloc.restype = vp; L.tmq_eigset_alloc.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.tmq_eigset_free.argtypes = [vp]; L.tmq_eigset_size.argtypes = [vp]
     L.tmq_eigset_vector.restype = vp; L.tmq_eigset_vector.argtypes = [vp, C.c_int]
     L.tmq_eigensolve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -178,9 +178,9 @@ class Spinor:
 class EigSet:
     """A set of parity vectors resident in HBM (tmq_eigset): Krylov basis / eigenvectors of QKXTM_Deflation."""
 
-    def __init__(self, ctx, nvec, prec=PREC_DOUBLE):
-        self.ctx, self.prec, self.nvec = ctx, prec, nvec
-        self.h = ctx.L.tmq_eigset_alloc(ctx.h, nvec, prec)
+    def __init__(self, ctx, nvec, prec=PREC_DOUBLE, subset=PARITY):
+        self.ctx, self.prec, self.nvec, self.subset = ctx, prec, nvec, subset
+        self.h = ctx.L.tmq_eigset_alloc(ctx.h, nvec, prec, subset)
         if not self.h:
             raise TmqError(ctx.L.tmq_last_error().decode())
         ctx._eigsets.add(self)
@@ -189,7 +189,7 @@ class EigSet:
         h = self.ctx.L.tmq_eigset_vector(self.h, i)
         if not h:
             raise TmqError(self.ctx.L.tmq_last_error().decode())
-        return Spinor(self.ctx, self.prec, PARITY, _handle=h)
+        return Spinor(self.ctx, self.prec, self.subset, _handle=h)
 
     def free(self):
         if self.h and self.ctx.h:
@@ -284,7 +284,7 @@ class Context:
     # -- eigensolver (QKXTM_Deflation)
     def poly_mdagm(self, out, inp, deg, amin, amax): _ck(self.L.tmq_poly_mdagm(out.h, inp.h, deg, amin, amax))
 
-    def eigset(self, nvec, prec=PREC_DOUBLE): return EigSet(self, nvec, prec)
+    def eigset(self, nvec, prec=PREC_DOUBLE, subset=PARITY): return EigSet(self, nvec, prec, subset)
 
     def eigensolve(self, eset, nev, nkv, poly_deg=0, amin=0.0, amax=0.0, tol=1e-10, max_restarts=100, which=0, seed=1):
         ev = np.zeros(nev); rs = np.zeros(nev)

@@ -39,6 +39,7 @@ if __name__ == "__main__":
         "download_both": r.download(even, odd),
         "scale": r.scale(vec, 2 * 0.1234),                                       # scaleVector_core.h
         "gamma5": r.gamma5(vec),                                                 # apply_gamma5_vector_core.h
+        "plaquette": np.array([r.plaquette(gauge)]),                             # plaquette_core.h + lib/qudaQKXTM_kernels.cu:910-957
     }
     np.savez_compressed(FIXTURE, **out)
     print("written", FIXTURE, os.path.getsize(FIXTURE), "bytes")

@@ -152,3 +152,61 @@ def test_deflation_projector(tmq):
     c.project(a, a, es, 4)
     assert lu.rel_l2(_cplx(a.get()), ref_p) < 1e-13
     c.close()
+
+
+# ---- the unpreconditioned operator (isFullOp: what calc_loops deflates with, lib/qudaQKXTM_interface.cpp:1725-1736) ----
+class FullSetup(Setup):
+    def __init__(self, T, X, part=None):
+        super().__init__(T, X, 0, part)
+        self.full = lu.spinor_eo_from_lex(lu.gaussian_spinor_lex(X, seed=101), X)
+
+    def A(self, v):
+        """oracle M_full^dag M_full on a complex vector of length 24 Vh ([even | odd] order)"""
+        from oracle.oracle import Oracle
+        self.orc = Oracle(self.X)
+        x = np.ascontiguousarray(np.stack([v.real, v.imag], axis=-1).reshape(2 * self.Vh, 4, 3, 2))
+        y = self.orc.mat(self.gauge, x, KAPPA, MU, 0)
+        return _cplx(self.orc.mat(self.gauge, y, KAPPA, MU, 1))
+
+
+@pytest.mark.parametrize("deg", [-1, 1, 2, 7])
+def test_full_operator_polynomial(tmq, deg):
+    from oracle.oracle import poly_operator
+    s = FullSetup(tmq, (4, 6, 4, 8))
+    c = s.ctx
+    a, b = c.spinor(8, tmq.FULL), c.spinor(8, tmq.FULL)
+    a.set(s.full)
+    c.poly_mdagm(b, a, deg, 0.05, 3.5)
+    ref = s.A(_cplx(s.full)) if deg < 0 else poly_operator(s.A, _cplx(s.full), deg, 0.05, 3.5)
+    assert lu.rel_l2(_cplx(b.get()), ref) < 5e-13, deg
+    c.close()
+
+
+@pytest.mark.parametrize("part", [None, (0, 0, 0, 1)])
+def test_full_operator_eigensolver_and_projection(tmq, part):
+    """isFullOp: smallest eigenpairs of M_full^dag M_full vs ARPACK on the oracle's full operator, and projectVector
+    (x - U U^dag x, lib/qudaQKXTM_Deflation.cpp:1926-2060) on FULL fields"""
+    from oracle.oracle import eigs_reference
+    s = FullSetup(tmq, X_SMALL, part)
+    c = s.ctx
+    nev, nkv = 6, 30
+    n = 24 * s.Vh
+    lam_ref, U_ref = eigs_reference(s.A, n, nev, nkv, "SR", tol=1e-12)
+    # Chebyshev window from the reference spectrum: just above the wanted eigenvalues, up to beyond the largest one
+    amin, amax = 1.6 * lam_ref[-1], 3.5
+    es = c.eigset(nkv + 1, tmq.PREC_DOUBLE, tmq.FULL)
+    r = c.eigensolve(es, nev, nkv, poly_deg=24, amin=amin, amax=amax, tol=1e-12, max_restarts=400, which=0, seed=7)
+    assert r["nconv"] == nev, r
+    assert np.allclose(r["evals"], lam_ref, rtol=1e-9, atol=0), (r["evals"], lam_ref)
+    V = np.stack([_cplx(es.vector(i).get()) for i in range(nev)], axis=1)
+    assert np.abs(V.conj().T @ V - np.eye(nev)).max() < 1e-11
+    sv = np.linalg.svd(U_ref.conj().T @ V, compute_uv=False)
+    assert sv.min() > 1 - 1e-8, sv
+    x, y = c.spinor(8, tmq.FULL), c.spinor(8, tmq.FULL)
+    x.set(s.full)
+    c.project(y, x, es, nev)
+    b = _cplx(s.full)
+    assert lu.rel_l2(_cplx(y.get()), b - V @ (V.conj().T @ b)) < 1e-13
+    c.deflate(y, x, es, r["evals"])
+    assert lu.rel_l2(_cplx(y.get()), V @ ((V.conj().T @ b) / r["evals"])) < 1e-12
+    c.close()

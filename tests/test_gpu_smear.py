@@ -135,4 +135,9 @@ def test_container_layout_kernels_match_reference_fixture(tmq):
     dg5 = d.put(vec)
     c.qkxtm_gamma5(dg5, 8)
     assert np.array_equal(d.get(dg5, vec.shape), gold["gamma5"])
+    # QKXTM_Gauge::calculatePlaq on the container's device layout vs the reference's plaquette kernel
+    _, gauge = G.golden_inputs()
+    dgauge = d.put(gauge)
+    want = float(gold["plaquette"][0])
+    assert abs(c.qkxtm_plaquette(dgauge, 8) - want) < 1e-12 * abs(want)
     d.close()

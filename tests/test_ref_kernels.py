@@ -76,3 +76,18 @@ def test_scale_and_gamma5_restatement_matches_reference(gold):
     g5 = Oracle(G.X).gamma5()
     v = _c(vec).reshape(4, 3, V)
     assert np.allclose(np.einsum("st,tcx->scx", g5, v), _c(gold["gamma5"]).reshape(4, 3, V), atol=0, rtol=0)
+
+
+def test_plaquette_restatement_matches_reference(gold):
+    """QKXTM_Gauge::calculatePlaq: the reference's plaquette kernel (block reduction emulated with one OS thread per CUDA
+    thread) against the oracle's plaquette on the same links in QDP even-odd order; the fixture uses the golden gauge field
+    (general complex matrices, not SU(3): the kernel is a polynomial in the links)"""
+    from oracle.oracle import Oracle
+    _, gauge = G.golden_inputs()
+    V = int(np.prod(G.X))
+    U_lex = np.transpose(_c(gauge), (0, 3, 1, 2))                    # [4][V][3][3]
+    gq = lu.gauge_qdp_from_lex(U_lex, G.X, t_boundary=+1)
+    assert abs(Oracle(G.X).plaquette(gq) - float(gold["plaquette"][0])) < 1e-13 * abs(float(gold["plaquette"][0]))
+    from oracle import ref
+    if ref.available():
+        assert ref.Ref(G.X).plaquette(gauge) == float(gold["plaquette"][0])
