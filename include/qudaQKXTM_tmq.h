@@ -117,6 +117,9 @@ typedef struct {                       // the hot-path slice of qudaQKXTMinfo (i
 
 void init_qudaQKXTM(qudaQKXTMinfo *info);      // lib/qudaQKXTM_kernels.cu:118-297 (one-shot; containers need it)
 void printf_qudaQKXTM();
+// include/qudaQKXTM_utils.h:36-37, lib/qudaQKXTM_utils.cpp:87-141 (gauge: 4 lexicographic link arrays, as packGauge takes)
+void testPlaquette(void **gauge);
+void testGaussSmearing(void **gauge);
 
 // stand-in for cudaColorSpinorField on this path: a device field in libtmq's native layout
 class ColorSpinorField {

@@ -144,6 +144,7 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
     A.cl_inv = (const VecT<F> *)(prec == 8 ? c->clov_inv_d.d : c->clov_inv_s.d) + off;
     A.cl_c = (const VecT<F> *)(prec == 8 ? c->clov_c_d.d : c->clov_c_s.d) + off;
     A.cl_dag1 = s.t1.dag; A.cl_dag3 = s.t3.dag;
+    A.out2 = (VecT<F> *)s.out2; A.cl_plain_x = s.cl_plain_x;
   }
 
   const Geom &g = c->g;
@@ -387,10 +388,14 @@ int op_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int pap_slot) {
   TMQ_TRY(apply_hop(c, prec, t0, in, k1));
   k2s.epi = EPI_MDAGM2; k2s.out_parity = p; k2s.t1 = tw_Ainv(c, 0); k2s.k = k2; k2s.x = in; k2s.t3 = tw_Ainv(c, 1);
   k2s.red_slot = pap_slot;
+  // twisted-clover: K2 also stores y = M in, and K4 forms y - k^2 D^dag u from it instead of applying A^dag to w
+  void *ybuf = nullptr;
+  if (c->clover_on) { TMQ_TRY(ensure_scratch(c, prec, 7)); ybuf = scr(c, prec, 6); k2s.out2 = ybuf; }
   TMQ_TRY(apply_hop(c, prec, t1, t0, k2s));
   k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1);
   TMQ_TRY(apply_hop(c, prec, t0, t1, k3));
   k4.epi = EPI_TWX_XPAY; k4.out_parity = p; k4.dagger = 1; k4.tx = tw_A(c, 1); k4.k = k2; k4.x = t1;
+  if (ybuf) { k4.x = ybuf; k4.cl_plain_x = 1; }
   return apply_hop(c, prec, out, t0, k4);
 }
 
@@ -405,10 +410,13 @@ static int cg_fused_matvec(tmq_ctx *c, int prec, void *r, const void *p_, int r2
   TMQ_TRY(apply_hop(c, prec, t0, p_, k1));
   k2s.epi = EPI_MDAGM2; k2s.out_parity = p; k2s.t1 = tw_Ainv(c, 0); k2s.k = k2; k2s.x = p_; k2s.t3 = tw_Ainv(c, 1);
   k2s.red_slot = SC_PAP;
+  void *ybuf = nullptr;
+  if (c->clover_on) { TMQ_TRY(ensure_scratch(c, prec, 7)); ybuf = scr(c, prec, 6); k2s.out2 = ybuf; }
   TMQ_TRY(apply_hop(c, prec, t1, t0, k2s));
   k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1);
   TMQ_TRY(apply_hop(c, prec, t0, t1, k3));
   k4.epi = EPI_CG4; k4.out_parity = p; k4.dagger = 1; k4.tx = tw_A(c, 1); k4.k = k2; k4.x = t1; k4.r = r;
+  if (ybuf) { k4.x = ybuf; k4.cl_plain_x = 1; }
   k4.red_slot = r2_new; k4.alpha_num = r2_old; k4.alpha_den = SC_PAP;
   return apply_hop(c, prec, nullptr, t0, k4);
 }

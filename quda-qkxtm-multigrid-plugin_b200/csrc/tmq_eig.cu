@@ -45,10 +45,13 @@ static int cheb_step(tmq_ctx *c, int prec, void *out, const void *y, const void 
     // w = A y - k^2 D t0   (= M_asym y)
     k2s.epi = EPI_TWX_XPAY; k2s.out_parity = p; k2s.tx = tw_A(c, 0); k2s.k = k2; k2s.x = y;
   }
+  void *ybuf = nullptr;
+  if (!asym && c->clover_on) { TMQ_TRY(ensure_scratch(c, prec, 7)); ybuf = scr(c, prec, 6); k2s.out2 = ybuf; }   // see op_mdagm
   TMQ_TRY(apply_hop(c, prec, t1, t0, k2s));
   k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1);
   TMQ_TRY(apply_hop(c, prec, t0, t1, k3));
   k4.epi = EPI_CHEB; k4.out_parity = p; k4.dagger = 1; k4.tx = tw_A(c, 1); k4.k = k2; k4.x = t1;
+  if (ybuf) { k4.x = ybuf; k4.cl_plain_x = 1; }
   k4.y = y; k4.r = const_cast<void *>(tm1); k4.d1 = d1; k4.d2 = d2; k4.d3 = d3;
   return apply_hop(c, prec, out, t0, k4);
 }

@@ -39,9 +39,9 @@ struct GaugeStore {
 };
 
 // per-precision scratch used by the operator (temporaries of M, M^dag M, CG)
-constexpr int NSCRATCH = 6;
+constexpr int NSCRATCH = 7;
 struct Scratch {
-  void *tmp[NSCRATCH] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // parity fields
+  void *tmp[NSCRATCH] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // parity fields
 };
 
 }  // namespace tmq
@@ -148,6 +148,8 @@ struct HopSpec {
   const void *x = nullptr;
   void *r = nullptr;
   const void *y = nullptr;          // EPI_CHEB
+  void *out2 = nullptr;             // clover EPI_MDAGM2: second output y = M p
+  int cl_plain_x = 0;               // clover: use the x term as it is
   double d1 = 0, d2 = 0, d3 = 0;    // EPI_CHEB
   int red_slot = SC_T3;
   int alpha_num = SC_ONE, alpha_den = SC_ONE;

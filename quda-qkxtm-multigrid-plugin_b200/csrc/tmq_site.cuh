@@ -483,7 +483,7 @@ TMQ_HD double dslash_site(const DslashArgs<F> &A, const Enum &en, uint32_t e, F 
       Spinor<F> x;
 #pragma unroll
       for (int j = 0; j < 6; j++) unpack_vec(x, j, A.x[(size_t)j * stride + c.idx]);
-      if (T::TWX) {
+      if (T::TWX && !A.cl_plain_x) {
         // (C + i ax g5) x
         Spinor<F> cx = x;
         clover_mul(cx, A.cl_c, c.idx, stride, false);
@@ -506,7 +506,11 @@ TMQ_HD double dslash_site(const DslashArgs<F> &A, const Enum &en, uint32_t e, F 
     }
     if (T::RED == 1) {
 #pragma unroll
-      for (int j = 0; j < 6; j++) redc += norm2_vec(pack_vec(o, j));
+      for (int j = 0; j < 6; j++) {
+        const VecT<F> yv = pack_vec(o, j);
+        redc += norm2_vec(yv);
+        if (A.out2) A.out2[(size_t)j * stride + c.idx] = yv;
+      }
     }
     if (T::TW3) clover_mul(o, A.cl_inv, c.idx, stride, A.cl_dag3 != 0);
 #pragma unroll

@@ -166,6 +166,9 @@ template <typename F> struct DslashArgs {
   const VecT<F> *cl_inv;   // (C + i a g5)^-1 ; its conjugate transpose is (C - i a g5)^-1
   const VecT<F> *cl_c;     // C = 1 + i csw kappa sum_{mu<nu} sigma_munu F_munu
   int cl_dag1, cl_dag3;    // apply the conjugate transpose in the post-hop (t1) / final (t3) position
+  VecT<F> *out2;           // clover EPI_MDAGM2: also store y = x + k t (= M p) here, so that the M^dag step can take it as a
+                           // plain x term instead of re-applying A^dag = C - i a g5 to w (192 B/site instead of 1152)
+  int cl_plain_x;          // clover: the x term is used as it is (no site matrix) although the epilogue has TWX
   int prefetch;            // unused (the L2-prefetch experiment was removed: no gain, and it cost the 4th resident CTA)
 };
 

@@ -29,6 +29,7 @@ int main(int argc, char **argv) {
   int nev = 4, nkv = 16, polydeg = 20;
   double amin = 0.385, amax = 2.0, eig_tol = 1e-10, csw = 0.0;
   std::string dslash_type = "twisted-mass";
+  int nsmearGauss = 0; double alphaGauss = 4.0;                              // qkxtm/QKXTM_util.cpp:1652-1654
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto need = [&](int n) { if (i + n >= argc) { usage(); exit(2); } };
@@ -48,6 +49,8 @@ int main(int argc, char **argv) {
     else if (a == "--verbosity-level") { need(1); verb = argv[++i]; }
     else if (a == "--out") { need(1); out = argv[++i]; }
     else if (a == "--dslash-type") { need(1); dslash_type = argv[++i]; }      // twisted-mass | twisted-clover (qkxtm/misc.cpp:830-859)
+    else if (a == "--nsmearGauss") { need(1); nsmearGauss = atoi(argv[++i]); }
+    else if (a == "--alphaGauss") { need(1); alphaGauss = atof(argv[++i]); }
     else if (a == "--csw") { need(1); csw = atof(argv[++i]); }                 // qkxtm/QKXTM_util.cpp:1642
     else if (a == "--PolyDeg") { need(1); polydeg = atoi(argv[++i]); }        // the reference's ARPACK flags (qkxtm/QKXTM_util.cpp)
     else if (a == "--nEv") { need(1); nev = atoi(argv[++i]); }
@@ -106,6 +109,7 @@ int main(int argc, char **argv) {
   memset(&info, 0, sizeof(info));
   for (int d = 0; d < 4; d++) info.lL[d] = dim[d];
   info.isEven = ((int)inv_param.matpc_type & 1) == 0;
+  info.nsmearGauss = nsmearGauss; info.alphaGauss = alphaGauss;
   info.kappa = inv_param.kappa; info.mu = mu; info.inv_tol = tol; info.Precision = QUDA_DOUBLE_PRECISION;
 
   // synthetic configuration: random SU(3), QDP even-odd order, anti-periodic T folded in
@@ -176,6 +180,7 @@ int main(int argc, char **argv) {
       }
     }
     result.resize((size_t)12 * V * 24);
+    if (nsmearGauss > 0) testGaussSmearing((void **)glex);                       // lib/qudaQKXTM_utils.cpp:116-141
     MG_bench((void **)glex, (void **)gauge, &gauge_param, &inv_param, info, result.data());
   } else { usage(); return 2; }
 

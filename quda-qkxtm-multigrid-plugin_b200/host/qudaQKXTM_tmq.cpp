@@ -264,6 +264,42 @@ void printf_qudaQKXTM() {
   printfQuda("Local volume is %lld\n", G.localVolume);
 }
 
+// lib/qudaQKXTM_utils.cpp:87-109: the plaquette of the same links through two container objects
+void testPlaquette(void **gauge) {
+  for (int rep = 0; rep < 2; rep++) {
+    QKXTM_Gauge<double> *gauge_object = new QKXTM_Gauge<double>(BOTH, GAUGE);
+    gauge_object->printInfo();
+    gauge_object->packGauge(gauge);
+    gauge_object->loadGauge();
+    gauge_object->calculatePlaq();
+    delete gauge_object;
+  }
+}
+// lib/qudaQKXTM_utils.cpp:116-141: Gaussian smearing of a point source at the origin; the 12 components at the origin are
+// printed like the reference does
+void testGaussSmearing(void **gauge) {
+  QKXTM_Gauge<double> *gauge_object = new QKXTM_Gauge<double>(BOTH, GAUGE);
+  gauge_object->printInfo();
+  gauge_object->packGauge(gauge);
+  gauge_object->loadGauge();
+  gauge_object->calculatePlaq();
+  QKXTM_Vector<double> *vecIn = new QKXTM_Vector<double>(BOTH, VECTOR);
+  QKXTM_Vector<double> *vecOut = new QKXTM_Vector<double>(BOTH, VECTOR);
+  double *input_vector = (double *)calloc((size_t)G.localVolume * 24, sizeof(double));   // (the reference leaves the rest uninitialised)
+  if (!input_vector) errorQuda("Error allocating memory for the host source");
+  input_vector[0] = 1.;
+  vecIn->packVector(input_vector);
+  vecIn->loadVector();
+  vecOut->gaussianSmearing(*vecIn, *gauge_object);
+  vecOut->download();
+  for (int mu = 0; mu < 4; mu++)
+    for (int c1 = 0; c1 < 3; c1++) printf("%+e %+e\n", vecOut->H_elem()[mu * 3 * 2 + c1 * 2 + 0], vecOut->H_elem()[mu * 3 * 2 + c1 * 2 + 1]);
+  free(input_vector);
+  delete vecOut;
+  delete vecIn;
+  delete gauge_object;
+}
+
 ColorSpinorField::ColorSpinorField(QudaSiteSubset subset, QudaPrecision prec) : h_(nullptr), subset_(subset) {
   if (!G.ctx) errorQuda("no context: call loadGaugeQuda / init_qudaQKXTM first");
   h_ = tmq_spinor_alloc(G.ctx, (int)prec, subset == QUDA_FULL_SITE_SUBSET ? TMQ_SUBSET_FULL : TMQ_SUBSET_PARITY);

@@ -136,3 +136,31 @@ def test_twisted_clover_invert_through_the_shim(tmp_path, env):
     oc.set_clover(None)
     assert tr <= 1.05e-10 and it > 5
     assert lu.rel_l2(r, b) < 1e-8
+
+
+def test_MG_bench_with_gaussian_smeared_sources(tmp_path, env):
+    """MG_bench with nsmearGauss > 0 (lib/qudaQKXTM_interface.cpp:181-185): every point source is Gaussian-smeared with the
+    links passed as gaugeSmeared before the solve, so M x = S delta; S from the oracle's restatement of Gauss_core.h (pinned
+    to the reference's kernel body by tests/test_ref_kernels.py).  The driver also runs testGaussSmearing, whose 12 printed
+    numbers are S delta at the origin."""
+    o, gauge, tmq = env
+    from oracle.oracle import gauss_smear
+    nsm, alpha = 3, 4.0
+    r, _, _, out = run(tmp_path, "--test", "mgbench", "--tol", "1e-10", "--nsmearGauss", str(nsm), "--alphaGauss", str(alpha), "--recon", "12")
+    V = int(np.prod(X))
+    cols = r.reshape(12, V, 4, 3, 2)
+    # the links of the synthetic configuration in the QKXTM layout [dir][c1][c2][x_lex] (anti-periodic sign included, as the
+    # driver passes the same field for both arguments)
+    U = lu.r2c(np.stack([lu.spinor_lex_from_eo(gauge[mu], X) for mu in range(4)]))      # [4][x_lex][3][3]
+    Uq = np.transpose(U, (0, 2, 3, 1))
+    for isc in (0, 7):
+        delta = np.zeros((12, V), dtype=np.complex128); delta[isc, 0] = 1.0
+        Sd = gauss_smear(delta, Uq, X, alpha, nsm)                                  # [12][V]
+        b_lex = lu.c2r(np.transpose(Sd.reshape(4, 3, V), (2, 0, 1)))               # [x_lex][s][c][ri]
+        b_eo = lu.spinor_eo_from_lex(b_lex, X)
+        x_eo = lu.spinor_eo_from_lex(cols[isc], X)
+        assert lu.rel_l2(o.mat(gauge, x_eo, KAPPA, MU, 0), b_eo) < 1e-8, isc
+        if isc == 0:
+            printed = np.array([[float(v) for v in ln.split()] for ln in out.splitlines()
+                                if len(ln.split()) == 2 and ln.lstrip()[0] in "+-" and "e" in ln][:12])
+            assert printed.shape == (12, 2) and np.allclose(printed, b_lex[0].reshape(12, 2), rtol=1e-6, atol=1e-12)
