@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Timing of the twisted-clover variant on one B200: hop + A^-1 kernel and the fused CG iteration with
 the site-dependent 6x6 chiral blocks.  Algorithmic bytes per parity site: twisted-mass bytes + 72 complex = 1152 B (fp64) for
-every launch that applies A^-1 (K1, K2, K3) and for the C field in K4."""
+every launch that applies A^-1 (K1, K2, K3); K2 also stores y = M p, which K4 takes as its x term."""
 import argparse
 import json
 import os
@@ -38,7 +38,8 @@ for clover in (0, 1):
         ms4, n4 = c.time_kernel(4, prec, a.reps, b)
         cl = 72 * 2 * prec * clover          # one 2 x 6x6 complex field per site
         b1 = (24 + 24 + 8 * 12) * prec + cl
-        b4 = (24 * 16 + 32 * 12) * prec + 4 * cl
+        # K1, K2, K3 load A^-1; K2 also stores y = M p and K4 reads it instead of w (one extra 24-real write)
+        b4 = (24 * 16 + 32 * 12) * prec + clover * (3 * cl + 24 * prec)
         print(json.dumps({"what": "twisted-clover" if clover else "twisted-mass", "lattice": X, "prec": prec,
                           "hop+Ainv_ms": ms1, "hop+Ainv_bytes_per_site": b1, "hop+Ainv_frac_of_hbm_peak": b1 * Vh / ms1 * 1e-6 / peak,
                           "cg_iter_ms": ms4, "cg_iter_launches": n4, "cg_iter_bytes_per_site": b4,
