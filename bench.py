@@ -397,7 +397,7 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-9)
     ap.add_argument("--maxiter", type=int, default=5000)
     ap.add_argument("--sloppy-prec", type=int, default=8, choices=[8, 4])
-    ap.add_argument("--delta", type=float, default=1e-1)
+    ap.add_argument("--delta", type=float, default=1e-4, help="reliable_delta of the mixed-precision solve (the reference drivers set 1e-4, qkxtm/Calc_Loops.cpp:481)")
     ap.add_argument("--e2e-solves", type=int, default=2)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")

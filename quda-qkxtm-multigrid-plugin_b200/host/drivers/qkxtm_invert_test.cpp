@@ -101,7 +101,7 @@ int main(int argc, char **argv) {
   inv_param.mass_normalization = massnorm == "mass" ? QUDA_MASS_NORMALIZATION : QUDA_KAPPA_NORMALIZATION;
   inv_param.residual_type = QUDA_L2_RELATIVE_RESIDUAL;
   inv_param.tol = tol; inv_param.maxiter = niter;
-  inv_param.reliable_delta = prec_sloppy == "single" ? 1e-1 : 1e-4;
+  inv_param.reliable_delta = 1e-4;                                             // qkxtm/Calc_Loops.cpp:481
   inv_param.verbosity = verb == "silent" ? QUDA_SILENT : (verb == "verbose" ? QUDA_VERBOSE : QUDA_SUMMARIZE);
   setVerbosityQuda(inv_param.verbosity);
 
