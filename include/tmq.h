@@ -123,7 +123,8 @@ int tmq_reconstruct(tmq_spinor *x_full, const tmq_spinor *x_pc, const tmq_spinor
 
 /* ---- solver: replaces Solver::create(CG) + (*solve)(out,in) on DiracMdagM
  *      (lib/qudaQKXTM_interface.cpp:2031-2037).  Solves M^dag M x = b for PARITY fields, x0 = 0.
- * sloppy_prec = 8: pure fp64; 4: fp32 inner iterations with reliable updates (delta), fp64 true residual.
+ * sloppy_prec = 8: pure fp64; 4: fp32 inner iterations with reliable updates (delta; <= 0 selects the reference drivers'
+ * 1e-4, qkxtm/Calc_Loops.cpp:481), fp64 true residual.
  * Outputs mirror QudaInvertParam::{iter,true_res,secs,gflops} (updateInvertParam).                         */
 int tmq_cg_mdagm(tmq_spinor *x, const tmq_spinor *b, double tol, int maxiter, double reliable_delta,
                  int sloppy_prec, int *iters, double *true_res, double *secs, double *gflops);

@@ -1016,7 +1016,7 @@ int tmq_cg_mdagm(tmq_spinor *x, const tmq_spinor *b, double tol, int maxiter, do
   int it = 0;
   double tr = 0;
   if (sloppy_prec == 8) TMQ_TRY(cg_double(c, x, b, tol, maxiter, &it, &tr));
-  else TMQ_TRY(cg_mixed(c, x, b, tol, maxiter, reliable_delta > 0 ? reliable_delta : 1e-1, &it, &tr));
+  else TMQ_TRY(cg_mixed(c, x, b, tol, maxiter, reliable_delta > 0 ? reliable_delta : 1e-4, &it, &tr));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   TMQ_TRY(check_device_error(c));
   const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -22,8 +22,13 @@ namespace tmq {
 #ifndef TMQ_MINBLOCKS_D_LIGHT
 #define TMQ_MINBLOCKS_D_LIGHT 4
 #endif
-template <typename F, int EPI> struct MinBlocks { static constexpr int v = (EPI == EPI_PLAIN || EPI == EPI_TW) ? TMQ_MINBLOCKS_D_LIGHT : TMQ_MINBLOCKS_D; };
-template <int EPI> struct MinBlocks<float, EPI> { static constexpr int v = 6; };
+template <typename F, int EPI, int RECON> struct MinBlocks { static constexpr int v = (EPI == EPI_PLAIN || EPI == EPI_TW) ? TMQ_MINBLOCKS_D_LIGHT : TMQ_MINBLOCKS_D; };
+// fp32: 7 CTAs/SM (72 registers, 4-24 byte spills) beat 6 by 4-5% with recon-12 and lose 1% with recon-18; 8 CTAs (64
+// registers, ~100 byte spills) lose everywhere (A/B: profiles/r14_variant_fp32.log)
+#ifndef TMQ_MINBLOCKS_S
+#define TMQ_MINBLOCKS_S 7
+#endif
+template <int EPI, int RECON> struct MinBlocks<float, EPI, RECON> { static constexpr int v = RECON == 12 ? TMQ_MINBLOCKS_S : 6; };
 
 // Boundary CTAs of a fused sharded launch: wait until every neighbour has published this application's
 // sequence number (its pack kernel has finished storing the faces into our ghost buffers over NVLink).
@@ -49,7 +54,7 @@ template <typename F> struct MinBlocksClover { static constexpr int v = 3; };
 template <> struct MinBlocksClover<float> { static constexpr int v = 5; };
 
 template <typename F, int RECON, int EPI, bool MULTI, bool CLOVER = false>
-__global__ void __launch_bounds__(TMQ_DSLASH_BLOCK, (CLOVER ? MinBlocksClover<F>::v : MinBlocks<F, EPI>::v))
+__global__ void __launch_bounds__(TMQ_DSLASH_BLOCK, (CLOVER ? MinBlocksClover<F>::v : MinBlocks<F, EPI, RECON>::v))
 dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
   uint32_t blk = blockIdx.x;
   const Enum *en = &A.en;

@@ -270,7 +270,7 @@ class Context:
     def prepare(self, src_pc, b_full): _ck(self.L.tmq_prepare(src_pc.h, b_full.h))
     def reconstruct(self, x_full, x_pc, b_full): _ck(self.L.tmq_reconstruct(x_full.h, x_pc.h, b_full.h))
 
-    def cg_mdagm(self, x, b, tol=1e-7, maxiter=10000, reliable_delta=1e-1, sloppy_prec=PREC_DOUBLE):
+    def cg_mdagm(self, x, b, tol=1e-7, maxiter=10000, reliable_delta=1e-4, sloppy_prec=PREC_DOUBLE):
         it = C.c_int(0); tr = C.c_double(0); secs = C.c_double(0); gf = C.c_double(0)
         _ck(self.L.tmq_cg_mdagm(x.h, b.h, tol, maxiter, reliable_delta, sloppy_prec, C.byref(it), C.byref(tr),
                                 C.byref(secs), C.byref(gf)))
