@@ -105,12 +105,25 @@ namespace quda {
 enum ALLOCATION_FLAG { NONE, HOST, DEVICE, BOTH, BOTH_EXTRA };                 // include/qudaQKXTM_utils.h:126
 enum CLASS_ENUM { FIELD, GAUGE, VECTOR, PROPAGATOR, PROPAGATOR3D, VECTOR3D };  // include/qudaQKXTM_utils.h:127
 
-typedef struct {                       // the hot-path slice of qudaQKXTMinfo (include/qudaQKXTM_utils.h:45-75)
+#define MAX_NSOURCES 1000                                                     // include/qudaQKXTM_utils.h:16
+#define MAX_NMOMENTA 5000                                                     // include/qudaQKXTM_utils.h:19
+enum CORR_SPACE { POSITION_SPACE, MOMENTUM_SPACE };                            // include/qudaQKXTM_utils.h:41
+enum FILE_WRITE_FORMAT { ASCII_FORM, HDF5_FORM };                              // include/qudaQKXTM_utils.h:42
+enum WHICHPARTICLE { PROTON, NEUTRON };                                        // include/qudaQKXTM_utils.h:128
+
+typedef struct {                       // the slice of qudaQKXTMinfo the built paths read (include/qudaQKXTM_utils.h:45-75)
   int nsmearAPE, nsmearGauss;
   double alphaAPE, alphaGauss;
   int lL[QUDAQKXTM_DIM];
   int Nsources;
+  int sourcePosition[MAX_NSOURCES][QUDAQKXTM_DIM];    // global (x, y, z, t)
   QudaPrecision Precision;
+  int Q_sq;                            // momenta with p^2 <= Q_sq (createMomenta, lib/qudaQKXTM_kernels.cu:98-116)
+  int traj;
+  bool check_files;
+  int run3pt_src[MAX_NSOURCES];        // must be 0: the three-point function is not built
+  FILE_WRITE_FORMAT CorrFileFormat;    // ASCII_FORM only (no HDF5 here)
+  CORR_SPACE CorrSpace;
   bool isEven;
   double kappa, mu, csw, inv_tol;
 } qudaQKXTMinfo;
@@ -136,6 +149,7 @@ public:
 
 template <typename Float> class QKXTM_Vector;
 template <typename Float> class QKXTM_Propagator;
+template <typename Float> class QKXTM_Propagator3D;
 
 template <typename Float> class QKXTM_Field {     // include/qudaQKXTM.h:104-160, lib/qudaQKXTM_Field.cpp:81-258
 protected:
@@ -189,6 +203,9 @@ public:
   void downloadFromCuda(ColorSpinorField *cudaVector, bool isEv = false);  // lib/qudaQKXTM_Vector.cpp:430-432
   void gaussianSmearing(QKXTM_Vector<Float> &vecIn, QKXTM_Gauge<Float> &gaugeAPE);   // lib/qudaQKXTM_Vector.cpp:386-421 (vecIn is clobbered, as in the reference)
   void scaleVector(double a);
+  void conjugate();                                // lib/code_pieces/conjugate_vector_core.h
+  void copyPropagator(QKXTM_Propagator<Float> &prop, int nu, int c2);                         // lib/qudaQKXTM_Vector.cpp:490-512
+  void copyPropagator3D(QKXTM_Propagator3D<Float> &prop, int timeslice, int nu, int c2);      // lib/qudaQKXTM_Vector.cpp:463-488
   void write(char *filename);                      // "DiracFermion_Sink" LIME file from h_elem (AoS), lib/qudaQKXTM_Vector.cpp:510-702
   void castDoubleToFloat(QKXTM_Vector<double> &vecIn);
   void castFloatToDouble(QKXTM_Vector<float> &vecIn);
@@ -201,7 +218,34 @@ public:
   QKXTM_Propagator(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT);
   void absorbVectorToHost(QKXTM_Vector<Float> &vec, int nu, int c2);
   void absorbVectorToDevice(QKXTM_Vector<Float> &vec, int nu, int c2);
+  void rotateToPhysicalBase_host(int sign);        // lib/qudaQKXTM_Propagator.cpp:117-180 (on h_elem)
+  void rotateToPhysicalBase_device(int sign);      // lib/qudaQKXTM_Propagator.cpp:108-112: sign = +1 (up) / -1 (down)
+  void conjugate();                                // lib/code_pieces/conjugate_propagator_core.h
+  void apply_gamma5();                             // lib/code_pieces/apply_gamma5_propagator_core.h
 };
+
+template <typename Float> class QKXTM_Propagator3D : public QKXTM_Field<Float> {   // include/qudaQKXTM.h:267-277
+public:
+  QKXTM_Propagator3D(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT);
+  void absorbTimeSlice(QKXTM_Propagator<Float> &prop, int timeslice);                 // lib/qudaQKXTM_Propagator.cpp:509-531
+  void absorbVectorTimeSlice(QKXTM_Vector<Float> &vec, int timeslice, int nu, int c2); // lib/qudaQKXTM_Propagator.cpp:533-550
+};
+
+// the meson two-point part of QKXTM_Contraction (include/qudaQKXTM.h:283-389; lib/qudaQKXTM_Contraction.cpp:1563-1648)
+template <typename Float> class QKXTM_Contraction {
+public:
+  QKXTM_Contraction() {}
+  // corrMesons, MOMENTUM_SPACE: Float[T_local * Nmoms * 2][2][10], entry [it*Nmoms*2 + imom*2 + ri][iu][ip], already summed over
+  // the ranks that share this rank's time slices (the reference leaves that sum on the space communicator's root);
+  // POSITION_SPACE: Float[2 * V_local][2][10], entry [2*x_lex + ri][iu][ip].  Float = float or double (the reference's launcher
+  // refuses double, lib/qudaQKXTM_kernels.cu:1222).
+  void contractMesons(QKXTM_Propagator<Float> &prop1, QKXTM_Propagator<Float> &prop2, void *corrMesons, int isource, CORR_SPACE CorrSpace);
+  // "ip it px py pz  re(up) im(up)  re(down) im(down)", time relative to the source, lib/qudaQKXTM_Contraction.cpp:1586-1599;
+  // every rank must call it, the rank holding global t = 0 .. writes (all ranks hold the full result)
+  void writeTwopMesons_ASCII(void *corrMesons, char *filename_out, int isource, CORR_SPACE CorrSpace);
+};
+int qkxtm_Nmoms();                                  // GK_Nmoms / GK_moms after init_qudaQKXTM
+const int *qkxtm_moms();                            // [Nmoms][3]
 
 // ---- exact deflation (include/qudaQKXTM.h:391-475, include/qudaQKXTM_utils.h:76-94) ------------------------------------
 enum WHICHSPECTRUM { SR, LR, SM, LM, SI, LI };
@@ -281,6 +325,15 @@ void calc_loops_solve(double *h_solution, double *h_source, QudaInvertParam *par
 // vector in the plug-in's AoS order [x_lex][s][c][ri] -> packVector/loadVector/uploadToCuda(parity isEven) ->
 // M_pc^dag M_pc -> downloadFromCuda/unloadVector/unpackVector; the other parity comes back zero-filled.
 void ApplyMdagM(double *h_out, double *h_in, QudaInvertParam *param, bool isEven);
+
+// calcMG_threepTwop_EvenOdd (include/qudaQKXTM.h:494-499, lib/qudaQKXTM_interface.cpp:236-1290), the MESON TWO-POINT part:
+// for every source position, 12 + 12 point-source solves (up: +mu, down: -mu; Gaussian-smeared source), columns cast to float
+// and absorbed into K_prop_up / K_prop_down, sink smearing, rotateToPhysicalBase_device(+-1), contractMesons, and the ASCII
+// file "<filename_twop>.mesons.SS.xx.yy.zz.tt.dat".  CG on M^dag M replaces the reference's GCR + multigrid solver (the
+// preconditionerUP/DN patch to quda.h, README:84-108).  Three-point functions (info.run3pt_src != 0), baryons and HDF5 output
+// are not built and are refused.
+void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param,
+                               quda::qudaQKXTMinfo info, char *filename_twop, char *filename_threep, quda::WHICHPARTICLE NUCLEON);
 
 // ---- configuration I/O (include/QKXTM_read_conf.h:816-848) -----------------------------------------------------------
 // reads this rank's sub-block of an ILDG / LIME configuration into the QDP even-odd host order of loadGaugeQuda and sets

@@ -194,9 +194,34 @@ int tmq_qkxtm_absorb(tmq_ctx *, void *d_prop, const void *d_vec, int prec, int n
  * nsmear steps of out = (psi + alpha sum_{mu=x,y,z} [U_mu(x) psi(x+mu) + U_mu(x-mu)^dag psi(x-mu)]) / (1 + 6 alpha) on the
  * QKXTM device layouts (vector d[(s*3+c)*V + x], gauge d[((dir*3+c1)*3+c2)*V + x]).  Like the reference it ping-pongs
  * between the two vectors: d_in is CLOBBERED, the result ends in d_out (nsmear = 0 copies).  The time direction does
- * not hop, so a T-sharded lattice needs no exchange; a z split is refused.  TMQ_OPT_SMEAR_BLOCK_T > 0 sweeps the
- * time slices in blocks of that many slices (block outer, step inner: L2-resident); 0 (default) = streaming order. */
+ * not hop, so a T-sharded lattice needs no exchange; on a z split (or with tmq_force_partition in z) the two z faces of
+ * the vector are exchanged with the z neighbours before every step and the neighbour's U_z face once per call, and the
+ * result is bit-identical to the unsharded sweep.  TMQ_OPT_SMEAR_BLOCK_T > 0 sweeps the time slices in blocks of that
+ * many slices (block outer, step inner: L2-resident; ignored on a z split); 0 (default) = streaming order.          */
 int tmq_qkxtm_gauss_smear(tmq_ctx *, void *d_out, void *d_in, const void *d_gauge, int prec, int nsmear, double alpha);
+
+/* ---- propagator container kernels and the meson two-point contraction: what calcMG_threepTwop_EvenOdd does with the solved
+ *      columns (lib/qudaQKXTM_interface.cpp:1190-1223).  Propagator layout d[((mu*4+nu)*9 + c1*3+c2)*V + x_lex]. ------------ */
+/* QKXTM_Vector::conjugate / QKXTM_Propagator::conjugate (lib/code_pieces/conjugate_{vector,propagator}_core.h): ncomp = 12 | 144 */
+int tmq_qkxtm_conjugate(tmq_ctx *, void *d, int prec, int ncomp);
+/* QKXTM_Propagator::apply_gamma5 (lib/code_pieces/apply_gamma5_propagator_core.h): gamma5 on the sink spin index              */
+int tmq_qkxtm_gamma5_prop(tmq_ctx *, void *d_prop, int prec);
+/* QKXTM_Propagator::rotateToPhysicalBase_device(sign) (lib/qudaQKXTM_Propagator.cpp:108-112, rotateToPhysicalBase_core.h):
+ * P <- 1/2 (1 + i sign gamma5) P (1 + i sign gamma5), sign = +-1                                                            */
+int tmq_qkxtm_rotate_physical(tmq_ctx *, void *d_prop, int prec, int sign);
+/* one (nu, c2) column between a propagator-like and a vector-like array whose component strides are prop_sites / vec_sites,
+ * for nsites sites starting at prop_site0 / vec_site0: covers absorbVectorToDevice and copyPropagator (all V sites) and
+ * copyPropagator3D / absorbVectorTimeSlice (one time slice of a 4-d field <-> a 3-d one), lib/qudaQKXTM_Vector.cpp:464-512,
+ * lib/qudaQKXTM_Propagator.cpp:90-106,533-550.  to_prop != 0: vector -> propagator, else propagator -> vector.            */
+int tmq_qkxtm_column_copy(tmq_ctx *, void *d_prop, long long prop_sites, long long prop_site0, void *d_vec, long long vec_sites,
+                          long long vec_site0, long long nsites, int prec, int nu, int c2, int to_prop);
+/* QKXTM_Contraction::contractMesons (lib/qudaQKXTM_Contraction.cpp:1606-1648, kernel bodies contractMesons_core{,_PosSpace}.h):
+ * the ten meson channels (pseudoscalar, scalar, g5g1..g5g4, g1..g4) C_G(x) = s_G tr[G S G^dag g5 S^dag g5] of prop1 (iu = 0) and
+ * of prop2 (iu = 1).  corr_pos (host, may be NULL): [x_lex local][iu][ip][re,im].  corr_mom (host, may be NULL):
+ * [t GLOBAL][imom][iu][ip][re,im] = sum_xvec exp(-2 pi i p.(x - src_pos)/L) C(x), moms = nmoms x (px,py,pz), src_pos global
+ * (x0,y0,z0); on a sharded lattice every rank gets the complete reduced result.                                              */
+int tmq_qkxtm_contract_mesons(tmq_ctx *, const void *d_prop1, const void *d_prop2, int prec, const int *moms, int nmoms,
+                              const int src_pos[3], double *corr_mom, double *corr_pos);
 
 /* ---- raw device memory for the containers (QKXTM_Field::create_device, lib/qudaQKXTM_Field.cpp:172) ----- */
 int tmq_dev_malloc(tmq_ctx *, void **ptr, size_t bytes);
@@ -204,6 +229,7 @@ int tmq_dev_free(tmq_ctx *, void *ptr);
 int tmq_dev_memset(tmq_ctx *, void *ptr, int value, size_t bytes);
 int tmq_h2d(tmq_ctx *, void *dst, const void *src, size_t bytes);
 int tmq_d2h(tmq_ctx *, void *dst, const void *src, size_t bytes);
+int tmq_d2d(tmq_ctx *, void *dst, const void *src, size_t bytes);     /* asynchronous on the context's stream */
 
 /* ---- measurement helpers (CUDA events on the context's stream) ------------------------------------------ */
 /* run `reps` back-to-back applications of one kernel flavour on (a copy of) the PARITY field `in` and return

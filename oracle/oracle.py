@@ -268,3 +268,64 @@ def gauss_smear(vec, gauge, X, alpha, nsmear):
     for _ in range(nsmear):
         cur = gauss_smear_step(cur, gauge, X, alpha)
     return cur.copy()
+
+
+# ---- propagator container kernels and the meson two-point contraction (the step after the solves) ---------------------
+def rotate_physical(prop, sign):
+    """lib/code_pieces/rotateToPhysicalBase_core.h: twisted -> physical basis, P <- 1/2 (1 + i s g5) P (1 + i s g5) on the
+    propagator device layout [4 mu][4 nu][3 c1][3 c2][V] complex (gamma5 = UKQCD spin swap)."""
+    g5 = _gamma5_ukqcd()
+    R = np.eye(4) + 1j * sign * g5
+    P = prop.reshape(4, 4, 3, 3, -1)
+    return (0.5 * np.einsum("am,mncdx,ng->agcdx", R, P, R)).reshape(prop.shape)
+
+
+def _gamma5_ukqcd():
+    g = gamma_ukqcd()
+    return g[0] @ g[1] @ g[2] @ g[3]
+
+
+def meson_gammas():
+    """The ten channels of the reference in its order (lib/qudaQKXTM_interface.cpp:305-314): pseudoscalar, scalar, g5g1..g5g4,
+    g1..g4, with the overall sign of its tables (lib/qudaQKXTM_kernels.cu:77-78): +1 for the first six, -1 for g_mu."""
+    g = gamma_ukqcd(); g5 = _gamma5_ukqcd()
+    G = [g5, np.eye(4, dtype=complex)] + [g5 @ g[m] for m in range(4)] + [g[m] for m in range(4)]
+    return G, [1.0] * 6 + [-1.0] * 4
+
+
+def contract_mesons_site(prop):
+    """C_G(x) = s_G tr[ G S(x) G^dag g5 S(x)^dag g5 ] over spin and colour for the ten channels, prop [4][4][3][3][V] complex
+    -> [10][V] complex.  (What lib/code_pieces/contractMesons_core.h:20-33 accumulates per site from the index tables.)"""
+    G, sG = meson_gammas(); g5 = _gamma5_ukqcd()
+    S = prop.reshape(4, 4, 3, 3, -1)
+    out = np.empty((10, S.shape[-1]), dtype=np.complex128)
+    for ip in range(10):
+        A = g5 @ G[ip]                       # (g5 G)[d, a]
+        B = G[ip].conj().T @ g5              # (G^dag g5)[b, g]
+        out[ip] = sG[ip] * np.einsum("da,abijx,bg,dgijx->x", A, S, B, S.conj())
+    return out
+
+
+def contract_mesons_mom(prop1, prop2, X, moms, src):
+    """QKXTM_Contraction::contractMesons, MOMENTUM_SPACE (lib/code_pieces/contractMesons_core.h:37-87): for every time slice
+    sum_xvec exp(-2 pi i p.(x - src)/L) C(x) -> [T][nmoms][2][10] complex (single rank)."""
+    Xd, Yd, Zd, Td = X
+    c = np.stack([contract_mesons_site(prop1), contract_mesons_site(prop2)]).reshape(2, 10, Td, Zd, Yd, Xd)
+    x = np.arange(Xd) - src[0]; y = np.arange(Yd) - src[1]; z = np.arange(Zd) - src[2]
+    out = np.empty((Td, len(moms), 2, 10), dtype=np.complex128)
+    for im, (px, py, pz) in enumerate(moms):
+        ph = np.exp(-2j * np.pi * (pz * z[:, None, None] / Zd + py * y[None, :, None] / Yd + px * x[None, None, :] / Xd))
+        out[:, im] = np.einsum("uptzyx,zyx->tup", c, ph)
+    return out
+
+
+def create_momenta(q_sq):
+    """createMomenta (lib/qudaQKXTM_kernels.cu:98-116): all integer momenta with p^2 <= Q_sq, in the reference's order."""
+    m = []
+    for iq in range(q_sq + 1):
+        for nx in range(iq, -iq - 1, -1):
+            for ny in range(iq, -iq - 1, -1):
+                for nz in range(iq, -iq - 1, -1):
+                    if nx * nx + ny * ny + nz * nz == iq:
+                        m.append((nx, ny, nz))
+    return m

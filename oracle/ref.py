@@ -30,6 +30,14 @@ def lib():
         L.qref_scale_vector.argtypes = [dp, C.c_double]
         L.qref_apply_gamma5_double.argtypes = [dp]
         L.qref_calculate_plaq.argtypes = [dp]; L.qref_calculate_plaq.restype = C.c_double
+        for f in ("qref_conjugate_vector_double", "qref_conjugate_propagator_double", "qref_gamma5_propagator_double"):
+            getattr(L, f).argtypes = [dp]
+        L.qref_rotate_physical_double.argtypes = [dp, C.c_int]
+        L.qref_rotate_physical_float.argtypes = [fp, C.c_int]
+        L.qref_set_momenta.argtypes = [ip, C.c_int]
+        L.qref_contract_mesons_mom_float.argtypes = [fp, fp, fp, ip]
+        L.qref_contract_mesons_mom_double.argtypes = [dp, dp, dp, ip]
+        L.qref_contract_mesons_pos_float.argtypes = [fp, fp, fp]
         _lib = L
     return _lib
 
@@ -90,6 +98,43 @@ class Ref:
     def plaquette(self, gauge):
         """QKXTM_Gauge::calculatePlaq on the QKXTM device layout [4][3][3][V][2]"""
         return self.L.qref_calculate_plaq(_dp(np.ascontiguousarray(gauge, dtype=np.float64)))
+
+    # ---- propagator kernels / meson contraction; propagator device layout [4 mu][4 nu][3 c1][3 c2][V][re,im] ----------------
+    def conjugate_vector(self, vec):
+        v = vec.copy(); self.L.qref_conjugate_vector_double(_dp(v)); return v
+
+    def conjugate_propagator(self, prop):
+        p = prop.copy(); self.L.qref_conjugate_propagator_double(_dp(p)); return p
+
+    def gamma5_propagator(self, prop):
+        p = prop.copy(); self.L.qref_gamma5_propagator_double(_dp(p)); return p
+
+    def rotate_physical(self, prop, sign):
+        p = prop.copy()
+        if p.dtype == np.float64:
+            self.L.qref_rotate_physical_double(_dp(p), int(sign))
+        else:
+            self.L.qref_rotate_physical_float(_fp(p), int(sign))
+        return p
+
+    def contract_mesons_mom(self, prop1, prop2, moms, src):
+        """contractMesons, MOMENTUM_SPACE: -> [T][nmoms][2][10][re,im] in the propagators' precision (float = what the
+        reference launches; double = the double instantiation of the same kernel body)"""
+        m = np.ascontiguousarray(np.asarray(moms, dtype=np.int32).reshape(-1, 3))
+        self.L.qref_set_momenta(m.ctypes.data_as(C.POINTER(C.c_int)), len(m))
+        out = np.zeros((self.X[3], len(m), 2, 10, 2), dtype=prop1.dtype)
+        s = (C.c_int * 3)(*[int(v) for v in src])
+        if prop1.dtype == np.float32:
+            self.L.qref_contract_mesons_mom_float(_fp(out), _fp(prop1), _fp(prop2), s)
+        else:
+            self.L.qref_contract_mesons_mom_double(_dp(out), _dp(prop1), _dp(prop2), s)
+        return out
+
+    def contract_mesons_pos(self, prop1, prop2):
+        """contractMesons, POSITION_SPACE (float): -> [T][V3][2][10][re,im]"""
+        out = np.zeros((self.X[3], self.V // self.X[3], 2, 10, 2), dtype=np.float32)
+        self.L.qref_contract_mesons_pos_float(_fp(out), _fp(prop1), _fp(prop2))
+        return out
 
 
 # ---- the reference's host utility file qkxtm/QKXTM_util.cpp compiled in place (oracle/_ref/libqkxtm_util_ref.so) ------

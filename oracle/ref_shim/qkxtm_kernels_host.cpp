@@ -15,8 +15,17 @@
 //   castDoubleToFloat_core.h, castFloatToDouble_core.h
 //   plaquette_core.h ............ QKXTM_Gauge::calculatePlaq               (8a row a13): its block reduction uses __shared__ and
 //                                 __syncthreads, emulated with one OS thread per CUDA thread of a block and a pthread barrier
+//   conjugate_vector_core.h, conjugate_propagator_core.h, apply_gamma5_propagator_core.h, rotateToPhysicalBase_core.h
+//                                 QKXTM_Vector::conjugate, QKXTM_Propagator::{conjugate, apply_gamma5, rotateToPhysicalBase_device}
+//   contractMesons_core.h, contractMesons_core_PosSpace.h
+//                                 QKXTM_Contraction::contractMesons (the two-point step after the solves,
+//                                 lib/qudaQKXTM_interface.cpp:1217-1223), with the reference's own channel tables
+//                                 (lib/qudaQKXTM_kernels.cu:77-78, extracted by the Makefile into _ref/qkxtm_meson_tables.h)
 #include <cstddef>
 #include <cstring>
+#include <cmath>
+#include <functional>
+#include <thread>
 #include <pthread.h>
 #include <vector>
 
@@ -31,6 +40,8 @@ static inline float2 operator*(const float2 a, const float2 b) { return cmul(a, 
 static inline double2 operator*(const double a, const double2 b) { double2 r; r.x = a * b.x; r.y = a * b.y; return r; }
 static inline float2 operator*(const float a, const float2 b) { float2 r; r.x = a * b.x; r.y = a * b.y; return r; }
 static inline float2 operator*(const double a, const float2 b) { float2 r; r.x = a * b.x; r.y = a * b.y; return r; }   // double constant x float2, as nvcc promotes
+static inline float2 operator*(const int a, const float2 b) { float2 r; r.x = a * b.x; r.y = a * b.y; return r; }       // the int template of :367-373
+static inline double2 operator*(const int a, const double2 b) { double2 r; r.x = a * b.x; r.y = a * b.y; return r; }
 static inline double2 operator+(const double2 a, const double2 b) { double2 r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 static inline float2 operator+(const float2 a, const float2 b) { float2 r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 static inline double2 operator-(const double2 a, const double2 b) { double2 r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
@@ -167,4 +178,140 @@ extern "C" double qref_calculate_plaq(const double *gauge) {
   double plaquette = 0.0;
   for (int i = 0; i < nblocks; i++) plaquette += partial[i];
   return plaquette / ((double)c_threads * c_nColor * 6);
+}
+
+// ---- site-local propagator / vector kernels (lib/qudaQKXTM_kernels.cu:826-859) ----------------------------------------------
+template <typename Float2> static void conj_vector_thread(int sid_, Float2 *inOut) {
+  THREAD_PREAMBLE
+#include <conjugate_vector_core.h>
+}
+template <typename Float2> static void conj_prop_thread(int sid_, Float2 *inOut) {
+  THREAD_PREAMBLE
+#include <conjugate_propagator_core.h>
+}
+template <typename Float2> static void gamma5_prop_thread(int sid_, Float2 *inOut) {
+  THREAD_PREAMBLE
+#include <apply_gamma5_propagator_core.h>
+}
+template <typename Float2> static void rotate_thread(int sid_, Float2 *inOut, int sign) {
+  THREAD_PREAMBLE
+#include <rotateToPhysicalBase_core.h>
+}
+extern "C" void qref_conjugate_vector_double(double *v) { for (int s = 0; s < c_threads; s++) conj_vector_thread<double2>(s, (double2 *)v); }
+extern "C" void qref_conjugate_propagator_double(double *p) { for (int s = 0; s < c_threads; s++) conj_prop_thread<double2>(s, (double2 *)p); }
+extern "C" void qref_gamma5_propagator_double(double *p) { for (int s = 0; s < c_threads; s++) gamma5_prop_thread<double2>(s, (double2 *)p); }
+extern "C" void qref_rotate_physical_double(double *p, int sign) { for (int s = 0; s < c_threads; s++) rotate_thread<double2>(s, (double2 *)p, sign); }
+extern "C" void qref_rotate_physical_float(float *p, int sign) { for (int s = 0; s < c_threads; s++) rotate_thread<float2>(s, (float2 *)p, sign); }
+
+// ---- meson two-point contraction (lib/qudaQKXTM_kernels.cu:474-511, launcher :1127-1225) --------------------------------------
+#define MAX_NMOMENTA 5000              // include/qudaQKXTM_utils.h:19
+#define PI 3.141592653589793           // lib/qudaQKXTM_kernels.cu:12
+#include "qkxtm_meson_tables.h"        // GK_mesons_indices / GK_mesons_values, the reference's own initialisers
+#define c_mesons_indices GK_mesons_indices
+#define c_mesons_values GK_mesons_values
+static int c_Nmoms;
+static short int c_moms[MAX_NMOMENTA][3];
+static int c_procPosition[4] = {0, 0, 0, 0};
+static int c_totalL[4];
+
+// a grid of blocks of THREADS_PER_BLOCK threads, one block at a time, its threads as OS threads meeting at g_block_barrier
+static void run_grid(int nblocks, const std::function<void(dim3_, dim3_, dim3_, dim3_)> &body) {
+  pthread_barrier_init(&g_block_barrier, nullptr, THREADS_PER_BLOCK);
+  for (int b = 0; b < nblocks; b++) {
+    std::vector<std::thread> th;
+    for (int t = 0; t < THREADS_PER_BLOCK; t++)
+      th.emplace_back([&, b, t]() { dim3_ bi = {b}, bd = {THREADS_PER_BLOCK}, ti = {t}, gd = {nblocks}; body(bi, bd, ti, gd); });
+    for (auto &x : th) x.join();
+  }
+  pthread_barrier_destroy(&g_block_barrier);
+}
+
+#define __shared__ static
+#define __syncthreads() pthread_barrier_wait(&g_block_barrier)
+static void mesons_mom_float_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, float2 *block, texf_t prop1Tex, texf_t prop2Tex,
+                                  int it, int x0, int y0, int z0) {
+#define FLOAT2 float2
+#define FLOAT float
+#define FETCH_FLOAT2 fetch_float2
+#include <contractMesons_core.h>
+#undef PROP
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+static void mesons_mom_double_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, double2 *block, texd_t prop1Tex, texd_t prop2Tex,
+                                   int it, int x0, int y0, int z0) {
+#define FLOAT2 double2
+#define FLOAT double
+#define FETCH_FLOAT2 fetch_double2
+#include <contractMesons_core.h>
+#undef PROP
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+static void mesons_pos_float_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, float2 *block, texf_t prop1Tex, texf_t prop2Tex,
+                                  int it, int x0, int y0, int z0) {
+#define FLOAT2 float2
+#define FLOAT float
+#define FETCH_FLOAT2 fetch_float2
+#include <contractMesons_core_PosSpace.h>
+#undef PROP
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+#undef __syncthreads
+#undef __shared__
+
+extern "C" void qref_set_momenta(const int *moms, int nmoms) {
+  c_Nmoms = nmoms;
+  for (int i = 0; i < nmoms; i++) for (int d = 0; d < 3; d++) c_moms[i][d] = (short int)moms[3 * i + d];
+  for (int d = 0; d < 4; d++) { c_totalL[d] = c_localL[d]; c_procPosition[d] = 0; }      // single rank
+}
+
+// contractMesons_kernel<Float2, Float> of the launcher, MOMENTUM_SPACE branch (lib/qudaQKXTM_kernels.cu:1167-1199), for all local
+// time slices: out[it][imom][iu][ip][re,im] (the reference's corr[it*Nmoms*2 + imom*2 + ri][iu][ip])
+template <typename Float, typename Float2, typename Tex, typename Body>
+static void mesons_mom(Float *out, const Float *prop1, const Float *prop2, const int src[3], Body body) {
+  const int SpVol = c_threads / c_localL[3];
+  const int grid = (SpVol + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK;
+  std::vector<Float> h_partial_block((size_t)c_Nmoms * 2 * 10 * grid * 2);
+  for (int it = 0; it < c_localL[3]; it++) {
+    run_grid(grid, [&](dim3_ b, dim3_ d, dim3_ t, dim3_ g) { body(b, d, t, g, (Float2 *)h_partial_block.data(), (Tex)prop1, (Tex)prop2, it, src[0], src[1], src[2]); });
+    for (int imom = 0; imom < c_Nmoms; imom++)
+      for (int iu = 0; iu < 2; iu++)
+        for (int ip = 0; ip < 10; ip++) {
+          Float re = 0, im = 0;           // the launcher's Float `reduction` buffer, blocks summed in order
+          for (int i = 0; i < grid; i++) {
+            re += h_partial_block[(size_t)imom * 2 * 10 * grid * 2 + iu * 10 * grid * 2 + ip * grid * 2 + i * 2 + 0];
+            im += h_partial_block[(size_t)imom * 2 * 10 * grid * 2 + iu * 10 * grid * 2 + ip * grid * 2 + i * 2 + 1];
+          }
+          Float *o = out + ((((size_t)it * c_Nmoms + imom) * 2 + iu) * 10 + ip) * 2;
+          o[0] = re; o[1] = im;
+        }
+  }
+}
+extern "C" void qref_contract_mesons_mom_float(float *out, const float *prop1, const float *prop2, const int src[3]) {
+  mesons_mom<float, float2, texf_t>(out, prop1, prop2, src, mesons_mom_float_body);
+}
+// the double instantiation of the same body (contractMesons_kernel_double, lib/qudaQKXTM_kernels.cu:500-511; its launcher refuses
+// precision 8, :1222, but the kernel is in the tree): a tight pin for the restatement
+extern "C" void qref_contract_mesons_mom_double(double *out, const double *prop1, const double *prop2, const int src[3]) {
+  mesons_mom<double, double2, texd_t>(out, prop1, prop2, src, mesons_mom_double_body);
+}
+// POSITION_SPACE branch (lib/qudaQKXTM_kernels.cu:1142-1166): out[it][sv][iu][ip][re,im]
+extern "C" void qref_contract_mesons_pos_float(float *out, const float *prop1, const float *prop2) {
+  const int SpVol = c_threads / c_localL[3];
+  const int grid = (SpVol + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK;
+  const size_t alloc = (size_t)THREADS_PER_BLOCK * grid;
+  std::vector<float> blk(alloc * 2 * 10 * 2);
+  for (int it = 0; it < c_localL[3]; it++) {
+    run_grid(grid, [&](dim3_ b, dim3_ d, dim3_ t, dim3_ g) { mesons_pos_float_body(b, d, t, g, (float2 *)blk.data(), (texf_t)prop1, (texf_t)prop2, it, 0, 0, 0); });
+    for (int pt = 0; pt < 2; pt++)
+      for (int mes = 0; mes < 10; mes++)
+        for (int sv = 0; sv < SpVol; sv++)
+          for (int ri = 0; ri < 2; ri++)
+            out[((((size_t)it * SpVol + sv) * 2 + pt) * 10 + mes) * 2 + ri] = blk[ri + 2 * sv + 2 * alloc * mes + 2 * alloc * 10 * pt];
+  }
 }

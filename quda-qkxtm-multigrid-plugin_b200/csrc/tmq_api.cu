@@ -579,6 +579,7 @@ int tmq_destroy(tmq_ctx *c) {
   if (c->ticket2) cudaFree(c->ticket2);
   if (c->seq_table) cudaFree(c->seq_table);
   if (c->stage) cudaFree(c->stage);
+  if (c->contract_ws) cudaFree(c->contract_ws);
   if (c->partials) cudaFree(c->partials);
   if (c->ticket) cudaFree(c->ticket);
   if (c->scal) cudaFree(c->scal);
@@ -1203,6 +1204,12 @@ int tmq_d2h(tmq_ctx *c, void *dst, const void *src, size_t bytes) {
   TMQ_REQUIRE(c && dst && src, "null argument");
   TMQ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int tmq_d2d(tmq_ctx *c, void *dst, const void *src, size_t bytes) {
+  TMQ_REQUIRE(c && dst && src, "null argument");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  TMQ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
   return 0;
 }
 

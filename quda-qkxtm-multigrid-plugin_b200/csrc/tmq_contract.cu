@@ -1,0 +1,450 @@
+// tmq_contract.cu -- what the plug-in does with the solved columns right after the hot path: the propagator container
+// kernels and the meson two-point contraction of calcMG_threepTwop_EvenOdd (reference lib/qudaQKXTM_interface.cpp:1190-1223):
+//   copyPropagator / absorbVectorToDevice (+ the time-slice variants)  lib/qudaQKXTM_Vector.cpp:464-512, Propagator.cpp:90-106,511-550
+//   conjugate (vector, propagator)                                      lib/code_pieces/conjugate_{vector,propagator}_core.h
+//   apply_gamma5 (propagator)                                           lib/code_pieces/apply_gamma5_propagator_core.h
+//   rotateToPhysicalBase_device(sign)                                   lib/code_pieces/rotateToPhysicalBase_core.h
+//   contractMesons (position and momentum space)                        lib/code_pieces/contractMesons_core{,_PosSpace}.h,
+//                                                                       lib/qudaQKXTM_kernels.cu:1127-1225, Contraction.cpp:1606-1648
+// All on the QKXTM device layouts: vector d[(s*3+c)*V + x], propagator d[((mu*4+nu)*9 + c1*3+c2)*V + x] (complex, x lexicographic).
+//
+// Meson contraction.  The reference's tables c_mesons_indices / c_mesons_values (lib/qudaQKXTM_kernels.cu:77-78) are the
+// non-zero entries of      C_G(x) = s_G  tr[ G S(x) G^dag g5 S(x)^dag g5 ],     s_G = +1 for G in {g5, 1, g5 g_mu}, -1 for g_mu
+// (channel order pseudoscalar, scalar, g5g1..g5g4, g1..g4, lib/qudaQKXTM_interface.cpp:305-314), evaluated for S = prop1 and for
+// S = prop2.  Here the tensors are DERIVED from the UKQCD gamma matrices at first use (nothing is tabulated): every G is a
+// monomial matrix whose permutation is an XOR of the spin index, a -> a ^ m_G, and g5 is a -> a ^ 2, so with phases
+// G[a][a^m] = phi_a
+//     C_G = s_G sum_{colour pairs} sum_{a,g} phi_a conj(phi_g) S[a^m][g^m] conj(S[a^2][g^2]) ,      phi_a conj(phi_g) = +-1.
+// The 16 products S[a^m][g^m] conj(S[a^2][g^2]) are shared by the channels with the same m (4 groups).
+//
+// The reference then projects every time slice on the momentum list inside the same kernel with one 64-thread shared-memory
+// tree per momentum (cost  V * Nmoms) and finishes the sum over blocks on the host, one launch + one blocking D2H per time
+// slice.  Here: one site kernel over the whole local lattice (HBM-bound: 2 x 144 complex read, 20 complex written per site),
+// then a SEPARABLE Fourier sum -- over x for the distinct p_x, over y for the distinct (p_x, p_y), over z for the momenta --
+// so the projection costs about one more read of the site values instead of Nmoms reads.  All sums are in fp64 and in a fixed
+// order (warp shuffle trees), the result is identical from run to run.  On a sharded lattice every rank fills its own time
+// slices of the GLOBAL-T result and one all-reduce both sums the z ranks and gathers the t ranks (the reference's MPI_Reduce
+// over GK_spaceComm + MPI_Gather over GK_timeComm, Contraction.cpp:1638, 98-111).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <algorithm>
+#include <complex>
+#include <map>
+#include <vector>
+#include "../../include/tmq.h"
+#include "tmq_internal.h"
+
+namespace tmq {
+
+constexpr int CT_BLOCK = 128;
+
+// ---- site-local container kernels --------------------------------------------------------------------------------------
+template <typename F> __global__ void __launch_bounds__(256) qk_conj_kernel(CplxT<F> *__restrict__ d, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) d[i].im = -d[i].im;
+}
+
+// gamma5 on the sink spin index of a propagator: rows mu <-> mu + 2 (UKQCD gamma5 is the spin swap)
+template <typename F> __global__ void __launch_bounds__(256) qk_gamma5_prop_kernel(CplxT<F> *__restrict__ d, size_t V) {
+  const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= V * 72) return;
+  const size_t pq = e / V, x = e - pq * V;           // pq = mu * 36 + (nu, c1, c2), mu in {0, 1}
+  const CplxT<F> lo = d[pq * V + x], hi = d[(pq + 72) * V + x];
+  d[pq * V + x] = hi;
+  d[(pq + 72) * V + x] = lo;
+}
+
+// twisted -> physical basis: P <- 1/2 (1 + i s g5) P (1 + i s g5), per colour pair
+template <typename F> __global__ void __launch_bounds__(CT_BLOCK) qk_rotate_kernel(CplxT<F> *__restrict__ d, size_t V, F s) {
+  const size_t e = (size_t)blockIdx.x * CT_BLOCK + threadIdx.x;
+  if (e >= V * 9) return;
+  const size_t cc = e / V, x = e - cc * V;
+  F P[16][2];
+#pragma unroll
+  for (int k = 0; k < 16; k++) { const CplxT<F> v = d[((size_t)k * 9 + cc) * V + x]; P[k][0] = v.re; P[k][1] = v.im; }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const int k = a * 4 + g, ka = (a ^ 2) * 4 + g, kg = a * 4 + (g ^ 2), kag = (a ^ 2) * 4 + (g ^ 2);
+      CplxT<F> o;      // i s z = (-s Im z, s Re z)
+      o.re = (F)0.5 * (P[k][0] - s * P[ka][1] - s * P[kg][1] - P[kag][0]);
+      o.im = (F)0.5 * (P[k][1] + s * P[ka][0] + s * P[kg][0] - P[kag][1]);
+      d[((size_t)k * 9 + cc) * V + x] = o;
+    }
+}
+
+// ---- meson contraction: site kernel ------------------------------------------------------------------------------------
+template <typename F> struct MesonSigns { F w[10][16]; };   // s_G phi_a conj(phi_g), index a*4+g; kernel parameter (constant bank)
+// XOR masks of the ten channels in the UKQCD basis (checked against the gamma matrices by meson_signs())
+#define TMQ_MESON_XORS {2, 0, 1, 1, 0, 2, 3, 3, 2, 0}
+
+// the channels i0, i1 (, i2) share the XOR mask M: acc[i] += w_i[a][g] * S[a^M][g^M] conj(S[a^2][g^2]) over the 16 (a, g)
+template <int M, typename F>
+__device__ __forceinline__ void meson_group(const F (&S)[16][2], const MesonSigns<F> &W, F (&acc)[10][2], int i0, int i1, int i2) {
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const int k1 = (a ^ M) * 4 + (g ^ M), k2 = (a ^ 2) * 4 + (g ^ 2), q = a * 4 + g;
+      const F tr = S[k1][0] * S[k2][0] + S[k1][1] * S[k2][1];      // S1 conj(S2)
+      const F ti = S[k1][1] * S[k2][0] - S[k1][0] * S[k2][1];
+      acc[i0][0] += W.w[i0][q] * tr; acc[i0][1] += W.w[i0][q] * ti;
+      acc[i1][0] += W.w[i1][q] * tr; acc[i1][1] += W.w[i1][q] * ti;
+      if (i2 >= 0) { acc[i2][0] += W.w[i2][q] * tr; acc[i2][1] += W.w[i2][q] * ti; }
+    }
+}
+
+// site values csite[(iu*10 + ip) * V + x] = C_ip(x) of propagator iu = blockIdx.y (complex double).  The 16 spin products of one
+// colour pair are formed and summed in the propagators' precision (the reference does the whole sum in float), the nine colour
+// pairs are added up in double.
+template <typename F>
+__global__ void __launch_bounds__(CT_BLOCK) meson_site_kernel(CplxT<double> *__restrict__ csite, const CplxT<F> *__restrict__ prop1,
+                                                             const CplxT<F> *__restrict__ prop2, size_t V, MesonSigns<F> W) {
+  const size_t x = (size_t)blockIdx.x * CT_BLOCK + threadIdx.x;
+  if (x >= V) return;
+  const int iu = blockIdx.y;
+  const CplxT<F> *__restrict__ prop = iu ? prop2 : prop1;
+  double c[10][2];
+#pragma unroll
+  for (int ip = 0; ip < 10; ip++) { c[ip][0] = 0; c[ip][1] = 0; }
+#pragma unroll 1
+  for (int cc = 0; cc < 9; cc++) {
+    F S[16][2];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { const CplxT<F> v = prop[((size_t)k * 9 + cc) * V + x]; S[k][0] = v.re; S[k][1] = v.im; }
+    if constexpr (sizeof(F) == 8) {
+      meson_group<0>(S, W, c, 1, 4, 9);
+      meson_group<1>(S, W, c, 2, 3, -1);
+      meson_group<2>(S, W, c, 0, 5, 8);
+      meson_group<3>(S, W, c, 6, 7, -1);
+    } else {
+      F acc[10][2];
+#pragma unroll
+      for (int ip = 0; ip < 10; ip++) { acc[ip][0] = 0; acc[ip][1] = 0; }
+      meson_group<0>(S, W, acc, 1, 4, 9);
+      meson_group<1>(S, W, acc, 2, 3, -1);
+      meson_group<2>(S, W, acc, 0, 5, 8);
+      meson_group<3>(S, W, acc, 6, 7, -1);
+#pragma unroll
+      for (int ip = 0; ip < 10; ip++) { c[ip][0] += (double)acc[ip][0]; c[ip][1] += (double)acc[ip][1]; }
+    }
+  }
+#pragma unroll
+  for (int ip = 0; ip < 10; ip++) {
+    CplxT<double> o; o.re = c[ip][0]; o.im = c[ip][1];
+    csite[((size_t)iu * 10 + ip) * V + x] = o;
+  }
+}
+
+// ---- one axis of the separable Fourier sum -----------------------------------------------------------------------------
+// in [ch][parent][outer][L] (L fastest) -> out[ch][child][outer]:  out = sum_k tab[q][k] in[.., k] for every entry q of the parent's
+// child list (child_start / child_out); one warp per input row, lanes stride the row, fixed-order shuffle tree.
+struct DftStage {
+  const CplxT<double> *in;
+  CplxT<double> *out;
+  const CplxT<double> *tab;      // [nlist][L]
+  const int *child_start;        // [nparent + 1]
+  const int *child_out;          // [nlist] -> output index
+  int nparent, nout, L, nch;
+  size_t outer;
+};
+constexpr int DFT_MAXK = 8;      // L <= 256
+__global__ void __launch_bounds__(256) axis_dft_kernel(DftStage s) {
+  const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const size_t nrows = (size_t)s.nch * s.nparent * s.outer;
+  if (row >= nrows) return;
+  const size_t o = row % s.outer, cp = row / s.outer;
+  const int p = (int)(cp % s.nparent), ch = (int)(cp / s.nparent);
+  double vr[DFT_MAXK], vi[DFT_MAXK];
+#pragma unroll
+  for (int j = 0; j < DFT_MAXK; j++) {
+    const int k = lane + 32 * j;
+    if (k < s.L) { const CplxT<double> v = s.in[row * s.L + k]; vr[j] = v.re; vi[j] = v.im; } else { vr[j] = 0; vi[j] = 0; }
+  }
+  for (int q = s.child_start[p]; q < s.child_start[p + 1]; q++) {
+    double ar = 0, ai = 0;
+#pragma unroll
+    for (int j = 0; j < DFT_MAXK; j++) {
+      const int k = lane + 32 * j;
+      if (k < s.L) {
+        const CplxT<double> e = s.tab[(size_t)q * s.L + k];
+        ar += e.re * vr[j] - e.im * vi[j];
+        ai += e.re * vi[j] + e.im * vr[j];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { ar += __shfl_down_sync(0xffffffffu, ar, off); ai += __shfl_down_sync(0xffffffffu, ai, off); }
+    if (lane == 0) { CplxT<double> r; r.re = ar; r.im = ai; s.out[((size_t)ch * s.nout + s.child_out[q]) * s.outer + o] = r; }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+typedef std::complex<double> cd;
+struct Mat4 { cd m[4][4]; };
+static Mat4 mul(const Mat4 &a, const Mat4 &b) {
+  Mat4 r;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { cd s = 0; for (int k = 0; k < 4; k++) s += a.m[i][k] * b.m[k][j]; r.m[i][j] = s; }
+  return r;
+}
+// UKQCD gamma matrices (lib/code_pieces/gammas_tm_base.h:21-32; gamma5 = g1 g2 g3 g4 = spin swap, apply_gamma5_vector_core.h)
+static void ukqcd_gammas(Mat4 g[5]) {
+  const cd I(0, 1);
+  for (int k = 0; k < 5; k++) for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) g[k].m[i][j] = 0;
+  g[0].m[0][3] = I; g[0].m[1][2] = I; g[0].m[2][1] = -I; g[0].m[3][0] = -I;
+  g[1].m[0][3] = 1; g[1].m[1][2] = -1; g[1].m[2][1] = -1; g[1].m[3][0] = 1;
+  g[2].m[0][2] = I; g[2].m[1][3] = -I; g[2].m[2][0] = -I; g[2].m[3][1] = I;
+  g[3].m[0][0] = 1; g[3].m[1][1] = 1; g[3].m[2][2] = -1; g[3].m[3][3] = -1;
+  g[4] = mul(mul(g[0], g[1]), mul(g[2], g[3]));
+}
+// signs s_G phi_a conj(phi_g) of the ten channels, derived from the gamma matrices; fails if a channel's permutation is not the
+// XOR the site kernel was compiled for, or if a weight is not +-1
+static int meson_signs(MesonSigns<double> *W) {
+  Mat4 g[5];
+  ukqcd_gammas(g);
+  Mat4 one;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) one.m[i][j] = i == j ? 1.0 : 0.0;
+  Mat4 G[10] = {g[4], one, mul(g[4], g[0]), mul(g[4], g[1]), mul(g[4], g[2]), mul(g[4], g[3]), g[0], g[1], g[2], g[3]};
+  const int xors[10] = TMQ_MESON_XORS;
+  for (int a = 0; a < 4; a++)
+    for (int b = 0; b < 4; b++)
+      if (std::abs(g[4].m[a][b] - ((a ^ 2) == b ? 1.0 : 0.0)) > 1e-15) { set_error("gamma5 is not the spin swap"); return 1; }
+  for (int ip = 0; ip < 10; ip++) {
+    const double sG = ip < 6 ? 1.0 : -1.0;
+    cd phi[4];
+    for (int a = 0; a < 4; a++) {
+      for (int b = 0; b < 4; b++)
+        if ((b == (a ^ xors[ip])) != (std::abs(G[ip].m[a][b]) > 0.5)) { set_error("meson channel %d: unexpected spin permutation", ip); return 1; }
+      phi[a] = G[ip].m[a][a ^ xors[ip]];
+    }
+    for (int a = 0; a < 4; a++)
+      for (int b = 0; b < 4; b++) {
+        const cd w = sG * phi[a] * std::conj(phi[b]);
+        if (std::abs(w.imag()) > 1e-15 || std::abs(std::abs(w.real()) - 1.0) > 1e-15) { set_error("meson channel %d: weight is not +-1", ip); return 1; }
+        W->w[ip][a * 4 + b] = w.real();
+      }
+  }
+  return 0;
+}
+
+// carve-out of the context's grow-only contraction work space (256-byte aligned pieces)
+struct WsPlan {
+  size_t total = 0;
+  size_t add(size_t bytes) { const size_t off = total; total += (bytes + 255) & ~(size_t)255; return off; }
+};
+static int ensure_contract_ws(tmq_ctx *c, size_t bytes) {
+  if (c->contract_ws_bytes >= bytes) return 0;
+  if (c->contract_ws) { TMQ_CUDA(cudaStreamSynchronize(c->stream)); TMQ_CUDA(cudaFree(c->contract_ws)); c->contract_ws = nullptr; c->contract_ws_bytes = 0; }
+  TMQ_CUDA(cudaMalloc(&c->contract_ws, bytes));
+  c->contract_ws_bytes = bytes;
+  return 0;
+}
+template <typename T> static cudaError_t upload(void *dst, const std::vector<T> &h, cudaStream_t st) {
+  return cudaMemcpyAsync(dst, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+static cudaError_t run_stage(const DftStage &s, cudaStream_t st) {
+  const size_t nrows = (size_t)s.nch * s.nparent * s.outer;
+  axis_dft_kernel<<<(unsigned int)((nrows + 7) / 8), 256, 0, st>>>(s);
+  return cudaGetLastError();
+}
+
+// exp(-2 pi i q (k + off - k0) / Ltot) for k = 0..L-1
+static void phase_row(std::vector<CplxT<double>> &tab, int q, int L, int off, int k0, int Ltot) {
+  for (int k = 0; k < L; k++) {
+    // reduce the integer numerator first: the phase is exact to the last bit of the argument
+    long long num = ((long long)q * (k + off - k0)) % Ltot;
+    const double ph = 2.0 * M_PI * (double)num / (double)Ltot;
+    CplxT<double> e; e.re = cos(ph); e.im = -sin(ph);
+    tab.push_back(e);
+  }
+}
+
+}  // namespace tmq
+
+using namespace tmq;
+
+extern "C" {
+
+int tmq_qkxtm_conjugate(tmq_ctx *c, void *d, int prec, int ncomp) {
+  TMQ_REQUIRE(c && d, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(ncomp > 0, "bad component count");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)2 * c->g.Vh * ncomp;
+  const unsigned int grid = (unsigned int)((n + 255) / 256);
+  if (prec == 8) qk_conj_kernel<double><<<grid, 256, 0, c->stream>>>((CplxT<double> *)d, n);
+  else qk_conj_kernel<float><<<grid, 256, 0, c->stream>>>((CplxT<float> *)d, n);
+  TMQ_CUDA(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int tmq_qkxtm_gamma5_prop(tmq_ctx *c, void *d_prop, int prec) {
+  TMQ_REQUIRE(c && d_prop, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  const size_t V = (size_t)2 * c->g.Vh, n = V * 72;
+  const unsigned int grid = (unsigned int)((n + 255) / 256);
+  if (prec == 8) qk_gamma5_prop_kernel<double><<<grid, 256, 0, c->stream>>>((CplxT<double> *)d_prop, V);
+  else qk_gamma5_prop_kernel<float><<<grid, 256, 0, c->stream>>>((CplxT<float> *)d_prop, V);
+  TMQ_CUDA(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int tmq_qkxtm_rotate_physical(tmq_ctx *c, void *d_prop, int prec, int sign) {
+  TMQ_REQUIRE(c && d_prop, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(sign == 1 || sign == -1, "The sign can be only +-1");      // lib/qudaQKXTM_Propagator.cpp:110
+  TMQ_CUDA(cudaSetDevice(c->device));
+  const size_t V = (size_t)2 * c->g.Vh, n = V * 9;
+  const unsigned int grid = (unsigned int)((n + CT_BLOCK - 1) / CT_BLOCK);
+  if (prec == 8) qk_rotate_kernel<double><<<grid, CT_BLOCK, 0, c->stream>>>((CplxT<double> *)d_prop, V, (double)sign);
+  else qk_rotate_kernel<float><<<grid, CT_BLOCK, 0, c->stream>>>((CplxT<float> *)d_prop, V, (float)sign);
+  TMQ_CUDA(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int tmq_qkxtm_column_copy(tmq_ctx *c, void *d_prop, long long prop_sites, long long prop_site0, void *d_vec, long long vec_sites,
+                          long long vec_site0, long long nsites, int prec, int nu, int c2, int to_prop) {
+  TMQ_REQUIRE(c && d_prop && d_vec, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(nu >= 0 && nu < 4 && c2 >= 0 && c2 < 3, "bad column");
+  TMQ_REQUIRE(nsites > 0 && prop_site0 >= 0 && vec_site0 >= 0 && prop_site0 + nsites <= prop_sites && vec_site0 + nsites <= vec_sites,
+              "site range out of bounds");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  const size_t cb = (size_t)2 * prec;
+  for (int mu = 0; mu < 4; mu++)
+    for (int c1 = 0; c1 < 3; c1++) {
+      char *p = (char *)d_prop + (((size_t)(mu * 4 + nu) * 9 + c1 * 3 + c2) * prop_sites + prop_site0) * cb;
+      char *v = (char *)d_vec + ((size_t)(mu * 3 + c1) * vec_sites + vec_site0) * cb;
+      TMQ_CUDA(cudaMemcpyAsync(to_prop ? p : v, to_prop ? v : p, (size_t)nsites * cb, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  return 0;
+}
+
+int tmq_qkxtm_contract_mesons(tmq_ctx *c, const void *d_prop1, const void *d_prop2, int prec, const int *moms, int nmoms,
+                              const int src_pos[3], double *corr_mom, double *corr_pos) {
+  TMQ_REQUIRE(c && d_prop1 && d_prop2, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(corr_mom || corr_pos, "no output requested");
+  TMQ_REQUIRE(!corr_mom || (moms && nmoms > 0 && src_pos), "momentum-space output needs a momentum list and a source position");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  static MesonSigns<double> W;
+  static MesonSigns<float> Wf;
+  static bool have_w = false;
+  if (!have_w) {
+    TMQ_TRY(meson_signs(&W));
+    for (int ip = 0; ip < 10; ip++) for (int q = 0; q < 16; q++) Wf.w[ip][q] = (float)W.w[ip][q];
+    have_w = true;
+  }
+  const int X = c->g.X[0], Y = c->g.X[1], Z = c->g.X[2], T = c->g.X[3];
+  const size_t V = (size_t)2 * c->g.Vh;
+  TMQ_REQUIRE(X <= 32 * DFT_MAXK && Y <= 32 * DFT_MAXK && Z <= 32 * DFT_MAXK, "spatial extent above %d not supported", 32 * DFT_MAXK);
+  cudaStream_t st = c->stream;
+
+  // ---- separable projection plan: distinct p_x, distinct (p_x, p_y), the momenta (host side, tiny) ------------------------------
+  std::vector<int> px_list;
+  std::map<int, int> px_idx;
+  std::vector<std::pair<int, int>> pair_list;      // (ix, py), grouped by ix
+  std::map<std::pair<int, int>, int> pair_idx;
+  if (corr_mom) {
+    for (int m = 0; m < nmoms; m++) if (!px_idx.count(moms[3 * m])) { px_idx[moms[3 * m]] = (int)px_list.size(); px_list.push_back(moms[3 * m]); }
+    for (int ix = 0; ix < (int)px_list.size(); ix++)
+      for (int m = 0; m < nmoms; m++) {
+        if (px_idx[moms[3 * m]] != ix) continue;
+        const std::pair<int, int> key(ix, moms[3 * m + 1]);
+        if (!pair_idx.count(key)) { pair_idx[key] = (int)pair_list.size(); pair_list.push_back(key); }
+      }
+  }
+  const int npx = (int)px_list.size(), npair = (int)pair_list.size();
+  const size_t outer1 = (size_t)T * Z * Y, outer2 = (size_t)T * Z, outer3 = (size_t)T;
+  const int gT = T * c->grid[3], t_off = c->coord[3] * T;
+  const size_t ntot = corr_mom ? (size_t)gT * nmoms * 40 : 0;
+  const size_t CB = sizeof(CplxT<double>);
+  WsPlan plan;
+  const size_t o_csite = plan.add(V * 20 * CB);
+  const size_t o_w1 = plan.add((size_t)20 * npx * outer1 * CB), o_w2 = plan.add((size_t)20 * npair * outer2 * CB);
+  const size_t o_w3 = plan.add((size_t)20 * nmoms * outer3 * CB);
+  const size_t o_tab1 = plan.add((size_t)npx * X * CB), o_tab2 = plan.add((size_t)npair * Y * CB), o_tab3 = plan.add((size_t)nmoms * Z * CB);
+  const size_t o_s1 = plan.add(2 * sizeof(int)), o_s2 = plan.add((npx + 1) * sizeof(int)), o_s3 = plan.add((npair + 1) * sizeof(int));
+  const size_t o_o1 = plan.add(npx * sizeof(int)), o_o2 = plan.add(npair * sizeof(int)), o_o3 = plan.add((size_t)nmoms * sizeof(int));
+  const size_t o_glob = plan.add(ntot * sizeof(double));
+  TMQ_TRY(ensure_contract_ws(c, plan.total));
+  char *ws = (char *)c->contract_ws;
+  CplxT<double> *csite = (CplxT<double> *)(ws + o_csite);
+
+  const dim3 grid((unsigned int)((V + CT_BLOCK - 1) / CT_BLOCK), 2);
+  if (prec == 8) meson_site_kernel<double><<<grid, CT_BLOCK, 0, st>>>(csite, (const CplxT<double> *)d_prop1, (const CplxT<double> *)d_prop2, V, W);
+  else meson_site_kernel<float><<<grid, CT_BLOCK, 0, st>>>(csite, (const CplxT<float> *)d_prop1, (const CplxT<float> *)d_prop2, V, Wf);
+  TMQ_CUDA(cudaGetLastError());
+  c->launches++;
+
+  if (corr_pos) {
+    // position space: [t][spatial site][iu][ip][re,im] like the reference's corr[2*sv + 2*SpVol*it + ri][pt][mes] (kernels.cu:1160-1165)
+    std::vector<double> h(V * 40);
+    TMQ_CUDA(cudaMemcpyAsync(h.data(), csite, V * 40 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TMQ_CUDA(cudaStreamSynchronize(st));
+    for (size_t x = 0; x < V; x++)
+      for (int ch = 0; ch < 20; ch++) { corr_pos[(x * 20 + ch) * 2] = h[((size_t)ch * V + x) * 2]; corr_pos[(x * 20 + ch) * 2 + 1] = h[((size_t)ch * V + x) * 2 + 1]; }
+  }
+  if (!corr_mom) return 0;
+
+  const int gX = X * c->grid[0], gY = Y * c->grid[1], gZ = Z * c->grid[2];
+  // stage 1 (x): one parent, children = all p_x
+  std::vector<CplxT<double>> tab1, tab2, tab3;
+  std::vector<int> start1 = {0, npx}, out1(npx), start2(npx + 1, 0), out2, start3(npair + 1, 0), out3;
+  for (int ix = 0; ix < npx; ix++) { out1[ix] = ix; phase_row(tab1, px_list[ix], X, c->coord[0] * X, src_pos[0], gX); }
+  // stage 2 (y): parent ix -> its pairs (contiguous by construction)
+  for (int ix = 0; ix < npx; ix++) {
+    start2[ix] = (int)out2.size();
+    for (int j = 0; j < npair; j++) if (pair_list[j].first == ix) { out2.push_back(j); phase_row(tab2, pair_list[j].second, Y, c->coord[1] * Y, src_pos[1], gY); }
+  }
+  start2[npx] = (int)out2.size();
+  // stage 3 (z): parent pair -> the momenta with that (p_x, p_y), output index = the caller's momentum index
+  for (int j = 0; j < npair; j++) {
+    start3[j] = (int)out3.size();
+    for (int m = 0; m < nmoms; m++)
+      if (px_idx[moms[3 * m]] == pair_list[j].first && moms[3 * m + 1] == pair_list[j].second) { out3.push_back(m); phase_row(tab3, moms[3 * m + 2], Z, c->coord[2] * Z, src_pos[2], gZ); }
+  }
+  start3[npair] = (int)out3.size();
+
+  TMQ_CUDA(upload(ws + o_tab1, tab1, st)); TMQ_CUDA(upload(ws + o_tab2, tab2, st)); TMQ_CUDA(upload(ws + o_tab3, tab3, st));
+  TMQ_CUDA(upload(ws + o_s1, start1, st)); TMQ_CUDA(upload(ws + o_s2, start2, st)); TMQ_CUDA(upload(ws + o_s3, start3, st));
+  TMQ_CUDA(upload(ws + o_o1, out1, st)); TMQ_CUDA(upload(ws + o_o2, out2, st)); TMQ_CUDA(upload(ws + o_o3, out3, st));
+  const bool sharded = c->nranks > 1;
+  typedef const CplxT<double> *cptr;
+  DftStage s1 = {csite, (CplxT<double> *)(ws + o_w1), (cptr)(ws + o_tab1), (const int *)(ws + o_s1), (const int *)(ws + o_o1), 1, npx, X, 20, outer1};
+  DftStage s2 = {(cptr)(ws + o_w1), (CplxT<double> *)(ws + o_w2), (cptr)(ws + o_tab2), (const int *)(ws + o_s2), (const int *)(ws + o_o2), npx, npair, Y, 20, outer2};
+  DftStage s3 = {(cptr)(ws + o_w2), (CplxT<double> *)(ws + o_w3), (cptr)(ws + o_tab3), (const int *)(ws + o_s3), (const int *)(ws + o_o3), npair, nmoms, Z, 20, outer3};
+  TMQ_CUDA(run_stage(s1, st)); TMQ_CUDA(run_stage(s2, st)); TMQ_CUDA(run_stage(s3, st));
+  c->launches += 3;
+
+  // w3[ch][m][t] -> corr_mom[t_global][m][iu][ip][re,im]
+  std::vector<double> h((size_t)40 * nmoms * T);
+  TMQ_CUDA(cudaMemcpyAsync(h.data(), ws + o_w3, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TMQ_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < ntot; i++) corr_mom[i] = 0.0;
+  for (int t = 0; t < T; t++)
+    for (int m = 0; m < nmoms; m++)
+      for (int ch = 0; ch < 20; ch++) {
+        const size_t src = (((size_t)ch * nmoms + m) * T + t) * 2, dst = ((((size_t)(t + t_off)) * nmoms + m) * 20 + ch) * 2;
+        corr_mom[dst] = h[src]; corr_mom[dst + 1] = h[src + 1];
+      }
+  if (sharded) {
+    // sum over the z ranks and gather over the t ranks in one all-reduce of the zero-padded global-T buffers
+    double *g = (double *)(ws + o_glob);
+    TMQ_CUDA(cudaMemcpyAsync(g, corr_mom, ntot * sizeof(double), cudaMemcpyHostToDevice, st));
+    // chunks of more than 4 doubles always take the NCCL path of comm_allreduce
+    TMQ_REQUIRE(ntot > 4, "internal: reduction too short");
+    TMQ_TRY(comm_allreduce(c, g, (int)ntot, st));
+    TMQ_CUDA(cudaMemcpyAsync(corr_mom, g, ntot * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TMQ_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+}  // extern "C"

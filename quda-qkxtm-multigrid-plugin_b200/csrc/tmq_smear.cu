@@ -6,8 +6,12 @@
 //      gauge  d[((dir*3+c1)*3+c2)*V + x]  (the APE-smeared links)              lib/qudaQKXTM_Gauge.cpp:73-89
 // The reference runs nsmear (= 50) texture-fetch launches, each followed by a synchronous host-staged ghost exchange
 // of the whole vector.  Here:
-//   * the time direction does not hop, so time slices are independent: a T-sharded lattice needs NO exchange at all
-//     (z-sharding is refused for this entry point), and
+//   * the time direction does not hop, so time slices are independent: a T-sharded lattice needs NO exchange at all;
+//     on a z split the two z faces of the vector (24 reals per face site, as the reference's ghost zone,
+//     lib/qudaQKXTM_Vector.cpp:334) are packed on the device and exchanged with the z neighbours before every step
+//     (NCCL send/recv; a device copy when the dimension wraps onto this rank), and the U_z links of the neighbour's
+//     last z slice are fetched once per call, so the arithmetic -- and hence every bit of the result -- is that of
+//     the unsharded sweep, and
 //   * optionally (TMQ_OPT_SMEAR_BLOCK_T) the sweep order is (block of time slices) outer, (smearing step) inner, so that
 //     the ping-pong vectors and the three spatial link directions of a block (90 MB for one 48^3 slice in fp64) stay
 //     resident in the 126 MB L2 across the nsmear steps.  MEASURED on B200 at 48^3x96 (profiles/r03_smear_bench.jsonl):
@@ -34,17 +38,19 @@ struct SmearGeom {
 
 // acc[s][a] += sum_b U[a][b] psi[s][b]   (apply_U_on_S, lib/code_pieces/core_def.h:498-513)
 // acc[s][a] += sum_b conj(U[b][a]) psi[s][b]   (apply_U_DAG_on_S, :515-530)
+// The link is read at gauge[glink + k*GV], the neighbour spinor at in[nsite + k*SV]: (GV, SV) = (V, V) in the bulk, the face
+// size when the operand comes from a ghost buffer.
 template <typename F, bool DAG>
-__device__ __forceinline__ void su3_acc(F (&acc)[12][2], const CplxT<F> *__restrict__ gauge, size_t glink, const CplxT<F> *__restrict__ in,
-                                        size_t nsite, size_t V) {
+__device__ __forceinline__ void su3_acc(F (&acc)[12][2], const CplxT<F> *__restrict__ gauge, size_t glink, size_t GV,
+                                        const CplxT<F> *__restrict__ in, size_t nsite, size_t SV) {
   F u[9][2];
 #pragma unroll
-  for (int k = 0; k < 9; k++) { const CplxT<F> g = gauge[glink + (size_t)k * V]; u[k][0] = g.re; u[k][1] = g.im; }
+  for (int k = 0; k < 9; k++) { const CplxT<F> g = gauge[glink + (size_t)k * GV]; u[k][0] = g.re; u[k][1] = g.im; }
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     F p[3][2];
 #pragma unroll
-    for (int b = 0; b < 3; b++) { const CplxT<F> v = in[(size_t)(s * 3 + b) * V + nsite]; p[b][0] = v.re; p[b][1] = v.im; }
+    for (int b = 0; b < 3; b++) { const CplxT<F> v = in[(size_t)(s * 3 + b) * SV + nsite]; p[b][0] = v.re; p[b][1] = v.im; }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       F re = acc[s * 3 + a][0], im = acc[s * 3 + a][1];
@@ -63,9 +69,17 @@ __device__ __forceinline__ void su3_acc(F (&acc)[12][2], const CplxT<F> *__restr
   }
 }
 
-template <typename F>
+// ghost operands of a z-partitioned sweep, all indexed by the face site f = (t*Y + y)*X + x with component stride F = X*Y*T:
+//   psi_fwd: the forward neighbour's z = 0 slice, psi_bwd / uz_bwd: the backward neighbour's z = L-1 slice and its U_z links
+template <typename F> struct SmearGhost {
+  const CplxT<F> *psi_fwd, *psi_bwd, *uz_bwd;
+  size_t F_;
+};
+
+template <typename F, bool ZGHOST>
 __global__ void __launch_bounds__(SMEAR_BLOCK, (sizeof(F) == 8 ? 4 : 8)) gauss_smear_kernel(CplxT<F> *__restrict__ out, const CplxT<F> *__restrict__ in,
-                                                                 const CplxT<F> *__restrict__ gauge, SmearGeom g, F alpha, F normalize) {
+                                                                 const CplxT<F> *__restrict__ gauge, SmearGeom g, F alpha, F normalize,
+                                                                 SmearGhost<F> gh) {
   const uint32_t e = blockIdx.x * SMEAR_BLOCK + threadIdx.x;
   const uint32_t nsl = (uint32_t)(g.X[0] * g.X[1] * g.X[2]);
   if (e >= nsl * (uint32_t)g.nt) return;
@@ -84,12 +98,21 @@ __global__ void __launch_bounds__(SMEAR_BLOCK, (sizeof(F) == 8 ? 4 : 8)) gauss_s
   F acc[12][2];
 #pragma unroll
   for (int k = 0; k < 12; k++) { acc[k][0] = 0; acc[k][1] = 0; }
-  su3_acc<F, false>(acc, gauge, (size_t)0 * 9 * V + sid, in, xp, V);
-  su3_acc<F, true>(acc, gauge, (size_t)0 * 9 * V + xm, in, xm, V);
-  su3_acc<F, false>(acc, gauge, (size_t)1 * 9 * V + sid, in, yp, V);
-  su3_acc<F, true>(acc, gauge, (size_t)1 * 9 * V + ym, in, ym, V);
-  su3_acc<F, false>(acc, gauge, (size_t)2 * 9 * V + sid, in, zp, V);
-  su3_acc<F, true>(acc, gauge, (size_t)2 * 9 * V + zm, in, zm, V);
+  su3_acc<F, false>(acc, gauge, (size_t)0 * 9 * V + sid, V, in, xp, V);
+  su3_acc<F, true>(acc, gauge, (size_t)0 * 9 * V + xm, V, in, xm, V);
+  su3_acc<F, false>(acc, gauge, (size_t)1 * 9 * V + sid, V, in, yp, V);
+  su3_acc<F, true>(acc, gauge, (size_t)1 * 9 * V + ym, V, in, ym, V);
+  if (ZGHOST) {
+    // same operands in the same order as the unsharded sweep, only fetched from the ghost buffers on the two z faces
+    const size_t f = ((size_t)t * g.X[1] + y) * g.X[0] + x;
+    if (z == g.X[2] - 1) su3_acc<F, false>(acc, gauge, (size_t)2 * 9 * V + sid, V, gh.psi_fwd, f, gh.F_);
+    else su3_acc<F, false>(acc, gauge, (size_t)2 * 9 * V + sid, V, in, zp, V);
+    if (z == 0) su3_acc<F, true>(acc, gh.uz_bwd, f, gh.F_, gh.psi_bwd, f, gh.F_);
+    else su3_acc<F, true>(acc, gauge, (size_t)2 * 9 * V + zm, V, in, zm, V);
+  } else {
+    su3_acc<F, false>(acc, gauge, (size_t)2 * 9 * V + sid, V, in, zp, V);
+    su3_acc<F, true>(acc, gauge, (size_t)2 * 9 * V + zm, V, in, zm, V);
+  }
 #pragma unroll
   for (int k = 0; k < 12; k++) {
     const CplxT<F> s = in[(size_t)k * V + sid];
@@ -101,11 +124,38 @@ __global__ void __launch_bounds__(SMEAR_BLOCK, (sizeof(F) == 8 ? 4 : 8)) gauss_s
 }
 
 template <typename F>
-static cudaError_t smear_launch(void *out, const void *in, const void *gauge, const SmearGeom &g, double alpha, cudaStream_t st) {
+static cudaError_t smear_launch(void *out, const void *in, const void *gauge, const SmearGeom &g, double alpha, const SmearGhost<F> *gh,
+                                cudaStream_t st) {
   const size_t n = (size_t)g.X[0] * g.X[1] * g.X[2] * g.nt;
   const unsigned int grid = (unsigned int)((n + SMEAR_BLOCK - 1) / SMEAR_BLOCK);
-  gauss_smear_kernel<F><<<grid, SMEAR_BLOCK, 0, st>>>((CplxT<F> *)out, (const CplxT<F> *)in, (const CplxT<F> *)gauge, g, (F)alpha,
-                                                     (F)(1.0 / (1.0 + 6.0 * alpha)));
+  if (gh)
+    gauss_smear_kernel<F, true><<<grid, SMEAR_BLOCK, 0, st>>>((CplxT<F> *)out, (const CplxT<F> *)in, (const CplxT<F> *)gauge, g, (F)alpha,
+                                                             (F)(1.0 / (1.0 + 6.0 * alpha)), *gh);
+  else
+    gauss_smear_kernel<F, false><<<grid, SMEAR_BLOCK, 0, st>>>((CplxT<F> *)out, (const CplxT<F> *)in, (const CplxT<F> *)gauge, g, (F)alpha,
+                                                              (F)(1.0 / (1.0 + 6.0 * alpha)), SmearGhost<F>{nullptr, nullptr, nullptr, 0});
+  return cudaGetLastError();
+}
+
+// gather ncomp components of the z slices 0 and L-1 of a QKXTM SoA field (component stride V) into contiguous face
+// buffers lo / hi [ncomp][T*Y*X]; either destination may be null.  One thread per (component, face site).
+template <typename F>
+__global__ void __launch_bounds__(SMEAR_BLOCK) zface_pack_kernel(CplxT<F> *__restrict__ lo, CplxT<F> *__restrict__ hi, const CplxT<F> *__restrict__ src,
+                                                                int ncomp, int X, int Y, int Z, int T, size_t V) {
+  const size_t nface = (size_t)X * Y * T;
+  const size_t e = (size_t)blockIdx.x * SMEAR_BLOCK + threadIdx.x;
+  if (e >= nface * ncomp) return;
+  const size_t k = e / nface, f = e - k * nface;
+  const size_t xy = f % ((size_t)X * Y), t = f / ((size_t)X * Y);
+  const size_t s0 = t * Z * X * Y + xy;                            // z = 0
+  if (lo) lo[e] = src[k * V + s0];
+  if (hi) hi[e] = src[k * V + s0 + (size_t)(Z - 1) * X * Y];       // z = L-1
+}
+template <typename F>
+static cudaError_t zface_pack(void *lo, void *hi, const void *src, int ncomp, const SmearGeom &g, cudaStream_t st) {
+  const size_t n = (size_t)g.X[0] * g.X[1] * g.X[3] * ncomp;
+  zface_pack_kernel<F><<<(unsigned int)((n + SMEAR_BLOCK - 1) / SMEAR_BLOCK), SMEAR_BLOCK, 0, st>>>((CplxT<F> *)lo, (CplxT<F> *)hi, (const CplxT<F> *)src,
+                                                                                                  ncomp, g.X[0], g.X[1], g.X[2], g.X[3], g.V);
   return cudaGetLastError();
 }
 
@@ -116,17 +166,50 @@ int smear_run(tmq_ctx *c, void *a, void *b, const void *gauge, int prec, int nsm
   g.dX = make_fastdiv((uint32_t)g.X[0]); g.dY = make_fastdiv((uint32_t)g.X[1]); g.dZ = make_fastdiv((uint32_t)g.X[2]);
   g.V = (size_t)2 * c->g.Vh;
   const int T = g.X[3];
-  if (block_t <= 0) block_t = T;        // default: plain streaming order (measured faster, see the header comment)
+  const bool zghost = c->g.part[2] != 0;   // z split across ranks, or forced onto the ghost path (tmq_force_partition)
+  if (block_t <= 0 || zghost) block_t = T;  // default: plain streaming order (measured faster, see the header comment)
   if (block_t > T) block_t = T;
-  for (int t0 = 0; t0 < T; t0 += block_t) {
+
+  // ghost-zone work space of a z-partitioned sweep: [send lo | send hi | recv from fwd | recv from bwd] spinor faces and the
+  // backward neighbour's U_z face (sent once: the links do not change between steps)
+  char *ws = nullptr;
+  const size_t nface = (size_t)g.X[0] * g.X[1] * T, cb = (size_t)2 * prec;
+  const size_t sp_face = 12 * nface * cb, u_face = 9 * nface * cb;
+  SmearGhost<double> ghd = {nullptr, nullptr, nullptr, nface};
+  SmearGhost<float> ghs = {nullptr, nullptr, nullptr, nface};
+  if (zghost && nsmear > 0) {
+    TMQ_CUDA(cudaMalloc((void **)&ws, 4 * sp_face + 2 * u_face));
+    char *u_send = ws + 4 * sp_face, *u_recv = u_send + u_face;
+    const char *uz = (const char *)gauge + (size_t)2 * 9 * g.V * cb;
+    TMQ_CUDA(prec == 8 ? zface_pack<double>(nullptr, u_send, uz, 9, g, c->stream) : zface_pack<float>(nullptr, u_send, uz, 9, g, c->stream));
+    c->launches++;
+    // only the forward-going face carries data; the backward-going message re-sends it and lands in the spinor area, unused
+    int rc = comm_sendrecv_dim(c, 2, u_send, u_send, ws, u_recv, u_face, c->stream);
+    if (rc) { cudaFree(ws); return rc; }
+    ghd.psi_fwd = (const CplxT<double> *)(ws + 2 * sp_face); ghd.psi_bwd = (const CplxT<double> *)(ws + 3 * sp_face); ghd.uz_bwd = (const CplxT<double> *)u_recv;
+    ghs.psi_fwd = (const CplxT<float> *)(ws + 2 * sp_face); ghs.psi_bwd = (const CplxT<float> *)(ws + 3 * sp_face); ghs.uz_bwd = (const CplxT<float> *)u_recv;
+  }
+  int rc = 0;
+  for (int t0 = 0; t0 < T && !rc; t0 += block_t) {
     g.t0 = t0; g.nt = (t0 + block_t <= T) ? block_t : T - t0;
     void *src = a, *dst = b;
-    for (int i = 0; i < nsmear; i++) {
-      TMQ_CUDA(prec == 8 ? smear_launch<double>(dst, src, gauge, g, alpha, c->stream) : smear_launch<float>(dst, src, gauge, g, alpha, c->stream));
+    for (int i = 0; i < nsmear && !rc; i++) {
+      cudaError_t e = cudaSuccess;
+      if (zghost) {
+        e = prec == 8 ? zface_pack<double>(ws, ws + sp_face, src, 12, g, c->stream) : zface_pack<float>(ws, ws + sp_face, src, 12, g, c->stream);
+        c->launches++;
+        if (e == cudaSuccess) rc = comm_sendrecv_dim(c, 2, ws, ws + sp_face, ws + 2 * sp_face, ws + 3 * sp_face, sp_face, c->stream);
+      }
+      if (e == cudaSuccess && !rc)
+        e = prec == 8 ? smear_launch<double>(dst, src, gauge, g, alpha, zghost ? &ghd : nullptr, c->stream)
+                      : smear_launch<float>(dst, src, gauge, g, alpha, zghost ? &ghs : nullptr, c->stream);
+      if (e != cudaSuccess) { set_error("%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e)); rc = 1; }
       c->launches++;
       void *tmp = src; src = dst; dst = tmp;
     }
   }
+  if (ws) { cudaStreamSynchronize(c->stream); cudaFree(ws); }
+  if (rc) return rc;
   *result = (nsmear & 1) ? b : a;
   return 0;
 }
@@ -142,8 +225,7 @@ int tmq_qkxtm_gauss_smear(tmq_ctx *c, void *d_out, void *d_in, const void *d_gau
   TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
   TMQ_REQUIRE(nsmear >= 0, "nsmear must be >= 0");
   TMQ_REQUIRE(d_out != d_in, "out must not alias in");
-  TMQ_REQUIRE(c->grid[0] == 1 && c->grid[1] == 1 && c->grid[2] == 1,
-              "Gaussian smearing is 3-dimensional: it needs no exchange on a T-sharded lattice, a z split is not supported");
+  TMQ_REQUIRE(c->grid[0] == 1 && c->grid[1] == 1, "only z and t may be partitioned");
   TMQ_CUDA(cudaSetDevice(c->device));
   void *res = nullptr;
   // the reference ping-pongs between `this` (out) and vecIn, first step vecIn -> this (lib/qudaQKXTM_Vector.cpp:403-417)

@@ -17,7 +17,9 @@ static void usage() {
   printf("qkxtm_invert_test --dim X Y Z T [--kappa k | --mass m] [--mu mu] [--tol t] [--niter n]\n"
          "   [--prec-sloppy double|single] [--recon 12|18] [--matpc even-even|odd-odd] [--mass-normalization kappa|mass]\n"
          "   [--test invert|mgbench|loops|mdagm|mat] [--source z4|gaussian] [--seed s] [--verbosity-level silent|summarize|verbose]\n"
-         "   [--out file] [--dump-inputs prefix]\n");
+         "   [--out file] [--dump-inputs prefix]\n"
+         "   --test twop [--Q_sq q] [--src x y z t] [--nsmearGauss n --alphaGauss a]: meson two-point function, written to\n"
+         "       <out>.mesons.SS.xx.yy.zz.tt.dat\n");
 }
 
 int main(int argc, char **argv) {
@@ -28,6 +30,7 @@ int main(int argc, char **argv) {
   unsigned long long seed = 100;
   int nev = 4, nkv = 16, polydeg = 20;
   double amin = 0.385, amax = 2.0, eig_tol = 1e-10, csw = 0.0;
+  int q_sq = 0, src_pos[4] = {0, 0, 0, 0};
   std::string dslash_type = "twisted-mass";
   int nsmearGauss = 0; double alphaGauss = 4.0;                              // qkxtm/QKXTM_util.cpp:1652-1654
   for (int i = 1; i < argc; i++) {
@@ -58,6 +61,8 @@ int main(int argc, char **argv) {
     else if (a == "--amin") { need(1); amin = atof(argv[++i]); }
     else if (a == "--amax") { need(1); amax = atof(argv[++i]); }
     else if (a == "--tolArpack") { need(1); eig_tol = atof(argv[++i]); }
+    else if (a == "--Q_sq") { need(1); q_sq = atoi(argv[++i]); }               // qkxtm/QKXTM_util.cpp (momenta with p^2 <= Q_sq)
+    else if (a == "--src") { need(4); for (int d = 0; d < 4; d++) src_pos[d] = atoi(argv[++i]); }
     else if (a == "--help") { usage(); return 0; }
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
   }
@@ -111,6 +116,8 @@ int main(int argc, char **argv) {
   info.isEven = ((int)inv_param.matpc_type & 1) == 0;
   info.nsmearGauss = nsmearGauss; info.alphaGauss = alphaGauss;
   info.kappa = inv_param.kappa; info.mu = mu; info.inv_tol = tol; info.Precision = QUDA_DOUBLE_PRECISION;
+  info.Nsources = 1; info.Q_sq = q_sq; info.CorrSpace = MOMENTUM_SPACE; info.CorrFileFormat = ASCII_FORM;
+  for (int d = 0; d < 4; d++) info.sourcePosition[0][d] = src_pos[d];
 
   // synthetic configuration: random SU(3), QDP even-odd order, anti-periodic T folded in
   std::vector<double> gbuf((size_t)4 * V * 18);
@@ -166,7 +173,7 @@ int main(int argc, char **argv) {
     result.insert(result.end(), K_defl.H_elem(), K_defl.H_elem() + (size_t)V * 24);
     inv_param.iter = deflation->MatVecs();
     delete deflation;
-  } else if (test == "mgbench") {
+  } else if (test == "mgbench" || test == "twop") {
     // lexicographic copy of the links for the plaquette print (gauge_Plaq in the drivers): unit test uses the
     // same synthetic field reordered even-odd -> lexicographic
     std::vector<double> lex((size_t)4 * V * 18);
@@ -179,9 +186,17 @@ int main(int argc, char **argv) {
         memcpy(glex[mu_] + i * 18, gauge[mu_] + eo * 18, 18 * sizeof(double));
       }
     }
-    result.resize((size_t)12 * V * 24);
-    if (nsmearGauss > 0) testGaussSmearing((void **)glex);                       // lib/qudaQKXTM_utils.cpp:116-141
-    MG_bench((void **)glex, (void **)gauge, &gauge_param, &inv_param, info, result.data());
+    if (test == "mgbench") {
+      result.resize((size_t)12 * V * 24);
+      if (nsmearGauss > 0) testGaussSmearing((void **)glex);                       // lib/qudaQKXTM_utils.cpp:116-141
+      MG_bench((void **)glex, (void **)gauge, &gauge_param, &inv_param, info, result.data());
+    } else {
+      // qkxtm/CalcMG_2pt3pt_EvenOdd.cpp main(): the two-point function of one source position
+      std::string base = out.empty() ? std::string("twop") : out;
+      std::vector<char> f2(base.begin(), base.end()); f2.push_back(0);
+      char f3[] = "unused";
+      calcMG_threepTwop_EvenOdd((void **)glex, (void **)gauge, &gauge_param, &inv_param, info, f2.data(), f3, PROTON);
+    }
   } else { usage(); return 2; }
 
   printf("RESULT test=%s iter=%d true_res=%.6e secs=%.6f gflops=%.3f kappa=%.17g mu=%.17g\n", test.c_str(), inv_param.iter,

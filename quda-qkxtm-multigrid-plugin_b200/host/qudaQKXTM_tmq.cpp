@@ -32,6 +32,8 @@ struct Globals {
   double op_kappa = 0, op_mu = 0;
   int nsmearGauss = 0;                // GK_nsmearGauss, GK_alphaGauss (lib/qudaQKXTM_kernels.cu:60-64)
   double alphaGauss = 0;
+  std::vector<int> moms;              // GK_moms [GK_Nmoms][3] (lib/qudaQKXTM_kernels.cu:75-76, createMomenta :98-116)
+  std::vector<int> sourcePosition;    // GK_sourcePosition [Nsources][4]
   int op_matpc = -1;
 } G;
 
@@ -246,6 +248,8 @@ void MatQuda(void *h_out, void *h_in, QudaInvertParam *param) {
 namespace quda {
 
 tmq_ctx *qkxtm_context() { return G.ctx; }
+int qkxtm_Nmoms() { return (int)G.moms.size() / 3; }
+const int *qkxtm_moms() { return G.moms.data(); }
 void qkxtm_set_error_handler(qkxtm_error_handler h) { G.on_error = h; }
 
 void init_qudaQKXTM(qudaQKXTMinfo *info) {
@@ -253,6 +257,16 @@ void init_qudaQKXTM(qudaQKXTMinfo *info) {
   if (!info) errorQuda("null info");
   ensure_context(info->lL);
   G.nsmearGauss = info->nsmearGauss; G.alphaGauss = info->alphaGauss;      // GK_nsmearGauss, GK_alphaGauss (:125-127)
+  // createMomenta(info->Q_sq) (lib/qudaQKXTM_kernels.cu:98-116,128): all integer momenta with p^2 <= Q_sq, shell by shell
+  G.moms.clear();
+  for (int iQ = 0; iQ <= info->Q_sq; iQ++)
+    for (int nx = iQ; nx >= -iQ; nx--)
+      for (int ny = iQ; ny >= -iQ; ny--)
+        for (int nz = iQ; nz >= -iQ; nz--)
+          if (nx * nx + ny * ny + nz * nz == iQ) { G.moms.push_back(nx); G.moms.push_back(ny); G.moms.push_back(nz); }
+  if ((int)G.moms.size() / 3 > MAX_NMOMENTA) errorQuda("Error exceeded max number of momenta");
+  if (info->Nsources < 0 || info->Nsources > MAX_NSOURCES) errorQuda("bad number of sources %d", info->Nsources);
+  G.sourcePosition.assign(&info->sourcePosition[0][0], &info->sourcePosition[0][0] + (size_t)info->Nsources * 4);   // :129-132
   G.qkxtm_initialized = true;
   printfQuda("qudaQKXTM has been initialized\n");
 }
@@ -463,6 +477,16 @@ template <typename Float> double QKXTM_Vector<Float>::norm2Host() {
   return res;
 }
 template <typename Float> void QKXTM_Vector<Float>::apply_gamma5() { TMQ_OK(tmq_qkxtm_gamma5(G.ctx, this->d_elem, (int)sizeof(Float))); }
+template <typename Float> void QKXTM_Vector<Float>::conjugate() { TMQ_OK(tmq_qkxtm_conjugate(G.ctx, this->d_elem, (int)sizeof(Float), 12)); }
+template <typename Float> void QKXTM_Vector<Float>::copyPropagator(QKXTM_Propagator<Float> &prop, int nu, int c2) {
+  const long long V = this->total_length;
+  TMQ_OK(tmq_qkxtm_column_copy(G.ctx, prop.D_elem(), V, 0, this->d_elem, V, 0, V, (int)sizeof(Float), nu, c2, 0));
+}
+template <typename Float> void QKXTM_Vector<Float>::copyPropagator3D(QKXTM_Propagator3D<Float> &prop, int timeslice, int nu, int c2) {
+  const long long V = this->total_length, V3 = V / G.localL[3];
+  if (timeslice < 0 || timeslice >= G.localL[3]) errorQuda("time slice %d outside the local lattice", timeslice);
+  TMQ_OK(tmq_qkxtm_column_copy(G.ctx, prop.D_elem(), V3, 0, this->d_elem, V, (long long)timeslice * V3, V3, (int)sizeof(Float), nu, c2, 0));
+}
 
 // ---- QKXTM_Propagator ------------------------------------------------------------------------------------------------------------
 template <typename Float> QKXTM_Propagator<Float>::QKXTM_Propagator(ALLOCATION_FLAG a, CLASS_ENUM c) : QKXTM_Field<Float>(a, c) {}
@@ -475,6 +499,107 @@ template <typename Float> void QKXTM_Propagator<Float>::absorbVectorToHost(QKXTM
     for (int c1 = 0; c1 < 3; c1++)
       TMQ_OK(tmq_d2h(G.ctx, this->h_elem + (((size_t)mu * 4 + nu) * 9 + c1 * 3 + c2) * V * 2, vec.D_elem() + ((size_t)mu * 3 + c1) * V * 2,
                      V * 2 * sizeof(Float)));
+}
+
+template <typename Float> void QKXTM_Propagator<Float>::rotateToPhysicalBase_device(int sign) {
+  if ((sign != +1) && (sign != -1)) errorQuda("The sign can be only +-1");
+  TMQ_OK(tmq_qkxtm_rotate_physical(G.ctx, this->d_elem, (int)sizeof(Float), sign));
+}
+template <typename Float> void QKXTM_Propagator<Float>::rotateToPhysicalBase_host(int sign) {
+  if ((sign != +1) && (sign != -1)) errorQuda("The sign can be only +-1");
+  // P <- 1/2 (1 + i s g5) P (1 + i s g5) with g5 the UKQCD spin swap, per site and colour pair
+  const size_t V = (size_t)this->total_length;
+  const Float s = (Float)sign;
+  for (size_t x = 0; x < V; x++)
+    for (int cc = 0; cc < 9; cc++) {
+      Float P[16][2], R[16][2];
+      for (int k = 0; k < 16; k++) { const Float *p = this->h_elem + (((size_t)k * 9 + cc) * V + x) * 2; P[k][0] = p[0]; P[k][1] = p[1]; }
+      for (int a = 0; a < 4; a++)
+        for (int g = 0; g < 4; g++) {
+          const int k = a * 4 + g, ka = (a ^ 2) * 4 + g, kg = a * 4 + (g ^ 2), kag = (a ^ 2) * 4 + (g ^ 2);
+          R[k][0] = (Float)0.5 * (P[k][0] - s * P[ka][1] - s * P[kg][1] - P[kag][0]);
+          R[k][1] = (Float)0.5 * (P[k][1] + s * P[ka][0] + s * P[kg][0] - P[kag][1]);
+        }
+      for (int k = 0; k < 16; k++) { Float *p = this->h_elem + (((size_t)k * 9 + cc) * V + x) * 2; p[0] = R[k][0]; p[1] = R[k][1]; }
+    }
+}
+template <typename Float> void QKXTM_Propagator<Float>::conjugate() { TMQ_OK(tmq_qkxtm_conjugate(G.ctx, this->d_elem, (int)sizeof(Float), 144)); }
+template <typename Float> void QKXTM_Propagator<Float>::apply_gamma5() { TMQ_OK(tmq_qkxtm_gamma5_prop(G.ctx, this->d_elem, (int)sizeof(Float))); }
+
+// ---- QKXTM_Propagator3D -------------------------------------------------------------------------------------------------------
+template <typename Float> QKXTM_Propagator3D<Float>::QKXTM_Propagator3D(ALLOCATION_FLAG a, CLASS_ENUM c) : QKXTM_Field<Float>(a, c) {
+  if (c != PROPAGATOR3D) errorQuda("QKXTM_Propagator3D needs the class PROPAGATOR3D");
+}
+template <typename Float> void QKXTM_Propagator3D<Float>::absorbTimeSlice(QKXTM_Propagator<Float> &prop, int timeslice) {
+  const long long V3 = this->total_length, V = V3 * G.localL[3];
+  if (timeslice < 0 || timeslice >= G.localL[3]) errorQuda("time slice %d outside the local lattice", timeslice);
+  // the 144 components are 12 columns of 12: a propagator is a vector-like array of columns for this purpose
+  for (int nu = 0; nu < 4; nu++)
+    for (int c2 = 0; c2 < 3; c2++)
+      for (int mu = 0; mu < 4; mu++)
+        for (int c1 = 0; c1 < 3; c1++) {
+          const size_t k = ((size_t)(mu * 4 + nu) * 9 + c1 * 3 + c2);
+          TMQ_OK(tmq_d2d(G.ctx, this->d_elem + k * V3 * 2, prop.D_elem() + (k * V + (size_t)timeslice * V3) * 2, (size_t)V3 * 2 * sizeof(Float)));
+        }
+}
+template <typename Float> void QKXTM_Propagator3D<Float>::absorbVectorTimeSlice(QKXTM_Vector<Float> &vec, int timeslice, int nu, int c2) {
+  const long long V3 = this->total_length, V = V3 * G.localL[3];
+  if (timeslice < 0 || timeslice >= G.localL[3]) errorQuda("time slice %d outside the local lattice", timeslice);
+  TMQ_OK(tmq_qkxtm_column_copy(G.ctx, this->d_elem, V3, 0, vec.D_elem(), V, (long long)timeslice * V3, V3, (int)sizeof(Float), nu, c2, 1));
+}
+
+// ---- QKXTM_Contraction (mesons) -----------------------------------------------------------------------------------------------
+template <typename Float>
+void QKXTM_Contraction<Float>::contractMesons(QKXTM_Propagator<Float> &prop1, QKXTM_Propagator<Float> &prop2, void *corrMesons, int isource,
+                                              CORR_SPACE CorrSpace) {
+  if (!corrMesons) errorQuda("null correlator buffer");
+  if (isource < 0 || (size_t)isource * 4 >= G.sourcePosition.size()) errorQuda("source %d was not given to init_qudaQKXTM", isource);
+  printfQuda("contractMesons: Will perform in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
+  Float *out = (Float *)corrMesons;
+  const long long V = G.localVolume;
+  const int Lt = G.localL[3], nm = qkxtm_Nmoms();
+  if (CorrSpace == POSITION_SPACE) {
+    std::vector<double> pos((size_t)V * 40);
+    TMQ_OK(tmq_qkxtm_contract_mesons(G.ctx, prop1.D_elem(), prop2.D_elem(), (int)sizeof(Float), NULL, 0, NULL, NULL, pos.data()));
+    for (long long x = 0; x < V; x++)
+      for (int ch = 0; ch < 20; ch++)
+        for (int ri = 0; ri < 2; ri++) out[((size_t)2 * x + ri) * 20 + ch] = (Float)pos[((size_t)x * 20 + ch) * 2 + ri];
+  } else if (CorrSpace == MOMENTUM_SPACE) {
+    if (nm <= 0) errorQuda("no momenta: init_qudaQKXTM was given Q_sq < 0");
+    const int gT = Lt * G.grid[3];
+    std::vector<double> mom((size_t)gT * nm * 40);
+    TMQ_OK(tmq_qkxtm_contract_mesons(G.ctx, prop1.D_elem(), prop2.D_elem(), (int)sizeof(Float), G.moms.data(), nm, &G.sourcePosition[(size_t)isource * 4],
+                                     mom.data(), NULL));
+    for (int it = 0; it < Lt; it++)
+      for (int im = 0; im < nm; im++)
+        for (int ch = 0; ch < 20; ch++)
+          for (int ri = 0; ri < 2; ri++)
+            out[(((size_t)it * nm + im) * 2 + ri) * 20 + ch] = (Float)mom[((((size_t)(it + G.coord[3] * Lt)) * nm + im) * 20 + ch) * 2 + ri];
+  } else errorQuda("contractMesons: Supports only POSITION_SPACE and MOMENTUM_SPACE!");
+}
+
+template <typename Float>
+void QKXTM_Contraction<Float>::writeTwopMesons_ASCII(void *corrMesons, char *filename_out, int isource, CORR_SPACE CorrSpace) {
+  if (CorrSpace != MOMENTUM_SPACE) errorQuda("writeTwopMesons_ASCII: Supports writing only in momentum-space!");
+  if (G.grid[3] != 1) errorQuda("writeTwopMesons_ASCII: gather the time ranks' buffers first (single rank in t here)");
+  printfQuda("writeTwopMesons_ASCII: Will write in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
+  const Float *c = (const Float *)corrMesons;
+  const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
+  const int *mv = qkxtm_moms();
+  bool root = true;
+  for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
+  if (!root) return;
+  FILE *ptr_out = fopen(filename_out, "w");
+  if (ptr_out == NULL) errorQuda("Error opening file for writing");
+  for (int ip = 0; ip < 10; ip++)
+    for (int it = 0; it < T; it++)
+      for (int imom = 0; imom < nm; imom++) {
+        const int it_shift = (it + G.sourcePosition[(size_t)isource * 4 + 3]) % T;
+        const size_t b = ((size_t)it_shift * nm + imom) * 2;
+        fprintf(ptr_out, "%d \t %d \t %+d %+d %+d \t %+e %+e \t %+e %+e\n", ip, it, mv[3 * imom], mv[3 * imom + 1], mv[3 * imom + 2],
+                (double)c[(b + 0) * 20 + ip], (double)c[(b + 1) * 20 + ip], (double)c[(b + 0) * 20 + 10 + ip], (double)c[(b + 1) * 20 + 10 + ip]);
+      }
+  fclose(ptr_out);
 }
 
 // ---- QKXTM_Deflation ----------------------------------------------------------------------------------------------------
@@ -608,6 +733,10 @@ template class QKXTM_Vector<double>;
 template class QKXTM_Vector<float>;
 template class QKXTM_Propagator<double>;
 template class QKXTM_Propagator<float>;
+template class QKXTM_Propagator3D<double>;
+template class QKXTM_Propagator3D<float>;
+template class QKXTM_Contraction<double>;
+template class QKXTM_Contraction<float>;
 
 }  // namespace quda
 
@@ -668,6 +797,105 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
   if (K_gaugeSmeared) delete K_gaugeSmeared;
   delete x;
   delete b;
+  printfQuda("...Done (%f sec)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
+}
+
+void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, qudaQKXTMinfo info,
+                               char *filename_twop, char *filename_threep, WHICHPARTICLE NUCLEON) {
+  (void)gauge; (void)filename_threep; (void)NUCLEON;
+  if (!param || !gauge_param || !filename_twop) errorQuda("null argument");
+  check_solver(param);
+  if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
+  if (param->gamma_basis != QUDA_UKQCD_GAMMA_BASIS) errorQuda("This function works only with ukqcd gamma basis");       // interface.cpp:270-273
+  if (info.CorrFileFormat != ASCII_FORM) errorQuda("only the ASCII two-point format is built (no HDF5 here)");
+  if (info.CorrSpace != MOMENTUM_SPACE) errorQuda("the ASCII two-point writer supports only momentum space");           // Contraction.cpp:1565
+  if (G.grid[3] != 1) errorQuda("the two-point driver gathers no time ranks: run it unsharded in t");
+  for (int i = 0; i < info.Nsources; i++) if (info.run3pt_src[i]) errorQuda("three-point functions are not built");
+  if (G.nsmearGauss != 0 && !gaugeSmeared) errorQuda("Gaussian smearing needs the smeared links (gaugeSmeared)");
+  const bool flag_eo = info.isEven;
+  const long long V = G.localVolume;
+  const int nm = qkxtm_Nmoms();
+  const auto T0 = std::chrono::steady_clock::now();
+  double *input_vector = (double *)malloc((size_t)V * 24 * sizeof(double));
+  if (!input_vector) errorQuda("Error allocating memory for the host source");
+  QKXTM_Gauge<double> *K_gaugeSmeared = NULL;
+  if (gaugeSmeared) {
+    K_gaugeSmeared = new QKXTM_Gauge<double>(BOTH, GAUGE);                       // interface.cpp:344-348
+    K_gaugeSmeared->packGauge(gaugeSmeared);
+    K_gaugeSmeared->loadGauge();
+    K_gaugeSmeared->calculatePlaq();
+  }
+  QKXTM_Vector<double> *K_vector = new QKXTM_Vector<double>(BOTH, VECTOR);
+  QKXTM_Vector<double> *K_guess = new QKXTM_Vector<double>(BOTH, VECTOR);
+  QKXTM_Vector<float> *K_temp = new QKXTM_Vector<float>(BOTH, VECTOR);
+  QKXTM_Propagator<float> *K_prop_up = new QKXTM_Propagator<float>(BOTH, PROPAGATOR);
+  QKXTM_Propagator<float> *K_prop_down = new QKXTM_Propagator<float>(BOTH, PROPAGATOR);
+  QKXTM_Contraction<float> *K_contract = new QKXTM_Contraction<float>();
+  float *corrMesons = (float *)calloc((size_t)G.localL[3] * nm * 2 * 10 * 2, sizeof(float));
+  if (!corrMesons) errorQuda("Cannot allocate memory for the meson two-point function");
+  printfQuda("Memory allocation was successfull\n");
+  ColorSpinorField *b = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  ColorSpinorField *x = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  const double mu_abs = param->mu < 0 ? -param->mu : param->mu;
+
+  for (int isource = 0; isource < info.Nsources; isource++) {
+    const int *sp = info.sourcePosition[isource];
+    printfQuda("\n ### Calculations for source-position %d - %02d.%02d.%02d.%02d begin now ###\n\n", isource, sp[0], sp[1], sp[2], sp[3]);
+    char filename_mesons[1024];
+    snprintf(filename_mesons, sizeof(filename_mesons), "%s.mesons.SS.%02d.%02d.%02d.%02d.dat", filename_twop, sp[0], sp[1], sp[2], sp[3]);   // :602-607
+    if (info.check_files) { FILE *f = fopen(filename_mesons, "r"); if (f) { fclose(f); continue; } }
+    printfQuda("Forward Inversions:\n");
+    for (int isc = 0; isc < 12; isc++) {
+      // point source at the source position if this rank holds it (interface.cpp:648-665), Gaussian-smeared
+      memset(input_vector, 0, (size_t)V * 24 * sizeof(double));
+      int my_src[4];
+      bool mine = true;
+      for (int i = 0; i < 4; i++) { my_src[i] = sp[i] - G.coord[i] * G.localL[i]; mine = mine && my_src[i] >= 0 && my_src[i] < G.localL[i]; }
+      if (mine)
+        input_vector[((((size_t)my_src[3] * G.localL[2] + my_src[2]) * G.localL[1] + my_src[1]) * G.localL[0] + my_src[0]) * 24 + isc * 2] = 1.0;
+      K_vector->packVector(input_vector);
+      K_vector->loadVector();
+      if (K_gaugeSmeared) K_guess->gaussianSmearing(*K_vector, *K_gaugeSmeared);
+      else { K_guess->packVector(input_vector); K_guess->loadVector(); }
+      for (int flavour = 0; flavour < 2; flavour++) {
+        param->mu = flavour == 0 ? mu_abs : -mu_abs;                      // "Ensure mu is +ve" / "-ve" (:667-668, :733-734)
+        K_guess->uploadToCuda(b, flag_eo);
+        printfQuda(" %s - %02d: \n", flavour == 0 ? "up" : "dn", isc);
+        solve_device(*x, *b, param);
+        K_vector->downloadFromCuda(x, flag_eo);
+        if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION)
+          K_vector->scaleVector(2 * param->kappa);
+        K_temp->castDoubleToFloat(*K_vector);
+        (flavour == 0 ? K_prop_up : K_prop_down)->absorbVectorToDevice(*K_temp, isc / 3, isc % 3);
+      }
+    }
+    // smear the forward propagators at the sink (interface.cpp:1190-1215; the reference stages this through the host and
+    // QUDA's performWuppertalnStep, here the same device kernel as at the source)
+    if (K_gaugeSmeared)
+      for (int nu = 0; nu < 4; nu++)
+        for (int c2 = 0; c2 < 3; c2++)
+          for (int flavour = 0; flavour < 2; flavour++) {
+            QKXTM_Propagator<float> *P = flavour == 0 ? K_prop_up : K_prop_down;
+            K_temp->copyPropagator(*P, nu, c2);
+            K_vector->castFloatToDouble(*K_temp);
+            K_guess->gaussianSmearing(*K_vector, *K_gaugeSmeared);
+            K_temp->castDoubleToFloat(*K_guess);
+            P->absorbVectorToDevice(*K_temp, nu, c2);
+          }
+    K_prop_up->rotateToPhysicalBase_device(+1);                            // :1217-1218
+    K_prop_down->rotateToPhysicalBase_device(-1);
+    const auto t1 = std::chrono::steady_clock::now();
+    K_contract->contractMesons(*K_prop_up, *K_prop_down, corrMesons, isource, info.CorrSpace);    // :1222
+    printfQuda("TIME_REPORT - Two-point Contractions: %f sec\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
+    printfQuda("The mesons two-point function ASCII filename is: %s\n", filename_mesons);
+    K_contract->writeTwopMesons_ASCII(corrMesons, filename_mesons, isource, info.CorrSpace);      // :1241-1248
+  }
+  param->mu = mu_abs;
+  free(corrMesons);
+  free(input_vector);
+  delete K_contract; delete K_prop_down; delete K_prop_up; delete K_temp; delete K_guess; delete K_vector;
+  if (K_gaugeSmeared) delete K_gaugeSmeared;
+  delete x; delete b;
   printfQuda("...Done (%f sec)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
 }
 

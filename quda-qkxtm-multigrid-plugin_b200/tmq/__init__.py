@@ -29,7 +29,8 @@ tmq_prepare tmq_reconstruct tmq_cg_mdagm tmq_cg_history tmq_zero tmq_copy tmq_ax
 tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm tmq_axpy_zpbx tmq_gamma5
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
-tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free""".split()
+tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free
+tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_d2d""".split()
 
 
 class TmqError(RuntimeError):
@@ -106,6 +107,12 @@ def load():
     L.tmq_deflate.argtypes = [vp, vp, vp, dp, C.c_int]
     L.tmq_project.argtypes = [vp, vp, vp, C.c_int]
     L.tmq_qkxtm_gauss_smear.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_double]
+    L.tmq_qkxtm_conjugate.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.tmq_qkxtm_gamma5_prop.argtypes = [vp, vp, C.c_int]
+    L.tmq_qkxtm_rotate_physical.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.tmq_qkxtm_column_copy.argtypes = [vp, vp, C.c_longlong, C.c_longlong, vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
+                                        C.c_int, C.c_int]
+    L.tmq_qkxtm_contract_mesons.argtypes = [vp, vp, vp, C.c_int, ip, C.c_int, ip, dp, dp]
     L.tmq_timer_start.argtypes = [vp]; L.tmq_timer_stop.argtypes = [vp, dp]
     L.tmq_clover_load.argtypes = [vp, C.c_double]; L.tmq_clover_free.argtypes = [vp]
     _lib = L
@@ -339,6 +346,27 @@ class Context:
     def qkxtm_cast(self, dst, dprec, src, sprec): _ck(self.L.tmq_qkxtm_cast(self.h, dst, dprec, src, sprec))
     def qkxtm_gamma5(self, dptr, prec): _ck(self.L.tmq_qkxtm_gamma5(self.h, dptr, prec))
     def qkxtm_absorb(self, dprop, dvec, prec, nu, c2): _ck(self.L.tmq_qkxtm_absorb(self.h, dprop, dvec, prec, nu, c2))
+
+    def qkxtm_conjugate(self, dptr, prec, ncomp): _ck(self.L.tmq_qkxtm_conjugate(self.h, dptr, prec, ncomp))
+    def qkxtm_gamma5_prop(self, dprop, prec): _ck(self.L.tmq_qkxtm_gamma5_prop(self.h, dprop, prec))
+    def qkxtm_rotate_physical(self, dprop, prec, sign): _ck(self.L.tmq_qkxtm_rotate_physical(self.h, dprop, prec, sign))
+    def qkxtm_column_copy(self, dprop, prop_sites, prop_site0, dvec, vec_sites, vec_site0, nsites, prec, nu, c2, to_prop):
+        _ck(self.L.tmq_qkxtm_column_copy(self.h, dprop, prop_sites, prop_site0, dvec, vec_sites, vec_site0, nsites, prec, nu, c2, int(to_prop)))
+
+    def qkxtm_contract_mesons(self, dprop1, dprop2, prec, moms=None, src=(0, 0, 0), global_T=None, pos=False):
+        """-> (corr_mom [T_global][nmoms][2][10] complex or None, corr_pos [V local][2][10] complex or None)"""
+        cm = cp = None
+        m = None
+        if moms is not None:
+            m = np.ascontiguousarray(np.asarray(moms, dtype=np.int32).reshape(-1, 3))
+            cm = np.zeros((int(global_T), len(m), 2, 10, 2))
+        if pos:
+            cp = np.zeros((2 * self.Vh, 2, 10, 2))
+        _ck(self.L.tmq_qkxtm_contract_mesons(self.h, dprop1, dprop2, prec, m.ctypes.data_as(C.POINTER(C.c_int)) if m is not None else None,
+                                             len(m) if m is not None else 0, _i4(list(src) + [0]), _dp(cm) if cm is not None else None,
+                                             _dp(cp) if cp is not None else None))
+        c = lambda a: None if a is None else a[..., 0] + 1j * a[..., 1]
+        return c(cm), c(cp)
 
     def qkxtm_gauss_smear(self, dout, din, dgauge, prec, nsmear, alpha):
         _ck(self.L.tmq_qkxtm_gauss_smear(self.h, dout, din, dgauge, prec, nsmear, alpha))

@@ -1,0 +1,55 @@
+"""Generates tests/golden/qkxtm_ref_contract_4x4x4x6.npz from the REFERENCE'S OWN kernel bodies compiled for the CPU by
+oracle/Makefile (oracle/_ref/libqkxtm_ref.so, needs /root/reference): the meson two-point contraction
+(lib/code_pieces/contractMesons_core.h, contractMesons_core_PosSpace.h, with the reference's channel tables
+lib/qudaQKXTM_kernels.cu:77-78) and the site-local propagator kernels (rotateToPhysicalBase_core.h,
+apply_gamma5_propagator_core.h, conjugate_propagator_core.h, conjugate_vector_core.h).  Inputs come from a seeded numpy
+generator (contract_inputs below, also used by the tests); the fixture stores the reference's outputs only.
+Run:  python tests/golden/make_golden_contract.py"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+X = (4, 4, 4, 6)
+Q_SQ = 3                      # 27 momenta
+SRC = (1, 2, 3)               # source position (x0, y0, z0)
+SAMPLE = np.array([0, 1, 5, 63, 64, 100, 191, 200, 255, 300, 383])     # sites kept of the site-local outputs
+FIXTURE = os.path.join(HERE, "qkxtm_ref_contract_4x4x4x6.npz")
+
+
+def contract_inputs():
+    """prop1, prop2 [4 mu][4 nu][3 c1][3 c2][V][2] (the contraction is a plain function of the numbers: random ones exercise
+    every index of the tables)"""
+    rng = np.random.Generator(np.random.PCG64(20171008))
+    V = int(np.prod(X))
+    return rng.standard_normal((4, 4, 3, 3, V, 2)), rng.standard_normal((4, 4, 3, 3, V, 2))
+
+
+def momenta():
+    from oracle.oracle import create_momenta
+    return create_momenta(Q_SQ)
+
+
+if __name__ == "__main__":
+    from oracle.ref import Ref
+    p1, p2 = contract_inputs()
+    f1, f2 = p1.astype(np.float32), p2.astype(np.float32)
+    r = Ref(X)
+    moms = momenta()
+    vec = np.ascontiguousarray(p1[:, 0, :, 0])                 # [4][3][V][2] as a vector
+    out = {
+        "mom_float": r.contract_mesons_mom(f1, f2, moms, SRC),                  # what the reference launches (float only)
+        "mom_double": r.contract_mesons_mom(p1, p2, moms, SRC),                 # contractMesons_kernel_double, same body
+        "pos_float": r.contract_mesons_pos(f1, f2),
+        "rotate_plus": r.rotate_physical(p1, +1)[..., SAMPLE, :],
+        "rotate_minus": r.rotate_physical(p1, -1)[..., SAMPLE, :],
+        "rotate_plus_f32": r.rotate_physical(f1, +1)[..., SAMPLE, :],
+        "gamma5_prop": r.gamma5_propagator(p1)[..., SAMPLE, :],
+        "conj_prop": r.conjugate_propagator(p1)[..., SAMPLE, :],
+        "conj_vec": r.conjugate_vector(vec.reshape(12, -1, 2))[..., SAMPLE, :],
+    }
+    np.savez_compressed(FIXTURE, **out)
+    print("written", FIXTURE, os.path.getsize(FIXTURE), "bytes")

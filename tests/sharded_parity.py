@@ -132,6 +132,42 @@ def main():
             fails.append(("clover-cg", info_c, it_ref_c))
         o.set_clover(None)
         ctx.clover_free()
+    # container layer on the sharded lattice (QKXTM device layouts, x lexicographic): Gaussian smearing (z faces exchanged before
+    # every step; nothing to exchange on a t split) and the meson contraction (z ranks summed and t ranks gathered by one
+    # all-reduce) against the oracle's restatements on the GLOBAL lattice
+    from oracle.oracle import gauss_smear, contract_mesons_mom, create_momenta
+    rng = np.random.default_rng(41)
+    Vg = int(np.prod(G)); Vl = int(np.prod(X))
+    gshape = (G[3], G[2], G[1], G[0])
+    sl = tuple(slice(coord[d] * X[d], (coord[d] + 1) * X[d]) for d in (3, 2, 1, 0))
+    loc_lex = lambda f: np.ascontiguousarray(f.reshape(f.shape[:-1] + gshape)[(Ellipsis,) + sl]).reshape(f.shape[:-1] + (Vl,))
+    c2r = lambda f: np.ascontiguousarray(np.stack([f.real, f.imag], axis=-1))
+    r2c = lambda f: f[..., 0] + 1j * f[..., 1]
+    def put(arr):
+        ptr = ctx.dev_malloc(arr.nbytes); ctx.h2d(ptr, np.ascontiguousarray(arr)); return ptr
+    vec_g = rng.standard_normal((12, Vg)) + 1j * rng.standard_normal((12, Vg))
+    Ulex = lu.random_su3_lex(G, seed=5)                                      # [4][x_lex][3][3]
+    gq_g = np.ascontiguousarray(np.transpose(Ulex, (0, 2, 3, 1))).reshape(36, Vg)
+    nsm, alpha = 5, 4.0
+    want = loc_lex(gauss_smear(vec_g, gq_g.reshape(4, 3, 3, Vg), G, alpha, nsm))
+    d_in, d_g = put(c2r(loc_lex(vec_g))), put(c2r(loc_lex(gq_g)))
+    d_out = put(np.zeros((12, Vl, 2)))
+    ctx.qkxtm_gauss_smear(d_out, d_in, d_g, 8, nsm, alpha)
+    got = np.empty((12, Vl, 2)); ctx.d2h(got, d_out)
+    e = lu.rel_l2(r2c(got), want)
+    if not e < 1e-13:
+        fails.append(("gauss-smear", e))
+    p1_g = rng.standard_normal((144, Vg)) + 1j * rng.standard_normal((144, Vg))
+    p2_g = rng.standard_normal((144, Vg)) + 1j * rng.standard_normal((144, Vg))
+    moms, srcp = create_momenta(2), (1, G[1] - 1, G[2] - 2)
+    want = contract_mesons_mom(p1_g.reshape(4, 4, 3, 3, Vg), p2_g.reshape(4, 4, 3, 3, Vg), G, moms, srcp)
+    d_p1, d_p2 = put(c2r(loc_lex(p1_g))), put(c2r(loc_lex(p2_g)))
+    mom, _ = ctx.qkxtm_contract_mesons(d_p1, d_p2, 8, moms, srcp, global_T=G[3])
+    e = np.abs(mom - want).max() / np.abs(want).max()
+    if not e < 1e-12:
+        fails.append(("contract-mesons", e))
+    for ptr in (d_in, d_g, d_out, d_p1, d_p2):
+        ctx.dev_free(ptr)
     n2 = ctx.norm2(b)
     if abs(n2 - np.sum(even_g * even_g)) > 1e-12 * n2:
         fails.append(("norm2-allreduce", n2))

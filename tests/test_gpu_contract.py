@@ -1,0 +1,212 @@
+"""GPU parity tests of the step after the solves: propagator container kernels and the meson two-point contraction
+(csrc/tmq_contract.cu) against the REFERENCE'S OWN kernel bodies -- the golden fixture made from contractMesons_core.h (with the
+reference's channel tables), rotateToPhysicalBase_core.h, apply_gamma5_propagator_core.h, conjugate_*_core.h compiled for the
+CPU (tests/golden/make_golden_contract.py) -- and, on other shapes, against the oracle's numpy restatement (pinned to the same
+kernels by tests/test_ref_contract.py).  Tolerances: fp64 propagators 1e-12 of the largest entry (the sums run in a different
+order), fp32 propagators 1e-5 (the reference accumulates in float, the device kernel multiplies in float and sums in double)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import lattice_util as lu
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden_contract as G  # noqa: E402
+from test_gpu_smear import Dev, _c, tmq  # noqa: E402,F401
+
+from oracle import oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRV = os.path.join(ROOT, "quda-qkxtm-multigrid-plugin_b200", "lib", "qkxtm_invert_test")
+
+
+def _relmax(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_meson_contraction_matches_reference_fixture(tmq):
+    gold = np.load(G.FIXTURE)
+    p1, p2 = G.contract_inputs()
+    d = Dev(tmq, G.X)
+    moms = G.momenta()
+    # fp64 propagators: the double instantiation of the reference's kernel body
+    d1, d2 = d.put(p1), d.put(p2)
+    mom, pos = d.c.qkxtm_contract_mesons(d1, d2, 8, moms, G.SRC, global_T=G.X[3], pos=True)
+    assert _relmax(mom, _c(gold["mom_double"])) < 1e-13
+    # fp32 propagators: what the reference launches
+    f1, f2 = d.put(p1.astype(np.float32)), d.put(p2.astype(np.float32))
+    momf, posf = d.c.qkxtm_contract_mesons(f1, f2, 4, moms, G.SRC, global_T=G.X[3], pos=True)
+    assert _relmax(momf, _c(gold["mom_float"]).astype(np.complex128)) < 1e-5
+    want_pos = _c(gold["pos_float"]).astype(np.complex128).reshape(-1, 2, 10)      # [T][V3] = x_lex
+    assert _relmax(posf, want_pos) < 1e-5
+    assert _relmax(pos, want_pos) < 1e-5
+    # repeatable to the bit (fixed summation order)
+    mom2, _ = d.c.qkxtm_contract_mesons(d1, d2, 8, moms, G.SRC, global_T=G.X[3])
+    assert np.array_equal(mom, mom2)
+    d.close()
+
+
+@pytest.mark.parametrize("X,q_sq,src", [((6, 4, 10, 4), 4, (5, 0, 7)), ((16, 12, 8, 6), 2, (3, 11, 2)), ((36, 4, 34, 2), 1, (0, 1, 33))])
+def test_meson_contraction_other_shapes_vs_restatement(tmq, X, q_sq, src):
+    """extents that are not multiples of the warp size, rows longer than a warp, more momenta"""
+    rng = np.random.default_rng(17)
+    V = int(np.prod(X))
+    p1 = rng.standard_normal((4, 4, 3, 3, V, 2)); p2 = rng.standard_normal((4, 4, 3, 3, V, 2))
+    moms = O.create_momenta(q_sq)
+    want = O.contract_mesons_mom(_c(p1), _c(p2), X, moms, src)
+    d = Dev(tmq, X)
+    mom, pos = d.c.qkxtm_contract_mesons(d.put(p1), d.put(p2), 8, moms, src, global_T=X[3], pos=True)
+    assert _relmax(mom, want) < 1e-12
+    site = np.stack([O.contract_mesons_site(_c(p1)), O.contract_mesons_site(_c(p2))])       # [2][10][V]
+    assert _relmax(pos, np.transpose(site, (2, 0, 1))) < 1e-13
+    # a momentum list in another order / with repeats maps to the same numbers
+    perm = [moms[i] for i in (3, 0, 3, len(moms) - 1)]
+    mom_p, _ = d.c.qkxtm_contract_mesons(d.bufs[0], d.bufs[1], 8, perm, src, global_T=X[3])
+    assert np.array_equal(mom_p[:, 0], mom[:, 3]) and np.array_equal(mom_p[:, 1], mom[:, 0]) and np.array_equal(mom_p[:, 3], mom[:, -1])
+    d.close()
+
+
+def test_site_local_propagator_kernels_match_reference_fixture(tmq):
+    gold = np.load(G.FIXTURE)
+    p1, _ = G.contract_inputs()
+    d = Dev(tmq, G.X)
+    V = d.V
+    for sign, key in ((+1, "rotate_plus"), (-1, "rotate_minus")):
+        dp = d.put(p1)
+        d.c.qkxtm_rotate_physical(dp, 8, sign)
+        got = d.get(dp, p1.shape)
+        assert np.abs(_c(got)[..., G.SAMPLE] - _c(gold[key])).max() < 1e-15
+        assert np.abs(_c(got) - O.rotate_physical(_c(p1), sign)).max() < 1e-15
+    df = d.put(p1.astype(np.float32))
+    d.c.qkxtm_rotate_physical(df, 4, +1)
+    assert np.abs(_c(d.get(df, p1.shape, np.float32))[..., G.SAMPLE] - _c(gold["rotate_plus_f32"])).max() < 1e-6
+    dp = d.put(p1)
+    d.c.qkxtm_gamma5_prop(dp, 8)
+    got = d.get(dp, p1.shape)
+    assert np.array_equal(got[..., G.SAMPLE, :], gold["gamma5_prop"]) and np.array_equal(got, p1[[2, 3, 0, 1]])
+    d.c.qkxtm_gamma5_prop(dp, 8)
+    d.c.qkxtm_conjugate(dp, 8, 144)
+    got = d.get(dp, p1.shape)
+    assert np.array_equal(got[..., G.SAMPLE, :], gold["conj_prop"])
+    vec = np.ascontiguousarray(p1[:, 0, :, 0]).reshape(12, V, 2)
+    dv = d.put(vec)
+    d.c.qkxtm_conjugate(dv, 8, 12)
+    assert np.array_equal(d.get(dv, vec.shape)[..., G.SAMPLE, :], gold["conj_vec"])
+    with pytest.raises(tmq.TmqError):
+        d.c.qkxtm_rotate_physical(dp, 8, 2)                     # "The sign can be only +-1" (lib/qudaQKXTM_Propagator.cpp:110)
+    d.close()
+
+
+def test_column_copies_between_propagator_and_vector(tmq):
+    """absorbVectorToDevice / copyPropagator (whole volume) and copyPropagator3D / absorbVectorTimeSlice (one time slice),
+    lib/qudaQKXTM_Vector.cpp:463-512, lib/qudaQKXTM_Propagator.cpp:90-106,533-550: bit-exact strided copies"""
+    X = (4, 4, 2, 6)
+    rng = np.random.default_rng(5)
+    V = int(np.prod(X)); V3 = V // X[3]
+    prop = rng.standard_normal((4, 4, 3, 3, V, 2)); vec = rng.standard_normal((4, 3, V, 2))
+    d = Dev(tmq, X)
+    dp, dv = d.put(prop), d.put(vec)
+    nu, c2 = 2, 1
+    d.c.qkxtm_column_copy(dp, V, 0, dv, V, 0, V, 8, nu, c2, True)
+    want = prop.copy(); want[:, nu, :, c2] = vec
+    assert np.array_equal(d.get(dp, prop.shape), want)
+    assert np.array_equal(d.get(dp, prop.shape), _absorb_ref(d, tmq, prop, vec, nu, c2))
+    dv2 = d.put(np.zeros_like(vec))
+    d.c.qkxtm_column_copy(dp, V, 0, dv2, V, 0, V, 8, 3, 0, False)
+    assert np.array_equal(d.get(dv2, vec.shape), want[:, 3, :, 0])
+    # 3-d propagator <- one time slice of a vector, and back into another slice of a vector
+    p3 = np.zeros((4, 4, 3, 3, V3, 2)); dp3 = d.put(p3)
+    ts = 4
+    d.c.qkxtm_column_copy(dp3, V3, 0, dv, V, ts * V3, V3, 8, nu, c2, True)
+    got3 = d.get(dp3, p3.shape)
+    assert np.array_equal(got3[:, nu, :, c2], vec[:, :, ts * V3:(ts + 1) * V3]) and np.count_nonzero(got3) == 12 * V3 * 2
+    d.c.qkxtm_column_copy(dp3, V3, 0, dv2, V, 1 * V3, V3, 8, nu, c2, False)
+    assert np.array_equal(d.get(dv2, vec.shape)[:, :, V3:2 * V3], vec[:, :, ts * V3:(ts + 1) * V3])
+    with pytest.raises(tmq.TmqError):
+        d.c.qkxtm_column_copy(dp3, V3, 0, dv, V, (X[3] - 1) * V3 + 1, V3, 8, nu, c2, True)      # runs off the vector
+    d.close()
+
+
+def _absorb_ref(d, tmq, prop, vec, nu, c2):
+    dp, dv = d.put(prop), d.put(vec)
+    d.c.qkxtm_absorb(dp, dv, 8, nu, c2)
+    return d.get(dp, prop.shape)
+
+
+# ---- the reference-shaped driver: calcMG_threepTwop_EvenOdd, meson two-point part -----------------------------------------------
+XD = (4, 6, 4, 8)
+KAPPA = 1.0 / (2.0 * 4.1)
+MU = 0.1
+
+
+def _oracle_propagator(o, gauge, src_lex, mu, smear=None):
+    """12 columns of M_full(mu)^-1 on point sources at src_lex through the CPU oracle (prepare -> M^dag -> CG -> reconstruct);
+    returns the propagator in the QKXTM layout [mu][nu][c1][c2][x_lex] complex"""
+    V = o.V
+    prop = np.zeros((4, 4, 3, 3, V), dtype=np.complex128)
+    for isc in range(12):
+        b = np.zeros((12, V), dtype=np.complex128); b[isc, src_lex] = 1.0
+        if smear is not None:
+            b = smear(b)
+        b_lex = lu.c2r(np.transpose(b.reshape(4, 3, V), (2, 0, 1)))
+        b_eo = lu.spinor_eo_from_lex(b_lex, XD)
+        src = o.prepare(gauge, b_eo, KAPPA, mu)
+        rhs = o.matpc(gauge, src, KAPPA, mu, 0, dagger=1)
+        x_pc, _, _, _ = o.cg_mdagm(gauge, rhs, KAPPA, mu, tol=1e-13)
+        x = np.zeros_like(b_eo); x[: V // 2] = x_pc
+        o.reconstruct(gauge, x, b_eo, KAPPA, mu)
+        col = lu.r2c(lu.spinor_lex_from_eo(x, XD))                                 # [x_lex][s][c]
+        if smear is not None:
+            col = np.transpose(smear(np.transpose(col, (1, 2, 0)).reshape(12, V)).reshape(4, 3, V), (2, 0, 1))
+        prop[:, isc // 3, :, isc % 3] = np.transpose(col, (1, 2, 0))
+    return prop
+
+
+@pytest.mark.parametrize("nsmear", [0, 2])
+def test_twop_driver_meson_correlators_match_oracle(tmp_path, tmq, nsmear):
+    """qkxtm_invert_test --test twop = calcMG_threepTwop_EvenOdd (lib/qudaQKXTM_interface.cpp:236-1290, meson two-point part):
+    24 solves (up / down), cast to float, [sink smearing,] rotateToPhysicalBase(+-1), contractMesons, ASCII file.  The oracle
+    redoes it on the CPU: its own CG for the 24 columns, then the restatement pinned to the reference's contraction kernel."""
+    from oracle.oracle import Oracle, gauss_smear
+    o = Oracle(XD)
+    gauge = tmq.gen_gauge(XD, seed=137, t_boundary=-1)
+    src = (1, 3, 2, 5)
+    q_sq, alpha = 2, 4.0
+    out = str(tmp_path / "tw")
+    cmd = [DRV, "--dim"] + [str(v) for v in XD] + ["--test", "twop", "--tol", "1e-11", "--recon", "12", "--Q_sq", str(q_sq), "--src"] + \
+          [str(v) for v in src] + ["--nsmearGauss", str(nsmear), "--alphaGauss", str(alpha), "--out", out]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count(" up - ") == 12 and p.stdout.count(" dn - ") == 12
+    fname = "%s.mesons.SS.%02d.%02d.%02d.%02d.dat" % ((out,) + src)
+    rows = np.loadtxt(fname)
+    moms = O.create_momenta(q_sq)
+    T = XD[3]
+    assert rows.shape == (10 * T * len(moms), 9)
+    got = (rows[:, 5] + 1j * rows[:, 6]).reshape(10, T, len(moms)), (rows[:, 7] + 1j * rows[:, 8]).reshape(10, T, len(moms))
+    assert np.array_equal(rows[: len(moms), 2:5], np.array(moms))
+
+    V = int(np.prod(XD))
+    smear = None
+    if nsmear:
+        U = lu.r2c(np.stack([lu.spinor_lex_from_eo(gauge[m], XD) for m in range(4)]))       # [4][x_lex][3][3], as the driver passes it
+        Uq = np.transpose(U, (0, 2, 3, 1))
+        smear = lambda v: gauss_smear(v, Uq, XD, alpha, nsmear)
+    src_lex = ((src[3] * XD[2] + src[2]) * XD[1] + src[1]) * XD[0] + src[0]
+    up = _oracle_propagator(o, gauge, src_lex, +MU, smear).astype(np.complex64).astype(np.complex128)     # K_temp is a float vector
+    dn = _oracle_propagator(o, gauge, src_lex, -MU, smear).astype(np.complex64).astype(np.complex128)
+    want = O.contract_mesons_mom(O.rotate_physical(up, +1), O.rotate_physical(dn, -1), XD, moms, src[:3])   # [T][nmoms][2][10]
+    for iu in range(2):
+        w = np.transpose(want[:, :, iu, :], (2, 0, 1))                               # [ip][t][imom]
+        w = np.roll(w, -src[3], axis=1)                                              # time relative to the source
+        assert _relmax(got[iu], w) < 2e-5, iu
+    # physics: the pseudoscalar correlator at zero momentum is sum |S|^2: real and positive for both flavours, largest at the source
+    for iu in range(2):
+        pion = got[iu][0, :, 0]
+        assert np.all(pion.real > 0) and np.abs(pion.imag).max() < 1e-6 * pion.real.max() and np.argmax(pion.real) == 0

@@ -141,3 +141,29 @@ def test_container_layout_kernels_match_reference_fixture(tmq):
     want = float(gold["plaquette"][0])
     assert abs(c.qkxtm_plaquette(dgauge, 8) - want) < 1e-12 * abs(want)
     d.close()
+
+
+@pytest.mark.parametrize("prec", [8, 4])
+def test_gauss_smear_on_a_z_partitioned_lattice_is_bit_identical(tmq, prec):
+    """a z split (T, then Z) needs the two z faces of the vector before every step and the neighbour's U_z face once
+    (the reference's ghost zone, lib/qudaQKXTM_Vector.cpp:172-382): with the ghost path forced onto a single rank
+    (tmq_force_partition, the reference's --partition) the exchange wraps onto this rank and every bit must agree with the
+    plain periodic sweep, which is pinned to the reference's kernel above"""
+    X, nsmear, alpha = (6, 4, 8, 6), 7, 4.0
+    rng = np.random.default_rng(23)
+    V = int(np.prod(X))
+    vec = rng.standard_normal((12, V, 2))
+    U = lu.random_su3_lex(X, seed=5)
+    Ut = np.transpose(U, (0, 2, 3, 1))
+    gq = np.ascontiguousarray(np.stack([Ut.real, Ut.imag], axis=-1)).reshape(36, V, 2)
+    d0 = Dev(tmq, X)
+    plain = smear(d0, vec, gq, prec, nsmear, alpha)
+    d0.close()
+    for part in ((0, 0, 1, 0), (0, 0, 1, 1)):
+        d1 = Dev(tmq, X)
+        d1.c.force_partition(part)
+        d1.c.set_option(tmq.OPT_SMEAR_BLOCK_T, 2)             # ignored on a z split
+        ghost = smear(d1, vec, gq, prec, nsmear, alpha)
+        assert np.array_equal(ghost, plain), part
+        assert np.array_equal(smear(d1, vec, gq, prec, 0, alpha), vec.astype(ghost.dtype))
+        d1.close()
