@@ -95,44 +95,71 @@ __device__ __forceinline__ void meson_group(const F (&S)[16][2], const MesonSign
     }
 }
 
-// site values csite[(iu*10 + ip) * V + x] = C_ip(x) of propagator iu = blockIdx.y (complex double).  The 16 spin products of one
-// colour pair are formed and summed in the propagators' precision (the reference does the whole sum in float), the nine colour
-// pairs are added up in double.
+// fp32 propagators: T[M][a*4+g] += S[a^M][g^M] conj(S[a^2][g^2]) for the four XOR masks (64 complex accumulators, 4 FFMA each);
+// the channel sums are taken once, after the nine colour pairs, from the summed products
+template <int M>
+__device__ __forceinline__ void meson_products(const float (&S)[16][2], float (&T)[16][2]) {
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const int k1 = (a ^ M) * 4 + (g ^ M), k2 = (a ^ 2) * 4 + (g ^ 2), q = a * 4 + g;
+      T[q][0] += S[k1][0] * S[k2][0]; T[q][0] += S[k1][1] * S[k2][1];
+      T[q][1] += S[k1][1] * S[k2][0]; T[q][1] -= S[k1][0] * S[k2][1];
+    }
+}
+__device__ __forceinline__ void meson_channels(const float (&T)[16][2], const MesonSigns<float> &W, float (&c)[10][2], int i0, int i1, int i2) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    c[i0][0] += W.w[i0][q] * T[q][0]; c[i0][1] += W.w[i0][q] * T[q][1];
+    c[i1][0] += W.w[i1][q] * T[q][0]; c[i1][1] += W.w[i1][q] * T[q][1];
+    if (i2 >= 0) { c[i2][0] += W.w[i2][q] * T[q][0]; c[i2][1] += W.w[i2][q] * T[q][1]; }
+  }
+}
+
+// site values csite[(iu*10 + ip) * V + x] = C_ip(x) of propagator iu = blockIdx.y (complex double).  fp64 propagators: everything
+// in fp64.  fp32 propagators: the per-site sum in fp32 (as the reference, which does the whole lattice sum in float); everything
+// after the site kernel is fp64.
 template <typename F>
-__global__ void __launch_bounds__(CT_BLOCK) meson_site_kernel(CplxT<double> *__restrict__ csite, const CplxT<F> *__restrict__ prop1,
+__global__ void __launch_bounds__(CT_BLOCK, (sizeof(F) == 4 ? 3 : 2)) meson_site_kernel(CplxT<double> *__restrict__ csite, const CplxT<F> *__restrict__ prop1,
                                                              const CplxT<F> *__restrict__ prop2, size_t V, MesonSigns<F> W) {
   const size_t x = (size_t)blockIdx.x * CT_BLOCK + threadIdx.x;
   if (x >= V) return;
   const int iu = blockIdx.y;
   const CplxT<F> *__restrict__ prop = iu ? prop2 : prop1;
-  double c[10][2];
+  F c[10][2];
 #pragma unroll
   for (int ip = 0; ip < 10; ip++) { c[ip][0] = 0; c[ip][1] = 0; }
+  if constexpr (sizeof(F) == 8) {
 #pragma unroll 1
-  for (int cc = 0; cc < 9; cc++) {
-    F S[16][2];
+    for (int cc = 0; cc < 9; cc++) {
+      F S[16][2];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { const CplxT<F> v = prop[((size_t)k * 9 + cc) * V + x]; S[k][0] = v.re; S[k][1] = v.im; }
-    if constexpr (sizeof(F) == 8) {
+      for (int k = 0; k < 16; k++) { const CplxT<F> v = prop[((size_t)k * 9 + cc) * V + x]; S[k][0] = v.re; S[k][1] = v.im; }
       meson_group<0>(S, W, c, 1, 4, 9);
       meson_group<1>(S, W, c, 2, 3, -1);
       meson_group<2>(S, W, c, 0, 5, 8);
       meson_group<3>(S, W, c, 6, 7, -1);
-    } else {
-      F acc[10][2];
-#pragma unroll
-      for (int ip = 0; ip < 10; ip++) { acc[ip][0] = 0; acc[ip][1] = 0; }
-      meson_group<0>(S, W, acc, 1, 4, 9);
-      meson_group<1>(S, W, acc, 2, 3, -1);
-      meson_group<2>(S, W, acc, 0, 5, 8);
-      meson_group<3>(S, W, acc, 6, 7, -1);
-#pragma unroll
-      for (int ip = 0; ip < 10; ip++) { c[ip][0] += (double)acc[ip][0]; c[ip][1] += (double)acc[ip][1]; }
     }
+  } else {
+    float T0[16][2], T1[16][2], T2[16][2], T3[16][2];
+#pragma unroll
+    for (int q = 0; q < 16; q++) { T0[q][0] = T0[q][1] = T1[q][0] = T1[q][1] = T2[q][0] = T2[q][1] = T3[q][0] = T3[q][1] = 0.f; }
+#pragma unroll 1
+    for (int cc = 0; cc < 9; cc++) {
+      float S[16][2];
+#pragma unroll
+      for (int k = 0; k < 16; k++) { const CplxT<F> v = prop[((size_t)k * 9 + cc) * V + x]; S[k][0] = v.re; S[k][1] = v.im; }
+      meson_products<0>(S, T0); meson_products<1>(S, T1); meson_products<2>(S, T2); meson_products<3>(S, T3);
+    }
+    meson_channels(T0, W, c, 1, 4, 9);
+    meson_channels(T1, W, c, 2, 3, -1);
+    meson_channels(T2, W, c, 0, 5, 8);
+    meson_channels(T3, W, c, 6, 7, -1);
   }
 #pragma unroll
   for (int ip = 0; ip < 10; ip++) {
-    CplxT<double> o; o.re = c[ip][0]; o.im = c[ip][1];
+    CplxT<double> o; o.re = (double)c[ip][0]; o.im = (double)c[ip][1];
     csite[((size_t)iu * 10 + ip) * V + x] = o;
   }
 }
