@@ -231,7 +231,7 @@ public:
   void absorbVectorTimeSlice(QKXTM_Vector<Float> &vec, int timeslice, int nu, int c2); // lib/qudaQKXTM_Propagator.cpp:533-550
 };
 
-// the meson two-point part of QKXTM_Contraction (include/qudaQKXTM.h:283-389; lib/qudaQKXTM_Contraction.cpp:1563-1648)
+// the two-point part of QKXTM_Contraction (include/qudaQKXTM.h:283-389; lib/qudaQKXTM_Contraction.cpp:1563-1648)
 template <typename Float> class QKXTM_Contraction {
 public:
   QKXTM_Contraction() {}
@@ -243,6 +243,12 @@ public:
   // "ip it px py pz  re(up) im(up)  re(down) im(down)", time relative to the source, lib/qudaQKXTM_Contraction.cpp:1586-1599;
   // every rank must call it, the rank holding global t = 0 .. writes (all ranks hold the full result)
   void writeTwopMesons_ASCII(void *corrMesons, char *filename_out, int isource, CORR_SPACE CorrSpace);
+  // corrBaryons, MOMENTUM_SPACE only: Float[T_local * Nmoms * 2][2][10][4][4], entry [it*Nmoms*2 + imom*2 + ri][iu][ip][gamma][gammap]
+  // (lib/qudaQKXTM_Contraction.cpp:906-960), summed over the ranks that share this rank's time slices
+  void contractBaryons(QKXTM_Propagator<Float> &prop1, QKXTM_Propagator<Float> &prop2, void *corrBaryons, int isource, CORR_SPACE CorrSpace);
+  // "ip it px py pz gamma gammap  re(iu=0) im(iu=0)  re(iu=1) im(iu=1)", time relative to the source, sign flip where the time wraps
+  // (anti-periodic boundary), lib/qudaQKXTM_Contraction.cpp:877-901
+  void writeTwopBaryons_ASCII(void *corrBaryons, char *filename_out, int isource, CORR_SPACE CorrSpace);
 };
 int qkxtm_Nmoms();                                  // GK_Nmoms / GK_moms after init_qudaQKXTM
 const int *qkxtm_moms();                            // [Nmoms][3]
@@ -326,12 +332,12 @@ void calc_loops_solve(double *h_solution, double *h_source, QudaInvertParam *par
 // M_pc^dag M_pc -> downloadFromCuda/unloadVector/unpackVector; the other parity comes back zero-filled.
 void ApplyMdagM(double *h_out, double *h_in, QudaInvertParam *param, bool isEven);
 
-// calcMG_threepTwop_EvenOdd (include/qudaQKXTM.h:494-499, lib/qudaQKXTM_interface.cpp:236-1290), the MESON TWO-POINT part:
+// calcMG_threepTwop_EvenOdd (include/qudaQKXTM.h:494-499, lib/qudaQKXTM_interface.cpp:236-1290), the TWO-POINT part:
 // for every source position, 12 + 12 point-source solves (up: +mu, down: -mu; Gaussian-smeared source), columns cast to float
-// and absorbed into K_prop_up / K_prop_down, sink smearing, rotateToPhysicalBase_device(+-1), contractMesons, and the ASCII
-// file "<filename_twop>.mesons.SS.xx.yy.zz.tt.dat".  CG on M^dag M replaces the reference's GCR + multigrid solver (the
-// preconditionerUP/DN patch to quda.h, README:84-108).  Three-point functions (info.run3pt_src != 0), baryons and HDF5 output
-// are not built and are refused.
+// and absorbed into K_prop_up / K_prop_down, sink smearing, rotateToPhysicalBase_device(+-1), contractBaryons, contractMesons, and
+// the ASCII files "<filename_twop>.baryons.SS.xx.yy.zz.tt.dat" / "<filename_twop>.mesons.SS.xx.yy.zz.tt.dat".  CG on M^dag M replaces the reference's GCR + multigrid solver (the
+// preconditionerUP/DN patch to quda.h, README:84-108).  Three-point functions (info.run3pt_src != 0) and HDF5 output are not built and
+// are refused.
 void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param,
                                quda::qudaQKXTMinfo info, char *filename_twop, char *filename_threep, quda::WHICHPARTICLE NUCLEON);
 

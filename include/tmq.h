@@ -222,6 +222,13 @@ int tmq_qkxtm_column_copy(tmq_ctx *, void *d_prop, long long prop_sites, long lo
  * (x0,y0,z0); on a sharded lattice every rank gets the complete reduced result.                                              */
 int tmq_qkxtm_contract_mesons(tmq_ctx *, const void *d_prop1, const void *d_prop2, int prec, const int *moms, int nmoms,
                               const int src_pos[3], double *corr_mom, double *corr_pos);
+/* QKXTM_Contraction::contractBaryons, MOMENTUM_SPACE (lib/qudaQKXTM_Contraction.cpp:906-960, kernel body contractBaryons_core.h):
+ * the ten baryon channels (nucl_nucl, nucl_roper, roper_nucl, roper_roper, deltapp_deltamm_11/22/33, deltap_deltaz_11/22/33), each a
+ * 4 x 4 matrix in the open spin indices, for the two propagator assignments iu = 0 (prop1 as the doubly occurring flavour, prop2 as
+ * the other one) and iu = 1 (swapped).  corr_mom (host): [t GLOBAL][imom][iu][ip][gamma][gamma'][re,im]; every rank gets the
+ * complete reduced result.  The reference's launcher accepts float propagators only; double is accepted here.               */
+int tmq_qkxtm_contract_baryons(tmq_ctx *, const void *d_prop1, const void *d_prop2, int prec, const int *moms, int nmoms,
+                               const int src_pos[3], double *corr_mom);
 
 /* ---- raw device memory for the containers (QKXTM_Field::create_device, lib/qudaQKXTM_Field.cpp:172) ----- */
 int tmq_dev_malloc(tmq_ctx *, void **ptr, size_t bytes);

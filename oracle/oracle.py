@@ -329,3 +329,75 @@ def create_momenta(q_sq):
                     if nx * nx + ny * ny + nz * nz == iq:
                         m.append((nx, ny, nz))
     return m
+
+
+# ---- baryon two-point contraction (the other half of the two-point step, lib/qudaQKXTM_interface.cpp:1220) ----------------
+def _eps3():
+    e = np.zeros((3, 3, 3))
+    e[0, 1, 2] = e[1, 2, 0] = e[2, 0, 1] = 1.0
+    e[2, 1, 0] = e[0, 2, 1] = e[1, 0, 2] = -1.0
+    return e
+
+
+def baryon_channels():
+    """The ten channels of lib/code_pieces/contractBaryons_core.h in the reference's order (lib/qudaQKXTM_interface.cpp:294-303:
+    nucl_nucl, nucl_roper, roper_nucl, roper_roper, deltapp_deltamm_11/22/33, deltap_deltaz_11/22/33).  Every channel is
+        C[g][g'] = sign * sum  Gs[a,b] conj(Gr)[a',b']  Xs[g,d] Xr[g',d']  eps eps'  sum_terms coef * P1[a,s1] P2[b,s2] P3[d,s3]
+    with (s1,s2,s3) a permutation of the primed spin slots (a', b', d') carrying the matching primed colours.  The index / value
+    tables of lib/qudaQKXTM_kernels.cu:79-88 are exactly the non-zero entries of Gs x conj(Gr) x Xs x Xr (checked numerically):
+    nucleon J = eps (u^T C g5 d) u, "roper" J = eps (u^T C d) g5 u, Delta J_k = eps (u^T C g_k u) u.
+    A term is (coef, (prop of line 1, 2, 3), slots) with props 'A' = the channel's own propagator (prop1 for iu = 0, prop2 for
+    iu = 1) and 'B' = the other one; slots name which primed index each line ends on."""
+    g = gamma_ukqcd(); g5 = _gamma5_ukqcd(); one = np.eye(4, dtype=complex)
+    Cm = g[3] @ g[1]                                   # charge conjugation C = g4 g2
+    nucl = [(+1.0, "ABA", ("a", "b", "d")), (-1.0, "ABA", ("d", "b", "a"))]            # contractBaryons_core.h:68-69
+    dpp = [(+1.0, "AAA", ("b", "d", "a")), (-1.0, "AAA", ("d", "b", "a")), (+1.0, "AAA", ("d", "a", "b")),
+           (-1.0, "AAA", ("a", "d", "b")), (-1.0, "AAA", ("b", "a", "d")), (+1.0, "AAA", ("a", "b", "d"))]   # :360-366
+    t = 1.0 / 3.0
+    dp = [(-4 * t, "ABA", ("d", "b", "a")), (+2 * t, "ABA", ("b", "d", "a")), (+2 * t, "AAB", ("d", "a", "b")),
+          (-2 * t, "AAB", ("a", "d", "b")), (-2 * t, "ABA", ("a", "d", "b")), (-1 * t, "AAB", ("b", "a", "d")),
+          (+1 * t, "AAB", ("a", "b", "d")), (+4 * t, "ABA", ("a", "b", "d"))]                                 # :445-453
+    ch = [dict(sign=+1.0, Gs=Cm @ g5, Gr=Cm @ g5, Xs=one, Xr=one, terms=nucl),
+          dict(sign=+1.0, Gs=Cm @ g5, Gr=Cm, Xs=one, Xr=g5, terms=nucl),
+          dict(sign=+1.0, Gs=Cm, Gr=Cm @ g5, Xs=g5, Xr=one, terms=nucl),
+          dict(sign=+1.0, Gs=Cm, Gr=Cm, Xs=g5, Xr=g5, terms=nucl)]
+    for k in range(3):
+        ch.append(dict(sign=+1.0, Gs=Cm @ g[k], Gr=Cm @ g[k], Xs=one, Xr=one, terms=dpp))
+    for k in range(3):
+        ch.append(dict(sign=+1.0, Gs=Cm @ g[k], Gr=Cm @ g[k], Xs=one, Xr=one, terms=dp))
+    return ch
+
+
+def contract_baryons_site(prop1, prop2):
+    """-> [2 iu][10 ip][4 gamma][4 gamma'][V] complex; prop [4][4][3][3][V] complex (spin sink, spin source, colour sink,
+    colour source)"""
+    e = _eps3()
+    P = [prop1.reshape(4, 4, 3, 3, -1), prop2.reshape(4, 4, 3, 3, -1)]
+    V = P[0].shape[-1]
+    out = np.zeros((2, 10, 4, 4, V), dtype=np.complex128)
+    # einsum letters: lines carry (spin, colour) = (a,i), (b,j), (d,k) at the sink; primed slots (A,I), (B,J), (D,K) at the source
+    slot = {"a": ("A", "I"), "b": ("B", "J"), "d": ("D", "K")}
+    for ip, c in enumerate(baryon_channels()):
+        for iu in range(2):
+            acc = np.zeros((4, 4, V), dtype=np.complex128)             # [d][D]
+            for coef, props, slots in c["terms"]:
+                ops = []
+                for line, (sp, co) in enumerate((("a", "i"), ("b", "j"), ("d", "k"))):
+                    S, Cc = slot[slots[line]]
+                    ops.append("%s%s%s%sx" % (sp, S, co, Cc))
+                pr = [P[iu] if ch == "A" else P[1 - iu] for ch in props]
+                acc += coef * np.einsum("ab,AB,ijk,IJK,%s,%s,%s->dDx" % tuple(ops), c["Gs"], c["Gr"].conj(), e, e, *pr, optimize=True)
+            out[iu, ip] = c["sign"] * np.einsum("gd,GD,dDx->gGx", c["Xs"], c["Xr"], acc)
+    return out
+
+
+def contract_baryons_mom(prop1, prop2, X, moms, src):
+    """QKXTM_Contraction::contractBaryons, MOMENTUM_SPACE -> [T][nmoms][2][10][4][4] complex (single rank)"""
+    Xd, Yd, Zd, Td = X
+    c = contract_baryons_site(prop1, prop2).reshape(2, 10, 4, 4, Td, Zd, Yd, Xd)
+    x = np.arange(Xd) - src[0]; y = np.arange(Yd) - src[1]; z = np.arange(Zd) - src[2]
+    out = np.empty((Td, len(moms), 2, 10, 4, 4), dtype=np.complex128)
+    for im, (px, py, pz) in enumerate(moms):
+        ph = np.exp(-2j * np.pi * (pz * z[:, None, None] / Zd + py * y[None, :, None] / Yd + px * x[None, None, :] / Xd))
+        out[:, im] = np.einsum("upgGtzyx,zyx->tupgG", c, ph)
+    return out

@@ -38,6 +38,8 @@ def lib():
         L.qref_contract_mesons_mom_float.argtypes = [fp, fp, fp, ip]
         L.qref_contract_mesons_mom_double.argtypes = [dp, dp, dp, ip]
         L.qref_contract_mesons_pos_float.argtypes = [fp, fp, fp]
+        L.qref_contract_baryons_mom_float.argtypes = [fp, fp, fp, ip]
+        L.qref_contract_baryons_mom_double.argtypes = [dp, dp, dp, ip]
         _lib = L
     return _lib
 
@@ -128,6 +130,18 @@ class Ref:
             self.L.qref_contract_mesons_mom_float(_fp(out), _fp(prop1), _fp(prop2), s)
         else:
             self.L.qref_contract_mesons_mom_double(_dp(out), _dp(prop1), _dp(prop2), s)
+        return out
+
+    def contract_baryons_mom(self, prop1, prop2, moms, src):
+        """contractBaryons, MOMENTUM_SPACE: -> [T][nmoms][2][10][4][4][re,im] (float = what the reference launches)"""
+        m = np.ascontiguousarray(np.asarray(moms, dtype=np.int32).reshape(-1, 3))
+        self.L.qref_set_momenta(m.ctypes.data_as(C.POINTER(C.c_int)), len(m))
+        out = np.zeros((self.X[3], len(m), 2, 10, 4, 4, 2), dtype=prop1.dtype)
+        s = (C.c_int * 3)(*[int(v) for v in src])
+        if prop1.dtype == np.float32:
+            self.L.qref_contract_baryons_mom_float(_fp(out), _fp(prop1), _fp(prop2), s)
+        else:
+            self.L.qref_contract_baryons_mom_double(_dp(out), _dp(prop1), _dp(prop2), s)
         return out
 
     def contract_mesons_pos(self, prop1, prop2):

@@ -21,6 +21,8 @@
 //                                 QKXTM_Contraction::contractMesons (the two-point step after the solves,
 //                                 lib/qudaQKXTM_interface.cpp:1217-1223), with the reference's own channel tables
 //                                 (lib/qudaQKXTM_kernels.cu:77-78, extracted by the Makefile into _ref/qkxtm_meson_tables.h)
+//   contractBaryons_core.h ...... QKXTM_Contraction::contractBaryons (lib/qudaQKXTM_interface.cpp:1220), ten channels x 4x4 spin,
+//                                 with the reference's tables (lib/qudaQKXTM_kernels.cu:79-88 -> _ref/qkxtm_baryon_tables.h)
 #include <cstddef>
 #include <cstring>
 #include <cmath>
@@ -314,4 +316,80 @@ extern "C" void qref_contract_mesons_pos_float(float *out, const float *prop1, c
           for (int ri = 0; ri < 2; ri++)
             out[((((size_t)it * SpVol + sv) * 2 + pt) * 10 + mes) * 2 + ri] = blk[ri + 2 * sv + 2 * alloc * mes + 2 * alloc * 10 * pt];
   }
+}
+
+// ---- baryon two-point contraction (lib/qudaQKXTM_kernels.cu:513-524, launcher :1228-1311) -------------------------------------
+#include "qkxtm_baryon_tables.h"       // GK_{NTN,NTR,RTN,RTR,Delta}_{indices,values}, the reference's own initialisers
+#define c_NTN_indices GK_NTN_indices
+#define c_NTN_values GK_NTN_values
+#define c_NTR_indices GK_NTR_indices
+#define c_NTR_values GK_NTR_values
+#define c_RTN_indices GK_RTN_indices
+#define c_RTN_values GK_RTN_values
+#define c_RTR_indices GK_RTR_indices
+#define c_RTR_values GK_RTR_values
+#define c_Delta_indices GK_Delta_indices
+#define c_Delta_values GK_Delta_values
+// the six permutations of (0,1,2) and their signs: the Levi-Civita symbol (lib/qudaQKXTM_kernels.cu:184-197)
+static const int c_eps[6][3] = {{0, 1, 2}, {2, 0, 1}, {1, 2, 0}, {2, 1, 0}, {0, 2, 1}, {1, 0, 2}};
+static const int c_sgn_eps[6] = {+1, +1, +1, -1, -1, -1};
+
+#define __shared__ static
+#define __syncthreads() pthread_barrier_wait(&g_block_barrier)
+static void baryons_mom_float_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, float2 *block, texf_t prop1Tex, texf_t prop2Tex,
+                                   int it, int x0, int y0, int z0, int ip) {
+#define FLOAT2 float2
+#define FLOAT float
+#define FETCH_FLOAT2 fetch_float2
+#include <contractBaryons_core.h>
+#undef PROP
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+// the same body instantiated in double (the reference keeps this instantiation commented out, lib/qudaQKXTM_kernels.cu:540-551):
+// a tight pin for the restatement
+static void baryons_mom_double_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, double2 *block, texd_t prop1Tex, texd_t prop2Tex,
+                                    int it, int x0, int y0, int z0, int ip) {
+#define FLOAT2 double2
+#define FLOAT double
+#define FETCH_FLOAT2 fetch_double2
+#include <contractBaryons_core.h>
+#undef PROP
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+#undef __syncthreads
+#undef __shared__
+
+// contractBaryons_kernel<Float2, Float>, MOMENTUM_SPACE branch (lib/qudaQKXTM_kernels.cu:1276-1311), all local time slices:
+// out[it][imom][iu][ip][gamma][gammap][re,im] (the reference's corr[it*Nmoms*2 + imom*2 + ri][iu][ip][gamma][gammap])
+template <typename Float, typename Float2, typename Tex, typename Body>
+static void baryons_mom(Float *out, const Float *prop1, const Float *prop2, const int src[3], Body body) {
+  const int SpVol = c_threads / c_localL[3];
+  const int grid = (SpVol + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK;
+  std::vector<Float> h((size_t)c_Nmoms * 2 * 4 * 4 * grid * 2);
+  for (int it = 0; it < c_localL[3]; it++)
+    for (int ip = 0; ip < 10; ip++) {
+      run_grid(grid, [&](dim3_ b, dim3_ d, dim3_ t, dim3_ g) { body(b, d, t, g, (Float2 *)h.data(), (Tex)prop1, (Tex)prop2, it, src[0], src[1], src[2], ip); });
+      for (int imom = 0; imom < c_Nmoms; imom++)
+        for (int iu = 0; iu < 2; iu++)
+          for (int ga = 0; ga < 4; ga++)
+            for (int gap = 0; gap < 4; gap++) {
+              Float re = 0, im = 0;
+              for (int i = 0; i < grid; i++) {
+                const size_t k = (size_t)imom * 2 * 4 * 4 * grid * 2 + (size_t)iu * 4 * 4 * grid * 2 + (size_t)ga * 4 * grid * 2 + (size_t)gap * grid * 2 + i * 2;
+                re += h[k]; im += h[k + 1];
+              }
+              Float *o = out + ((((((size_t)it * c_Nmoms + imom) * 2 + iu) * 10 + ip) * 4 + ga) * 4 + gap) * 2;
+              o[0] = re; o[1] = im;
+            }
+    }
+}
+extern "C" void qref_contract_baryons_mom_float(float *out, const float *prop1, const float *prop2, const int src[3]) {
+  baryons_mom<float, float2, texf_t>(out, prop1, prop2, src, baryons_mom_float_body);
+}
+extern "C" void qref_contract_baryons_mom_double(double *out, const double *prop1, const double *prop2, const int src[3]) {
+  baryons_mom<double, double2, texd_t>(out, prop1, prop2, src, baryons_mom_double_body);
 }

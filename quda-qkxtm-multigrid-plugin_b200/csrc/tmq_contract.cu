@@ -27,6 +27,7 @@
 // over GK_spaceComm + MPI_Gather over GK_timeComm, Contraction.cpp:1638, 98-111).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <string.h>
 #include <algorithm>
 #include <complex>
 #include <map>
@@ -164,6 +165,144 @@ __global__ void __launch_bounds__(CT_BLOCK, (sizeof(F) == 4 ? 3 : 2)) meson_site
   }
 }
 
+
+// ---- baryon two-point contraction -------------------------------------------------------------------------------------------------
+// The reference's ten channels (lib/code_pieces/contractBaryons_core.h; nucl_nucl, nucl_roper, roper_nucl, roper_roper,
+// deltapp_deltamm_11/22/33, deltap_deltaz_11/22/33, lib/qudaQKXTM_interface.cpp:294-303) all have the form
+//   C[g][g'] = sum Gs[a,b] conj(Gr)[a',b'] Xs[g,d] Xr[g',d'] eps_{ijk} eps_{i'j'k'} sum_terms coef P1[a,s1]^{i c1} P2[b,s2]^{j c2} P3[d,s3]^{k c3}
+// where (s1,s2,s3) / (c1,c2,c3) is a permutation of the source spins (a',b',d') / colours (i',j',k'): nucleon J = eps (u^T C g5 d) u,
+// "roper" J = eps (u^T C d) g5 u, Delta J_k = eps (u^T C g_k u) u; its index / value tables (lib/qudaQKXTM_kernels.cu:79-88) are the
+// non-zero entries of Gs x conj(Gr) x Xs x Xr (checked numerically, oracle/oracle.py: baryon_channels).  All four matrices are
+// monomial (one entry per row), so they are kept as a permutation and a phase per row, derived from the gamma matrices on the host.
+// The reference evaluates every term as a 16 x 36 x 16-fold sum of triple products per (g, g'); here a term whose third line ends on
+// the open source index is a scalar (16 products) times a spin matrix, and the others are two 4x4 matrix products per colour
+// combination:  M[d][a] = sum_A conj(Gr)_A P3[d][y(A)] Q[row(a)][x(A)],  R[d][D] += sum_a M[d][a] Gs_a W[row'(a)][D].
+struct Mono { int perm[4]; float re[4], im[4]; };          // row r: column perm[r], value (re, im)
+struct BaryonTerm { double coef; int prop[3]; int slot[3]; };   // prop: 0 = the channel's own propagator, 1 = the other; slot 0,1,2 = (a', b', d')
+struct BaryonChannel { Mono gs, grc; int xs_inv[4], xr_inv[4]; float xs_re[4], xs_im[4], xr_re[4], xr_im[4]; int term0, nterm; };
+struct BaryonTables { BaryonChannel ch[10]; BaryonTerm term[16]; };
+__constant__ BaryonTables c_baryon;
+
+constexpr int BY_SITES = 32;      // sites per CTA = lanes of a warp; 4 warps share the 20 (channel, propagator) tasks
+constexpr int BY_THREADS = 128;
+
+template <typename F> struct Cx { F re, im; };
+template <typename F> __device__ __forceinline__ Cx<F> cmul(Cx<F> a, Cx<F> b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+template <typename F> __device__ __forceinline__ void cmac(Cx<F> &acc, Cx<F> a, Cx<F> b) {
+  acc.re += a.re * b.re; acc.re -= a.im * b.im; acc.im += a.re * b.im; acc.im += a.im * b.re;
+}
+
+// site values csite[((iu*10 + ip)*16 + g*4 + g') * nsites + x] for the nsites sites starting at site0 (complex double)
+template <typename F>
+__global__ void __launch_bounds__(BY_THREADS) baryon_site_kernel(CplxT<double> *__restrict__ csite, const CplxT<F> *__restrict__ prop1,
+                                                                const CplxT<F> *__restrict__ prop2, size_t V, size_t site0, size_t nsites) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CplxT<F> *P = (CplxT<F> *)smem_raw;                       // [2 prop][144 comp][BY_SITES]
+  const size_t base = (size_t)blockIdx.x * BY_SITES;
+  for (int idx = threadIdx.x; idx < 2 * 144 * BY_SITES; idx += BY_THREADS) {
+    const int s = idx % BY_SITES, k = (idx / BY_SITES) % 144, pr = idx / (BY_SITES * 144);
+    CplxT<F> v; v.re = 0; v.im = 0;
+    if (base + s < nsites) v = (pr ? prop2 : prop1)[(size_t)k * V + site0 + base + s];
+    P[idx] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = base + lane < nsites;
+  // P element (spin row mu, spin column nu, colour row c1, colour column c2) of propagator pr at this lane's site
+  auto ld = [&](int pr, int mu, int nu, int c1, int c2) -> Cx<F> {
+    const CplxT<F> v = P[((pr * 144) + (mu * 4 + nu) * 9 + c1 * 3 + c2) * BY_SITES + lane];
+    return {v.re, v.im};
+  };
+  for (int task = warp; task < 20; task += 4) {
+    const int ip = task >> 1, iu = task & 1;
+    const BaryonChannel &ch = c_baryon.ch[ip];
+    Cx<F> R[4][4];
+#pragma unroll
+    for (int d = 0; d < 4; d++)
+#pragma unroll
+      for (int D = 0; D < 4; D++) R[d][D] = {0, 0};
+    for (int it = 0; it < ch.nterm; it++) {
+      const BaryonTerm &tm = c_baryon.term[ch.term0 + it];
+      const int p1 = tm.prop[0] ^ iu, p2 = tm.prop[1] ^ iu, p3 = tm.prop[2] ^ iu;
+      const int s1 = tm.slot[0], s2 = tm.slot[1], s3 = tm.slot[2];
+#pragma unroll 1
+      for (int cc = 0; cc < 36; cc++) {
+        const int e1 = cc / 6, e2 = cc - e1 * 6;
+        // the six permutations of (0,1,2): even ones first
+        int ci[3], cs[3];
+        ci[0] = e1 < 3 ? e1 : (e1 - 3); ci[1] = e1 < 3 ? (e1 + 1) % 3 : (e1 - 3 + 2) % 3; ci[2] = 3 - ci[0] - ci[1];
+        cs[0] = e2 < 3 ? e2 : (e2 - 3); cs[1] = e2 < 3 ? (e2 + 1) % 3 : (e2 - 3 + 2) % 3; cs[2] = 3 - cs[0] - cs[1];
+        const F w = (F)(((e1 < 3) == (e2 < 3)) ? tm.coef : -tm.coef);
+        const int k1 = s1 == 0 ? cs[0] : (s1 == 1 ? cs[1] : cs[2]), k2 = s2 == 0 ? cs[0] : (s2 == 1 ? cs[1] : cs[2]),
+                  k3 = s3 == 0 ? cs[0] : (s3 == 1 ? cs[1] : cs[2]);
+        if (s3 == 2) {
+          // third line ends on the open index: scalar * P3
+          Cx<F> sc = {0, 0};
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int A = 0; A < 4; A++) {
+              const int b = ch.gs.perm[a], B = ch.grc.perm[A];
+              const Cx<F> ph = cmul<F>({(F)ch.gs.re[a], (F)ch.gs.im[a]}, {(F)ch.grc.re[A], (F)ch.grc.im[A]});
+              const Cx<F> u = ld(p1, a, s1 == 0 ? A : B, ci[0], k1), v = ld(p2, b, s2 == 0 ? A : B, ci[1], k2);
+              cmac(sc, cmul(ph, u), v);
+            }
+          sc.re *= w; sc.im *= w;
+#pragma unroll
+          for (int d = 0; d < 4; d++)
+#pragma unroll
+            for (int D = 0; D < 4; D++) cmac(R[d][D], sc, ld(p3, d, D, ci[2], k3));
+        } else {
+          // line `wl` (1 or 2) ends on the open index; the other one (`ol`) and line 3 are tied over the source spin A
+          const bool w1 = s1 == 2;                                   // true: line 1 is the open one
+          const int po = w1 ? p2 : p1, pw = w1 ? p1 : p2, so = w1 ? s2 : s1, ko = w1 ? k2 : k1, kw = w1 ? k1 : k2;
+          const int cio = w1 ? ci[1] : ci[0], ciw = w1 ? ci[0] : ci[1];
+          Cx<F> Q[4][4], Wm[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; a++) {
+            const int ro = w1 ? ch.gs.perm[a] : a, rw = w1 ? a : ch.gs.perm[a];
+            const Cx<F> phs = {(F)(w * ch.gs.re[a]), (F)(w * ch.gs.im[a])};
+#pragma unroll
+            for (int A = 0; A < 4; A++) {
+              const int B = ch.grc.perm[A];
+              Q[a][A] = cmul<F>({(F)ch.grc.re[A], (F)ch.grc.im[A]}, ld(po, ro, so == 0 ? A : B, cio, ko));
+              Wm[a][A] = cmul(phs, ld(pw, rw, A, ciw, kw));          // second index of Wm is the open source spin D
+            }
+          }
+#pragma unroll
+          for (int d = 0; d < 4; d++) {
+            Cx<F> P3r[4], Md[4];
+#pragma unroll
+            for (int A = 0; A < 4; A++) P3r[A] = ld(p3, d, s3 == 0 ? A : ch.grc.perm[A], ci[2], k3);
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+              Md[a] = {0, 0};
+#pragma unroll
+              for (int A = 0; A < 4; A++) cmac(Md[a], P3r[A], Q[a][A]);
+            }
+#pragma unroll
+            for (int D = 0; D < 4; D++)
+#pragma unroll
+              for (int a = 0; a < 4; a++) cmac(R[d][D], Md[a], Wm[a][D]);
+          }
+        }
+      }
+    }
+    // out[g][g'] = sum Xs[g][d] Xr[g'][D] R[d][D]: the monomial X matrices only move and rephase the entries
+    if (live) {
+#pragma unroll
+      for (int d = 0; d < 4; d++)
+#pragma unroll
+        for (int D = 0; D < 4; D++) {
+          const Cx<F> ph = cmul<F>({(F)ch.xs_re[d], (F)ch.xs_im[d]}, {(F)ch.xr_re[D], (F)ch.xr_im[D]});
+          const Cx<F> o = cmul(ph, R[d][D]);
+          CplxT<double> v; v.re = (double)o.re; v.im = (double)o.im;
+          csite[((size_t)((iu * 10 + ip) * 16 + ch.xs_inv[d] * 4 + ch.xr_inv[D])) * nsites + base + lane] = v;
+        }
+    }
+  }
+}
+
 // ---- one axis of the separable Fourier sum -----------------------------------------------------------------------------
 // in [ch][parent][outer][L] (L fastest) -> out[ch][child][outer]:  out = sum_k tab[q][k] in[.., k] for every entry q of the parent's
 // child list (child_start / child_out); one warp per input row, lanes stride the row, fixed-order shuffle tree.
@@ -255,6 +394,52 @@ static int meson_signs(MesonSigns<double> *W) {
   return 0;
 }
 
+
+// one entry per row? -> permutation + phases
+static int to_mono(const Mat4 &m, Mono *o, const char *what) {
+  for (int r = 0; r < 4; r++) {
+    int n = 0;
+    for (int cidx = 0; cidx < 4; cidx++)
+      if (std::abs(m.m[r][cidx]) > 1e-12) { o->perm[r] = cidx; o->re[r] = (float)m.m[r][cidx].real(); o->im[r] = (float)m.m[r][cidx].imag(); n++; }
+    if (n != 1) { set_error("baryon tables: %s is not a monomial matrix", what); return 1; }
+  }
+  return 0;
+}
+static Mat4 conj4(const Mat4 &a) { Mat4 r; for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) r.m[i][j] = std::conj(a.m[i][j]); return r; }
+// the channel / term tables, derived from the UKQCD gamma matrices (C = g4 g2)
+static int baryon_tables(BaryonTables *t) {
+  Mat4 g[5];
+  ukqcd_gammas(g);
+  Mat4 one;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) one.m[i][j] = i == j ? 1.0 : 0.0;
+  const Mat4 C = mul(g[3], g[1]), Cg5 = mul(C, g[4]);
+  memset(t, 0, sizeof(*t));
+  // terms: nucleon-type (2), Delta++ (6), Delta+ (8)  (contractBaryons_core.h:68-69, 360-366, 445-453)
+  const BaryonTerm nucl[2] = {{+1., {0, 1, 0}, {0, 1, 2}}, {-1., {0, 1, 0}, {2, 1, 0}}};
+  const BaryonTerm dpp[6] = {{+1., {0, 0, 0}, {1, 2, 0}}, {-1., {0, 0, 0}, {2, 1, 0}}, {+1., {0, 0, 0}, {2, 0, 1}},
+                             {-1., {0, 0, 0}, {0, 2, 1}}, {-1., {0, 0, 0}, {1, 0, 2}}, {+1., {0, 0, 0}, {0, 1, 2}}};
+  const double th = 1. / 3.;
+  const BaryonTerm dp[8] = {{-4 * th, {0, 1, 0}, {2, 1, 0}}, {+2 * th, {0, 1, 0}, {1, 2, 0}}, {+2 * th, {0, 0, 1}, {2, 0, 1}},
+                            {-2 * th, {0, 0, 1}, {0, 2, 1}}, {-2 * th, {0, 1, 0}, {0, 2, 1}}, {-1 * th, {0, 0, 1}, {1, 0, 2}},
+                            {+1 * th, {0, 0, 1}, {0, 1, 2}}, {+4 * th, {0, 1, 0}, {0, 1, 2}}};
+  memcpy(&t->term[0], nucl, sizeof(nucl)); memcpy(&t->term[2], dpp, sizeof(dpp)); memcpy(&t->term[8], dp, sizeof(dp));
+  struct Def { Mat4 gs, gr, xs, xr; int term0, nterm; };
+  std::vector<Def> defs = {{Cg5, Cg5, one, one, 0, 2}, {Cg5, C, one, g[4], 0, 2}, {C, Cg5, g[4], one, 0, 2}, {C, C, g[4], g[4], 0, 2}};
+  for (int k = 0; k < 3; k++) defs.push_back({mul(C, g[k]), mul(C, g[k]), one, one, 2, 6});
+  for (int k = 0; k < 3; k++) defs.push_back({mul(C, g[k]), mul(C, g[k]), one, one, 8, 8});
+  for (int ip = 0; ip < 10; ip++) {
+    BaryonChannel &c = t->ch[ip];
+    Mono xs, xr;
+    if (to_mono(defs[ip].gs, &c.gs, "Gs") || to_mono(conj4(defs[ip].gr), &c.grc, "conj(Gr)") || to_mono(defs[ip].xs, &xs, "Xs") || to_mono(defs[ip].xr, &xr, "Xr")) return 1;
+    for (int gidx = 0; gidx < 4; gidx++) {      // Xs[g][d] != 0 for d = xs.perm[g]: entry d of R goes to row g
+      c.xs_inv[xs.perm[gidx]] = gidx; c.xs_re[xs.perm[gidx]] = xs.re[gidx]; c.xs_im[xs.perm[gidx]] = xs.im[gidx];
+      c.xr_inv[xr.perm[gidx]] = gidx; c.xr_re[xr.perm[gidx]] = xr.re[gidx]; c.xr_im[xr.perm[gidx]] = xr.im[gidx];
+    }
+    c.term0 = defs[ip].term0; c.nterm = defs[ip].nterm;
+  }
+  return 0;
+}
+
 // carve-out of the context's grow-only contraction work space (256-byte aligned pieces)
 struct WsPlan {
   size_t total = 0;
@@ -286,6 +471,100 @@ static void phase_row(std::vector<CplxT<double>> &tab, int q, int L, int off, in
     CplxT<double> e; e.re = cos(ph); e.im = -sin(ph);
     tab.push_back(e);
   }
+}
+
+
+// ---- the separable momentum projection as a reusable plan ------------------------------------------------------------------------
+// Built once per call from the momentum list; project() runs the three axis stages on the site values of nt consecutive local
+// time slices, csite[ch][nt*Z*Y*X], and adds the result into this rank's slices of the caller's GLOBAL-T host array
+// corr[t global][imom][ch][re,im].
+struct MomProjector {
+  tmq_ctx *c = nullptr;
+  int nmoms = 0, npx = 0, npair = 0, X = 0, Y = 0, Z = 0, T = 0;
+  std::vector<CplxT<double>> tab1, tab2, tab3;
+  std::vector<int> start1, out1, start2, out2, start3, out3;
+  // byte offsets into the work space (filled by plan())
+  size_t o_w1 = 0, o_w2 = 0, o_w3 = 0, o_tab1 = 0, o_tab2 = 0, o_tab3 = 0, o_s1 = 0, o_s2 = 0, o_s3 = 0, o_o1 = 0, o_o2 = 0, o_o3 = 0;
+
+  void build(tmq_ctx *ctx, const int *moms, int n, const int src_pos[3]) {
+    c = ctx; nmoms = n;
+    X = c->g.X[0]; Y = c->g.X[1]; Z = c->g.X[2]; T = c->g.X[3];
+    std::vector<int> px_list;
+    std::map<int, int> px_idx;
+    std::vector<std::pair<int, int>> pair_list;      // (ix, py), grouped by ix
+    std::map<std::pair<int, int>, int> pair_idx;
+    for (int m = 0; m < nmoms; m++) if (!px_idx.count(moms[3 * m])) { px_idx[moms[3 * m]] = (int)px_list.size(); px_list.push_back(moms[3 * m]); }
+    for (int ix = 0; ix < (int)px_list.size(); ix++)
+      for (int m = 0; m < nmoms; m++) {
+        if (px_idx[moms[3 * m]] != ix) continue;
+        const std::pair<int, int> key(ix, moms[3 * m + 1]);
+        if (!pair_idx.count(key)) { pair_idx[key] = (int)pair_list.size(); pair_list.push_back(key); }
+      }
+    npx = (int)px_list.size(); npair = (int)pair_list.size();
+    const int gX = X * c->grid[0], gY = Y * c->grid[1], gZ = Z * c->grid[2];
+    // stage 1 (x): one parent, children = all p_x
+    start1 = {0, npx}; out1.assign(npx, 0); start2.assign(npx + 1, 0); start3.assign(npair + 1, 0);
+    for (int ix = 0; ix < npx; ix++) { out1[ix] = ix; phase_row(tab1, px_list[ix], X, c->coord[0] * X, src_pos[0], gX); }
+    // stage 2 (y): parent ix -> its pairs (contiguous by construction)
+    for (int ix = 0; ix < npx; ix++) {
+      start2[ix] = (int)out2.size();
+      for (int j = 0; j < npair; j++) if (pair_list[j].first == ix) { out2.push_back(j); phase_row(tab2, pair_list[j].second, Y, c->coord[1] * Y, src_pos[1], gY); }
+    }
+    start2[npx] = (int)out2.size();
+    // stage 3 (z): parent pair -> the momenta with that (p_x, p_y), output index = the caller's momentum index
+    for (int j = 0; j < npair; j++) {
+      start3[j] = (int)out3.size();
+      for (int m = 0; m < nmoms; m++)
+        if (px_idx[moms[3 * m]] == pair_list[j].first && moms[3 * m + 1] == pair_list[j].second) { out3.push_back(m); phase_row(tab3, moms[3 * m + 2], Z, c->coord[2] * Z, src_pos[2], gZ); }
+    }
+    start3[npair] = (int)out3.size();
+  }
+  // reserve the stage buffers for nch channels x nt time slices and the tables
+  void plan(WsPlan &p, int nch, int nt) {
+    const size_t CB = sizeof(CplxT<double>);
+    o_w1 = p.add((size_t)nch * npx * nt * Z * Y * CB); o_w2 = p.add((size_t)nch * npair * nt * Z * CB); o_w3 = p.add((size_t)nch * nmoms * nt * CB);
+    o_tab1 = p.add(tab1.size() * CB); o_tab2 = p.add(tab2.size() * CB); o_tab3 = p.add(tab3.size() * CB);
+    o_s1 = p.add(start1.size() * sizeof(int)); o_s2 = p.add(start2.size() * sizeof(int)); o_s3 = p.add(start3.size() * sizeof(int));
+    o_o1 = p.add(out1.size() * sizeof(int)); o_o2 = p.add(out2.size() * sizeof(int)); o_o3 = p.add(out3.size() * sizeof(int));
+  }
+  int upload_tables(char *ws, cudaStream_t st) {
+    TMQ_CUDA(upload(ws + o_tab1, tab1, st)); TMQ_CUDA(upload(ws + o_tab2, tab2, st)); TMQ_CUDA(upload(ws + o_tab3, tab3, st));
+    TMQ_CUDA(upload(ws + o_s1, start1, st)); TMQ_CUDA(upload(ws + o_s2, start2, st)); TMQ_CUDA(upload(ws + o_s3, start3, st));
+    TMQ_CUDA(upload(ws + o_o1, out1, st)); TMQ_CUDA(upload(ws + o_o2, out2, st)); TMQ_CUDA(upload(ws + o_o3, out3, st));
+    return 0;
+  }
+  // csite: [nch][nt*Z*Y*X] site values of the local time slices t0 .. t0+nt-1; corr: [gT][nmoms][nch][2] host doubles
+  int project(char *ws, const CplxT<double> *csite, int nch, int t0, int nt, double *corr, cudaStream_t st) {
+    typedef const CplxT<double> *cptr;
+    const size_t outer1 = (size_t)nt * Z * Y, outer2 = (size_t)nt * Z, outer3 = (size_t)nt;
+    DftStage s1 = {csite, (CplxT<double> *)(ws + o_w1), (cptr)(ws + o_tab1), (const int *)(ws + o_s1), (const int *)(ws + o_o1), 1, npx, X, nch, outer1};
+    DftStage s2 = {(cptr)(ws + o_w1), (CplxT<double> *)(ws + o_w2), (cptr)(ws + o_tab2), (const int *)(ws + o_s2), (const int *)(ws + o_o2), npx, npair, Y, nch, outer2};
+    DftStage s3 = {(cptr)(ws + o_w2), (CplxT<double> *)(ws + o_w3), (cptr)(ws + o_tab3), (const int *)(ws + o_s3), (const int *)(ws + o_o3), npair, nmoms, Z, nch, outer3};
+    TMQ_CUDA(run_stage(s1, st)); TMQ_CUDA(run_stage(s2, st)); TMQ_CUDA(run_stage(s3, st));
+    c->launches += 3;
+    std::vector<double> h((size_t)2 * nch * nmoms * nt);
+    TMQ_CUDA(cudaMemcpyAsync(h.data(), ws + o_w3, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TMQ_CUDA(cudaStreamSynchronize(st));
+    const int t_off = c->coord[3] * T;
+    for (int t = 0; t < nt; t++)
+      for (int m = 0; m < nmoms; m++)
+        for (int ch = 0; ch < nch; ch++) {
+          const size_t src = (((size_t)ch * nmoms + m) * nt + t) * 2, dst = ((((size_t)(t0 + t + t_off)) * nmoms + m) * nch + ch) * 2;
+          corr[dst] = h[src]; corr[dst + 1] = h[src + 1];
+        }
+    return 0;
+  }
+};
+// sum over the z ranks and gather over the t ranks in one all-reduce of the zero-padded global-T host buffer
+static int allreduce_host(tmq_ctx *c, char *ws, size_t off, double *corr, size_t n, cudaStream_t st) {
+  if (c->nranks <= 1) return 0;
+  double *g = (double *)(ws + off);
+  TMQ_CUDA(cudaMemcpyAsync(g, corr, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  TMQ_REQUIRE(n > 4 && n < ((size_t)1 << 31), "internal: reduction length out of range");      // > 4 doubles: always the NCCL path of comm_allreduce
+  TMQ_TRY(comm_allreduce(c, g, (int)n, st));
+  TMQ_CUDA(cudaMemcpyAsync(corr, g, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TMQ_CUDA(cudaStreamSynchronize(st));
+  return 0;
 }
 
 }  // namespace tmq
@@ -373,32 +652,13 @@ int tmq_qkxtm_contract_mesons(tmq_ctx *c, const void *d_prop1, const void *d_pro
   TMQ_REQUIRE(X <= 32 * DFT_MAXK && Y <= 32 * DFT_MAXK && Z <= 32 * DFT_MAXK, "spatial extent above %d not supported", 32 * DFT_MAXK);
   cudaStream_t st = c->stream;
 
-  // ---- separable projection plan: distinct p_x, distinct (p_x, p_y), the momenta (host side, tiny) ------------------------------
-  std::vector<int> px_list;
-  std::map<int, int> px_idx;
-  std::vector<std::pair<int, int>> pair_list;      // (ix, py), grouped by ix
-  std::map<std::pair<int, int>, int> pair_idx;
-  if (corr_mom) {
-    for (int m = 0; m < nmoms; m++) if (!px_idx.count(moms[3 * m])) { px_idx[moms[3 * m]] = (int)px_list.size(); px_list.push_back(moms[3 * m]); }
-    for (int ix = 0; ix < (int)px_list.size(); ix++)
-      for (int m = 0; m < nmoms; m++) {
-        if (px_idx[moms[3 * m]] != ix) continue;
-        const std::pair<int, int> key(ix, moms[3 * m + 1]);
-        if (!pair_idx.count(key)) { pair_idx[key] = (int)pair_list.size(); pair_list.push_back(key); }
-      }
-  }
-  const int npx = (int)px_list.size(), npair = (int)pair_list.size();
-  const size_t outer1 = (size_t)T * Z * Y, outer2 = (size_t)T * Z, outer3 = (size_t)T;
-  const int gT = T * c->grid[3], t_off = c->coord[3] * T;
+  MomProjector mp;
+  if (corr_mom) mp.build(c, moms, nmoms, src_pos);
+  const int gT = T * c->grid[3];
   const size_t ntot = corr_mom ? (size_t)gT * nmoms * 40 : 0;
-  const size_t CB = sizeof(CplxT<double>);
   WsPlan plan;
-  const size_t o_csite = plan.add(V * 20 * CB);
-  const size_t o_w1 = plan.add((size_t)20 * npx * outer1 * CB), o_w2 = plan.add((size_t)20 * npair * outer2 * CB);
-  const size_t o_w3 = plan.add((size_t)20 * nmoms * outer3 * CB);
-  const size_t o_tab1 = plan.add((size_t)npx * X * CB), o_tab2 = plan.add((size_t)npair * Y * CB), o_tab3 = plan.add((size_t)nmoms * Z * CB);
-  const size_t o_s1 = plan.add(2 * sizeof(int)), o_s2 = plan.add((npx + 1) * sizeof(int)), o_s3 = plan.add((npair + 1) * sizeof(int));
-  const size_t o_o1 = plan.add(npx * sizeof(int)), o_o2 = plan.add(npair * sizeof(int)), o_o3 = plan.add((size_t)nmoms * sizeof(int));
+  const size_t o_csite = plan.add(V * 20 * sizeof(CplxT<double>));
+  if (corr_mom) mp.plan(plan, 20, T);
   const size_t o_glob = plan.add(ntot * sizeof(double));
   TMQ_TRY(ensure_contract_ws(c, plan.total));
   char *ws = (char *)c->contract_ws;
@@ -420,57 +680,62 @@ int tmq_qkxtm_contract_mesons(tmq_ctx *c, const void *d_prop1, const void *d_pro
   }
   if (!corr_mom) return 0;
 
-  const int gX = X * c->grid[0], gY = Y * c->grid[1], gZ = Z * c->grid[2];
-  // stage 1 (x): one parent, children = all p_x
-  std::vector<CplxT<double>> tab1, tab2, tab3;
-  std::vector<int> start1 = {0, npx}, out1(npx), start2(npx + 1, 0), out2, start3(npair + 1, 0), out3;
-  for (int ix = 0; ix < npx; ix++) { out1[ix] = ix; phase_row(tab1, px_list[ix], X, c->coord[0] * X, src_pos[0], gX); }
-  // stage 2 (y): parent ix -> its pairs (contiguous by construction)
-  for (int ix = 0; ix < npx; ix++) {
-    start2[ix] = (int)out2.size();
-    for (int j = 0; j < npair; j++) if (pair_list[j].first == ix) { out2.push_back(j); phase_row(tab2, pair_list[j].second, Y, c->coord[1] * Y, src_pos[1], gY); }
-  }
-  start2[npx] = (int)out2.size();
-  // stage 3 (z): parent pair -> the momenta with that (p_x, p_y), output index = the caller's momentum index
-  for (int j = 0; j < npair; j++) {
-    start3[j] = (int)out3.size();
-    for (int m = 0; m < nmoms; m++)
-      if (px_idx[moms[3 * m]] == pair_list[j].first && moms[3 * m + 1] == pair_list[j].second) { out3.push_back(m); phase_row(tab3, moms[3 * m + 2], Z, c->coord[2] * Z, src_pos[2], gZ); }
-  }
-  start3[npair] = (int)out3.size();
-
-  TMQ_CUDA(upload(ws + o_tab1, tab1, st)); TMQ_CUDA(upload(ws + o_tab2, tab2, st)); TMQ_CUDA(upload(ws + o_tab3, tab3, st));
-  TMQ_CUDA(upload(ws + o_s1, start1, st)); TMQ_CUDA(upload(ws + o_s2, start2, st)); TMQ_CUDA(upload(ws + o_s3, start3, st));
-  TMQ_CUDA(upload(ws + o_o1, out1, st)); TMQ_CUDA(upload(ws + o_o2, out2, st)); TMQ_CUDA(upload(ws + o_o3, out3, st));
-  const bool sharded = c->nranks > 1;
-  typedef const CplxT<double> *cptr;
-  DftStage s1 = {csite, (CplxT<double> *)(ws + o_w1), (cptr)(ws + o_tab1), (const int *)(ws + o_s1), (const int *)(ws + o_o1), 1, npx, X, 20, outer1};
-  DftStage s2 = {(cptr)(ws + o_w1), (CplxT<double> *)(ws + o_w2), (cptr)(ws + o_tab2), (const int *)(ws + o_s2), (const int *)(ws + o_o2), npx, npair, Y, 20, outer2};
-  DftStage s3 = {(cptr)(ws + o_w2), (CplxT<double> *)(ws + o_w3), (cptr)(ws + o_tab3), (const int *)(ws + o_s3), (const int *)(ws + o_o3), npair, nmoms, Z, 20, outer3};
-  TMQ_CUDA(run_stage(s1, st)); TMQ_CUDA(run_stage(s2, st)); TMQ_CUDA(run_stage(s3, st));
-  c->launches += 3;
-
-  // w3[ch][m][t] -> corr_mom[t_global][m][iu][ip][re,im]
-  std::vector<double> h((size_t)40 * nmoms * T);
-  TMQ_CUDA(cudaMemcpyAsync(h.data(), ws + o_w3, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-  TMQ_CUDA(cudaStreamSynchronize(st));
   for (size_t i = 0; i < ntot; i++) corr_mom[i] = 0.0;
-  for (int t = 0; t < T; t++)
-    for (int m = 0; m < nmoms; m++)
-      for (int ch = 0; ch < 20; ch++) {
-        const size_t src = (((size_t)ch * nmoms + m) * T + t) * 2, dst = ((((size_t)(t + t_off)) * nmoms + m) * 20 + ch) * 2;
-        corr_mom[dst] = h[src]; corr_mom[dst + 1] = h[src + 1];
-      }
-  if (sharded) {
-    // sum over the z ranks and gather over the t ranks in one all-reduce of the zero-padded global-T buffers
-    double *g = (double *)(ws + o_glob);
-    TMQ_CUDA(cudaMemcpyAsync(g, corr_mom, ntot * sizeof(double), cudaMemcpyHostToDevice, st));
-    // chunks of more than 4 doubles always take the NCCL path of comm_allreduce
-    TMQ_REQUIRE(ntot > 4, "internal: reduction too short");
-    TMQ_TRY(comm_allreduce(c, g, (int)ntot, st));
-    TMQ_CUDA(cudaMemcpyAsync(corr_mom, g, ntot * sizeof(double), cudaMemcpyDeviceToHost, st));
-    TMQ_CUDA(cudaStreamSynchronize(st));
+  TMQ_TRY(mp.upload_tables(ws, st));
+  TMQ_TRY(mp.project(ws, csite, 20, 0, T, corr_mom, st));
+  TMQ_TRY(allreduce_host(c, ws, o_glob, corr_mom, ntot, st));
+  return 0;
+}
+
+int tmq_qkxtm_contract_baryons(tmq_ctx *c, const void *d_prop1, const void *d_prop2, int prec, const int *moms, int nmoms,
+                               const int src_pos[3], double *corr_mom) {
+  TMQ_REQUIRE(c && d_prop1 && d_prop2 && corr_mom && moms && src_pos, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(nmoms > 0, "empty momentum list");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  static bool have_tables = false;
+  if (!have_tables) {
+    BaryonTables t;
+    TMQ_TRY(baryon_tables(&t));
+    TMQ_CUDA(cudaMemcpyToSymbol(c_baryon, &t, sizeof(t)));
+    have_tables = true;
   }
+  const int X = c->g.X[0], Y = c->g.X[1], Z = c->g.X[2], T = c->g.X[3];
+  const size_t V = (size_t)2 * c->g.Vh, V3 = (size_t)X * Y * Z;
+  TMQ_REQUIRE(X <= 32 * DFT_MAXK && Y <= 32 * DFT_MAXK && Z <= 32 * DFT_MAXK, "spatial extent above %d not supported", 32 * DFT_MAXK);
+  cudaStream_t st = c->stream;
+  const int NCH = 320;                                    // 2 propagator assignments x 10 channels x 4 x 4 spin components
+  // time slices per pass: the site values of a pass (320 complex doubles per site) are held to about 2 GiB
+  int nt = (int)(((size_t)2 << 30) / (V3 * NCH * sizeof(CplxT<double>)));
+  if (nt < 1) nt = 1;
+  if (nt > T) nt = T;
+  MomProjector mp;
+  mp.build(c, moms, nmoms, src_pos);
+  const int gT = T * c->grid[3];
+  const size_t ntot = (size_t)gT * nmoms * NCH * 2;
+  WsPlan plan;
+  const size_t o_csite = plan.add((size_t)nt * V3 * NCH * sizeof(CplxT<double>));
+  mp.plan(plan, NCH, nt);
+  const size_t o_glob = plan.add(ntot * sizeof(double));
+  TMQ_TRY(ensure_contract_ws(c, plan.total));
+  char *ws = (char *)c->contract_ws;
+  CplxT<double> *csite = (CplxT<double> *)(ws + o_csite);
+  TMQ_TRY(mp.upload_tables(ws, st));
+  for (size_t i = 0; i < ntot; i++) corr_mom[i] = 0.0;
+  const size_t smem = (size_t)2 * 144 * BY_SITES * 2 * prec;
+  if (prec == 8) TMQ_CUDA(cudaFuncSetAttribute(baryon_site_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else TMQ_CUDA(cudaFuncSetAttribute(baryon_site_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int t0 = 0; t0 < T; t0 += nt) {
+    const int n = t0 + nt <= T ? nt : T - t0;
+    const size_t nsites = (size_t)n * V3, site0 = (size_t)t0 * V3;
+    const unsigned int grid = (unsigned int)((nsites + BY_SITES - 1) / BY_SITES);
+    if (prec == 8) baryon_site_kernel<double><<<grid, BY_THREADS, smem, st>>>(csite, (const CplxT<double> *)d_prop1, (const CplxT<double> *)d_prop2, V, site0, nsites);
+    else baryon_site_kernel<float><<<grid, BY_THREADS, smem, st>>>(csite, (const CplxT<float> *)d_prop1, (const CplxT<float> *)d_prop2, V, site0, nsites);
+    TMQ_CUDA(cudaGetLastError());
+    c->launches++;
+    TMQ_TRY(mp.project(ws, csite, NCH, t0, n, corr_mom, st));
+  }
+  TMQ_TRY(allreduce_host(c, ws, o_glob, corr_mom, ntot, st));
   return 0;
 }
 

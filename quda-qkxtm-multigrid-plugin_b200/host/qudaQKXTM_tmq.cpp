@@ -602,6 +602,55 @@ void QKXTM_Contraction<Float>::writeTwopMesons_ASCII(void *corrMesons, char *fil
   fclose(ptr_out);
 }
 
+template <typename Float>
+void QKXTM_Contraction<Float>::contractBaryons(QKXTM_Propagator<Float> &prop1, QKXTM_Propagator<Float> &prop2, void *corrBaryons, int isource,
+                                               CORR_SPACE CorrSpace) {
+  if (!corrBaryons) errorQuda("null correlator buffer");
+  if (isource < 0 || (size_t)isource * 4 >= G.sourcePosition.size()) errorQuda("source %d was not given to init_qudaQKXTM", isource);
+  if (CorrSpace != MOMENTUM_SPACE) errorQuda("contractBaryons: only MOMENTUM_SPACE is built");
+  printfQuda("contractBaryons: Will perform in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
+  Float *out = (Float *)corrBaryons;
+  const int Lt = G.localL[3], nm = qkxtm_Nmoms(), gT = Lt * G.grid[3];
+  if (nm <= 0) errorQuda("no momenta: init_qudaQKXTM was given Q_sq < 0");
+  std::vector<double> mom((size_t)gT * nm * 320 * 2);
+  TMQ_OK(tmq_qkxtm_contract_baryons(G.ctx, prop1.D_elem(), prop2.D_elem(), (int)sizeof(Float), G.moms.data(), nm, &G.sourcePosition[(size_t)isource * 4],
+                                    mom.data()));
+  for (int it = 0; it < Lt; it++)
+    for (int im = 0; im < nm; im++)
+      for (int ch = 0; ch < 320; ch++)
+        for (int ri = 0; ri < 2; ri++)
+          out[(((size_t)it * nm + im) * 2 + ri) * 320 + ch] = (Float)mom[((((size_t)(it + G.coord[3] * Lt)) * nm + im) * 320 + ch) * 2 + ri];
+}
+
+template <typename Float>
+void QKXTM_Contraction<Float>::writeTwopBaryons_ASCII(void *corrBaryons, char *filename_out, int isource, CORR_SPACE CorrSpace) {
+  if (CorrSpace != MOMENTUM_SPACE) errorQuda("writeTwopBaryons_ASCII: Supports writing only in momentum-space!");
+  if (G.grid[3] != 1) errorQuda("writeTwopBaryons_ASCII: gather the time ranks' buffers first (single rank in t here)");
+  printfQuda("writeTwopBaryons_ASCII: Will write in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
+  const Float *c = (const Float *)corrBaryons;
+  const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
+  const int *mv = qkxtm_moms();
+  bool root = true;
+  for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
+  if (!root) return;
+  FILE *ptr_out = fopen(filename_out, "w");
+  if (ptr_out == NULL) errorQuda("Error opening file for writing");
+  const int tsrc = G.sourcePosition[(size_t)isource * 4 + 3];
+  for (int ip = 0; ip < 10; ip++)
+    for (int it = 0; it < T; it++)
+      for (int imom = 0; imom < nm; imom++)
+        for (int gamma = 0; gamma < 4; gamma++)
+          for (int gammap = 0; gammap < 4; gammap++) {
+            const int it_shift = (it + tsrc) % T;
+            const int sign = (it + tsrc) >= T ? -1 : +1;       // the baryon picks up the anti-periodic boundary sign when the time wraps
+            const size_t b = ((size_t)it_shift * nm + imom) * 2, k = (size_t)ip * 16 + gamma * 4 + gammap;
+            fprintf(ptr_out, "%d \t %d \t %+d %+d %+d \t %d %d \t %+e %+e \t %+e %+e\n", ip, it, mv[3 * imom], mv[3 * imom + 1], mv[3 * imom + 2],
+                    gamma, gammap, sign * (double)c[(b + 0) * 320 + k], sign * (double)c[(b + 1) * 320 + k], sign * (double)c[(b + 0) * 320 + 160 + k],
+                    sign * (double)c[(b + 1) * 320 + 160 + k]);
+          }
+  fclose(ptr_out);
+}
+
 // ---- QKXTM_Deflation ----------------------------------------------------------------------------------------------------
 template <typename Float>
 QKXTM_Deflation<Float>::QKXTM_Deflation(QudaInvertParam *param, qudaQKXTM_arpackInfo ai)
@@ -832,7 +881,8 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   QKXTM_Propagator<float> *K_prop_down = new QKXTM_Propagator<float>(BOTH, PROPAGATOR);
   QKXTM_Contraction<float> *K_contract = new QKXTM_Contraction<float>();
   float *corrMesons = (float *)calloc((size_t)G.localL[3] * nm * 2 * 10 * 2, sizeof(float));
-  if (!corrMesons) errorQuda("Cannot allocate memory for the meson two-point function");
+  float *corrBaryons = (float *)calloc((size_t)G.localL[3] * nm * 2 * 10 * 4 * 4 * 2, sizeof(float));
+  if (!corrMesons || !corrBaryons) errorQuda("Cannot allocate memory for the two-point functions");
   printfQuda("Memory allocation was successfull\n");
   ColorSpinorField *b = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
   ColorSpinorField *x = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
@@ -841,9 +891,16 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   for (int isource = 0; isource < info.Nsources; isource++) {
     const int *sp = info.sourcePosition[isource];
     printfQuda("\n ### Calculations for source-position %d - %02d.%02d.%02d.%02d begin now ###\n\n", isource, sp[0], sp[1], sp[2], sp[3]);
-    char filename_mesons[1024];
-    snprintf(filename_mesons, sizeof(filename_mesons), "%s.mesons.SS.%02d.%02d.%02d.%02d.dat", filename_twop, sp[0], sp[1], sp[2], sp[3]);   // :602-607
-    if (info.check_files) { FILE *f = fopen(filename_mesons, "r"); if (f) { fclose(f); continue; } }
+    char filename_mesons[1024], filename_baryons[1024];
+    snprintf(filename_mesons, sizeof(filename_mesons), "%s.mesons.SS.%02d.%02d.%02d.%02d.dat", filename_twop, sp[0], sp[1], sp[2], sp[3]);   // :602-613
+    snprintf(filename_baryons, sizeof(filename_baryons), "%s.baryons.SS.%02d.%02d.%02d.%02d.dat", filename_twop, sp[0], sp[1], sp[2], sp[3]);
+    if (info.check_files) {
+      FILE *f = fopen(filename_mesons, "r"), *fb = fopen(filename_baryons, "r");
+      const bool both = f && fb;
+      if (f) fclose(f);
+      if (fb) fclose(fb);
+      if (both) continue;                                                   // :633-638
+    }
     printfQuda("Forward Inversions:\n");
     for (int isc = 0; isc < 12; isc++) {
       // point source at the source position if this rank holds it (interface.cpp:648-665), Gaussian-smeared
@@ -885,13 +942,17 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
     K_prop_up->rotateToPhysicalBase_device(+1);                            // :1217-1218
     K_prop_down->rotateToPhysicalBase_device(-1);
     const auto t1 = std::chrono::steady_clock::now();
+    K_contract->contractBaryons(*K_prop_up, *K_prop_down, corrBaryons, isource, info.CorrSpace);  // :1220
     K_contract->contractMesons(*K_prop_up, *K_prop_down, corrMesons, isource, info.CorrSpace);    // :1222
     printfQuda("TIME_REPORT - Two-point Contractions: %f sec\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
     printfQuda("The mesons two-point function ASCII filename is: %s\n", filename_mesons);
-    K_contract->writeTwopMesons_ASCII(corrMesons, filename_mesons, isource, info.CorrSpace);      // :1241-1248
+    printfQuda("The baryons two-point function ASCII filename is: %s\n", filename_baryons);
+    K_contract->writeTwopBaryons_ASCII(corrBaryons, filename_baryons, isource, info.CorrSpace);   // :1241-1248
+    K_contract->writeTwopMesons_ASCII(corrMesons, filename_mesons, isource, info.CorrSpace);
   }
   param->mu = mu_abs;
   free(corrMesons);
+  free(corrBaryons);
   free(input_vector);
   delete K_contract; delete K_prop_down; delete K_prop_up; delete K_temp; delete K_guess; delete K_vector;
   if (K_gaugeSmeared) delete K_gaugeSmeared;

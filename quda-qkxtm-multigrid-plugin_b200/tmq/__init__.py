@@ -30,7 +30,7 @@ tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm t
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
 tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free
-tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_d2d""".split()
+tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_d2d""".split()
 
 
 class TmqError(RuntimeError):
@@ -113,6 +113,7 @@ def load():
     L.tmq_qkxtm_column_copy.argtypes = [vp, vp, C.c_longlong, C.c_longlong, vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                         C.c_int, C.c_int]
     L.tmq_qkxtm_contract_mesons.argtypes = [vp, vp, vp, C.c_int, ip, C.c_int, ip, dp, dp]
+    L.tmq_qkxtm_contract_baryons.argtypes = [vp, vp, vp, C.c_int, ip, C.c_int, ip, dp]
     L.tmq_timer_start.argtypes = [vp]; L.tmq_timer_stop.argtypes = [vp, dp]
     L.tmq_clover_load.argtypes = [vp, C.c_double]; L.tmq_clover_free.argtypes = [vp]
     _lib = L
@@ -367,6 +368,14 @@ class Context:
                                              _dp(cp) if cp is not None else None))
         c = lambda a: None if a is None else a[..., 0] + 1j * a[..., 1]
         return c(cm), c(cp)
+
+    def qkxtm_contract_baryons(self, dprop1, dprop2, prec, moms, src, global_T):
+        """-> corr [T_global][nmoms][2 iu][10 ip][4][4] complex"""
+        m = np.ascontiguousarray(np.asarray(moms, dtype=np.int32).reshape(-1, 3))
+        out = np.zeros((int(global_T), len(m), 2, 10, 4, 4, 2))
+        _ck(self.L.tmq_qkxtm_contract_baryons(self.h, dprop1, dprop2, prec, m.ctypes.data_as(C.POINTER(C.c_int)), len(m),
+                                              _i4(list(src) + [0]), _dp(out)))
+        return out[..., 0] + 1j * out[..., 1]
 
     def qkxtm_gauss_smear(self, dout, din, dgauge, prec, nsmear, alpha):
         _ck(self.L.tmq_qkxtm_gauss_smear(self.h, dout, din, dgauge, prec, nsmear, alpha))

@@ -17,6 +17,8 @@ X = (4, 4, 4, 6)
 Q_SQ = 3                      # 27 momenta
 SRC = (1, 2, 3)               # source position (x0, y0, z0)
 SAMPLE = np.array([0, 1, 5, 63, 64, 100, 191, 200, 255, 300, 383])     # sites kept of the site-local outputs
+X_SMALL = (2, 2, 2, 2)        # a second, tiny lattice: the numpy restatement of the baryon contraction is slow
+SRC_SMALL = (1, 0, 1)
 FIXTURE = os.path.join(HERE, "qkxtm_ref_contract_4x4x4x6.npz")
 
 
@@ -31,6 +33,16 @@ def contract_inputs():
 def momenta():
     from oracle.oracle import create_momenta
     return create_momenta(Q_SQ)
+
+
+def baryon_momenta():
+    return momenta()[::6]     # 5 of the 27: the baryon output is 16 times the meson one
+
+
+def small_inputs():
+    rng = np.random.Generator(np.random.PCG64(20171009))
+    V = int(np.prod(X_SMALL))
+    return rng.standard_normal((4, 4, 3, 3, V, 2)), rng.standard_normal((4, 4, 3, 3, V, 2))
 
 
 if __name__ == "__main__":
@@ -50,6 +62,11 @@ if __name__ == "__main__":
         "gamma5_prop": r.gamma5_propagator(p1)[..., SAMPLE, :],
         "conj_prop": r.conjugate_propagator(p1)[..., SAMPLE, :],
         "conj_vec": r.conjugate_vector(vec.reshape(12, -1, 2))[..., SAMPLE, :],
+        # contractBaryons_core.h with the tables of lib/qudaQKXTM_kernels.cu:79-88: [T][nmoms][2][10][4][4][2]
+        "baryon_mom_float": r.contract_baryons_mom(f1, f2, baryon_momenta(), SRC),      # what the reference launches (float only)
+        "baryon_mom_double": r.contract_baryons_mom(p1, p2, baryon_momenta(), SRC),     # the same body instantiated in double
     }
+    s1, s2 = small_inputs()
+    out["baryon_small_double"] = Ref(X_SMALL).contract_baryons_mom(s1, s2, [(0, 0, 0), (1, 0, -1)], SRC_SMALL)
     np.savez_compressed(FIXTURE, **out)
     print("written", FIXTURE, os.path.getsize(FIXTURE), "bytes")

@@ -166,6 +166,15 @@ def main():
     e = np.abs(mom - want).max() / np.abs(want).max()
     if not e < 1e-12:
         fails.append(("contract-mesons", e))
+    from oracle import ref as qref
+    if qref.available():                                                     # the reference's own baryon kernel body on the global lattice
+        bm = [(0, 0, 0), (1, 0, -1)]
+        wantb = qref.Ref(G).contract_baryons_mom(c2r(p1_g.reshape(4, 4, 3, 3, Vg)), c2r(p2_g.reshape(4, 4, 3, 3, Vg)), bm, srcp)
+        wantb = wantb[..., 0] + 1j * wantb[..., 1]
+        gotb = ctx.qkxtm_contract_baryons(d_p1, d_p2, 8, bm, srcp, G[3])
+        e = np.abs(gotb - wantb).max() / np.abs(wantb).max()
+        if not e < 1e-12:
+            fails.append(("contract-baryons", e))
     for ptr in (d_in, d_g, d_out, d_p1, d_p2):
         ctx.dev_free(ptr)
     n2 = ctx.norm2(b)

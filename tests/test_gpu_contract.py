@@ -72,6 +72,48 @@ def test_meson_contraction_other_shapes_vs_restatement(tmq, X, q_sq, src):
     d.close()
 
 
+def test_baryon_contraction_matches_reference_fixture(tmq):
+    """ten baryon channels x 4x4 spin x two propagator assignments against the reference's kernel body (contractBaryons_core.h with
+    the reference's tables) compiled for the CPU: its double instantiation to 1e-12, the float one it launches to 2e-5"""
+    gold = np.load(G.FIXTURE)
+    p1, p2 = G.contract_inputs()
+    d = Dev(tmq, G.X)
+    moms = G.baryon_momenta()
+    got = d.c.qkxtm_contract_baryons(d.put(p1), d.put(p2), 8, moms, G.SRC, G.X[3])
+    want = _c(gold["baryon_mom_double"])
+    assert got.shape == want.shape
+    for ip in range(10):
+        for iu in range(2):
+            assert _relmax(got[:, :, iu, ip], want[:, :, iu, ip]) < 1e-12, (ip, iu)
+    gotf = d.c.qkxtm_contract_baryons(d.put(p1.astype(np.float32)), d.put(p2.astype(np.float32)), 4, moms, G.SRC, G.X[3])
+    wantf = _c(gold["baryon_mom_float"]).astype(np.complex128)
+    for ip in range(10):
+        assert _relmax(gotf[:, :, :, ip], wantf[:, :, :, ip]) < 2e-5, ip
+        assert _relmax(gotf[:, :, :, ip], want[:, :, :, ip]) < 2e-5, ip
+    got2 = d.c.qkxtm_contract_baryons(d.bufs[0], d.bufs[1], 8, moms, G.SRC, G.X[3])
+    assert np.array_equal(got, got2)                                  # fixed summation order
+    d.close()
+
+
+@pytest.mark.parametrize("X,src", [((6, 4, 2, 4), (5, 0, 1)), ((10, 2, 6, 2), (3, 1, 2))])
+def test_baryon_contraction_other_shapes_vs_live_reference_kernel(tmq, X, src):
+    """sites per time slice that are not a multiple of the 32-site CTA tile, against the reference kernel body run live (the prebuilt
+    oracle/_ref library travels to the GPU box)"""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(29)
+    V = int(np.prod(X))
+    p1 = rng.standard_normal((4, 4, 3, 3, V, 2)); p2 = rng.standard_normal((4, 4, 3, 3, V, 2))
+    moms = [(0, 0, 0), (1, -1, 0), (0, 0, 2)]
+    want = _c(ref.Ref(X).contract_baryons_mom(p1, p2, moms, src))
+    d = Dev(tmq, X)
+    got = d.c.qkxtm_contract_baryons(d.put(p1), d.put(p2), 8, moms, src, X[3])
+    for ip in range(10):
+        assert _relmax(got[:, :, :, ip], want[:, :, :, ip]) < 1e-12, ip
+    d.close()
+
+
 def test_site_local_propagator_kernels_match_reference_fixture(tmq):
     gold = np.load(G.FIXTURE)
     p1, _ = G.contract_inputs()
@@ -206,6 +248,23 @@ def test_twop_driver_meson_correlators_match_oracle(tmp_path, tmq, nsmear):
         w = np.transpose(want[:, :, iu, :], (2, 0, 1))                               # [ip][t][imom]
         w = np.roll(w, -src[3], axis=1)                                              # time relative to the source
         assert _relmax(got[iu], w) < 2e-5, iu
+    # the baryon file of the same run: "ip it px py pz gamma gammap re(iu=0) im(iu=0) re(iu=1) im(iu=1)", time relative to the source
+    # with the sign flip of the anti-periodic boundary where it wraps (lib/qudaQKXTM_Contraction.cpp:886-898)
+    from oracle import ref
+    if nsmear == 0 and ref.available():
+        rb = np.loadtxt("%s.baryons.SS.%02d.%02d.%02d.%02d.dat" % ((out,) + src))
+        assert rb.shape == (10 * T * len(moms) * 16, 11)
+        gb = [(rb[:, 7 + 2 * iu] + 1j * rb[:, 8 + 2 * iu]).reshape(10, T, len(moms), 4, 4) for iu in range(2)]
+        # the reference's own kernel body (float, as the reference launches it) on the oracle's rotated float propagators
+        c2r32 = lambda z: np.ascontiguousarray(np.stack([z.real, z.imag], axis=-1).astype(np.float32))
+        bw = _c(ref.Ref(XD).contract_baryons_mom(c2r32(O.rotate_physical(up, +1)), c2r32(O.rotate_physical(dn, -1)), moms[:3], src[:3]))
+        bw = bw.astype(np.complex128)                                               # [T][3 moms][2][10][4][4]
+        for iu in range(2):
+            w = np.transpose(bw[:, :, iu], (2, 0, 1, 3, 4))                       # [ip][t][imom][g][g']
+            w = np.roll(w, -src[3], axis=1)
+            w[:, T - src[3]:] *= -1.0
+            for ip in range(10):
+                assert _relmax(gb[iu][ip][:, :3], w[ip]) < 1e-4, (iu, ip)
     # physics: the pseudoscalar correlator at zero momentum is sum |S|^2: real and positive for both flavours, largest at the source
     for iu in range(2):
         pion = got[iu][0, :, 0]

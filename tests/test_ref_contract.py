@@ -86,3 +86,27 @@ def test_site_local_propagator_kernels_match_reference(gold):
     # the rotation is an involution up to the twist: rotating with +1 then -1 gives back 1/4 (1 + g5 g5) P (1 + ...) = P
     back = O.rotate_physical(O.rotate_physical(P, +1), -1)
     assert np.abs(back - P).max() < 1e-14
+
+
+def test_baryon_contraction_restatement_matches_reference(gold):
+    """the ten baryon channels written as Gs x conj(Gr) x Xs x Xr gamma structures with explicit Wick terms (oracle.baryon_channels)
+    reproduce the reference's table-driven kernel body (its double instantiation) to rounding, on a tiny lattice (the einsum
+    restatement is slow); the big fixture entries are what the GPU kernel is compared with"""
+    s1, s2 = G.small_inputs()
+    want = O.contract_baryons_mom(_c(s1), _c(s2), G.X_SMALL, [(0, 0, 0), (1, 0, -1)], G.SRC_SMALL)
+    got = _c(gold["baryon_small_double"])
+    assert got.shape == want.shape == (2, 2, 2, 10, 4, 4)
+    for ip in range(10):
+        for iu in range(2):
+            assert np.abs(got[:, :, iu, ip] - want[:, :, iu, ip]).max() / np.abs(want[:, :, iu, ip]).max() < 1e-13, (ip, iu)
+    # float (what the reference launches) vs double instantiation of the same body on the larger fixture lattice
+    d, f = _c(gold["baryon_mom_double"]), _c(gold["baryon_mom_float"]).astype(np.complex128)
+    assert np.abs(d - f).max() / np.abs(d).max() < 2e-5
+
+
+def test_baryon_fixture_matches_live_reference_library(gold):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    s1, s2 = G.small_inputs()
+    assert np.array_equal(ref.Ref(G.X_SMALL).contract_baryons_mom(s1, s2, [(0, 0, 0), (1, 0, -1)], G.SRC_SMALL), gold["baryon_small_double"])

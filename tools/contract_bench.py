@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--lattice", type=int, nargs=4, default=[48, 48, 48, 96])
 ap.add_argument("--precs", default="4,8")
 ap.add_argument("--qsq", default="0,3,16")
+ap.add_argument("--baryons", type=int, default=0, help="also time the baryon contraction (Q_sq = 3)")
 a = ap.parse_args()
 X = tuple(a.lattice)
 V = int(np.prod(X))
@@ -47,6 +48,15 @@ for prec in [int(p) for p in a.precs.split(",")]:
                           "Q_sq": q, "nmoms": len(moms), "device_span_ms": ms, "wall_ms": wall, "launches": c.launch_count() - l0,
                           "site_kernel_algorithmic_GB": gb, "GB/s_if_all_time_were_the_site_kernel": gb / (ms * 1e-3),
                           "frac_of_hbm_peak": gb / (ms * 1e-3) / peak}), flush=True)
+    if a.baryons:
+        moms = create_momenta(3)
+        c.qkxtm_contract_baryons(p1, p2, prec, moms, (1, 2, 3), X[3])           # warm-up (work space)
+        l0 = c.launch_count()
+        c.timer_start()
+        c.qkxtm_contract_baryons(p1, p2, prec, moms, (1, 2, 3), X[3])
+        ms = c.timer_stop()
+        print(json.dumps({"what": "baryon contraction (10 channels x 4x4 spin x 2 assignments) + momentum projection", "lattice": X, "prec": prec,
+                          "Q_sq": 3, "nmoms": len(moms), "device_span_ms": ms, "launches": c.launch_count() - l0}), flush=True)
     for p in (p1, p2):
         c.dev_free(p)
 c.close()
