@@ -401,3 +401,88 @@ def contract_baryons_mom(prop1, prop2, X, moms, src):
         ph = np.exp(-2j * np.pi * (pz * z[:, None, None] / Zd + py * y[None, :, None] / Yd + px * x[None, None, :] / Xd))
         out[:, im] = np.einsum("upgGtzyx,zyx->tupgG", c, ph)
     return out
+
+
+# ---- fixed-sink three-point function: projectors, sequential sources, ultra-local insertion ------------------------------------
+PROTON, NEUTRON = 0, 1                        # WHICHPARTICLE (include/qudaQKXTM_utils.h:128)
+G4, G5G123, G5G1, G5G2, G5G3 = range(5)       # WHICHPROJECTOR (include/qudaQKXTM_utils.h:129)
+
+
+def _twist_rotate(M, s):
+    """physical -> twisted basis at maximal twist: 1/2 (1 + i s g5) M (1 + i s g5)"""
+    R = np.eye(4) + 1j * s * _gamma5_ukqcd()
+    return 0.5 * R @ M @ R
+
+
+def projector_tm(pid, particle):
+    """lib/code_pieces/projectors_tm_base.h as a formula: the physical projector 1/4 (1 + g4) [x i g5 g_k, or summed over k]
+    rotated to the twisted basis with s = +1 (proton) / -1 (neutron)"""
+    g = gamma_ukqcd(); g5 = _gamma5_ukqcd()
+    P0 = 0.25 * (np.eye(4) + g[3])
+    Pk = [P0 @ (1j * g5 @ g[k]) for k in range(3)]
+    phys = {G4: P0, G5G123: Pk[0] + Pk[1] + Pk[2], G5G1: Pk[0], G5G2: Pk[1], G5G3: Pk[2]}[pid]
+    return _twist_rotate(phys, +1 if particle == PROTON else -1)
+
+
+def operator_tm(flag, particle, partflag):
+    """lib/code_pieces/gammas_tm_base.h as a formula: the 16 insertions 1, g1..g4, g5, g5g1..g5g4, -i sigma_{12,13,23,41,42,43}
+    rotated to the twisted basis; s = +1 for (proton, part 1) and (neutron, part 2), -1 otherwise"""
+    g = gamma_ukqcd(); g5 = _gamma5_ukqcd()
+    sig = lambda a, b: 0.5 * (g[a] @ g[b] - g[b] @ g[a])
+    ops = [np.eye(4, dtype=complex)] + [g[k] for k in range(4)] + [g5] + [g5 @ g[k] for k in range(4)] + \
+          [-1j * sig(a, b) for a, b in ((0, 1), (0, 2), (1, 2), (3, 0), (3, 1), (3, 2))]
+    s = +1 if (particle == PROTON) == (partflag == 1) else -1
+    return _twist_rotate(ops[flag], s)
+
+
+def seq_source_part1(T1, T2, nu_f, c2_f, pid, particle):
+    """lib/code_pieces/seqSourceFixSinkPart1_core.h: sequential source at the sink time slice for the quark line that occurs twice
+    in the nucleon; T1, T2 3-d propagators [4][4][3][3][V3] complex -> [4 spin][3 colour][V3].  (G = C g5, P the projector)"""
+    g = gamma_ukqcd(); Gm = (g[3] @ g[1]) @ _gamma5_ukqcd()
+    P = projector_tm(pid, particle); e = _eps3(); ef = e[:, :, c2_f]
+    # common factor  -eps_{c1 c2 c3} eps_{c1' c2' c2f} G[m,g] G[j,k] P[b,a] T2[g,j]^{c1 c1'}  times the four T1 placements
+    A = -np.einsum("mg,jk,gjuUx->mkuUx", Gm, Gm, T2, optimize=True)          # [m][k][c1][c1'][x]
+    out = np.zeros((4, 3, T1.shape[-1]), dtype=np.complex128)
+    for b in range(4):
+        for a in range(4):
+            if abs(P[b, a]) < 1e-3:
+                continue
+            # (mu == nu, b == nu_f): T1[a][k]
+            if b == nu_f:
+                out += P[b, a] * np.einsum("uvw,UV,nkuUx,kvVx->nwx", e, ef, A, T1[a], optimize=True)
+                # (a == nu, b == nu_f): T1[m][k], output spin a
+                out[a] += P[b, a] * np.einsum("uvw,UV,mkuUx,mkvVx->wx", e, ef, A, T1, optimize=True)
+            # (mu == nu, k == nu_f): T1[a][b]
+            out += P[b, a] * np.einsum("uvw,UV,nuUx,vVx->nwx", e, ef, A[:, nu_f], T1[a, b], optimize=True)
+            # (a == nu, k == nu_f): T1[m][b], output spin a
+            out[a] += P[b, a] * np.einsum("uvw,UV,muUx,mvVx->wx", e, ef, A[:, nu_f], T1[:, b], optimize=True)
+    return out
+
+
+def seq_source_part2(T, nu_f, c2_f, pid, particle):
+    """lib/code_pieces/seqSourceFixSinkPart2_core.h: sequential source for the quark line that occurs once"""
+    g = gamma_ukqcd(); Gm = (g[3] @ g[1]) @ _gamma5_ukqcd()
+    P = projector_tm(pid, particle); e = _eps3(); ef = e[:, :, c2_f]
+    # S[n][c3] = -eps eps' G[m,n] G[nu_f,k] P[b,a] ( T[m,b]^{c1c1'} T[a,k]^{c2c2'} + T[m,k]^{c1c1'} T[a,b]^{c2c2'} )
+    t1 = np.einsum("uvw,UV,mn,k,ba,mbuUx,akvVx->nwx", e, ef, Gm, Gm[nu_f], P, T, T, optimize=True)
+    t2 = np.einsum("uvw,UV,mn,k,ba,mkuUx,abvVx->nwx", e, ef, Gm, Gm[nu_f], P, T, T, optimize=True)
+    return -(t1 + t2)
+
+
+def fixsink_local_site(fwd, seq, particle, partflag):
+    """lib/code_pieces/fixSinkContractions_local_core.h:38-48: C_iop(x) = sum Gamma_iop[n][r] F[r][m'](b,a') S[n][m'](b,a')
+    -> [16][V] complex; fwd / seq propagators [4][4][3][3][V] complex"""
+    return np.stack([np.einsum("nr,rmbax,nmbax->x", operator_tm(i, particle, partflag), fwd, seq, optimize=True) for i in range(16)])
+
+
+def fixsink_local_mom(fwd, seq, X, moms, src, particle, partflag):
+    """... projected with exp(+2 pi i p.(x - src)/L) (fixSinkContractions_local_core.h:52-56: expon = cos + i sin)
+    -> [T][nmoms][16] complex (single rank)"""
+    Xd, Yd, Zd, Td = X
+    c = fixsink_local_site(fwd.reshape(4, 4, 3, 3, -1), seq.reshape(4, 4, 3, 3, -1), particle, partflag).reshape(16, Td, Zd, Yd, Xd)
+    x = np.arange(Xd) - src[0]; y = np.arange(Yd) - src[1]; z = np.arange(Zd) - src[2]
+    out = np.empty((Td, len(moms), 16), dtype=np.complex128)
+    for im, (px, py, pz) in enumerate(moms):
+        ph = np.exp(+2j * np.pi * (pz * z[:, None, None] / Zd + py * y[None, :, None] / Yd + px * x[None, None, :] / Xd))
+        out[:, im] = np.einsum("otzyx,zyx->to", c, ph)
+    return out

@@ -21,6 +21,9 @@
 //                                 QKXTM_Contraction::contractMesons (the two-point step after the solves,
 //                                 lib/qudaQKXTM_interface.cpp:1217-1223), with the reference's own channel tables
 //                                 (lib/qudaQKXTM_kernels.cu:77-78, extracted by the Makefile into _ref/qkxtm_meson_tables.h)
+//   seqSourceFixSinkPart1_core.h, seqSourceFixSinkPart2_core.h (+ projectors_tm_base.h), fixSinkContractions_local_core.h
+//   (+ gammas_tm_base.h) ........ QKXTM_Contraction::{seqSourceFixSinkPart1, seqSourceFixSinkPart2, contractFixSink (local part)}: the
+//                                 fixed-sink three-point function of calcMG_threepTwop_EvenOdd (lib/qudaQKXTM_interface.cpp:838-1170)
 //   contractBaryons_core.h ...... QKXTM_Contraction::contractBaryons (lib/qudaQKXTM_interface.cpp:1220), ten channels x 4x4 spin,
 //                                 with the reference's tables (lib/qudaQKXTM_kernels.cu:79-88 -> _ref/qkxtm_baryon_tables.h)
 #include <cstddef>
@@ -392,4 +395,108 @@ extern "C" void qref_contract_baryons_mom_float(float *out, const float *prop1, 
 }
 extern "C" void qref_contract_baryons_mom_double(double *out, const double *prop1, const double *prop2, const int src[3]) {
   baryons_mom<double, double2, texd_t>(out, prop1, prop2, src, baryons_mom_double_body);
+}
+
+// ---- fixed-sink three-point function: sequential sources and the ultra-local insertion (lib/qudaQKXTM_kernels.cu:412-424,552-626) -----
+enum WHICHPARTICLE { PROTON, NEUTRON };                      // include/qudaQKXTM_utils.h:128
+enum WHICHPROJECTOR { G4, G5G123, G5G1, G5G2, G5G3 };        // include/qudaQKXTM_utils.h:129
+static inline float norm(const float2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
+static inline double norm(const double2 a) { return sqrt(a.x * a.x + a.y * a.y); }
+template <typename Float2> static inline void get_Projector(Float2 projector[4][4], WHICHPARTICLE PARTICLE, WHICHPROJECTOR PID) {
+#include <projectors_tm_base.h>
+}
+template <typename Float2> static inline void get_Operator(Float2 gamma[4][4], int flag, WHICHPARTICLE TESTPARTICLE, int partFlag) {
+#include <gammas_tm_base.h>
+}
+static void seq1_double_thread(int sid_, double2 *out, int timeslice, texd_t tex1, texd_t tex2, int c_nu, int c_c2, WHICHPROJECTOR PID, WHICHPARTICLE PARTICLE) {
+  THREAD_PREAMBLE
+#define FLOAT2 double2
+#define FLOAT double
+#define FETCH_FLOAT2 fetch_double2
+#include <seqSourceFixSinkPart1_core.h>
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+static void seq2_double_thread(int sid_, double2 *out, int timeslice, texd_t tex, int c_nu, int c_c2, WHICHPROJECTOR PID, WHICHPARTICLE PARTICLE) {
+  THREAD_PREAMBLE
+#define FLOAT2 double2
+#define FLOAT double
+#define FETCH_FLOAT2 fetch_double2
+#include <seqSourceFixSinkPart2_core.h>
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+// run_seqSourceFixSinkPart1 / Part2 (lib/qudaQKXTM_kernels.cu:1428-1460): out is a 4-d vector, only the time slice is written;
+// tex1 / tex2 / tex are PROPAGATOR3D fields [4][4][3][3][V3]
+extern "C" void qref_seq_source_part1_double(double *out, int timeslice, const double *p3d_1, const double *p3d_2, int nu, int c2, int pid, int particle) {
+  const int V3 = c_localL[0] * c_localL[1] * c_localL[2];
+  for (int s = 0; s < V3; s++) seq1_double_thread(s, (double2 *)out, timeslice, (texd_t)p3d_1, (texd_t)p3d_2, nu, c2, (WHICHPROJECTOR)pid, (WHICHPARTICLE)particle);
+}
+extern "C" void qref_seq_source_part2_double(double *out, int timeslice, const double *p3d, int nu, int c2, int pid, int particle) {
+  const int V3 = c_localL[0] * c_localL[1] * c_localL[2];
+  for (int s = 0; s < V3; s++) seq2_double_thread(s, (double2 *)out, timeslice, (texd_t)p3d, nu, c2, (WHICHPROJECTOR)pid, (WHICHPARTICLE)particle);
+}
+
+#define __shared__ static
+#define __syncthreads() pthread_barrier_wait(&g_block_barrier)
+static void fixsink_local_float_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, float2 *block, texf_t fwdTex, texf_t seqTex,
+                                     WHICHPARTICLE TESTPARTICLE, int partflag, int it, int x0, int y0, int z0) {
+#define FLOAT2 float2
+#define FLOAT float
+#define FETCH_FLOAT2 fetch_float2
+#include <fixSinkContractions_local_core.h>
+#undef PROP
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+// the same body in double (the reference launches the float instantiation only): a tight pin
+static void fixsink_local_double_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, double2 *block, texd_t fwdTex, texd_t seqTex,
+                                      WHICHPARTICLE TESTPARTICLE, int partflag, int it, int x0, int y0, int z0) {
+#define FLOAT2 double2
+#define FLOAT double
+#define FETCH_FLOAT2 fetch_double2
+#include <fixSinkContractions_local_core.h>
+#undef PROP
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+#undef __syncthreads
+#undef __shared__
+// the local part of run_fixSinkContractions, MOMENTUM_SPACE: out[it][imom][iop][re,im]
+template <typename Float, typename Float2, typename Tex, typename Body>
+static void fixsink_local(Float *out, const Float *fwd, const Float *seq, int particle, int partflag, const int src[3], Body body) {
+  const int SpVol = c_threads / c_localL[3];
+  const int grid = (SpVol + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK;
+  std::vector<Float> h((size_t)c_Nmoms * 16 * grid * 2);
+  for (int it = 0; it < c_localL[3]; it++) {
+    run_grid(grid, [&](dim3_ b, dim3_ d, dim3_ t, dim3_ g) { body(b, d, t, g, (Float2 *)h.data(), (Tex)fwd, (Tex)seq, (WHICHPARTICLE)particle, partflag, it, src[0], src[1], src[2]); });
+    for (int imom = 0; imom < c_Nmoms; imom++)
+      for (int iop = 0; iop < 16; iop++) {
+        Float re = 0, im = 0;
+        for (int i = 0; i < grid; i++) { re += h[((size_t)imom * 16 * grid + (size_t)iop * grid + i) * 2]; im += h[((size_t)imom * 16 * grid + (size_t)iop * grid + i) * 2 + 1]; }
+        Float *o = out + (((size_t)it * c_Nmoms + imom) * 16 + iop) * 2;
+        o[0] = re; o[1] = im;
+      }
+  }
+}
+extern "C" void qref_fixsink_local_float(float *out, const float *fwd, const float *seq, int particle, int partflag, const int src[3]) {
+  fixsink_local<float, float2, texf_t>(out, fwd, seq, particle, partflag, src, fixsink_local_float_body);
+}
+extern "C" void qref_fixsink_local_double(double *out, const double *fwd, const double *seq, int particle, int partflag, const int src[3]) {
+  fixsink_local<double, double2, texd_t>(out, fwd, seq, particle, partflag, src, fixsink_local_double_body);
+}
+// the tables themselves, so that the restatement can state them as formulas and check the formulas entry by entry
+extern "C" void qref_get_projector(double *out32, int pid, int particle) {
+  double2 p[4][4];
+  get_Projector(p, (WHICHPARTICLE)particle, (WHICHPROJECTOR)pid);
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { out32[(i * 4 + j) * 2] = p[i][j].x; out32[(i * 4 + j) * 2 + 1] = p[i][j].y; }
+}
+extern "C" void qref_get_operator(double *out32, int flag, int particle, int partflag) {
+  double2 g[4][4];
+  get_Operator(g, flag, (WHICHPARTICLE)particle, partflag);
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { out32[(i * 4 + j) * 2] = g[i][j].x; out32[(i * 4 + j) * 2 + 1] = g[i][j].y; }
 }

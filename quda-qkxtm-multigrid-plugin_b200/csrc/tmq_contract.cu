@@ -303,6 +303,130 @@ __global__ void __launch_bounds__(BY_THREADS) baryon_site_kernel(CplxT<double> *
   }
 }
 
+// ---- fixed-sink three-point function: sequential sources and the ultra-local insertion ----------------------------------------------
+// (lib/code_pieces/seqSourceFixSinkPart{1,2}_core.h + projectors_tm_base.h, fixSinkContractions_local_core.h + gammas_tm_base.h;
+//  restated as formulas in oracle/oracle.py: seq_source_part1/2, projector_tm, operator_tm, fixsink_local_site, each checked against
+//  the reference's kernel body to rounding.)  With G = C g5, P the twisted-basis projector, (nu_f, c2_f) the fixed source spin / colour:
+//   part 2:  S[n][w] = - eps_{uvw} eps_{UV c2_f} G[m,n] G[nu_f,k] P[b,a] ( T[m,b]^{uU} T[a,k]^{vV} + T[m,k]^{uU} T[a,b]^{vV} )
+//   part 1:  S[n][w] = - eps eps' G[m,g] G[j,k] P[b,a] T2[g,j]^{uU} ( d_{mn} d_{b nu_f} T1[a,k] + d_{mn} d_{k nu_f} T1[a,b]
+//                                                                    + d_{an} d_{b nu_f} T1[m,k] + d_{an} d_{k nu_f} T1[m,b] )^{vV}
+// One thread per spatial site of ONE time slice, called 12 times per sink: negligible next to the 12 solves that follow.
+struct SeqSrcTables { int gperm[4], ginv[4]; double gre[4], gim[4]; double pre[4][4], pim[4][4]; int nu_f, c2_f; };
+
+template <typename F>
+__global__ void __launch_bounds__(128) seq_source_kernel(CplxT<F> *__restrict__ out, size_t V, size_t V3, int timeslice, const CplxT<F> *__restrict__ T1,
+                                                        const CplxT<F> *__restrict__ T2, SeqSrcTables t, int part) {
+  const size_t sid = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (sid >= V3) return;
+  auto ld = [&](const CplxT<F> *T, int mu, int nu, int c1, int c2) -> Cx<double> {
+    const CplxT<F> v = T[((size_t)(mu * 4 + nu) * 9 + c1 * 3 + c2) * V3 + sid];
+    return {(double)v.re, (double)v.im};
+  };
+  auto G = [&](int row) -> Cx<double> { return {t.gre[row], t.gim[row]}; };          // G[row][gperm[row]]
+  auto Pj = [&](int b, int a) -> Cx<double> { return {t.pre[b][a], t.pim[b][a]}; };
+  Cx<double> S[4][3];
+#pragma unroll
+  for (int n = 0; n < 4; n++)
+#pragma unroll
+    for (int w = 0; w < 3; w++) S[n][w] = {0, 0};
+  const int kf = t.gperm[t.nu_f];               // G[nu_f][kf] != 0
+  const int jf = t.ginv[t.nu_f];                // G[jf][nu_f] != 0
+  for (int e1 = 0; e1 < 6; e1++) {
+    const int u = e1 < 3 ? e1 : e1 - 3, v = e1 < 3 ? (e1 + 1) % 3 : (e1 - 3 + 2) % 3, w = 3 - u - v;
+    for (int e2 = 0; e2 < 2; e2++) {
+      const int U = e2 == 0 ? (t.c2_f + 1) % 3 : (t.c2_f + 2) % 3, Vc = 3 - U - t.c2_f;
+      const double sg = -(((e1 < 3) == (e2 == 0)) ? 1.0 : -1.0);        // - sgn sgn'
+#pragma unroll
+      for (int n = 0; n < 4; n++) {
+        Cx<double> acc = {0, 0};
+        if (part == 2) {
+          const int m = t.ginv[n];                                       // G[m][n]
+          const Cx<double> gg = cmul(G(m), G(t.nu_f));
+          for (int b = 0; b < 4; b++)
+            for (int a = 0; a < 4; a++) {
+              const Cx<double> p = Pj(b, a);
+              if (p.re == 0.0 && p.im == 0.0) continue;
+              Cx<double> tt = cmul(ld(T1, m, b, u, U), ld(T1, a, kf, v, Vc));
+              cmac(tt, ld(T1, m, kf, u, U), ld(T1, a, b, v, Vc));
+              cmac(acc, cmul(gg, p), tt);
+            }
+        } else {
+          const int gn = t.gperm[n];                                     // m = n: G[n][gn]
+          for (int j = 0; j < 4; j++) {
+            const int k = t.gperm[j];
+            // (m = n, b = nu_f): sum_a P[nu_f][a] T2[gn][j] T1[a][k]
+            const Cx<double> c0 = cmul(cmul(G(n), G(j)), ld(T2, gn, j, u, U));
+            for (int a = 0; a < 4; a++) cmac(acc, cmul(c0, Pj(t.nu_f, a)), ld(T1, a, k, v, Vc));
+          }
+          {  // (m = n, k = nu_f -> j = jf): sum_{a,b} P[b][a] T2[gn][jf] T1[a][b]
+            const Cx<double> c0 = cmul(cmul(G(n), G(jf)), ld(T2, gn, jf, u, U));
+            for (int b = 0; b < 4; b++)
+              for (int a = 0; a < 4; a++) cmac(acc, cmul(c0, Pj(b, a)), ld(T1, a, b, v, Vc));
+          }
+          for (int m = 0; m < 4; m++) {
+            const int g = t.gperm[m];
+            // (a = n, b = nu_f): sum_j P[nu_f][n] T2[g][j] T1[m][k(j)]
+            for (int j = 0; j < 4; j++)
+              cmac(acc, cmul(cmul(cmul(G(m), G(j)), Pj(t.nu_f, n)), ld(T2, g, j, u, U)), ld(T1, m, t.gperm[j], v, Vc));
+            // (a = n, k = nu_f -> j = jf): sum_b P[b][n] T2[g][jf] T1[m][b]
+            const Cx<double> c1 = cmul(cmul(G(m), G(jf)), ld(T2, g, jf, u, U));
+            for (int b = 0; b < 4; b++) cmac(acc, cmul(c1, Pj(b, n)), ld(T1, m, b, v, Vc));
+          }
+        }
+        // the colour index w is a run-time value: add into the matching accumulator without indexing the register array
+#pragma unroll
+        for (int ww = 0; ww < 3; ww++)
+          if (ww == w) { S[n][ww].re += sg * acc.re; S[n][ww].im += sg * acc.im; }
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 4; n++)
+#pragma unroll
+    for (int w = 0; w < 3; w++) {
+      CplxT<F> o; o.re = (F)S[n][w].re; o.im = (F)S[n][w].im;
+      out[(size_t)(n * 3 + w) * V + (size_t)timeslice * V3 + sid] = o;
+    }
+}
+
+// ultra-local insertion: C_iop(x) = sum_{n,r} Gamma_iop[n][r] sum_{m,b,a} F[r][m]^{ba}(x) S[n][m]^{ba}(x), 16 operators
+struct OpTables { double re[16][16], im[16][16]; };     // [iop][n*4 + r]
+__constant__ OpTables c_ops;
+template <typename F>
+__global__ void __launch_bounds__(CT_BLOCK) fixsink_local_site_kernel(CplxT<double> *__restrict__ csite, const CplxT<F> *__restrict__ fwd,
+                                                                     const CplxT<F> *__restrict__ seq, size_t V) {
+  const size_t x = (size_t)blockIdx.x * CT_BLOCK + threadIdx.x;
+  if (x >= V) return;
+  Cx<F> M[4][4];                                           // [n][r]
+#pragma unroll
+  for (int n = 0; n < 4; n++)
+#pragma unroll
+    for (int r = 0; r < 4; r++) M[n][r] = {0, 0};
+#pragma unroll 1
+  for (int mc = 0; mc < 36; mc++) {                        // (m, b, a)
+    const int m = mc / 9, ba = mc - m * 9;
+    Cx<F> Fr[4], Sn[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const CplxT<F> f = fwd[((size_t)(r * 4 + m) * 9 + ba) * V + x], q = seq[((size_t)(r * 4 + m) * 9 + ba) * V + x];
+      Fr[r] = {f.re, f.im}; Sn[r] = {q.re, q.im};
+    }
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) cmac(M[n][r], Fr[r], Sn[n]);
+  }
+  for (int iop = 0; iop < 16; iop++) {
+    Cx<double> acc = {0, 0};
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) cmac<double>(acc, {c_ops.re[iop][n * 4 + r], c_ops.im[iop][n * 4 + r]}, {(double)M[n][r].re, (double)M[n][r].im});
+    CplxT<double> o; o.re = acc.re; o.im = acc.im;
+    csite[(size_t)iop * V + x] = o;
+  }
+}
+
 // ---- one axis of the separable Fourier sum -----------------------------------------------------------------------------
 // in [ch][parent][outer][L] (L fastest) -> out[ch][child][outer]:  out = sum_k tab[q][k] in[.., k] for every entry q of the parent's
 // child list (child_start / child_out); one warp per input row, lanes stride the row, fixed-order shuffle tree.
@@ -440,6 +564,46 @@ static int baryon_tables(BaryonTables *t) {
   return 0;
 }
 
+// 1/2 (1 + i s g5) M (1 + i s g5): physical -> twisted basis at maximal twist
+static Mat4 twist_rotate(const Mat4 &M, const Mat4 &g5, double s) {
+  Mat4 R, out;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) R.m[i][j] = (i == j ? 1.0 : 0.0) + cd(0, s) * g5.m[i][j];
+  out = mul(mul(R, M), R);
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out.m[i][j] *= 0.5;
+  return out;
+}
+static Mat4 add4(const Mat4 &a, const Mat4 &b) { Mat4 r; for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) r.m[i][j] = a.m[i][j] + b.m[i][j]; return r; }
+static Mat4 scale4(const Mat4 &a, cd z) { Mat4 r; for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) r.m[i][j] = z * a.m[i][j]; return r; }
+static Mat4 eye4() { Mat4 r; for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) r.m[i][j] = i == j ? 1.0 : 0.0; return r; }
+// projectors_tm_base.h as a formula: 1/4 (1 + g4) [ i g5 g_k | summed over k ] rotated with s = +1 (proton) / -1 (neutron);
+// pid: 0 G4, 1 G5G123, 2..4 G5G1..G5G3 (WHICHPROJECTOR, include/qudaQKXTM_utils.h:129)
+static Mat4 projector_tm(int pid, int particle) {
+  Mat4 g[5];
+  ukqcd_gammas(g);
+  const Mat4 P0 = scale4(add4(eye4(), g[3]), 0.25);
+  Mat4 Pk[3];
+  for (int k = 0; k < 3; k++) Pk[k] = mul(P0, scale4(mul(g[4], g[k]), cd(0, 1)));
+  Mat4 phys = pid == 0 ? P0 : (pid == 1 ? add4(add4(Pk[0], Pk[1]), Pk[2]) : Pk[pid - 2]);
+  return twist_rotate(phys, g[4], particle == 0 ? +1.0 : -1.0);
+}
+// gammas_tm_base.h as a formula: 1, g1..g4, g5, g5 g1..g5 g4, -i sigma_{12,13,23,41,42,43} rotated with s = +1 for (proton, part 1) and
+// (neutron, part 2), -1 otherwise
+static void operator_tables(OpTables *t, int particle, int partflag) {
+  Mat4 g[5];
+  ukqcd_gammas(g);
+  std::vector<Mat4> ops = {eye4(), g[0], g[1], g[2], g[3], g[4], mul(g[4], g[0]), mul(g[4], g[1]), mul(g[4], g[2]), mul(g[4], g[3])};
+  const int pr[6][2] = {{0, 1}, {0, 2}, {1, 2}, {3, 0}, {3, 1}, {3, 2}};
+  for (int q = 0; q < 6; q++) {
+    const Mat4 ab = mul(g[pr[q][0]], g[pr[q][1]]), ba = mul(g[pr[q][1]], g[pr[q][0]]);
+    ops.push_back(scale4(add4(ab, scale4(ba, -1.0)), cd(0, -0.5)));          // -i * 1/2 [g_a, g_b]
+  }
+  const double s = ((particle == 0) == (partflag == 1)) ? +1.0 : -1.0;
+  for (int iop = 0; iop < 16; iop++) {
+    const Mat4 G = twist_rotate(ops[iop], g[4], s);
+    for (int n = 0; n < 4; n++) for (int r = 0; r < 4; r++) { t->re[iop][n * 4 + r] = G.m[n][r].real(); t->im[iop][n * 4 + r] = G.m[n][r].imag(); }
+  }
+}
+
 // carve-out of the context's grow-only contraction work space (256-byte aligned pieces)
 struct WsPlan {
   size_t total = 0;
@@ -462,13 +626,13 @@ static cudaError_t run_stage(const DftStage &s, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// exp(-2 pi i q (k + off - k0) / Ltot) for k = 0..L-1
-static void phase_row(std::vector<CplxT<double>> &tab, int q, int L, int off, int k0, int Ltot) {
+// exp(sgn 2 pi i q (k + off - k0) / Ltot) for k = 0..L-1 (sgn = -1: two-point functions, +1: the three-point insertion)
+static void phase_row(std::vector<CplxT<double>> &tab, int q, int L, int off, int k0, int Ltot, int sgn = -1) {
   for (int k = 0; k < L; k++) {
     // reduce the integer numerator first: the phase is exact to the last bit of the argument
     long long num = ((long long)q * (k + off - k0)) % Ltot;
     const double ph = 2.0 * M_PI * (double)num / (double)Ltot;
-    CplxT<double> e; e.re = cos(ph); e.im = -sin(ph);
+    CplxT<double> e; e.re = cos(ph); e.im = sgn * sin(ph);
     tab.push_back(e);
   }
 }
@@ -486,7 +650,7 @@ struct MomProjector {
   // byte offsets into the work space (filled by plan())
   size_t o_w1 = 0, o_w2 = 0, o_w3 = 0, o_tab1 = 0, o_tab2 = 0, o_tab3 = 0, o_s1 = 0, o_s2 = 0, o_s3 = 0, o_o1 = 0, o_o2 = 0, o_o3 = 0;
 
-  void build(tmq_ctx *ctx, const int *moms, int n, const int src_pos[3]) {
+  void build(tmq_ctx *ctx, const int *moms, int n, const int src_pos[3], int sgn = -1) {
     c = ctx; nmoms = n;
     X = c->g.X[0]; Y = c->g.X[1]; Z = c->g.X[2]; T = c->g.X[3];
     std::vector<int> px_list;
@@ -504,18 +668,18 @@ struct MomProjector {
     const int gX = X * c->grid[0], gY = Y * c->grid[1], gZ = Z * c->grid[2];
     // stage 1 (x): one parent, children = all p_x
     start1 = {0, npx}; out1.assign(npx, 0); start2.assign(npx + 1, 0); start3.assign(npair + 1, 0);
-    for (int ix = 0; ix < npx; ix++) { out1[ix] = ix; phase_row(tab1, px_list[ix], X, c->coord[0] * X, src_pos[0], gX); }
+    for (int ix = 0; ix < npx; ix++) { out1[ix] = ix; phase_row(tab1, px_list[ix], X, c->coord[0] * X, src_pos[0], gX, sgn); }
     // stage 2 (y): parent ix -> its pairs (contiguous by construction)
     for (int ix = 0; ix < npx; ix++) {
       start2[ix] = (int)out2.size();
-      for (int j = 0; j < npair; j++) if (pair_list[j].first == ix) { out2.push_back(j); phase_row(tab2, pair_list[j].second, Y, c->coord[1] * Y, src_pos[1], gY); }
+      for (int j = 0; j < npair; j++) if (pair_list[j].first == ix) { out2.push_back(j); phase_row(tab2, pair_list[j].second, Y, c->coord[1] * Y, src_pos[1], gY, sgn); }
     }
     start2[npx] = (int)out2.size();
     // stage 3 (z): parent pair -> the momenta with that (p_x, p_y), output index = the caller's momentum index
     for (int j = 0; j < npair; j++) {
       start3[j] = (int)out3.size();
       for (int m = 0; m < nmoms; m++)
-        if (px_idx[moms[3 * m]] == pair_list[j].first && moms[3 * m + 1] == pair_list[j].second) { out3.push_back(m); phase_row(tab3, moms[3 * m + 2], Z, c->coord[2] * Z, src_pos[2], gZ); }
+        if (px_idx[moms[3 * m]] == pair_list[j].first && moms[3 * m + 1] == pair_list[j].second) { out3.push_back(m); phase_row(tab3, moms[3 * m + 2], Z, c->coord[2] * Z, src_pos[2], gZ, sgn); }
     }
     start3[npair] = (int)out3.size();
   }
@@ -693,13 +857,11 @@ int tmq_qkxtm_contract_baryons(tmq_ctx *c, const void *d_prop1, const void *d_pr
   TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
   TMQ_REQUIRE(nmoms > 0, "empty momentum list");
   TMQ_CUDA(cudaSetDevice(c->device));
+  // __constant__ memory is per device: upload on every call (2.6 KB) rather than tracking which devices have it
+  static BaryonTables tables;
   static bool have_tables = false;
-  if (!have_tables) {
-    BaryonTables t;
-    TMQ_TRY(baryon_tables(&t));
-    TMQ_CUDA(cudaMemcpyToSymbol(c_baryon, &t, sizeof(t)));
-    have_tables = true;
-  }
+  if (!have_tables) { TMQ_TRY(baryon_tables(&tables)); have_tables = true; }
+  TMQ_CUDA(cudaMemcpyToSymbolAsync(c_baryon, &tables, sizeof(tables), 0, cudaMemcpyHostToDevice, c->stream));
   const int X = c->g.X[0], Y = c->g.X[1], Z = c->g.X[2], T = c->g.X[3];
   const size_t V = (size_t)2 * c->g.Vh, V3 = (size_t)X * Y * Z;
   TMQ_REQUIRE(X <= 32 * DFT_MAXK && Y <= 32 * DFT_MAXK && Z <= 32 * DFT_MAXK, "spatial extent above %d not supported", 32 * DFT_MAXK);
@@ -735,6 +897,72 @@ int tmq_qkxtm_contract_baryons(tmq_ctx *c, const void *d_prop1, const void *d_pr
     c->launches++;
     TMQ_TRY(mp.project(ws, csite, NCH, t0, n, corr_mom, st));
   }
+  TMQ_TRY(allreduce_host(c, ws, o_glob, corr_mom, ntot, st));
+  return 0;
+}
+
+int tmq_qkxtm_seq_source(tmq_ctx *c, void *d_vec_out, int timeslice, const void *d_prop3d_1, const void *d_prop3d_2, int prec, int nu, int c2,
+                         int pid, int particle, int part) {
+  TMQ_REQUIRE(c && d_vec_out && d_prop3d_1, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(part == 1 || part == 2, "part must be 1 or 2");
+  TMQ_REQUIRE(part == 2 || d_prop3d_2, "part 1 needs two 3-d propagators");
+  TMQ_REQUIRE(nu >= 0 && nu < 4 && c2 >= 0 && c2 < 3, "bad source spin / colour");
+  TMQ_REQUIRE(pid >= 0 && pid < 5 && (particle == 0 || particle == 1), "bad projector / particle");
+  TMQ_REQUIRE(timeslice >= 0 && timeslice < c->g.X[3], "time slice outside the local lattice");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  Mat4 g[5];
+  ukqcd_gammas(g);
+  Mono gm;
+  TMQ_TRY(to_mono(mul(mul(g[3], g[1]), g[4]), &gm, "C g5"));
+  SeqSrcTables t;
+  for (int r = 0; r < 4; r++) { t.gperm[r] = gm.perm[r]; t.ginv[gm.perm[r]] = r; t.gre[r] = gm.re[r]; t.gim[r] = gm.im[r]; }
+  const Mat4 P = projector_tm(pid, particle);
+  for (int b = 0; b < 4; b++) for (int a = 0; a < 4; a++) { t.pre[b][a] = std::abs(P.m[b][a]) > 1e-3 ? P.m[b][a].real() : 0.0; t.pim[b][a] = std::abs(P.m[b][a]) > 1e-3 ? P.m[b][a].imag() : 0.0; }
+  t.nu_f = nu; t.c2_f = c2;
+  const size_t V = (size_t)2 * c->g.Vh, V3 = V / c->g.X[3];
+  const unsigned int grid = (unsigned int)((V3 + 127) / 128);
+  if (prec == 8) seq_source_kernel<double><<<grid, 128, 0, c->stream>>>((CplxT<double> *)d_vec_out, V, V3, timeslice, (const CplxT<double> *)d_prop3d_1, (const CplxT<double> *)d_prop3d_2, t, part);
+  else seq_source_kernel<float><<<grid, 128, 0, c->stream>>>((CplxT<float> *)d_vec_out, V, V3, timeslice, (const CplxT<float> *)d_prop3d_1, (const CplxT<float> *)d_prop3d_2, t, part);
+  TMQ_CUDA(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int tmq_qkxtm_fixsink_local(tmq_ctx *c, const void *d_seq_prop, const void *d_fwd_prop, int prec, int particle, int partflag, const int *moms,
+                            int nmoms, const int src_pos[3], double *corr_mom) {
+  TMQ_REQUIRE(c && d_seq_prop && d_fwd_prop && moms && src_pos && corr_mom, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(nmoms > 0, "empty momentum list");
+  TMQ_REQUIRE((particle == 0 || particle == 1) && (partflag == 1 || partflag == 2), "bad particle / part");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  static OpTables ops;                                   // must outlive the asynchronous upload
+  operator_tables(&ops, particle, partflag);
+  cudaStream_t st = c->stream;
+  TMQ_CUDA(cudaStreamSynchronize(st));                   // a previous call's upload of `ops` has completed
+  TMQ_CUDA(cudaMemcpyToSymbolAsync(c_ops, &ops, sizeof(ops), 0, cudaMemcpyHostToDevice, st));
+  const int X = c->g.X[0], Y = c->g.X[1], Z = c->g.X[2], T = c->g.X[3];
+  const size_t V = (size_t)2 * c->g.Vh;
+  TMQ_REQUIRE(X <= 32 * DFT_MAXK && Y <= 32 * DFT_MAXK && Z <= 32 * DFT_MAXK, "spatial extent above %d not supported", 32 * DFT_MAXK);
+  MomProjector mp;
+  mp.build(c, moms, nmoms, src_pos, +1);                 // exp(+i p x) (fixSinkContractions_local_core.h:52-56)
+  const int gT = T * c->grid[3];
+  const size_t ntot = (size_t)gT * nmoms * 16 * 2;
+  WsPlan plan;
+  const size_t o_csite = plan.add(V * 16 * sizeof(CplxT<double>));
+  mp.plan(plan, 16, T);
+  const size_t o_glob = plan.add(ntot * sizeof(double));
+  TMQ_TRY(ensure_contract_ws(c, plan.total));
+  char *ws = (char *)c->contract_ws;
+  CplxT<double> *csite = (CplxT<double> *)(ws + o_csite);
+  const unsigned int grid = (unsigned int)((V + CT_BLOCK - 1) / CT_BLOCK);
+  if (prec == 8) fixsink_local_site_kernel<double><<<grid, CT_BLOCK, 0, st>>>(csite, (const CplxT<double> *)d_fwd_prop, (const CplxT<double> *)d_seq_prop, V);
+  else fixsink_local_site_kernel<float><<<grid, CT_BLOCK, 0, st>>>(csite, (const CplxT<float> *)d_fwd_prop, (const CplxT<float> *)d_seq_prop, V);
+  TMQ_CUDA(cudaGetLastError());
+  c->launches++;
+  for (size_t i = 0; i < ntot; i++) corr_mom[i] = 0.0;
+  TMQ_TRY(mp.upload_tables(ws, st));
+  TMQ_TRY(mp.project(ws, csite, 16, 0, T, corr_mom, st));
   TMQ_TRY(allreduce_host(c, ws, o_glob, corr_mom, ntot, st));
   return 0;
 }
