@@ -110,6 +110,9 @@ enum CLASS_ENUM { FIELD, GAUGE, VECTOR, PROPAGATOR, PROPAGATOR3D, VECTOR3D };  /
 enum CORR_SPACE { POSITION_SPACE, MOMENTUM_SPACE };                            // include/qudaQKXTM_utils.h:41
 enum FILE_WRITE_FORMAT { ASCII_FORM, HDF5_FORM };                              // include/qudaQKXTM_utils.h:42
 enum WHICHPARTICLE { PROTON, NEUTRON };                                        // include/qudaQKXTM_utils.h:128
+enum WHICHPROJECTOR { G4, G5G123, G5G1, G5G2, G5G3 };                          // include/qudaQKXTM_utils.h:129
+#define MAX_TSINK 10                                                          // include/qudaQKXTM_utils.h:20
+#define MAX_PROJS 5                                                           // include/qudaQKXTM_utils.h:23
 
 typedef struct {                       // the slice of qudaQKXTMinfo the built paths read (include/qudaQKXTM_utils.h:45-75)
   int nsmearAPE, nsmearGauss;
@@ -121,7 +124,11 @@ typedef struct {                       // the slice of qudaQKXTMinfo the built p
   int Q_sq;                            // momenta with p^2 <= Q_sq (createMomenta, lib/qudaQKXTM_kernels.cu:98-116)
   int traj;
   bool check_files;
-  int run3pt_src[MAX_NSOURCES];        // must be 0: the three-point function is not built
+  int Ntsink;                          // sink-source separations of the three-point function
+  int Nproj[MAX_TSINK];
+  int tsinkSource[MAX_TSINK];
+  int proj_list[MAX_TSINK][MAX_PROJS]; // WHICHPROJECTOR values
+  int run3pt_src[MAX_NSOURCES];        // != 0: also the fixed-sink three-point function (ultra-local insertion) for this source
   FILE_WRITE_FORMAT CorrFileFormat;    // ASCII_FORM only (no HDF5 here)
   CORR_SPACE CorrSpace;
   bool isEven;
@@ -249,6 +256,20 @@ public:
   // "ip it px py pz gamma gammap  re(iu=0) im(iu=0)  re(iu=1) im(iu=1)", time relative to the source, sign flip where the time wraps
   // (anti-periodic boundary), lib/qudaQKXTM_Contraction.cpp:877-901
   void writeTwopBaryons_ASCII(void *corrBaryons, char *filename_out, int isource, CORR_SPACE CorrSpace);
+  // fixed-sink sequential sources (lib/qudaQKXTM_Contraction.cpp:1652-1688): written into time slice `timeslice` of vec
+  void seqSourceFixSinkPart1(QKXTM_Vector<Float> &vec, QKXTM_Propagator3D<Float> &prop1, QKXTM_Propagator3D<Float> &prop2, int timeslice, int nu,
+                             int c2, WHICHPROJECTOR PID, WHICHPARTICLE testParticle);
+  void seqSourceFixSinkPart2(QKXTM_Vector<Float> &vec, QKXTM_Propagator3D<Float> &prop, int timeslice, int nu, int c2, WHICHPROJECTOR PID,
+                             WHICHPARTICLE testParticle);
+  // lib/qudaQKXTM_Contraction.cpp:3008-3110, the ULTRA-LOCAL insertion only: corrThp_local Float[T_local * Nmoms * 16 * 2], entry
+  // [it*Nmoms*16*2 + imom*16*2 + iop*2 + ri]; corrThp_noether / corrThp_oneD must be NULL (the conserved-current and one-derivative
+  // insertions are not built); gauge is unused by the local insertion
+  void contractFixSink(QKXTM_Propagator<Float> &seqProp, QKXTM_Propagator<Float> &prop, QKXTM_Gauge<Float> &gauge, void *corrThp_local,
+                       void *corrThp_noether, void *corrThp_oneD, WHICHPROJECTOR typeProj, WHICHPARTICLE testParticle, int partflag, int isource,
+                       CORR_SPACE CorrSpace);
+  // "<filename_out>.<proton|neutron>.<up|down>.ultra_local.SS.xx.yy.zz.tt.dat": "iop it px py pz re im" (lib/qudaQKXTM_Contraction.cpp:2842-2960)
+  void writeThrp_ASCII(void *corrThp_local, void *corrThp_noether, void *corrThp_oneD, WHICHPARTICLE testParticle, int partflag, char *filename_out,
+                       int isource, int tsinkMtsource, CORR_SPACE CorrSpace);
 };
 int qkxtm_Nmoms();                                  // GK_Nmoms / GK_moms after init_qudaQKXTM
 const int *qkxtm_moms();                            // [Nmoms][3]

@@ -229,6 +229,21 @@ int tmq_qkxtm_contract_mesons(tmq_ctx *, const void *d_prop1, const void *d_prop
  * complete reduced result.  The reference's launcher accepts float propagators only; double is accepted here.               */
 int tmq_qkxtm_contract_baryons(tmq_ctx *, const void *d_prop1, const void *d_prop2, int prec, const int *moms, int nmoms,
                                const int src_pos[3], double *corr_mom);
+/* fixed-sink three-point function of the nucleon (lib/qudaQKXTM_interface.cpp:764-1170), ultra-local insertion.
+ * tmq_qkxtm_seq_source: QKXTM_Contraction::seqSourceFixSinkPart1 / Part2 (lib/qudaQKXTM_Contraction.cpp:1652-1688, kernel bodies
+ * seqSourceFixSinkPart{1,2}_core.h + projectors_tm_base.h): the sequential source for source spin / colour (nu, c2) written into time
+ * slice `timeslice` of the 4-d vector d_vec_out (the rest of the vector is not touched: zero it first, as the reference does) from
+ * the 3-d propagators of that time slice d[((mu*4+nu)*9 + c1*3+c2)*V3 + x].  part = 1: the quark line that occurs twice in the
+ * nucleon (two propagators: tex1, tex2 of the reference), part = 2: the line that occurs once (d_prop3d_2 ignored).
+ * pid: 0 G4, 1 G5G123, 2 G5G1, 3 G5G2, 4 G5G3 (WHICHPROJECTOR); particle: 0 proton, 1 neutron (WHICHPARTICLE).                    */
+int tmq_qkxtm_seq_source(tmq_ctx *, void *d_vec_out, int timeslice, const void *d_prop3d_1, const void *d_prop3d_2, int prec, int nu, int c2,
+                         int pid, int particle, int part);
+/* the ultra-local part of QKXTM_Contraction::contractFixSink (lib/qudaQKXTM_Contraction.cpp:3008-3110, kernel body
+ * fixSinkContractions_local_core.h + gammas_tm_base.h): 16 insertions (1, g1..g4, g5, g5g1..g5g4, g5 sigma) in the twisted basis,
+ * corr_mom (host): [t GLOBAL][imom][iop][re,im] = sum_xvec exp(+2 pi i p.(x - src_pos)/L) sum Gamma_iop[n][r] F[r][m]^{ba} S[n][m]^{ba};
+ * partflag 1 | 2 selects the rotation sign together with the particle, as in the reference.                                        */
+int tmq_qkxtm_fixsink_local(tmq_ctx *, const void *d_seq_prop, const void *d_fwd_prop, int prec, int particle, int partflag, const int *moms,
+                            int nmoms, const int src_pos[3], double *corr_mom);
 
 /* ---- raw device memory for the containers (QKXTM_Field::create_device, lib/qudaQKXTM_Field.cpp:172) ----- */
 int tmq_dev_malloc(tmq_ctx *, void **ptr, size_t bytes);

@@ -38,6 +38,12 @@ def lib():
         L.qref_contract_mesons_mom_float.argtypes = [fp, fp, fp, ip]
         L.qref_contract_mesons_mom_double.argtypes = [dp, dp, dp, ip]
         L.qref_contract_mesons_pos_float.argtypes = [fp, fp, fp]
+        L.qref_seq_source_part1_double.argtypes = [dp, C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.qref_seq_source_part2_double.argtypes = [dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.qref_fixsink_local_float.argtypes = [fp, fp, fp, C.c_int, C.c_int, ip]
+        L.qref_fixsink_local_double.argtypes = [dp, dp, dp, C.c_int, C.c_int, ip]
+        L.qref_get_projector.argtypes = [dp, C.c_int, C.c_int]
+        L.qref_get_operator.argtypes = [dp, C.c_int, C.c_int, C.c_int]
         L.qref_contract_baryons_mom_float.argtypes = [fp, fp, fp, ip]
         L.qref_contract_baryons_mom_double.argtypes = [dp, dp, dp, ip]
         _lib = L
@@ -142,6 +148,35 @@ class Ref:
             self.L.qref_contract_baryons_mom_float(_fp(out), _fp(prop1), _fp(prop2), s)
         else:
             self.L.qref_contract_baryons_mom_double(_dp(out), _dp(prop1), _dp(prop2), s)
+        return out
+
+    # ---- fixed-sink three-point function ------------------------------------------------------------------------------------
+    def projector(self, pid, particle):
+        a = np.zeros(32); self.L.qref_get_projector(_dp(a), pid, particle); return (a[0::2] + 1j * a[1::2]).reshape(4, 4)
+
+    def operator(self, flag, particle, partflag):
+        a = np.zeros(32); self.L.qref_get_operator(_dp(a), flag, particle, partflag); return (a[0::2] + 1j * a[1::2]).reshape(4, 4)
+
+    def seq_source(self, part, timeslice, p3d_1, p3d_2, nu, c2, pid, particle):
+        """seqSourceFixSinkPart1 / Part2 (double): 3-d propagators [4][4][3][3][V3][2] -> the 4-d vector [12][V][2] (only the
+        time slice is written)"""
+        out = np.zeros((12, self.V, 2))
+        if part == 1:
+            self.L.qref_seq_source_part1_double(_dp(out), timeslice, _dp(p3d_1), _dp(p3d_2), nu, c2, pid, particle)
+        else:
+            self.L.qref_seq_source_part2_double(_dp(out), timeslice, _dp(p3d_1), nu, c2, pid, particle)
+        return out
+
+    def fixsink_local(self, fwd, seq, particle, partflag, moms, src):
+        """ultra-local part of contractFixSink, MOMENTUM_SPACE -> [T][nmoms][16][re,im]"""
+        m = np.ascontiguousarray(np.asarray(moms, dtype=np.int32).reshape(-1, 3))
+        self.L.qref_set_momenta(m.ctypes.data_as(C.POINTER(C.c_int)), len(m))
+        out = np.zeros((self.X[3], len(m), 16, 2), dtype=fwd.dtype)
+        s = (C.c_int * 3)(*[int(v) for v in src])
+        if fwd.dtype == np.float32:
+            self.L.qref_fixsink_local_float(_fp(out), _fp(fwd), _fp(seq), particle, partflag, s)
+        else:
+            self.L.qref_fixsink_local_double(_dp(out), _dp(fwd), _dp(seq), particle, partflag, s)
         return out
 
     def contract_mesons_pos(self, prop1, prop2):

@@ -19,7 +19,7 @@ static void usage() {
          "   [--test invert|mgbench|loops|mdagm|mat] [--source z4|gaussian] [--seed s] [--verbosity-level silent|summarize|verbose]\n"
          "   [--out file] [--dump-inputs prefix]\n"
          "   --test twop [--Q_sq q] [--src x y z t] [--nsmearGauss n --alphaGauss a]: meson two-point function, written to\n"
-         "       <out>.mesons.SS.xx.yy.zz.tt.dat\n");
+         "       <out>.mesons.SS.xx.yy.zz.tt.dat; with --tsink dt [--proj 0..4] [--particle proton|neutron] also the three-point function\n");
 }
 
 int main(int argc, char **argv) {
@@ -30,7 +30,8 @@ int main(int argc, char **argv) {
   unsigned long long seed = 100;
   int nev = 4, nkv = 16, polydeg = 20;
   double amin = 0.385, amax = 2.0, eig_tol = 1e-10, csw = 0.0;
-  int q_sq = 0, src_pos[4] = {0, 0, 0, 0};
+  int q_sq = 0, src_pos[4] = {0, 0, 0, 0}, tsink = 0, proj = 0;
+  std::string particle = "proton";
   std::string dslash_type = "twisted-mass";
   int nsmearGauss = 0; double alphaGauss = 4.0;                              // qkxtm/QKXTM_util.cpp:1652-1654
   for (int i = 1; i < argc; i++) {
@@ -63,6 +64,9 @@ int main(int argc, char **argv) {
     else if (a == "--tolArpack") { need(1); eig_tol = atof(argv[++i]); }
     else if (a == "--Q_sq") { need(1); q_sq = atoi(argv[++i]); }               // qkxtm/QKXTM_util.cpp (momenta with p^2 <= Q_sq)
     else if (a == "--src") { need(4); for (int d = 0; d < 4; d++) src_pos[d] = atoi(argv[++i]); }
+    else if (a == "--tsink") { need(1); tsink = atoi(argv[++i]); }             // > 0: also the three-point function at this sink-source separation
+    else if (a == "--proj") { need(1); proj = atoi(argv[++i]); }               // WHICHPROJECTOR 0..4
+    else if (a == "--particle") { need(1); particle = argv[++i]; }            // proton | neutron
     else if (a == "--help") { usage(); return 0; }
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
   }
@@ -118,6 +122,7 @@ int main(int argc, char **argv) {
   info.kappa = inv_param.kappa; info.mu = mu; info.inv_tol = tol; info.Precision = QUDA_DOUBLE_PRECISION;
   info.Nsources = 1; info.Q_sq = q_sq; info.CorrSpace = MOMENTUM_SPACE; info.CorrFileFormat = ASCII_FORM;
   for (int d = 0; d < 4; d++) info.sourcePosition[0][d] = src_pos[d];
+  if (tsink > 0) { info.run3pt_src[0] = 1; info.Ntsink = 1; info.tsinkSource[0] = tsink; info.Nproj[0] = 1; info.proj_list[0][0] = proj; }
 
   // synthetic configuration: random SU(3), QDP even-odd order, anti-periodic T folded in
   std::vector<double> gbuf((size_t)4 * V * 18);
@@ -194,8 +199,9 @@ int main(int argc, char **argv) {
       // qkxtm/CalcMG_2pt3pt_EvenOdd.cpp main(): the two-point function of one source position
       std::string base = out.empty() ? std::string("twop") : out;
       std::vector<char> f2(base.begin(), base.end()); f2.push_back(0);
-      char f3[] = "unused";
-      calcMG_threepTwop_EvenOdd((void **)glex, (void **)gauge, &gauge_param, &inv_param, info, f2.data(), f3, PROTON);
+      std::string base3 = base + ".threep";
+      std::vector<char> f3(base3.begin(), base3.end()); f3.push_back(0);
+      calcMG_threepTwop_EvenOdd((void **)glex, (void **)gauge, &gauge_param, &inv_param, info, f2.data(), f3.data(), particle == "neutron" ? NEUTRON : PROTON);
     }
   } else { usage(); return 2; }
 

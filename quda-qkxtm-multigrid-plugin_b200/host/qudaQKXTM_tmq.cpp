@@ -651,6 +651,67 @@ void QKXTM_Contraction<Float>::writeTwopBaryons_ASCII(void *corrBaryons, char *f
   fclose(ptr_out);
 }
 
+template <typename Float>
+void QKXTM_Contraction<Float>::seqSourceFixSinkPart1(QKXTM_Vector<Float> &vec, QKXTM_Propagator3D<Float> &prop1, QKXTM_Propagator3D<Float> &prop2,
+                                                     int timeslice, int nu, int c2, WHICHPROJECTOR PID, WHICHPARTICLE testParticle) {
+  TMQ_OK(tmq_qkxtm_seq_source(G.ctx, vec.D_elem(), timeslice, prop1.D_elem(), prop2.D_elem(), (int)sizeof(Float), nu, c2, (int)PID, (int)testParticle, 1));
+}
+template <typename Float>
+void QKXTM_Contraction<Float>::seqSourceFixSinkPart2(QKXTM_Vector<Float> &vec, QKXTM_Propagator3D<Float> &prop, int timeslice, int nu, int c2,
+                                                     WHICHPROJECTOR PID, WHICHPARTICLE testParticle) {
+  TMQ_OK(tmq_qkxtm_seq_source(G.ctx, vec.D_elem(), timeslice, prop.D_elem(), NULL, (int)sizeof(Float), nu, c2, (int)PID, (int)testParticle, 2));
+}
+template <typename Float>
+void QKXTM_Contraction<Float>::contractFixSink(QKXTM_Propagator<Float> &seqProp, QKXTM_Propagator<Float> &prop, QKXTM_Gauge<Float> &gauge,
+                                               void *corrThp_local, void *corrThp_noether, void *corrThp_oneD, WHICHPROJECTOR typeProj,
+                                               WHICHPARTICLE testParticle, int partflag, int isource, CORR_SPACE CorrSpace) {
+  (void)gauge; (void)typeProj;
+  if (!corrThp_local) errorQuda("null correlator buffer");
+  if (corrThp_noether || corrThp_oneD) errorQuda("contractFixSink: the Noether and one-derivative insertions are not built (pass NULL)");
+  if (CorrSpace != MOMENTUM_SPACE) errorQuda("contractFixSink: only MOMENTUM_SPACE is built");
+  if (isource < 0 || (size_t)isource * 4 >= G.sourcePosition.size()) errorQuda("source %d was not given to init_qudaQKXTM", isource);
+  printfQuda("contractFixSink: Will perform in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
+  const int Lt = G.localL[3], nm = qkxtm_Nmoms(), gT = Lt * G.grid[3];
+  if (nm <= 0) errorQuda("no momenta: init_qudaQKXTM was given Q_sq < 0");
+  std::vector<double> mom((size_t)gT * nm * 16 * 2);
+  TMQ_OK(tmq_qkxtm_fixsink_local(G.ctx, seqProp.D_elem(), prop.D_elem(), (int)sizeof(Float), (int)testParticle, partflag, G.moms.data(), nm,
+                                 &G.sourcePosition[(size_t)isource * 4], mom.data()));
+  Float *out = (Float *)corrThp_local;
+  for (size_t i = 0; i < (size_t)Lt * nm * 32; i++) out[i] = (Float)mom[(size_t)G.coord[3] * Lt * nm * 32 + i];
+}
+template <typename Float>
+void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrThp_noether, void *corrThp_oneD, WHICHPARTICLE testParticle, int partflag,
+                                               char *filename_out, int isource, int tsinkMtsource, CORR_SPACE CorrSpace) {
+  if (CorrSpace != MOMENTUM_SPACE) errorQuda("writeThrp_ASCII: Supports writing only in momentum-space!");
+  if (corrThp_noether || corrThp_oneD) errorQuda("writeThrp_ASCII: the Noether and one-derivative insertions are not built (pass NULL)");
+  if (G.grid[3] != 1) errorQuda("writeThrp_ASCII: gather the time ranks' buffers first (single rank in t here)");
+  if (partflag != 1 && partflag != 2) errorQuda("writeThrp_ASCII: Got the wrong part! Should be either 1 or 2.");
+  printfQuda("writeThrp_ASCII: Will write in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
+  const char *particle = testParticle == PROTON ? "proton" : "neutron";
+  const char *flavour = (testParticle == PROTON) == (partflag == 1) ? "up" : "down";          // Contraction.cpp:2903-2914
+  const int *sp = &G.sourcePosition[(size_t)isource * 4];
+  char fname_local[1024];
+  snprintf(fname_local, sizeof(fname_local), "%s.%s.%s.%s.SS.%02d.%02d.%02d.%02d.dat", filename_out, particle, flavour, "ultra_local", sp[0], sp[1], sp[2], sp[3]);
+  bool root = true;
+  for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
+  if (!root) return;
+  const Float *c = (const Float *)corrThp_local;
+  const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
+  const int *mv = qkxtm_moms();
+  FILE *ptr_local = fopen(fname_local, "w");
+  if (ptr_local == NULL) errorQuda("Error opening file for writing");
+  for (int iop = 0; iop < 16; iop++)
+    for (int it = 0; it < T; it++)
+      for (int imom = 0; imom < nm; imom++) {
+        const int it_shift = (it + sp[3]) % T;
+        const int sign = (tsinkMtsource + sp[3]) >= T ? -1 : +1;            // the sink lies beyond the anti-periodic boundary
+        const size_t k = ((size_t)it_shift * nm + imom) * 32 + iop * 2;
+        fprintf(ptr_local, "%d \t %d \t %+d %+d %+d \t %+e %+e\n", iop, it, mv[3 * imom], mv[3 * imom + 1], mv[3 * imom + 2], sign * (double)c[k],
+                sign * (double)c[k + 1]);
+      }
+  fclose(ptr_local);
+}
+
 // ---- QKXTM_Deflation ----------------------------------------------------------------------------------------------------
 template <typename Float>
 QKXTM_Deflation<Float>::QKXTM_Deflation(QudaInvertParam *param, qudaQKXTM_arpackInfo ai)
@@ -851,7 +912,7 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
 
 void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, qudaQKXTMinfo info,
                                char *filename_twop, char *filename_threep, WHICHPARTICLE NUCLEON) {
-  (void)gauge; (void)filename_threep; (void)NUCLEON;
+  (void)gauge;
   if (!param || !gauge_param || !filename_twop) errorQuda("null argument");
   check_solver(param);
   if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
@@ -859,7 +920,10 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   if (info.CorrFileFormat != ASCII_FORM) errorQuda("only the ASCII two-point format is built (no HDF5 here)");
   if (info.CorrSpace != MOMENTUM_SPACE) errorQuda("the ASCII two-point writer supports only momentum space");           // Contraction.cpp:1565
   if (G.grid[3] != 1) errorQuda("the two-point driver gathers no time ranks: run it unsharded in t");
-  for (int i = 0; i < info.Nsources; i++) if (info.run3pt_src[i]) errorQuda("three-point functions are not built");
+  bool any3pt = false;
+  for (int i = 0; i < info.Nsources; i++) any3pt = any3pt || info.run3pt_src[i];
+  if (any3pt && !filename_threep) errorQuda("null three-point file name");
+  if (any3pt && (info.Ntsink < 0 || info.Ntsink > MAX_TSINK)) errorQuda("bad number of sink-source separations %d", info.Ntsink);
   if (G.nsmearGauss != 0 && !gaugeSmeared) errorQuda("Gaussian smearing needs the smeared links (gaugeSmeared)");
   const bool flag_eo = info.isEven;
   const long long V = G.localVolume;
@@ -880,6 +944,18 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   QKXTM_Propagator<float> *K_prop_up = new QKXTM_Propagator<float>(BOTH, PROPAGATOR);
   QKXTM_Propagator<float> *K_prop_down = new QKXTM_Propagator<float>(BOTH, PROPAGATOR);
   QKXTM_Contraction<float> *K_contract = new QKXTM_Contraction<float>();
+  QKXTM_Propagator<float> *K_seqProp = NULL;
+  QKXTM_Propagator3D<float> *K_prop3D_up = NULL, *K_prop3D_down = NULL;
+  float *corrThp_local = NULL;
+  if (any3pt) {
+    K_seqProp = new QKXTM_Propagator<float>(BOTH, PROPAGATOR);                     // interface.cpp:372-376
+    K_prop3D_up = new QKXTM_Propagator3D<float>(BOTH, PROPAGATOR3D);
+    K_prop3D_down = new QKXTM_Propagator3D<float>(BOTH, PROPAGATOR3D);
+    corrThp_local = (float *)calloc((size_t)G.localL[3] * nm * 16 * 2, sizeof(float));
+    if (!corrThp_local) errorQuda("Cannot allocate memory for the three-point function");
+  }
+  static const char *proj_names[5] = {"G4", "G5G123", "G5G1", "G5G2", "G5G3"};  // info.thrp_proj_type (:284-288)
+  QKXTM_Gauge<float> K_gaugeContractions(NONE, GAUGE);      // only the (unbuilt) Noether / one-derivative insertions would read the links
   float *corrMesons = (float *)calloc((size_t)G.localL[3] * nm * 2 * 10 * 2, sizeof(float));
   float *corrBaryons = (float *)calloc((size_t)G.localL[3] * nm * 2 * 10 * 4 * 4 * 2, sizeof(float));
   if (!corrMesons || !corrBaryons) errorQuda("Cannot allocate memory for the two-point functions");
@@ -926,6 +1002,72 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
         (flavour == 0 ? K_prop_up : K_prop_down)->absorbVectorToDevice(*K_temp, isc / 3, isc % 3);
       }
     }
+    // ---- fixed-sink three-point function, ultra-local insertion (interface.cpp:764-1170); uses the forward propagators BEFORE
+    //      their sink smearing and rotation, as the reference does -------------------------------------------------------------
+    if (info.run3pt_src[isource]) {
+      const int T = G.localL[3] * G.grid[3];
+      for (int its = 0; its < info.Ntsink; its++) {
+        const int my_fixSinkTime = (info.tsinkSource[its] + sp[3]) % T - G.coord[3] * G.localL[3];
+        const bool mine_t = my_fixSinkTime >= 0 && my_fixSinkTime < G.localL[3];
+        if (mine_t) { K_prop3D_up->absorbTimeSlice(*K_prop_up, my_fixSinkTime); K_prop3D_down->absorbTimeSlice(*K_prop_down, my_fixSinkTime); }
+        // sink smearing of the 3-d propagators, column by column (:790-826)
+        for (int nu = 0; nu < 4; nu++)
+          for (int c2 = 0; c2 < 3; c2++)
+            for (int flavour = 0; flavour < 2; flavour++) {
+              QKXTM_Propagator3D<float> *P3 = flavour == 0 ? K_prop3D_up : K_prop3D_down;
+              K_temp->zero_device();
+              if (mine_t) K_temp->copyPropagator3D(*P3, my_fixSinkTime, nu, c2);
+              K_vector->castFloatToDouble(*K_temp);
+              if (K_gaugeSmeared) K_guess->gaussianSmearing(*K_vector, *K_gaugeSmeared);
+              K_temp->castDoubleToFloat(K_gaugeSmeared ? *K_guess : *K_vector);
+              if (mine_t) P3->absorbVectorTimeSlice(*K_temp, my_fixSinkTime, nu, c2);
+            }
+        for (int proj = 0; proj < info.Nproj[its]; proj++) {
+          const WHICHPROJECTOR PID = (WHICHPROJECTOR)info.proj_list[its][proj];
+          if ((int)PID < 0 || (int)PID > 4) errorQuda("bad projector %d", (int)PID);
+          printfQuda("\n# Three-point function calculation for source-position = %d, sink-source = %d, projector %s begins now\n", isource,
+                     info.tsinkSource[its], proj_names[(int)PID]);
+          char filename_threep_base[1024];
+          snprintf(filename_threep_base, sizeof(filename_threep_base), "%s_tsink%d_proj%s", filename_threep, info.tsinkSource[its], proj_names[(int)PID]);   // :838-840
+          for (int part = 1; part <= 2; part++) {
+            // part 1: the flavour that occurs twice (up for the proton) with the OTHER flavour's operator; part 2 the reverse (:853-866, 1007-1022)
+            const bool up_line = (NUCLEON == PROTON) == (part == 1);
+            param->mu = up_line ? -mu_abs : mu_abs;
+            printfQuda("Sequential Inversions, flavor %s:\n", up_line ? "up" : "dn");
+            for (int nu = 0; nu < 4; nu++)
+              for (int c2 = 0; c2 < 3; c2++) {
+                K_temp->zero_device();
+                if (mine_t) {
+                  if (part == 1) {
+                    if (NUCLEON == PROTON) K_contract->seqSourceFixSinkPart1(*K_temp, *K_prop3D_up, *K_prop3D_down, my_fixSinkTime, nu, c2, PID, NUCLEON);
+                    else K_contract->seqSourceFixSinkPart1(*K_temp, *K_prop3D_down, *K_prop3D_up, my_fixSinkTime, nu, c2, PID, NUCLEON);
+                  } else {
+                    K_contract->seqSourceFixSinkPart2(*K_temp, NUCLEON == PROTON ? *K_prop3D_up : *K_prop3D_down, my_fixSinkTime, nu, c2, PID, NUCLEON);
+                  }
+                }
+                K_temp->conjugate();
+                K_temp->apply_gamma5();
+                K_vector->castFloatToDouble(*K_temp);
+                K_vector->scaleVector(1e+10);                              // "Scale up vector to avoid MP errors" (:880)
+                if (K_gaugeSmeared) K_guess->gaussianSmearing(*K_vector, *K_gaugeSmeared);
+                (K_gaugeSmeared ? K_guess : K_vector)->uploadToCuda(b, flag_eo);
+                printfQuda("%02d - \n", nu * 3 + c2);
+                solve_device(*x, *b, param);
+                K_vector->downloadFromCuda(x, flag_eo);
+                if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION)
+                  K_vector->scaleVector(2 * param->kappa);
+                K_vector->scaleVector(1e-10);                              // "Rescale to normal"
+                K_temp->castDoubleToFloat(*K_vector);
+                K_seqProp->absorbVectorToDevice(*K_temp, nu, c2);
+              }
+            // part 1 contracts with the forward propagator of the doubly occurring flavour, part 2 with the other (:937-951, 1095-1109)
+            QKXTM_Propagator<float> *fwd = up_line ? K_prop_up : K_prop_down;
+            K_contract->contractFixSink(*K_seqProp, *fwd, K_gaugeContractions, corrThp_local, NULL, NULL, PID, NUCLEON, part, isource, info.CorrSpace);
+            K_contract->writeThrp_ASCII(corrThp_local, NULL, NULL, NUCLEON, part, filename_threep_base, isource, info.tsinkSource[its], info.CorrSpace);
+          }
+        }
+      }
+    }
     // smear the forward propagators at the sink (interface.cpp:1190-1215; the reference stages this through the host and
     // QUDA's performWuppertalnStep, here the same device kernel as at the source)
     if (K_gaugeSmeared)
@@ -953,6 +1095,10 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   param->mu = mu_abs;
   free(corrMesons);
   free(corrBaryons);
+  if (corrThp_local) free(corrThp_local);
+  if (K_seqProp) delete K_seqProp;
+  if (K_prop3D_up) delete K_prop3D_up;
+  if (K_prop3D_down) delete K_prop3D_down;
   free(input_vector);
   delete K_contract; delete K_prop_down; delete K_prop_up; delete K_temp; delete K_guess; delete K_vector;
   if (K_gaugeSmeared) delete K_gaugeSmeared;

@@ -30,6 +30,11 @@ def contract_inputs():
     return rng.standard_normal((4, 4, 3, 3, V, 2)), rng.standard_normal((4, 4, 3, 3, V, 2))
 
 
+# sequential-source cases kept in the fixture: key -> (part, projector, particle, source spin, source colour)
+SEQ_CASES = {"seq1_G4_proton_00": (1, 0, 0, 0, 0), "seq1_G5G123_neutron_21": (1, 1, 1, 2, 1), "seq1_G5G2_proton_32": (1, 3, 0, 3, 2),
+             "seq2_G4_proton_11": (2, 0, 0, 1, 1), "seq2_G5G3_neutron_30": (2, 4, 1, 3, 0), "seq2_G5G123_proton_02": (2, 1, 0, 0, 2)}
+
+
 def momenta():
     from oracle.oracle import create_momenta
     return create_momenta(Q_SQ)
@@ -66,6 +71,15 @@ if __name__ == "__main__":
         "baryon_mom_float": r.contract_baryons_mom(f1, f2, baryon_momenta(), SRC),      # what the reference launches (float only)
         "baryon_mom_double": r.contract_baryons_mom(p1, p2, baryon_momenta(), SRC),     # the same body instantiated in double
     }
+    # fixed-sink three-point function: the projector / operator tables, sequential sources and the ultra-local insertion
+    out["proj_tables"] = np.array([[r.projector(pid, part) for part in range(2)] for pid in range(5)])
+    out["op_tables"] = np.array([[[r.operator(f, part, pf) for pf in (1, 2)] for part in range(2)] for f in range(16)])
+    V3 = int(np.prod(X[:3]))
+    t1, t2 = np.ascontiguousarray(p1[..., 2 * V3:3 * V3, :]), np.ascontiguousarray(p2[..., 2 * V3:3 * V3, :])     # 3-d propagators: time slice 2
+    for key, (part, pid, particle, nu, c2) in SEQ_CASES.items():
+        out[key] = r.seq_source(part, 4, t1, t2, nu, c2, pid, particle)[:, 4 * V3:5 * V3]
+    out["thrp_local_double"] = r.fixsink_local(p1, p2, 0, 1, baryon_momenta(), SRC)
+    out["thrp_local_float"] = r.fixsink_local(f1, f2, 1, 1, baryon_momenta(), SRC)
     s1, s2 = small_inputs()
     out["baryon_small_double"] = Ref(X_SMALL).contract_baryons_mom(s1, s2, [(0, 0, 0), (1, 0, -1)], SRC_SMALL)
     np.savez_compressed(FIXTURE, **out)

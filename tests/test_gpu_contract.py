@@ -114,6 +114,52 @@ def test_baryon_contraction_other_shapes_vs_live_reference_kernel(tmq, X, src):
     d.close()
 
 
+def test_sequential_sources_and_local_insertion_match_reference_fixture(tmq):
+    """seqSourceFixSinkPart1 / Part2 and the ultra-local fixed-sink contraction against the reference's kernel bodies (fixture), plus
+    every projector / particle combination against the restatement (pinned to the same kernels by tests/test_ref_contract.py)"""
+    gold = np.load(G.FIXTURE)
+    p1, p2 = G.contract_inputs()
+    X = G.X
+    V = int(np.prod(X)); V3 = V // X[3]
+    d = Dev(tmq, X)
+    t1, t2 = np.ascontiguousarray(p1[..., 2 * V3:3 * V3, :]), np.ascontiguousarray(p2[..., 2 * V3:3 * V3, :])
+    d1, d2 = d.put(t1), d.put(t2)
+    ts = 4
+    for key, (part, pid, particle, nu, c2) in G.SEQ_CASES.items():
+        dv = d.put(np.full((12, V, 2), 7.0))
+        d.c.qkxtm_seq_source(dv, ts, d1, d2 if part == 1 else None, 8, nu, c2, pid, particle, part)
+        got = d.get(dv, (12, V, 2))
+        assert np.all(got[:, :ts * V3] == 7.0) and np.all(got[:, (ts + 1) * V3:] == 7.0)        # only the time slice is written
+        want = _c(gold[key])
+        assert np.abs(_c(got[:, ts * V3:(ts + 1) * V3]) - want).max() / np.abs(want).max() < 1e-13, key
+    for pid in range(5):
+        for particle in range(2):
+            for part, (nu, c2) in ((1, (1, 2)), (2, (2, 0))):
+                dv = d.put(np.zeros((12, V, 2)))
+                d.c.qkxtm_seq_source(dv, 0, d1, d2 if part == 1 else None, 8, nu, c2, pid, particle, part)
+                got = _c(d.get(dv, (12, V, 2)))[:, :V3].reshape(4, 3, V3)
+                want = O.seq_source_part1(_c(t1), _c(t2), nu, c2, pid, particle) if part == 1 else O.seq_source_part2(_c(t1), nu, c2, pid, particle)
+                assert np.abs(got - want).max() / np.abs(want).max() < 1e-13, (pid, particle, part)
+    # float 3-d propagators (what the driver uses)
+    f1, f2 = d.put(t1.astype(np.float32)), d.put(t2.astype(np.float32))
+    dv = d.put(np.zeros((12, V, 2), dtype=np.float32))
+    d.c.qkxtm_seq_source(dv, ts, f1, f2, 4, 0, 0, 0, 0, 1)
+    want = _c(gold["seq1_G4_proton_00"])
+    assert np.abs(_c(d.get(dv, (12, V, 2), np.float32))[:, ts * V3:(ts + 1) * V3] - want).max() / np.abs(want).max() < 1e-5
+    # ultra-local insertion
+    moms = G.baryon_momenta()
+    got = d.c.qkxtm_fixsink_local(d.put(p2), d.put(p1), 8, 0, 1, moms, G.SRC, X[3])            # (seq, fwd) = (p2, p1) as in the fixture call
+    want = _c(gold["thrp_local_double"])
+    assert _relmax(got, want) < 1e-13
+    gotf = d.c.qkxtm_fixsink_local(d.put(p2.astype(np.float32)), d.put(p1.astype(np.float32)), 4, 1, 1, moms, G.SRC, X[3])
+    assert _relmax(gotf, _c(gold["thrp_local_float"]).astype(np.complex128)) < 1e-5
+    for particle in range(2):
+        for pf in (1, 2):
+            got = d.c.qkxtm_fixsink_local(d.bufs[-4], d.bufs[-3], 8, particle, pf, moms[:2], G.SRC, X[3])
+            assert _relmax(got, O.fixsink_local_mom(_c(p1), _c(p2), X, moms[:2], G.SRC, particle, pf)) < 1e-13, (particle, pf)
+    d.close()
+
+
 def test_site_local_propagator_kernels_match_reference_fixture(tmq):
     gold = np.load(G.FIXTURE)
     p1, _ = G.contract_inputs()
@@ -269,3 +315,63 @@ def test_twop_driver_meson_correlators_match_oracle(tmp_path, tmq, nsmear):
     for iu in range(2):
         pion = got[iu][0, :, 0]
         assert np.all(pion.real > 0) and np.abs(pion.imag).max() < 1e-6 * pion.real.max() and np.argmax(pion.real) == 0
+
+
+@pytest.mark.parametrize("particle,proj", [("proton", 0), ("neutron", 3)])
+def test_threep_driver_local_insertion_matches_oracle(tmp_path, tmq, particle, proj):
+    """qkxtm_invert_test --test twop --tsink dt: the fixed-sink three-point function of calcMG_threepTwop_EvenOdd
+    (lib/qudaQKXTM_interface.cpp:764-1170, ultra-local insertion): 24 forward solves, 3-d propagators at the sink, 12 + 12
+    sequential sources -> conjugate, gamma5 -> solve with the other flavour -> K_seqProp -> contractFixSink -> ASCII files.
+    The oracle redoes the whole chain on the CPU with its own CG and the restatements pinned to the reference's kernel bodies."""
+    from oracle.oracle import Oracle
+    o = Oracle(XD)
+    gauge = tmq.gen_gauge(XD, seed=137, t_boundary=-1)
+    src, dt, q_sq = (1, 3, 2, 5), 5, 1           # sink at t = (5 + 5) % 8 = 2: beyond the anti-periodic boundary -> sign flip in the file
+    out = str(tmp_path / "tw")
+    cmd = [DRV, "--dim"] + [str(v) for v in XD] + ["--test", "twop", "--tol", "1e-12", "--recon", "12", "--Q_sq", str(q_sq), "--src"] + \
+          [str(v) for v in src] + ["--tsink", str(dt), "--proj", str(proj), "--particle", particle, "--out", out]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    T = XD[3]; V = int(np.prod(XD)); V3 = V // T
+    moms = O.create_momenta(q_sq)
+    part_id = 0 if particle == "proton" else 1
+    pname = ["G4", "G5G123", "G5G1", "G5G2", "G5G3"][proj]
+    src_lex = ((src[3] * XD[2] + src[2]) * XD[1] + src[1]) * XD[0] + src[0]
+    f32 = lambda z: z.astype(np.complex64).astype(np.complex128)
+    up, dn = f32(_oracle_propagator(o, gauge, src_lex, +MU)), f32(_oracle_propagator(o, gauge, src_lex, -MU))
+    tsink = (src[3] + dt) % T
+    up3, dn3 = up[..., tsink * V3:(tsink + 1) * V3], dn[..., tsink * V3:(tsink + 1) * V3]
+    g5 = O._gamma5_ukqcd()
+    for part in (1, 2):
+        up_line = (particle == "proton") == (part == 1)
+        mu_solve = -MU if up_line else +MU
+        seq = np.zeros((4, 4, 3, 3, V), dtype=np.complex128)
+        for nu in range(4):
+            for c2 in range(3):
+                if part == 1:
+                    a, b = (up3, dn3) if particle == "proton" else (dn3, up3)
+                    s3 = O.seq_source_part1(a, b, nu, c2, proj, part_id)
+                else:
+                    s3 = O.seq_source_part2(up3 if particle == "proton" else dn3, nu, c2, proj, part_id)
+                s3 = f32(s3)                                              # K_temp is a float vector
+                vec = np.zeros((4, 3, V), dtype=np.complex128); vec[:, :, tsink * V3:(tsink + 1) * V3] = np.einsum("ab,bcx->acx", g5, s3.conj())
+                b_lex = lu.c2r(np.transpose(vec, (2, 0, 1)))
+                b_eo = lu.spinor_eo_from_lex(np.ascontiguousarray(b_lex), XD)
+                pc = o.prepare(gauge, b_eo, KAPPA, mu_solve)
+                rhs = o.matpc(gauge, pc, KAPPA, mu_solve, 0, dagger=1)
+                x_pc, _, _, _ = o.cg_mdagm(gauge, rhs, KAPPA, mu_solve, tol=1e-13)
+                xf = np.zeros_like(b_eo); xf[: V // 2] = x_pc
+                o.reconstruct(gauge, xf, b_eo, KAPPA, mu_solve)
+                col = lu.r2c(lu.spinor_lex_from_eo(xf, XD))             # [x][s][c]
+                seq[:, nu, :, c2] = np.transpose(col, (1, 2, 0))
+        seq = f32(seq)
+        fwd = up if up_line else dn
+        want = O.fixsink_local_mom(fwd, seq, XD, moms, src[:3], part_id, part)        # [T][nmoms][16]
+        flavour = "up" if up_line else "down"
+        fname = "%s.threep_tsink%d_proj%s.%s.%s.ultra_local.SS.%02d.%02d.%02d.%02d.dat" % ((out, dt, pname, particle, flavour) + src)
+        rows = np.loadtxt(fname)
+        assert rows.shape == (16 * T * len(moms), 7)
+        got = (rows[:, 5] + 1j * rows[:, 6]).reshape(16, T, len(moms))
+        w = -np.roll(np.transpose(want, (2, 0, 1)), -src[3], axis=1)       # time relative to the source; src_t + dt >= T -> sign -1
+        scale = np.abs(w).max()
+        assert np.abs(got - w).max() / scale < 2e-4, (part, np.abs(got - w).max() / scale)

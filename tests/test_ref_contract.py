@@ -110,3 +110,30 @@ def test_baryon_fixture_matches_live_reference_library(gold):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     s1, s2 = G.small_inputs()
     assert np.array_equal(ref.Ref(G.X_SMALL).contract_baryons_mom(s1, s2, [(0, 0, 0), (1, 0, -1)], G.SRC_SMALL), gold["baryon_small_double"])
+
+
+def test_threep_tables_are_twisted_rotations_of_the_physical_structures(gold):
+    """projectors_tm_base.h = 1/4 (1 + g4)[i g5 g_k] and gammas_tm_base.h = the 16 insertions, both rotated with 1/2 (1 + i s g5) . (1 + i s g5)"""
+    for pid in range(5):
+        for part in range(2):
+            assert np.abs(O.projector_tm(pid, part) - gold["proj_tables"][pid, part]).max() < 1e-15, (pid, part)
+    for f in range(16):
+        for part in range(2):
+            for ipf, pf in enumerate((1, 2)):
+                assert np.abs(O.operator_tm(f, part, pf) - gold["op_tables"][f, part, ipf]).max() < 1e-15, (f, part, pf)
+
+
+def test_sequential_sources_and_local_insertion_match_reference(gold):
+    p1, p2 = G.contract_inputs()
+    V3 = int(np.prod(G.X[:3]))
+    t1, t2 = _c(p1)[..., 2 * V3:3 * V3], _c(p2)[..., 2 * V3:3 * V3]
+    for key, (part, pid, particle, nu, c2) in G.SEQ_CASES.items():
+        want = _c(gold[key]).reshape(4, 3, V3)
+        got = O.seq_source_part1(t1, t2, nu, c2, pid, particle) if part == 1 else O.seq_source_part2(t1, nu, c2, pid, particle)
+        assert np.abs(got - want).max() / np.abs(want).max() < 1e-13, key
+    want = _c(gold["thrp_local_double"])
+    got = O.fixsink_local_mom(_c(p1), _c(p2), G.X, G.baryon_momenta(), G.SRC, 0, 1)
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-13
+    wantf = _c(gold["thrp_local_float"]).astype(np.complex128)
+    gotf = O.fixsink_local_mom(_c(p1), _c(p2), G.X, G.baryon_momenta(), G.SRC, 1, 1)
+    assert np.abs(gotf - wantf).max() / np.abs(wantf).max() < 2e-6
