@@ -261,13 +261,16 @@ public:
                              int c2, WHICHPROJECTOR PID, WHICHPARTICLE testParticle);
   void seqSourceFixSinkPart2(QKXTM_Vector<Float> &vec, QKXTM_Propagator3D<Float> &prop, int timeslice, int nu, int c2, WHICHPROJECTOR PID,
                              WHICHPARTICLE testParticle);
-  // lib/qudaQKXTM_Contraction.cpp:3008-3110, the ULTRA-LOCAL insertion only: corrThp_local Float[T_local * Nmoms * 16 * 2], entry
-  // [it*Nmoms*16*2 + imom*16*2 + iop*2 + ri]; corrThp_noether / corrThp_oneD must be NULL (the conserved-current and one-derivative
-  // insertions are not built); gauge is unused by the local insertion
+  // lib/qudaQKXTM_Contraction.cpp:3008-3110: corrThp_local Float[T_local * Nmoms * 16 * 2], entry [it*Nmoms*16*2 + imom*16*2 + iop*2 + ri];
+  // corrThp_noether Float[T_local * Nmoms * 4 * 2] (entry [.. + dir*2 + ri]) and corrThp_oneD Float[T_local * Nmoms * 4 * 16 * 2] (entry
+  // [.. + dir*16*2 + iop*2 + ri]) may both be NULL (ultra-local insertion only); when given, gauge must hold the links on the device
+  // and the lattice must not be split (the conserved-current and one-derivative insertions read the neighbours' propagators)
   void contractFixSink(QKXTM_Propagator<Float> &seqProp, QKXTM_Propagator<Float> &prop, QKXTM_Gauge<Float> &gauge, void *corrThp_local,
                        void *corrThp_noether, void *corrThp_oneD, WHICHPROJECTOR typeProj, WHICHPARTICLE testParticle, int partflag, int isource,
                        CORR_SPACE CorrSpace);
-  // "<filename_out>.<proton|neutron>.<up|down>.ultra_local.SS.xx.yy.zz.tt.dat": "iop it px py pz re im" (lib/qudaQKXTM_Contraction.cpp:2842-2960)
+  // "<filename_out>.<proton|neutron>.<up|down>.{ultra_local,noether,oneD}.SS.xx.yy.zz.tt.dat": "iop it px py pz re im" (ultra_local and
+  // noether, iop = direction there) and "iop dir it px py pz re im" (oneD), lib/qudaQKXTM_Contraction.cpp:2842-3000; the noether and oneD
+  // files are written when their buffers are given
   void writeThrp_ASCII(void *corrThp_local, void *corrThp_noether, void *corrThp_oneD, WHICHPARTICLE testParticle, int partflag, char *filename_out,
                        int isource, int tsinkMtsource, CORR_SPACE CorrSpace);
 };
@@ -361,6 +364,11 @@ void ApplyMdagM(double *h_out, double *h_in, QudaInvertParam *param, bool isEven
 // are refused.
 void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param,
                                quda::qudaQKXTMinfo info, char *filename_twop, char *filename_threep, quda::WHICHPARTICLE NUCLEON);
+
+// calcLowModeProjection (include/qudaQKXTM.h:508-510, lib/qudaQKXTM_interface.cpp:1342-1401): the low modes of M^dag M through
+// QKXTM_Deflation::eigenSolver, with the reference's consistency checks (asymmetric operators only, parity of the operator and of
+// arpackInfo must agree).  Returns nothing, like the reference; nconv / evals (optional, not in the reference) report the result.
+void calcLowModeProjection(QudaInvertParam *evInvParam, quda::qudaQKXTM_arpackInfo arpackInfo, int *nconv = nullptr, double *evals = nullptr);
 
 // ---- configuration I/O (include/QKXTM_read_conf.h:816-848) -----------------------------------------------------------
 // reads this rank's sub-block of an ILDG / LIME configuration into the QDP even-odd host order of loadGaugeQuda and sets

@@ -244,6 +244,13 @@ int tmq_qkxtm_seq_source(tmq_ctx *, void *d_vec_out, int timeslice, const void *
  * partflag 1 | 2 selects the rotation sign together with the particle, as in the reference.                                        */
 int tmq_qkxtm_fixsink_local(tmq_ctx *, const void *d_seq_prop, const void *d_fwd_prop, int prec, int particle, int partflag, const int *moms,
                             int nmoms, const int src_pos[3], double *corr_mom);
+/* the conserved-current (Noether) and one-derivative parts of contractFixSink (kernel bodies fixSinkContractions_noether_core.h,
+ * fixSinkContractions_oneD_core.h): d_gauge is the QKXTM gauge container d[((dir*3+c1)*3+c2)*V + x] of the links the current is built
+ * from.  corr_noether (host): [t][imom][dir][re,im]; corr_oneD (host): [t][imom][dir][iop][re,im] (the reference's
+ * corrThp_oneD[it*Nmoms*4*16*2 + imom*4*16*2 + dir*16*2 + iop*2 + ri], lib/qudaQKXTM_kernels.cu:1694-1712), both with the reference's
+ * 1/4.  Periodic neighbours on this rank only: refused on a split lattice (the reference exchanges propagator ghost zones).      */
+int tmq_qkxtm_fixsink_derivative(tmq_ctx *, const void *d_seq_prop, const void *d_fwd_prop, const void *d_gauge, int prec, int particle, int partflag,
+                                 const int *moms, int nmoms, const int src_pos[3], double *corr_noether, double *corr_oneD);
 
 /* ---- raw device memory for the containers (QKXTM_Field::create_device, lib/qudaQKXTM_Field.cpp:172) ----- */
 int tmq_dev_malloc(tmq_ctx *, void **ptr, size_t bytes);

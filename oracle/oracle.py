@@ -486,3 +486,47 @@ def fixsink_local_mom(fwd, seq, X, moms, src, particle, partflag):
         ph = np.exp(+2j * np.pi * (pz * z[:, None, None] / Zd + py * y[None, :, None] / Yd + px * x[None, None, :] / Xd))
         out[:, im] = np.einsum("otzyx,zyx->to", c, ph)
     return out
+
+
+def fixsink_derivative_site(fwd, seq, gauge, X, particle, partflag):
+    """Conserved-current (Noether) and one-derivative insertions of the fixed-sink three-point function
+    (lib/code_pieces/fixSinkContractions_noether_core.h:117-147, fixSinkContractions_oneD_core.h:100-134), single rank, periodic.
+    With the four hop blocks per direction d (spin matrices [k][l], colours and the source spin summed)
+        Af = S(x) U_d(x) F(x+d),   Ab = S(x) U_d(x-d)^dag F(x-d),   Bf = S(x+d) U_d(x)^dag F(x),   Bb = S(x-d) U_d(x-d) F(x)
+    noether[d] = 1/4 { tr[(1+g_d)^T (Ab + Bf)] - tr[(1-g_d)^T (Af + Bb)] },   oneD[iop][d] = 1/4 tr[Gamma_iop^T (Af - Ab - Bf + Bb)]
+    (the 1/4 is applied when the block sums are stored, noether_core.h:162, oneD_core.h:167).
+    fwd / seq [4][4][3][3][V] complex, gauge [4][3][3][V] complex -> noether [4][V], oneD [16][4][V]"""
+    Xd, Yd, Zd, Td = X
+    g = gamma_ukqcd()
+    F = fwd.reshape(4, 4, 3, 3, Td, Zd, Yd, Xd); S = seq.reshape(4, 4, 3, 3, Td, Zd, Yd, Xd); U = gauge.reshape(4, 3, 3, Td, Zd, Yd, Xd)
+    noether = np.empty((4,) + F.shape[4:], dtype=np.complex128)
+    oneD = np.empty((16, 4) + F.shape[4:], dtype=np.complex128)
+    ops = [operator_tm(i, particle, partflag) for i in range(16)]
+    for d, ax in enumerate((-1, -2, -3, -4)):                # x, y, z, t axes (counted from the end: the same for every array)
+        up = lambda A: np.roll(A, -1, axis=ax)               # A(x + d)
+        dn = lambda A: np.roll(A, +1, axis=ax)               # A(x - d)
+        Ud = U[d]; Udm = dn(Ud)                              # U_d(x - d)
+        Af = np.einsum("kpab...,ac...,lpcb...->kl...", S, Ud, up(F), optimize=True)
+        Ab = np.einsum("kpab...,ca...,lpcb...->kl...", S, Udm.conj(), dn(F), optimize=True)
+        Bf = np.einsum("kpab...,ca...,lpcb...->kl...", up(S), Ud.conj(), F, optimize=True)
+        Bb = np.einsum("kpab...,ac...,lpcb...->kl...", dn(S), Udm, F, optimize=True)
+        onePg, oneMg = np.eye(4) + g[d], np.eye(4) - g[d]    # operators 16+d / 20+d of gammas_tm_base.h: not rotated
+        noether[d] = 0.25 * (np.einsum("kl,kl...->...", onePg, Ab + Bf) - np.einsum("kl,kl...->...", oneMg, Af + Bb))
+        D = 0.25 * (Af - Ab - Bf + Bb)
+        for i in range(16):
+            oneD[i, d] = np.einsum("kl,kl...->...", ops[i], D)
+    return noether.reshape(4, -1), oneD.reshape(16, 4, -1)
+
+
+def fixsink_derivative_mom(fwd, seq, gauge, X, moms, src, particle, partflag):
+    """... projected with exp(+2 pi i p.(x - src)/L) -> noether [T][nmoms][4], oneD [T][nmoms][4 dir][16 iop] complex"""
+    Xd, Yd, Zd, Td = X
+    n, o = fixsink_derivative_site(fwd, seq, gauge, X, particle, partflag)
+    n = n.reshape(4, Td, Zd, Yd, Xd); o = o.reshape(16, 4, Td, Zd, Yd, Xd)
+    x = np.arange(Xd) - src[0]; y = np.arange(Yd) - src[1]; z = np.arange(Zd) - src[2]
+    out_n = np.empty((Td, len(moms), 4), dtype=np.complex128); out_o = np.empty((Td, len(moms), 4, 16), dtype=np.complex128)
+    for im, (px, py, pz) in enumerate(moms):
+        ph = np.exp(+2j * np.pi * (pz * z[:, None, None] / Zd + py * y[None, :, None] / Yd + px * x[None, None, :] / Xd))
+        out_n[:, im] = np.einsum("dtzyx,zyx->td", n, ph)
+        out_o[:, im] = np.einsum("idtzyx,zyx->tdi", o, ph)
+    return out_n, out_o

@@ -42,6 +42,7 @@ def lib():
         L.qref_seq_source_part2_double.argtypes = [dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.qref_fixsink_local_float.argtypes = [fp, fp, fp, C.c_int, C.c_int, ip]
         L.qref_fixsink_local_double.argtypes = [dp, dp, dp, C.c_int, C.c_int, ip]
+        L.qref_fixsink_derivative_double.argtypes = [dp, dp, dp, dp, dp, C.c_int, C.c_int, ip]
         L.qref_get_projector.argtypes = [dp, C.c_int, C.c_int]
         L.qref_get_operator.argtypes = [dp, C.c_int, C.c_int, C.c_int]
         L.qref_contract_baryons_mom_float.argtypes = [fp, fp, fp, ip]
@@ -178,6 +179,14 @@ class Ref:
         else:
             self.L.qref_fixsink_local_double(_dp(out), _dp(fwd), _dp(seq), particle, partflag, s)
         return out
+
+    def fixsink_derivative(self, fwd, seq, gauge, particle, partflag, moms, src):
+        """Noether and one-derivative parts of contractFixSink (double): -> ([T][nmoms][4][2], [T][nmoms][4 dir][16 iop][2])"""
+        m = np.ascontiguousarray(np.asarray(moms, dtype=np.int32).reshape(-1, 3))
+        self.L.qref_set_momenta(m.ctypes.data_as(C.POINTER(C.c_int)), len(m))
+        n = np.zeros((self.X[3], len(m), 4, 2)); o = np.zeros((self.X[3], len(m), 4, 16, 2))
+        self.L.qref_fixsink_derivative_double(_dp(n), _dp(o), _dp(fwd), _dp(seq), _dp(gauge), particle, partflag, (C.c_int * 3)(*[int(v) for v in src]))
+        return n, o
 
     def contract_mesons_pos(self, prop1, prop2):
         """contractMesons, POSITION_SPACE (float): -> [T][V3][2][10][re,im]"""

@@ -500,3 +500,78 @@ extern "C" void qref_get_operator(double *out32, int flag, int particle, int par
   get_Operator(g, flag, (WHICHPARTICLE)particle, partflag);
   for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { out32[(i * 4 + j) * 2] = g[i][j].x; out32[(i * 4 + j) * 2 + 1] = g[i][j].y; }
 }
+
+// ---- conserved-current (Noether) and one-derivative insertions (lib/qudaQKXTM_kernels.cu:676-760, launcher :1636-1715) -------------
+// single rank: c_dimBreak is false in every direction, so the bodies take their periodic "Str" paths (no ghost zones)
+#define __shared__ static
+#define __syncthreads() pthread_barrier_wait(&g_block_barrier)
+static void noether_double_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, double2 *block, texd_t fwdTex, texd_t seqTex, texd_t gaugeTex,
+                                WHICHPARTICLE TESTPARTICLE, int partflag, int it, int x0, int y0, int z0) {
+#define FLOAT2 double2
+#define FLOAT double
+#define FETCH_FLOAT2 fetch_double2
+#include <fixSinkContractions_noether_core.h>
+#undef PROP
+#undef GAUGE
+#undef PROPplusSur
+#undef PROPminusSur
+#undef GAUGEminusSur
+#undef PROPplusStr
+#undef PROPminusStr
+#undef GAUGEminusStr
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+static void oneD_double_body(dim3_ blockIdx, dim3_ blockDim, dim3_ threadIdx, dim3_ gridDim, double2 *block, texd_t fwdTex, texd_t seqTex, texd_t gaugeTex,
+                             WHICHPARTICLE TESTPARTICLE, int partflag, int it, int dir, int x0, int y0, int z0) {
+#define FLOAT2 double2
+#define FLOAT double
+#define FETCH_FLOAT2 fetch_double2
+#include <fixSinkContractions_oneD_core.h>
+#undef PROP
+#undef GAUGE
+#undef PROPplusSur
+#undef PROPminusSur
+#undef GAUGEminusSur
+#undef PROPplusStr
+#undef PROPminusStr
+#undef GAUGEminusStr
+#undef FETCH_FLOAT2
+#undef FLOAT2
+#undef FLOAT
+}
+#undef __syncthreads
+#undef __shared__
+// noether: out_n[it][imom][dir][re,im]; oneD: out_d[it][imom][dir][iop][re,im] (the reference's corrThp_oneD[it*Nmoms*4*16*2 + imom*4*16*2 +
+// dir*16*2 + iop*2 + ri], lib/qudaQKXTM_kernels.cu:1694-1712)
+extern "C" void qref_fixsink_derivative_double(double *out_n, double *out_d, const double *fwd, const double *seq, const double *gauge, int particle,
+                                               int partflag, const int src[3]) {
+  const int SpVol = c_threads / c_localL[3];
+  const int grid = (SpVol + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK;
+  std::vector<double> h((size_t)c_Nmoms * 16 * grid * 2);
+  for (int it = 0; it < c_localL[3]; it++) {
+    run_grid(grid, [&](dim3_ b, dim3_ d, dim3_ t, dim3_ g) {
+      noether_double_body(b, d, t, g, (double2 *)h.data(), (texd_t)fwd, (texd_t)seq, (texd_t)gauge, (WHICHPARTICLE)particle, partflag, it, src[0], src[1], src[2]);
+    });
+    for (int imom = 0; imom < c_Nmoms; imom++)
+      for (int dir = 0; dir < 4; dir++) {
+        double re = 0, im = 0;
+        for (int i = 0; i < grid; i++) { re += h[((size_t)imom * 4 * grid + (size_t)dir * grid + i) * 2]; im += h[((size_t)imom * 4 * grid + (size_t)dir * grid + i) * 2 + 1]; }
+        double *o = out_n + (((size_t)it * c_Nmoms + imom) * 4 + dir) * 2;
+        o[0] = re; o[1] = im;
+      }
+    for (int dir = 0; dir < 4; dir++) {
+      run_grid(grid, [&](dim3_ b, dim3_ d, dim3_ t, dim3_ g) {
+        oneD_double_body(b, d, t, g, (double2 *)h.data(), (texd_t)fwd, (texd_t)seq, (texd_t)gauge, (WHICHPARTICLE)particle, partflag, it, dir, src[0], src[1], src[2]);
+      });
+      for (int imom = 0; imom < c_Nmoms; imom++)
+        for (int iop = 0; iop < 16; iop++) {
+          double re = 0, im = 0;
+          for (int i = 0; i < grid; i++) { re += h[((size_t)imom * 16 * grid + (size_t)iop * grid + i) * 2]; im += h[((size_t)imom * 16 * grid + (size_t)iop * grid + i) * 2 + 1]; }
+          double *o = out_d + ((((size_t)it * c_Nmoms + imom) * 4 + dir) * 16 + iop) * 2;
+          o[0] = re; o[1] = im;
+        }
+    }
+  }
+}

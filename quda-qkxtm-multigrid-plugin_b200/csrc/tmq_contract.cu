@@ -427,6 +427,103 @@ __global__ void __launch_bounds__(CT_BLOCK) fixsink_local_site_kernel(CplxT<doub
   }
 }
 
+// conserved-current (Noether) and one-derivative insertions (lib/code_pieces/fixSinkContractions_{noether,oneD}_core.h; formulas in
+// oracle.fixsink_derivative_site, pinned to the reference's kernel bodies).  Per site and direction d the four hop blocks
+//   Af = S(x) U_d(x) F(x+d),  Ab = S(x) U_d(x-d)^dag F(x-d),  Bf = S(x+d) U_d(x)^dag F(x),  Bb = S(x-d) U_d(x-d) F(x)
+// (4x4 spin matrices; colours and the source spin summed) only enter as P = Ab + Bf and Q = Af + Bb:
+//   noether[d] = 1/4 ( tr[(1+g_d)^T P] - tr[(1-g_d)^T Q] ),     oneD[iop][d] = 1/4 tr[Gamma_iop^T (Q - P)].
+// One thread per (site, direction); periodic neighbours on this rank (the entry point refuses a split lattice).
+struct DerivTables { double pg_re[4][16], pg_im[4][16], mg_re[4][16], mg_im[4][16]; };     // (1 + g_d)[k*4+l], (1 - g_d)[k*4+l]
+__constant__ DerivTables c_deriv;
+
+// M[k][l] += sum_{p, a, b, c} S[k,p]^{ab} V^{ac} F[l,p]^{cb},  V = U (DAG = false) or U^dag (DAG = true); S, F, U point at the sites to use
+template <typename F, bool DAG>
+__device__ __forceinline__ void hop_block(Cx<F> (&M)[4][4], const CplxT<F> *__restrict__ S, const CplxT<F> *__restrict__ Fw, const CplxT<F> *__restrict__ U,
+                                          size_t V) {
+  Cx<F> u[3][3];                                            // V^{ac}
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const CplxT<F> g = DAG ? U[(size_t)(c * 3 + a) * V] : U[(size_t)(a * 3 + c) * V];
+      u[a][c] = {g.re, DAG ? -g.im : g.im};
+    }
+#pragma unroll 1
+  for (int pb = 0; pb < 12; pb++) {
+    const int p = pb / 3, b = pb - p * 3;
+    Cx<F> W[4][3];                                          // W[l][a] = sum_c V^{ac} F[l,p]^{cb}
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      Cx<F> f[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) { const CplxT<F> v = Fw[((size_t)(l * 4 + p) * 9 + c * 3 + b) * V]; f[c] = {v.re, v.im}; }
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        W[l][a] = {0, 0};
+#pragma unroll
+        for (int c = 0; c < 3; c++) cmac(W[l][a], u[a][c], f[c]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      Cx<F> sv[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) { const CplxT<F> v = S[((size_t)(k * 4 + p) * 9 + a * 3 + b) * V]; sv[a] = {v.re, v.im}; }
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+#pragma unroll
+        for (int a = 0; a < 3; a++) cmac(M[k][l], sv[a], W[l][a]);
+    }
+  }
+}
+
+// csite[ch][nsites]: ch = d (noether), 4 + d*16 + iop (oneD); sites site0 .. site0 + nsites - 1 of the local lattice
+template <typename F>
+__global__ void __launch_bounds__(CT_BLOCK) fixsink_deriv_site_kernel(CplxT<double> *__restrict__ csite, const CplxT<F> *__restrict__ fwd,
+                                                                     const CplxT<F> *__restrict__ seq, const CplxT<F> *__restrict__ gauge, size_t V,
+                                                                     size_t site0, size_t nsites, int X0, int X1, int X2, int X3) {
+  const size_t i = (size_t)blockIdx.x * CT_BLOCK + threadIdx.x;
+  if (i >= nsites) return;
+  const int d = blockIdx.y;
+  const size_t x = site0 + i;
+  const int L[4] = {X0, X1, X2, X3};
+  const size_t str[4] = {1, (size_t)X0, (size_t)X0 * X1, (size_t)X0 * X1 * X2};
+  const int cd_ = (int)((x / str[d]) % L[d]);
+  const size_t xp = cd_ == L[d] - 1 ? x - (size_t)(L[d] - 1) * str[d] : x + str[d];
+  const size_t xm = cd_ == 0 ? x + (size_t)(L[d] - 1) * str[d] : x - str[d];
+  const CplxT<F> *Ud = gauge + (size_t)d * 9 * V;
+  Cx<F> P[4][4], Q[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int l = 0; l < 4; l++) { P[k][l] = {0, 0}; Q[k][l] = {0, 0}; }
+  hop_block<F, false>(Q, seq + x, fwd + xp, Ud + x, V);      // Af
+  hop_block<F, false>(Q, seq + xm, fwd + x, Ud + xm, V);     // Bb
+  hop_block<F, true>(P, seq + x, fwd + xm, Ud + xm, V);      // Ab
+  hop_block<F, true>(P, seq + xp, fwd + x, Ud + x, V);       // Bf
+  Cx<double> n = {0, 0};
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int q = k * 4 + l;
+      cmac<double>(n, {c_deriv.pg_re[d][q], c_deriv.pg_im[d][q]}, {(double)P[k][l].re, (double)P[k][l].im});
+      cmac<double>(n, {-c_deriv.mg_re[d][q], -c_deriv.mg_im[d][q]}, {(double)Q[k][l].re, (double)Q[k][l].im});
+    }
+  CplxT<double> o; o.re = 0.25 * n.re; o.im = 0.25 * n.im;
+  csite[(size_t)d * nsites + i] = o;
+  for (int iop = 0; iop < 16; iop++) {
+    Cx<double> acc = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+        cmac<double>(acc, {c_ops.re[iop][k * 4 + l], c_ops.im[iop][k * 4 + l]}, {(double)Q[k][l].re - (double)P[k][l].re, (double)Q[k][l].im - (double)P[k][l].im});
+    o.re = 0.25 * acc.re; o.im = 0.25 * acc.im;
+    csite[(size_t)(4 + d * 16 + iop) * nsites + i] = o;
+  }
+}
+
 // ---- one axis of the separable Fourier sum -----------------------------------------------------------------------------
 // in [ch][parent][outer][L] (L fastest) -> out[ch][child][outer]:  out = sum_k tab[q][k] in[.., k] for every entry q of the parent's
 // child list (child_start / child_out); one warp per input row, lanes stride the row, fixed-order shuffle tree.
@@ -964,6 +1061,68 @@ int tmq_qkxtm_fixsink_local(tmq_ctx *c, const void *d_seq_prop, const void *d_fw
   TMQ_TRY(mp.upload_tables(ws, st));
   TMQ_TRY(mp.project(ws, csite, 16, 0, T, corr_mom, st));
   TMQ_TRY(allreduce_host(c, ws, o_glob, corr_mom, ntot, st));
+  return 0;
+}
+
+int tmq_qkxtm_fixsink_derivative(tmq_ctx *c, const void *d_seq_prop, const void *d_fwd_prop, const void *d_gauge, int prec, int particle, int partflag,
+                                 const int *moms, int nmoms, const int src_pos[3], double *corr_noether, double *corr_oneD) {
+  TMQ_REQUIRE(c && d_seq_prop && d_fwd_prop && d_gauge && moms && src_pos && corr_noether && corr_oneD, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(nmoms > 0, "empty momentum list");
+  TMQ_REQUIRE((particle == 0 || particle == 1) && (partflag == 1 || partflag == 2), "bad particle / part");
+  TMQ_REQUIRE(c->nranks == 1 && !c->g.part[2] && !c->g.part[3], "the derivative insertions need the neighbours' propagators: not built for a split lattice");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  static OpTables ops;
+  static DerivTables der;
+  cudaStream_t st = c->stream;
+  TMQ_CUDA(cudaStreamSynchronize(st));                   // a previous call's uploads of the static tables have completed
+  operator_tables(&ops, particle, partflag);
+  {
+    Mat4 g[5];
+    ukqcd_gammas(g);
+    for (int d = 0; d < 4; d++)
+      for (int k = 0; k < 4; k++)
+        for (int l = 0; l < 4; l++) {          // operators 16+d / 20+d of gammas_tm_base.h: 1 +- g_d, not rotated
+          const cd one = k == l ? 1.0 : 0.0;
+          der.pg_re[d][k * 4 + l] = (one + g[d].m[k][l]).real(); der.pg_im[d][k * 4 + l] = (one + g[d].m[k][l]).imag();
+          der.mg_re[d][k * 4 + l] = (one - g[d].m[k][l]).real(); der.mg_im[d][k * 4 + l] = (one - g[d].m[k][l]).imag();
+        }
+  }
+  TMQ_CUDA(cudaMemcpyToSymbolAsync(c_ops, &ops, sizeof(ops), 0, cudaMemcpyHostToDevice, st));
+  TMQ_CUDA(cudaMemcpyToSymbolAsync(c_deriv, &der, sizeof(der), 0, cudaMemcpyHostToDevice, st));
+  const int X = c->g.X[0], Y = c->g.X[1], Z = c->g.X[2], T = c->g.X[3];
+  const size_t V = (size_t)2 * c->g.Vh, V3 = (size_t)X * Y * Z;
+  TMQ_REQUIRE(X <= 32 * DFT_MAXK && Y <= 32 * DFT_MAXK && Z <= 32 * DFT_MAXK, "spatial extent above %d not supported", 32 * DFT_MAXK);
+  const int NCH = 68;                                    // 4 noether + 4 x 16 one-derivative
+  int nt = (int)(((size_t)2 << 30) / (V3 * NCH * sizeof(CplxT<double>)));
+  if (nt < 1) nt = 1;
+  if (nt > T) nt = T;
+  MomProjector mp;
+  mp.build(c, moms, nmoms, src_pos, +1);
+  WsPlan plan;
+  const size_t o_csite = plan.add((size_t)nt * V3 * NCH * sizeof(CplxT<double>));
+  mp.plan(plan, NCH, nt);
+  TMQ_TRY(ensure_contract_ws(c, plan.total));
+  char *ws = (char *)c->contract_ws;
+  CplxT<double> *csite = (CplxT<double> *)(ws + o_csite);
+  TMQ_TRY(mp.upload_tables(ws, st));
+  std::vector<double> corr((size_t)T * nmoms * NCH * 2, 0.0);
+  for (int t0 = 0; t0 < T; t0 += nt) {
+    const int n = t0 + nt <= T ? nt : T - t0;
+    const size_t nsites = (size_t)n * V3, site0 = (size_t)t0 * V3;
+    const dim3 grid((unsigned int)((nsites + CT_BLOCK - 1) / CT_BLOCK), 4);
+    if (prec == 8) fixsink_deriv_site_kernel<double><<<grid, CT_BLOCK, 0, st>>>(csite, (const CplxT<double> *)d_fwd_prop, (const CplxT<double> *)d_seq_prop, (const CplxT<double> *)d_gauge, V, site0, nsites, X, Y, Z, T);
+    else fixsink_deriv_site_kernel<float><<<grid, CT_BLOCK, 0, st>>>(csite, (const CplxT<float> *)d_fwd_prop, (const CplxT<float> *)d_seq_prop, (const CplxT<float> *)d_gauge, V, site0, nsites, X, Y, Z, T);
+    TMQ_CUDA(cudaGetLastError());
+    c->launches++;
+    TMQ_TRY(mp.project(ws, csite, NCH, t0, n, corr.data(), st));
+  }
+  for (int t = 0; t < T; t++)
+    for (int m = 0; m < nmoms; m++) {
+      const double *src = &corr[(((size_t)t * nmoms + m) * NCH) * 2];
+      for (int q = 0; q < 8; q++) corr_noether[(((size_t)t * nmoms + m) * 4) * 2 + q] = src[q];
+      for (int q = 0; q < 128; q++) corr_oneD[(((size_t)t * nmoms + m) * 64) * 2 + q] = src[8 + q];
+    }
   return 0;
 }
 

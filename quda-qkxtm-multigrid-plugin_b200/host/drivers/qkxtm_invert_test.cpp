@@ -178,6 +178,16 @@ int main(int argc, char **argv) {
     result.insert(result.end(), K_defl.H_elem(), K_defl.H_elem() + (size_t)V * 24);
     inv_param.iter = deflation->MatVecs();
     delete deflation;
+  } else if (test == "lowmodes") {
+    // qkxtm/CalcLowModeProjection.cpp main(): the low modes of the asymmetric even-odd M^dag M
+    qudaQKXTM_arpackInfo ai;
+    memset(&ai, 0, sizeof(ai));
+    ai.PolyDeg = polydeg; ai.nEv = nev; ai.nKv = nkv; ai.spectrumPart = SR; ai.isACC = polydeg > 0;
+    ai.tolArpack = eig_tol; ai.maxIterArpack = 1000; ai.amin = amin; ai.amax = amax; ai.isEven = info.isEven; ai.isFullOp = false;
+    int nconv = 0;
+    result.resize(nev);
+    calcLowModeProjection(&inv_param, ai, &nconv, result.data());
+    inv_param.iter = nconv;
   } else if (test == "mgbench" || test == "twop") {
     // lexicographic copy of the links for the plaquette print (gauge_Plaq in the drivers): unit test uses the
     // same synthetic field reordered even-odd -> lexicographic
@@ -201,7 +211,7 @@ int main(int argc, char **argv) {
       std::vector<char> f2(base.begin(), base.end()); f2.push_back(0);
       std::string base3 = base + ".threep";
       std::vector<char> f3(base3.begin(), base3.end()); f3.push_back(0);
-      calcMG_threepTwop_EvenOdd((void **)glex, (void **)gauge, &gauge_param, &inv_param, info, f2.data(), f3.data(), particle == "neutron" ? NEUTRON : PROTON);
+      calcMG_threepTwop_EvenOdd((void **)glex, (void **)glex, &gauge_param, &inv_param, info, f2.data(), f3.data(), particle == "neutron" ? NEUTRON : PROTON);   // both in the lexicographic layout of packGauge
     }
   } else { usage(); return 2; }
 

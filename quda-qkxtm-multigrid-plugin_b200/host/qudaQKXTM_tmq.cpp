@@ -665,9 +665,9 @@ template <typename Float>
 void QKXTM_Contraction<Float>::contractFixSink(QKXTM_Propagator<Float> &seqProp, QKXTM_Propagator<Float> &prop, QKXTM_Gauge<Float> &gauge,
                                                void *corrThp_local, void *corrThp_noether, void *corrThp_oneD, WHICHPROJECTOR typeProj,
                                                WHICHPARTICLE testParticle, int partflag, int isource, CORR_SPACE CorrSpace) {
-  (void)gauge; (void)typeProj;
+  (void)typeProj;
   if (!corrThp_local) errorQuda("null correlator buffer");
-  if (corrThp_noether || corrThp_oneD) errorQuda("contractFixSink: the Noether and one-derivative insertions are not built (pass NULL)");
+  if ((corrThp_noether == NULL) != (corrThp_oneD == NULL)) errorQuda("contractFixSink: give both the Noether and the one-derivative buffer, or neither");
   if (CorrSpace != MOMENTUM_SPACE) errorQuda("contractFixSink: only MOMENTUM_SPACE is built");
   if (isource < 0 || (size_t)isource * 4 >= G.sourcePosition.size()) errorQuda("source %d was not given to init_qudaQKXTM", isource);
   printfQuda("contractFixSink: Will perform in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
@@ -678,20 +678,30 @@ void QKXTM_Contraction<Float>::contractFixSink(QKXTM_Propagator<Float> &seqProp,
                                  &G.sourcePosition[(size_t)isource * 4], mom.data()));
   Float *out = (Float *)corrThp_local;
   for (size_t i = 0; i < (size_t)Lt * nm * 32; i++) out[i] = (Float)mom[(size_t)G.coord[3] * Lt * nm * 32 + i];
+  if (corrThp_noether) {
+    if (!gauge.D_elem()) errorQuda("contractFixSink: the Noether and one-derivative insertions need the gauge links on the device");
+    std::vector<double> cn((size_t)Lt * nm * 4 * 2), co((size_t)Lt * nm * 64 * 2);
+    TMQ_OK(tmq_qkxtm_fixsink_derivative(G.ctx, seqProp.D_elem(), prop.D_elem(), gauge.D_elem(), (int)sizeof(Float), (int)testParticle, partflag,
+                                        G.moms.data(), nm, &G.sourcePosition[(size_t)isource * 4], cn.data(), co.data()));
+    for (size_t i = 0; i < cn.size(); i++) ((Float *)corrThp_noether)[i] = (Float)cn[i];
+    for (size_t i = 0; i < co.size(); i++) ((Float *)corrThp_oneD)[i] = (Float)co[i];
+  }
 }
 template <typename Float>
 void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrThp_noether, void *corrThp_oneD, WHICHPARTICLE testParticle, int partflag,
                                                char *filename_out, int isource, int tsinkMtsource, CORR_SPACE CorrSpace) {
   if (CorrSpace != MOMENTUM_SPACE) errorQuda("writeThrp_ASCII: Supports writing only in momentum-space!");
-  if (corrThp_noether || corrThp_oneD) errorQuda("writeThrp_ASCII: the Noether and one-derivative insertions are not built (pass NULL)");
+  if ((corrThp_noether == NULL) != (corrThp_oneD == NULL)) errorQuda("writeThrp_ASCII: give both the Noether and the one-derivative buffer, or neither");
   if (G.grid[3] != 1) errorQuda("writeThrp_ASCII: gather the time ranks' buffers first (single rank in t here)");
   if (partflag != 1 && partflag != 2) errorQuda("writeThrp_ASCII: Got the wrong part! Should be either 1 or 2.");
   printfQuda("writeThrp_ASCII: Will write in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
   const char *particle = testParticle == PROTON ? "proton" : "neutron";
   const char *flavour = (testParticle == PROTON) == (partflag == 1) ? "up" : "down";          // Contraction.cpp:2903-2914
   const int *sp = &G.sourcePosition[(size_t)isource * 4];
-  char fname_local[1024];
+  char fname_local[1024], fname_noether[1024], fname_oneD[1024];
   snprintf(fname_local, sizeof(fname_local), "%s.%s.%s.%s.SS.%02d.%02d.%02d.%02d.dat", filename_out, particle, flavour, "ultra_local", sp[0], sp[1], sp[2], sp[3]);
+  snprintf(fname_noether, sizeof(fname_noether), "%s.%s.%s.%s.SS.%02d.%02d.%02d.%02d.dat", filename_out, particle, flavour, "noether", sp[0], sp[1], sp[2], sp[3]);
+  snprintf(fname_oneD, sizeof(fname_oneD), "%s.%s.%s.%s.SS.%02d.%02d.%02d.%02d.dat", filename_out, particle, flavour, "oneD", sp[0], sp[1], sp[2], sp[3]);
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
   if (!root) return;
@@ -710,6 +720,28 @@ void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrTh
                 sign * (double)c[k + 1]);
       }
   fclose(ptr_local);
+  if (!corrThp_noether) return;
+  const Float *cn = (const Float *)corrThp_noether, *co = (const Float *)corrThp_oneD;
+  FILE *ptr_noether = fopen(fname_noether, "w"), *ptr_oneD = fopen(fname_oneD, "w");
+  if (ptr_noether == NULL || ptr_oneD == NULL) errorQuda("Error opening file for writing");
+  const int sign = (tsinkMtsource + sp[3]) >= T ? -1 : +1;
+  for (int iop = 0; iop < 4; iop++)                                        // :2960-2975 (iop = direction)
+    for (int it = 0; it < T; it++)
+      for (int imom = 0; imom < nm; imom++) {
+        const size_t k = ((size_t)((it + sp[3]) % T) * nm + imom) * 8 + iop * 2;
+        fprintf(ptr_noether, "%d \t %d \t %+d %+d %+d \t %+e %+e\n", iop, it, mv[3 * imom], mv[3 * imom + 1], mv[3 * imom + 2], sign * (double)cn[k],
+                sign * (double)cn[k + 1]);
+      }
+  for (int iop = 0; iop < 16; iop++)                                       // :2976-2995
+    for (int dir = 0; dir < 4; dir++)
+      for (int it = 0; it < T; it++)
+        for (int imom = 0; imom < nm; imom++) {
+          const size_t k = ((size_t)((it + sp[3]) % T) * nm + imom) * 128 + dir * 32 + iop * 2;
+          fprintf(ptr_oneD, "%d \t %d \t %d \t %+d %+d %+d \t %+e %+e\n", iop, dir, it, mv[3 * imom], mv[3 * imom + 1], mv[3 * imom + 2],
+                  sign * (double)co[k], sign * (double)co[k + 1]);
+        }
+  fclose(ptr_noether);
+  fclose(ptr_oneD);
 }
 
 // ---- QKXTM_Deflation ----------------------------------------------------------------------------------------------------
@@ -912,7 +944,6 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
 
 void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, qudaQKXTMinfo info,
                                char *filename_twop, char *filename_threep, WHICHPARTICLE NUCLEON) {
-  (void)gauge;
   if (!param || !gauge_param || !filename_twop) errorQuda("null argument");
   check_solver(param);
   if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
@@ -955,7 +986,19 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
     if (!corrThp_local) errorQuda("Cannot allocate memory for the three-point function");
   }
   static const char *proj_names[5] = {"G4", "G5G123", "G5G1", "G5G2", "G5G3"};  // info.thrp_proj_type (:284-288)
-  QKXTM_Gauge<float> K_gaugeContractions(NONE, GAUGE);      // only the (unbuilt) Noether / one-derivative insertions would read the links
+  // the links of the conserved-current / one-derivative insertions (interface.cpp:351-357: K_gaugeContractions->packGauge(gauge))
+  QKXTM_Gauge<float> *K_gaugeContractions = NULL;
+  float *corrThp_noether = NULL, *corrThp_oneD = NULL;
+  if (any3pt && gauge) {
+    K_gaugeContractions = new QKXTM_Gauge<float>(BOTH, GAUGE);
+    K_gaugeContractions->packGauge(gauge);
+    K_gaugeContractions->loadGauge();
+    corrThp_noether = (float *)calloc((size_t)G.localL[3] * nm * 4 * 2, sizeof(float));
+    corrThp_oneD = (float *)calloc((size_t)G.localL[3] * nm * 4 * 16 * 2, sizeof(float));
+    if (!corrThp_noether || !corrThp_oneD) errorQuda("Cannot allocate memory for the three-point function");
+  } else if (any3pt) {
+    K_gaugeContractions = new QKXTM_Gauge<float>(NONE, GAUGE);
+  }
   float *corrMesons = (float *)calloc((size_t)G.localL[3] * nm * 2 * 10 * 2, sizeof(float));
   float *corrBaryons = (float *)calloc((size_t)G.localL[3] * nm * 2 * 10 * 4 * 4 * 2, sizeof(float));
   if (!corrMesons || !corrBaryons) errorQuda("Cannot allocate memory for the two-point functions");
@@ -1062,8 +1105,10 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
               }
             // part 1 contracts with the forward propagator of the doubly occurring flavour, part 2 with the other (:937-951, 1095-1109)
             QKXTM_Propagator<float> *fwd = up_line ? K_prop_up : K_prop_down;
-            K_contract->contractFixSink(*K_seqProp, *fwd, K_gaugeContractions, corrThp_local, NULL, NULL, PID, NUCLEON, part, isource, info.CorrSpace);
-            K_contract->writeThrp_ASCII(corrThp_local, NULL, NULL, NUCLEON, part, filename_threep_base, isource, info.tsinkSource[its], info.CorrSpace);
+            K_contract->contractFixSink(*K_seqProp, *fwd, *K_gaugeContractions, corrThp_local, corrThp_noether, corrThp_oneD, PID, NUCLEON, part, isource,
+                                        info.CorrSpace);
+            K_contract->writeThrp_ASCII(corrThp_local, corrThp_noether, corrThp_oneD, NUCLEON, part, filename_threep_base, isource, info.tsinkSource[its],
+                                        info.CorrSpace);
           }
         }
       }
@@ -1096,6 +1141,9 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   free(corrMesons);
   free(corrBaryons);
   if (corrThp_local) free(corrThp_local);
+  if (corrThp_noether) free(corrThp_noether);
+  if (corrThp_oneD) free(corrThp_oneD);
+  if (K_gaugeContractions) delete K_gaugeContractions;
   if (K_seqProp) delete K_seqProp;
   if (K_prop3D_up) delete K_prop3D_up;
   if (K_prop3D_down) delete K_prop3D_down;
@@ -1104,6 +1152,28 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   if (K_gaugeSmeared) delete K_gaugeSmeared;
   delete x; delete b;
   printfQuda("...Done (%f sec)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
+}
+
+void calcLowModeProjection(QudaInvertParam *evInvParam, qudaQKXTM_arpackInfo arpackInfo, int *nconv, double *evals) {
+  const char *fname = "calcLowModeProjection";
+  if (!evInvParam) errorQuda("null argument");
+  if (!G.quda_initialized) errorQuda("%s: QUDA not initialized", fname);
+  // checks for the exact deflation part (interface.cpp:1360-1368)
+  if ((evInvParam->matpc_type != QUDA_MATPC_EVEN_EVEN_ASYMMETRIC) && (evInvParam->matpc_type != QUDA_MATPC_ODD_ODD_ASYMMETRIC))
+    errorQuda("Only asymmetric operators are supported in deflation");
+  if (arpackInfo.isEven && (evInvParam->matpc_type != QUDA_MATPC_EVEN_EVEN_ASYMMETRIC)) errorQuda("%s: Inconsistency between operator types!", fname);
+  if ((!arpackInfo.isEven) && (evInvParam->matpc_type != QUDA_MATPC_ODD_ODD_ASYMMETRIC)) errorQuda("%s: Inconsistency between operator types!", fname);
+  QKXTM_Deflation<double> *deflation = new QKXTM_Deflation<double>(evInvParam, arpackInfo);
+  deflation->printInfo();
+  const auto t1 = std::chrono::steady_clock::now();
+  deflation->eigenSolver();
+  printfQuda("%s TIME REPORT:Full Operator EigenVector Calculation: %f sec\n", fname,
+             std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
+  if (nconv) *nconv = deflation->Converged();
+  if (evals) for (int i = 0; i < deflation->NeVs(); i++) evals[i] = deflation->EigenValues()[2 * i];
+  printfQuda("\nCleaning up...\n");
+  delete deflation;
+  printfQuda("...Done\n");
 }
 
 void readLimeGauge(void **gauge, char *fname, QudaGaugeParam *param, QudaInvertParam *inv_param, int gridSize[4]) {

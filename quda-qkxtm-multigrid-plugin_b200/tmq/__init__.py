@@ -30,7 +30,7 @@ tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm t
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
 tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free
-tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_d2d""".split()
+tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d""".split()
 
 
 class TmqError(RuntimeError):
@@ -116,6 +116,7 @@ def load():
     L.tmq_qkxtm_contract_baryons.argtypes = [vp, vp, vp, C.c_int, ip, C.c_int, ip, dp]
     L.tmq_qkxtm_seq_source.argtypes = [vp, vp, C.c_int, vp, vp] + [C.c_int] * 6
     L.tmq_qkxtm_fixsink_local.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, ip, C.c_int, ip, dp]
+    L.tmq_qkxtm_fixsink_derivative.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, ip, C.c_int, ip, dp, dp]
     L.tmq_timer_start.argtypes = [vp]; L.tmq_timer_stop.argtypes = [vp, dp]
     L.tmq_clover_load.argtypes = [vp, C.c_double]; L.tmq_clover_free.argtypes = [vp]
     _lib = L
@@ -389,6 +390,15 @@ class Context:
         _ck(self.L.tmq_qkxtm_fixsink_local(self.h, dseq, dfwd, prec, particle, partflag, m.ctypes.data_as(C.POINTER(C.c_int)), len(m),
                                            _i4(list(src) + [0]), _dp(out)))
         return out[..., 0] + 1j * out[..., 1]
+
+    def qkxtm_fixsink_derivative(self, dseq, dfwd, dgauge, prec, particle, partflag, moms, src):
+        """-> (noether [T][nmoms][4], oneD [T][nmoms][4 dir][16 iop]) complex"""
+        m = np.ascontiguousarray(np.asarray(moms, dtype=np.int32).reshape(-1, 3))
+        T = self.X[3]
+        n = np.zeros((T, len(m), 4, 2)); o = np.zeros((T, len(m), 4, 16, 2))
+        _ck(self.L.tmq_qkxtm_fixsink_derivative(self.h, dseq, dfwd, dgauge, prec, particle, partflag, m.ctypes.data_as(C.POINTER(C.c_int)), len(m),
+                                                _i4(list(src) + [0]), _dp(n), _dp(o)))
+        return n[..., 0] + 1j * n[..., 1], o[..., 0] + 1j * o[..., 1]
 
     def qkxtm_gauss_smear(self, dout, din, dgauge, prec, nsmear, alpha):
         _ck(self.L.tmq_qkxtm_gauss_smear(self.h, dout, din, dgauge, prec, nsmear, alpha))

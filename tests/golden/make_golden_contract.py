@@ -44,6 +44,12 @@ def baryon_momenta():
     return momenta()[::6]     # 5 of the 27: the baryon output is 16 times the meson one
 
 
+def deriv_gauge():
+    """links for the conserved-current / one-derivative insertions [4][3][3][V][2] (the contraction is linear in them)"""
+    rng = np.random.Generator(np.random.PCG64(20171010))
+    return rng.standard_normal((4, 3, 3, int(np.prod(X)), 2))
+
+
 def small_inputs():
     rng = np.random.Generator(np.random.PCG64(20171009))
     V = int(np.prod(X_SMALL))
@@ -80,6 +86,7 @@ if __name__ == "__main__":
         out[key] = r.seq_source(part, 4, t1, t2, nu, c2, pid, particle)[:, 4 * V3:5 * V3]
     out["thrp_local_double"] = r.fixsink_local(p1, p2, 0, 1, baryon_momenta(), SRC)
     out["thrp_local_float"] = r.fixsink_local(f1, f2, 1, 1, baryon_momenta(), SRC)
+    out["thrp_noether_double"], out["thrp_oneD_double"] = r.fixsink_derivative(p1, p2, deriv_gauge(), 1, 2, baryon_momenta(), SRC)
     s1, s2 = small_inputs()
     out["baryon_small_double"] = Ref(X_SMALL).contract_baryons_mom(s1, s2, [(0, 0, 0), (1, 0, -1)], SRC_SMALL)
     np.savez_compressed(FIXTURE, **out)

@@ -160,6 +160,37 @@ def test_sequential_sources_and_local_insertion_match_reference_fixture(tmq):
     d.close()
 
 
+def test_derivative_insertions_match_reference_fixture(tmq):
+    """Noether and one-derivative insertions against the reference's kernel bodies (fixture) and, on a lattice with unequal
+    extents and float inputs, against the restatement"""
+    gold = np.load(G.FIXTURE)
+    p1, p2 = G.contract_inputs()
+    U = G.deriv_gauge()
+    d = Dev(tmq, G.X)
+    moms = G.baryon_momenta()
+    gn, go = d.c.qkxtm_fixsink_derivative(d.put(p2), d.put(p1), d.put(U), 8, 1, 2, moms, G.SRC)       # (seq, fwd) = (p2, p1)
+    assert _relmax(gn, _c(gold["thrp_noether_double"])) < 1e-13
+    assert _relmax(go, _c(gold["thrp_oneD_double"])) < 1e-13
+    d.close()
+    X = (6, 4, 2, 8)
+    rng = np.random.default_rng(31)
+    V = int(np.prod(X))
+    F = rng.standard_normal((4, 4, 3, 3, V, 2)).astype(np.float32); S = rng.standard_normal((4, 4, 3, 3, V, 2)).astype(np.float32)
+    Ug = rng.standard_normal((4, 3, 3, V, 2)).astype(np.float32)
+    d = Dev(tmq, X)
+    mm, src = [(0, 0, 0), (1, -1, 0), (0, 2, 1)], (5, 1, 0)
+    gn, go = d.c.qkxtm_fixsink_derivative(d.put(S), d.put(F), d.put(Ug), 4, 0, 1, mm, src)
+    wn, wo = O.fixsink_derivative_mom(_c(F).astype(np.complex128), _c(S).astype(np.complex128), _c(Ug).astype(np.complex128), X, mm, src, 0, 1)
+    assert _relmax(gn, wn) < 2e-5 and _relmax(go, wo) < 2e-5
+    d.close()
+    # a split lattice is refused (the neighbours' propagators would be needed)
+    d = Dev(tmq, X)
+    d.c.force_partition((0, 0, 0, 1))
+    with pytest.raises(tmq.TmqError):
+        d.c.qkxtm_fixsink_derivative(d.put(S), d.put(F), d.put(Ug), 4, 0, 1, mm, src)
+    d.close()
+
+
 def test_site_local_propagator_kernels_match_reference_fixture(tmq):
     gold = np.load(G.FIXTURE)
     p1, _ = G.contract_inputs()
@@ -342,6 +373,8 @@ def test_threep_driver_local_insertion_matches_oracle(tmp_path, tmq, particle, p
     tsink = (src[3] + dt) % T
     up3, dn3 = up[..., tsink * V3:(tsink + 1) * V3], dn[..., tsink * V3:(tsink + 1) * V3]
     g5 = O._gamma5_ukqcd()
+    Ulex = lu.r2c(np.stack([lu.spinor_lex_from_eo(gauge[m], XD) for m in range(4)]))      # [4][x_lex][3][3], what the driver passes as `gauge`
+    Uq = np.ascontiguousarray(np.transpose(Ulex, (0, 2, 3, 1))).astype(np.complex64).astype(np.complex128)   # K_gaugeContractions is a float container
     for part in (1, 2):
         up_line = (particle == "proton") == (part == 1)
         mu_solve = -MU if up_line else +MU
@@ -375,3 +408,13 @@ def test_threep_driver_local_insertion_matches_oracle(tmp_path, tmq, particle, p
         w = -np.roll(np.transpose(want, (2, 0, 1)), -src[3], axis=1)       # time relative to the source; src_t + dt >= T -> sign -1
         scale = np.abs(w).max()
         assert np.abs(got - w).max() / scale < 2e-4, (part, np.abs(got - w).max() / scale)
+        # the conserved-current and one-derivative files of the same run (links: the configuration itself, as the driver passes it)
+        wn, wo = O.fixsink_derivative_mom(fwd, seq, Uq.reshape(4, 3, 3, V), XD, moms, src[:3], part_id, part)
+        rn = np.loadtxt(fname.replace("ultra_local", "noether")); ro = np.loadtxt(fname.replace("ultra_local", "oneD"))
+        assert rn.shape == (4 * T * len(moms), 7) and ro.shape == (16 * 4 * T * len(moms), 8)
+        gn = (rn[:, 5] + 1j * rn[:, 6]).reshape(4, T, len(moms))
+        go = (ro[:, 6] + 1j * ro[:, 7]).reshape(16, 4, T, len(moms))
+        wn_f = -np.roll(np.transpose(wn, (2, 0, 1)), -src[3], axis=1)                  # [dir][t][imom]
+        wo_f = -np.roll(np.transpose(wo, (3, 2, 0, 1)), -src[3], axis=2)               # [iop][dir][t][imom]
+        assert np.abs(gn - wn_f).max() / np.abs(wn_f).max() < 2e-4, part
+        assert np.abs(go - wo_f).max() / np.abs(wo_f).max() < 2e-4, part

@@ -164,3 +164,21 @@ def test_MG_bench_with_gaussian_smeared_sources(tmp_path, env):
             printed = np.array([[float(v) for v in ln.split()] for ln in out.splitlines()
                                 if len(ln.split()) == 2 and ln.lstrip()[0] in "+-" and "e" in ln][:12])
             assert printed.shape == (12, 2) and np.allclose(printed, b_lex[0].reshape(12, 2), rtol=1e-6, atol=1e-12)
+
+
+def test_calcLowModeProjection_entry_point(tmp_path, env):
+    """calcLowModeProjection (lib/qudaQKXTM_interface.cpp:1342-1401): parameter checks + QKXTM_Deflation::eigenSolver; the eigenvalues
+    agree with ARPACK on the oracle operator, and a symmetric operator type is refused like in the reference"""
+    o, gauge, tmq = env
+    from oracle.oracle import eigs_reference
+    nev = 4
+    r, nconv, _, _ = run(tmp_path, "--test", "lowmodes", "--matpc", "even-even-asym", "--nEv", str(nev), "--nKv", "24", "--PolyDeg", "20",
+                         "--amin", "0.34", "--amax", "2.0", "--tolArpack", "1e-11")
+    assert nconv == nev
+    cplx = lambda v: np.ascontiguousarray(v[..., 0] + 1j * v[..., 1]).ravel()
+    real = lambda v: np.ascontiguousarray(np.stack([v.real, v.imag], axis=-1).reshape(o.Vh, 4, 3, 2))
+    A = lambda v: cplx(o.mdagm(gauge, real(v), KAPPA, MU, 2))
+    lam, _ = eigs_reference(A, 12 * o.Vh, nev, 24, "SR", poly=(20, 0.34, 2.0), tol=1e-12)
+    assert np.allclose(r[:nev], lam, rtol=1e-9)
+    p = subprocess.run([DRV, "--dim"] + [str(x) for x in X] + ["--test", "lowmodes", "--matpc", "even-even"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "Only asymmetric operators are supported in deflation" in p.stderr

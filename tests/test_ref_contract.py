@@ -137,3 +137,12 @@ def test_sequential_sources_and_local_insertion_match_reference(gold):
     wantf = _c(gold["thrp_local_float"]).astype(np.complex128)
     gotf = O.fixsink_local_mom(_c(p1), _c(p2), G.X, G.baryon_momenta(), G.SRC, 1, 1)
     assert np.abs(gotf - wantf).max() / np.abs(wantf).max() < 2e-6
+
+
+def test_derivative_insertions_match_reference(gold):
+    """conserved-current (Noether) and one-derivative insertions: four hop blocks per direction with the reference's 1/4"""
+    p1, p2 = G.contract_inputs()
+    wn, wo = O.fixsink_derivative_mom(_c(p1), _c(p2), _c(G.deriv_gauge()), G.X, G.baryon_momenta(), G.SRC, 1, 2)
+    gn, go = _c(gold["thrp_noether_double"]), _c(gold["thrp_oneD_double"])
+    assert np.abs(gn - wn).max() / np.abs(wn).max() < 1e-13
+    assert np.abs(go - wo).max() / np.abs(wo).max() < 1e-13
