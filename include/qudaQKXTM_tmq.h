@@ -9,7 +9,7 @@
 // loops, file I/O, ghost exchange of the containers) is deliberately absent -- see DESIGN.md.
 //
 // Threading / state: like the reference, one host thread per rank and library-global state (one context,
-// one resident gauge field, one-shot init_qudaQKXTM); not re-entrant.
+// one resident gauge field, one-shot init_qudaQKXTM); not re-entrant.  Multi-GPU: one process per rank, see initCommsGridQuda.
 #ifndef QUDAQKXTM_TMQ_H
 #define QUDAQKXTM_TMQ_H
 
@@ -86,8 +86,15 @@ typedef struct QudaInvertParam_s {      // fields read / written on the path (SU
 
 QudaGaugeParam newQudaGaugeParam(void);
 QudaInvertParam newQudaInvertParam(void);
-void initCommsGridQuda(int nDim, const int *dims, void *func, void *fdata);   // qkxtm/QKXTM_util.cpp:66
-void initQuda(int device);                                                     // qkxtm/Calc_Loops.cpp:753
+// qkxtm/QKXTM_util.cpp:48-68.  dims = the process grid (x, y, z, t), only z and t may exceed 1.  One process per rank; rank and world
+// size come from the launcher's environment (RANK / WORLD_SIZE of torchrun --no-python, OMPI_COMM_WORLD_*, PMI_*, SLURM_*), the rank <->
+// coordinate map has t fastest.  The NCCL communicator is created when the first field is (loadGaugeQuda / init_qudaQKXTM): rank 0
+// passes the id to the others through a file (TMQ_COMM_ID_FILE, default /tmp/tmq_nccl_id_<parent pid>_<MASTER_PORT>).
+void initCommsGridQuda(int nDim, const int *dims, void *func, void *fdata);
+int comm_rank(void);
+int comm_size(void);
+int comm_coord(int dim);
+void initQuda(int device);                                                     // qkxtm/Calc_Loops.cpp:753 (device < 0: the launcher's local rank)
 void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param);                      // qkxtm/Calc_Loops.cpp:759 (void *gauge[4], QDP order)
 void freeGaugeQuda(void);
 // loadCloverQuda(NULL, NULL, &inv_param) (qkxtm/MG_Bench.cpp:605-608): the clover field is BUILT on the device from the resident
@@ -194,7 +201,7 @@ public:
   void loadGaugeFromBackup();
   void justDownloadGauge();
   void loadGauge();
-  double calculatePlaq();                          // prints like the reference and also returns the value
+  double calculatePlaq();                          // prints like the reference and also returns the value (skipped, 0, on a split lattice)
 };
 
 template <typename Float> class QKXTM_Vector : public QKXTM_Field<Float> {      // include/qudaQKXTM.h:189-225
@@ -248,7 +255,8 @@ public:
   // refuses double, lib/qudaQKXTM_kernels.cu:1222).
   void contractMesons(QKXTM_Propagator<Float> &prop1, QKXTM_Propagator<Float> &prop2, void *corrMesons, int isource, CORR_SPACE CorrSpace);
   // "ip it px py pz  re(up) im(up)  re(down) im(down)", time relative to the source, lib/qudaQKXTM_Contraction.cpp:1586-1599;
-  // every rank must call it, the rank holding global t = 0 .. writes (all ranks hold the full result)
+  // every rank calls it, rank 0 writes; on a t split the complete correlator is taken from the preceding contractMesons call (libtmq
+  // returns the reduced result for all time slices to every rank: no MPI_Gather over the time communicator)
   void writeTwopMesons_ASCII(void *corrMesons, char *filename_out, int isource, CORR_SPACE CorrSpace);
   // corrBaryons, MOMENTUM_SPACE only: Float[T_local * Nmoms * 2][2][10][4][4], entry [it*Nmoms*2 + imom*2 + ri][iu][ip][gamma][gammap]
   // (lib/qudaQKXTM_Contraction.cpp:906-960), summed over the ranks that share this rank's time slices

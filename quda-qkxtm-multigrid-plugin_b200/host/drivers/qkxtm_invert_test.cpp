@@ -17,7 +17,7 @@ static void usage() {
   printf("qkxtm_invert_test --dim X Y Z T [--kappa k | --mass m] [--mu mu] [--tol t] [--niter n]\n"
          "   [--prec-sloppy double|single] [--recon 12|18] [--matpc even-even|odd-odd] [--mass-normalization kappa|mass]\n"
          "   [--test invert|mgbench|loops|mdagm|mat] [--source z4|gaussian] [--seed s] [--verbosity-level silent|summarize|verbose]\n"
-         "   [--out file] [--dump-inputs prefix]\n"
+         "   [--out file] [--dump-inputs prefix] [--gridsize gx gy gz gt]  (--dim is the LOCAL lattice; one process per rank)\n"
          "   --test twop [--Q_sq q] [--src x y z t] [--nsmearGauss n --alphaGauss a]: meson two-point function, written to\n"
          "       <out>.mesons.SS.xx.yy.zz.tt.dat; with --tsink dt [--proj 0..4] [--particle proton|neutron] also the three-point function\n");
 }
@@ -31,6 +31,7 @@ int main(int argc, char **argv) {
   int nev = 4, nkv = 16, polydeg = 20;
   double amin = 0.385, amax = 2.0, eig_tol = 1e-10, csw = 0.0;
   int q_sq = 0, src_pos[4] = {0, 0, 0, 0}, tsink = 0, proj = 0;
+  int grid[4] = {1, 1, 1, 1};
   std::string particle = "proton";
   std::string dslash_type = "twisted-mass";
   int nsmearGauss = 0; double alphaGauss = 4.0;                              // qkxtm/QKXTM_util.cpp:1652-1654
@@ -64,6 +65,7 @@ int main(int argc, char **argv) {
     else if (a == "--tolArpack") { need(1); eig_tol = atof(argv[++i]); }
     else if (a == "--Q_sq") { need(1); q_sq = atoi(argv[++i]); }               // qkxtm/QKXTM_util.cpp (momenta with p^2 <= Q_sq)
     else if (a == "--src") { need(4); for (int d = 0; d < 4; d++) src_pos[d] = atoi(argv[++i]); }
+    else if (a == "--gridsize") { need(4); for (int d = 0; d < 4; d++) grid[d] = atoi(argv[++i]); }   // process grid x y z t (qkxtm/QKXTM_util.cpp:2198); --dim is LOCAL
     else if (a == "--tsink") { need(1); tsink = atoi(argv[++i]); }             // > 0: also the three-point function at this sink-source separation
     else if (a == "--proj") { need(1); proj = atoi(argv[++i]); }               // WHICHPROJECTOR 0..4
     else if (a == "--particle") { need(1); particle = argv[++i]; }            // proton | neutron
@@ -71,7 +73,7 @@ int main(int argc, char **argv) {
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
   }
   const long long V = (long long)dim[0] * dim[1] * dim[2] * dim[3];
-  const int grid[4] = {1, 1, 1, 1}, coord[4] = {0, 0, 0, 0};
+  int coord[4] = {0, 0, 0, 0};
 
   // setGaugeParam (qkxtm/Calc_Loops.cpp:189-225)
   QudaGaugeParam gauge_param = newQudaGaugeParam();
@@ -124,13 +126,18 @@ int main(int argc, char **argv) {
   for (int d = 0; d < 4; d++) info.sourcePosition[0][d] = src_pos[d];
   if (tsink > 0) { info.run3pt_src[0] = 1; info.Ntsink = 1; info.tsinkSource[0] = tsink; info.Nproj[0] = 1; info.proj_list[0][0] = proj; }
 
-  // synthetic configuration: random SU(3), QDP even-odd order, anti-periodic T folded in
+  // one process per rank (torchrun --no-python / mpirun / srun export the rank): qkxtm/QKXTM_util.cpp:48-68
+  initCommsGridQuda(4, grid, nullptr, nullptr);
+  for (int d = 0; d < 4; d++) coord[d] = comm_coord(d);
+  const bool root = comm_rank() == 0;
+  if (comm_size() > 1 && !out.empty()) out += ".rank" + std::to_string(comm_rank());
+
+  // synthetic configuration: random SU(3), QDP even-odd order, anti-periodic T folded in (this rank's block of the global field)
   std::vector<double> gbuf((size_t)4 * V * 18);
   double *gauge[4] = {gbuf.data(), gbuf.data() + (size_t)V * 18, gbuf.data() + (size_t)2 * V * 18, gbuf.data() + (size_t)3 * V * 18};
   tmq_fieldgen_gauge_qdp(gauge, dim, grid, coord, 137, -1);
 
-  initCommsGridQuda(4, grid, nullptr, nullptr);
-  initQuda(0);
+  initQuda(comm_size() > 1 ? -1 : 0);
   init_qudaQKXTM(&info);
   printf_qudaQKXTM();
   loadGaugeQuda((void *)gauge, &gauge_param);
@@ -208,6 +215,7 @@ int main(int argc, char **argv) {
     } else {
       // qkxtm/CalcMG_2pt3pt_EvenOdd.cpp main(): the two-point function of one source position
       std::string base = out.empty() ? std::string("twop") : out;
+      if (comm_size() > 1 && !out.empty()) base = out.substr(0, out.rfind(".rank"));      // correlator files are written once, by rank 0
       std::vector<char> f2(base.begin(), base.end()); f2.push_back(0);
       std::string base3 = base + ".threep";
       std::vector<char> f3(base3.begin(), base3.end()); f3.push_back(0);
@@ -215,8 +223,9 @@ int main(int argc, char **argv) {
     }
   } else { usage(); return 2; }
 
-  printf("RESULT test=%s iter=%d true_res=%.6e secs=%.6f gflops=%.3f kappa=%.17g mu=%.17g\n", test.c_str(), inv_param.iter,
-         inv_param.true_res, inv_param.secs, inv_param.gflops, inv_param.kappa, inv_param.mu);
+  if (root)
+    printf("RESULT test=%s iter=%d true_res=%.6e secs=%.6f gflops=%.3f kappa=%.17g mu=%.17g\n", test.c_str(), inv_param.iter,
+           inv_param.true_res, inv_param.secs, inv_param.gflops, inv_param.kappa, inv_param.mu);
   if (!out.empty()) {
     FILE *f = fopen(out.c_str(), "wb");
     if (!f) { perror("fopen"); return 1; }

@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <thread>
+#include <unistd.h>
 #include <vector>
 
 using namespace quda;
@@ -24,6 +26,7 @@ struct Globals {
   bool clover_loaded = false;
   int grid[4] = {1, 1, 1, 1};
   int coord[4] = {0, 0, 0, 0};
+  int rank = 0, nranks = 1;           // comm_rank() / comm_size(): from the launcher's environment (initCommsGridQuda)
   int localL[4] = {0, 0, 0, 0};
   long long localVolume = 0;
   tmq_ctx *ctx = nullptr;
@@ -34,6 +37,9 @@ struct Globals {
   double alphaGauss = 0;
   std::vector<int> moms;              // GK_moms [GK_Nmoms][3] (lib/qudaQKXTM_kernels.cu:75-76, createMomenta :98-116)
   std::vector<int> sourcePosition;    // GK_sourcePosition [Nsources][4]
+  // the complete (all time slices, reduced over ranks) result of the last contractMesons / contractBaryons / contractFixSink: libtmq hands
+  // it to every rank, so that the writers need no MPI_Gather over the time communicator (lib/qudaQKXTM_Contraction.cpp:1580-1584)
+  std::vector<double> glob_mesons, glob_baryons, glob_thrp;
   int op_matpc = -1;
 } G;
 
@@ -54,12 +60,55 @@ void default_error(const char *msg) {
   } while (0)
 #define printfQuda(...)                                              \
   do {                                                               \
-    if (G.verbosity > QUDA_SILENT) { printf(__VA_ARGS__); fflush(stdout); } \
+    if (G.verbosity > QUDA_SILENT && G.rank == 0) { printf(__VA_ARGS__); fflush(stdout); } \
   } while (0)
 #define TMQ_OK(call)                                                        \
   do {                                                                      \
     if ((call) != 0) errorQuda("libtmq: %s", tmq_last_error());             \
   } while (0)
+
+// ---- process grid ----------------------------------------------------------------------------------------------------------------
+// The reference builds its communicator with MPI (qkxtm/QKXTM_util.cpp:48-68).  Here every rank is one process started by any
+// launcher that exports a rank and a world size (torchrun --no-python, mpirun, srun); the 128-byte NCCL id travels from rank 0 to
+// the others through a file that all ranks of ONE launch agree on (same parent process id, or TMQ_COMM_ID_FILE).
+static int env_int(const char *const *names, int dflt) {
+  for (int i = 0; names[i]; i++) {
+    const char *v = getenv(names[i]);
+    if (v && *v) return atoi(v);
+  }
+  return dflt;
+}
+static void comm_bootstrap() {
+  char path[512];
+  const char *f = getenv("TMQ_COMM_ID_FILE");
+  if (f && *f) snprintf(path, sizeof(path), "%s", f);
+  else snprintf(path, sizeof(path), "/tmp/tmq_nccl_id_%ld_%s", (long)getppid(), getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
+  char id[128];
+  if (G.rank == 0) {
+    TMQ_OK(tmq_comm_unique_id(id));
+    char tmp[600];
+    snprintf(tmp, sizeof(tmp), "%s.tmp", path);
+    FILE *fp = fopen(tmp, "wb");
+    if (!fp || fwrite(id, 1, 128, fp) != 128) errorQuda("cannot write the communicator id file %s", tmp);
+    fclose(fp);
+    if (rename(tmp, path) != 0) errorQuda("cannot publish the communicator id file %s", path);
+  } else {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+      FILE *fp = fopen(path, "rb");
+      if (fp) {
+        const size_t n = fread(id, 1, 128, fp);
+        fclose(fp);
+        if (n == 128) break;
+      }
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+        errorQuda("rank %d: no communicator id from rank 0 after 120 s (%s)", G.rank, path);
+      std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    }
+  }
+  TMQ_OK(tmq_comm_init(G.ctx, id, G.nranks, G.rank));     // collective: returns once every rank has joined
+  if (G.rank == 0) remove(path);
+}
 
 static void ensure_context(const int X[4]) {
   if (!G.quda_initialized) errorQuda("initQuda must be called first");
@@ -72,6 +121,7 @@ static void ensure_context(const int X[4]) {
   G.localVolume = (long long)X[0] * X[1] * X[2] * X[3];
   G.ctx = tmq_create(G.device, X, G.grid, G.coord);
   if (!G.ctx) errorQuda("libtmq: %s", tmq_last_error());
+  if (G.nranks > 1) comm_bootstrap();
 }
 
 // ---- QUDA C API slice ---------------------------------------------------------------------------------------------------
@@ -111,17 +161,29 @@ void setVerbosityQuda(QudaVerbosity v) { G.verbosity = v; }
 
 void initCommsGridQuda(int nDim, const int *dims, void *, void *) {
   if (nDim != 4) errorQuda("Number of communication grid dimensions must be 4");
-  // single-process host layer: multi-rank runs bootstrap NCCL through tmq_comm_init
-  for (int d = 0; d < 4; d++) {
-    if (dims[d] != 1) errorQuda("this host layer drives one rank; use the C ABI (tmq_create + tmq_comm_init) for a process grid");
-    G.grid[d] = dims[d];
-  }
+  if (G.ctx) errorQuda("initCommsGridQuda must come before the first field is created");
+  if (dims[0] != 1 || dims[1] != 1) errorQuda("only z and t may be partitioned (gridsize %d %d %d %d)", dims[0], dims[1], dims[2], dims[3]);
+  static const char *rank_names[] = {"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID", NULL};
+  static const char *size_names[] = {"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS", NULL};
+  G.rank = env_int(rank_names, 0);
+  G.nranks = env_int(size_names, 1);
+  long long prod = 1;
+  for (int d = 0; d < 4; d++) { if (dims[d] < 1) errorQuda("bad gridsize"); G.grid[d] = dims[d]; prod *= dims[d]; }
+  if (prod != G.nranks) errorQuda("gridsize %d x %d x %d x %d needs %lld ranks, the launcher started %d", dims[0], dims[1], dims[2], dims[3], prod, G.nranks);
+  if (G.rank < 0 || G.rank >= G.nranks) errorQuda("bad rank %d of %d", G.rank, G.nranks);
+  // rank <-> coordinate: t fastest, rank = ((cx gy + cy) gz + cz) gt + ct (include/tmq.h; QUDA's default lexicographic map)
+  int r = G.rank;
+  for (int d = 3; d >= 0; d--) { G.coord[d] = r % G.grid[d]; r /= G.grid[d]; }
 }
+int comm_rank(void) { return G.rank; }
+int comm_size(void) { return G.nranks; }
+int comm_coord(int dim) { return (dim >= 0 && dim < 4) ? G.coord[dim] : 0; }
 
 void initQuda(int device) {
   if (G.quda_initialized) return;
   if (tmq_device_count() <= 0) errorQuda("no CUDA device (there is no CPU fallback)");
-  G.device = device < 0 ? 0 : device;
+  static const char *local_names[] = {"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", NULL};
+  G.device = device < 0 ? env_int(local_names, 0) % tmq_device_count() : device;     // initQuda(-1): one GPU per local rank
   G.quda_initialized = true;
 }
 
@@ -405,6 +467,12 @@ template <typename Float> void QKXTM_Gauge<Float>::loadGaugeFromBackup() {
 template <typename Float> void QKXTM_Gauge<Float>::justDownloadGauge() { TMQ_OK(tmq_d2h(G.ctx, this->h_elem, this->d_elem, this->bytes_total_length)); }
 template <typename Float> double QKXTM_Gauge<Float>::calculatePlaq() {
   double plaq = 0;
+  if (G.nranks > 1) {
+    // the container keeps no ghost links (the reference stages them through the host, lib/qudaQKXTM_Gauge.cpp:143-373); the plaquette is
+    // a printed sanity check only, so a split lattice skips it instead of aborting the run
+    printfQuda("Calculated plaquette: skipped on a split lattice\n");
+    return 0.0;
+  }
   TMQ_OK(tmq_qkxtm_plaquette(G.ctx, this->d_elem, (int)sizeof(Float), &plaq));
   if (sizeof(Float) == 4) printfQuda("Calculated plaquette in single precision is %f\n", plaq);
   else printfQuda("Calculated plaquette in double precision is %lf\n", plaq);
@@ -570,6 +638,7 @@ void QKXTM_Contraction<Float>::contractMesons(QKXTM_Propagator<Float> &prop1, QK
     std::vector<double> mom((size_t)gT * nm * 40);
     TMQ_OK(tmq_qkxtm_contract_mesons(G.ctx, prop1.D_elem(), prop2.D_elem(), (int)sizeof(Float), G.moms.data(), nm, &G.sourcePosition[(size_t)isource * 4],
                                      mom.data(), NULL));
+    G.glob_mesons = mom;
     for (int it = 0; it < Lt; it++)
       for (int im = 0; im < nm; im++)
         for (int ch = 0; ch < 20; ch++)
@@ -581,10 +650,20 @@ void QKXTM_Contraction<Float>::contractMesons(QKXTM_Propagator<Float> &prop1, QK
 template <typename Float>
 void QKXTM_Contraction<Float>::writeTwopMesons_ASCII(void *corrMesons, char *filename_out, int isource, CORR_SPACE CorrSpace) {
   if (CorrSpace != MOMENTUM_SPACE) errorQuda("writeTwopMesons_ASCII: Supports writing only in momentum-space!");
-  if (G.grid[3] != 1) errorQuda("writeTwopMesons_ASCII: gather the time ranks' buffers first (single rank in t here)");
   printfQuda("writeTwopMesons_ASCII: Will write in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
-  const Float *c = (const Float *)corrMesons;
   const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
+  // on a t split the complete correlator comes from the last contractMesons (every rank has it), rounded to Float like the caller's
+  std::vector<Float> gathered;
+  const Float *c = (const Float *)corrMesons;
+  if (G.grid[3] != 1) {
+    if (G.glob_mesons.size() != (size_t)T * nm * 40) errorQuda("writeTwopMesons_ASCII: call contractMesons first");
+    gathered.resize((size_t)T * nm * 40);
+    for (int it = 0; it < T; it++)
+      for (int im = 0; im < nm; im++)
+        for (int ch = 0; ch < 20; ch++)
+          for (int ri = 0; ri < 2; ri++) gathered[(((size_t)it * nm + im) * 2 + ri) * 20 + ch] = (Float)G.glob_mesons[(((size_t)it * nm + im) * 20 + ch) * 2 + ri];
+    c = gathered.data();
+  }
   const int *mv = qkxtm_moms();
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
@@ -615,6 +694,7 @@ void QKXTM_Contraction<Float>::contractBaryons(QKXTM_Propagator<Float> &prop1, Q
   std::vector<double> mom((size_t)gT * nm * 320 * 2);
   TMQ_OK(tmq_qkxtm_contract_baryons(G.ctx, prop1.D_elem(), prop2.D_elem(), (int)sizeof(Float), G.moms.data(), nm, &G.sourcePosition[(size_t)isource * 4],
                                     mom.data()));
+  G.glob_baryons = mom;
   for (int it = 0; it < Lt; it++)
     for (int im = 0; im < nm; im++)
       for (int ch = 0; ch < 320; ch++)
@@ -625,10 +705,19 @@ void QKXTM_Contraction<Float>::contractBaryons(QKXTM_Propagator<Float> &prop1, Q
 template <typename Float>
 void QKXTM_Contraction<Float>::writeTwopBaryons_ASCII(void *corrBaryons, char *filename_out, int isource, CORR_SPACE CorrSpace) {
   if (CorrSpace != MOMENTUM_SPACE) errorQuda("writeTwopBaryons_ASCII: Supports writing only in momentum-space!");
-  if (G.grid[3] != 1) errorQuda("writeTwopBaryons_ASCII: gather the time ranks' buffers first (single rank in t here)");
   printfQuda("writeTwopBaryons_ASCII: Will write in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
-  const Float *c = (const Float *)corrBaryons;
   const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
+  std::vector<Float> gathered;
+  const Float *c = (const Float *)corrBaryons;
+  if (G.grid[3] != 1) {
+    if (G.glob_baryons.size() != (size_t)T * nm * 640) errorQuda("writeTwopBaryons_ASCII: call contractBaryons first");
+    gathered.resize((size_t)T * nm * 640);
+    for (int it = 0; it < T; it++)
+      for (int im = 0; im < nm; im++)
+        for (int ch = 0; ch < 320; ch++)
+          for (int ri = 0; ri < 2; ri++) gathered[(((size_t)it * nm + im) * 2 + ri) * 320 + ch] = (Float)G.glob_baryons[(((size_t)it * nm + im) * 320 + ch) * 2 + ri];
+    c = gathered.data();
+  }
   const int *mv = qkxtm_moms();
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
@@ -678,6 +767,7 @@ void QKXTM_Contraction<Float>::contractFixSink(QKXTM_Propagator<Float> &seqProp,
                                  &G.sourcePosition[(size_t)isource * 4], mom.data()));
   Float *out = (Float *)corrThp_local;
   for (size_t i = 0; i < (size_t)Lt * nm * 32; i++) out[i] = (Float)mom[(size_t)G.coord[3] * Lt * nm * 32 + i];
+  G.glob_thrp = mom;
   if (corrThp_noether) {
     if (!gauge.D_elem()) errorQuda("contractFixSink: the Noether and one-derivative insertions need the gauge links on the device");
     std::vector<double> cn((size_t)Lt * nm * 4 * 2), co((size_t)Lt * nm * 64 * 2);
@@ -692,7 +782,6 @@ void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrTh
                                                char *filename_out, int isource, int tsinkMtsource, CORR_SPACE CorrSpace) {
   if (CorrSpace != MOMENTUM_SPACE) errorQuda("writeThrp_ASCII: Supports writing only in momentum-space!");
   if ((corrThp_noether == NULL) != (corrThp_oneD == NULL)) errorQuda("writeThrp_ASCII: give both the Noether and the one-derivative buffer, or neither");
-  if (G.grid[3] != 1) errorQuda("writeThrp_ASCII: gather the time ranks' buffers first (single rank in t here)");
   if (partflag != 1 && partflag != 2) errorQuda("writeThrp_ASCII: Got the wrong part! Should be either 1 or 2.");
   printfQuda("writeThrp_ASCII: Will write in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
   const char *particle = testParticle == PROTON ? "proton" : "neutron";
@@ -705,9 +794,15 @@ void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrTh
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
   if (!root) return;
-  const Float *c = (const Float *)corrThp_local;
   const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
   const int *mv = qkxtm_moms();
+  std::vector<Float> gathered;
+  const Float *c = (const Float *)corrThp_local;
+  if (G.grid[3] != 1) {
+    if (G.glob_thrp.size() != (size_t)T * nm * 32) errorQuda("writeThrp_ASCII: call contractFixSink first");
+    gathered.assign(G.glob_thrp.begin(), G.glob_thrp.end());
+    c = gathered.data();
+  }
   FILE *ptr_local = fopen(fname_local, "w");
   if (ptr_local == NULL) errorQuda("Error opening file for writing");
   for (int iop = 0; iop < 16; iop++)
@@ -912,7 +1007,8 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
     const auto t4 = std::chrono::steady_clock::now();
     memset(input_vector, 0, (size_t)V * 24 * sizeof(double));
     if (param->mu < 0) param->mu *= -1.0;                 // "Ensure mu is positive" (interface.cpp:162-163)
-    input_vector[isc * 2] = 1.0;                          // point source at the origin, spin-colour isc
+    if (G.coord[0] == 0 && G.coord[1] == 0 && G.coord[2] == 0 && G.coord[3] == 0)
+      input_vector[isc * 2] = 1.0;                        // point source at the origin, spin-colour isc (on the rank that holds it)
     K_vector->packVector(input_vector);
     K_vector->loadVector();
     if (K_gaugeSmeared) {
@@ -950,7 +1046,6 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   if (param->gamma_basis != QUDA_UKQCD_GAMMA_BASIS) errorQuda("This function works only with ukqcd gamma basis");       // interface.cpp:270-273
   if (info.CorrFileFormat != ASCII_FORM) errorQuda("only the ASCII two-point format is built (no HDF5 here)");
   if (info.CorrSpace != MOMENTUM_SPACE) errorQuda("the ASCII two-point writer supports only momentum space");           // Contraction.cpp:1565
-  if (G.grid[3] != 1) errorQuda("the two-point driver gathers no time ranks: run it unsharded in t");
   bool any3pt = false;
   for (int i = 0; i < info.Nsources; i++) any3pt = any3pt || info.run3pt_src[i];
   if (any3pt && !filename_threep) errorQuda("null three-point file name");
@@ -989,7 +1084,9 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   // the links of the conserved-current / one-derivative insertions (interface.cpp:351-357: K_gaugeContractions->packGauge(gauge))
   QKXTM_Gauge<float> *K_gaugeContractions = NULL;
   float *corrThp_noether = NULL, *corrThp_oneD = NULL;
-  if (any3pt && gauge) {
+  if (any3pt && gauge && G.nranks > 1 && G.rank == 0)
+    fprintf(stderr, "WARNING: the conserved-current and one-derivative insertions are skipped on a split lattice\n");
+  if (any3pt && gauge && G.nranks == 1) {
     K_gaugeContractions = new QKXTM_Gauge<float>(BOTH, GAUGE);
     K_gaugeContractions->packGauge(gauge);
     K_gaugeContractions->loadGauge();
