@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--grid", type=int, nargs=4, default=None)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--prec", type=int, default=8, choices=[8, 4])
-    ap.add_argument("--recon", type=int, default=12, choices=[12, 18])
+    ap.add_argument("--recon", type=int, default=12, choices=[8, 12, 18])
     ap.add_argument("--tile", type=int, nargs=3, default=None)
     ap.add_argument("--boundary-at", type=int, default=None, help="%% of interior CTAs scheduled before the boundary CTAs")
     ap.add_argument("--pack-async", type=int, default=None, help="1: launch the face pack on the exchange stream (TMQ_OPT_PACK_ASYNC)")

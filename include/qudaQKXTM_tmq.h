@@ -21,7 +21,7 @@
 
 // ---- the slice of quda.h / enum_quda.h the path reads ----------------------------------------------
 typedef enum { QUDA_SINGLE_PRECISION = 4, QUDA_DOUBLE_PRECISION = 8 } QudaPrecision;
-typedef enum { QUDA_RECONSTRUCT_NO = 18, QUDA_RECONSTRUCT_12 = 12 } QudaReconstructType;
+typedef enum { QUDA_RECONSTRUCT_NO = 18, QUDA_RECONSTRUCT_12 = 12, QUDA_RECONSTRUCT_8 = 8 } QudaReconstructType;
 typedef enum { QUDA_ANTI_PERIODIC_T = -1, QUDA_PERIODIC_T = 1 } QudaTboundary;
 typedef enum { QUDA_QDP_GAUGE_ORDER = 0 } QudaGaugeFieldOrder;
 typedef enum { QUDA_WILSON_LINKS = 0, QUDA_SMEARED_LINKS = 1 } QudaLinkType;

@@ -34,7 +34,7 @@ enum { TMQ_PREC_SINGLE = 4, TMQ_PREC_DOUBLE = 8 };          /* bytes, as QKXTM_F
 enum { TMQ_SUBSET_PARITY = 1, TMQ_SUBSET_FULL = 2 };          /* QUDA_PARITY_SITE_SUBSET / QUDA_FULL_SITE_SUBSET            */
 enum { TMQ_MATPC_EVEN_EVEN = 0, TMQ_MATPC_ODD_ODD = 1,        /* qkxtm/Calc_Loops.cpp:443-450                               */
        TMQ_MATPC_EVEN_EVEN_ASYM = 2, TMQ_MATPC_ODD_ODD_ASYM = 3 };
-enum { TMQ_RECON_12 = 12, TMQ_RECON_18 = 18 };                /* --recon 12 / 18 (qkxtm/misc.cpp:661-683)                   */
+enum { TMQ_RECON_8 = 8, TMQ_RECON_12 = 12, TMQ_RECON_18 = 18 }; /* --recon 8 / 12 / 18 (qkxtm/misc.cpp:661-683)               */
 enum { TMQ_SOLUTION_MAT = 0, TMQ_SOLUTION_MATPC = 1 };        /* QUDA_MAT_SOLUTION / QUDA_MATPC_SOLUTION                    */
 
 const char *tmq_last_error(void);
@@ -73,7 +73,9 @@ int tmq_halo_mode(tmq_ctx *);
  * qdp_eo_gauge[mu]: host, double, [even Vh | odd Vh] x 3x3 complex row-major (QDP order,
  * qkxtm/QKXTM_util.cpp:840-857), with the T boundary condition ALREADY folded into U_t on the last
  * global time slice when t_boundary = -1 (applyGaugeFieldScaling, qkxtm/QKXTM_util.cpp:698-705).
- * Creates resident fp64 and fp32 copies with the requested reconstruct.                                   */
+ * Creates resident fp64 and fp32 copies with the requested reconstruct: 18 (all nine entries), 12 (rows 0, 1; row 2 rebuilt in
+ * registers) or 8 (U01, U02, U10 and tan(arg U00 / 4), tan(arg U20 / 4): a trig-free 8-real format, 2 square roots and 3 divisions
+ * to unpack; fields with |U01|^2 + |U02|^2 < 1e-6 on some link -- a unit field -- cannot be stored and are refused).               */
 int tmq_gauge_load(tmq_ctx *, const void *const qdp_eo_gauge[4], int t_boundary, int recon);
 int tmq_gauge_free(tmq_ctx *);
 /* sum Re tr P / (V_global * 3 * 6): QKXTM_Gauge::calculatePlaq (lib/qudaQKXTM_Gauge.cpp:376-386,

@@ -1,0 +1,7 @@
+// Dslash kernels, precision = double, gauge reconstruct = 8 (see tmq_dslash_inst.cuh, tmq_site.cuh: reconstruct_from8)
+#include "tmq_dslash_inst.cuh"
+namespace tmq {
+cudaError_t launch_dslash_d8(int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st) {
+  return launch_dslash_t<double, 8>(epi, multi, A, st);
+}
+}  // namespace tmq

@@ -97,10 +97,10 @@ static int ensure_stage(tmq_ctx *c, size_t bytes) {
 
 template <typename F> static cudaError_t launch_any(tmq_ctx *c, int epi, bool multi, const DslashArgs<F> &A, cudaStream_t st);
 template <> cudaError_t launch_any<double>(tmq_ctx *c, int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st) {
-  return c->recon == 12 ? launch_dslash_d12(epi, multi, A, st) : launch_dslash_d18(epi, multi, A, st);
+  return c->recon == 8 ? launch_dslash_d8(epi, multi, A, st) : (c->recon == 12 ? launch_dslash_d12(epi, multi, A, st) : launch_dslash_d18(epi, multi, A, st));
 }
 template <> cudaError_t launch_any<float>(tmq_ctx *c, int epi, bool multi, const DslashArgs<float> &A, cudaStream_t st) {
-  return c->recon == 12 ? launch_dslash_s12(epi, multi, A, st) : launch_dslash_s18(epi, multi, A, st);
+  return c->recon == 8 ? launch_dslash_s8(epi, multi, A, st) : (c->recon == 12 ? launch_dslash_s12(epi, multi, A, st) : launch_dslash_s18(epi, multi, A, st));
 }
 template <typename F> static cudaError_t pack_any(tmq_ctx *c, const DslashArgs<F> &A, int dim, void *sb, void *sf, cudaStream_t st);
 template <> cudaError_t pack_any<double>(tmq_ctx *c, const DslashArgs<double> &A, int dim, void *sb, void *sf, cudaStream_t st) {
@@ -644,8 +644,21 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
 // ---- gauge ----------------------------------------------------------------------------------------------------------
 int tmq_gauge_load(tmq_ctx *c, const void *const qdp[4], int t_boundary, int recon) {
   TMQ_REQUIRE(c, "null context");
-  TMQ_REQUIRE(recon == 12 || recon == 18, "reconstruct must be 12 or 18 (got %d)", recon);
+  TMQ_REQUIRE(recon == 8 || recon == 12 || recon == 18, "reconstruct must be 8, 12 or 18 (got %d)", recon);
   TMQ_REQUIRE(t_boundary == 1 || t_boundary == -1, "t_boundary must be +1 or -1");
+  if (recon == 8) {
+    // the 8-real format divides by |U01|^2 + |U02|^2: links with a (nearly) vanishing rest of the first row -- a unit field -- cannot be stored
+    const size_t nlinks = (size_t)2 * c->g.Vh;
+    for (int mu = 0; mu < 4; mu++) {
+      TMQ_REQUIRE(qdp[mu], "gauge[%d] is null", mu);
+      const double *u = (const double *)qdp[mu];
+      for (size_t i = 0; i < nlinks; i++) {
+        const double *l = u + i * 18;
+        TMQ_REQUIRE(l[2] * l[2] + l[3] * l[3] + l[4] * l[4] + l[5] * l[5] >= 1e-6,
+                    "reconstruct 8 cannot store link (mu %d, site %zu): |U01|^2 + |U02|^2 < 1e-6 (unit or near-diagonal field; use 12)", mu, i);
+      }
+    }
+  }
   TMQ_CUDA(cudaSetDevice(c->device));
   tmq_gauge_free(c);
   c->recon = recon;

@@ -407,7 +407,8 @@ int tmq_clover_load(tmq_ctx *c, double clover_coeff) {
     const size_t next = (size_t)ext.E[0] * ext.E[1] * ext.E[2] * ext.E[3];
     TMQ_CUDA(cudaMalloc((void **)&E, next * 72 * sizeof(double)));
     TMQ_CUDA(cudaMemsetAsync(E, 0, next * 72 * sizeof(double), c->stream));
-    if (c->recon == 12) ext_fill_kernel<12><<<grid, 128, 0, c->stream>>>(E, ext, c->gauge_d.d, g);
+    if (c->recon == 8) ext_fill_kernel<8><<<grid, 128, 0, c->stream>>>(E, ext, c->gauge_d.d, g);
+    else if (c->recon == 12) ext_fill_kernel<12><<<grid, 128, 0, c->stream>>>(E, ext, c->gauge_d.d, g);
     else ext_fill_kernel<18><<<grid, 128, 0, c->stream>>>(E, ext, c->gauge_d.d, g);
     TMQ_CUDA(cudaGetLastError()); c->launches++;
     if (g.part[2]) {
@@ -430,7 +431,8 @@ int tmq_clover_load(tmq_ctx *c, double clover_coeff) {
     }
     ext.d = E;
   }
-  if (c->recon == 12) clover_compute_kernel<12><<<grid, 128, 0, c->stream>>>((VecT<double> *)c->clov_c_d.d, c->gauge_d.d, ext, c->g, S, clover_coeff);
+  if (c->recon == 8) clover_compute_kernel<8><<<grid, 128, 0, c->stream>>>((VecT<double> *)c->clov_c_d.d, c->gauge_d.d, ext, c->g, S, clover_coeff);
+  else if (c->recon == 12) clover_compute_kernel<12><<<grid, 128, 0, c->stream>>>((VecT<double> *)c->clov_c_d.d, c->gauge_d.d, ext, c->g, S, clover_coeff);
   else clover_compute_kernel<18><<<grid, 128, 0, c->stream>>>((VecT<double> *)c->clov_c_d.d, c->gauge_d.d, ext, c->g, S, clover_coeff);
   TMQ_CUDA(cudaGetLastError()); c->launches++;
   if (E) { TMQ_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(E); if (zbuf) cudaFree(zbuf); }

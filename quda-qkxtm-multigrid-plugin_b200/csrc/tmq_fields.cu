@@ -20,7 +20,14 @@ __global__ void gauge_reorder_kernel(void *dst, const double *__restrict__ src, 
   if (i >= 2 * Vh) return;
   const int parity = i / Vh, idx = i - parity * Vh;
   const double *s = src + (size_t)i * 18;
-  if (RECON == 12) {
+  if (RECON == 8) {
+    // (U01, U02), (U10, tan(arg U00 / 4), tan(arg U20 / 4)); the phases are taken in double whatever F is
+    VecT<F> *b = (VecT<F> *)dst + (size_t)((parity * 4 + mu) * 2) * (size_t)Vh + idx;
+    VecT<F> v; v.a = (F)s[2]; v.b = (F)s[3]; v.c = (F)s[4]; v.d = (F)s[5];
+    b[0] = v;
+    v.a = (F)s[6]; v.b = (F)s[7]; v.c = (F)tan(0.25 * atan2(s[1], s[0])); v.d = (F)tan(0.25 * atan2(s[13], s[12]));
+    b[(size_t)Vh] = v;
+  } else if (RECON == 12) {
     VecT<F> *b = (VecT<F> *)dst + (size_t)((parity * 4 + mu) * 3) * (size_t)Vh + idx;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -37,11 +44,13 @@ __global__ void gauge_reorder_kernel(void *dst, const double *__restrict__ src, 
 cudaError_t gauge_reorder(int prec, int recon, void *dst, const double *src_mu, int mu, int Vh, cudaStream_t st) {
   const int grid = (2 * Vh + FB - 1) / FB;
   if (prec == 8) {
-    if (recon == 12) gauge_reorder_kernel<double, 12><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
-    else             gauge_reorder_kernel<double, 18><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
+    if (recon == 8)       gauge_reorder_kernel<double, 8><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
+    else if (recon == 12) gauge_reorder_kernel<double, 12><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
+    else                  gauge_reorder_kernel<double, 18><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
   } else {
-    if (recon == 12) gauge_reorder_kernel<float, 12><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
-    else             gauge_reorder_kernel<float, 18><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
+    if (recon == 8)       gauge_reorder_kernel<float, 8><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
+    else if (recon == 12) gauge_reorder_kernel<float, 12><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
+    else                  gauge_reorder_kernel<float, 18><<<grid, FB, 0, st>>>(dst, src_mu, mu, Vh);
   }
   return cudaGetLastError();
 }
@@ -188,7 +197,8 @@ __global__ void __launch_bounds__(128) plaquette_kernel(const void *gauge, Geom 
 }
 cudaError_t plaquette_launch(int recon, const void *gauge_d, const Geom &g, const BlasRed &r, cudaStream_t st) {
   const int grid = (2 * g.Vh + 127) / 128;
-  if (recon == 12) plaquette_kernel<12><<<grid, 128, 0, st>>>(gauge_d, g, r);
+  if (recon == 8) plaquette_kernel<8><<<grid, 128, 0, st>>>(gauge_d, g, r);
+  else if (recon == 12) plaquette_kernel<12><<<grid, 128, 0, st>>>(gauge_d, g, r);
   else plaquette_kernel<18><<<grid, 128, 0, st>>>(gauge_d, g, r);
   return cudaGetLastError();
 }

@@ -118,16 +118,20 @@ static cudaError_t pack_t(const DslashArgs<F> &A, int dim, void *sb, void *sf, c
 
 cudaError_t halo_pack(int prec, int recon, const DslashArgs<double> *Ad, const DslashArgs<float> *As, int dim,
                       void *send_bwd, void *send_fwd, cudaStream_t st) {
-  if (prec == 8) return recon == 12 ? pack_t<double, 12>(*Ad, dim, send_bwd, send_fwd, st) : pack_t<double, 18>(*Ad, dim, send_bwd, send_fwd, st);
-  return recon == 12 ? pack_t<float, 12>(*As, dim, send_bwd, send_fwd, st) : pack_t<float, 18>(*As, dim, send_bwd, send_fwd, st);
+  if (prec == 8)
+    return recon == 8 ? pack_t<double, 8>(*Ad, dim, send_bwd, send_fwd, st)
+                      : (recon == 12 ? pack_t<double, 12>(*Ad, dim, send_bwd, send_fwd, st) : pack_t<double, 18>(*Ad, dim, send_bwd, send_fwd, st));
+  return recon == 8 ? pack_t<float, 8>(*As, dim, send_bwd, send_fwd, st)
+                    : (recon == 12 ? pack_t<float, 12>(*As, dim, send_bwd, send_fwd, st) : pack_t<float, 18>(*As, dim, send_bwd, send_fwd, st));
 }
 
 template <typename F> static cudaError_t pack_p2p_t(int recon, const DslashArgs<F> &A, const PackDst<F> &D, cudaStream_t st) {
   int maxface = 0;
   for (int s = 0; s < D.nslot; s++) maxface = A.g.face[D.dim[s]] > maxface ? A.g.face[D.dim[s]] : maxface;
   dim3 grid((maxface + 127) / 128, 2, D.nslot);
-  if (recon == 12) halo_pack_p2p_kernel<F, 12><<<grid, 128, 0, st>>>(A, D);
-  else             halo_pack_p2p_kernel<F, 18><<<grid, 128, 0, st>>>(A, D);
+  if (recon == 8)       halo_pack_p2p_kernel<F, 8><<<grid, 128, 0, st>>>(A, D);
+  else if (recon == 12) halo_pack_p2p_kernel<F, 12><<<grid, 128, 0, st>>>(A, D);
+  else                  halo_pack_p2p_kernel<F, 18><<<grid, 128, 0, st>>>(A, D);
   return cudaGetLastError();
 }
 cudaError_t halo_pack_p2p(int recon, const DslashArgs<double> &A, const PackDst<double> &D, cudaStream_t st) { return pack_p2p_t<double>(recon, A, D, st); }

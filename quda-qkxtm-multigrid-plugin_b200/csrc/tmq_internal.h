@@ -181,6 +181,8 @@ int op_poly_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int deg, doub
 void eig_release(tmq_ctx *c);   // frees the eigensolver workspace of a context
 
 // dslash launchers (one TU per precision x recon)
+cudaError_t launch_dslash_d8(int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st);
+cudaError_t launch_dslash_s8(int epi, bool multi, const DslashArgs<float> &A, cudaStream_t st);
 cudaError_t launch_dslash_d12(int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st);
 cudaError_t launch_dslash_d18(int epi, bool multi, const DslashArgs<double> &A, cudaStream_t st);
 cudaError_t launch_dslash_s12(int epi, bool multi, const DslashArgs<float> &A, cudaStream_t st);

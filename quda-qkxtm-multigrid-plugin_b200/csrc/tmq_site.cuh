@@ -130,9 +130,97 @@ template <typename F> TMQ_HD void reconstruct_row2(Link<F> &L, F sign) {
 #undef U
 }
 
+// 8-real format (tools/recon8_study.py): U01, U02, U10 and t00 = tan(arg U00 / 4), t20 = tan(arg U20 / 4) are stored; for a unitary
+// link (times the boundary sign)  |U00|^2 = 1 - |U01|^2 - |U02|^2,  |U20|^2 = |U01|^2 + |U02|^2 - |U10|^2,  the phases come back by
+// the rational half-angle formulas (1 + t^2 in [1, 2]: no singular point, no trigonometric function), U11 and U12 solve
+//   conj(U01) U11 + conj(U02) U12 = -U10 conj(U00)   (rows 0 and 1 orthogonal)
+//   -U02 U11 + U01 U12 = sign conj(U20)              (row 2 = sign conj(row0 x row1), column 0)
+// whose determinant is |U01|^2 + |U02|^2 (links with U01 = U02 = 0, e.g. a unit field, cannot be stored: refused at load time).
+// reciprocal and reciprocal square root for the unpacking: a single-precision hardware seed and two Newton steps (the IEEE division
+// and square root of fp64 made the 8-real kernels compute-bound: 1.02 ms against 0.96 ms for the 12-real K1 at 48^3x96,
+// profiles/r25_sweep_recon8_exact_sqrt_div.jsonl); arguments lie in [1e-6, 8], well inside the single-precision range
+TMQ_HD double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double r = (double)__frcp_rn((float)x);
+  r = r * (2.0 - x * r);
+  return r * (2.0 - x * r);
+#else
+  return 1.0 / x;
+#endif
+}
+TMQ_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+// sqrt(x) for x >= 0 as x * rsqrt(x); 0 for x below the smallest normal single (rounding residue of an exactly vanishing entry)
+TMQ_HD double fast_sqrt_nn(double x) {
+#if defined(__CUDA_ARCH__)
+  if (!(x > 1e-36)) return 0.0;
+  double r = (double)rsqrtf((float)x);
+  r = r * (1.5 - 0.5 * x * r * r);
+  r = r * (1.5 - 0.5 * x * r * r);
+  return x * r;
+#else
+  return x > 0.0 ? sqrt(x) : 0.0;
+#endif
+}
+TMQ_HD float fast_sqrt_nn(float x) {
+#if defined(__CUDA_ARCH__)
+  return x > 1e-36f ? x * rsqrtf(x) : 0.0f;
+#else
+  return x > 0.0f ? sqrtf(x) : 0.0f;
+#endif
+}
+
+template <typename F> TMQ_HD void reconstruct_from8(Link<F> &L, F t00, F t20, F sign) {
+#define U(r, c, p) L.u[r][c][p]
+  const F rs = U(0, 1, 0) * U(0, 1, 0) + U(0, 1, 1) * U(0, 1, 1) + U(0, 2, 0) * U(0, 2, 0) + U(0, 2, 1) * U(0, 2, 1);
+  const F b2 = U(1, 0, 0) * U(1, 0, 0) + U(1, 0, 1) * U(1, 0, 1);
+  const F m00 = fast_sqrt_nn((F)1 - rs), m20 = fast_sqrt_nn(rs - b2);
+  // one reciprocal serves the three divisions: 1/(1 + t00^2), 1/(1 + t20^2), 1/rs
+  const F e00 = (F)1 + t00 * t00, e20 = (F)1 + t20 * t20;
+  const F q = fast_rcp(e00 * e20 * rs);
+  const F inv = q * e00 * e20;
+  {
+    const F d = q * e20 * rs, c2 = ((F)1 - t00 * t00) * d, s2 = (F)2 * t00 * d;
+    U(0, 0, 0) = m00 * (c2 * c2 - s2 * s2); U(0, 0, 1) = m00 * ((F)2 * s2 * c2);
+  }
+  {
+    const F d = q * e00 * rs, c2 = ((F)1 - t20 * t20) * d, s2 = (F)2 * t20 * d;
+    U(2, 0, 0) = m20 * (c2 * c2 - s2 * s2); U(2, 0, 1) = m20 * ((F)2 * s2 * c2);
+  }
+  // rhs1 = -U10 conj(U00), rhs2 = sign conj(U20)
+  const F r1r = -(U(1, 0, 0) * U(0, 0, 0) + U(1, 0, 1) * U(0, 0, 1)), r1i = -(U(1, 0, 1) * U(0, 0, 0) - U(1, 0, 0) * U(0, 0, 1));
+  const F r2r = sign * U(2, 0, 0), r2i = -sign * U(2, 0, 1);
+  // U11 = (rhs1 U01 - conj(U02) rhs2) / rs
+  U(1, 1, 0) = inv * (r1r * U(0, 1, 0) - r1i * U(0, 1, 1) - (U(0, 2, 0) * r2r + U(0, 2, 1) * r2i));
+  U(1, 1, 1) = inv * (r1r * U(0, 1, 1) + r1i * U(0, 1, 0) - (U(0, 2, 0) * r2i - U(0, 2, 1) * r2r));
+  // U12 = (conj(U01) rhs2 + U02 rhs1) / rs
+  U(1, 2, 0) = inv * (U(0, 1, 0) * r2r + U(0, 1, 1) * r2i + U(0, 2, 0) * r1r - U(0, 2, 1) * r1i);
+  U(1, 2, 1) = inv * (U(0, 1, 0) * r2i - U(0, 1, 1) * r2r + U(0, 2, 0) * r1i + U(0, 2, 1) * r1r);
+  F ar, ai;
+  // U21 = sign conj(U02 U10 - U00 U12),  U22 = sign conj(U00 U11 - U01 U10)   (as reconstruct_row2)
+  ar = U(0, 2, 0) * U(1, 0, 0) - U(0, 2, 1) * U(1, 0, 1) - U(0, 0, 0) * U(1, 2, 0) + U(0, 0, 1) * U(1, 2, 1);
+  ai = U(0, 2, 0) * U(1, 0, 1) + U(0, 2, 1) * U(1, 0, 0) - U(0, 0, 0) * U(1, 2, 1) - U(0, 0, 1) * U(1, 2, 0);
+  U(2, 1, 0) = sign * ar; U(2, 1, 1) = -sign * ai;
+  ar = U(0, 0, 0) * U(1, 1, 0) - U(0, 0, 1) * U(1, 1, 1) - U(0, 1, 0) * U(1, 0, 0) + U(0, 1, 1) * U(1, 0, 1);
+  ai = U(0, 0, 0) * U(1, 1, 1) + U(0, 0, 1) * U(1, 1, 0) - U(0, 1, 0) * U(1, 0, 1) - U(0, 1, 1) * U(1, 0, 0);
+  U(2, 2, 0) = sign * ar; U(2, 2, 1) = -sign * ai;
+#undef U
+}
+
 template <typename F, int RECON>
 TMQ_HD void load_link(Link<F> &L, const void *gauge, int parity, int mu, int idx, int stride, F sign12) {
-  if (RECON == 12) {
+  if (RECON == 8) {
+    const VecT<F> *b = (const VecT<F> *)gauge + (size_t)((parity * 4 + mu) * 2) * (size_t)stride + idx;
+    VecT<F> v0 = ld_stream(b), v1 = ld_stream(b + stride);
+    L.u[0][1][0] = v0.a; L.u[0][1][1] = v0.b; L.u[0][2][0] = v0.c; L.u[0][2][1] = v0.d;
+    L.u[1][0][0] = v1.a; L.u[1][0][1] = v1.b;
+    reconstruct_from8(L, v1.c, v1.d, sign12);
+  } else if (RECON == 12) {
     const VecT<F> *b = (const VecT<F> *)gauge + (size_t)((parity * 4 + mu) * 3) * (size_t)stride + idx;
     VecT<F> v0 = ld_stream(b), v1 = ld_stream(b + stride), v2 = ld_stream(b + 2 * (size_t)stride);
     L.u[0][0][0] = v0.a; L.u[0][0][1] = v0.b; L.u[0][1][0] = v0.c; L.u[0][1][1] = v0.d;

@@ -85,7 +85,7 @@ int main(int argc, char **argv) {
   gauge_param.cpu_prec = QUDA_DOUBLE_PRECISION;
   gauge_param.cuda_prec = QUDA_DOUBLE_PRECISION;
   gauge_param.cuda_prec_sloppy = prec_sloppy == "single" ? QUDA_SINGLE_PRECISION : QUDA_DOUBLE_PRECISION;
-  gauge_param.reconstruct = gauge_param.reconstruct_sloppy = recon == 12 ? QUDA_RECONSTRUCT_12 : QUDA_RECONSTRUCT_NO;
+  gauge_param.reconstruct = gauge_param.reconstruct_sloppy = recon == 8 ? QUDA_RECONSTRUCT_8 : (recon == 12 ? QUDA_RECONSTRUCT_12 : QUDA_RECONSTRUCT_NO);
   gauge_param.gauge_fix = QUDA_GAUGE_FIXED_NO;
   gauge_param.ga_pad = 0;
 

@@ -206,7 +206,7 @@ void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param) {
   }
   ensure_context(param->X);
   const int recon = (int)param->reconstruct;
-  if (recon != 12 && recon != 18) errorQuda("reconstruct must be 12 or 18");
+  if (recon != 8 && recon != 12 && recon != 18) errorQuda("reconstruct must be 8, 12 or 18");
   TMQ_OK(tmq_gauge_load(G.ctx, (const void *const *)h_gauge, (int)param->t_boundary, recon));
   G.gauge_loaded = true;
 }

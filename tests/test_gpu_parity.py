@@ -381,3 +381,56 @@ def test_error_paths_fail_loudly(tmq):
     with pytest.raises(tmq.TmqError):
         c.cg_mdagm(s4, s4)                           # solution must be fp64
     c.close()
+
+
+# ---- 8-real gauge format (opt-in; csrc/tmq_site.cuh: reconstruct_from8, tools/recon8_study.py) ---------------------------------
+def test_reconstruct_8_matches_oracle_and_the_12_real_path(tmq):
+    """the trig-free 8-real link format: hop (both parities, daggers) and M^dag M against the oracle within the fp64 / fp32 bounds, the
+    same CG iteration count as the CPU CG, the ghost-zone path (halo pack with U^dag from 8 reals), the clover build and the
+    plaquette from the 8-real field; a unit field cannot be stored and is refused"""
+    X = (4, 6, 4, 8)
+    s = get_setup(tmq, X, 8); o = s.oracle(); c = s.ctx
+    for prec in (8, 4):
+        a, b = c.spinor(prec), c.spinor(prec)
+        for out_parity in (0, 1):
+            src = s.odd if out_parity == 0 else s.even
+            a.set(src)
+            for dagger in (0, 1):
+                c.dslash(b, a, out_parity, dagger)
+                assert lu.rel_l2(b.get(), o.dslash(s.gauge, src, out_parity, dagger)) < TOL[prec], (prec, out_parity, dagger)
+        c.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
+        a.set(s.even)
+        c.mdagm(b, a)
+        assert lu.rel_l2(b.get(), o.mdagm(s.gauge, s.even, KAPPA, MU, 0)) < 2 * TOL[prec]
+    assert abs(c.plaquette() - o.plaquette(s.gauge)) < 1e-13
+    x, bb = c.spinor(8), c.spinor(8)
+    bb.set(s.even)
+    x_ref, it_ref, _, _ = o.cg_mdagm(s.gauge, s.even, KAPPA, MU, 0, tol=1e-10, maxiter=2000)
+    info = c.cg_mdagm(x, bb, tol=1e-10, maxiter=2000)
+    assert abs(info["iter"] - it_ref) <= 2 and info["true_res"] < 1.05e-10 and lu.rel_l2(x.get(), x_ref) < 1e-9
+    info4 = c.cg_mdagm(x, bb, tol=1e-10, maxiter=2000, sloppy_prec=4)
+    assert info4["true_res"] < 1.05e-10 and lu.rel_l2(x.get(), x_ref) < 1e-8
+    # ghost-zone path and clover on the 8-real field
+    c2 = tmq.Context(X)
+    c2.force_partition((0, 0, 1, 1))
+    c2.load_gauge(s.gauge, t_boundary=-1, recon=8)
+    c2.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
+    a2, b2 = c2.spinor(8), c2.spinor(8)
+    a2.set(s.even)
+    c2.mdagm(b2, a2)
+    assert lu.rel_l2(b2.get(), o.mdagm(s.gauge, s.even, KAPPA, MU, 0)) < 2e-13
+    csw = 1.57551
+    c2.clover_load(csw * KAPPA)
+    o.set_clover(o.clover_compute(s.gauge, csw * KAPPA))
+    c2.mdagm(b2, a2)
+    want = o.mdagm(s.gauge, s.even, KAPPA, MU, 0)
+    o.set_clover(None)
+    assert lu.rel_l2(b2.get(), want) < 4e-13
+    c2.close()
+    # a unit field has U01 = U02 = 0 everywhere: refused, like any field the format cannot hold
+    unit = np.zeros_like(s.gauge); unit[..., 0, 0, 0] = unit[..., 1, 1, 0] = unit[..., 2, 2, 0] = 1.0
+    c3 = tmq.Context(X)
+    with pytest.raises(tmq.TmqError):
+        c3.load_gauge(unit, t_boundary=1, recon=8)
+    c3.load_gauge(unit, t_boundary=1, recon=12)
+    c3.close()
