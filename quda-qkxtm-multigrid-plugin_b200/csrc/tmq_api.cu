@@ -625,6 +625,7 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
   switch (option) {
     case TMQ_OPT_PREFETCH: c->opt_prefetch = value ? 1 : 0; return 0;
     case TMQ_OPT_PACK_ASYNC: c->opt_pack_async = value ? 1 : 0; return 0;
+    case TMQ_OPT_CONTRACT_SLICES: c->opt_contract_slices = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_SMEAR_BLOCK_T: c->opt_smear_block_t = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {

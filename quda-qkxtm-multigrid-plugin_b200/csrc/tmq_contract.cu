@@ -966,6 +966,7 @@ int tmq_qkxtm_contract_baryons(tmq_ctx *c, const void *d_prop1, const void *d_pr
   const int NCH = 320;                                    // 2 propagator assignments x 10 channels x 4 x 4 spin components
   // time slices per pass: the site values of a pass (320 complex doubles per site) are held to about 2 GiB
   int nt = (int)(((size_t)2 << 30) / (V3 * NCH * sizeof(CplxT<double>)));
+  if (c->opt_contract_slices > 0 && c->opt_contract_slices < nt) nt = c->opt_contract_slices;
   if (nt < 1) nt = 1;
   if (nt > T) nt = T;
   MomProjector mp;
@@ -1095,6 +1096,7 @@ int tmq_qkxtm_fixsink_derivative(tmq_ctx *c, const void *d_seq_prop, const void 
   TMQ_REQUIRE(X <= 32 * DFT_MAXK && Y <= 32 * DFT_MAXK && Z <= 32 * DFT_MAXK, "spatial extent above %d not supported", 32 * DFT_MAXK);
   const int NCH = 68;                                    // 4 noether + 4 x 16 one-derivative
   int nt = (int)(((size_t)2 << 30) / (V3 * NCH * sizeof(CplxT<double>)));
+  if (c->opt_contract_slices > 0 && c->opt_contract_slices < nt) nt = c->opt_contract_slices;
   if (nt < 1) nt = 1;
   if (nt > T) nt = T;
   MomProjector mp;

@@ -107,6 +107,7 @@ struct tmq_ctx {
   unsigned int *ticket2;     // pack-kernel ticket
   unsigned int *seq_table;   // device table seq_table[i] = i: source of the copy-engine flag writes
   // grow-only device work space of the meson contraction (site values + the stages of the separable Fourier sum)
+  int opt_contract_slices = 0;   // TMQ_OPT_CONTRACT_SLICES
   void *contract_ws = nullptr;
   size_t contract_ws_bytes = 0;
 };

@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("TMQ_LIB_PATH") or os.path.join(os.path.dirname(_HERE)
 
 PREC_SINGLE, PREC_DOUBLE = 4, 8
 OPT_PREFETCH, OPT_HALO_P2P, OPT_BOUNDARY_AT_PCT, OPT_SMEAR_BLOCK_T = 1, 2, 3, 4
+OPT_PACK_ASYNC, OPT_CONTRACT_SLICES = 5, 6
 PARITY, FULL = 1, 2
 MATPC_EVEN_EVEN, MATPC_ODD_ODD, MATPC_EVEN_EVEN_ASYM, MATPC_ODD_ODD_ASYM = 0, 1, 2, 3
 

@@ -92,6 +92,11 @@ def test_baryon_contraction_matches_reference_fixture(tmq):
         assert _relmax(gotf[:, :, :, ip], want[:, :, :, ip]) < 2e-5, ip
     got2 = d.c.qkxtm_contract_baryons(d.bufs[0], d.bufs[1], 8, moms, G.SRC, G.X[3])
     assert np.array_equal(got, got2)                                  # fixed summation order
+    # large lattices are contracted in passes of a few time slices (2 GiB of site values per pass): force 1 and 4 slices per pass
+    for nslices in (1, 4):
+        d.c.set_option(tmq.OPT_CONTRACT_SLICES, nslices)
+        assert np.array_equal(d.c.qkxtm_contract_baryons(d.bufs[0], d.bufs[1], 8, moms, G.SRC, G.X[3]), got), nslices
+    d.c.set_option(tmq.OPT_CONTRACT_SLICES, 0)
     d.close()
 
 
@@ -171,6 +176,9 @@ def test_derivative_insertions_match_reference_fixture(tmq):
     gn, go = d.c.qkxtm_fixsink_derivative(d.put(p2), d.put(p1), d.put(U), 8, 1, 2, moms, G.SRC)       # (seq, fwd) = (p2, p1)
     assert _relmax(gn, _c(gold["thrp_noether_double"])) < 1e-13
     assert _relmax(go, _c(gold["thrp_oneD_double"])) < 1e-13
+    d.c.set_option(tmq.OPT_CONTRACT_SLICES, 1)                        # one time slice per pass: the neighbours in t lie outside the pass
+    gn1, go1 = d.c.qkxtm_fixsink_derivative(d.bufs[0], d.bufs[1], d.bufs[2], 8, 1, 2, moms, G.SRC)
+    assert np.array_equal(gn1, gn) and np.array_equal(go1, go)
     d.close()
     X = (6, 4, 2, 8)
     rng = np.random.default_rng(31)
