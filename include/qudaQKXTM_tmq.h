@@ -19,128 +19,115 @@
 
 #define QUDAQKXTM_DIM 4
 
-// ---- the slice of quda.h / enum_quda.h the path reads ----------------------------------------------
-typedef enum { QUDA_SINGLE_PRECISION = 4, QUDA_DOUBLE_PRECISION = 8 } QudaPrecision;
-typedef enum { QUDA_RECONSTRUCT_NO = 18, QUDA_RECONSTRUCT_12 = 12, QUDA_RECONSTRUCT_8 = 8 } QudaReconstructType;
-typedef enum { QUDA_ANTI_PERIODIC_T = -1, QUDA_PERIODIC_T = 1 } QudaTboundary;
-typedef enum { QUDA_QDP_GAUGE_ORDER = 0 } QudaGaugeFieldOrder;
-typedef enum { QUDA_WILSON_LINKS = 0, QUDA_SMEARED_LINKS = 1 } QudaLinkType;
-typedef enum { QUDA_GAUGE_FIXED_NO = 0 } QudaGaugeFixed;
-typedef enum { QUDA_TWISTED_MASS_DSLASH = 0, QUDA_WILSON_DSLASH = 1, QUDA_TWISTED_CLOVER_DSLASH = 2 } QudaDslashType;
-typedef enum { QUDA_CG_INVERTER = 0, QUDA_GCR_INVERTER = 1, QUDA_BICGSTAB_INVERTER = 2, QUDA_INVALID_INVERTER = -1 } QudaInverterType;
-typedef enum { QUDA_MAT_SOLUTION = 0, QUDA_MATPC_SOLUTION = 1, QUDA_MATPCDAG_MATPC_SOLUTION = 2 } QudaSolutionType;
-typedef enum { QUDA_DIRECT_SOLVE = 0, QUDA_NORMOP_SOLVE = 1, QUDA_DIRECT_PC_SOLVE = 2, QUDA_NORMOP_PC_SOLVE = 3 } QudaSolveType;
-typedef enum { QUDA_MATPC_EVEN_EVEN = 0, QUDA_MATPC_ODD_ODD = 1, QUDA_MATPC_EVEN_EVEN_ASYMMETRIC = 2,
-               QUDA_MATPC_ODD_ODD_ASYMMETRIC = 3 } QudaMatPCType;
-typedef enum { QUDA_KAPPA_NORMALIZATION = 0, QUDA_MASS_NORMALIZATION = 1, QUDA_ASYMMETRIC_MASS_NORMALIZATION = 2 } QudaMassNormalization;
-typedef enum { QUDA_DEGRAND_ROSSI_GAMMA_BASIS = 0, QUDA_UKQCD_GAMMA_BASIS = 1 } QudaGammaBasis;
-typedef enum { QUDA_DIRAC_ORDER = 0 } QudaDiracFieldOrder;
-typedef enum { QUDA_TWIST_SINGLET = 1, QUDA_TWIST_NO = 0 } QudaTwistFlavorType;
-typedef enum { QUDA_DAG_NO = 0, QUDA_DAG_YES = 1 } QudaDagType;
-typedef enum { QUDA_PRESERVE_SOURCE_NO = 0, QUDA_PRESERVE_SOURCE_YES = 1 } QudaPreserveSource;
-typedef enum { QUDA_CPU_FIELD_LOCATION = 1, QUDA_CUDA_FIELD_LOCATION = 2 } QudaFieldLocation;
-typedef enum { QUDA_L2_RELATIVE_RESIDUAL = 1 } QudaResidualType;
-typedef enum { QUDA_SILENT = 0, QUDA_SUMMARIZE = 1, QUDA_VERBOSE = 2 } QudaVerbosity;
-typedef enum { QUDA_PARITY_SITE_SUBSET = 1, QUDA_FULL_SITE_SUBSET = 2 } QudaSiteSubset;
-
-typedef struct QudaGaugeParam_s {       // fields set at qkxtm/Calc_Loops.cpp:189-225
-  int X[4];
-  double anisotropy;
-  QudaLinkType type;
-  QudaGaugeFieldOrder gauge_order;
-  QudaTboundary t_boundary;
-  QudaPrecision cpu_prec, cuda_prec, cuda_prec_sloppy, cuda_prec_precondition;
-  QudaReconstructType reconstruct, reconstruct_sloppy, reconstruct_precondition;
-  QudaGaugeFixed gauge_fix;
-  int ga_pad;
-} QudaGaugeParam;
-
-typedef struct QudaInvertParam_s {      // fields read / written on the path
-  double kappa, mu, mass;
-  double clover_coeff;                 // csw * kappa (qkxtm/MG_Bench.cpp:249), used by loadCloverQuda
-  QudaDslashType dslash_type;
-  QudaTwistFlavorType twist_flavor;
-  QudaMatPCType matpc_type;
-  QudaSolveType solve_type;
-  QudaSolutionType solution_type;
-  QudaInverterType inv_type, inv_type_precondition;
-  QudaMassNormalization mass_normalization;
-  QudaGammaBasis gamma_basis;
-  QudaDiracFieldOrder dirac_order;
-  QudaPrecision cpu_prec, cuda_prec, cuda_prec_sloppy, cuda_prec_precondition;
-  QudaPreserveSource preserve_source;
-  QudaFieldLocation input_location, output_location;
-  int sp_pad, cl_pad, Ls;
-  QudaDagType dagger;
-  double tol, tol_hq;
-  QudaResidualType residual_type;
-  int maxiter;
-  double reliable_delta;
-  int pipeline, gcrNkrylov;
-  QudaVerbosity verbosity, verbosity_precondition;
-  void *preconditioner;
-  // outputs (zeroed before each solve, lib/qudaQKXTM_interface.cpp:95-97; filled like updateInvertParam)
-  double spinorGiB, secs, gflops, true_res;
-  int iter;
-} QudaInvertParam;
-
-QudaGaugeParam newQudaGaugeParam(void);
-QudaInvertParam newQudaInvertParam(void);
-// qkxtm/QKXTM_util.cpp:48-68.  dims = the process grid (x, y, z, t), only z and t may exceed 1.  One process per rank; rank and world
-// size come from the launcher's environment (RANK / WORLD_SIZE of torchrun --no-python, OMPI_COMM_WORLD_*, PMI_*, SLURM_*), the rank <->
-// coordinate map has t fastest.  The NCCL communicator is created when the first field is (loadGaugeQuda / init_qudaQKXTM): rank 0
-// passes the id to the others through a file (TMQ_COMM_ID_FILE, default /tmp/tmq_nccl_id_<parent pid>_<MASTER_PORT>).
-void initCommsGridQuda(int nDim, const int *dims, void *func, void *fdata);
-int comm_rank(void);
-int comm_size(void);
-int comm_coord(int dim);
-void initQuda(int device);                                                     // qkxtm/Calc_Loops.cpp:753 (device < 0: the launcher's local rank)
-void loadGaugeQuda(void *h_gauge, QudaGaugeParam *param);                      // qkxtm/Calc_Loops.cpp:759 (void *gauge[4], QDP order)
-void freeGaugeQuda(void);
-// loadCloverQuda(NULL, NULL, &inv_param) (qkxtm/MG_Bench.cpp:605-608): the clover field is BUILT on the device from the resident
-// gauge field with inv_param->clover_coeff; host clover fields (h_clover / h_clovinv != NULL) are not supported
-void loadCloverQuda(void *h_clover, void *h_clovinv, QudaInvertParam *inv_param);
-void freeCloverQuda(void);
-void endQuda(void);
-// host spinors: full lattice, even-odd site order [even Vh | odd Vh][spin][colour][re,im], double
-void invertQuda(void *h_x, void *h_b, QudaInvertParam *param);
-void MatQuda(void *h_out, void *h_in, QudaInvertParam *param);                 // full operator (dslash_test-style check)
-void setVerbosityQuda(QudaVerbosity v);
+// ---- the slice of quda.h / enum_quda.h the path reads: enums, QudaGaugeParam, QudaInvertParam, QudaMultigridParam and the
+//      C API entry points (initQuda, loadGaugeQuda, invertQuda, ...) -----------------------------------------------------------------
+#include "quda_tmq.h"
 
 namespace quda {
 
 enum ALLOCATION_FLAG { NONE, HOST, DEVICE, BOTH, BOTH_EXTRA };                 // include/qudaQKXTM_utils.h:126
 enum CLASS_ENUM { FIELD, GAUGE, VECTOR, PROPAGATOR, PROPAGATOR3D, VECTOR3D };  // include/qudaQKXTM_utils.h:127
 
-#define MAX_NSOURCES 1000                                                     // include/qudaQKXTM_utils.h:16
-#define MAX_NMOMENTA 5000                                                     // include/qudaQKXTM_utils.h:19
-enum CORR_SPACE { POSITION_SPACE, MOMENTUM_SPACE };                            // include/qudaQKXTM_utils.h:41
-enum FILE_WRITE_FORMAT { ASCII_FORM, HDF5_FORM };                              // include/qudaQKXTM_utils.h:42
-enum WHICHPARTICLE { PROTON, NEUTRON };                                        // include/qudaQKXTM_utils.h:128
-enum WHICHPROJECTOR { G4, G5G123, G5G1, G5G2, G5G3 };                          // include/qudaQKXTM_utils.h:129
-#define MAX_TSINK 10                                                          // include/qudaQKXTM_utils.h:20
-#define MAX_PROJS 5                                                           // include/qudaQKXTM_utils.h:23
+// include/qudaQKXTM_utils.h:16-23
+#define MAX_NSOURCES 1000
+#define MAX_NMOMENTA 5000
+#define MAX_TSINK 10
+#define MAX_DEFLSTEPS 10
+#define MAX_LP_CRIT 10
+#define MAX_PROJS 5
+// include/qudaQKXTM_utils.h:25-29
+#define LEXIC(it,iz,iy,ix,L) ( (it)*L[0]*L[1]*L[2] + (iz)*L[0]*L[1] + (iy)*L[0] + (ix) )
+#define LEXIC_TZY(it,iz,iy,L) ( (it)*L[1]*L[2] + (iz)*L[1] + (iy) )
+#define LEXIC_TZX(it,iz,ix,L) ( (it)*L[0]*L[2] + (iz)*L[0] + (ix) )
+#define LEXIC_TYX(it,iy,ix,L) ( (it)*L[0]*L[1] + (iy)*L[0] + (ix) )
+#define LEXIC_ZYX(iz,iy,ix,L) ( (iz)*L[0]*L[1] + (iy)*L[0] + (ix) )
 
-typedef struct {                       // the slice of qudaQKXTMinfo the built paths read (include/qudaQKXTM_utils.h:45-75)
-  int nsmearAPE, nsmearGauss;
-  double alphaAPE, alphaGauss;
+enum SOURCE_T { UNITY, RANDOM };                                               // include/qudaQKXTM_utils.h:41-43
+enum CORR_SPACE { POSITION_SPACE, MOMENTUM_SPACE };
+enum FILE_WRITE_FORMAT { ASCII_FORM, HDF5_FORM };
+enum WHICHPARTICLE { PROTON, NEUTRON };                                        // include/qudaQKXTM_utils.h:128-132
+enum WHICHPROJECTOR { G4, G5G123, G5G1, G5G2, G5G3 };
+enum THRP_TYPE { THRP_LOCAL, THRP_NOETHER, THRP_ONED };
+enum APEDIM { D3, D4 };
+
+// qudaQKXTMinfo, FIELD FOR FIELD as include/qudaQKXTM_utils.h:45-75: every entry point takes it BY VALUE, so the layout is part of the
+// ABI (tests/test_dropin_compile.py static_asserts sizeof / offsetof of every member against the reference header).  Members the built
+// paths do not read (nsmearAPE / alphaAPE, the name tables, HighMomForm, csw, ...) are present and ignored.
+typedef struct {
+  int nsmearAPE;
+  int nsmearGauss;
+  double alphaAPE;
+  double alphaGauss;
   int lL[QUDAQKXTM_DIM];
   int Nsources;
   int sourcePosition[MAX_NSOURCES][QUDAQKXTM_DIM];    // global (x, y, z, t)
   QudaPrecision Precision;
   int Q_sq;                            // momenta with p^2 <= Q_sq (createMomenta, lib/qudaQKXTM_kernels.cu:98-116)
-  int traj;
-  bool check_files;
   int Ntsink;                          // sink-source separations of the three-point function
   int Nproj[MAX_TSINK];
+  int traj;
+  bool check_files;
+  char *thrp_type[3];                  // filled by the entry points themselves (lib/qudaQKXTM_interface.cpp:276-288), never read from the caller
+  char *thrp_proj_type[5];
+  char *baryon_type[10];
+  char *meson_type[10];
   int tsinkSource[MAX_TSINK];
   int proj_list[MAX_TSINK][MAX_PROJS]; // WHICHPROJECTOR values
-  int run3pt_src[MAX_NSOURCES];        // != 0: also the fixed-sink three-point function (ultra-local insertion) for this source
+  int run3pt_src[MAX_NSOURCES];        // != 0: also the fixed-sink three-point function for this source
   FILE_WRITE_FORMAT CorrFileFormat;    // ASCII_FORM only (no HDF5 here)
+  SOURCE_T source_type;                // stochastic sources of calc_loops: RANDOM (Z4 noise) or UNITY
   CORR_SPACE CorrSpace;
+  bool HighMomForm;
   bool isEven;
-  double kappa, mu, csw, inv_tol;
+  double kappa;
+  double mu;
+  double csw;
+  double inv_tol;
 } qudaQKXTMinfo;
+
+// include/qudaQKXTM_utils.h:77-94 (the reference guards it with HAVE_ARPACK; the eigensolver here is libtmq's own, so it is always there)
+enum WHICHSPECTRUM { SR, LR, SM, LM, SI, LI };
+typedef struct {
+  int PolyDeg;                 // degree of the Chebyshev polynomial
+  int nEv;                     // number of eigenvectors wanted
+  int nKv;                     // size of the Krylov space
+  WHICHSPECTRUM spectrumPart;  // SR or LR (eigenvalues of M^dag M are real and positive: SM = SR, LM = LR)
+  bool isACC;
+  double tolArpack;
+  int maxIterArpack;
+  char arpack_logfile[512];    // unused (no ARPACK)
+  double amin;
+  double amax;
+  bool isEven;
+  bool isFullOp;               // false: even-odd M_pc^dag M_pc; true: the unpreconditioned M^dag M (what calc_loops deflates with)
+  int modeArpack;              // unused
+} qudaQKXTM_arpackInfo;
+
+// include/qudaQKXTM_utils.h:96-124 (with HAVE_ARPACK: nSteps_defl / deflStep are members)
+typedef struct {
+  int Nstoch;                  // number of stochastic sources
+  unsigned long int seed;      // gsl_rng_ranlux seed; rank r uses seed + r * seed (lib/qudaQKXTM_interface.cpp:1951)
+  int Ndump;                   // dump every Ndump sources
+  char loop_fname[512];
+  int nSteps_defl;
+  int deflStep[MAX_DEFLSTEPS];
+  int traj;
+  int Nprint;
+  int Nmoms;
+  int Qsq = 0;
+  FILE_WRITE_FORMAT FileFormat;
+  char *loop_type[6];          // filled by calc_loops itself (lib/qudaQKXTM_interface.cpp:1517-1534)
+  bool loop_oneD[6];
+  int k_probing;               // <= 0: hierarchical probing off
+  int hadamLow;
+  int hadamHigh;
+  bool spinColorDil;           // spin-colour dilution: 12 solves per noise vector
+  bool HighMomForm;
+  double kappa;
+  double mu;
+  double csw;
+  double inv_tol;
+} qudaQKXTM_loopInfo;
 
 void init_qudaQKXTM(qudaQKXTMinfo *info);      // lib/qudaQKXTM_kernels.cu:118-297 (one-shot; containers need it)
 void printf_qudaQKXTM();
@@ -286,21 +273,6 @@ int qkxtm_Nmoms();                                  // GK_Nmoms / GK_moms after 
 const int *qkxtm_moms();                            // [Nmoms][3]
 
 // ---- exact deflation (include/qudaQKXTM.h:391-475, include/qudaQKXTM_utils.h:76-94) ------------------------------------
-enum WHICHSPECTRUM { SR, LR, SM, LM, SI, LI };
-typedef struct {
-  int PolyDeg;                 // degree of the Chebyshev polynomial
-  int nEv;                     // number of eigenvectors wanted
-  int nKv;                     // size of the Krylov space
-  WHICHSPECTRUM spectrumPart;  // SR or LR (eigenvalues of M^dag M are real and positive: SM = SR, LM = LR)
-  bool isACC;
-  double tolArpack;
-  int maxIterArpack;
-  char arpack_logfile[512];    // unused (no ARPACK)
-  double amin, amax;
-  bool isEven;
-  bool isFullOp;               // false: even-odd M_pc^dag M_pc; true: the unpreconditioned M^dag M (what calc_loops deflates with)
-  int modeArpack;              // unused
-} qudaQKXTM_arpackInfo;
 
 // QKXTM_Deflation for the even-odd or the full M^dag M: the Krylov basis and the eigenvectors stay resident in HBM (the reference
 // keeps NkV host vectors and stages every ARPACK reverse-communication step through PCIe).  The eigensolver is a
@@ -333,7 +305,10 @@ public:
   void eigenSolver();                                                                  // Deflation.cpp:1069-1475
   void polynomialOperator(ColorSpinorField &out, const ColorSpinorField &in);         // :997-1063
   void deflateVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in);     // :614-800 (vec_in: host AoS)
-  void projectVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in, int is, int NeV_defl);   // :1926-2060 (isFullOp)
+  void projectVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in, int is);                 // :1931-2059 (isFullOp; all NeV vectors)
+  void projectVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in, int is, int NeV_defl);   // :2063-2190 (isFullOp)
+  void MapEvenOddToFull();                                                                                // :285-335 (nothing to do here: see the .cpp)
+  void MapEvenOddToFull(int i);
   void ApplyMdagM(Float *vec_out, Float *vec_in, QudaInvertParam *param);             // :189-281
   void copyEigenVectorToQKXTM_Vector(int eigenVector_id, Float *vec);                 // :449-536 (full volume, AoS)
   tmq_eigset *EigenSet() const { return set; }
@@ -346,16 +321,58 @@ void qkxtm_set_error_handler(qkxtm_error_handler h);   // default: print and abo
 
 }  // namespace quda
 
-// ---- solve entry points (include/qudaQKXTM.h:484-513) --------------------------------------------------------------
+// ---- solve entry points: EXACTLY the reference's signatures (include/qudaQKXTM.h:484-513; structs by value), plus overloads that
+//      hand results back to the caller.  A driver written against the reference header links against these symbols unchanged. -------
 // MG_bench: the 12-column point-source propagator skeleton of lib/qudaQKXTM_interface.cpp:19-233 with the
 // solver swapped for CG on M^dag M, as the calc_loops CG branch does (lib/qudaQKXTM_interface.cpp:2031-2038):
 //   point source -> packVector -> loadVector -> uploadToCuda -> prepare -> in <- M^dag in -> CG -> reconstruct
 //   -> downloadFromCuda -> scaleVector(2 kappa) if mass-normalised.
 // gaugeSmeared: lexicographic links for the plaquette print (may be NULL); gauge: unused, as in the reference
-// (the solver uses the field resident since loadGaugeQuda).  prop_out (optional, not in the reference, which
-// discards the columns): 12 x V x 24 doubles, column-major host AoS.
-void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param,
-              quda::qudaQKXTMinfo info, double *prop_out = nullptr);
+// (the solver uses the field resident since loadGaugeQuda).
+void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, quda::qudaQKXTMinfo info);
+// overload (not in the reference, which discards the columns): prop_out = 12 x V x 24 doubles, column-major host AoS; the D2H copy of
+// column k runs behind the solve of column k+1
+void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, quda::qudaQKXTMinfo info, double *prop_out);
+
+// calc_loops (include/qudaQKXTM.h:501-507, lib/qudaQKXTM_interface.cpp:1409-2233), everything except the loop CONTRACTIONS (SURVEY.md 2:
+// out of scope; upstream's contract / covariant-derivative conventions are not in the tree):
+//   parameter checks (:1473-1494) -> QKXTM_Deflation::eigenSolver on the operator of EVparam (:1725-1736) -> [exact part: hook only]
+//   -> plaquette of gaugeToPlaquette (:1843-1848) -> for every stochastic source is < Nstoch: Z4 / unity noise from gsl_rng_ranlux
+//   seeded seed + rank * seed (:1951,1982; the generator is restated and pinned to GSL's own known-answer test), for every Hadamard
+//   vector of the hierarchical probing (k_probing > 0, :1438-1458, lib/qudaQKXTM_utils.cpp:476-717) and every spin-colour component
+//   (spinColorDil, :1994-2005): packVector -> loadVector -> uploadToCuda -> prepare -> M^dag -> CG -> reconstruct (:2008-2041), then for
+//   every deflation step downloadFromCuda -> projectVector(NeV_defl) -> uploadToCuda (:2056-2067) -> [oneEndTrick_w_One_Der: hook only].
+// Where the reference contracts, the installed hook (if any) receives the projected solution; without a hook the step is a no-op and
+// no loop files are written.  HDF5 output and the GCR + multigrid solver are refused.
+void calc_loops(void **gaugeToPlaquette, QudaInvertParam *EVparam, QudaInvertParam *param, QudaGaugeParam *gauge_param,
+                quda::qudaQKXTM_arpackInfo arpackInfo, quda::qudaQKXTM_loopInfo loopInfo, quda::qudaQKXTMinfo info);
+namespace quda {
+// what calc_loops hands to the hook in place of the reference's contraction calls
+struct qkxtm_loop_event {
+  int kind;                    // 0: eigenpair n of the exact part (Loop_w_One_Der_FullOp_Exact, :1775); 1: projected solution (oneEndTrick_w_One_Der, :2074)
+  int is, ih, sc;              // stochastic source, Hadamard vector, spin-colour component (kind 1); n in `is` for kind 0
+  int dstep, NeV_defl;         // deflation step and its number of projected-out eigenvectors (kind 1)
+  ColorSpinorField *x;         // kind 1: the projected full-volume solution on the device; kind 0: eigenvector n (FULL field)
+  double eigenvalue;           // kind 0
+  const double *h_source;      // kind 1: the (diluted) host source of this solve, plug-in AoS order [x_lex][s][c][ri]
+  int iter;                    // kind 1: CG iterations of this solve
+  double true_res;
+};
+typedef void (*qkxtm_loop_hook)(const qkxtm_loop_event *ev, void *user);
+void qkxtm_set_loop_hook(qkxtm_loop_hook hook, void *user);
+// the noise / dilution helpers of lib/qudaQKXTM_utils.cpp on host vectors in the plug-in's AoS order (exposed for tests and drivers)
+void *qkxtm_rng_alloc(unsigned long int seed);                              // gsl_rng_alloc(gsl_rng_ranlux) + gsl_rng_set
+void qkxtm_rng_free(void *rng);
+unsigned long int qkxtm_rng_get(void *rng);                                 // gsl_rng_get
+unsigned long int qkxtm_rng_uniform_int(void *rng, unsigned long int n);    // gsl_rng_uniform_int
+template <typename Float> void getStochasticRandomSource(void *spinorIn, void *rng, SOURCE_T source_type);                  // :148-180
+unsigned short int *hch_coloring(int k, int d);                                                                              // :666-717 (malloc'ed)
+int HadamardElements(int i, int j);                                                                                          // :696-708
+template <typename Float> void get_probing4D_spinColor_dilution(void *temp_input_vector, void *input_vector, unsigned short int *Vc, int ih, int sc);
+template <typename Float> void get_spinColor_dilution(void *temp_input_vector, void *input_vector, int sc);
+template <typename Float> void get_probing4D_dilution(void *temp_input_vector, void *input_vector, unsigned short int *Vc, int ih);
+}  // namespace quda
+
 // the per-RHS solve of calc_loops' CG branch (lib/qudaQKXTM_interface.cpp:2008-2041,2062) for one host source in
 // the plug-in's AoS order [x_lex][s][c][ri]; the solution comes back in the same order.
 void calc_loops_solve(double *h_solution, double *h_source, QudaInvertParam *param, quda::qudaQKXTMinfo info);
@@ -364,19 +381,20 @@ void calc_loops_solve(double *h_solution, double *h_source, QudaInvertParam *par
 // M_pc^dag M_pc -> downloadFromCuda/unloadVector/unpackVector; the other parity comes back zero-filled.
 void ApplyMdagM(double *h_out, double *h_in, QudaInvertParam *param, bool isEven);
 
-// calcMG_threepTwop_EvenOdd (include/qudaQKXTM.h:494-499, lib/qudaQKXTM_interface.cpp:236-1290), the TWO-POINT part:
-// for every source position, 12 + 12 point-source solves (up: +mu, down: -mu; Gaussian-smeared source), columns cast to float
-// and absorbed into K_prop_up / K_prop_down, sink smearing, rotateToPhysicalBase_device(+-1), contractBaryons, contractMesons, and
-// the ASCII files "<filename_twop>.baryons.SS.xx.yy.zz.tt.dat" / "<filename_twop>.mesons.SS.xx.yy.zz.tt.dat".  CG on M^dag M replaces the reference's GCR + multigrid solver (the
-// preconditionerUP/DN patch to quda.h, README:84-108).  Three-point functions (info.run3pt_src != 0) and HDF5 output are not built and
-// are refused.
+// calcMG_threepTwop_EvenOdd (include/qudaQKXTM.h:494-499, lib/qudaQKXTM_interface.cpp:236-1290): for every source position, 12 + 12
+// point-source solves (up: +mu, down: -mu; Gaussian-smeared source), columns cast to float and absorbed into K_prop_up / K_prop_down,
+// the fixed-sink three-point functions where info.run3pt_src != 0, sink smearing, rotateToPhysicalBase_device(+-1), contractBaryons,
+// contractMesons, and the ASCII files "<filename_twop>.baryons.SS.xx.yy.zz.tt.dat" / "<filename_twop>.mesons.SS.xx.yy.zz.tt.dat".  CG on
+// M^dag M replaces the reference's GCR + multigrid solver (the preconditionerUP/DN patch to quda.h, README:84-108).  HDF5 output is refused.
 void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param,
                                quda::qudaQKXTMinfo info, char *filename_twop, char *filename_threep, quda::WHICHPARTICLE NUCLEON);
 
 // calcLowModeProjection (include/qudaQKXTM.h:508-510, lib/qudaQKXTM_interface.cpp:1342-1401): the low modes of M^dag M through
 // QKXTM_Deflation::eigenSolver, with the reference's consistency checks (asymmetric operators only, parity of the operator and of
-// arpackInfo must agree).  Returns nothing, like the reference; nconv / evals (optional, not in the reference) report the result.
-void calcLowModeProjection(QudaInvertParam *evInvParam, quda::qudaQKXTM_arpackInfo arpackInfo, int *nconv = nullptr, double *evals = nullptr);
+// arpackInfo must agree).  Returns nothing, like the reference.
+void calcLowModeProjection(QudaInvertParam *evInvParam, quda::qudaQKXTM_arpackInfo arpackInfo);
+// overload: nconv / evals report the result
+void calcLowModeProjection(QudaInvertParam *evInvParam, quda::qudaQKXTM_arpackInfo arpackInfo, int *nconv, double *evals);
 
 // ---- configuration I/O (include/QKXTM_read_conf.h:816-848) -----------------------------------------------------------
 // reads this rank's sub-block of an ILDG / LIME configuration into the QDP even-odd host order of loadGaugeQuda and sets

@@ -53,6 +53,11 @@ int tmq_sync(tmq_ctx *);
  * communicator QUDA builds in initCommsGridQuda (qkxtm/QKXTM_util.cpp:48-68).                             */
 int tmq_comm_unique_id(char id128[128]);
 int tmq_comm_init(tmq_ctx *, const char id128[128], int nranks, int rank);
+/* rendezvous of all ranks of the communicator: an NCCL all-reduce (which waits without a time limit) followed by a host wait on
+ * the context's streams.  Replaces the MPI_Barrier / MPI_Bcast / MPI_Gather ordering points of the reference's host code
+ * (e.g. lib/qudaQKXTM_Vector.cpp:625, lib/qudaQKXTM_Contraction.cpp:1580-1584): call it after any phase in which ranks diverge
+ * (file I/O by one rank), so that the bounded halo waits of the next Dslash never see that skew.  No-op on one rank.            */
+int tmq_barrier(tmq_ctx *);
 /* force the ghost-zone (pack -> exchange -> interior/boundary) path in dimension d even when grid[d] = 1,
  * where the exchange wraps onto this rank: the reference's --partition mask (qkxtm/QKXTM_util.cpp:1717-1720).
  * Only z (part[2]) and t (part[3]) may be set.  Must be called before any field is created.              */

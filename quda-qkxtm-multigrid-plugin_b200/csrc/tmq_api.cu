@@ -610,6 +610,11 @@ int tmq_comm_init(tmq_ctx *c, const char id128[128], int nranks, int rank) {
   TMQ_TRY(comm_init(c, id128, nranks, rank));
   return comm_setup_p2p(c);     // map the neighbours' ghost arenas (CUDA IPC); falls back to NCCL send/recv
 }
+int tmq_barrier(tmq_ctx *c) {
+  TMQ_REQUIRE(c, "null context");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  return comm_barrier(c);
+}
 int tmq_halo_mode(tmq_ctx *c) { return c ? (c->multi ? (c->p2p ? 1 + c->opt_p2p : 1) : 0) : -1; }
 
 int tmq_set_tile(tmq_ctx *c, int ty, int tz, int tt) {

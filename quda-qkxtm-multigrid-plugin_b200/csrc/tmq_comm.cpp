@@ -190,6 +190,16 @@ int comm_setup_p2p(tmq_ctx *c) {
   return 0;
 }
 
+// rendezvous: NCCL all-reduce of a scratch scalar (NCCL waits for every rank, however late) + host wait
+int comm_barrier(tmq_ctx *c) {
+  TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  TMQ_CUDA(cudaStreamSynchronize(c->comm_stream));
+  if (!c->comm || c->comm->nranks == 1) return 0;
+  TMQ_NCCL(g_nccl.AllReduce(c->scal + SC_BARRIER, c->scal + SC_BARRIER, 1, ncclDouble, ncclSum, c->comm->comm, c->stream));
+  TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // in-place sum of n doubles of the device scalar block across ranks
 int comm_allreduce(tmq_ctx *c, double *d_ptr, int n, cudaStream_t st) {
   if (!c->comm || c->comm->nranks == 1) return 0;

@@ -243,6 +243,7 @@ int comm_init(tmq_ctx *c, const char id128[128], int nranks, int rank);
 void comm_destroy(tmq_ctx *c);
 int comm_exchange(tmq_ctx *c, int pi, int prec, cudaStream_t st);
 int comm_allreduce(tmq_ctx *c, double *d_ptr, int n, cudaStream_t st);
+int comm_barrier(tmq_ctx *c);
 int comm_sendrecv_dim(tmq_ctx *c, int dim, const void *send_bwd, const void *send_fwd, void *recv_from_fwd, void *recv_from_bwd,
                       size_t nbytes, cudaStream_t st);
 

@@ -15,6 +15,7 @@ enum {
   SC_T0 = 4, SC_T1 = 5, SC_T2 = 6, SC_T3 = 7,   // generic reduction results (norm2, dots)
   SC_ONE = 8, SC_ZERO = 9,
   SC_ERR = 10,                // raised by a Dslash kernel whose halo wait timed out
+  SC_BARRIER = 11,            // scratch of tmq_barrier's all-reduce
   SC_COUNT = 16
 };
 

@@ -34,6 +34,9 @@ int main(int argc, char **argv) {
   int grid[4] = {1, 1, 1, 1};
   std::string particle = "proton";
   std::string dslash_type = "twisted-mass";
+  int Nstoch = 1, NdumpStep = 1, k_probing = 0, hadamLow = 0, hadamHigh = 0, n_defl_steps = 0, defl_step_nEv[MAX_DEFLSTEPS] = {0};
+  bool spinColorDil = false, isFullOp = false;
+  std::string source_type = "random";
   int nsmearGauss = 0; double alphaGauss = 4.0;                              // qkxtm/QKXTM_util.cpp:1652-1654
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -69,6 +72,15 @@ int main(int argc, char **argv) {
     else if (a == "--tsink") { need(1); tsink = atoi(argv[++i]); }             // > 0: also the three-point function at this sink-source separation
     else if (a == "--proj") { need(1); proj = atoi(argv[++i]); }               // WHICHPROJECTOR 0..4
     else if (a == "--particle") { need(1); particle = argv[++i]; }            // proton | neutron
+    else if (a == "--Nstoch") { need(1); Nstoch = atoi(argv[++i]); }           // the loop flags of qkxtm/QKXTM_util.cpp (Calc_Loops.cpp:87-103)
+    else if (a == "--NdumpStep") { need(1); NdumpStep = atoi(argv[++i]); }
+    else if (a == "--k-probing") { need(1); k_probing = atoi(argv[++i]); }
+    else if (a == "--hadamLow") { need(1); hadamLow = atoi(argv[++i]); }
+    else if (a == "--hadamHigh") { need(1); hadamHigh = atoi(argv[++i]); }
+    else if (a == "--spinColorDil") { need(1); spinColorDil = std::string(argv[++i]) == "yes"; }
+    else if (a == "--isFullOp") { need(1); isFullOp = std::string(argv[++i]) == "yes"; }
+    else if (a == "--source-type") { need(1); source_type = argv[++i]; }      // random | unity
+    else if (a == "--defl-steps") { need(1); n_defl_steps = atoi(argv[++i]); need(n_defl_steps); for (int d = 0; d < n_defl_steps && d < MAX_DEFLSTEPS; d++) defl_step_nEv[d] = atoi(argv[++i]); }
     else if (a == "--help") { usage(); return 0; }
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
   }
@@ -185,6 +197,53 @@ int main(int argc, char **argv) {
     result.insert(result.end(), K_defl.H_elem(), K_defl.H_elem() + (size_t)V * 24);
     inv_param.iter = deflation->MatVecs();
     delete deflation;
+  } else if (test == "calcloops") {
+    // qkxtm/Calc_Loops.cpp main() (:585-791): arpackInfo, loopInfo, the operator of the eigensolver, then calc_loops.  The hook stands where
+    // the reference contracts: it records every eigenvalue of the exact part and, for every solve and deflation step, the host source and
+    // the projected solution (both in the plug-in's AoS order), so that the test can check the whole chain against the CPU oracle.
+    qudaQKXTM_arpackInfo arpackInfo;
+    memset(&arpackInfo, 0, sizeof(arpackInfo));
+    arpackInfo.PolyDeg = polydeg; arpackInfo.nEv = nev; arpackInfo.nKv = nkv; arpackInfo.isACC = polydeg > 0; arpackInfo.tolArpack = eig_tol;
+    arpackInfo.maxIterArpack = 1000; arpackInfo.amin = amin; arpackInfo.amax = amax; arpackInfo.isEven = info.isEven; arpackInfo.isFullOp = isFullOp;
+    arpackInfo.spectrumPart = SR;
+    info.source_type = source_type == "unity" ? UNITY : RANDOM;
+    qudaQKXTM_loopInfo loopInfo;
+    memset((void *)&loopInfo, 0, sizeof(loopInfo));
+    loopInfo.Nstoch = Nstoch; loopInfo.seed = (unsigned long int)seed; loopInfo.Ndump = NdumpStep; loopInfo.traj = 0; loopInfo.Qsq = q_sq;
+    loopInfo.k_probing = k_probing; loopInfo.spinColorDil = spinColorDil; loopInfo.hadamLow = hadamLow; loopInfo.hadamHigh = hadamHigh;
+    snprintf(loopInfo.loop_fname, sizeof(loopInfo.loop_fname), "%s", out.empty() ? "loop" : out.c_str());
+    loopInfo.kappa = inv_param.kappa; loopInfo.csw = csw; loopInfo.mu = mu; loopInfo.inv_tol = tol; loopInfo.FileFormat = ASCII_FORM;
+    loopInfo.Nprint = loopInfo.Nstoch / loopInfo.Ndump;
+    if (n_defl_steps == 0) { loopInfo.nSteps_defl = 1; loopInfo.deflStep[0] = nev; }       // Calc_Loops.cpp:656-659
+    else { loopInfo.nSteps_defl = n_defl_steps; for (int a_ = 0; a_ < n_defl_steps; a_++) loopInfo.deflStep[a_] = defl_step_nEv[a_]; }
+    if (inv_param.mu > 0) inv_param.mu = -inv_param.mu;                        // "For the loops we invert the negative mu" (Calc_Loops.cpp:424)
+    QudaInvertParam EVinv_param = inv_param;                                    // Calc_Loops.cpp:709-715
+    EVinv_param.matpc_type = info.isEven ? QUDA_MATPC_EVEN_EVEN_ASYMMETRIC : QUDA_MATPC_ODD_ODD_ASYMMETRIC;
+    EVinv_param.mass_normalization = QUDA_MASS_NORMALIZATION;
+    std::vector<double> lex((size_t)4 * V * 18);
+    double *glex[4];
+    for (int mu_ = 0; mu_ < 4; mu_++) {
+      glex[mu_] = lex.data() + (size_t)mu_ * V * 18;
+      for (long long i = 0; i < V; i++) {
+        const int x0 = i % dim[0], y = (i / dim[0]) % dim[1], z = (i / ((long long)dim[0] * dim[1])) % dim[2], t = i / ((long long)dim[0] * dim[1] * dim[2]);
+        const long long eo = (long long)((x0 + y + z + t) & 1) * (V / 2) + i / 2;
+        memcpy(glex[mu_] + i * 18, gauge[mu_] + eo * 18, 18 * sizeof(double));
+      }
+    }
+    struct Rec { std::vector<double> *out; long long V; bool isEven; } rec = {&result, V, info.isEven};
+    qkxtm_set_loop_hook([](const qkxtm_loop_event *ev, void *user) {
+      Rec *r = (Rec *)user;
+      QKXTM_Vector<double> K(BOTH, VECTOR);
+      K.downloadFromCuda(ev->x, r->isEven);
+      K.download();
+      const double head[8] = {(double)ev->kind, (double)ev->is, (double)ev->ih, (double)ev->sc, (double)ev->dstep, (double)ev->NeV_defl,
+                              ev->kind == 0 ? ev->eigenvalue : (double)ev->iter, ev->true_res};
+      r->out->insert(r->out->end(), head, head + 8);
+      if (ev->kind == 1) r->out->insert(r->out->end(), ev->h_source, ev->h_source + (size_t)r->V * 24);
+      r->out->insert(r->out->end(), K.H_elem(), K.H_elem() + (size_t)r->V * 24);
+    }, &rec);
+    calc_loops((void **)glex, &EVinv_param, &inv_param, &gauge_param, arpackInfo, loopInfo, info);
+    qkxtm_set_loop_hook(nullptr, nullptr);
   } else if (test == "lowmodes") {
     // qkxtm/CalcLowModeProjection.cpp main(): the low modes of the asymmetric even-odd M^dag M
     qudaQKXTM_arpackInfo ai;

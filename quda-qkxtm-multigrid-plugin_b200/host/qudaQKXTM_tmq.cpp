@@ -4,6 +4,7 @@
 // which the reference also runs on the CPU; everything else is a call into the CUDA library.
 #include "../../include/qudaQKXTM_tmq.h"
 #include "../../include/tmq_host.h"
+#include "qkxtm_internal.h"
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -157,9 +158,29 @@ QudaInvertParam newQudaInvertParam(void) {
   return p;
 }
 
-void setVerbosityQuda(QudaVerbosity v) { G.verbosity = v; }
+void setVerbosityQuda(QudaVerbosity v, const char *, FILE *) { G.verbosity = v; }
 
-void initCommsGridQuda(int nDim, const int *dims, void *, void *) {
+QudaMultigridParam newQudaMultigridParam(void) {
+  QudaMultigridParam p;
+  memset(&p, 0, sizeof(p));
+  return p;
+}
+// The multigrid solver is out of scope.  qkxtm/MG_Bench.cpp:614 and CalcMG_2pt3pt_EvenOdd.cpp call newMultigridQuda
+// unconditionally and only pass the handle on in inv_param.preconditioner, so it must not abort: it warns and returns an inert handle;
+// the solves then run CG on the normal operator (--inv-type cg --solve-type normop-pc), anything else is refused by the entry points.
+static int g_mg_sentinel;
+void *newMultigridQuda(QudaMultigridParam *) {
+  if (G.verbosity > QUDA_SILENT && G.rank == 0)
+    fprintf(stderr, "WARNING: newMultigridQuda: the multigrid preconditioner is not provided by this library; the handle is inert and the solves use "
+                    "CG on M^dag M (run the drivers with --inv-type cg --solve-type normop-pc)\n");
+  return &g_mg_sentinel;
+}
+void destroyMultigridQuda(void *mg_instance) {
+  if (mg_instance && mg_instance != &g_mg_sentinel) errorQuda("destroyMultigridQuda: not a handle of this library");
+}
+
+void initCommsGridQuda(int nDim, const int *dims, QudaCommsMap func, void *) {
+  if (func) errorQuda("initCommsGridQuda: a custom rank map is not supported (pass NULL: lexicographic, t fastest)");
   if (nDim != 4) errorQuda("Number of communication grid dimensions must be 4");
   if (G.ctx) errorQuda("initCommsGridQuda must come before the first field is created");
   if (dims[0] != 1 || dims[1] != 1) errorQuda("only z and t may be partitioned (gridsize %d %d %d %d)", dims[0], dims[1], dims[2], dims[3]);
@@ -175,9 +196,42 @@ void initCommsGridQuda(int nDim, const int *dims, void *, void *) {
   int r = G.rank;
   for (int d = 3; d >= 0; d--) { G.coord[d] = r % G.grid[d]; r /= G.grid[d]; }
 }
+// the slice of upstream's comm_quda.h / util_quda.h that the reference's driver-side sources use (qkxtm/QKXTM_util.cpp:55-68,
+// include/QKXTM_read_conf.h:98): declared in include/compat/{comm_quda.h,util_quda.h}
+struct Topology { int dims[4]; int coords[4]; };
+static Topology g_topo = {{1, 1, 1, 1}, {0, 0, 0, 0}};
+Topology *default_topo = &g_topo;
+extern "C" const int *comm_coords(const Topology *) { return G.coord; }
+extern "C" const int *comm_dims(const Topology *) { return G.grid; }
+extern "C" void comm_dim_partitioned_set(int) {}      // the --partition mask of the drivers: tmq_force_partition is the test-only equivalent
+extern "C" QudaVerbosity getVerbosity(void) { return G.verbosity; }
+extern "C" void qkxtm_error_at(const char *file, int line, const char *func, const char *fmt, ...) {
+  char b[1024];
+  int n = snprintf(b, sizeof(b), "ERROR: ");
+  va_list ap;
+  va_start(ap, fmt);
+  n += vsnprintf(b + n, sizeof(b) - n, fmt, ap);
+  va_end(ap);
+  if (n < (int)sizeof(b)) snprintf(b + n, sizeof(b) - n, " (%s:%d in %s())", file, line, func);
+  (G.on_error ? G.on_error : default_error)(b);
+}
+// upstream's tests/misc.cpp has it, the reference's copy (qkxtm/misc.cpp) does not although qkxtm/QKXTM_util.cpp calls it
+QudaSchwarzType get_schwarz_type(char *s) {
+  if (strcmp(s, "additive") == 0) return QUDA_ADDITIVE_SCHWARZ;
+  if (strcmp(s, "multiplicative") == 0) return QUDA_MULTIPLICATIVE_SCHWARZ;
+  fprintf(stderr, "Error: invalid Schwarz type %s\n", s);
+  exit(1);
+}
 int comm_rank(void) { return G.rank; }
 int comm_size(void) { return G.nranks; }
 int comm_coord(int dim) { return (dim >= 0 && dim < 4) ? G.coord[dim] : 0; }
+int comm_dim(int dim) { return (dim >= 0 && dim < 4) ? G.grid[dim] : 1; }
+int comm_dim_partitioned(int dim) { return (dim >= 0 && dim < 4) ? (G.grid[dim] > 1) : 0; }
+// a real rendezvous of all ranks (the reference gets its ordering from MPI collectives, e.g. lib/qudaQKXTM_Vector.cpp:625): phases in
+// which ranks diverge -- rank 0 writing a file, reading a configuration -- end with one, so that no rank runs ahead into a halo exchange
+void comm_barrier(void) {
+  if (G.nranks > 1 && G.ctx) TMQ_OK(tmq_barrier(G.ctx));
+}
 
 void initQuda(int device) {
   if (G.quda_initialized) return;
@@ -288,12 +342,10 @@ void invertQuda(void *h_x, void *h_b, QudaInvertParam *param) {
   ColorSpinorField b(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION), x(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
   TMQ_OK(tmq_spinor_from_host(b.handle(), (const double *)h_b));
   solve_device(x, b, param);
+  // x *= 2 kappa for the mass normalisations (lib/qudaQKXTM_interface.cpp:200-203), on the device
+  if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION)
+    TMQ_OK(tmq_ax(2.0 * param->kappa, x.handle()));
   TMQ_OK(tmq_spinor_to_host((double *)h_x, x.handle()));
-  if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION) {
-    const double s = 2.0 * param->kappa;
-    double *p = (double *)h_x;
-    for (long long i = 0; i < G.localVolume * 24; i++) p[i] *= s;
-  }
 }
 
 void MatQuda(void *h_out, void *h_in, QudaInvertParam *param) {
@@ -310,6 +362,9 @@ void MatQuda(void *h_out, void *h_in, QudaInvertParam *param) {
 namespace quda {
 
 tmq_ctx *qkxtm_context() { return G.ctx; }
+const int *qkxtm_local_extent() { return G.localL; }
+long long qkxtm_local_volume() { return G.localVolume; }
+void qkxtm_raise(const char *msg) { errorQuda("%s", msg); }
 int qkxtm_Nmoms() { return (int)G.moms.size() / 3; }
 const int *qkxtm_moms() { return G.moms.data(); }
 void qkxtm_set_error_handler(qkxtm_error_handler h) { G.on_error = h; }
@@ -321,14 +376,21 @@ void init_qudaQKXTM(qudaQKXTMinfo *info) {
   G.nsmearGauss = info->nsmearGauss; G.alphaGauss = info->alphaGauss;      // GK_nsmearGauss, GK_alphaGauss (:125-127)
   // createMomenta(info->Q_sq) (lib/qudaQKXTM_kernels.cu:98-116,128): all integer momenta with p^2 <= Q_sq, shell by shell
   G.moms.clear();
+  if (info->Q_sq > 3 * 4096) errorQuda("Error exceeded max number of momenta (Q_sq = %d; uninitialised?)", info->Q_sq);
   for (int iQ = 0; iQ <= info->Q_sq; iQ++)
     for (int nx = iQ; nx >= -iQ; nx--)
       for (int ny = iQ; ny >= -iQ; ny--)
         for (int nz = iQ; nz >= -iQ; nz--)
           if (nx * nx + ny * ny + nz * nz == iQ) { G.moms.push_back(nx); G.moms.push_back(ny); G.moms.push_back(nz); }
   if ((int)G.moms.size() / 3 > MAX_NMOMENTA) errorQuda("Error exceeded max number of momenta");
-  if (info->Nsources < 0 || info->Nsources > MAX_NSOURCES) errorQuda("bad number of sources %d", info->Nsources);
-  G.sourcePosition.assign(&info->sourcePosition[0][0], &info->sourcePosition[0][0] + (size_t)info->Nsources * 4);   // :129-132
+  // qkxtm/MG_Bench.cpp:534-544 and CalcLowModeProjection.cpp leave Nsources (and more) of their stack-allocated info unset; the reference
+  // copies that many positions without a check (lib/qudaQKXTM_kernels.cu:129-132).  Out-of-range values are taken as "no sources".
+  int nsrc = info->Nsources;
+  if (nsrc < 0 || nsrc > MAX_NSOURCES) {
+    if (G.rank == 0 && G.verbosity > QUDA_SILENT) fprintf(stderr, "WARNING: init_qudaQKXTM: info.Nsources = %d is out of range (uninitialised?): no source positions are kept\n", nsrc);
+    nsrc = 0;
+  }
+  G.sourcePosition.assign(&info->sourcePosition[0][0], &info->sourcePosition[0][0] + (size_t)nsrc * 4);   // :129-132
   G.qkxtm_initialized = true;
   printfQuda("qudaQKXTM has been initialized\n");
 }
@@ -526,6 +588,15 @@ template <typename Float> void QKXTM_Vector<Float>::gaussianSmearing(QKXTM_Vecto
 }
 template <typename Float> void QKXTM_Vector<Float>::write(char *filename) {
   // h_elem holds the host AoS vector (after download()), as in the reference (lib/qudaQKXTM_Vector.cpp:676-690)
+  // rank 0 creates the file and writes the headers, then every rank writes its sub-block at its own offset.  The reference orders the
+  // two steps with the MPI_Bcast of the payload offset (lib/qudaQKXTM_Vector.cpp:625); here: create -> barrier -> blocks -> barrier
+  if (G.nranks > 1) {
+    if (G.rank == 0 && tmq_lime_write_vector_header(filename, (int)sizeof(Float), G.localL, G.grid)) errorQuda("%s", tmq_lime_last_error());
+    comm_barrier();
+    if (tmq_lime_write_vector_block(filename, this->h_elem, (int)sizeof(Float), G.localL, G.grid, G.coord)) errorQuda("%s", tmq_lime_last_error());
+    comm_barrier();
+    return;
+  }
   if (tmq_lime_write_vector(filename, this->h_elem, (int)sizeof(Float), G.localL, G.grid, G.coord)) errorQuda("%s", tmq_lime_last_error());
 }
 template <typename Float> void QKXTM_Vector<Float>::scaleVector(double a) { TMQ_OK(tmq_qkxtm_scale(G.ctx, this->d_elem, (int)sizeof(Float), a)); }
@@ -941,6 +1012,12 @@ template <typename Float> void QKXTM_Deflation<Float>::ApplyMdagM(Float *vec_out
 template <typename Float> void QKXTM_Deflation<Float>::projectVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in, int is, int NeV_defl) {
   (void)is;
   if (!isFullOp) errorQuda("projectVector: This function only works with the Full Operator");
+  if (NeV_defl == 0 || NeV == 0) {                                          // Deflation.cpp:2071-2076
+    printfQuda("projectVector: Got NeV = %d. Will not project vector!\n", NeV_defl);
+    vec_defl.packVector((Float *)vec_in.H_elem());
+    vec_defl.loadVector();
+    return;
+  }
   QKXTM_Vector<Float> stage(BOTH, VECTOR);
   stage.packVector(vec_in.H_elem());
   stage.loadVector();
@@ -949,6 +1026,22 @@ template <typename Float> void QKXTM_Deflation<Float>::projectVector(QKXTM_Vecto
   TMQ_OK(tmq_project(in.handle(), in.handle(), set, NeV_defl < NeV ? NeV_defl : NeV));
   vec_defl.downloadFromCuda(&in, false);
   vec_defl.unloadVector();
+}
+template <typename Float> void QKXTM_Deflation<Float>::projectVector(QKXTM_Vector<Float> &vec_defl, QKXTM_Vector<Float> &vec_in, int is) {
+  projectVector(vec_defl, vec_in, is, NeV);                                 // Deflation.cpp:1931-2059: all NeV vectors
+}
+// Deflation.cpp:285-385: the reference reorders its HOST copy of the eigenvectors from [even | odd] to lexicographic sites, the order its
+// host zgemv in projectVector needs.  Here the basis stays on the device in the native [even | odd] layout and projectVector converts the
+// vector it is given instead, so there is nothing to reorder; the calls are kept so that calc_loops reads like the reference.
+template <typename Float> void QKXTM_Deflation<Float>::MapEvenOddToFull() {
+  if (!isFullOp) { printfQuda("WARNING: MapEvenOddToFull: This function only works with the Full Operator\n"); return; }
+  if (NeV == 0) return;
+  printfQuda("MapEvenOddToFull: Completed successfully\n");
+}
+template <typename Float> void QKXTM_Deflation<Float>::MapEvenOddToFull(int i) {
+  if (!isFullOp) errorQuda("MapEvenOddToFull: This function only works with the Full Operator");
+  if (NeV == 0) return;
+  printfQuda("MapEvenOddToFull: Vector %d completed successfully\n", i);
 }
 template <typename Float> void QKXTM_Deflation<Float>::copyEigenVectorToQKXTM_Vector(int id, Float *vec) {
   if (NeV == 0) return;
@@ -978,6 +1071,9 @@ template class QKXTM_Contraction<float>;
 }  // namespace quda
 
 // ---- solve entry points ---------------------------------------------------------------------------------------------------------
+void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, qudaQKXTMinfo info) {
+  MG_bench(gaugeSmeared, gauge, gauge_param, param, info, (double *)NULL);
+}
 void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, qudaQKXTMinfo info,
               double *prop_out) {
   (void)gauge;
@@ -1251,6 +1347,9 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   printfQuda("...Done (%f sec)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
 }
 
+void calcLowModeProjection(QudaInvertParam *evInvParam, qudaQKXTM_arpackInfo arpackInfo) {
+  calcLowModeProjection(evInvParam, arpackInfo, (int *)NULL, (double *)NULL);
+}
 void calcLowModeProjection(QudaInvertParam *evInvParam, qudaQKXTM_arpackInfo arpackInfo, int *nconv, double *evals) {
   const char *fname = "calcLowModeProjection";
   if (!evInvParam) errorQuda("null argument");
@@ -1335,4 +1434,228 @@ void ApplyMdagM(double *h_out, double *h_in, QudaInvertParam *param, bool isEven
   Kvec->unpackVector();
   memcpy(h_out, Kvec->H_elem(), (size_t)G.localVolume * 24 * sizeof(double));
   delete Kvec;
+}
+
+// ---- calc_loops (include/qudaQKXTM.h:501-507, lib/qudaQKXTM_interface.cpp:1409-2233) -----------------------------------------------
+namespace {
+quda::qkxtm_loop_hook g_loop_hook = nullptr;
+void *g_loop_hook_user = nullptr;
+}
+namespace quda {
+void qkxtm_set_loop_hook(qkxtm_loop_hook hook, void *user) { g_loop_hook = hook; g_loop_hook_user = user; }
+}
+
+// QKXTM_LOOP_DUMP=<file>: a built-in hook for drivers that install none (the reference's own Calc_Loops.cpp): appends, for every event,
+// 8 doubles (kind, is, ih, sc, dstep, NeV_defl, eigenvalue | iterations, true_res), then for kind 1 the host source, then the vector
+// handed to the hook (downloaded, plug-in AoS order) -- what a contraction would consume, in a form a test can check
+static void dump_hook(const qkxtm_loop_event *ev, void *user) {
+  FILE *f = (FILE *)user;
+  QKXTM_Vector<double> K(BOTH, VECTOR);
+  K.downloadFromCuda(ev->x, false);
+  K.download();
+  const double head[8] = {(double)ev->kind, (double)ev->is, (double)ev->ih, (double)ev->sc, (double)ev->dstep, (double)ev->NeV_defl,
+                          ev->kind == 0 ? ev->eigenvalue : (double)ev->iter, ev->true_res};
+  const size_t n = (size_t)G.localVolume * 24;
+  bool ok = fwrite(head, sizeof(double), 8, f) == 8;
+  if (ev->kind == 1) ok = ok && fwrite(ev->h_source, sizeof(double), n, f) == n;
+  ok = ok && fwrite(K.H_elem(), sizeof(double), n, f) == n;
+  if (!ok) errorQuda("QKXTM_LOOP_DUMP: short write");
+}
+
+void calc_loops(void **gaugeToPlaquette, QudaInvertParam *EvInvParam, QudaInvertParam *param, QudaGaugeParam *gauge_param,
+                qudaQKXTM_arpackInfo arpackInfo, qudaQKXTM_loopInfo loopInfo, qudaQKXTMinfo info) {
+  const char *fname = "calc_loops";
+  if (!EvInvParam || !param || !gauge_param) errorQuda("%s: null argument", fname);
+  FILE *dump_file = NULL;
+  const qkxtm_loop_hook hook_saved = g_loop_hook;
+  void *const hook_user_saved = g_loop_hook_user;
+  if (!g_loop_hook && getenv("QKXTM_LOOP_DUMP") && *getenv("QKXTM_LOOP_DUMP")) {
+    char path[1024];
+    if (G.nranks > 1) snprintf(path, sizeof(path), "%s.rank%d", getenv("QKXTM_LOOP_DUMP"), G.rank);
+    else snprintf(path, sizeof(path), "%s", getenv("QKXTM_LOOP_DUMP"));
+    dump_file = fopen(path, "wb");
+    if (!dump_file) errorQuda("QKXTM_LOOP_DUMP: cannot open %s", path);
+    g_loop_hook = dump_hook; g_loop_hook_user = dump_file;
+  }
+  // ---- parameter checks (:1427-1494) ----
+  unsigned short int *Vc = NULL;
+  const int k_probing = loopInfo.k_probing;
+  const bool spinColorDil = loopInfo.spinColorDil;
+  bool isProbing = false, isProbingMstep = false;
+  int Nc = 1, Nc_low = 0, Nc_high = 1;
+  if (!G.quda_initialized) errorQuda("%s: QUDA not initialized", fname);
+  if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
+  if (k_probing > 0) {
+    Nc = 2 * (int)std::lround(std::pow(2.0, 4 * (k_probing - 1)));
+    Vc = hch_coloring(k_probing, 4);                       // 4D hierarchical coloring
+    isProbing = true;
+    if (loopInfo.hadamLow < 0 || loopInfo.hadamHigh < 0) errorQuda("Error: You cannot give negative values for hadamLow or hadamHigh");
+    if (loopInfo.hadamLow > loopInfo.hadamHigh) errorQuda("Error: hadamLow cannot be greater than hadamHigh");
+    Nc_low = loopInfo.hadamLow;
+    Nc_high = loopInfo.hadamHigh == 0 ? Nc : loopInfo.hadamHigh;
+    if (Nc_high > Nc) errorQuda("Error: You cannot choose hadamHigh to be greater than Nc");
+    if (Nc_low > 0 || Nc_high < Nc) isProbingMstep = true;
+  }
+  const int Nsc = spinColorDil ? 12 : 1;
+  const QudaVerbosity verbosity_saved = G.verbosity;
+  G.verbosity = param->verbosity;                          // pushVerbosity(param->verbosity)
+  printfQuda("\n### %s: Loop calculation begins now\n\n", fname);
+  if ((EvInvParam->matpc_type != QUDA_MATPC_EVEN_EVEN_ASYMMETRIC) && (EvInvParam->matpc_type != QUDA_MATPC_ODD_ODD_ASYMMETRIC))
+    errorQuda("Only asymmetric operators are supported in deflation");
+  if (arpackInfo.isEven && (EvInvParam->matpc_type != QUDA_MATPC_EVEN_EVEN_ASYMMETRIC)) errorQuda("%s: Inconsistency between operator types!", fname);
+  if ((!arpackInfo.isEven) && (EvInvParam->matpc_type != QUDA_MATPC_ODD_ODD_ASYMMETRIC)) errorQuda("%s: Inconsistency between operator types!", fname);
+  if ((param->inv_type != QUDA_GCR_INVERTER) && (param->inv_type != QUDA_CG_INVERTER)) errorQuda("%s: This function works only with GCR/CG solver", fname);
+  if (param->inv_type == QUDA_GCR_INVERTER) errorQuda("%s: the GCR + multigrid solver is not provided by this library (use --inv-type cg)", fname);
+  if (param->gamma_basis != QUDA_UKQCD_GAMMA_BASIS) errorQuda("%s: This function works only with ukqcd gamma basis", fname);
+  if (param->dirac_order != QUDA_DIRAC_ORDER) errorQuda("%s: This function works only with color-inside-spin", fname);
+  if (loopInfo.FileFormat == HDF5_FORM && g_loop_hook == nullptr) printfQuda("%s: no contraction hook installed: no loop files (HDF5 or ASCII) are written\n", fname);
+  check_solver(param);
+
+  const int Nstoch = loopInfo.Nstoch;
+  const unsigned long int seed = loopInfo.seed;
+  const int Ndump = loopInfo.Ndump;
+  loopInfo.Nmoms = qkxtm_Nmoms();
+  const int deflSteps = loopInfo.nSteps_defl;
+  if (deflSteps < 0 || deflSteps > MAX_DEFLSTEPS) errorQuda("%s: bad number of deflation steps %d", fname, deflSteps);
+  if (Nstoch < 0 || Ndump <= 0) errorQuda("%s: bad Nstoch / Ndump", fname);
+  // names the reference fills into its by-value copy (:1517-1534); they feed its writers only
+  static char lt0[] = "Scalar", lt1[] = "dOp", lt2[] = "Loops", lt3[] = "LoopsCv", lt4[] = "LpsDw", lt5[] = "LpsDwCv";
+  char *lts[6] = {lt0, lt1, lt2, lt3, lt4, lt5};
+  for (int i = 0; i < 6; i++) { loopInfo.loop_type[i] = lts[i]; loopInfo.loop_oneD[i] = i >= 2; }
+
+  printfQuda("\nLoop Calculation Info\n=====================\n");
+  printfQuda(" The seed is: %ld\n", seed);
+  printfQuda(" The conf trajectory is: %04d\n", loopInfo.traj);
+  printfQuda(" Will produce the loop for %d Momentum Combinations\n", loopInfo.Nmoms);
+  printfQuda(" The loop base name is %s\n", loopInfo.loop_fname);
+  if (isProbingMstep)
+    printfQuda(" %d Stoch vectors, %d Hadamard vectors (using Mstep), %d spin-colour diluted : %04d inversions\n", Nstoch, Nc_high - Nc_low, Nsc,
+               Nstoch * (Nc_high - Nc_low) * Nsc);
+  else
+    printfQuda(" %d Stoch vectors, %d Hadamard vectors, %d spin-colour diluted : %04d inversions\n", Nstoch, Nc, Nsc, Nstoch * Nc * Nsc);
+  printfQuda(" Will project\n");
+  for (int a = 0; a < deflSteps; a++) printfQuda(" Ndefl %d: %d\n", a, loopInfo.deflStep[a]);
+  printfQuda(" exact eigenmodes fom the solutions\n");
+  if (info.source_type == RANDOM) printfQuda(" Will use RANDOM stochastic sources\n");
+  else if (info.source_type == UNITY) printfQuda(" Will use UNITY stochastic sources\n");
+  printfQuda("=====================\n\n");
+
+  // ---- exact part (:1713-1838): the low modes of the operator of EvInvParam; the loop contraction of each eigenpair is the hook ----
+  printfQuda("\n ### Exact part calculation ###\n");
+  const int NeV_Full = arpackInfo.nEv;
+  QKXTM_Deflation<double> *deflation = new QKXTM_Deflation<double>(EvInvParam, arpackInfo);
+  deflation->printInfo();
+  auto t1 = std::chrono::steady_clock::now();
+  deflation->eigenSolver();
+  printfQuda("%s TIME REPORT:Full Operator EigenVector Calculation: %f sec\n", fname,
+             std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
+  deflation->MapEvenOddToFull();
+  if (g_loop_hook && NeV_Full > 0 && arpackInfo.isFullOp) {
+    ColorSpinorField ev(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+    for (int n = 0; n < NeV_Full; n++) {
+      TMQ_OK(tmq_copy(ev.handle(), tmq_eigset_vector(deflation->EigenSet(), n)));
+      qkxtm_loop_event e;
+      memset(&e, 0, sizeof(e));
+      e.kind = 0; e.is = n; e.x = &ev; e.eigenvalue = (double)deflation->EigenValues()[2 * n];
+      g_loop_hook(&e, g_loop_hook_user);                   // Loop_w_One_Der_FullOp_Exact(n, ...) (:1775)
+    }
+  }
+  printfQuda("\n ### Exact part calculation Done ###\n");
+
+  // ---- stochastic part (:1840-2134) ----
+  printfQuda("\n ### Stochastic part calculation ###\n\n");
+  if (gaugeToPlaquette) {
+    QKXTM_Gauge<double> *K_gauge = new QKXTM_Gauge<double>(BOTH, GAUGE);     // :1846-1850
+    K_gauge->packGauge(gaugeToPlaquette);
+    K_gauge->loadGauge();
+    K_gauge->calculatePlaq();
+    delete K_gauge;
+  }
+  bool flag_eo = false;
+  if (info.isEven) { printfQuda("%s: Solving for the Even-Even operator\n", fname); flag_eo = true; }
+  else printfQuda("%s: Solving for the Odd-Odd operator\n", fname);
+
+  const long long V = G.localVolume;
+  double *input_vector = (double *)calloc((size_t)V * 24, sizeof(double));
+  double *temp_input_vector = (isProbing || spinColorDil) ? (double *)calloc((size_t)V * 24, sizeof(double)) : NULL;
+  if (!input_vector || ((isProbing || spinColorDil) && !temp_input_vector)) errorQuda("%s: Error allocating memory for the host sources", fname);
+  ColorSpinorField *b = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  ColorSpinorField *x = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  ColorSpinorField *sol = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  QKXTM_Vector<double> *K_vector = new QKXTM_Vector<double>(BOTH, VECTOR);
+
+  void *rNum = qkxtm_rng_alloc(seed + (unsigned long int)comm_rank() * seed);   // gsl_rng_set(rNum, seed + comm_rank()*seed) (:1951)
+  if (!rNum) errorQuda("%s: cannot allocate the random number generator", fname);
+  const char *msg_str = "LOOPS";
+  int iPrint = -1;
+  for (int is = 0; is < Nstoch; is++) {
+    t1 = std::chrono::steady_clock::now();
+    getStochasticRandomSource<double>(input_vector, rNum, info.source_type);   // :1981-1982
+    printfQuda("TIME_REPORT: %s %04d - Source creation: %f sec\n", msg_str, is + 1,
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
+    for (int ih = Nc_low; ih < Nc_high; ih++) {
+      for (int sc = 0; sc < Nsc; sc++) {
+        const auto t3 = std::chrono::steady_clock::now();
+        double *src = input_vector;
+        if (spinColorDil) {                                                  // :1994-2005
+          if (isProbing) get_probing4D_spinColor_dilution<double>(temp_input_vector, input_vector, Vc, ih, sc);
+          else get_spinColor_dilution<double>(temp_input_vector, input_vector, sc);
+          src = temp_input_vector;
+        } else if (isProbing) {
+          get_probing4D_dilution<double>(temp_input_vector, input_vector, Vc, ih);
+          src = temp_input_vector;
+        }
+        K_vector->packVector(src);                                           // :2008
+        K_vector->loadVector();                                              // :2009
+        K_vector->uploadToCuda(b, flag_eo);                                  // :2010
+        const double orig_tol = param->tol;
+        const int orig_maxiter = param->maxiter;
+        solve_device(*sol, *b, param);                                       // :2020-2041 (prepare, M^dag, CG, reconstruct)
+        printfQuda("TIME_REPORT: %s Stoch = %02d, HadVec = %02d, Spin-colour = %02d - Full Inversion Time: %f sec\n", msg_str, is, ih, sc, param->secs);
+        param->tol = orig_tol;
+        param->maxiter = orig_maxiter;
+        for (int dstep = 0; dstep < deflSteps; dstep++) {                    // :2056-2112
+          const int NeV_defl = loopInfo.deflStep[dstep];
+          t1 = std::chrono::steady_clock::now();
+          // x <- (1 - U U^dag) sol.  The reference stages this through the host (downloadFromCuda -> download -> projectVector ->
+          // uploadToCuda, :2059-2066); the basis lives on the device here, so the projection never leaves it.
+          if (NeV_defl > 0 && NeV_Full > 0) {
+            if (!arpackInfo.isFullOp) errorQuda("projectVector: This function only works with the Full Operator");
+            TMQ_OK(tmq_project(x->handle(), sol->handle(), deflation->EigenSet(), NeV_defl < NeV_Full ? NeV_defl : NeV_Full));
+          } else {
+            printfQuda("projectVector: Got NeV = %d. Will not project vector!\n", NeV_defl);
+            TMQ_OK(tmq_copy(x->handle(), sol->handle()));
+          }
+          TMQ_OK(tmq_sync(G.ctx));
+          printfQuda("TIME_REPORT: %s Stoch = %02d, HadVec = %02d, Spin-colour = %02d, NeV = %04d, Solution projection: %f sec\n", msg_str, is, ih, sc,
+                     NeV_defl, std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
+          if (g_loop_hook) {                                                 // oneEndTrick_w_One_Der (:2074-2078): not built, hook only
+            qkxtm_loop_event e;
+            memset(&e, 0, sizeof(e));
+            e.kind = 1; e.is = is; e.ih = ih; e.sc = sc; e.dstep = dstep; e.NeV_defl = NeV_defl; e.x = x; e.h_source = src;
+            e.iter = param->iter; e.true_res = param->true_res;
+            g_loop_hook(&e, g_loop_hook_user);
+          }
+          if (((is + 1) % Ndump == 0) && (ih * Nsc + sc == Nc_high * Nsc - 1) && dstep == 0) iPrint++;   // :2087-2089 (the FT + copy follow there)
+        }
+        printfQuda("TIME_REPORT: %s Stoch = %02d, HadVec = %02d, Spin-colour = %02d - Total Processing Time %f sec\n", msg_str, is, ih, sc,
+                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t3).count());
+      }
+    }
+  }
+  (void)iPrint;
+  qkxtm_rng_free(rNum);
+  printfQuda("\n ### Stochastic part calculation Done ###\n");
+  printfQuda("\nCleaning up...\n");
+  free(input_vector);
+  if (temp_input_vector) free(temp_input_vector);
+  if (Vc) free(Vc);
+  delete deflation;
+  delete K_vector;
+  delete sol;
+  delete x;
+  delete b;
+  if (dump_file) { fclose(dump_file); g_loop_hook = hook_saved; g_loop_hook_user = hook_user_saved; }
+  printfQuda("...Done\n");
+  G.verbosity = verbosity_saved;                           // popVerbosity()
 }

@@ -252,14 +252,16 @@ int tmq_lime_write_gauge(const char *fname, const double *const gauge[4], const 
 
 /* QKXTM_Vector::write: host vector in the plug-in's AoS order [x_lex][spin][colour][re,im] (local) -> "DiracFermion_Sink"
  * file of the GLOBAL lattice; prec = 8 | 4 selects the precision of both the source buffer and the file.           */
-int tmq_lime_write_vector(const char *fname, const void *h_aos, int prec, const int localX[4], const int grid[4], const int coord[4]) {
+/* step 1 (ONE rank): create the file -- an existing one of that name is replaced atomically, never written into -- with the three
+ * record headers and room for the payload.  On a process grid every rank must wait (a barrier) before step 2.                 */
+int tmq_lime_write_vector_header(const char *fname, int prec, const int localX[4], const int grid[4]) {
   if (prec != 8 && prec != 4) return fail("bad precision%s", "");
   int G[4];
   for (int d = 0; d < 4; d++) G[d] = localX[d] * grid[d];
   const long long lvol = (long long)G[0] * G[1] * G[2] * G[3];
-  const bool first = coord[0] == 0 && coord[1] == 0 && coord[2] == 0 && coord[3] == 0;
-  if (first) {
-    FILE *f = fopen(fname, "wb");
+  {
+    const std::string tmpname = std::string(fname) + ".tmp";
+    FILE *f = fopen(tmpname.c_str(), "wb");
     if (!f) return fail("Error open file to write propagator %s", fname);
     const char *ptype = "DiracFermion_Sink";
     char fmt[1024];
@@ -271,8 +273,16 @@ int tmq_lime_write_vector(const char *fname, const void *h_aos, int prec, const 
     rc |= write_header(f, "scidac-binary-data", (uint64_t)lvol * 24 * prec, true, true);
     if (!rc) rc = (fflush(f) != 0) || (ftruncate(fileno(f), ftell(f) + (off_t)lvol * 24 * prec) != 0);
     fclose(f);
+    if (!rc) rc = rename(tmpname.c_str(), fname) != 0;
     if (rc) return fail("LIME write header error in %s", fname);
   }
+  return 0;
+}
+/* step 2 (EVERY rank, after step 1 is complete): write this rank's sub-block at its own offsets                                 */
+int tmq_lime_write_vector_block(const char *fname, const void *h_aos, int prec, const int localX[4], const int grid[4], const int coord[4]) {
+  if (prec != 8 && prec != 4) return fail("bad precision%s", "");
+  int G[4];
+  for (int d = 0; d < 4; d++) G[d] = localX[d] * grid[d];
   const int fd = open(fname, O_RDWR);
   if (fd < 0) return fail("Could not open %s", fname);
   std::vector<Record> recs;
@@ -280,6 +290,7 @@ int tmq_lime_write_vector(const char *fname, const void *h_aos, int prec, const 
   const Record *bin = nullptr;
   for (const Record &r : recs) if (r.type == "scidac-binary-data") { bin = &r; break; }
   if (!bin) { close(fd); return fail("no scidac-binary-data record in %s", fname); }
+  if (bin->bytes != (uint64_t)G[0] * G[1] * G[2] * G[3] * 24 * prec) { close(fd); return fail("the payload record of %s does not match the lattice (stale file?)", fname); }
   const size_t site = (size_t)24 * prec;
   std::vector<unsigned char> row((size_t)localX[0] * site);
   const bool swap = !host_is_big_endian();
@@ -293,6 +304,12 @@ int tmq_lime_write_vector(const char *fname, const void *h_aos, int prec, const 
   });
   close(fd);
   return rc;
+}
+/* both steps in one call, for a single process (or for callers that serialise the ranks themselves, rank (0,0,0,0) first)         */
+int tmq_lime_write_vector(const char *fname, const void *h_aos, int prec, const int localX[4], const int grid[4], const int coord[4]) {
+  const bool first = coord[0] == 0 && coord[1] == 0 && coord[2] == 0 && coord[3] == 0;
+  if (first && tmq_lime_write_vector_header(fname, prec, localX, grid)) return 1;
+  return tmq_lime_write_vector_block(fname, h_aos, prec, localX, grid, coord);
 }
 
 /* reads a DiracFermion_Sink file back into the local AoS order (the reference has the matching reader for sources in

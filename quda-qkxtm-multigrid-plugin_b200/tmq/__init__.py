@@ -31,7 +31,7 @@ tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm t
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
 tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free
-tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d""".split()
+tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d tmq_barrier""".split()
 
 
 class TmqError(RuntimeError):
@@ -52,7 +52,7 @@ def load():
     vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
     L.tmq_last_error.restype = C.c_char_p
     L.tmq_create.restype = vp; L.tmq_create.argtypes = [C.c_int, ip, ip, ip]
-    L.tmq_destroy.argtypes = [vp]; L.tmq_sync.argtypes = [vp]
+    L.tmq_destroy.argtypes = [vp]; L.tmq_sync.argtypes = [vp]; L.tmq_barrier.argtypes = [vp]
     L.tmq_comm_unique_id.argtypes = [C.c_char_p]
     L.tmq_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     L.tmq_force_partition.argtypes = [vp, ip]
@@ -253,6 +253,7 @@ class Context:
     def halo_mode(self): return self.L.tmq_halo_mode(self.h)
     def comm_init(self, uid, nranks, rank): _ck(self.L.tmq_comm_init(self.h, uid, nranks, rank))
     def sync(self): _ck(self.L.tmq_sync(self.h))
+    def barrier(self): _ck(self.L.tmq_barrier(self.h))
 
     def load_gauge(self, gauge_qdp, t_boundary=-1, recon=12):
         """gauge_qdp: float64 [4][V][3][3][2], QDP even-odd order, boundary sign already folded in"""
@@ -512,3 +513,55 @@ def lime_read_vector(fname, localX, dtype=np.float64, grid=(1, 1, 1, 1), coord=(
 
 def apply_t_boundary(gauge_qdp, localX, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0), t_boundary=-1):
     load_host().tmq_apply_t_boundary(_g4(gauge_qdp), _i4(localX), _i4(grid), _i4(coord), t_boundary)
+
+
+# ---- noise vectors of calc_loops (host/qkxtm_noise.cpp) -------------------------------------------------------------
+def _noise_lib():
+    H = load_host()
+    if not getattr(H, "_noise_ready", False):
+        H.tmq_ranlux_alloc.argtypes = [C.c_ulong]; H.tmq_ranlux_alloc.restype = C.c_void_p
+        H.tmq_ranlux_free.argtypes = [C.c_void_p]
+        H.tmq_ranlux_get.argtypes = [C.c_void_p]; H.tmq_ranlux_get.restype = C.c_ulong
+        H.tmq_ranlux_uniform_int.argtypes = [C.c_void_p, C.c_ulong]; H.tmq_ranlux_uniform_int.restype = C.c_ulong
+        H.tmq_noise_z4.argtypes = [C.POINTER(C.c_double), C.c_longlong, C.c_void_p, C.c_int]
+        H.tmq_hch_coloring.argtypes = [C.POINTER(C.c_ushort), C.POINTER(C.c_int), C.c_int, C.c_int]
+        H.tmq_hadamard_element.argtypes = [C.c_int, C.c_int]
+        H._noise_ready = True
+    return H
+
+
+class Ranlux:
+    """gsl_rng_ranlux restated (see include/tmq_host.h)"""
+
+    def __init__(self, seed):
+        self.H = _noise_lib()
+        self.h = self.H.tmq_ranlux_alloc(seed)
+
+    def get(self): return int(self.H.tmq_ranlux_get(self.h))
+
+    def uniform_int(self, n): return int(self.H.tmq_ranlux_uniform_int(self.h, n))
+
+    def z4(self, ncomplex, unity=False):
+        out = np.empty((ncomplex, 2), dtype=np.float64)
+        self.H.tmq_noise_z4(_dp(out), ncomplex, self.h, int(unity))
+        return out
+
+    def __del__(self):
+        try:
+            self.H.tmq_ranlux_free(self.h)
+        except Exception:
+            pass
+
+
+def hch_coloring(L, k, d=4):
+    H = _noise_lib()
+    n = int(np.prod(L[:d]))
+    out = np.empty(n, dtype=np.uint16)
+    rc = H.tmq_hch_coloring(out.ctypes.data_as(C.POINTER(C.c_ushort)), (C.c_int * d)(*L[:d]), k, d)
+    if rc:
+        raise TmqError("tmq_hch_coloring failed (%d)" % rc)
+    return out
+
+
+def hadamard_element(i, j):
+    return int(_noise_lib().tmq_hadamard_element(i, j))
