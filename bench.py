@@ -154,15 +154,56 @@ def dist_sum(dist, v):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_cg_sample(X, budget_s, gauge=None, rhs=None, iters=None):
-    """the CPU oracle (port) timed on this box: `iters` CG iterations (or as many as fit in budget_s)."""
+def workload_config(GX):
+    """`config` of BOTH arms (the driver compares them): the workload BASELINE.json's metric is quoted on"""
+    return {"workload": "%dx%dx%dx%d even-odd twisted-mass Dslash in CG on MdagM, fp64" % tuple(GX), "lattice": list(GX),
+            "kappa": KAPPA, "mu": MU, "matpc": "even-even", "gauge": "random SU(3), anti-periodic T, seed 137", "source": "Z4 noise, seed 100"}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle(X):
+    """the CPU oracle with ALL host cores: launchers such as torchrun export OMP_NUM_THREADS=1 to every worker, so the thread
+    count is set explicitly"""
     from oracle.oracle import Oracle
-    import tmq
     o = Oracle(X)
-    if gauge is None:
-        gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1)
-    if rhs is None:
-        rhs = np.ascontiguousarray(tmq.gen_spinor(X, "z4", seed=100)[: o.Vh])
+    o.set_num_threads(host_cores())
+    return o
+
+
+def numpy_fields(X):
+    """synthetic gauge field (QDP even-odd, anti-periodic T folded in) and the even half of a Z4 source, generated with numpy only
+    (tests/lattice_util.py: the same counter-based generator as the product's host library, which the CPU arms must not load), in
+    blocks of time slices to bound the memory"""
+    import lattice_util as lu
+    V = int(np.prod(X)); Vh = V // 2
+    tc = 8 if X[3] % 8 == 0 else 2
+    nch = X[3] // tc
+    Xc = (X[0], X[1], X[2], tc)
+    Vch = int(np.prod(Xc)) // 2
+    grid = (1, 1, 1, nch)
+    gauge = np.empty((4, V, 3, 3, 2), dtype=np.float64)
+    rhs = np.empty((Vh, 4, 3, 2), dtype=np.float64)
+    def block(c):
+        g = lu.random_gauge_qdp(Xc, 137, -1, grid, (0, 0, 0, c))
+        gauge[:, c * Vch:(c + 1) * Vch] = g[:, :Vch]
+        gauge[:, Vh + c * Vch: Vh + (c + 1) * Vch] = g[:, Vch:]
+        s = lu.spinor_eo_from_lex(lu.z4_source_lex(Xc, 100, grid, (0, 0, 0, c)), Xc)
+        rhs[c * Vch:(c + 1) * Vch] = s[:Vch]
+    from concurrent.futures import ThreadPoolExecutor      # numpy releases the GIL in its array loops
+    with ThreadPoolExecutor(max_workers=min(host_cores(), 32)) as ex:
+        list(ex.map(block, range(nch)))
+    return gauge, rhs
+
+
+def cpu_cg_sample(X, budget_s, gauge, rhs, iters=None):
+    """the CPU oracle (port) timed on this box: `iters` CG iterations (or as many as fit in budget_s)."""
+    o = cpu_oracle(X)
     t0 = time.perf_counter()
     o.mdagm(gauge, rhs, KAPPA, MU, 0)                      # calibration (and page-in)
     t1 = time.perf_counter() - t0
@@ -173,47 +214,35 @@ def cpu_cg_sample(X, budget_s, gauge=None, rhs=None, iters=None):
     dt = time.perf_counter() - t0
     gf = FLOPS_ITER * o.Vh * it / dt * 1e-9
     return {"value": gf, "unit": "GFLOP/s", "cores": o.num_threads(), "kind": "port",
-            "sample": "%dx%dx%dx%d fp64, %d CG iterations on MdagM (%.2f s)" % (X + (it, dt)), "ms_per_iter": dt / it * 1e3}
+            "sample": "%dx%dx%dx%d fp64, %d CG iterations on MdagM (%.2f s)" % (tuple(X) + (it, dt)), "ms_per_iter": dt / it * 1e3,
+            "note": "scalar C99 + OpenMP port of the host reference (-ffp-contract=off), a reported baseline and not an optimised CPU code"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  Its own host Dslash/CG is upstream QUDA
     (tests/wilson_dslash_reference.cpp), absent from /root/reference and not buildable here, so the timed code
-    is the oracle port with all host threads.  Each step = one CPU CG iteration on a bounded sample lattice."""
+    is the oracle port with all host threads.  Each step = one CPU CG iteration on M_pc^dag M_pc of the SAME 48^3x96 workload (bounded
+    by the number of steps: --steps 20 --warmup 5 take about 40 s on 16 cores).  Only the oracle library is loaded: fields come from numpy."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    from oracle.oracle import Oracle
-    import tmq
-    # choose the largest sample lattice whose (steps + warmup) iterations fit in ~150 s
-    ladder = [(48, 48, 48, 96), (32, 32, 32, 64), (24, 24, 24, 48), (16, 16, 16, 32), (8, 8, 8, 16)]
-    Xc = (16, 16, 16, 32)
-    o = Oracle(Xc)
-    g = tmq.gen_gauge(Xc); r = np.ascontiguousarray(tmq.gen_spinor(Xc, "z4")[: o.Vh])
-    o.mdagm(g, r, KAPPA, MU, 0)
-    t0 = time.perf_counter(); o.mdagm(g, r, KAPPA, MU, 0); per_site = (time.perf_counter() - t0) / o.Vh
-    X = ladder[-1]
-    for cand in ladder:
-        if per_site * (np.prod(cand) / 2) * (steps + warm + 2) * 1.3 < 150.0:
-            X = cand
-            break
-    o = Oracle(X)
-    gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1)
-    rhs = np.ascontiguousarray(tmq.gen_spinor(X, "z4", seed=100)[: o.Vh])
+    X = tuple(args.lattice)
+    o = cpu_oracle(X)
+    gauge, rhs = numpy_fields(X)
     if warm > 0:
         o.cg_mdagm(gauge, rhs, KAPPA, MU, 0, tol=1e-30, maxiter=warm)
     t0 = time.perf_counter()
     _, it, _, _ = o.cg_mdagm(gauge, rhs, KAPPA, MU, 0, tol=1e-30, maxiter=steps)
     dt = time.perf_counter() - t0
     gf = FLOPS_ITER * o.Vh * it / dt * 1e-9
-    sample = "%dx%dx%dx%d fp64 sample of the 48x48x48x96 workload, %d CG iterations on MdagM per run" % (X + (it,))
+    sample = "%d CG iterations on MdagM of the %dx%dx%dx%d fp64 workload per run (%d warm-up)" % ((it,) + X + (warm,))
     line = {"impl": "reference", "metric": "tm_dslash_cg_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt / max(it, 1) * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "48x48x48x96 even-odd twisted-mass Dslash in CG on MdagM, fp64 (CPU sample: %dx%dx%dx%d)" % X,
-                       "kappa": KAPPA, "mu": MU, "matpc": "even-even"},
-            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": o.num_threads(), "kind": "port", "sample": sample},
+            "config": workload_config(X),
+            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": o.num_threads(), "kind": "port", "sample": sample,
+                             "note": "scalar C99 + OpenMP port of the host reference (-ffp-contract=off); upstream QUDA's own host code is not in /root/reference"},
             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))

@@ -65,7 +65,10 @@ int tmq_force_partition(tmq_ctx *, const int part[4]);
 /* tuning knobs (tile of the thread->site map); 0 keeps the default                                        */
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
 enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3, TMQ_OPT_SMEAR_BLOCK_T = 4, TMQ_OPT_PACK_ASYNC = 5,
-       TMQ_OPT_CONTRACT_SLICES = 6 /* > 0: time slices per pass of the baryon / derivative contractions (default: what fits 2 GiB) */ };   /* TMQ_OPT_PREFETCH: accepted and ignored (the L2-prefetch experiment was removed: no gain) */
+       TMQ_OPT_CONTRACT_SLICES = 6 /* > 0: time slices per pass of the baryon / derivative contractions (default: what fits 2 GiB) */,
+       TMQ_OPT_HALO_TIMEOUT_MS = 7 /* wall-clock limit (ms, default 120000; env TMQ_HALO_TIMEOUT_MS) of a device-side wait for a neighbour's
+                                      ghost face or all-reduce contribution; on expiry nothing is computed from stale ghosts, the device
+                                      error scalar is raised and the enclosing call (tmq_sync, tmq_cg_mdagm, ...) fails */ };   /* TMQ_OPT_PREFETCH: accepted and ignored (the L2-prefetch experiment was removed: no gain) */
 int tmq_set_option(tmq_ctx *, int option, int value);
 /* TMQ_OPT_HALO_P2P selects the ghost exchange.  0: ncclSend/ncclRecv on a separate stream + interior / boundary
  * launches.  1: the pack kernel stores the faces straight into the neighbours' ghost arenas over NVLink peer mappings

@@ -74,6 +74,7 @@ def lib():
                                    C.c_int, dp, dp]
         L.orc_cg_mdagm.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_clover_compute.argtypes = [dp, dpp, C.c_double]
         L.orc_set_clover.argtypes = [dp]
         L.orc_site_A.argtypes = [dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
@@ -164,6 +165,7 @@ class Oracle:
         return x, it, tr.value, hist[: it + 1]
 
     def num_threads(self): return self.L.orc_num_threads()
+    def set_num_threads(self, n): self.L.orc_set_num_threads(int(n))
 
     # -- twisted-clover: after set_clover every operator above uses A = C + i a g5 (set_clover(None) switches back)
     def clover_compute(self, gauge, coeff):

@@ -31,6 +31,14 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+/* launchers such as torchrun export OMP_NUM_THREADS=1 to every worker: the timed CPU baseline sets its thread count itself */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 /* ---- geometry: qkxtm/QKXTM_util.cpp:94-128 (setDims), :418-442, :455-470, :191-197 ---------- */
 void orc_set_lattice(const int X[4]) {

@@ -100,6 +100,7 @@ int orc_cg_mdagm(double *x, double *gauge[4], const double *b, double kappa, dou
                  double tol, int maxiter, int pr_beta, double *true_res, double *r2_hist);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

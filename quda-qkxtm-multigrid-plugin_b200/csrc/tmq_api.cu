@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <chrono>
 #include "../../include/tmq.h"
@@ -153,6 +154,7 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   A.nblk[0] = A.nblk[1] = A.nblk[2] = 0;
   A.npre = 0x7fffffff;
   A.hw.n = 0; A.hw.seq = 0; A.hw.err = c->scal + SC_ERR;
+  A.hw.timeout_ns = (unsigned long long)c->opt_halo_timeout_ms * 1000000ull;
   if (!c->multi) {
     const int lo[3] = {0, 0, 0}, ext[3] = {g.X[1], g.X[2], g.X[3]};
     A.en = make_enum(g, lo, ext, c->tile);
@@ -474,6 +476,8 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->opt_prefetch = 0;
   c->opt_smear_block_t = 0;
   c->opt_pack_async = 0;
+  c->opt_halo_timeout_ms = 120000;
+  if (const char *e = getenv("TMQ_HALO_TIMEOUT_MS")) { const int v = atoi(e); if (v > 0) c->opt_halo_timeout_ms = v; }
   c->opt_pre_pct = 50; c->red_seq = 0; memset(c->rank_arena, 0, sizeof(c->rank_arena));
   c->opt_p2p = 2; c->p2p = false; c->seq_table = nullptr; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
   memset(c->peer_arena, 0, sizeof(c->peer_arena));
@@ -632,6 +636,7 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
     case TMQ_OPT_PACK_ASYNC: c->opt_pack_async = value ? 1 : 0; return 0;
     case TMQ_OPT_CONTRACT_SLICES: c->opt_contract_slices = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_SMEAR_BLOCK_T: c->opt_smear_block_t = value < 0 ? 0 : value; return 0;
+    case TMQ_OPT_HALO_TIMEOUT_MS: c->opt_halo_timeout_ms = value > 0 ? value : 120000; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {
       c->opt_p2p = value < 0 ? 0 : (value > 2 ? 2 : value);

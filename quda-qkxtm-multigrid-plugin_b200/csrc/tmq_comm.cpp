@@ -210,6 +210,7 @@ int comm_allreduce(tmq_ctx *c, double *d_ptr, int n, cudaStream_t st) {
     R.scal = c->scal; R.slot = (int)(d_ptr - c->scal); R.n = n;
     R.rank = c->comm->rank; R.nranks = c->comm->nranks; R.seq = ++c->red_seq;
     R.err = c->scal + SC_ERR;
+    R.timeout_ns = (unsigned long long)c->opt_halo_timeout_ms * 1000000ull;
     for (int r = 0; r < R.nranks; r++) {
       R.mbox[r] = (double *)(c->rank_arena[r] + c->arena_layout.mbox);
       R.mflag[r] = (unsigned int *)(c->rank_arena[r] + c->arena_layout.mflag);

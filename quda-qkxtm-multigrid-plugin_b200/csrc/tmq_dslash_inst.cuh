@@ -31,21 +31,34 @@ template <typename F, int EPI, int RECON> struct MinBlocks { static constexpr in
 template <int EPI, int RECON> struct MinBlocks<float, EPI, RECON> { static constexpr int v = RECON == 12 ? TMQ_MINBLOCKS_S : 6; };
 
 // Boundary CTAs of a fused sharded launch: wait until every neighbour has published this application's
-// sequence number (its pack kernel has finished storing the faces into our ghost buffers over NVLink).
-// Bounded: after ~1 s the wait gives up and raises the device error scalar instead of hanging the GPU.
-__device__ __forceinline__ void halo_wait(const HaloWait &hw) {
+// sequence number (its faces have landed in our ghost buffers over NVLink).  The wait is bounded by WALL-CLOCK time
+// (%globaltimer; TMQ_OPT_HALO_TIMEOUT_MS, default 120 s: ordinary rank skew -- file I/O on one rank, a slow first NCCL init --
+// must not trip it, only a dead neighbour).  On a timeout the device error scalar is raised and the CTA returns false: its
+// sites are NOT computed from stale ghosts (the caller still takes part in the grid reduction), and the host fails the call.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool halo_wait(const HaloWait &hw) {
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
   if ((int)threadIdx.x < hw.n) {
     const unsigned int *f = hw.flag[threadIdx.x];
     unsigned int v = 0;
+    unsigned long long t0 = 0;
     int spins = 0;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if (hw.exact ? (v == hw.seq) : ((int)(v - hw.seq) >= 0)) break;
-      if (++spins > (1 << 23)) { *((volatile double *)hw.err) = 1.0; break; }
-      __nanosleep(100);
+      if (++spins == 64) t0 = global_ns();                 // the clock is only read once the wait is not instantaneous
+      if (spins > 64 && (spins & 255) == 0 && global_ns() - t0 > hw.timeout_ns) { *((volatile double *)hw.err) = 1.0; timed_out = 1; break; }
+      __nanosleep(spins < 64 ? 100 : 500);
     }
   }
   __syncthreads();
+  return timed_out == 0;
 }
 
 // twisted-clover variants: the site matrices add 36 vector loads per application and a second spinor in the x-term
@@ -59,6 +72,7 @@ dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
   uint32_t blk = blockIdx.x;
   const Enum *en = &A.en;
   bool boundary = MULTI && A.all_boundary;
+  bool ghosts_ok = true;
   if (MULTI && blk >= (uint32_t)A.npre) {
     // fused sharded launch: the first npre interior CTAs overlap the halo transfer; the boundary CTAs come next
     // (they wait on the arrival flags, normally already set) and the remaining interior CTAs keep the SMs busy
@@ -69,7 +83,7 @@ dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
       if (blk < (uint32_t)A.nblk[1]) en = &A.en_b[0];
       else { blk -= (uint32_t)A.nblk[1]; en = &A.en_b[1]; }
       boundary = true;
-      if (A.hw.n > 0) halo_wait(A.hw);
+      if (A.hw.n > 0) ghosts_ok = halo_wait(A.hw);
     } else {
       blk -= nb;
     }
@@ -78,7 +92,7 @@ dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
   F alpha = 0;
   if (EpiTraits<EPI>::RED == 2) alpha = (F)(A.scal[A.alpha_num] / A.scal[A.alpha_den]);
   double red[1] = {0.0};
-  if (e < (uint32_t)en->nsites) {
+  if (e < (uint32_t)en->nsites && ghosts_ok) {
     // interior sites never touch a ghost zone: they run the branch-free single-GPU body (the ghost-aware body
     // costs ~8% because its conditional loads cannot be hoisted); only boundary CTAs pay for it
     if (MULTI && boundary) red[0] = dslash_site<F, RECON, EPI, true, CLOVER>(A, *en, e, alpha);

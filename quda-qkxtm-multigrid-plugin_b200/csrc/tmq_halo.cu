@@ -150,12 +150,17 @@ __global__ void __launch_bounds__(32) p2p_allreduce_kernel(const __grid_constant
     // wait for rank t's contribution to arrive in our own mailbox
     const unsigned int *f = R.mflag[R.rank] + buf * TMQ_MAX_RANKS + t;
     unsigned int v = 0;
+    unsigned long long t0 = 0, now = 0;
     int spins = 0;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if ((int)(v - R.seq) >= 0) break;
-      if (++spins > (1 << 23)) { *((volatile double *)R.err) = 1.0; break; }
-      __nanosleep(50);
+      if (++spins == 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      if (spins > 64 && (spins & 255) == 0) {              // wall-clock bound (see halo_wait in tmq_dslash_inst.cuh)
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > R.timeout_ns) { *((volatile double *)R.err) = 1.0; break; }
+      }
+      __nanosleep(spins < 64 ? 50 : 500);
     }
   }
   __syncwarp();

@@ -96,6 +96,7 @@ struct tmq_ctx {
   // peer-memory halo path
   int opt_p2p;               // requested: 0 NCCL send/recv, 1 peer stores from the pack kernel, 2 copy-engine peer copies
   int opt_pre_pct;           // % of the interior CTAs scheduled before the boundary CTAs in a fused launch
+  int opt_halo_timeout_ms;   // wall-clock limit of a halo / mailbox wait before the device error scalar is raised
   bool p2p;                  // active: every neighbour's arena is mapped
   char *arena;               // own ghost arena (cudaMalloc)
   tmq::HaloArena arena_layout;

@@ -105,6 +105,7 @@ struct P2PRed {
   double *mbox[TMQ_MAX_RANKS];         // mbox[r]: base of rank r's mailbox [2 buf][4][TMQ_MAX_RANKS] (own for r == rank)
   unsigned int *mflag[TMQ_MAX_RANKS];  // mflag[r]: rank r's flags [2 buf][TMQ_MAX_RANKS]
   double *err;
+  unsigned long long timeout_ns;       // wall-clock limit of the wait for the other ranks' contributions
 };
 
 template <typename F> struct Epi {
@@ -133,6 +134,7 @@ struct HaloWait {
   unsigned int seq;
   int exact;                     // 1: wait for flag == seq (copy-engine path, sequence numbers modulo the table size)
   double *err;                   // device scalar set to 1 if a wait times out (never hang the GPU)
+  unsigned long long timeout_ns; // wall-clock limit of one wait (%globaltimer), TMQ_OPT_HALO_TIMEOUT_MS
 };
 
 template <typename F> struct DslashArgs {

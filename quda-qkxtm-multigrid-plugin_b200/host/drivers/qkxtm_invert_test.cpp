@@ -278,7 +278,10 @@ int main(int argc, char **argv) {
       std::vector<char> f2(base.begin(), base.end()); f2.push_back(0);
       std::string base3 = base + ".threep";
       std::vector<char> f3(base3.begin(), base3.end()); f3.push_back(0);
-      calcMG_threepTwop_EvenOdd((void **)glex, (void **)glex, &gauge_param, &inv_param, info, f2.data(), f3.data(), particle == "neutron" ? NEUTRON : PROTON);   // both in the lexicographic layout of packGauge
+      // both link arrays in the lexicographic layout of packGauge; on a process grid the links of the derivative insertions are withheld
+      // (gauge = NULL: ultra-local insertion only -- the library refuses the derivative insertions on a split lattice)
+      calcMG_threepTwop_EvenOdd((void **)glex, comm_size() > 1 ? (void **)NULL : (void **)glex, &gauge_param, &inv_param, info, f2.data(), f3.data(),
+                                particle == "neutron" ? NEUTRON : PROTON);
     }
   } else { usage(); return 2; }
 

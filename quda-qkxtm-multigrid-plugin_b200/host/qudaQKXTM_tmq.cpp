@@ -12,6 +12,9 @@
 #include <cstring>
 #include <chrono>
 #include <thread>
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <vector>
 
@@ -79,36 +82,94 @@ static int env_int(const char *const *names, int dflt) {
   }
   return dflt;
 }
+// One launch = one nonce.  Every rank derives it independently from what the launcher gives all of them: the run / job id
+// (TORCHELASTIC_RUN_ID, SLURM_JOB_ID, TMQ_COMM_NONCE), MASTER_PORT, the world size and -- when the file is node-local -- the parent
+// process and ITS start time (a later launch from a recycled pid differs).  A rank only accepts a file that carries its own nonce, so an
+// id file left behind by a run that died can never be taken for the current one.
+static unsigned long long parent_start_time() {
+  char path[64], buf[1024];
+  snprintf(path, sizeof(path), "/proc/%ld/stat", (long)getppid());
+  FILE *fp = fopen(path, "r");
+  if (!fp) return 0;
+  const size_t n = fread(buf, 1, sizeof(buf) - 1, fp);
+  fclose(fp);
+  buf[n] = 0;
+  const char *p = strrchr(buf, ')');            // the command name may contain spaces: fields are counted after it
+  if (!p) return 0;
+  unsigned long long v = 0;
+  int field = 2;
+  for (p++; *p; ) {
+    while (*p == ' ') p++;
+    field++;
+    if (field == 22) { v = strtoull(p, NULL, 10); break; }
+    while (*p && *p != ' ') p++;
+  }
+  return v;
+}
+static bool ranks_span_nodes() {
+  static const char *local_size[] = {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE", NULL};
+  static const char *nnodes[] = {"GROUP_WORLD_SIZE", "SLURM_NNODES", NULL};
+  const int ls = env_int(local_size, -1), nn = env_int(nnodes, -1);
+  return (ls > 0 && ls < G.nranks) || nn > 1;
+}
 static void comm_bootstrap() {
-  char path[512];
+  char path[512], nonce[256];
   const char *f = getenv("TMQ_COMM_ID_FILE");
-  if (f && *f) snprintf(path, sizeof(path), "%s", f);
-  else snprintf(path, sizeof(path), "/tmp/tmq_nccl_id_%ld_%s", (long)getppid(), getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
-  char id[128];
+  const char *port = getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0";
+  const char *run = getenv("TMQ_COMM_NONCE") ? getenv("TMQ_COMM_NONCE")
+                    : (getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : (getenv("SLURM_JOB_ID") ? getenv("SLURM_JOB_ID") : "-"));
+  const bool shared = f && *f;
+  memset(nonce, 0, sizeof(nonce));
+  if (shared) {
+    snprintf(path, sizeof(path), "%s", f);
+    snprintf(nonce, sizeof(nonce), "tmq1|%s|%s|%d", run, port, G.nranks);
+  } else {
+    // /tmp is node-local and the parent differs per node: a launch that spans nodes must name a file on a shared filesystem
+    if (ranks_span_nodes())
+      errorQuda("the ranks span several nodes: set TMQ_COMM_ID_FILE to a path on a filesystem all of them share (the default id file is node-local)");
+    // a directory only this user can write to; the name inside is predictable, the directory makes that harmless
+    char dir[256];
+    snprintf(dir, sizeof(dir), "/tmp/tmq-%ld", (long)getuid());
+    if (mkdir(dir, 0700) != 0 && errno != EEXIST) errorQuda("cannot create %s", dir);
+    struct stat st;
+    if (lstat(dir, &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != getuid() || (st.st_mode & 077) != 0)
+      errorQuda("%s must be a directory owned by this user with mode 0700", dir);
+    snprintf(path, sizeof(path), "%s/nccl_id_%ld_%s", dir, (long)getppid(), port);
+    snprintf(nonce, sizeof(nonce), "tmq1|%s|%s|%d|%ld|%llu", run, port, G.nranks, (long)getppid(), parent_start_time());
+  }
+  char id[128], rec[sizeof(nonce) + 128];
   if (G.rank == 0) {
     TMQ_OK(tmq_comm_unique_id(id));
     char tmp[600];
     snprintf(tmp, sizeof(tmp), "%s.tmp", path);
-    FILE *fp = fopen(tmp, "wb");
-    if (!fp || fwrite(id, 1, 128, fp) != 128) errorQuda("cannot write the communicator id file %s", tmp);
-    fclose(fp);
+    unlink(path);                                  // whatever an earlier run left behind
+    unlink(tmp);
+    const int fd = open(tmp, O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+    if (fd < 0) errorQuda("cannot create the communicator id file %s", tmp);
+    memcpy(rec, nonce, sizeof(nonce));
+    memcpy(rec + sizeof(nonce), id, 128);
+    const bool ok = write(fd, rec, sizeof(rec)) == (ssize_t)sizeof(rec) && fsync(fd) == 0;
+    close(fd);
+    if (!ok) errorQuda("cannot write the communicator id file %s", tmp);
     if (rename(tmp, path) != 0) errorQuda("cannot publish the communicator id file %s", path);
   } else {
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
-      FILE *fp = fopen(path, "rb");
-      if (fp) {
-        const size_t n = fread(id, 1, 128, fp);
-        fclose(fp);
-        if (n == 128) break;
+      const int fd = open(path, O_RDONLY | O_NOFOLLOW);
+      if (fd >= 0) {
+        struct stat st;
+        const bool mine = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && (shared || st.st_uid == getuid());
+        const ssize_t n = mine ? read(fd, rec, sizeof(rec)) : -1;
+        close(fd);
+        if (n == (ssize_t)sizeof(rec) && memcmp(rec, nonce, sizeof(nonce)) == 0) { memcpy(id, rec + sizeof(nonce), 128); break; }
       }
-      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
-        errorQuda("rank %d: no communicator id from rank 0 after 120 s (%s)", G.rank, path);
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 300.0)
+        errorQuda("rank %d: no communicator id for this launch from rank 0 after 300 s (%s)", G.rank, path);
       std::this_thread::sleep_for(std::chrono::milliseconds(20));
     }
   }
   TMQ_OK(tmq_comm_init(G.ctx, id, G.nranks, G.rank));     // collective: returns once every rank has joined
-  if (G.rank == 0) remove(path);
+  if (G.rank == 0) unlink(path);
 }
 
 static void ensure_context(const int X[4]) {
@@ -738,7 +799,7 @@ void QKXTM_Contraction<Float>::writeTwopMesons_ASCII(void *corrMesons, char *fil
   const int *mv = qkxtm_moms();
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
-  if (!root) return;
+  if (!root) { comm_barrier(); return; }       // the writing rank joins when its file is complete (the reference has an MPI_Gather here)
   FILE *ptr_out = fopen(filename_out, "w");
   if (ptr_out == NULL) errorQuda("Error opening file for writing");
   for (int ip = 0; ip < 10; ip++)
@@ -750,6 +811,7 @@ void QKXTM_Contraction<Float>::writeTwopMesons_ASCII(void *corrMesons, char *fil
                 (double)c[(b + 0) * 20 + ip], (double)c[(b + 1) * 20 + ip], (double)c[(b + 0) * 20 + 10 + ip], (double)c[(b + 1) * 20 + 10 + ip]);
       }
   fclose(ptr_out);
+  comm_barrier();
 }
 
 template <typename Float>
@@ -792,7 +854,7 @@ void QKXTM_Contraction<Float>::writeTwopBaryons_ASCII(void *corrBaryons, char *f
   const int *mv = qkxtm_moms();
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
-  if (!root) return;
+  if (!root) { comm_barrier(); return; }       // the writing rank joins when its file is complete (the reference has an MPI_Gather here)
   FILE *ptr_out = fopen(filename_out, "w");
   if (ptr_out == NULL) errorQuda("Error opening file for writing");
   const int tsrc = G.sourcePosition[(size_t)isource * 4 + 3];
@@ -809,6 +871,7 @@ void QKXTM_Contraction<Float>::writeTwopBaryons_ASCII(void *corrBaryons, char *f
                     sign * (double)c[(b + 1) * 320 + 160 + k]);
           }
   fclose(ptr_out);
+  comm_barrier();
 }
 
 template <typename Float>
@@ -864,7 +927,7 @@ void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrTh
   snprintf(fname_oneD, sizeof(fname_oneD), "%s.%s.%s.%s.SS.%02d.%02d.%02d.%02d.dat", filename_out, particle, flavour, "oneD", sp[0], sp[1], sp[2], sp[3]);
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
-  if (!root) return;
+  if (!root) { comm_barrier(); return; }       // the writing rank joins when its file is complete (the reference has an MPI_Gather here)
   const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
   const int *mv = qkxtm_moms();
   std::vector<Float> gathered;
@@ -886,7 +949,7 @@ void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrTh
                 sign * (double)c[k + 1]);
       }
   fclose(ptr_local);
-  if (!corrThp_noether) return;
+  if (!corrThp_noether) { comm_barrier(); return; }
   const Float *cn = (const Float *)corrThp_noether, *co = (const Float *)corrThp_oneD;
   FILE *ptr_noether = fopen(fname_noether, "w"), *ptr_oneD = fopen(fname_oneD, "w");
   if (ptr_noether == NULL || ptr_oneD == NULL) errorQuda("Error opening file for writing");
@@ -908,6 +971,7 @@ void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrTh
         }
   fclose(ptr_noether);
   fclose(ptr_oneD);
+  comm_barrier();
 }
 
 // ---- QKXTM_Deflation ----------------------------------------------------------------------------------------------------
@@ -1180,8 +1244,12 @@ void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam
   // the links of the conserved-current / one-derivative insertions (interface.cpp:351-357: K_gaugeContractions->packGauge(gauge))
   QKXTM_Gauge<float> *K_gaugeContractions = NULL;
   float *corrThp_noether = NULL, *corrThp_oneD = NULL;
-  if (any3pt && gauge && G.nranks > 1 && G.rank == 0)
-    fprintf(stderr, "WARNING: the conserved-current and one-derivative insertions are skipped on a split lattice\n");
+  // the conserved-current and one-derivative insertions read the neighbours' propagators and links; their halo exchange is not
+  // built, so on a split lattice the request is REFUSED (the reference computes them there: a silent skip would lose two of the
+  // three output files).  Passing gauge = NULL asks for the ultra-local insertion only, on any process grid.
+  if (any3pt && gauge && G.nranks > 1)
+    errorQuda("calcMG_threepTwop_EvenOdd: the conserved-current / one-derivative insertions are not available on a split lattice "
+              "(%d ranks); pass gauge = NULL for the ultra-local three-point function only", G.nranks);
   if (any3pt && gauge && G.nranks == 1) {
     K_gaugeContractions = new QKXTM_Gauge<float>(BOTH, GAUGE);
     K_gaugeContractions->packGauge(gauge);
@@ -1389,6 +1457,7 @@ void readLimeGauge(void **gauge, char *fname, QudaGaugeParam *param, QudaInvertP
   }
   printfQuda("Volume:   \t%ix%ix%ix%i\nSubvolume:\t%ix%ix%ix%i\n", GX[0], GX[1], GX[2], GX[3], param->X[0], param->X[1], param->X[2], param->X[3]);
   if (tmq_lime_read_gauge(fname, (double *const *)gauge, param->X, gridSize, G.coord)) errorQuda("%s", tmq_lime_last_error());
+  comm_barrier();      // ranks read their blocks at different speeds (the reference's MPI_File_read_all is collective)
 }
 void readLimeGaugeSmeared(void **gauge, char *fname, QudaGaugeParam *param, QudaInvertParam *inv_param, int gridSize[4]) {
   readLimeGauge(gauge, fname, param, inv_param, gridSize);      // same record layout (QKXTM_read_conf.h:401-675)
