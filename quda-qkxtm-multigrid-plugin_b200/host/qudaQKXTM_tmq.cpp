@@ -45,6 +45,7 @@ struct Globals {
   // it to every rank, so that the writers need no MPI_Gather over the time communicator (lib/qudaQKXTM_Contraction.cpp:1580-1584)
   std::vector<double> glob_mesons, glob_baryons, glob_thrp;
   int op_matpc = -1;
+  bool moms_overflow = false;         // init_qudaQKXTM saw more than MAX_NMOMENTA momenta
 } G;
 
 void default_error(const char *msg) {
@@ -435,15 +436,26 @@ void init_qudaQKXTM(qudaQKXTMinfo *info) {
   if (!info) errorQuda("null info");
   ensure_context(info->lL);
   G.nsmearGauss = info->nsmearGauss; G.alphaGauss = info->alphaGauss;      // GK_nsmearGauss, GK_alphaGauss (:125-127)
-  // createMomenta(info->Q_sq) (lib/qudaQKXTM_kernels.cu:98-116,128): all integer momenta with p^2 <= Q_sq, shell by shell
+  // createMomenta(info->Q_sq) (lib/qudaQKXTM_kernels.cu:98-116,128): all integer momenta with p^2 <= Q_sq, shell by shell.  More than
+  // MAX_NMOMENTA is an error in the reference; qkxtm/MG_Bench.cpp:534-544 never sets Q_sq (stack garbage), so the error is deferred to the
+  // first call that needs momenta: here the list is left empty with a warning
   G.moms.clear();
-  if (info->Q_sq > 3 * 4096) errorQuda("Error exceeded max number of momenta (Q_sq = %d; uninitialised?)", info->Q_sq);
-  for (int iQ = 0; iQ <= info->Q_sq; iQ++)
-    for (int nx = iQ; nx >= -iQ; nx--)
-      for (int ny = iQ; ny >= -iQ; ny--)
-        for (int nz = iQ; nz >= -iQ; nz--)
-          if (nx * nx + ny * ny + nz * nz == iQ) { G.moms.push_back(nx); G.moms.push_back(ny); G.moms.push_back(nz); }
-  if ((int)G.moms.size() / 3 > MAX_NMOMENTA) errorQuda("Error exceeded max number of momenta");
+  G.moms_overflow = false;
+  for (int iQ = 0; iQ <= info->Q_sq && !G.moms_overflow; iQ++) {
+    const int r = (int)std::floor(std::sqrt((double)iQ));
+    for (int nx = r; nx >= -r && !G.moms_overflow; nx--)
+      for (int ny = r; ny >= -r && !G.moms_overflow; ny--)
+        for (int nz = r; nz >= -r; nz--)
+          if (nx * nx + ny * ny + nz * nz == iQ) {
+            if ((int)G.moms.size() / 3 >= MAX_NMOMENTA) { G.moms_overflow = true; break; }
+            G.moms.push_back(nx); G.moms.push_back(ny); G.moms.push_back(nz);
+          }
+  }
+  if (G.moms_overflow) {
+    G.moms.clear();
+    if (G.rank == 0 && G.verbosity > QUDA_SILENT)
+      fprintf(stderr, "WARNING: init_qudaQKXTM: Q_sq = %d gives more than %d momenta (uninitialised info.Q_sq?): no momenta are kept, contractions will refuse\n", info->Q_sq, MAX_NMOMENTA);
+  }
   // qkxtm/MG_Bench.cpp:534-544 and CalcLowModeProjection.cpp leave Nsources (and more) of their stack-allocated info unset; the reference
   // copies that many positions without a check (lib/qudaQKXTM_kernels.cu:129-132).  Out-of-range values are taken as "no sources".
   int nsrc = info->Nsources;
@@ -765,6 +777,7 @@ void QKXTM_Contraction<Float>::contractMesons(QKXTM_Propagator<Float> &prop1, QK
       for (int ch = 0; ch < 20; ch++)
         for (int ri = 0; ri < 2; ri++) out[((size_t)2 * x + ri) * 20 + ch] = (Float)pos[((size_t)x * 20 + ch) * 2 + ri];
   } else if (CorrSpace == MOMENTUM_SPACE) {
+    if (G.moms_overflow) errorQuda("Error exceeded max number of momenta");     // lib/qudaQKXTM_kernels.cu:113
     if (nm <= 0) errorQuda("no momenta: init_qudaQKXTM was given Q_sq < 0");
     const int gT = Lt * G.grid[3];
     std::vector<double> mom((size_t)gT * nm * 40);
