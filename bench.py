@@ -6,13 +6,17 @@ One JSON line on stdout (rank 0).  Definitions (DESIGN.md section "Measurement")
            reductions) + 1 fused update launch, on a resident 48^3x96 (global) lattice, no host sync
   value    GFLOP/s over the K timed steps, QUDA flop model 5904 flop per parity site per iteration
            (SURVEY.md 8d), CUDA events on the launching stream, max over ranks
-  e2e      the same metric through the host-facing call: pinned host source -> H2D -> prepare -> M^dag ->
-           CG to tol (real iteration count) -> reconstruct -> D2H of the solution; copies inside the timed
-           region; flops = 5904 x Vh x iterations
+  solver_loop  the same iteration inside the real solver (tmq_cg_mdagm, stopping test included)
+  e2e      the same metric through the reference-facing plug-in calls of libqkxtm_tmq.so with HOST buffers (one process per rank running
+           the qkxtm_invert_test driver): invertMultiSrcQuda over 12 right-hand sides -- pinned host source -> H2D -> prepare -> M^dag ->
+           CG to tol (real iteration count) -> reconstruct -> D2H per column, every copy inside the timed region, the copies of the
+           neighbouring columns behind each solve; flops = 5904 x Vh x iterations.  The single invertQuda (fp64 and fp32-sloppy) is
+           reported beside it: one solve cannot hide its own copies
   roofline the hop + A^-1 Dslash kernel (EPI_TW, half of all Dslash launches) timed alone with CUDA events:
            algorithmic bytes (24 + 24 + 8*12) * 8 = 1152 B per output parity site (fp64, recon 12)
+  scale64  BASELINE.json configs[4], 64^3x128 sharded T then Z (T x Z at 8 GPUs): ms per fused CG iteration and the checksum of a solve
   cpu_baseline / --impl reference: the CPU oracle (oracle/, a port: the reference's own host code cannot be
-           built here) running CG iterations on the box's host cores
+           built here) running CG iterations of the same 48^3x96 workload on all host cores
 """
 import argparse
 import ctypes
@@ -54,17 +58,6 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-
-def committed_traffic(prec, recon, X):
-    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture (profiles/), if one exists
-    for this exact kernel and local lattice; else None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            t = json.load(f)
-        return t.get("dslash_kernel<%s,%d,EPI_TW>@%dx%dx%dx%d" % (("double" if prec == 8 else "float", recon) + tuple(X)))
-    except Exception:
-        return None
 
 
 class ClockSampler:
@@ -249,6 +242,129 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def kernel_source_hash():
+    """sha256 of the Dslash kernel sources: an ncu traffic figure is only quoted for the sources it was captured on"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("tmq_site.cuh", "tmq_dslash_inst.cuh", "tmq_types.h"):
+        with open(os.path.join(ROOT, "quda-qkxtm-multigrid-plugin_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(prec, recon, X):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture (profiles/ncu_traffic.json), if one exists
+    for this exact kernel, local lattice AND kernel sources (the capture records their hash); else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("kernel_source_sha256_16") != kernel_source_hash():
+            return None, "capture %s is of older kernel sources" % t.get("capture", "?")
+        return t.get("dslash_kernel<%s,%d,EPI_TW>@%dx%dx%dx%d" % (("double" if prec == 8 else "float", recon) + tuple(X))), t.get("capture")
+    except Exception:
+        return None, None
+
+
+def make_context(tmq, dist, rank, local_rank, X, grid, coord, args, n):
+    ctx = tmq.Context(X, grid=grid, coord=coord, device=local_rank)
+    if n > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(tmq.comm_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(uid, src=0)
+        ctx.comm_init(bytes(uid.numpy().tobytes()), n, rank)
+    if args.tile:
+        ctx.set_tile(*args.tile)
+    ctx.set_option(tmq.OPT_HALO_P2P, {"p2p": 2, "store": 1, "nccl": 0}[args.halo])
+    if args.boundary_at is not None:
+        ctx.set_option(3, args.boundary_at)
+    if args.pack_async is not None:
+        ctx.set_option(5, args.pack_async)
+    return ctx
+
+
+HALO_NAMES = {0: "none", 1: "nccl send/recv", 2: "peer-memory stores + fused launch", 3: "copy-engine peer copies + fused launch"}
+
+
+def e2e_through_the_plugin(args, n, rank, local_rank, GX, grid, dist):
+    """the e2e leg: the C++ QKXTM shim (libqkxtm_tmq.so: initQuda -> loadGaugeQuda -> invertQuda / invertMultiSrcQuda) driven by the
+    qkxtm_invert_test driver, one process per rank, page-locked HOST sources and solutions, every copy inside the timed region"""
+    drv = os.path.join(ROOT, "quda-qkxtm-multigrid-plugin_b200", "lib", "qkxtm_invert_test")
+    X = tuple(GX[d] // grid[d] for d in range(4))
+    env = dict(os.environ)
+    env["TMQ_COMM_ID_FILE"] = "/tmp/tmq_bench_id_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid())
+    env["TMQ_COMM_NONCE"] = "bench-%d-%s" % (os.getppid(), os.environ.get("TORCHELASTIC_RUN_ID", "-"))
+    env["LOCAL_RANK"] = str(local_rank)
+    env.pop("OMP_NUM_THREADS", None)                     # the host-side field generator may use the cores
+    cmd = [drv, "--dim"] + [str(v) for v in X] + ["--gridsize"] + [str(v) for v in grid] + \
+          ["--test", "e2e", "--tol", repr(args.tol), "--niter", str(args.maxiter), "--recon", str(args.recon), "--kappa", repr(KAPPA), "--mu", repr(MU),
+           "--nsrc", str(args.e2e_columns), "--e2e-reps", str(args.e2e_solves), "--seed", "100", "--verbosity-level", "silent"]
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+    if p.returncode != 0:
+        raise RuntimeError("e2e driver failed on rank %d: %s" % (rank, (p.stdout + p.stderr)[-2000:]))
+    if rank != 0:
+        return None
+    import re
+    r = json.loads(re.search(r"RESULT_E2E (\{.*\})", p.stdout).group(1))
+    Vh_glob = int(np.prod(GX)) // 2
+    field = r["bytes_per_field"] * n
+    gf = lambda it, secs: FLOPS_ITER * Vh_glob * it / secs * 1e-9
+    return {"value": gf(r["multi_iter"], r["multi_secs"]), "unit": "GFLOP/s",
+            "h2d_bytes_per_step": int(field * r["nsrc"] / max(r["multi_iter"], 1)), "d2h_bytes_per_step": int(field * r["nsrc"] / max(r["multi_iter"], 1)),
+            "what": "invertMultiSrcQuda of libqkxtm_tmq.so, %d right-hand sides (a point-to-all propagator has 12 columns), fp64, tol %g: pinned host source -> H2D -> "
+                    "prepare -> Mdag -> CG -> reconstruct -> D2H per column, the copies of columns k+-1 behind the solve of column k; step = one CG "
+                    "iteration, bytes amortised per iteration" % (r["nsrc"], args.tol),
+            "columns": r["nsrc"], "secs": r["multi_secs"], "iterations": r["multi_iter"], "true_res": r["multi_true_res"],
+            "solver_secs": r["multi_solver_secs"], "solver_ms_per_iter": r["multi_solver_secs"] / max(r["multi_iter"], 1) * 1e3,
+            "h2d_bytes_total": int(field * r["nsrc"]), "d2h_bytes_total": int(field * r["nsrc"]),
+            "single_solve": {"what": "one invertQuda, fp64 (nothing to hide the 2 x %.2f GB of PCIe traffic behind)" % (field / 1e9), "value": gf(r["single_iter"], r["single_secs"]),
+                             "secs": r["single_secs"], "iterations": r["single_iter"], "true_res": r["single_true_res"]},
+            "single_solve_mixed": {"what": "one invertQuda, cuda_prec_sloppy = single, reliable_delta = 1e-4 (the reference drivers' setting)",
+                                   "value": gf(r["mixed_iter"], r["mixed_secs"]), "secs": r["mixed_secs"], "iterations": r["mixed_iter"], "true_res": r["mixed_true_res"]}}
+
+
+def scale64_leg(tmq, args, n, rank, local_rank, dist):
+    """BASELINE.json configs[4]: 64^3 x 128, T then Z (T x Z at 8 GPUs), one fused CG iteration per step + a CG solve whose solution
+    checksum (sum of all components, |x|^2) must not depend on N"""
+    GX = (64, 64, 64, 128)
+    grid = {1: (1, 1, 1, 1), 2: (1, 1, 1, 2), 4: (1, 1, 1, 4), 8: (1, 1, 2, 4)}[n]
+    X = tuple(GX[d] // grid[d] for d in range(4))
+    coord = (0, 0, (rank // grid[3]) % grid[2], rank % grid[3])
+    Vh_loc = int(np.prod(X)) // 2
+    ctx = make_context(tmq, dist, rank, local_rank, X, grid, coord, args, n)
+    gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1, grid=grid, coord=coord)
+    ctx.load_gauge(gauge, t_boundary=-1, recon=args.recon)
+    del gauge
+    ctx.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
+    src = tmq.gen_spinor(X, "z4", seed=100, grid=grid, coord=coord)
+    b = ctx.spinor(8); b.set(src[:Vh_loc])
+    del src
+    ctx.time_kernel(4, 8, 3, b)
+    ctx.sync()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, _ = ctx.time_kernel(4, 8, max(args.steps, 10), b)
+    ms = dist_max(dist, ms)
+    x = ctx.spinor(8)
+    info = ctx.cg_mdagm(x, b, tol=1e-9, maxiter=2000)
+    clocks = sampler.stop() if rank == 0 else None
+    ones = ctx.spinor(8); ones.set(np.ones((Vh_loc, 4, 3, 2)))
+    sum_x = ctx.redot(ones, x)                                   # all-reduced over the ranks inside libtmq
+    norm2_x = ctx.norm2(x)
+    out = {"lattice": list(GX), "grid": list(grid), "local_lattice": list(X), "halo": HALO_NAMES[ctx.halo_mode()], "ms_per_step": ms,
+           "value": FLOPS_ITER * (int(np.prod(GX)) // 2) / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s",
+           "step": "1 fused CG iteration (4 Dslash + 1 update launch), fp64 recon %d" % args.recon,
+           "solution_checksum": {"sum_x": sum_x, "norm2_x": norm2_x, "iterations": info["iter"], "true_res": info["true_res"], "tol": 1e-9,
+                                 "solver_ms_per_iter": info["secs"] / max(info["iter"], 1) * 1e3},
+           "clocks": clocks}
+    ctx.close()
+    return out
+
+
 def run_native(args):
     import tmq
     n = args.gpus
@@ -268,27 +384,14 @@ def run_native(args):
     Vh_loc = int(np.prod(X)) // 2
     Vh_glob = int(np.prod(GX)) // 2
 
-    ctx = tmq.Context(X, grid=grid, coord=coord, device=local_rank)
-    if n > 1:
-        import torch
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(tmq.comm_unique_id()), dtype=torch.uint8).clone()
-        dist.broadcast(uid, src=0)
-        ctx.comm_init(bytes(uid.numpy().tobytes()), n, rank)
-    if args.tile:
-        ctx.set_tile(*args.tile)
-    ctx.set_option(tmq.OPT_HALO_P2P, {"p2p": 2, "store": 1, "nccl": 0}[args.halo])
-    if args.boundary_at is not None:
-        ctx.set_option(3, args.boundary_at)
-    if args.pack_async is not None:
-        ctx.set_option(5, args.pack_async)
-    halo_mode = {0: "none", 1: "nccl send/recv", 2: "peer-memory stores + fused launch", 3: "copy-engine peer copies + fused launch"}[ctx.halo_mode()]
+    ctx = make_context(tmq, dist, rank, local_rank, X, grid, coord, args, n)
+    halo_mode = HALO_NAMES[ctx.halo_mode()]
     gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1, grid=grid, coord=coord)
     ctx.load_gauge(gauge, t_boundary=-1, recon=recon)
     ctx.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
     src_full = tmq.gen_spinor(X, "z4", seed=100, grid=grid, coord=coord)
     b_par = ctx.spinor(8); b_par.set(src_full[:Vh_loc])
+    del src_full
 
     def barrier():
         ctx.sync()
@@ -311,6 +414,13 @@ def run_native(args):
     for kind in (0, 1, 2):
         ms, _ = ctx.time_kernel(kind, prec, max(args.steps, 10), b_par)
         kern[kind] = dist_max(dist, ms)
+    # the REAL solver loop (tmq_cg_mdagm: the same kernels plus the stopping test): K iterations, wall clock inside the library
+    xs = ctx.spinor(8)
+    ctx.cg_mdagm(xs, b_par, tol=1e-30, maxiter=3)
+    barrier()
+    loop = ctx.cg_mdagm(xs, b_par, tol=1e-30, maxiter=max(args.steps, 10))
+    solver_ms = dist_max(dist, loop["secs"] / max(loop["iter"], 1) * 1e3)
+    xs.free()
     clocks = sampler.stop() if rank == 0 else None
     l1 = ctx.launch_count()
     ms_step = dist_max(dist, ms_step)
@@ -319,89 +429,58 @@ def run_native(args):
     peak, peak_src = measured_peak()
     bps = bytes_per_site(1, prec, recon)
     ach = bps * Vh_loc / (kern[1] * 1e-3) * 1e-9
+    traffic, capture = (args.ncu_traffic, "command line") if args.ncu_traffic is not None else committed_traffic(prec, recon, X)
     roofline = {"bound": "hbm", "kernel": "dslash_kernel<%s,%d,EPI_TW> (hop + A^-1)" % ("double" if prec == 8 else "float", recon),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_site": bps, "sites_per_launch": Vh_loc, "ms_per_launch": kern[1],
-                "traffic": args.ncu_traffic if args.ncu_traffic is not None else committed_traffic(prec, recon, X)}
+                "traffic": traffic, "traffic_source": capture}
     kernels = {}
     for kind in (0, 1, 2):
-        b = bytes_per_site(kind, prec, recon)
-        kernels[KNAME[kind]] = {"ms": kern[kind], "GB/s": b * Vh_loc / (kern[kind] * 1e-3) * 1e-9,
+        bb = bytes_per_site(kind, prec, recon)
+        kernels[KNAME[kind]] = {"ms": kern[kind], "GB/s": bb * Vh_loc / (kern[kind] * 1e-3) * 1e-9,
                                 "GFLOP/s": FLOPS_K[kind] * Vh_loc / (kern[kind] * 1e-3) * 1e-9,
-                                "frac_of_hbm_peak": b * Vh_loc / (kern[kind] * 1e-3) * 1e-9 / peak}
+                                "frac_of_hbm_peak": bb * Vh_loc / (kern[kind] * 1e-3) * 1e-9 / peak}
     step_gbs = step_bytes_per_site(prec, recon) * Vh_loc / (ms_step * 1e-3) * 1e-9
-
-    # ---- e2e: the host-facing solve with HOST buffers (pinned), copies inside the timed region
-    e2e = None
-    cg_info = None
-    if not args.no_e2e:
-        import torch
-        host_b = torch.from_numpy(src_full.reshape(-1)).pin_memory() if torch.cuda.is_available() else None
-        hb = host_b.numpy().reshape(src_full.shape) if host_b is not None else src_full
-        host_x_t = torch.empty(src_full.size, dtype=torch.float64).pin_memory() if torch.cuda.is_available() else None
-        hx = host_x_t.numpy().reshape(src_full.shape) if host_x_t is not None else np.empty_like(src_full)
-        b = ctx.spinor(8, tmq.FULL); x = ctx.spinor(8, tmq.FULL)
-        spc, rhs, xpc = ctx.spinor(8), ctx.spinor(8), ctx.spinor(8)
-
-        def solve(sloppy=None):
-            b.set(hb)                                   # H2D
-            ctx.prepare(spc, b)
-            ctx.matpc(rhs, spc, 1)                      # in <- M^dag in (lib/qudaQKXTM_interface.cpp:2034)
-            info = ctx.cg_mdagm(xpc, rhs, tol=args.tol, maxiter=args.maxiter,
-                                sloppy_prec=args.sloppy_prec if sloppy is None else sloppy, reliable_delta=args.delta)
-            ctx.reconstruct(x, xpc, b)
-            ctx.L.tmq_spinor_to_host(hx.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), x.h)   # D2H
-            return info
-
-        solve()                                          # warm-up solve
-        barrier()
-        t0 = time.perf_counter()
-        reps = args.e2e_solves
-        for _ in range(reps):
-            cg_info = solve()
-        barrier()
-        dt = dist_max(dist, (time.perf_counter() - t0) / reps)
-        iters = cg_info["iter"]
-        e2e = {"value": FLOPS_ITER * Vh_glob * iters / dt * 1e-9, "unit": "GFLOP/s",
-               "h2d_bytes_per_step": int(src_full.nbytes * n / max(iters, 1)), "d2h_bytes_per_step": int(src_full.nbytes * n / max(iters, 1)),
-               "what": "host source -> H2D -> prepare -> Mdag -> CG(tol=%g) -> reconstruct -> D2H, per solve; bytes amortised per CG iteration" % args.tol,
-               "solve_secs": dt, "iterations": iters, "true_res": cg_info["true_res"],
-               "h2d_bytes_per_solve": int(src_full.nbytes * n), "d2h_bytes_per_solve": int(src_full.nbytes * n)}
-        # the drivers' usual invocation (--prec double --prec-sloppy single): same solve, fp32 inner
-        # iterations with reliable updates, fp64 true residual; reported beside the fp64 headline, not instead of it
-        if args.sloppy_prec == 8:
-            solve(4)
-            barrier()
-            t0 = time.perf_counter()
-            mi = solve(4)
-            barrier()
-            dtm = dist_max(dist, time.perf_counter() - t0)
-            e2e["mixed_precision_solve"] = {"solve_secs": dtm, "iterations": mi["iter"], "true_res": mi["true_res"],
-                                            "speedup_vs_fp64": dt / dtm}
 
     # ---- CPU baseline on rank 0, N=1 only (bounded sample of the same workload)
     cpu = None
     if n == 1 and not args.no_cpu:
-        del src_full
         rhs_np = np.ascontiguousarray(b_par.get())
         cpu = cpu_cg_sample(X, args.cpu_budget, gauge=gauge, rhs=rhs_np)
+        del rhs_np
+    del gauge
+    ctx.close()
+
+    # ---- e2e: through the plug-in's host-facing calls, HOST buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_through_the_plugin(args, n, rank, local_rank, GX, grid, dist)
+        if dist is not None:
+            dist.barrier()
+
+    # ---- 64^3 x 128 (BASELINE.json configs[4])
+    s64 = None
+    if args.scale64 and args.scaling == "strong":
+        s64 = scale64_leg(tmq, args, n, rank, local_rank, dist)
 
     if rank == 0:
+        cfg = workload_config(GX)
+        cfg["l2_policy"] = "inputs larger than L2 at every N: per step one GPU streams 4 gauge sweeps + 16 spinor fields = %.1f GB at N = %d (126 MB L2)" \
+                           % (step_bytes_per_site(prec, recon) * Vh_loc / 1e9, n)
         line = {"metric": "tm_dslash_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": n, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64" if prec == 8 else "f32", "data": "synthetic",
-                "config": {"workload": "%dx%dx%dx%d even-odd twisted-mass Dslash in CG on MdagM" % GX,
-                           "local_lattice": list(X), "grid": list(grid), "halo": halo_mode, "recon": recon, "kappa": KAPPA, "mu": MU,
-                           "matpc": "even-even", "step": "1 CG iteration = 4 Dslash launches + 1 fused update launch",
-                           "l2_policy": "inputs larger than L2 (parity spinor %.0f MB, gauge %.0f MB per sweep vs 126 MB L2)"
-                                        % (Vh_loc * 24 * prec / 1e6, Vh_loc * 8 * recon * prec / 1e6),
-                           "timing": "CUDA events on libtmq's compute stream, max over ranks; wall %.3f s" % wall},
+                "config": cfg,
+                "run": {"local_lattice": list(X), "grid": list(grid), "halo": halo_mode, "recon": recon,
+                        "step": "1 CG iteration = 4 Dslash launches + 1 fused update launch, no host sync (tmq_time_kernel kind 4)",
+                        "timing": "CUDA events on libtmq's compute stream, max over ranks; wall %.3f s" % wall},
+                "solver_loop": {"what": "the same iteration inside tmq_cg_mdagm (stopping test included), wall clock in the library, max over ranks",
+                                "ms_per_iter": solver_ms, "iterations": loop["iter"], "value": FLOPS_ITER * Vh_glob / (solver_ms * 1e-3) * 1e-9},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
                 "gpu_launches_total": int(l1 - l0),
                 "step_hbm_gbs": step_gbs, "step_frac_of_hbm_peak": step_gbs / peak,
-                "kernels": kernels, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+                "kernels": kernels, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "scale64": s64}
         print(json.dumps(line))
-    ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -427,7 +506,9 @@ def main():
     ap.add_argument("--maxiter", type=int, default=5000)
     ap.add_argument("--sloppy-prec", type=int, default=8, choices=[8, 4])
     ap.add_argument("--delta", type=float, default=1e-4, help="reliable_delta of the mixed-precision solve (the reference drivers set 1e-4, qkxtm/Calc_Loops.cpp:481)")
-    ap.add_argument("--e2e-solves", type=int, default=2)
+    ap.add_argument("--e2e-solves", type=int, default=2, help="repetitions of the single-solve legs of the e2e measurement")
+    ap.add_argument("--e2e-columns", type=int, default=12, help="right-hand sides of the pipelined e2e leg (a propagator has 12 columns)")
+    ap.add_argument("--scale64", type=int, default=1, help="also time 64^3x128 (BASELINE.json configs[4]) and emit its solution checksum")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -258,6 +258,8 @@ void freeCloverQuda(void);
 void endQuda(void);
 /* host spinors: full lattice, even-odd site order [even Vh | odd Vh][spin][colour][re,im], double */
 void invertQuda(void *h_x, void *h_b, QudaInvertParam *param);
+/* param->num_src right-hand sides; uploads / downloads of neighbouring columns run behind each solve */
+void invertMultiSrcQuda(void **hp_x, void **hp_b, QudaInvertParam *param);
 void MatQuda(void *h_out, void *h_in, QudaInvertParam *param);                 /* full operator */
 void setVerbosityQuda(QudaVerbosity verbosity, const char prefix[], FILE *outfile);
 /* multigrid is out of scope: newMultigridQuda aborts through errorQuda, destroyMultigridQuda(NULL) is a no-op */

@@ -271,6 +271,24 @@ int tmq_h2d(tmq_ctx *, void *dst, const void *src, size_t bytes);
 int tmq_d2h(tmq_ctx *, void *dst, const void *src, size_t bytes);
 int tmq_d2d(tmq_ctx *, void *dst, const void *src, size_t bytes);     /* asynchronous on the context's stream */
 
+/* ---- host <-> device pipelining for multi-RHS drivers (MG_bench's 12 columns, invertMultiSrcQuda): the PCIe copies of column k+-1
+ *      run behind the solve of column k.  Replaces the blocking cudaMemcpy of QKXTM_Vector::loadVector / unloadVector
+ *      (lib/qudaQKXTM_Vector.cpp:120-133) and of invertQuda's host fields around each solve (lib/qudaQKXTM_interface.cpp:118-131,205).
+ * Host fields are FULL, V*24 doubles, in one of two orders.  Two staging slots per direction; a slot may be reused as soon as the call
+ * that consumes it has been issued (the library orders the reuse with events).  Host buffers should be page-locked
+ * (tmq_host_alloc_pinned / tmq_host_register) or the copies degrade to synchronous staged ones (still correct).                    */
+enum { TMQ_HOST_ORDER_EO = 0,   /* [even Vh | odd Vh][spin][colour][re,im]: invertQuda's host spinors                                 */
+       TMQ_HOST_ORDER_LEX = 1   /* [x_lex][spin][colour][re,im]: the plug-in's host vectors before packVector / after unpackVector    */ };
+int tmq_host_prefetch(tmq_ctx *, int slot, const double *h_full);                  /* start the upload of a host field into slot       */
+int tmq_spinor_from_prefetch(tmq_spinor *dst_full, int slot, int host_order);      /* compute stream: wait for the upload, convert     */
+/* convert (times scale) into download slot `slot` on the compute stream, then copy to h_full on the download stream; returns at once */
+int tmq_spinor_to_host_async(double *h_full, const tmq_spinor *src_full, int slot, int host_order, double scale);
+int tmq_host_wait(tmq_ctx *);                                                     /* every outstanding upload / download is complete  */
+int tmq_host_alloc_pinned(tmq_ctx *, void **ptr, size_t bytes);
+int tmq_host_free_pinned(tmq_ctx *, void *ptr);
+int tmq_host_register(tmq_ctx *, void *ptr, size_t bytes);                        /* page-lock a caller-owned buffer (idempotent)      */
+int tmq_host_unregister(tmq_ctx *, void *ptr);
+
 /* ---- measurement helpers (CUDA events on the context's stream) ------------------------------------------ */
 /* run `reps` back-to-back applications of one kernel flavour on (a copy of) the PARITY field `in` and return
  * the average device time per application in milliseconds (CUDA events on the launching stream).

@@ -428,6 +428,8 @@ static int cg_fused_matvec(tmq_ctx *c, int prec, void *r, const void *p_, int r2
 using namespace tmq;
 
 // =====================================================================================================================
+extern "C" { static void io_release(tmq_ctx *c); }
+
 extern "C" {
 
 const char *tmq_last_error(void) { return tmq::g_err; }
@@ -567,6 +569,7 @@ int tmq_destroy(tmq_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   while (!c->spinors.empty()) tmq_spinor_free(*c->spinors.begin());
+  io_release(c);
   comm_destroy(c);
   eig_release(c);
   tmq_clover_free(c);
@@ -808,6 +811,147 @@ int tmq_spinor_to_host(double *h, const tmq_spinor *src) {
   return 0;
 }
 
+#define REQ_PARITY(s) TMQ_REQUIRE((s) && (s)->subset == TMQ_SUBSET_PARITY, #s " must be a PARITY field")
+#define REQ_FULL(s) TMQ_REQUIRE((s) && (s)->subset == TMQ_SUBSET_FULL, #s " must be a FULL field")
+#define REQ_SAME(a, b) TMQ_REQUIRE((a)->ctx == (b)->ctx && (a)->prec == (b)->prec, #a " and " #b " must share context and precision")
+#define REQ_OP(c) TMQ_REQUIRE((c)->op_set, "operator parameters not set (tmq_op_set)")
+
+// ---- host <-> device pipelining for multi-RHS drivers -----------------------------------------------------------------------
+// Column k of a propagator needs all of its source before the solve can start and has its solution only when the solve ends, so the
+// PCIe copies of ONE solve cannot hide behind it -- but the upload of column k+1 and the download of column k-1 can run behind the
+// solve of column k.  Uploads and downloads have their own streams (both DMA directions busy at once) and two staging slots each.
+static int io_ensure(tmq_ctx *c) {
+  if (c->up_stream) return 0;
+  TMQ_CUDA(cudaSetDevice(c->device));
+  TMQ_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  TMQ_CUDA(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+  const size_t bytes = (size_t)2 * c->g.Vh * 24 * sizeof(double);
+  for (int i = 0; i < 2; i++) {
+    TMQ_CUDA(cudaMalloc(&c->io_up[i], bytes));
+    TMQ_CUDA(cudaMalloc(&c->io_down[i], bytes));
+    TMQ_CUDA(cudaEventCreateWithFlags(&c->ev_up_done[i], cudaEventDisableTiming));
+    TMQ_CUDA(cudaEventCreateWithFlags(&c->ev_up_free[i], cudaEventDisableTiming));
+    TMQ_CUDA(cudaEventCreateWithFlags(&c->ev_down_ready[i], cudaEventDisableTiming));
+    TMQ_CUDA(cudaEventCreateWithFlags(&c->ev_down_done[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+static void io_release(tmq_ctx *c) {
+  if (!c->up_stream) return;
+  cudaStreamSynchronize(c->up_stream);
+  cudaStreamSynchronize(c->down_stream);
+  for (int i = 0; i < 2; i++) {
+    if (c->io_up[i]) cudaFree(c->io_up[i]);
+    if (c->io_down[i]) cudaFree(c->io_down[i]);
+    if (c->ev_up_done[i]) cudaEventDestroy(c->ev_up_done[i]);
+    if (c->ev_up_free[i]) cudaEventDestroy(c->ev_up_free[i]);
+    if (c->ev_down_ready[i]) cudaEventDestroy(c->ev_down_ready[i]);
+    if (c->ev_down_done[i]) cudaEventDestroy(c->ev_down_done[i]);
+    c->io_up[i] = c->io_down[i] = nullptr;
+  }
+  cudaStreamDestroy(c->up_stream);
+  cudaStreamDestroy(c->down_stream);
+  c->up_stream = c->down_stream = nullptr;
+  for (void *p : c->host_registered) cudaHostUnregister(p);
+  c->host_registered.clear();
+}
+
+int tmq_host_prefetch(tmq_ctx *c, int slot, const double *h_full) {
+  TMQ_REQUIRE(c && h_full, "null argument");
+  TMQ_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  TMQ_TRY(io_ensure(c));
+  // the slot is free once the conversion that read its previous content has run (first use: the event is unrecorded = complete)
+  TMQ_CUDA(cudaStreamWaitEvent(c->up_stream, c->ev_up_free[slot], 0));
+  TMQ_CUDA(cudaMemcpyAsync(c->io_up[slot], h_full, (size_t)2 * c->g.Vh * 24 * sizeof(double), cudaMemcpyHostToDevice, c->up_stream));
+  TMQ_CUDA(cudaEventRecord(c->ev_up_done[slot], c->up_stream));
+  return 0;
+}
+int tmq_spinor_from_prefetch(tmq_spinor *dst, int slot, int host_order) {
+  REQ_FULL(dst);
+  tmq_ctx *c = dst->ctx;
+  TMQ_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  TMQ_REQUIRE(c->up_stream, "tmq_host_prefetch has not been called");
+  TMQ_REQUIRE(host_order == TMQ_HOST_ORDER_EO || host_order == TMQ_HOST_ORDER_LEX, "bad host order");
+  const size_t pb = parity_bytes(c, dst->prec), blk = (size_t)c->g.Vh * 24 * sizeof(double);
+  TMQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up_done[slot], 0));
+  if (host_order == TMQ_HOST_ORDER_EO) {
+    for (int p = 0; p < 2; p++) {
+      TMQ_CUDA(spinor_from_host_eo(dst->prec, (char *)dst->d + (size_t)p * pb, (const double *)((const char *)c->io_up[slot] + (size_t)p * blk), c->g.Vh, c->stream));
+      c->launches++;
+    }
+  } else {
+    TMQ_CUDA(spinor_from_host_lex(dst->prec, dst->d, (char *)dst->d + pb, (const double *)c->io_up[slot], c->g, c->stream));
+    c->launches++;
+  }
+  TMQ_CUDA(cudaEventRecord(c->ev_up_free[slot], c->stream));
+  return 0;
+}
+int tmq_spinor_to_host_async(double *h_full, const tmq_spinor *src, int slot, int host_order, double scale) {
+  TMQ_REQUIRE(h_full, "null argument");
+  REQ_FULL(src);
+  tmq_ctx *c = src->ctx;
+  TMQ_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  TMQ_REQUIRE(host_order == TMQ_HOST_ORDER_EO || host_order == TMQ_HOST_ORDER_LEX, "bad host order");
+  TMQ_TRY(io_ensure(c));
+  const size_t pb = parity_bytes(c, src->prec), blk = (size_t)c->g.Vh * 24 * sizeof(double);
+  TMQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_down_done[slot], 0));       // the slot's previous download has left it
+  if (host_order == TMQ_HOST_ORDER_EO) {
+    if (scale != 1.0) {
+      // (the eo converter has no scale: apply it in place on a scratch-free path -- the lexicographic converter multiplies on the fly)
+      for (int p = 0; p < 2; p++) { TMQ_CUDA(blas_ax(src->prec, scale, (char *)src->d + (size_t)p * pb, nvec(c), c->stream)); c->launches++; }
+    }
+    for (int p = 0; p < 2; p++) {
+      TMQ_CUDA(spinor_to_host_eo((double *)((char *)c->io_down[slot] + (size_t)p * blk), src->prec, (const char *)src->d + (size_t)p * pb, c->g.Vh, c->stream));
+      c->launches++;
+    }
+  } else {
+    TMQ_CUDA(spinor_to_host_lex((double *)c->io_down[slot], src->prec, src->d, (const char *)src->d + pb, scale, c->g, c->stream));
+    c->launches++;
+  }
+  TMQ_CUDA(cudaEventRecord(c->ev_down_ready[slot], c->stream));
+  TMQ_CUDA(cudaStreamWaitEvent(c->down_stream, c->ev_down_ready[slot], 0));
+  TMQ_CUDA(cudaMemcpyAsync(h_full, c->io_down[slot], (size_t)2 * blk, cudaMemcpyDeviceToHost, c->down_stream));
+  TMQ_CUDA(cudaEventRecord(c->ev_down_done[slot], c->down_stream));
+  return 0;
+}
+int tmq_host_wait(tmq_ctx *c) {
+  TMQ_REQUIRE(c, "null context");
+  if (c->up_stream) { TMQ_CUDA(cudaStreamSynchronize(c->up_stream)); TMQ_CUDA(cudaStreamSynchronize(c->down_stream)); }
+  TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int tmq_host_alloc_pinned(tmq_ctx *c, void **ptr, size_t bytes) {
+  TMQ_REQUIRE(c && ptr, "null argument");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  TMQ_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return 0;
+}
+int tmq_host_free_pinned(tmq_ctx *c, void *ptr) {
+  TMQ_REQUIRE(c, "null context");
+  TMQ_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+int tmq_host_register(tmq_ctx *c, void *ptr, size_t bytes) {
+  TMQ_REQUIRE(c && ptr, "null argument");
+  for (void *p : c->host_registered) if (p == ptr) return 0;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost) return 0;      // already page-locked
+  cudaGetLastError();
+  TMQ_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  c->host_registered.push_back(ptr);
+  return 0;
+}
+int tmq_host_unregister(tmq_ctx *c, void *ptr) {
+  TMQ_REQUIRE(c && ptr, "null argument");
+  for (size_t i = 0; i < c->host_registered.size(); i++)
+    if (c->host_registered[i] == ptr) {
+      TMQ_CUDA(cudaHostUnregister(ptr));
+      c->host_registered.erase(c->host_registered.begin() + i);
+      return 0;
+    }
+  return 0;
+}
+
 // ---- operator -------------------------------------------------------------------------------------------------------
 int tmq_op_set(tmq_ctx *c, double kappa, double mu, int matpc) {
   TMQ_REQUIRE(c, "null context");
@@ -816,10 +960,6 @@ int tmq_op_set(tmq_ctx *c, double kappa, double mu, int matpc) {
   return 0;
 }
 
-#define REQ_PARITY(s) TMQ_REQUIRE((s) && (s)->subset == TMQ_SUBSET_PARITY, #s " must be a PARITY field")
-#define REQ_FULL(s) TMQ_REQUIRE((s) && (s)->subset == TMQ_SUBSET_FULL, #s " must be a FULL field")
-#define REQ_SAME(a, b) TMQ_REQUIRE((a)->ctx == (b)->ctx && (a)->prec == (b)->prec, #a " and " #b " must share context and precision")
-#define REQ_OP(c) TMQ_REQUIRE((c)->op_set, "operator parameters not set (tmq_op_set)")
 
 int tmq_dslash(tmq_spinor *out, const tmq_spinor *in, int out_parity, int dagger) {
   REQ_PARITY(out); REQ_PARITY(in); REQ_SAME(out, in);

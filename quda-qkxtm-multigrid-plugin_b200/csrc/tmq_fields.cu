@@ -139,6 +139,52 @@ template <typename F> __global__ void to_aos_kernel(double *aos, const VecT<F> *
     s[4 * j] = v.a; s[4 * j + 1] = v.b; s[4 * j + 2] = v.c; s[4 * j + 3] = v.d;
   }
 }
+// plug-in host order [x_lex][spin][colour][re,im] (lib/qudaQKXTM_Vector.cpp:72-81 BEFORE packVector) <-> native, both parities at once:
+// thread sid owns the lexicographic sites 2 sid and 2 sid + 1 (384 contiguous bytes), one of each parity (uploadToCuda_core.h:7-20)
+template <typename F> __global__ void from_aos_lex_kernel(VecT<F> *even, VecT<F> *odd, const double *__restrict__ aos, Geom g) {
+  const int sid = blockIdx.x * FB + threadIdx.x;
+  if (sid >= g.Vh) return;
+  const int row = sid / g.Xh;
+  const int y = row % g.X[1], z = (row / g.X[1]) % g.X[2], t = row / (g.X[1] * g.X[2]);
+  const int oddFirst = (y + z + t) & 1;
+  VecT<F> *dst0 = oddFirst ? odd : even, *dst1 = oddFirst ? even : odd;
+  const double *s = aos + (size_t)sid * 48;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    VecT<F> v; v.a = (F)s[4 * j]; v.b = (F)s[4 * j + 1]; v.c = (F)s[4 * j + 2]; v.d = (F)s[4 * j + 3];
+    dst0[(size_t)j * g.Vh + sid] = v;
+    VecT<F> w; w.a = (F)s[24 + 4 * j]; w.b = (F)s[24 + 4 * j + 1]; w.c = (F)s[24 + 4 * j + 2]; w.d = (F)s[24 + 4 * j + 3];
+    dst1[(size_t)j * g.Vh + sid] = w;
+  }
+}
+template <typename F> __global__ void to_aos_lex_kernel(double *aos, const VecT<F> *__restrict__ even, const VecT<F> *__restrict__ odd, double scale, Geom g) {
+  const int sid = blockIdx.x * FB + threadIdx.x;
+  if (sid >= g.Vh) return;
+  const int row = sid / g.Xh;
+  const int y = row % g.X[1], z = (row / g.X[1]) % g.X[2], t = row / (g.X[1] * g.X[2]);
+  const int oddFirst = (y + z + t) & 1;
+  const VecT<F> *src0 = oddFirst ? odd : even, *src1 = oddFirst ? even : odd;
+  double *s = aos + (size_t)sid * 48;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const VecT<F> v = src0[(size_t)j * g.Vh + sid], w = src1[(size_t)j * g.Vh + sid];
+    s[4 * j] = scale * v.a; s[4 * j + 1] = scale * v.b; s[4 * j + 2] = scale * v.c; s[4 * j + 3] = scale * v.d;
+    s[24 + 4 * j] = scale * w.a; s[24 + 4 * j + 1] = scale * w.b; s[24 + 4 * j + 2] = scale * w.c; s[24 + 4 * j + 3] = scale * w.d;
+  }
+}
+cudaError_t spinor_from_host_lex(int prec, void *even, void *odd, const double *d_aos, const Geom &g, cudaStream_t st) {
+  const int grid = (g.Vh + FB - 1) / FB;
+  if (prec == 8) from_aos_lex_kernel<double><<<grid, FB, 0, st>>>((VecT<double> *)even, (VecT<double> *)odd, d_aos, g);
+  else from_aos_lex_kernel<float><<<grid, FB, 0, st>>>((VecT<float> *)even, (VecT<float> *)odd, d_aos, g);
+  return cudaGetLastError();
+}
+cudaError_t spinor_to_host_lex(double *d_aos, int prec, const void *even, const void *odd, double scale, const Geom &g, cudaStream_t st) {
+  const int grid = (g.Vh + FB - 1) / FB;
+  if (prec == 8) to_aos_lex_kernel<double><<<grid, FB, 0, st>>>(d_aos, (const VecT<double> *)even, (const VecT<double> *)odd, scale, g);
+  else to_aos_lex_kernel<float><<<grid, FB, 0, st>>>(d_aos, (const VecT<float> *)even, (const VecT<float> *)odd, scale, g);
+  return cudaGetLastError();
+}
+
 cudaError_t spinor_from_host_eo(int prec, void *dst, const double *d_aos, int Vh, cudaStream_t st) {
   const int grid = (Vh + FB - 1) / FB;
   if (prec == 8) from_aos_kernel<double><<<grid, FB, 0, st>>>((VecT<double> *)dst, d_aos, Vh);

@@ -86,6 +86,13 @@ struct tmq_ctx {
   // grow-only device staging buffer for host <-> native conversions
   void *stage;
   size_t stage_bytes;
+  // host <-> device pipelining of multi-RHS drivers (tmq_host_prefetch / tmq_spinor_from_prefetch / tmq_spinor_to_host_async): two
+  // upload and two download staging slots of one FULL host field each, their own copy streams, and the events that order slot reuse
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;
+  void *io_up[2] = {nullptr, nullptr}, *io_down[2] = {nullptr, nullptr};
+  cudaEvent_t ev_up_done[2] = {nullptr, nullptr}, ev_up_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_down_ready[2] = {nullptr, nullptr}, ev_down_done[2] = {nullptr, nullptr};
+  std::vector<void *> host_registered;
   // live spinor handles allocated on this context (freed by tmq_destroy; their handles die with the context)
   std::set<tmq_spinor *> spinors;
   // timing-kernel scratch (tmq_time_kernel)
@@ -221,6 +228,8 @@ cudaError_t spinor_to_qkxtm(void *qk, int qprec, int prec, const void *even, con
                             const Geom &g, cudaStream_t st);
 cudaError_t spinor_from_host_eo(int prec, void *dst, const double *d_aos, int Vh, cudaStream_t st);
 cudaError_t spinor_to_host_eo(double *d_aos, int prec, const void *src, int Vh, cudaStream_t st);
+cudaError_t spinor_from_host_lex(int prec, void *even, void *odd, const double *d_aos, const Geom &g, cudaStream_t st);
+cudaError_t spinor_to_host_lex(double *d_aos, int prec, const void *even, const void *odd, double scale, const Geom &g, cudaStream_t st);
 cudaError_t plaquette_launch(int recon, const void *gauge_d, const Geom &g, const BlasRed &r, cudaStream_t st);
 cudaError_t qkxtm_plaquette(const void *gq, int prec, const Geom &g, const BlasRed &r, cudaStream_t st);
 cudaError_t qkxtm_scale(void *d, int prec, double a, size_t ncplx, cudaStream_t st);

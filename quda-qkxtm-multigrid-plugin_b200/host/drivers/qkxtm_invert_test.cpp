@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 #include "../../../include/qudaQKXTM_tmq.h"
@@ -37,6 +38,7 @@ int main(int argc, char **argv) {
   int Nstoch = 1, NdumpStep = 1, k_probing = 0, hadamLow = 0, hadamHigh = 0, n_defl_steps = 0, defl_step_nEv[MAX_DEFLSTEPS] = {0};
   bool spinColorDil = false, isFullOp = false;
   std::string source_type = "random";
+  int nsrc = 12, e2e_reps = 2;
   int nsmearGauss = 0; double alphaGauss = 4.0;                              // qkxtm/QKXTM_util.cpp:1652-1654
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -81,6 +83,8 @@ int main(int argc, char **argv) {
     else if (a == "--isFullOp") { need(1); isFullOp = std::string(argv[++i]) == "yes"; }
     else if (a == "--source-type") { need(1); source_type = argv[++i]; }      // random | unity
     else if (a == "--defl-steps") { need(1); n_defl_steps = atoi(argv[++i]); need(n_defl_steps); for (int d = 0; d < n_defl_steps && d < MAX_DEFLSTEPS; d++) defl_step_nEv[d] = atoi(argv[++i]); }
+    else if (a == "--nsrc") { need(1); nsrc = atoi(argv[++i]); }               // columns of the pipelined multi-RHS leg of --test e2e
+    else if (a == "--e2e-reps") { need(1); e2e_reps = atoi(argv[++i]); }
     else if (a == "--help") { usage(); return 0; }
     else { fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
   }
@@ -197,6 +201,60 @@ int main(int argc, char **argv) {
     result.insert(result.end(), K_defl.H_elem(), K_defl.H_elem() + (size_t)V * 24);
     inv_param.iter = deflation->MatVecs();
     delete deflation;
+  } else if (test == "e2e") {
+    // END-TO-END timing through the reference-facing calls with HOST buffers (bench.py's e2e leg): page-locked host sources and
+    // solutions, every copy inside the timed region.  (1) one invertQuda, fp64; (2) one invertQuda with the drivers' usual fp32 sloppy
+    // precision; (3) nsrc columns through invertMultiSrcQuda, fp64, uploads / downloads of neighbouring columns behind each solve.
+    const size_t nbytes = (size_t)V * 24 * sizeof(double);
+    double *hb[2], *hx[2];
+    for (int k = 0; k < 2; k++) {
+      void *p = nullptr;
+      if (tmq_host_alloc_pinned(qkxtm_context(), &p, nbytes)) { fprintf(stderr, "%s\n", tmq_last_error()); return 1; }
+      hb[k] = (double *)p;
+      if (tmq_host_alloc_pinned(qkxtm_context(), &p, nbytes)) { fprintf(stderr, "%s\n", tmq_last_error()); return 1; }
+      hx[k] = (double *)p;
+      tmq_fieldgen_spinor_z4(hb[k], dim, grid, coord, seed + k, 1);
+    }
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const QudaPrecision sloppy_saved = inv_param.cuda_prec_sloppy;
+    inv_param.cuda_prec_sloppy = QUDA_DOUBLE_PRECISION;
+    invertQuda(hx[0], hb[0], &inv_param);                                       // warm-up (module load, scratch allocation)
+    comm_barrier();
+    auto t0 = now();
+    for (int r = 0; r < e2e_reps; r++) invertQuda(hx[r & 1], hb[r & 1], &inv_param);
+    comm_barrier();
+    const double t_single = secs(t0, now()) / e2e_reps;
+    const int it_single = inv_param.iter;
+    const double res_single = inv_param.true_res;
+    inv_param.cuda_prec_sloppy = QUDA_SINGLE_PRECISION;
+    invertQuda(hx[0], hb[0], &inv_param);
+    comm_barrier();
+    t0 = now();
+    for (int r = 0; r < e2e_reps; r++) invertQuda(hx[r & 1], hb[r & 1], &inv_param);
+    comm_barrier();
+    const double t_mixed = secs(t0, now()) / e2e_reps;
+    const int it_mixed = inv_param.iter;
+    const double res_mixed = inv_param.true_res;
+    inv_param.cuda_prec_sloppy = QUDA_DOUBLE_PRECISION;
+    std::vector<void *> pb(nsrc), px(nsrc);
+    for (int k = 0; k < nsrc; k++) { pb[k] = hb[k & 1]; px[k] = hx[k & 1]; }
+    inv_param.num_src = nsrc;
+    comm_barrier();
+    t0 = now();
+    invertMultiSrcQuda(px.data(), pb.data(), &inv_param);
+    comm_barrier();
+    const double t_multi = secs(t0, now());
+    const int it_multi = inv_param.iter;
+    const double res_multi = inv_param.true_res, solver_secs_multi = inv_param.secs;
+    inv_param.cuda_prec_sloppy = sloppy_saved;
+    // the last solution is returned (even-odd host order) so that the caller can check it
+    result.assign(hx[(nsrc - 1) & 1], hx[(nsrc - 1) & 1] + (size_t)V * 24);
+    if (root)
+      printf("RESULT_E2E {\"single_secs\": %.6f, \"single_iter\": %d, \"single_true_res\": %.6e, \"mixed_secs\": %.6f, \"mixed_iter\": %d, "
+             "\"mixed_true_res\": %.6e, \"nsrc\": %d, \"multi_secs\": %.6f, \"multi_iter\": %d, \"multi_true_res\": %.6e, \"multi_solver_secs\": %.6f, "
+             "\"bytes_per_field\": %zu}\n", t_single, it_single, res_single, t_mixed, it_mixed, res_mixed, nsrc, t_multi, it_multi, res_multi, solver_secs_multi, nbytes);
+    for (int k = 0; k < 2; k++) { tmq_host_free_pinned(qkxtm_context(), hb[k]); tmq_host_free_pinned(qkxtm_context(), hx[k]); }
   } else if (test == "calcloops") {
     // qkxtm/Calc_Loops.cpp main() (:585-791): arpackInfo, loopInfo, the operator of the eigensolver, then calc_loops.  The hook stands where
     // the reference contracts: it records every eigenvalue of the exact part and, for every solve and deflation step, the host source and

@@ -364,6 +364,24 @@ static void check_solver(const QudaInvertParam *p) {
   if (p->solution_type != QUDA_MAT_SOLUTION) errorQuda("solution_type must be QUDA_MAT_SOLUTION (qkxtm/Calc_Loops.cpp:439)");
   if (p->tol <= 0 || p->maxiter <= 0) errorQuda("tol and maxiter must be positive");
 }
+// The reference's propagator drivers hard-wire GCR preconditioned by multigrid (qkxtm/MG_Bench.cpp:361,443; lib/qudaQKXTM_interface.cpp:32,
+// 267 refuse anything else).  That solver is out of scope; the SYSTEM it solves is not: the entry points substitute CG on the even-odd
+// normal operator for it -- the same solution to the same tolerance -- say so once, and restore the caller's parameters on return.
+struct SolverSubstitution {
+  QudaInvertParam *p;
+  QudaInverterType inv;
+  QudaSolveType solve;
+  SolverSubstitution(QudaInvertParam *param, const char *who) : p(param), inv(param->inv_type), solve(param->solve_type) {
+    if (p->inv_type != QUDA_GCR_INVERTER) return;
+    static bool told = false;
+    if (!told && G.rank == 0 && G.verbosity > QUDA_SILENT)
+      fprintf(stderr, "WARNING: %s: GCR (+ multigrid) was requested; this library solves the same system with CG on M^dag M (even-odd, fp64 or fp32/fp64 mixed)\n", who);
+    told = true;
+    p->inv_type = QUDA_CG_INVERTER;
+    p->solve_type = QUDA_NORMOP_PC_SOLVE;
+  }
+  ~SolverSubstitution() { p->inv_type = inv; p->solve_type = solve; }
+};
 // createDirac: the operator parameters live in the context
 static void create_dirac(const QudaInvertParam *p) {
   const int m = matpc_of(p);
@@ -408,6 +426,39 @@ void invertQuda(void *h_x, void *h_b, QudaInvertParam *param) {
   if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION)
     TMQ_OK(tmq_ax(2.0 * param->kappa, x.handle()));
   TMQ_OK(tmq_spinor_to_host((double *)h_x, x.handle()));
+}
+
+// invertMultiSrcQuda (upstream quda.h): param->num_src right-hand sides, hp_b[k] -> hp_x[k], same host order as invertQuda.  The
+// solves run one after the other on the compute stream; the upload of source k+1 and the download of solution k-1 run behind the
+// solve of column k on their own streams (tmq_host_prefetch / tmq_spinor_to_host_async), so that in the steady state a column costs
+// its solve and nothing else.  param->iter / secs / gflops are summed over the columns, true_res is the largest one.
+void invertMultiSrcQuda(void **hp_x, void **hp_b, QudaInvertParam *param) {
+  if (!hp_x || !hp_b || !param) errorQuda("null argument");
+  const int n = param->num_src;
+  if (n < 1) errorQuda("invertMultiSrcQuda: num_src = %d", n);
+  for (int k = 0; k < n; k++) if (!hp_x[k] || !hp_b[k]) errorQuda("invertMultiSrcQuda: null host field %d", k);
+  check_solver(param);
+  const bool massnorm = param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION;
+  const double scale = massnorm ? 2.0 * param->kappa : 1.0;
+  if (getenv("TMQ_HOST_REGISTER") && atoi(getenv("TMQ_HOST_REGISTER")) > 0)      // page-lock the caller's buffers (kept until endQuda)
+    for (int k = 0; k < n; k++) {
+      TMQ_OK(tmq_host_register(G.ctx, hp_b[k], (size_t)G.localVolume * 24 * sizeof(double)));
+      TMQ_OK(tmq_host_register(G.ctx, hp_x[k], (size_t)G.localVolume * 24 * sizeof(double)));
+    }
+  ColorSpinorField b(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION), x(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  int iter = 0;
+  double secs = 0, flops = 0, worst = 0;
+  TMQ_OK(tmq_host_prefetch(G.ctx, 0, (const double *)hp_b[0]));
+  for (int k = 0; k < n; k++) {
+    if (k + 1 < n) TMQ_OK(tmq_host_prefetch(G.ctx, (k + 1) & 1, (const double *)hp_b[k + 1]));
+    TMQ_OK(tmq_spinor_from_prefetch(b.handle(), k & 1, TMQ_HOST_ORDER_EO));
+    solve_device(x, b, param);
+    iter += param->iter; secs += param->secs; flops += param->gflops * param->secs;
+    worst = param->true_res > worst ? param->true_res : worst;
+    TMQ_OK(tmq_spinor_to_host_async((double *)hp_x[k], x.handle(), k & 1, TMQ_HOST_ORDER_EO, scale));
+  }
+  TMQ_OK(tmq_host_wait(G.ctx));
+  param->iter = iter; param->secs = secs; param->gflops = secs > 0 ? flops / secs : 0; param->true_res = worst;
 }
 
 void MatQuda(void *h_out, void *h_in, QudaInvertParam *param) {
@@ -1155,14 +1206,13 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
               double *prop_out) {
   (void)gauge;
   if (!param || !gauge_param) errorQuda("null argument");
+  SolverSubstitution subst(param, "MG_bench");
   check_solver(param);
   if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
   if (G.nsmearGauss != 0 && !gaugeSmeared) errorQuda("Gaussian smearing of the source needs the smeared links (gaugeSmeared)");
   const bool flag_eo = info.isEven;     // (the reference leaves this unset; b and x are full fields, so it is moot)
   const auto T0 = std::chrono::steady_clock::now();
   const long long V = G.localVolume;
-  double *input_vector = (double *)malloc((size_t)V * 24 * sizeof(double));
-  if (!input_vector) errorQuda("Error allocating memory for the host source");
   QKXTM_Vector<double> *K_vector = new QKXTM_Vector<double>(BOTH, VECTOR);
   QKXTM_Vector<double> *K_guess = new QKXTM_Vector<double>(BOTH, VECTOR);
   QKXTM_Gauge<double> *K_gaugeSmeared = NULL;
@@ -1176,14 +1226,18 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
   ColorSpinorField *b = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
   ColorSpinorField *x = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
   printfQuda("\n ### Calculations for source-position %d - %02d.%02d.%02d.%02d begin now ###\n\nForward Inversions:\n", 0, 0, 0, 0, 0);
+  const bool massnorm = param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION;
   for (int isc = 0; isc < 12; isc++) {
     const auto t4 = std::chrono::steady_clock::now();
-    memset(input_vector, 0, (size_t)V * 24 * sizeof(double));
     if (param->mu < 0) param->mu *= -1.0;                 // "Ensure mu is positive" (interface.cpp:162-163)
-    if (G.coord[0] == 0 && G.coord[1] == 0 && G.coord[2] == 0 && G.coord[3] == 0)
-      input_vector[isc * 2] = 1.0;                        // point source at the origin, spin-colour isc (on the rank that holds it)
-    K_vector->packVector(input_vector);
-    K_vector->loadVector();
+    // point source at the origin, spin-colour isc (on the rank that holds it).  The reference zeroes a host vector, sets one entry,
+    // packVector()s it and copies V x 24 reals over PCIe (interface.cpp:165-176); the same device vector is made here by a device
+    // memset and ONE 16-byte copy into component isc of site 0 of the QKXTM layout d[(s*3+c)*V + x]
+    K_vector->zero_device();
+    if (G.coord[0] == 0 && G.coord[1] == 0 && G.coord[2] == 0 && G.coord[3] == 0) {
+      const double one[2] = {1.0, 0.0};
+      TMQ_OK(tmq_h2d(G.ctx, K_vector->D_elem() + (size_t)isc * V * 2, one, sizeof(one)));
+    }
     if (K_gaugeSmeared) {
       K_guess->gaussianSmearing(*K_vector, *K_gaugeSmeared);            // interface.cpp:184 (nsmearGauss = 0 copies)
       K_guess->uploadToCuda(b, flag_eo);                                // :185
@@ -1193,16 +1247,14 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
     printfQuda(" up - %02d: \n", isc);
     solve_device(*x, *b, param);
     K_vector->downloadFromCuda(x, flag_eo);
-    if (param->mass_normalization == QUDA_MASS_NORMALIZATION || param->mass_normalization == QUDA_ASYMMETRIC_MASS_NORMALIZATION)
-      K_vector->scaleVector(2 * param->kappa);
-    if (prop_out) {
-      K_vector->download();
-      memcpy(prop_out + (size_t)isc * V * 24, K_vector->H_elem(), (size_t)V * 24 * sizeof(double));
-    }
+    if (massnorm) K_vector->scaleVector(2 * param->kappa);
+    // column isc to the caller: converted to the host order on the device and copied on the download stream, behind the next solve
+    if (prop_out)
+      TMQ_OK(tmq_spinor_to_host_async(prop_out + (size_t)isc * V * 24, x->handle(), isc & 1, TMQ_HOST_ORDER_LEX, massnorm ? 2 * param->kappa : 1.0));
     printfQuda("Inversion up = %d, for source = %d finished in time %f sec\n", isc, 0,
                std::chrono::duration<double>(std::chrono::steady_clock::now() - t4).count());
   }
-  free(input_vector);
+  if (prop_out) TMQ_OK(tmq_host_wait(G.ctx));
   delete K_vector;
   delete K_guess;
   if (K_gaugeSmeared) delete K_gaugeSmeared;
@@ -1214,6 +1266,7 @@ void MG_bench(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, Qu
 void calcMG_threepTwop_EvenOdd(void **gaugeSmeared, void **gauge, QudaGaugeParam *gauge_param, QudaInvertParam *param, qudaQKXTMinfo info,
                                char *filename_twop, char *filename_threep, WHICHPARTICLE NUCLEON) {
   if (!param || !gauge_param || !filename_twop) errorQuda("null argument");
+  SolverSubstitution subst(param, "calcMG_threepTwop_EvenOdd");
   check_solver(param);
   if (!G.qkxtm_initialized) errorQuda("You must initialize init_qudaQKXTM first");
   if (param->gamma_basis != QUDA_UKQCD_GAMMA_BASIS) errorQuda("This function works only with ukqcd gamma basis");       // interface.cpp:270-273
@@ -1587,7 +1640,7 @@ void calc_loops(void **gaugeToPlaquette, QudaInvertParam *EvInvParam, QudaInvert
   if (arpackInfo.isEven && (EvInvParam->matpc_type != QUDA_MATPC_EVEN_EVEN_ASYMMETRIC)) errorQuda("%s: Inconsistency between operator types!", fname);
   if ((!arpackInfo.isEven) && (EvInvParam->matpc_type != QUDA_MATPC_ODD_ODD_ASYMMETRIC)) errorQuda("%s: Inconsistency between operator types!", fname);
   if ((param->inv_type != QUDA_GCR_INVERTER) && (param->inv_type != QUDA_CG_INVERTER)) errorQuda("%s: This function works only with GCR/CG solver", fname);
-  if (param->inv_type == QUDA_GCR_INVERTER) errorQuda("%s: the GCR + multigrid solver is not provided by this library (use --inv-type cg)", fname);
+  SolverSubstitution subst(param, fname);          // the GCR branch (:2025-2030) solves the same system
   if (param->gamma_basis != QUDA_UKQCD_GAMMA_BASIS) errorQuda("%s: This function works only with ukqcd gamma basis", fname);
   if (param->dirac_order != QUDA_DIRAC_ORDER) errorQuda("%s: This function works only with color-inside-spin", fname);
   if (loopInfo.FileFormat == HDF5_FORM && g_loop_hook == nullptr) printfQuda("%s: no contraction hook installed: no loop files (HDF5 or ASCII) are written\n", fname);

@@ -140,7 +140,7 @@ def test_reference_MG_Bench_driver_on_libtmq(env):
     o, gauge = env["o"], env["gauge"]
     out, err = run_ref("MG_Bench", COMMON + ["--load-gauge", env["conf"], "--load-gauge-smeared", env["conf"], "--nsmearGauss", 0, "--useEven", "true"])
     assert "Begin MG bench routine" in out
-    assert "multigrid preconditioner is not provided" in err
+    assert "multigrid preconditioner is not provided" in err and "GCR (+ multigrid) was requested" in err      # the driver hard-wires GCR + MG
     assert out.count("Inversion up =") == 12
     iters = [int(m) for m in re.findall(r"CG: Convergence at (\d+) iterations", out)]
     assert len(iters) == 12
@@ -153,14 +153,15 @@ def test_reference_MG_Bench_driver_on_libtmq(env):
 
 
 def test_reference_driver_refuses_what_is_not_built(env):
-    """--inv-type gcr (the reference's multigrid path) is refused with an errorQuda abort, not silently replaced"""
+    """--prec single asks for an fp32 solution field, which the QKXTM containers cannot take (the upload kernel writes double2,
+    lib/qudaQKXTM_kernels.cu:1031): refused with an errorQuda abort, not silently replaced"""
     path = os.path.join(DROPIN, "MG_Bench")
     if not os.path.exists(path):
         pytest.skip("oracle/_ref/dropin not built")
     args = [str(a) for a in COMMON]
-    args[args.index("cg")] = "gcr"
+    args[args.index("--prec") + 1] = "single"
     p = subprocess.run([path] + args + ["--load-gauge", env["conf"], "--load-gauge-smeared", env["conf"], "--nsmearGauss", "0"], capture_output=True, text=True, timeout=300)
-    assert p.returncode != 0 and "CG inverter only" in p.stderr
+    assert p.returncode != 0 and "ERROR" in p.stderr
 
 
 @pytest.mark.parametrize("mode", ["dilution", "probing", "unity"])

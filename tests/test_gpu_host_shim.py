@@ -182,3 +182,20 @@ def test_calcLowModeProjection_entry_point(tmp_path, env):
     assert np.allclose(r[:nev], lam, rtol=1e-9)
     p = subprocess.run([DRV, "--dim"] + [str(x) for x in X] + ["--test", "lowmodes", "--matpc", "even-even"], capture_output=True, text=True, timeout=120)
     assert p.returncode != 0 and "Only asymmetric operators are supported in deflation" in p.stderr
+
+
+def test_invertMultiSrcQuda_pipeline_and_e2e_driver(tmp_path, env):
+    """--test e2e: invertQuda (fp64, then fp32-sloppy) and invertMultiSrcQuda with page-locked host fields; the uploads / downloads of
+    neighbouring columns run behind each solve (tmq_host_prefetch / tmq_spinor_to_host_async).  The last column's solution must solve
+    M x = b for ITS source, i.e. no column was mixed up by the slot reuse, and the mass normalisation is applied on the device."""
+    import json
+    o, gauge, tmq = env
+    nsrc = 5
+    for norm, scale in (("kappa", 1.0), ("mass", 2 * KAPPA)):
+        x, _, _, out = run(tmp_path, "--test", "e2e", "--tol", "1e-10", "--recon", "12", "--nsrc", str(nsrc), "--seed", "100", "--mass-normalization", norm)
+        r = json.loads(re.search(r"RESULT_E2E (\{.*\})", out).group(1))
+        b = tmq.gen_spinor(X, "z4", seed=100 + ((nsrc - 1) & 1))          # the driver alternates two sources (seed, seed + 1)
+        assert lu.rel_l2(o.mat(gauge, x.reshape(b.shape) / scale, KAPPA, MU, 0), b) < 1e-8
+        assert r["single_true_res"] <= 1.05e-10 and r["mixed_true_res"] <= 1.05e-10 and r["multi_true_res"] <= 1.05e-10
+        assert abs(r["single_iter"] - r["mixed_iter"]) <= 2
+        assert r["nsrc"] == nsrc and abs(r["multi_iter"] - nsrc * r["single_iter"]) <= 2 * nsrc
