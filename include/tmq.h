@@ -139,6 +139,9 @@ int tmq_reconstruct(tmq_spinor *x_full, const tmq_spinor *x_pc, const tmq_spinor
  * Outputs mirror QudaInvertParam::{iter,true_res,secs,gflops} (updateInvertParam).                         */
 int tmq_cg_mdagm(tmq_spinor *x, const tmq_spinor *b, double tol, int maxiter, double reliable_delta,
                  int sloppy_prec, int *iters, double *true_res, double *secs, double *gflops);
+/* statistics of the last solve: wall time of the iteration loop alone (set-up and the final true-residual computation excluded),
+ * number of reliable updates (fp64 residual recomputations) of a mixed-precision solve; either pointer may be NULL             */
+int tmq_cg_stats(tmq_ctx *, double *loop_secs, int *reliable_updates);
 /* optional residual history of the last solve (|r|^2 per iteration), up to n entries                       */
 int tmq_cg_history(tmq_ctx *, double *r2, int n);
 

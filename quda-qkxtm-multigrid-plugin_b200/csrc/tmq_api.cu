@@ -1055,6 +1055,8 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
   double r2 = b2;
   int k = 0;
   if (b2 == 0.0) { *iters = 0; *true_res = 0.0; return 0; }
+  const auto tl0 = std::chrono::steady_clock::now();
+  c->cg_reliable_updates = 0;
   while (r2 > stop && k < maxiter) {
     const int so = SC_R2_0 + (k & 1), sn = SC_R2_0 + ((k + 1) & 1);
     if (fused) {
@@ -1078,6 +1080,8 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
     c->cg_hist.push_back(r2);
     if (!(r2 == r2)) { set_error("CG broke down (NaN residual) at iteration %d", k); return 1; }
   }
+  TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  c->cg_loop_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - tl0).count();
   // true residual |b - M^dag M x| / |b|
   void *Ax = p;
   TMQ_TRY(op_mdagm(c, prec, Ax, x->d, SC_T3));
@@ -1118,6 +1122,8 @@ static int cg_mixed(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol, 
   const double stop = tol * tol * b2;
   double r2 = b2, rNorm = sqrt(r2), r0Norm = rNorm, maxrx = rNorm, maxrr = rNorm;
   int k = 0, cur = 0;   // scal[SC_R2_0 + cur] holds r2
+  const auto tl0 = std::chrono::steady_clock::now();
+  c->cg_reliable_updates = 0;
   while (r2 > stop && k < maxiter) {
     const int so = SC_R2_0 + cur, sn = SC_R2_0 + (1 - cur);
     TMQ_TRY(cg_fused_matvec(c, 4, rS, pS, so, sn));
@@ -1150,11 +1156,14 @@ static int cg_mixed(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol, 
       r2 = r2t;
       rNorm = sqrt(r2);
       r0Norm = rNorm; maxrr = rNorm; maxrx = rNorm;
+      c->cg_reliable_updates++;
     }
     cur = 1 - cur;
     k++;
     c->cg_hist.push_back(r2);
   }
+  TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  c->cg_loop_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - tl0).count();
   // flush what is left in the sloppy accumulator and compute the true residual
   TMQ_CUDA(blas_xpy_mixed(y, xS, n, c->stream)); c->launches++;
   TMQ_TRY(op_mdagm(c, 8, AyD, y, SC_T3));
@@ -1192,6 +1201,12 @@ int tmq_cg_mdagm(tmq_spinor *x, const tmq_spinor *b, double tol, int maxiter, do
   return 0;
 }
 
+int tmq_cg_stats(tmq_ctx *c, double *loop_secs, int *reliable_updates) {
+  TMQ_REQUIRE(c, "null context");
+  if (loop_secs) *loop_secs = c->cg_loop_secs;
+  if (reliable_updates) *reliable_updates = c->cg_reliable_updates;
+  return 0;
+}
 int tmq_cg_history(tmq_ctx *c, double *r2, int n) {
   TMQ_REQUIRE(c && r2, "null argument");
   const int m = (int)c->cg_hist.size();

@@ -83,6 +83,8 @@ struct tmq_ctx {
   tmq::Comm *comm;
   long long launches;
   std::vector<double> cg_hist;
+  double cg_loop_secs = 0;     // wall time of the iteration loop of the last solve (without set-up and the true-residual computation)
+  int cg_reliable_updates = 0;
   // grow-only device staging buffer for host <-> native conversions
   void *stage;
   size_t stage_bytes;

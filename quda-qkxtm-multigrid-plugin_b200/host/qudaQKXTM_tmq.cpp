@@ -46,6 +46,8 @@ struct Globals {
   std::vector<double> glob_mesons, glob_baryons, glob_thrp;
   int op_matpc = -1;
   bool moms_overflow = false;         // init_qudaQKXTM saw more than MAX_NMOMENTA momenta
+  quda::ColorSpinorField *work[3] = {nullptr, nullptr, nullptr};   // parity work fields of solve_device
+  quda::ColorSpinorField *io_b = nullptr, *io_x = nullptr;         // FULL fields of invertQuda / invertMultiSrcQuda
 } G;
 
 void default_error(const char *msg) {
@@ -303,7 +305,13 @@ void initQuda(int device) {
   G.quda_initialized = true;
 }
 
+static void release_work_fields() {
+  for (int i = 0; i < 3; i++) { delete G.work[i]; G.work[i] = nullptr; }
+  delete G.io_b; delete G.io_x;
+  G.io_b = G.io_x = nullptr;
+}
 void endQuda(void) {
+  release_work_fields();
   if (G.ctx) { tmq_destroy(G.ctx); G.ctx = nullptr; }
   G.quda_initialized = G.qkxtm_initialized = G.gauge_loaded = false;
   G.op_matpc = -1;
@@ -339,6 +347,7 @@ void freeCloverQuda(void) {
   G.clover_loaded = false;
 }
 void freeGaugeQuda(void) {
+  release_work_fields();
   if (G.ctx) tmq_gauge_free(G.ctx);
   G.gauge_loaded = false;
 }
@@ -396,8 +405,11 @@ static void solve_device(ColorSpinorField &x, ColorSpinorField &b, QudaInvertPar
   create_dirac(param);
   param->secs = 0; param->gflops = 0; param->iter = 0; param->true_res = 0;       // interface.cpp:95-97
   param->spinorGiB = (double)G.localVolume * 24 * 8 * 5 / (1024.0 * 1024.0 * 1024.0);
-  ColorSpinorField in(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION), out(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION),
-      tmp(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  // the three parity work fields live as long as the gauge field: the reference allocates them per call (interface.cpp:1923-1937), but a
+  // cudaFree per solve is a device-wide synchronisation that would also stall the copies running behind it on the other streams
+  for (int i = 0; i < 3; i++)
+    if (!G.work[i]) G.work[i] = new ColorSpinorField(QUDA_PARITY_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  ColorSpinorField &in = *G.work[0], &out = *G.work[1], &tmp = *G.work[2];
   const auto t0 = std::chrono::steady_clock::now();
   TMQ_OK(tmq_prepare(tmp.handle(), b.handle()));                                   // dirac.prepare            (:2020)
   TMQ_OK(tmq_matpc(in.handle(), tmp.handle(), 1));                                 // in <- M^dag in           (:2034)
@@ -409,9 +421,12 @@ static void solve_device(ColorSpinorField &x, ColorSpinorField &b, QudaInvertPar
   TMQ_OK(tmq_sync(G.ctx));
   param->iter = iters; param->true_res = true_res; param->gflops = gflops;         // updateInvertParam
   param->secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  double loop_secs = 0;
+  int nrel = 0;
+  tmq_cg_stats(G.ctx, &loop_secs, &nrel);
   if (G.verbosity >= QUDA_SUMMARIZE)
-    printfQuda("CG: Convergence at %d iterations, L2 relative residual: true = %e (tol %e); %.3f secs, %.1f Gflops\n",
-               iters, true_res, param->tol, param->secs, gflops);
+    printfQuda("CG: Convergence at %d iterations, L2 relative residual: true = %e (tol %e); %.3f secs (solver %.3f, its iteration loop %.3f, %d reliable updates), %.1f Gflops\n",
+               iters, true_res, param->tol, param->secs, secs, loop_secs, nrel, gflops);
   if (iters >= param->maxiter && G.verbosity > QUDA_SILENT)
     fprintf(stderr, "WARNING: Exceeded maximum iterations %d\n", param->maxiter);   // warningQuda continues
 }
@@ -419,7 +434,9 @@ static void solve_device(ColorSpinorField &x, ColorSpinorField &b, QudaInvertPar
 void invertQuda(void *h_x, void *h_b, QudaInvertParam *param) {
   if (!h_x || !h_b || !param) errorQuda("null argument");
   check_solver(param);
-  ColorSpinorField b(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION), x(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  if (!G.io_b) G.io_b = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  if (!G.io_x) G.io_x = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  ColorSpinorField &b = *G.io_b, &x = *G.io_x;
   TMQ_OK(tmq_spinor_from_host(b.handle(), (const double *)h_b));
   solve_device(x, b, param);
   // x *= 2 kappa for the mass normalisations (lib/qudaQKXTM_interface.cpp:200-203), on the device
@@ -445,7 +462,9 @@ void invertMultiSrcQuda(void **hp_x, void **hp_b, QudaInvertParam *param) {
       TMQ_OK(tmq_host_register(G.ctx, hp_b[k], (size_t)G.localVolume * 24 * sizeof(double)));
       TMQ_OK(tmq_host_register(G.ctx, hp_x[k], (size_t)G.localVolume * 24 * sizeof(double)));
     }
-  ColorSpinorField b(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION), x(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  if (!G.io_b) G.io_b = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  if (!G.io_x) G.io_x = new ColorSpinorField(QUDA_FULL_SITE_SUBSET, QUDA_DOUBLE_PRECISION);
+  ColorSpinorField &b = *G.io_b, &x = *G.io_x;
   int iter = 0;
   double secs = 0, flops = 0, worst = 0;
   TMQ_OK(tmq_host_prefetch(G.ctx, 0, (const double *)hp_b[0]));

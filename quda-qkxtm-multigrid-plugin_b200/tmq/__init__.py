@@ -31,7 +31,7 @@ tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm t
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
 tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free
-tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d tmq_barrier tmq_host_prefetch tmq_spinor_from_prefetch tmq_spinor_to_host_async tmq_host_wait tmq_host_alloc_pinned tmq_host_free_pinned tmq_host_register tmq_host_unregister""".split()
+tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d tmq_barrier tmq_host_prefetch tmq_spinor_from_prefetch tmq_spinor_to_host_async tmq_host_wait tmq_host_alloc_pinned tmq_host_free_pinned tmq_host_register tmq_host_unregister tmq_cg_stats""".split()
 
 
 class TmqError(RuntimeError):
@@ -77,6 +77,7 @@ def load():
     L.tmq_mat_full.argtypes = [vp, vp, C.c_int]
     L.tmq_prepare.argtypes = [vp, vp]; L.tmq_reconstruct.argtypes = [vp, vp, vp]
     L.tmq_cg_mdagm.argtypes = [vp, vp, C.c_double, C.c_int, C.c_double, C.c_int, ip, dp, dp, dp]
+    L.tmq_cg_stats.argtypes = [vp, dp, ip]
     L.tmq_cg_history.argtypes = [vp, dp, C.c_int]
     L.tmq_zero.argtypes = [vp]; L.tmq_copy.argtypes = [vp, vp]
     L.tmq_ax.argtypes = [C.c_double, vp]
@@ -287,7 +288,9 @@ class Context:
         it = C.c_int(0); tr = C.c_double(0); secs = C.c_double(0); gf = C.c_double(0)
         _ck(self.L.tmq_cg_mdagm(x.h, b.h, tol, maxiter, reliable_delta, sloppy_prec, C.byref(it), C.byref(tr),
                                 C.byref(secs), C.byref(gf)))
-        return dict(iter=it.value, true_res=tr.value, secs=secs.value, gflops=gf.value)
+        ls = C.c_double(0); ru = C.c_int(0)
+        _ck(self.L.tmq_cg_stats(self.h, C.byref(ls), C.byref(ru)))
+        return dict(iter=it.value, true_res=tr.value, secs=secs.value, gflops=gf.value, loop_secs=ls.value, reliable_updates=ru.value)
 
     def cg_history(self, n):
         h = np.zeros(n)
