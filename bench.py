@@ -276,7 +276,7 @@ def make_context(tmq, dist, rank, local_rank, X, grid, coord, args, n):
         ctx.comm_init(bytes(uid.numpy().tobytes()), n, rank)
     if args.tile:
         ctx.set_tile(*args.tile)
-    ctx.set_option(tmq.OPT_HALO_P2P, {"p2p": 2, "store": 1, "nccl": 0}[args.halo])
+    ctx.set_option(tmq.OPT_HALO_P2P, {"fused": 3, "p2p": 2, "store": 1, "nccl": 0}[args.halo])
     if args.boundary_at is not None:
         ctx.set_option(3, args.boundary_at)
     if args.pack_async is not None:
@@ -284,7 +284,8 @@ def make_context(tmq, dist, rank, local_rank, X, grid, coord, args, n):
     return ctx
 
 
-HALO_NAMES = {0: "none", 1: "nccl send/recv", 2: "peer-memory stores + fused launch", 3: "copy-engine peer copies + fused launch"}
+HALO_NAMES = {0: "none", 1: "nccl send/recv", 2: "peer-memory stores + fused launch", 3: "copy-engine peer copies + fused launch",
+              4: "fused compute + halo exchange: boundary CTAs store the next application's faces into the neighbours' arenas"}
 
 
 def e2e_through_the_plugin(args, n, rank, local_rank, GX, grid, dist):
@@ -500,7 +501,7 @@ def main():
     ap.add_argument("--tile", type=int, nargs=3, default=None)
     ap.add_argument("--boundary-at", type=int, default=None, help="%% of interior CTAs scheduled before the boundary CTAs")
     ap.add_argument("--pack-async", type=int, default=None, help="1: launch the face pack on the exchange stream (TMQ_OPT_PACK_ASYNC)")
-    ap.add_argument("--halo", default="p2p", choices=["p2p", "store", "nccl"],
+    ap.add_argument("--halo", default="p2p", choices=["fused", "p2p", "store", "nccl"],
                     help="ghost exchange: copy-engine peer copies (p2p) or peer stores from the pack kernel (store), both with one fused Dslash launch; or ncclSend/Recv")
     ap.add_argument("--tol", type=float, default=1e-9)
     ap.add_argument("--maxiter", type=int, default=5000)

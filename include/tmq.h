@@ -70,6 +70,11 @@ enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3, 
                                       ghost face or all-reduce contribution; on expiry nothing is computed from stale ghosts, the device
                                       error scalar is raised and the enclosing call (tmq_sync, tmq_cg_mdagm, ...) fails */ };   /* TMQ_OPT_PREFETCH: accepted and ignored (the L2-prefetch experiment was removed: no gain) */
 int tmq_set_option(tmq_ctx *, int option, int value);
+/* TMQ_OPT_HALO_P2P = 3: FUSED compute + halo exchange.  Inside the chains of applications the library issues back to back (M_pc,
+ * M^dag M, the CG iteration) the boundary CTAs of the launch that PRODUCES a field pack its faces for the next application and store
+ * them straight into the neighbours' arenas over NVLink, then publish the arrival flags: one kernel per application, no pack launch,
+ * no copy-engine transfer, no NCCL call.  Only the first application of a chain uses the stand-alone pack launch of mode 1.
+ * tmq_halo_mode returns 4.  */
 /* TMQ_OPT_HALO_P2P selects the ghost exchange.  0: ncclSend/ncclRecv on a separate stream + interior / boundary
  * launches.  1: the pack kernel stores the faces straight into the neighbours' ghost arenas over NVLink peer mappings
  * (CUDA IPC, set up by tmq_comm_init).  2 (default): faces are packed locally and pushed by the copy engines into the

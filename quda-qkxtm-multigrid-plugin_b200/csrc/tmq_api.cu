@@ -228,6 +228,66 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
     return 0;
   }
 
+  if (c->p2p && c->opt_p2p == 3) {
+    // ---- fused compute + halo exchange: ONE launch per application.  Its boundary CTAs wait for this application's faces
+    //      (arrival flags in our own arena), compute, and then pack the faces of their OUTPUT for the NEXT application straight into
+    //      the neighbours' arenas over NVLink; the last boundary CTA publishes the next sequence number.  The boundary CTAs sit in
+    //      the middle of the grid, so the peer stores overlap the remaining interior CTAs.  Only the first application of a chain
+    //      (whose input was not produced by a Dslash launch, e.g. the CG search direction) needs the stand-alone pack launch.
+    //      Buffer reuse: faces for application N+1 go into buffer (N+1)&1 = (N-1)&1 of the neighbour, which it read in application
+    //      N-1; a boundary CTA only packs after it has seen the neighbour's flag N, which the neighbour publishes after ALL its
+    //      boundary CTAs of application N-1 are done.
+    const unsigned int seq = ++c->halo_seq;
+    const int buf = (int)(seq & 1u);
+    const HaloArena &L = c->arena_layout;
+    auto fill_dst = [&](PackDst<F> &D, unsigned int sq) {
+      memset(&D, 0, sizeof(D));
+      const int b2 = (int)(sq & 1u);
+      D.seq = sq; D.ticket = c->ticket2;
+      for (int d = 2; d < 4; d++) {
+        if (!g.part[d]) continue;
+        const int sl = D.nslot++;
+        D.dim[sl] = d;
+        // slice 0 is the "from forward neighbour" ghost (dir 1) of rank-1; slice L-1 the dir-0 ghost of rank+1
+        D.dst[sl][0] = (VecT<F> *)(c->peer_arena[d][0] + L.recv[b2][pi][d][1]);
+        D.flag[sl][0] = (unsigned int *)(c->peer_arena[d][0] + arena_flag_off(L, b2, d, 1));
+        D.dst[sl][1] = (VecT<F> *)(c->peer_arena[d][1] + L.recv[b2][pi][d][0]);
+        D.flag[sl][1] = (unsigned int *)(c->peer_arena[d][1] + arena_flag_off(L, b2, d, 0));
+      }
+    };
+    for (int d = 2; d < 4; d++) {
+      if (!g.part[d]) continue;
+      for (int dir = 0; dir < 2; dir++) {
+        A.ghost[d][dir] = (const VecT<F> *)(c->arena + L.recv[buf][pi][d][dir]);
+        A.hw.flag[A.hw.n++] = (const unsigned int *)(c->arena + arena_flag_off(L, buf, d, dir));
+      }
+    }
+    A.hw.seq = seq;
+    if (c->prepacked_seq == seq) {
+      TMQ_REQUIRE(c->prepacked_in == in && c->prepacked_dagger == s.dagger && c->prepacked_parity == s.out_parity && c->prepacked_prec == prec,
+                  "internal error: the faces sent ahead by the previous launch do not belong to this application");
+    } else {
+      PackDst<F> D;
+      fill_dst(D, seq);
+      TMQ_CUDA(halo_pack_p2p(c->recon, A, D, c->stream));
+      c->launches++;
+    }
+    if (s.pack_next && out != nullptr && s.epi != EPI_CG4) {
+      fill_dst(A.pk, seq + 1);
+      A.pk_on = 1;
+      A.pk_dsign = s.next_dagger ? (F)-1 : (F)1;
+      c->prepacked_seq = seq + 1; c->prepacked_in = out; c->prepacked_dagger = s.next_dagger ? 1 : 0;
+      c->prepacked_parity = 1 - s.out_parity; c->prepacked_prec = prec;
+    }
+    A.en = en_int; A.en_b[0] = en_t; A.en_b[1] = en_z;
+    A.nblk[0] = nblocks(en_int); A.nblk[1] = nblocks(en_t); A.nblk[2] = nblocks(en_z);
+    A.npre = (int)((long long)A.nblk[0] * c->opt_pre_pct / 100);
+    TMQ_CUDA(launch_any<F>(c, s.epi, true, A, c->stream));
+    c->launches++;
+    if (has_red) TMQ_TRY(comm_allreduce(c, c->scal + s.red_slot, 1, c->stream));
+    return 0;
+  }
+
   if (c->p2p) {
     // ---- peer-memory path: faces are stored straight into the neighbours' ghost arenas by ONE pack launch;
     //      ONE Dslash launch computes interior CTAs first and boundary CTAs last, which wait on arrival flags.
@@ -352,20 +412,20 @@ int op_matpc(tmq_ctx *c, int prec, void *out, const void *in, int dagger) {
   void *t0 = scr(c, prec, 0), *t1 = scr(c, prec, 1);
   HopSpec a, b;
   if (!asym && !dagger) {
-    a.epi = EPI_TW; a.out_parity = q; a.t1 = tw_Ainv(c, 0);
+    a.epi = EPI_TW; a.out_parity = q; a.t1 = tw_Ainv(c, 0); a.pack_next = 1; a.next_dagger = 0;
     TMQ_TRY(apply_hop(c, prec, t0, in, a));
     b.epi = EPI_TW_XPAY; b.out_parity = p; b.t1 = tw_Ainv(c, 0); b.k = k2; b.x = in;
     return apply_hop(c, prec, out, t0, b);
   }
   if (!asym && dagger) {
     TMQ_TRY(site_op(c, prec, t1, in, p, tw_Ainv(c, 1)));
-    a.epi = EPI_TW; a.out_parity = q; a.dagger = 1; a.t1 = tw_Ainv(c, 1);
+    a.epi = EPI_TW; a.out_parity = q; a.dagger = 1; a.t1 = tw_Ainv(c, 1); a.pack_next = 1; a.next_dagger = 1;
     TMQ_TRY(apply_hop(c, prec, t0, t1, a));
     b.epi = EPI_XPAY; b.out_parity = p; b.dagger = 1; b.k = k2; b.x = in;
     return apply_hop(c, prec, out, t0, b);
   }
   // asymmetric, either direction: t = A^-(dag) D(dag) in ; out = A(dag) in - k^2 D(dag) t
-  a.epi = EPI_TW; a.out_parity = q; a.dagger = dagger; a.t1 = tw_Ainv(c, dagger);
+  a.epi = EPI_TW; a.out_parity = q; a.dagger = dagger; a.t1 = tw_Ainv(c, dagger); a.pack_next = 1; a.next_dagger = dagger;
   TMQ_TRY(apply_hop(c, prec, t0, in, a));
   b.epi = EPI_TWX_XPAY; b.out_parity = p; b.dagger = dagger; b.tx = tw_A(c, dagger); b.k = k2; b.x = in;
   return apply_hop(c, prec, out, t0, b);
@@ -386,15 +446,15 @@ int op_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int pap_slot) {
   TMQ_TRY(ensure_scratch(c, prec, 2));
   void *t0 = scr(c, prec, 0), *t1 = scr(c, prec, 1);
   HopSpec k1, k2s, k3, k4;
-  k1.epi = EPI_TW; k1.out_parity = q; k1.t1 = tw_Ainv(c, 0);
+  k1.epi = EPI_TW; k1.out_parity = q; k1.t1 = tw_Ainv(c, 0); k1.pack_next = 1; k1.next_dagger = 0;
   TMQ_TRY(apply_hop(c, prec, t0, in, k1));
   k2s.epi = EPI_MDAGM2; k2s.out_parity = p; k2s.t1 = tw_Ainv(c, 0); k2s.k = k2; k2s.x = in; k2s.t3 = tw_Ainv(c, 1);
-  k2s.red_slot = pap_slot;
+  k2s.red_slot = pap_slot; k2s.pack_next = 1; k2s.next_dagger = 1;
   // twisted-clover: K2 also stores y = M in, and K4 forms y - k^2 D^dag u from it instead of applying A^dag to w
   void *ybuf = nullptr;
   if (c->clover_on) { TMQ_TRY(ensure_scratch(c, prec, 7)); ybuf = scr(c, prec, 6); k2s.out2 = ybuf; }
   TMQ_TRY(apply_hop(c, prec, t1, t0, k2s));
-  k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1);
+  k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1); k3.pack_next = 1; k3.next_dagger = 1;
   TMQ_TRY(apply_hop(c, prec, t0, t1, k3));
   k4.epi = EPI_TWX_XPAY; k4.out_parity = p; k4.dagger = 1; k4.tx = tw_A(c, 1); k4.k = k2; k4.x = t1;
   if (ybuf) { k4.x = ybuf; k4.cl_plain_x = 1; }
@@ -408,14 +468,14 @@ static int cg_fused_matvec(tmq_ctx *c, int prec, void *r, const void *p_, int r2
   const double k2 = -c->kappa * c->kappa;
   void *t0 = scr(c, prec, 0), *t1 = scr(c, prec, 1);
   HopSpec k1, k2s, k3, k4;
-  k1.epi = EPI_TW; k1.out_parity = q; k1.t1 = tw_Ainv(c, 0);
+  k1.epi = EPI_TW; k1.out_parity = q; k1.t1 = tw_Ainv(c, 0); k1.pack_next = 1; k1.next_dagger = 0;
   TMQ_TRY(apply_hop(c, prec, t0, p_, k1));
   k2s.epi = EPI_MDAGM2; k2s.out_parity = p; k2s.t1 = tw_Ainv(c, 0); k2s.k = k2; k2s.x = p_; k2s.t3 = tw_Ainv(c, 1);
-  k2s.red_slot = SC_PAP;
+  k2s.red_slot = SC_PAP; k2s.pack_next = 1; k2s.next_dagger = 1;
   void *ybuf = nullptr;
   if (c->clover_on) { TMQ_TRY(ensure_scratch(c, prec, 7)); ybuf = scr(c, prec, 6); k2s.out2 = ybuf; }
   TMQ_TRY(apply_hop(c, prec, t1, t0, k2s));
-  k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1);
+  k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1); k3.pack_next = 1; k3.next_dagger = 1;
   TMQ_TRY(apply_hop(c, prec, t0, t1, k3));
   k4.epi = EPI_CG4; k4.out_parity = p; k4.dagger = 1; k4.tx = tw_A(c, 1); k4.k = k2; k4.x = t1; k4.r = r;
   if (ybuf) { k4.x = ybuf; k4.cl_plain_x = 1; }
@@ -642,7 +702,8 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
     case TMQ_OPT_HALO_TIMEOUT_MS: c->opt_halo_timeout_ms = value > 0 ? value : 120000; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {
-      c->opt_p2p = value < 0 ? 0 : (value > 2 ? 2 : value);
+      c->opt_p2p = value < 0 ? 0 : (value > 3 ? 3 : value);
+      c->prepacked_seq = 0;
       bool all_mapped = c->multi;
       for (int d = 2; d < 4; d++)
         if (c->g.part[d]) all_mapped = all_mapped && c->peer_arena[d][0] && c->peer_arena[d][1];

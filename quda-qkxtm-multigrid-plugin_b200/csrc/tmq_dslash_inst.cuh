@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "tmq_site.cuh"
+#include "tmq_pack.cuh"
 #include "tmq_reduce.cuh"
 
 namespace tmq {
@@ -97,6 +98,24 @@ dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
     // costs ~8% because its conditional loads cannot be hoisted); only boundary CTAs pay for it
     if (MULTI && boundary) red[0] = dslash_site<F, RECON, EPI, true, CLOVER>(A, *en, e, alpha);
     else                   red[0] = dslash_site<F, RECON, EPI, false, CLOVER>(A, *en, e, alpha);
+  }
+  if constexpr (MULTI && EPI != EPI_CG4) {
+    // fused halo exchange: pack this launch's output faces for the next application into the neighbours' arenas (block-uniform branch)
+    if (boundary && A.pk_on) {
+      if (e < (uint32_t)en->nsites && ghosts_ok) pack_out<F, RECON>(A, *en, e);
+      __threadfence_system();            // this thread's peer stores are ordered before the ticket
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int nb = (unsigned int)(A.nblk[1] + A.nblk[2]);
+        const unsigned int t = atomicInc(A.pk.ticket, nb - 1);
+        if (t == nb - 1) {
+          __threadfence_system();
+          for (int s = 0; s < A.pk.nslot; s++)
+            for (int d = 0; d < 2; d++)
+              asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.pk.flag[s][d]), "r"(A.pk.seq) : "memory");
+        }
+      }
+    }
   }
   if (EpiTraits<EPI>::RED != 0) block_reduce_finalize<1>(red, A.partials, A.ticket, A.scal, A.red_slot, A.red_accum != 0);
 }

@@ -11,62 +11,9 @@
 // plug-in's own host-staged ghost exchange (lib/qudaQKXTM_Vector.cpp:172-382).
 #include "tmq_internal.h"
 #include "tmq_site.cuh"
+#include "tmq_pack.cuh"
 
 namespace tmq {
-
-template <typename F> __device__ __forceinline__ void store_half(VecT<F> *base, int f, int fstride, const Half<F> &h) {
-#pragma unroll
-  for (int j = 0; j < 3; j++) {
-    const int k0 = 2 * j, k1 = 2 * j + 1;
-    VecT<F> v;
-    v.a = h.h[k0 / 3][k0 % 3][0]; v.b = h.h[k0 / 3][k0 % 3][1];
-    v.c = h.h[k1 / 3][k1 % 3][0]; v.d = h.h[k1 / 3][k1 % 3][1];
-    base[(size_t)j * fstride + f] = v;
-  }
-}
-
-template <typename F, int MU> __device__ __forceinline__ void project_any(Half<F> &h, const Spinor<F> &p, F sg) {
-  if constexpr (MU < 3) project<F, MU>(h, p, sg);
-  else {
-    const int o = sg > (F)0 ? 2 : 0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      h.h[0][c][0] = 2 * (o ? p.v[2][c][0] : p.v[0][c][0]); h.h[0][c][1] = 2 * (o ? p.v[2][c][1] : p.v[0][c][1]);
-      h.h[1][c][0] = 2 * (o ? p.v[3][c][0] : p.v[1][c][0]); h.h[1][c][1] = 2 * (o ? p.v[3][c][1] : p.v[1][c][1]);
-    }
-  }
-}
-
-// one face site: project (and for the forward-going face multiply by U^dag) and store into `dst`
-template <typename F, int RECON, int MU>
-__device__ __forceinline__ void pack_site(const DslashArgs<F> &A, int f, bool fwd, VecT<F> *dst) {
-  const Geom &g = A.g;
-  const int face = g.face[MU];
-  const int q = 1 - A.parity;
-  const int slice = fwd ? g.X[MU] - 1 : 0;
-  int idx;
-  if (MU == 3) idx = slice * face + f;
-  else {   // MU == 2: f = (t*Y + y)*Xh + xh
-    const int plane = g.X[1] * g.Xh;
-    const int t = f / plane, rem = f - t * plane;
-    idx = (t * g.X[2] + slice) * plane + rem;
-  }
-  Spinor<F> p;
-  load_spinor(p, A.in, idx, g.Vh);
-  Half<F> h;
-  if (!fwd) {
-    project_any<F, MU>(h, p, A.dsign);          // receiver's forward hop: 1 - s g
-    store_half(dst, f, face, h);
-  } else {
-    project_any<F, MU>(h, p, -A.dsign);         // receiver's backward hop: 1 + s g
-    Link<F> L;
-    const F s12 = (MU == 3 && g.tb_last) ? (F)g.tb_sign : (F)1;
-    load_link<F, RECON>(L, A.gauge, q, MU, idx, g.Vh, s12);
-    Half<F> u;
-    su3_apply<F, true>(u, L, h);
-    store_half(dst, f, face, u);
-  }
-}
 
 // NCCL path: pack into local send buffers.  blockIdx.y = 0: backward-going face (slice 0), 1: forward-going (L-1)
 template <typename F, int RECON, int MU>

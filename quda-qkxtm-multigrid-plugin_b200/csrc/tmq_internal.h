@@ -114,6 +114,10 @@ struct tmq_ctx {
   unsigned int red_seq;
   std::vector<void *> ipc_opened;
   unsigned int halo_seq;
+  // fused halo mode: application `prepacked_seq` has had its faces sent by the launch that produced its input field
+  unsigned int prepacked_seq = 0;
+  const void *prepacked_in = nullptr;
+  int prepacked_dagger = 0, prepacked_parity = 0, prepacked_prec = 0;
   unsigned int *ticket2;     // pack-kernel ticket
   unsigned int *seq_table;   // device table seq_table[i] = i: source of the copy-engine flag writes
   // grow-only device work space of the meson contraction (site values + the stages of the separable Fourier sum)
@@ -167,6 +171,9 @@ struct HopSpec {
   double d1 = 0, d2 = 0, d3 = 0;    // EPI_CHEB
   int red_slot = SC_T3;
   int alpha_num = SC_ONE, alpha_den = SC_ONE;
+  // fused halo mode: this application's output is the input of the NEXT application (with dagger next_dagger): its boundary CTAs pack
+  // and send the faces themselves.  Only set inside chains of applications that this library issues back to back.
+  int pack_next = 0, next_dagger = 0;
 };
 inline double tw_a(const tmq_ctx *c) { return 2.0 * c->kappa * c->mu; }
 inline Tw tw_A(const tmq_ctx *c, int dag) { return {1.0, dag ? -tw_a(c) : tw_a(c), 0, dag}; }

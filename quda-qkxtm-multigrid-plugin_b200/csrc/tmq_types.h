@@ -172,6 +172,11 @@ template <typename F> struct DslashArgs {
                            // plain x term instead of re-applying A^dag = C - i a g5 to w (192 B/site instead of 1152)
   int cl_plain_x;          // clover: the x term is used as it is (no site matrix) although the epilogue has TWX
   int prefetch;            // unused (the L2-prefetch experiment was removed: no gain, and it cost the 4th resident CTA)
+  // fused compute + halo exchange (TMQ_OPT_HALO_P2P = 3): the boundary CTAs of THIS launch pack the faces of its output for the NEXT
+  // application and store them into the neighbours' ghost arenas; the last boundary CTA publishes pk.seq in the neighbours' flags
+  int pk_on;
+  F pk_dsign;              // projector sign of the next application (+1: D, -1: D^dagger)
+  PackDst<F> pk;
 };
 
 }  // namespace tmq

@@ -211,7 +211,7 @@ def test_mixed_precision_cg_reaches_fp64_residual(tmq, recon):
 @pytest.mark.parametrize("part", [(0, 0, 0, 1), (0, 0, 1, 0), (0, 0, 1, 1)])
 @pytest.mark.parametrize("recon", [12, 18])
 @pytest.mark.parametrize("prec", [8, 4])
-@pytest.mark.parametrize("p2p", [2, 1, 0])
+@pytest.mark.parametrize("p2p", [3, 2, 1, 0])
 def test_ghost_zone_path_equals_periodic_path(tmq, part, recon, prec, p2p):
     """--partition style self-exchange (qkxtm/QKXTM_util.cpp:1717-1720): pack -> exchange -> interior +
     boundary launches must reproduce the single-launch result and the oracle."""
@@ -236,11 +236,26 @@ def test_ghost_zone_path_equals_periodic_path(tmq, part, recon, prec, p2p):
     a.set(s.even)
     c.mdagm(b, a)
     assert lu.rel_l2(b.get(), o.mdagm(s.gauge, s.even, KAPPA, MU, 0)) < 2 * TOL[prec]
+    # p2p = 3: fused compute + halo exchange -- inside M_pc / M^dag M / the CG iteration the boundary CTAs of the launch that produces
+    # a field send its faces for the next application themselves (both matpc directions and daggers, the asymmetric operator too)
+    for dagger in (0, 1):
+        c.matpc(b, a, dagger)
+        assert lu.rel_l2(b.get(), o.matpc(s.gauge, s.even, KAPPA, MU, 0, dagger)) < 2 * TOL[prec]
+    c.set_op(KAPPA, MU, tmq.MATPC_ODD_ODD_ASYM)
+    a.set(s.odd)
+    for dagger in (0, 1):
+        c.matpc(b, a, dagger)
+        assert lu.rel_l2(b.get(), o.matpc(s.gauge, s.odd, KAPPA, MU, 3, dagger)) < 2 * TOL[prec]
+    c.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
+    a.set(s.even)
     if prec == 8:
         x_ref, it_ref, _, _ = o.cg_mdagm(s.gauge, s.even, KAPPA, MU, 0, tol=1e-9, maxiter=5000)
         x = c.spinor()
         info = c.cg_mdagm(x, a, tol=1e-9, maxiter=5000)
         assert abs(info["iter"] - it_ref) <= 2 and info["true_res"] <= 1.05e-9
+        assert lu.rel_l2(x.get(), x_ref) < 1e-8
+        infom = c.cg_mdagm(x, a, tol=1e-9, maxiter=5000, sloppy_prec=4, reliable_delta=1e-4)
+        assert abs(infom["iter"] - it_ref) <= 2 and infom["true_res"] <= 1.05e-9
     c.close()
 
 

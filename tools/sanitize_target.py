@@ -1,6 +1,6 @@
 """Target of tools/sanitize.sh (compute-sanitizer): the hot path on 8^3 x 16 -- hop, M^dag M, fp64 and mixed CG, Chebyshev filter,
 blas reductions, prepare / reconstruct -- plainly and with the ghost-zone path forced on one GPU in each halo mode
-(tmq_force_partition; mode 2 copy-engine peer copies + flag waits, mode 1 peer stores + ticket, mode 0 NCCL-style staging)."""
+(tmq_force_partition; mode 3 fused compute + peer stores, mode 2 copy-engine peer copies + flag waits, mode 1 peer stores + ticket, mode 0 NCCL-style staging)."""
 import os
 import sys
 
