@@ -157,6 +157,8 @@ protected:
   int field_length;
   long long total_length;                          // 64-bit: the reference's int overflows at 64^3x128
   size_t bytes_total_length;
+  long long ghost_length;                          // ghost sites behind the local volume (0 on an unpartitioned lattice)
+  size_t bytes_ghost_length, bytes_total_plus_ghost_length;
   Float *h_elem, *h_elem_backup, *d_elem;
   bool isAllocHost, isAllocDevice, isAllocHostBackup;
   void create_host();
@@ -165,6 +167,7 @@ protected:
   void destroy_host_backup();
   void create_device();
   void destroy_device();
+  void exchange_ghost_device();                    // the device-side body of the ghost trio of the derived containers
 public:
   QKXTM_Field(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT);
   virtual ~QKXTM_Field();
@@ -174,8 +177,8 @@ public:
   Float *H_elem() const { return h_elem; }
   Float *D_elem() const { return d_elem; }
   size_t Bytes_total() const { return bytes_total_length; }
-  size_t Bytes_ghost() const { return 0; }         // the containers' own ghost exchange is not on this path
-  size_t Bytes_total_plus_ghost() const { return bytes_total_length; }
+  size_t Bytes_ghost() const { return bytes_ghost_length; }
+  size_t Bytes_total_plus_ghost() const { return bytes_total_plus_ghost_length; }
   int Precision() const { return (int)sizeof(Float); }
   void printInfo();
 };
@@ -187,8 +190,13 @@ public:
   void packGaugeToBackup(void **gauge);
   void loadGaugeFromBackup();
   void justDownloadGauge();
+  // include/qudaQKXTM.h:177-179: after the three calls the ghost region of the DEVICE array ([ncomp][V] followed by the plus / minus ghost of
+  // every partitioned dimension) holds the neighbours' boundary slices.  The exchange runs on the device inside cpuExchangeGhost.
+  void ghostToHost();
+  void cpuExchangeGhost();
+  void ghostToDevice();
   void loadGauge();
-  double calculatePlaq();                          // prints like the reference and also returns the value (skipped, 0, on a split lattice)
+  double calculatePlaq();                          // prints like the reference and also returns the value (all-reduced over the ranks)
 };
 
 template <typename Float> class QKXTM_Vector : public QKXTM_Field<Float> {      // include/qudaQKXTM.h:189-225
@@ -212,6 +220,9 @@ public:
   void castFloatToDouble(QKXTM_Vector<float> &vecIn);
   double norm2Host();
   void apply_gamma5();
+  void ghostToHost();                              // include/qudaQKXTM.h:199-201 (see QKXTM_Gauge)
+  void cpuExchangeGhost();
+  void ghostToDevice();
 };
 
 template <typename Float> class QKXTM_Propagator : public QKXTM_Field<Float> {  // include/qudaQKXTM.h:244-265
@@ -223,6 +234,9 @@ public:
   void rotateToPhysicalBase_device(int sign);      // lib/qudaQKXTM_Propagator.cpp:108-112: sign = +1 (up) / -1 (down)
   void conjugate();                                // lib/code_pieces/conjugate_propagator_core.h
   void apply_gamma5();                             // lib/code_pieces/apply_gamma5_propagator_core.h
+  void ghostToHost();                              // include/qudaQKXTM.h:244-246 (see QKXTM_Gauge)
+  void cpuExchangeGhost();
+  void ghostToDevice();
 };
 
 template <typename Float> class QKXTM_Propagator3D : public QKXTM_Field<Float> {   // include/qudaQKXTM.h:267-277

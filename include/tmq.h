@@ -202,8 +202,17 @@ int tmq_project(tmq_spinor *out, const tmq_spinor *in, tmq_eigset *set, int nvec
 
 /* ---- QKXTM container kernels on the QKXTM device layout (lib/qudaQKXTM_kernels.cu:1110-1124,1353-1365,
  *      lib/code_pieces/apply_gamma5_vector_core.h, lib/qudaQKXTM_Propagator.cpp:90-106) ------------------- */
+/* The containers' ghost zones (lib/qudaQKXTM_Field.cpp:116-125, lib/qudaQKXTM_kernels.cu:160-170): a container's device array is
+ * [ncomp][V] complex followed, for every partitioned dimension in ascending order, by the "plus" ghost (the forward neighbour's slice 0)
+ * and the "minus" ghost (the backward neighbour's slice L-1), each [ncomp][surface]; tmq_qkxtm_ghost_sites = the number of ghost sites.
+ * tmq_qkxtm_exchange_ghost replaces ghostToHost -> cpuExchangeGhost -> ghostToDevice (lib/qudaQKXTM_Gauge.cpp:143-373,
+ * lib/qudaQKXTM_Vector.cpp:172-382) by one device-side exchange per partitioned dimension (nothing is staged through the host);
+ * ncomp = 36 (gauge), 12 (vector), 144 (propagator).                                                                              */
+size_t tmq_qkxtm_ghost_sites(tmq_ctx *);
+int tmq_qkxtm_exchange_ghost(tmq_ctx *, void *d_elem, int prec, int ncomp);
 /* plaquette of a gauge field in the QKXTM device layout d[((dir*3+c1)*3+c2)*V + x_lex] (lib/qudaQKXTM_Gauge.cpp:73-89):
- * QKXTM_Gauge::calculatePlaq (lib/qudaQKXTM_Gauge.cpp:376-386).  Single rank.                                  */
+ * QKXTM_Gauge::calculatePlaq (lib/qudaQKXTM_Gauge.cpp:376-386).  On a partitioned lattice the array must include its ghost region,
+ * which is exchanged here first, and the sum is all-reduced over the ranks.                                      */
 int tmq_qkxtm_plaquette(tmq_ctx *, const void *d_gauge_qkxtm, int prec, double *plaq);
 int tmq_qkxtm_scale(tmq_ctx *, void *d_qkxtm, int prec, double a);
 int tmq_qkxtm_cast(tmq_ctx *, void *d_dst, int dst_prec, const void *d_src, int src_prec);

@@ -380,8 +380,20 @@ int reduce_finish(tmq_ctx *c, int slot, int n) {
   if (c->multi && c->nranks > 1) TMQ_TRY(comm_allreduce(c, c->scal + slot, n, c->stream));
   return 0;
 }
+// Scalars travel to the host through MAPPED pinned memory, written by a one-warp kernel, not through a copy engine: a cudaMemcpy of 8
+// bytes would queue behind whatever bulk download is in flight on the same DMA engine (the 2 GB solution of the previous column of a
+// propagator: +40 ms on the first read-back of every solve, measured in profiles/r2_e2e_probe.md).
+__global__ void scal_to_host_kernel(double *h, const double *d, int n) {
+  if ((int)threadIdx.x < n) h[threadIdx.x] = d[threadIdx.x];
+  __threadfence_system();
+}
+int scal_to_host(tmq_ctx *c, int slot, int n) {
+  scal_to_host_kernel<<<1, 32, 0, c->stream>>>(c->h_scal_dev + slot, c->scal + slot, n);
+  TMQ_CUDA(cudaGetLastError());
+  return 0;
+}
 int fetch_scal(tmq_ctx *c, int slot, int n, double *out) {
-  TMQ_CUDA(cudaMemcpyAsync(c->h_scal + slot, c->scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TMQ_TRY(scal_to_host(c, slot, n));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; i++) out[i] = c->h_scal[slot + i];
   return 0;
@@ -566,7 +578,8 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   ok = ok && cudaMalloc(&c->ticket2, sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->seq_table, SEQ_TABLE * sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->scal, SC_COUNT * sizeof(double)) == cudaSuccess;
-  ok = ok && cudaMallocHost(&c->h_scal, SC_COUNT * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void **)&c->h_scal, SC_COUNT * sizeof(double), cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostGetDevicePointer((void **)&c->h_scal_dev, c->h_scal, 0) == cudaSuccess;
   if (ok) {
     double init[SC_COUNT];
     for (int i = 0; i < SC_COUNT; i++) init[i] = 0.0;
@@ -1132,7 +1145,7 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
       TMQ_TRY(reduce_finish(c, sn, 1));
     }
     // |r|^2 travels to the host while the update kernel runs
-    TMQ_CUDA(cudaMemcpyAsync(c->h_scal + sn, c->scal + sn, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    TMQ_TRY(scal_to_host(c, sn, 1));
     TMQ_CUDA(cudaEventRecord(c->ev_r2, c->stream));
     TMQ_CUDA(blas_cg_update(prec, x->d, p, r, n, c->scal, so, SC_PAP, sn, so, c->stream)); c->launches++;
     TMQ_CUDA(cudaEventSynchronize(c->ev_r2));
@@ -1376,12 +1389,45 @@ int tmq_gamma5(tmq_spinor *x) {
 }
 
 // ---- QKXTM container kernels ------------------------------------------------------------------------------------------
+size_t tmq_qkxtm_ghost_sites(tmq_ctx *c) {
+  if (!c) return 0;
+  const QkGhost gh = qk_ghost_layout(c->g);
+  return gh.total_sites - (size_t)2 * c->g.Vh;
+}
+// the containers' ghost exchange: replaces ghostToHost -> cpuExchangeGhost -> ghostToDevice (lib/qudaQKXTM_Gauge.cpp:143-373,
+// lib/qudaQKXTM_Vector.cpp:172-382, lib/qudaQKXTM_Propagator.cpp) by ONE device-side exchange per partitioned dimension: the two boundary
+// slices are gathered on the device and sent to the neighbours (ncclSend / ncclRecv over NVLink), which receive them straight into the
+// ghost region behind their local volume.  Nothing is staged through the host.
+int tmq_qkxtm_exchange_ghost(tmq_ctx *c, void *d_elem, int prec, int ncomp) {
+  TMQ_REQUIRE(c && d_elem, "null argument");
+  TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
+  TMQ_REQUIRE(ncomp > 0, "bad number of components");
+  const QkGhost gh = qk_ghost_layout(c->g);
+  const size_t cb = (size_t)2 * prec;            // bytes per complex
+  for (int d = 2; d < 4; d++) {
+    if (!c->g.part[d]) continue;
+    const size_t nbytes = gh.surf[d] * ncomp * cb;
+    char *lo = nullptr;
+    TMQ_CUDA(cudaMalloc((void **)&lo, 2 * nbytes));
+    char *hi = lo + nbytes;
+    TMQ_CUDA(qkxtm_face_gather(lo, hi, d_elem, prec, c->g, d, ncomp, c->stream)); c->launches++;
+    // my slice 0 -> rank-1 (its plus ghost), my slice L-1 -> rank+1 (its minus ghost)
+    int rc = comm_sendrecv_dim(c, d, lo, hi, (char *)d_elem + gh.plus[d] * ncomp * cb, (char *)d_elem + gh.minus[d] * ncomp * cb, nbytes, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(lo);
+    if (rc) return rc;
+  }
+  return 0;
+}
+// sum Re tr P / (V_global * 3 * 6) of a gauge container.  On a partitioned lattice d_gauge must own its ghost region
+// ((V + tmq_qkxtm_ghost_sites) * 36 complex): it is exchanged here, as QKXTM_Gauge::calculatePlaq does before its kernel.
 int tmq_qkxtm_plaquette(tmq_ctx *c, const void *d_gauge, int prec, double *plaq) {
   TMQ_REQUIRE(c && d_gauge && plaq, "null argument");
   TMQ_REQUIRE(prec == 8 || prec == 4, "bad precision");
-  TMQ_REQUIRE(c->nranks == 1, "tmq_qkxtm_plaquette is a single-rank sanity check");
   TMQ_REQUIRE((size_t)(c->g.Vh / 64 + 1) * 1 <= c->partials_len, "partials too small");
+  if (c->multi) TMQ_TRY(tmq_qkxtm_exchange_ghost(c, (void *)d_gauge, prec, 36));
   TMQ_CUDA(qkxtm_plaquette(d_gauge, prec, c->g, red_at(c, SC_T0), c->stream)); c->launches++;
+  TMQ_TRY(reduce_finish(c, SC_T0, 1));
   double s;
   TMQ_TRY(fetch_scal(c, SC_T0, 1, &s));
   *plaq = s / ((double)c->Vglobal * 3.0 * 6.0);

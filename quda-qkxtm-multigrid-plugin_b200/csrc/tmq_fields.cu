@@ -249,10 +249,51 @@ cudaError_t plaquette_launch(int recon, const void *gauge_d, const Geom &g, cons
   return cudaGetLastError();
 }
 
-// ---- plaquette on the QKXTM gauge layout d[((dir*3+c1)*3+c2)*V + x_lex] (lib/qudaQKXTM_Gauge.cpp:73-89):
-//      QKXTM_Gauge::calculatePlaq (lib/qudaQKXTM_Gauge.cpp:376-386, lib/code_pieces/plaquette_core.h).  Single rank.
+// ---- the containers' ghost zones (lib/qudaQKXTM_Field.cpp:116-125, lib/qudaQKXTM_kernels.cu:160-170) --------------------------------
+// A container's device array is [ncomp][V] complex followed, for every partitioned dimension d in ascending order, by the "plus" ghost
+// (the forward neighbour's slice 0) and the "minus" ghost (the backward neighbour's slice L-1), each [ncomp][surface3D[d]]; the face
+// site index is the lexicographic index of the three other coordinates (LEXIC_ZYX for t, LEXIC_TYX for z, include/qudaQKXTM_utils.h:25-29).
+QkGhost qk_ghost_layout(const Geom &g) {
+  QkGhost G;
+  const size_t V = (size_t)2 * g.Vh;
+  size_t last = V;
+  for (int d = 0; d < 4; d++) {
+    G.surf[d] = g.part[d] ? V / g.X[d] : 0;
+    G.plus[d] = G.minus[d] = 0;
+    if (g.part[d]) { G.plus[d] = last; G.minus[d] = last + G.surf[d]; last += 2 * G.surf[d]; }
+  }
+  G.total_sites = last;
+  return G;
+}
+// gather the slices 0 (lo) and L-1 (hi) of dimension d, all components: out[comp][face]
 template <typename Q>
-__global__ void __launch_bounds__(128) qk_plaquette_kernel(const CplxT<Q> *__restrict__ gq, Geom g, BlasRed r) {
+__global__ void qk_face_gather_kernel(CplxT<Q> *lo, CplxT<Q> *hi, const CplxT<Q> *__restrict__ d, Geom g, int dim, int ncomp) {
+  const size_t V = (size_t)2 * g.Vh, surf = V / g.X[dim];
+  const size_t i = (size_t)blockIdx.x * FB + threadIdx.x;
+  if (i >= surf * ncomp) return;
+  const size_t comp = i / surf, f = i - comp * surf;
+  size_t x0, x1;
+  if (dim == 3) { x0 = f; x1 = (size_t)(g.X[3] - 1) * surf + f; }
+  else {   // dim == 2: f = t * (X Y) + (y X + x)
+    const size_t plane = (size_t)g.X[0] * g.X[1], t = f / plane, rem = f - t * plane;
+    x0 = (t * g.X[2]) * plane + rem; x1 = (t * g.X[2] + g.X[2] - 1) * plane + rem;
+  }
+  lo[i] = d[comp * V + x0];
+  hi[i] = d[comp * V + x1];
+}
+cudaError_t qkxtm_face_gather(void *lo, void *hi, const void *d, int prec, const Geom &g, int dim, int ncomp, cudaStream_t st) {
+  const size_t n = ((size_t)2 * g.Vh / g.X[dim]) * ncomp;
+  const int grid = (int)((n + FB - 1) / FB);
+  if (prec == 8) qk_face_gather_kernel<double><<<grid, FB, 0, st>>>((CplxT<double> *)lo, (CplxT<double> *)hi, (const CplxT<double> *)d, g, dim, ncomp);
+  else qk_face_gather_kernel<float><<<grid, FB, 0, st>>>((CplxT<float> *)lo, (CplxT<float> *)hi, (const CplxT<float> *)d, g, dim, ncomp);
+  return cudaGetLastError();
+}
+
+// ---- plaquette on the QKXTM gauge layout d[((dir*3+c1)*3+c2)*V + x_lex] (lib/qudaQKXTM_Gauge.cpp:73-89):
+//      QKXTM_Gauge::calculatePlaq (lib/qudaQKXTM_Gauge.cpp:376-386, lib/code_pieces/plaquette_core.h).  On a partitioned dimension the
+//      forward neighbour across the boundary is read from the container's "plus" ghost zone (plaquette_core.h:30-50).
+template <typename Q>
+__global__ void __launch_bounds__(128) qk_plaquette_kernel(const CplxT<Q> *__restrict__ gq, Geom g, QkGhost gh, BlasRed r) {
   const size_t V = (size_t)2 * g.Vh;
   const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
   double red[1] = {0.0};
@@ -265,12 +306,25 @@ __global__ void __launch_bounds__(128) qk_plaquette_kernel(const CplxT<Q> *__res
 #pragma unroll
       for (int k = 0; k < 9; k++) { CplxT<Q> z = gq[((size_t)mu * 9 + k) * V + x]; u[k / 3][k % 3][0] = (double)z.re; u[k / 3][k % 3][1] = (double)z.im; }
     };
+    // link mu at the site one step forward in direction d from c (ghost zone if that crosses a partitioned boundary)
+    auto ld_fwd = [&](double (&u)[3][3][2], int mu, int d) {
+      if (g.part[d] && c[d] == g.X[d] - 1) {
+        size_t f;
+        if (d == 3) f = (size_t)c[0] + (size_t)g.X[0] * (c[1] + (size_t)g.X[1] * c[2]);
+        else f = (size_t)c[0] + (size_t)g.X[0] * (c[1] + (size_t)g.X[1] * c[3]);      // d == 2 (only z and t are ever partitioned)
+        const size_t base = gh.plus[d] * 36 + (size_t)mu * 9 * gh.surf[d] + f;
+#pragma unroll
+        for (int k = 0; k < 9; k++) { CplxT<Q> z = gq[base + (size_t)k * gh.surf[d]]; u[k / 3][k % 3][0] = (double)z.re; u[k / 3][k % 3][1] = (double)z.im; }
+      } else {
+        int xn[4] = {c[0], c[1], c[2], c[3]};
+        xn[d] = (xn[d] + 1) % g.X[d];
+        ld(u, mu, lex(xn));
+      }
+    };
     for (int mu = 0; mu < 4; mu++)
       for (int nu = mu + 1; nu < 4; nu++) {
-        int xm[4] = {c[0], c[1], c[2], c[3]}, xn[4] = {c[0], c[1], c[2], c[3]};
-        xm[mu] = (xm[mu] + 1) % g.X[mu]; xn[nu] = (xn[nu] + 1) % g.X[nu];
         double A[3][3][2], B[3][3][2], C[3][3][2], D[3][3][2], ab[3][3][2], cd[3][3][2];
-        ld(A, mu, i); ld(B, nu, lex(xm)); ld(C, nu, i); ld(D, mu, lex(xn));
+        ld(A, mu, i); ld_fwd(B, nu, mu); ld(C, nu, i); ld_fwd(D, mu, nu);
         mm(ab, A, B); mm(cd, C, D);
 #pragma unroll
         for (int a = 0; a < 3; a++)
@@ -282,8 +336,9 @@ __global__ void __launch_bounds__(128) qk_plaquette_kernel(const CplxT<Q> *__res
 }
 cudaError_t qkxtm_plaquette(const void *gq, int prec, const Geom &g, const BlasRed &r, cudaStream_t st) {
   const int grid = (2 * g.Vh + 127) / 128;
-  if (prec == 8) qk_plaquette_kernel<double><<<grid, 128, 0, st>>>((const CplxT<double> *)gq, g, r);
-  else qk_plaquette_kernel<float><<<grid, 128, 0, st>>>((const CplxT<float> *)gq, g, r);
+  const QkGhost gh = qk_ghost_layout(g);
+  if (prec == 8) qk_plaquette_kernel<double><<<grid, 128, 0, st>>>((const CplxT<double> *)gq, g, gh, r);
+  else qk_plaquette_kernel<float><<<grid, 128, 0, st>>>((const CplxT<float> *)gq, g, gh, r);
   return cudaGetLastError();
 }
 

@@ -76,7 +76,8 @@ struct tmq_ctx {
   size_t partials_len;
   unsigned int *ticket;      // device
   double *scal;              // device scalar block [SC_COUNT]
-  double *h_scal;            // pinned host mirror [SC_COUNT]
+  double *h_scal;            // pinned, mapped host mirror [SC_COUNT]
+  double *h_scal_dev;        // the same memory as the device sees it (written by scal_to_host_kernel)
   // halo buffers per precision: [dim][dir] send / recv, vec[3][face]
   void *halo_send[2][4][2];
   void *halo_recv[2][4][2];
@@ -191,6 +192,7 @@ int ensure_scratch(tmq_ctx *c, int prec, int n);
 inline void *scr(tmq_ctx *c, int prec, int i) { return (prec == 8 ? c->scr_d : c->scr_s).tmp[i]; }
 int reduce_finish(tmq_ctx *c, int slot, int n);
 int fetch_scal(tmq_ctx *c, int slot, int n, double *out);
+int scal_to_host(tmq_ctx *c, int slot, int n);
 int check_device_error(tmq_ctx *c);
 int op_matpc(tmq_ctx *c, int prec, void *out, const void *in, int dagger);
 int op_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int pap_slot);
@@ -241,6 +243,11 @@ cudaError_t spinor_from_host_lex(int prec, void *even, void *odd, const double *
 cudaError_t spinor_to_host_lex(double *d_aos, int prec, const void *even, const void *odd, double scale, const Geom &g, cudaStream_t st);
 cudaError_t plaquette_launch(int recon, const void *gauge_d, const Geom &g, const BlasRed &r, cudaStream_t st);
 cudaError_t qkxtm_plaquette(const void *gq, int prec, const Geom &g, const BlasRed &r, cudaStream_t st);
+// ghost zones of the QKXTM containers: site offsets (in units of sites: multiply by the number of components) of the plus / minus ghost
+// of every partitioned dimension behind the local volume, and the face sizes
+struct QkGhost { size_t plus[4], minus[4], surf[4], total_sites; };
+QkGhost qk_ghost_layout(const Geom &g);
+cudaError_t qkxtm_face_gather(void *lo, void *hi, const void *d, int prec, const Geom &g, int dim, int ncomp, cudaStream_t st);
 cudaError_t qkxtm_scale(void *d, int prec, double a, size_t ncplx, cudaStream_t st);
 cudaError_t qkxtm_cast(void *dst, int dprec, const void *src, int sprec, size_t ncplx, cudaStream_t st);
 cudaError_t qkxtm_gamma5(void *d, int prec, int V, cudaStream_t st);

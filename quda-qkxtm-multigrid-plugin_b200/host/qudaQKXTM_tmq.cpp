@@ -604,6 +604,10 @@ QKXTM_Field<Float>::QKXTM_Field(ALLOCATION_FLAG alloc_flag, CLASS_ENUM classT)
     case VECTOR3D: field_length = 4 * 3; total_length = G.localVolume / G.localL[3]; break;
   }
   bytes_total_length = (size_t)total_length * field_length * 2 * sizeof(Float);
+  // ghost zones behind the local volume, one pair per partitioned dimension (lib/qudaQKXTM_Field.cpp:116-125); 4-d containers only
+  ghost_length = (classT == PROPAGATOR3D || classT == VECTOR3D) ? 0 : (long long)tmq_qkxtm_ghost_sites(G.ctx);
+  bytes_ghost_length = (size_t)ghost_length * field_length * 2 * sizeof(Float);
+  bytes_total_plus_ghost_length = bytes_total_length + bytes_ghost_length;
   if (alloc_flag == BOTH) { create_host(); create_device(); }
   else if (alloc_flag == HOST) create_host();
   else if (alloc_flag == DEVICE) create_device();
@@ -628,7 +632,7 @@ template <typename Float> void QKXTM_Field<Float>::create_host_backup() {
 }
 template <typename Float> void QKXTM_Field<Float>::create_device() {
   void *p = nullptr;
-  TMQ_OK(tmq_dev_malloc(G.ctx, &p, bytes_total_length));
+  TMQ_OK(tmq_dev_malloc(G.ctx, &p, bytes_total_plus_ghost_length));
   d_elem = (Float *)p;
   isAllocDevice = true;
   zero_device();
@@ -641,7 +645,17 @@ template <typename Float> void QKXTM_Field<Float>::destroy_device() {
 }
 template <typename Float> void QKXTM_Field<Float>::zero_host() { memset(h_elem, 0, bytes_total_length); }
 template <typename Float> void QKXTM_Field<Float>::zero_host_backup() { memset(h_elem_backup, 0, bytes_total_length); }
-template <typename Float> void QKXTM_Field<Float>::zero_device() { TMQ_OK(tmq_dev_memset(G.ctx, d_elem, 0, bytes_total_length)); }
+template <typename Float> void QKXTM_Field<Float>::zero_device() { TMQ_OK(tmq_dev_memset(G.ctx, d_elem, 0, bytes_total_plus_ghost_length)); }
+// The ghost trio (include/qudaQKXTM.h:177-179,199-201,244-246; lib/qudaQKXTM_Gauge.cpp:143-373, lib/qudaQKXTM_Vector.cpp:172-382).  The reference
+// gathers the boundary slices with cudaMemcpy2D into the host array, exchanges them over MPI and copies the received faces back; the
+// contract is "after the three calls the ghost region behind the local volume holds the neighbours' slices".  Here the middle call does
+// all of it on the device (tmq_qkxtm_exchange_ghost: gather kernel + ncclSend/Recv straight into the ghost region); the outer two have
+// nothing left to do.
+template <typename Float> void QKXTM_Field<Float>::exchange_ghost_device() {
+  if (!isAllocDevice) errorQuda("the ghost exchange needs the device copy of the container");
+  if (ghost_length == 0) return;
+  TMQ_OK(tmq_qkxtm_exchange_ghost(G.ctx, d_elem, (int)sizeof(Float), field_length));
+}
 template <typename Float> void QKXTM_Field<Float>::printInfo() {
   printfQuda("GPU memory needed is %f MB \n", bytes_total_length / (1024.0 * 1024.0));
 }
@@ -664,6 +678,9 @@ template <typename Float> void QKXTM_Gauge<Float>::packGaugeToBackup(void **gaug
   if (this->h_elem_backup == NULL) errorQuda("Error you can call this method only if you allocate memory for h_elem_backup");
   pack_gauge_into(this->h_elem_backup, gauge, this->total_length);
 }
+template <typename Float> void QKXTM_Gauge<Float>::ghostToHost() {}
+template <typename Float> void QKXTM_Gauge<Float>::cpuExchangeGhost() { this->exchange_ghost_device(); }
+template <typename Float> void QKXTM_Gauge<Float>::ghostToDevice() {}
 template <typename Float> void QKXTM_Gauge<Float>::loadGauge() { TMQ_OK(tmq_h2d(G.ctx, this->d_elem, this->h_elem, this->bytes_total_length)); }
 template <typename Float> void QKXTM_Gauge<Float>::loadGaugeFromBackup() {
   if (this->h_elem_backup == NULL) errorQuda("Error you can call this method only if you allocate memory for h_elem_backup");
@@ -672,13 +689,10 @@ template <typename Float> void QKXTM_Gauge<Float>::loadGaugeFromBackup() {
 template <typename Float> void QKXTM_Gauge<Float>::justDownloadGauge() { TMQ_OK(tmq_d2h(G.ctx, this->h_elem, this->d_elem, this->bytes_total_length)); }
 template <typename Float> double QKXTM_Gauge<Float>::calculatePlaq() {
   double plaq = 0;
-  if (G.nranks > 1) {
-    // the container keeps no ghost links (the reference stages them through the host, lib/qudaQKXTM_Gauge.cpp:143-373); the plaquette is
-    // a printed sanity check only, so a split lattice skips it instead of aborting the run
-    printfQuda("Calculated plaquette: skipped on a split lattice\n");
-    return 0.0;
-  }
-  TMQ_OK(tmq_qkxtm_plaquette(G.ctx, this->d_elem, (int)sizeof(Float), &plaq));
+  ghostToHost();                      // lib/qudaQKXTM_Gauge.cpp:379-381
+  cpuExchangeGhost();
+  ghostToDevice();
+  TMQ_OK(tmq_qkxtm_plaquette(G.ctx, this->d_elem, (int)sizeof(Float), &plaq));     // all-reduced over the ranks
   if (sizeof(Float) == 4) printfQuda("Calculated plaquette in single precision is %f\n", plaq);
   else printfQuda("Calculated plaquette in double precision is %lf\n", plaq);
   return plaq;
@@ -710,6 +724,9 @@ template <typename Float> void QKXTM_Vector<Float>::unpackVector() {
   unpackVector(tmp);
   free(tmp);
 }
+template <typename Float> void QKXTM_Vector<Float>::ghostToHost() {}
+template <typename Float> void QKXTM_Vector<Float>::cpuExchangeGhost() { this->exchange_ghost_device(); }
+template <typename Float> void QKXTM_Vector<Float>::ghostToDevice() {}
 template <typename Float> void QKXTM_Vector<Float>::loadVector() { TMQ_OK(tmq_h2d(G.ctx, this->d_elem, this->h_elem, this->bytes_total_length)); }
 template <typename Float> void QKXTM_Vector<Float>::unloadVector() { TMQ_OK(tmq_d2h(G.ctx, this->h_elem, this->d_elem, this->bytes_total_length)); }
 template <typename Float> void QKXTM_Vector<Float>::download() { unloadVector(); unpackVector(); }
@@ -772,6 +789,9 @@ template <typename Float> void QKXTM_Vector<Float>::copyPropagator3D(QKXTM_Propa
 
 // ---- QKXTM_Propagator ------------------------------------------------------------------------------------------------------------
 template <typename Float> QKXTM_Propagator<Float>::QKXTM_Propagator(ALLOCATION_FLAG a, CLASS_ENUM c) : QKXTM_Field<Float>(a, c) {}
+template <typename Float> void QKXTM_Propagator<Float>::ghostToHost() {}
+template <typename Float> void QKXTM_Propagator<Float>::cpuExchangeGhost() { this->exchange_ghost_device(); }
+template <typename Float> void QKXTM_Propagator<Float>::ghostToDevice() {}
 template <typename Float> void QKXTM_Propagator<Float>::absorbVectorToDevice(QKXTM_Vector<Float> &vec, int nu, int c2) {
   TMQ_OK(tmq_qkxtm_absorb(G.ctx, this->d_elem, vec.D_elem(), (int)sizeof(Float), nu, c2));
 }

@@ -31,7 +31,7 @@ tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm t
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
 tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free
-tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d tmq_barrier tmq_host_prefetch tmq_spinor_from_prefetch tmq_spinor_to_host_async tmq_host_wait tmq_host_alloc_pinned tmq_host_free_pinned tmq_host_register tmq_host_unregister tmq_cg_stats""".split()
+tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d tmq_barrier tmq_host_prefetch tmq_spinor_from_prefetch tmq_spinor_to_host_async tmq_host_wait tmq_host_alloc_pinned tmq_host_free_pinned tmq_host_register tmq_host_unregister tmq_cg_stats tmq_qkxtm_ghost_sites tmq_qkxtm_exchange_ghost""".split()
 
 
 class TmqError(RuntimeError):
@@ -91,6 +91,8 @@ def load():
     L.tmq_axpy_zpbx.argtypes = [C.c_double, vp, vp, vp, C.c_double]
     L.tmq_gamma5.argtypes = [vp]
     L.tmq_qkxtm_plaquette.argtypes = [vp, vp, C.c_int, dp]
+    L.tmq_qkxtm_ghost_sites.argtypes = [vp]; L.tmq_qkxtm_ghost_sites.restype = C.c_size_t
+    L.tmq_qkxtm_exchange_ghost.argtypes = [vp, vp, C.c_int, C.c_int]
     L.tmq_qkxtm_scale.argtypes = [vp, vp, C.c_int, C.c_double]
     L.tmq_qkxtm_cast.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.tmq_qkxtm_gamma5.argtypes = [vp, vp, C.c_int]
@@ -351,6 +353,8 @@ class Context:
         _ck(self.L.tmq_spinor_to_qkxtm(dptr, qprec, src.h, parity, scale))
     def qkxtm_plaquette(self, dgauge, prec):
         o = C.c_double(0); _ck(self.L.tmq_qkxtm_plaquette(self.h, dgauge, prec, C.byref(o))); return o.value
+    def qkxtm_ghost_sites(self): return int(self.L.tmq_qkxtm_ghost_sites(self.h))
+    def qkxtm_exchange_ghost(self, dptr, prec, ncomp): _ck(self.L.tmq_qkxtm_exchange_ghost(self.h, dptr, prec, ncomp))
     def qkxtm_scale(self, dptr, prec, a): _ck(self.L.tmq_qkxtm_scale(self.h, dptr, prec, a))
     def qkxtm_cast(self, dst, dprec, src, sprec): _ck(self.L.tmq_qkxtm_cast(self.h, dst, dprec, src, sprec))
     def qkxtm_gamma5(self, dptr, prec): _ck(self.L.tmq_qkxtm_gamma5(self.h, dptr, prec))

@@ -167,3 +167,50 @@ def test_gauss_smear_on_a_z_partitioned_lattice_is_bit_identical(tmq, prec):
         assert np.array_equal(ghost, plain), part
         assert np.array_equal(smear(d1, vec, gq, prec, 0, alpha), vec.astype(ghost.dtype))
         d1.close()
+
+
+@pytest.mark.parametrize("part", [(0, 0, 0, 1), (0, 0, 1, 0), (0, 0, 1, 1)])
+@pytest.mark.parametrize("ncomp,prec", [(36, 8), (12, 4), (144, 8)])
+def test_container_ghost_exchange_layout_and_plaquette(tmq, part, ncomp, prec):
+    """the containers' ghost trio (ghostToHost / cpuExchangeGhost / ghostToDevice, lib/qudaQKXTM_Gauge.cpp:143-373) as ONE device-side
+    exchange: behind the [ncomp][V] array, per partitioned dimension in ascending order, the plus ghost = the forward neighbour's slice 0
+    and the minus ghost = the backward neighbour's slice L-1, each [ncomp][surface] with the lexicographic face index of the other three
+    coordinates (lib/qudaQKXTM_kernels.cu:160-170, plaquette_core.h:30-50).  With the partition forced onto one rank the neighbours are
+    the rank itself.  The plaquette read through the ghost zones must equal the periodic one."""
+    X = (6, 4, 8, 6)
+    V = int(np.prod(X))
+    dt = np.float64 if prec == 8 else np.float32
+    rng = np.random.default_rng(ncomp)
+    d = Dev(tmq, X)
+    d.c.force_partition(part)
+    nghost = d.c.qkxtm_ghost_sites()
+    surf = {2: V // X[2], 3: V // X[3]}
+    assert nghost == sum(2 * surf[dim] for dim in (2, 3) if part[dim])
+    field = rng.standard_normal((ncomp, V, 2)).astype(dt)
+    buf = np.concatenate([field.reshape(-1), np.full(nghost * ncomp * 2, -7.0, dtype=dt)])
+    p = d.put(buf)
+    d.c.qkxtm_exchange_ghost(p, prec, ncomp)
+    got = d.get(p, buf.shape, dt)
+    assert np.array_equal(got[: field.size], field.reshape(-1))
+    f4 = field.reshape(ncomp, X[3], X[2], X[1], X[0], 2)
+    off = field.size
+    for dim in (2, 3):
+        if not part[dim]:
+            continue
+        lo = f4[:, 0] if dim == 3 else f4[:, :, 0]                 # slice 0 of the forward neighbour (= this rank)
+        hi = f4[:, -1] if dim == 3 else f4[:, :, -1]               # slice L-1 of the backward neighbour
+        n = ncomp * surf[dim] * 2
+        assert np.array_equal(got[off: off + n], np.ascontiguousarray(lo).reshape(-1)), ("plus", dim)
+        assert np.array_equal(got[off + n: off + 2 * n], np.ascontiguousarray(hi).reshape(-1)), ("minus", dim)
+        off += 2 * n
+    assert off == buf.size
+    if ncomp == 36:
+        U = lu.random_su3_lex(X, seed=5)
+        Ut = np.transpose(U, (0, 2, 3, 1))
+        gq = np.ascontiguousarray(np.stack([Ut.real, Ut.imag], axis=-1)).reshape(36, V, 2)
+        d0 = Dev(tmq, X)
+        want = d0.c.qkxtm_plaquette(d0.put(gq), 8)
+        d0.close()
+        pg = d.put(np.concatenate([gq.reshape(-1), np.zeros(nghost * 36 * 2)]))
+        assert abs(d.c.qkxtm_plaquette(pg, 8) - want) < 1e-13 * abs(want)
+    d.close()
