@@ -320,6 +320,11 @@ int tmq_time_kernel(tmq_ctx *, int kind, int prec, int reps, const tmq_spinor *i
  * records a second one, waits for it and returns the device time between them in milliseconds                */
 int tmq_timer_start(tmq_ctx *);
 int tmq_timer_stop(tmq_ctx *, double *ms);
+/* Out-of-bounds net of the library's own (compute-sanitizer is not available on every GPU pool): with the environment variable
+ * TMQ_GUARD_BYTES = n every device allocation of the library carries red zones of n bytes filled with a NaN pattern; an out-of-bounds
+ * read then poisons the result, and this call returns the number of allocations whose red zones have been written to (0 = clean,
+ * < 0 = CUDA error; details in tmq_last_error()).  Always 0 when the variable is unset.                                           */
+int tmq_guard_check(void);
 /* number of kernels this library has launched on the context since creation                                 */
 long long tmq_launch_count(tmq_ctx *);
 

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
+#include <map>
 #include "../../include/tmq.h"
 #include "tmq_internal.h"
 
@@ -30,6 +31,73 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// ---- guarded allocations (see tmq_internal.h) ----
+#undef cudaMalloc
+#undef cudaFree
+struct GuardRec { char *base; size_t n; };
+static std::map<void *, GuardRec> g_guard;
+static long long g_guard_bytes = -1;
+static size_t guard_size() {
+  if (g_guard_bytes < 0) {
+    const char *e = getenv("TMQ_GUARD_BYTES");
+    long long v = e ? atoll(e) : 0;
+    g_guard_bytes = v > 0 ? ((v + 255) / 256) * 256 : 0;
+  }
+  return (size_t)g_guard_bytes;
+}
+cudaError_t guard_malloc(void **p, size_t n) {
+  const size_t G = guard_size();
+  if (G == 0) return cudaMalloc(p, n);
+  char *base = nullptr;
+  const size_t body = ((n + 255) / 256) * 256;
+  cudaError_t e = cudaMalloc((void **)&base, body + 2 * G);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(base, 0xFF, body + 2 * G);          // the body too: reading memory the library never wrote shows up as NaN
+  if (e != cudaSuccess) return e;
+  g_guard[base + G] = GuardRec{base, n};
+  *p = base + G;
+  return cudaSuccess;
+}
+cudaError_t guard_free(void *p) {
+  if (guard_size() == 0 || p == nullptr) return cudaFree(p);
+  auto it = g_guard.find(p);
+  if (it == g_guard.end()) return cudaFree(p);
+  char *base = it->second.base;
+  g_guard.erase(it);
+  return cudaFree(base);
+}
+// number of live allocations whose red zones were written to (0 = clean); the first offender is described in tmq_last_error()
+static int guard_check_all() {
+  const size_t G = guard_size();
+  if (G == 0) return 0;
+  cudaDeviceSynchronize();
+  std::vector<unsigned char> h(G);
+  int bad = 0;
+  for (auto &kv : g_guard) {
+    const size_t body = ((kv.second.n + 255) / 256) * 256;
+    for (int side = 0; side < 2; side++) {
+      const char *zone = side == 0 ? kv.second.base : kv.second.base + G + body;
+      if (cudaMemcpy(h.data(), zone, G, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+      size_t first = G;
+      for (size_t i = 0; i < G; i++) if (h[i] != 0xFF) { first = i; break; }
+      // the slack between n and the 256-byte rounded body belongs to the tail zone as well
+      if (first == G && side == 1 && body > kv.second.n) {
+        std::vector<unsigned char> t(body - kv.second.n);
+        if (cudaMemcpy(t.data(), kv.second.base + G + kv.second.n, t.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        for (size_t i = 0; i < t.size(); i++) if (t[i] != 0xFF) { first = 0; break; }
+      }
+      if (first != G) {
+        if (bad == 0) set_error("out-of-bounds write %s an allocation of %zu bytes (offset %zu into the red zone)", side == 0 ? "before" : "behind", kv.second.n, first);
+        bad++;
+      }
+    }
+  }
+  return bad;
+}
+
+#define cudaMalloc(p, n) tmq::guard_malloc((void **)(p), (n))
+#define cudaFree(p) tmq::guard_free((void *)(p))
 
 static int largest_divisor_le(int n, int pref) {
   if (pref < 1) pref = 1;
@@ -695,6 +763,7 @@ int tmq_barrier(tmq_ctx *c) {
   TMQ_CUDA(cudaSetDevice(c->device));
   return comm_barrier(c);
 }
+int tmq_guard_check(void) { return tmq::guard_check_all(); }
 int tmq_halo_mode(tmq_ctx *c) { return c ? (c->multi ? (c->p2p ? 1 + c->opt_p2p : 1) : 0) : -1; }
 
 int tmq_set_tile(tmq_ctx *c, int ty, int tz, int tt) {

@@ -274,3 +274,15 @@ int comm_sendrecv_dim(tmq_ctx *c, int dim, const void *send_bwd, const void *sen
                       size_t nbytes, cudaStream_t st);
 
 }  // namespace tmq
+
+// ---- guarded device allocations (TMQ_GUARD_BYTES=n, n a multiple of 256) ----------------------------------------------------------------
+// compute-sanitizer is not available on the GPU pool, so the library carries its own out-of-bounds net: with the environment variable set
+// every device allocation of the library gets a red zone of n bytes on either side, filled with 0xFF -- a NaN pattern in fp32 and fp64, so
+// an out-of-bounds READ poisons the result and fails the parity checks, and tmq_guard_check() finds every out-of-bounds WRITE.  Off by
+// default (zero overhead: a plain cudaMalloc).  Every translation unit of the library allocates through these two.
+namespace tmq {
+cudaError_t guard_malloc(void **p, size_t n);
+cudaError_t guard_free(void *p);
+}
+#define cudaMalloc(p, n) tmq::guard_malloc((void **)(p), (n))
+#define cudaFree(p) tmq::guard_free((void *)(p))

@@ -10,7 +10,9 @@ mkdir -p $OUT
 CS=/usr/local/cuda/bin/compute-sanitizer
 summ() { grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Race reported|Hazard|Invalid|Uninitialized|sanitize target|Error" "$1" | sort | uniq -c | head -40; }
 for tool in memcheck racecheck synccheck initcheck; do
-  for what in plain mode3 mode2 mode1 mode0; do
+  targets="plain mode3 mode2 mode1 mode0"
+  if [ $tool = synccheck ] || [ $tool = initcheck ]; then targets="plain mode3"; fi
+  for what in $targets; do
     f=$OUT/sanitize_${TAG}_${tool}_${what}.txt
     timeout 600 $CS --tool $tool --print-limit 20 python tools/sanitize_target.py $what 3 > $f 2>&1
     echo "== $tool $what rc=$?" | tee -a $OUT/sanitize_${TAG}_summary.txt
