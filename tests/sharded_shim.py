@@ -40,7 +40,7 @@ def main():
     run(1, G, (1, 1, 1, 1), ref_t, *twop)
     names = ["mesons.SS.01.03.02.05.dat", "baryons.SS.01.03.02.05.dat",
              "threep_tsink5_projG5G123.proton.up.ultra_local.SS.01.03.02.05.dat", "threep_tsink5_projG5G123.proton.down.ultra_local.SS.01.03.02.05.dat"]
-    for tag, grid, port in (("T", (1, 1, 1, 2), 29531), ("Z", (1, 1, 2, 1), 29533)):
+    for tag, grid, port in (("T", (1, 1, 1, 2), 29531), ("Z", (1, 1, 2, 1), 29535)):
         local = tuple(G[d] // grid[d] for d in range(4))
         out = os.path.join(tmp, "sh_%s.bin" % tag)
         log = run(2, local, grid, out, "--test", "invert", "--tol", "1e-11", "--recon", "12", "--prec-sloppy", "single", port=port)
@@ -60,7 +60,14 @@ def main():
             e = np.abs(va - vb).max() / np.abs(va).max()
             if a.shape != b.shape or not e < 2e-5:
                 fails.append((nm, tag, e))
-        print("grid %s: invertQuda slabs and two-/three-point files compared" % (grid,), flush=True)
+        # MG_bench on the split lattice: the plaquette of the "smeared" links goes through the containers' ghost zones (ghostToHost ->
+        # cpuExchangeGhost -> ghostToDevice, one device-side exchange) and must print the single-rank value
+        import re
+        want = float(re.search(r"Calculated plaquette in double precision is (\S+)", run(1, G, (1, 1, 1, 1), os.path.join(tmp, "mg1.bin"), "--test", "mgbench", "--tol", "1e-5", "--recon", "12")).group(1))
+        got = float(re.search(r"Calculated plaquette in double precision is (\S+)", run(2, local, grid, os.path.join(tmp, "mg2.bin"), "--test", "mgbench", "--tol", "1e-5", "--recon", "12", port=port + 2)).group(1))
+        if not abs(want - got) < 2e-6:
+            fails.append(("plaquette through the ghost zones", tag, want, got))
+        print("grid %s: invertQuda slabs, two-/three-point files and the container plaquette compared" % (grid,), flush=True)
     print("failures:", fails)
     sys.exit(1 if fails else 0)
 
