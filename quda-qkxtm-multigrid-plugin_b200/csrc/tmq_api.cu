@@ -179,6 +179,25 @@ template <> cudaError_t pack_any<float>(tmq_ctx *c, const DslashArgs<float> &A, 
   return halo_pack(4, c->recon, nullptr, &A, dim, sb, sf, st);
 }
 
+// destinations of the faces of application `sq` in the neighbours' arenas (peer-store modes)
+template <typename F> static void fill_pack_dst(tmq_ctx *c, PackDst<F> &D, unsigned int sq) {
+  const int pi = sizeof(F) == 8 ? 0 : 1;
+  const HaloArena &L = c->arena_layout;
+  memset(&D, 0, sizeof(D));
+  const int b2 = (int)(sq & 1u);
+  D.seq = sq; D.ticket = c->ticket2;
+  for (int d = 2; d < 4; d++) {
+    if (!c->g.part[d]) continue;
+    const int sl = D.nslot++;
+    D.dim[sl] = d;
+    // slice 0 is the "from forward neighbour" ghost (dir 1) of rank-1; slice L-1 the dir-0 ghost of rank+1
+    D.dst[sl][0] = (VecT<F> *)(c->peer_arena[d][0] + L.recv[b2][pi][d][1]);
+    D.flag[sl][0] = (unsigned int *)(c->peer_arena[d][0] + arena_flag_off(L, b2, d, 1));
+    D.dst[sl][1] = (VecT<F> *)(c->peer_arena[d][1] + L.recv[b2][pi][d][0]);
+    D.flag[sl][1] = (unsigned int *)(c->peer_arena[d][1] + arena_flag_off(L, b2, d, 0));
+  }
+}
+
 template <typename F>
 static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) {
   const int prec = (int)sizeof(F);
@@ -305,24 +324,36 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
     //      Buffer reuse: faces for application N+1 go into buffer (N+1)&1 = (N-1)&1 of the neighbour, which it read in application
     //      N-1; a boundary CTA only packs after it has seen the neighbour's flag N, which the neighbour publishes after ALL its
     //      boundary CTAs of application N-1 are done.
-    const unsigned int seq = ++c->halo_seq;
-    const int buf = (int)(seq & 1u);
+    unsigned int seq = ++c->halo_seq;
     const HaloArena &L = c->arena_layout;
-    auto fill_dst = [&](PackDst<F> &D, unsigned int sq) {
-      memset(&D, 0, sizeof(D));
-      const int b2 = (int)(sq & 1u);
-      D.seq = sq; D.ticket = c->ticket2;
-      for (int d = 2; d < 4; d++) {
-        if (!g.part[d]) continue;
-        const int sl = D.nslot++;
-        D.dim[sl] = d;
-        // slice 0 is the "from forward neighbour" ghost (dir 1) of rank-1; slice L-1 the dir-0 ghost of rank+1
-        D.dst[sl][0] = (VecT<F> *)(c->peer_arena[d][0] + L.recv[b2][pi][d][1]);
-        D.flag[sl][0] = (unsigned int *)(c->peer_arena[d][0] + arena_flag_off(L, b2, d, 1));
-        D.dst[sl][1] = (VecT<F> *)(c->peer_arena[d][1] + L.recv[b2][pi][d][0]);
-        D.flag[sl][1] = (unsigned int *)(c->peer_arena[d][1] + arena_flag_off(L, b2, d, 0));
+    bool sent_ahead = false, discard = false;
+    if (c->prepacked_seq == seq) {
+      sent_ahead = c->prepacked_in == in && c->prepacked_dagger == s.dagger && c->prepacked_parity == s.out_parity && c->prepacked_prec == prec;
+      if (!sent_ahead) {
+        // faces were sent ahead for an application that is not this one (the update of the LAST CG iteration sends the search direction
+        // of an iteration that never runs): that sequence number is skipped on every rank alike.  Its flags were published by the
+        // neighbours' launches too, and only after they were done with application seq - 1 -- so the stand-alone pack below waits for
+        // them before it overwrites the buffers of application seq - 1.
+        discard = true;
+        seq = ++c->halo_seq;
       }
-    };
+    }
+    const int buf = (int)(seq & 1u);
+    if (!sent_ahead) {
+      PackDst<F> D;
+      fill_pack_dst<F>(c, D, seq);
+      if (discard) {
+        const int pbuf = (int)((seq - 1) & 1u);
+        for (int d = 2; d < 4; d++) {
+          if (!g.part[d]) continue;
+          for (int dir = 0; dir < 2; dir++) A.hw.flag[A.hw.n++] = (const unsigned int *)(c->arena + arena_flag_off(L, pbuf, d, dir));
+        }
+        A.hw.seq = seq - 1;
+      }
+      TMQ_CUDA(halo_pack_p2p(c->recon, A, D, c->stream));
+      c->launches++;
+      A.hw.n = 0;
+    }
     for (int d = 2; d < 4; d++) {
       if (!g.part[d]) continue;
       for (int dir = 0; dir < 2; dir++) {
@@ -331,17 +362,8 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
       }
     }
     A.hw.seq = seq;
-    if (c->prepacked_seq == seq) {
-      TMQ_REQUIRE(c->prepacked_in == in && c->prepacked_dagger == s.dagger && c->prepacked_parity == s.out_parity && c->prepacked_prec == prec,
-                  "internal error: the faces sent ahead by the previous launch do not belong to this application");
-    } else {
-      PackDst<F> D;
-      fill_dst(D, seq);
-      TMQ_CUDA(halo_pack_p2p(c->recon, A, D, c->stream));
-      c->launches++;
-    }
     if (s.pack_next && out != nullptr && s.epi != EPI_CG4) {
-      fill_dst(A.pk, seq + 1);
+      fill_pack_dst<F>(c, A.pk, seq + 1);
       A.pk_on = 1;
       A.pk_dsign = s.next_dagger ? (F)-1 : (F)1;
       c->prepacked_seq = seq + 1; c->prepacked_in = out; c->prepacked_dagger = s.next_dagger ? 1 : 0;
@@ -479,6 +501,32 @@ int check_device_error(tmq_ctx *c) {
     set_error("halo exchange timed out: a neighbour rank did not deliver its ghost face");
     return 1;
   }
+  return 0;
+}
+
+// x += alpha p ; p = r + beta p (alpha = scal[an]/scal[ad], beta = scal[bn]/scal[bd]).  Fused halo mode: the same launch packs the
+// new p for the first Dslash launch of the next iteration (K1: D, output parity q) and sends it to the neighbours.
+template <typename F> static int cg_update_fused(tmq_ctx *c, void *x, void *p, const void *r, int an, int ad, int bn, int bd) {
+  const int prec = (int)sizeof(F);
+  const GaugeStore &gs = prec == 8 ? c->gauge_d : c->gauge_s;
+  DslashArgs<F> A;
+  memset(&A, 0, sizeof(A));
+  A.g = c->g;
+  A.gauge = gs.d;
+  A.parity = c->matpc & 1;                           // p lives on the parity the preconditioned operator acts on
+  const unsigned int next = c->halo_seq + 1;
+  fill_pack_dst<F>(c, A.pk, next);
+  A.pk_on = 1; A.pk_dsign = (F)1;
+  TMQ_CUDA(cg_update_pack(c->recon, x, p, r, c->scal, an, ad, bn, bd, A, c->stream));
+  c->launches++;
+  c->prepacked_seq = next; c->prepacked_in = p; c->prepacked_dagger = 0; c->prepacked_parity = 1 - (c->matpc & 1); c->prepacked_prec = prec;
+  return 0;
+}
+int cg_update(tmq_ctx *c, int prec, void *x, void *p, const void *r, int an, int ad, int bn, int bd) {
+  if (c->multi && c->p2p && c->opt_p2p == 3 && c->matpc < 2)
+    return prec == 8 ? cg_update_fused<double>(c, x, p, r, an, ad, bn, bd) : cg_update_fused<float>(c, x, p, r, an, ad, bn, bd);
+  TMQ_CUDA(blas_cg_update(prec, x, p, r, (size_t)6 * c->g.Vh, c->scal, an, ad, bn, bd, c->stream));
+  c->launches++;
   return 0;
 }
 
@@ -1216,7 +1264,7 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
     // |r|^2 travels to the host while the update kernel runs
     TMQ_TRY(scal_to_host(c, sn, 1));
     TMQ_CUDA(cudaEventRecord(c->ev_r2, c->stream));
-    TMQ_CUDA(blas_cg_update(prec, x->d, p, r, n, c->scal, so, SC_PAP, sn, so, c->stream)); c->launches++;
+    TMQ_TRY(cg_update(c, prec, x->d, p, r, so, SC_PAP, sn, so));
     TMQ_CUDA(cudaEventSynchronize(c->ev_r2));
     r2 = c->h_scal[sn];
     k++;
@@ -1280,7 +1328,7 @@ static int cg_mixed(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol, 
     const bool updateX = rNorm < delta * r0Norm && r0Norm <= maxrx;
     const bool updateR = (rNorm < delta * maxrr && r0Norm <= maxrr) || updateX;
     if (!updateR && r2n > stop) {
-      TMQ_CUDA(blas_cg_update(4, xS, pS, rS, n, c->scal, so, SC_PAP, sn, so, c->stream)); c->launches++;
+      TMQ_TRY(cg_update(c, 4, xS, pS, rS, so, SC_PAP, sn, so));
       r2 = r2n;
     } else {
       // reliable update (also taken when the sloppy residual claims convergence, so that the loop only
@@ -1616,7 +1664,7 @@ int tmq_time_kernel(tmq_ctx *c, int kind, int prec, int reps, const tmq_spinor *
       default: {
         const int so = SC_R2_0 + (it & 1), sn = SC_R2_0 + ((it + 1) & 1);
         TMQ_TRY(cg_fused_matvec(c, prec, r, p, so, sn));
-        TMQ_CUDA(blas_cg_update(prec, dst, p, r, n, c->scal, so, SC_PAP, sn, so, c->stream)); c->launches++;
+        TMQ_TRY(cg_update(c, prec, dst, p, r, so, SC_PAP, sn, so));
         return 0;
       }
     }

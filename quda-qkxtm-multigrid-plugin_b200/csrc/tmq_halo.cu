@@ -36,6 +36,30 @@ __global__ void __launch_bounds__(128) halo_pack_p2p_kernel(const __grid_constan
   const int mu = D.dim[slot];
   const bool fwd = blockIdx.y == 1;
   const int f = blockIdx.x * 128 + threadIdx.x;
+  // fused mode, after faces that were sent ahead had to be discarded: the neighbours' buffers may only be overwritten once the
+  // neighbours have published the discarded sequence number (A.hw), i.e. are done reading what this launch overwrites
+  if (A.hw.n > 0) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < A.hw.n) {
+      unsigned int v = 0;
+      unsigned long long t0 = 0, now = 0;
+      int spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(A.hw.flag[threadIdx.x]) : "memory");
+        if ((int)(v - A.hw.seq) >= 0) break;
+        if (++spins == 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        if (spins > 64 && (spins & 255) == 0) {
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (now - t0 > A.hw.timeout_ns) { *((volatile double *)A.hw.err) = 1.0; bad = 1; break; }
+        }
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+    if (bad) return;
+  }
   if (f < A.g.face[mu]) {
     if (mu == 3) pack_site<F, RECON, 3>(A, f, fwd, D.dst[slot][fwd ? 1 : 0]);
     else         pack_site<F, RECON, 2>(A, f, fwd, D.dst[slot][fwd ? 1 : 0]);
@@ -84,6 +108,59 @@ template <typename F> static cudaError_t pack_p2p_t(int recon, const DslashArgs<
 cudaError_t halo_pack_p2p(int recon, const DslashArgs<double> &A, const PackDst<double> &D, cudaStream_t st) { return pack_p2p_t<double>(recon, A, D, st); }
 cudaError_t halo_pack_p2p(int recon, const DslashArgs<float> &A, const PackDst<float> &D, cudaStream_t st) { return pack_p2p_t<float>(recon, A, D, st); }
 
+
+// ---- CG update fused with the halo exchange of the next iteration (fused halo mode) -----------------------------------------------
+// x += alpha p ; p = r + beta p, one thread per site (18 vector loads, 12 stores: the same bytes as the streaming update kernel); the
+// threads on a partitioned boundary pack the new p -- the input of the next iteration's first Dslash launch -- straight into the
+// neighbours' arenas, the last CTA publishes the arrival flags.  A.parity = parity of p's sites, A.pk / A.pk_dsign as in the Dslash launch.
+template <typename F, int RECON>
+__global__ void __launch_bounds__(128) cg_update_pack_kernel(VecT<F> *x, VecT<F> *p, const VecT<F> *__restrict__ r, const double *scal, int an, int ad,
+                                                             int bn, int bd, const __grid_constant__ DslashArgs<F> A) {
+  const Geom &g = A.g;
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx < g.Vh) {
+    const F alpha = (F)(scal[an] / scal[ad]), beta = (F)(scal[bn] / scal[bd]);
+    Spinor<F> ps;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      const size_t o = (size_t)j * g.Vh + idx;
+      VecT<F> xv = x[o], pv = p[o];
+      const VecT<F> rv = r[o];
+      xv.a += alpha * pv.a; xv.b += alpha * pv.b; xv.c += alpha * pv.c; xv.d += alpha * pv.d;
+      pv.a = rv.a + beta * pv.a; pv.b = rv.b + beta * pv.b; pv.c = rv.c + beta * pv.c; pv.d = rv.d + beta * pv.d;
+      x[o] = xv; p[o] = pv;
+      unpack_vec(ps, j, pv);
+    }
+    const int plane = g.X[1] * g.Xh, vol3 = plane * g.X[2];
+    const int t = idx / vol3, rem = idx - t * vol3, z = rem / plane, rem2 = rem - z * plane, y = rem2 / g.Xh, xh = rem2 - y * g.Xh;
+    if (on_packed_boundary(A, z, t)) pack_spinor<F, RECON>(A, ps, idx, xh, y, z, t);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(A.pk.ticket, gridDim.x - 1);
+    if (t == gridDim.x - 1) {
+      __threadfence_system();
+      for (int s = 0; s < A.pk.nslot; s++)
+        for (int d = 0; d < 2; d++)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.pk.flag[s][d]), "r"(A.pk.seq) : "memory");
+    }
+  }
+}
+template <typename F>
+static cudaError_t cg_update_pack_t(int recon, void *x, void *p, const void *r, const double *scal, int an, int ad, int bn, int bd, const DslashArgs<F> &A, cudaStream_t st) {
+  const int grid = (A.g.Vh + 127) / 128;
+  if (recon == 8)       cg_update_pack_kernel<F, 8><<<grid, 128, 0, st>>>((VecT<F> *)x, (VecT<F> *)p, (const VecT<F> *)r, scal, an, ad, bn, bd, A);
+  else if (recon == 12) cg_update_pack_kernel<F, 12><<<grid, 128, 0, st>>>((VecT<F> *)x, (VecT<F> *)p, (const VecT<F> *)r, scal, an, ad, bn, bd, A);
+  else                  cg_update_pack_kernel<F, 18><<<grid, 128, 0, st>>>((VecT<F> *)x, (VecT<F> *)p, (const VecT<F> *)r, scal, an, ad, bn, bd, A);
+  return cudaGetLastError();
+}
+cudaError_t cg_update_pack(int recon, void *x, void *p, const void *r, const double *scal, int an, int ad, int bn, int bd, const DslashArgs<double> &A, cudaStream_t st) {
+  return cg_update_pack_t<double>(recon, x, p, r, scal, an, ad, bn, bd, A, st);
+}
+cudaError_t cg_update_pack(int recon, void *x, void *p, const void *r, const double *scal, int an, int ad, int bn, int bd, const DslashArgs<float> &A, cudaStream_t st) {
+  return cg_update_pack_t<float>(recon, x, p, r, scal, an, ad, bn, bd, A, st);
+}
 
 // ---- scalar all-reduce over peer memory -------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) p2p_allreduce_kernel(const __grid_constant__ P2PRed R) {

@@ -258,6 +258,10 @@ cudaError_t halo_pack(int prec, int recon, const DslashArgs<double> *Ad, const D
 cudaError_t halo_pack_p2p(int recon, const DslashArgs<double> &A, const PackDst<double> &D, cudaStream_t st);
 cudaError_t halo_pack_p2p(int recon, const DslashArgs<float> &A, const PackDst<float> &D, cudaStream_t st);
 cudaError_t p2p_allreduce(const P2PRed &R, cudaStream_t st);
+cudaError_t cg_update_pack(int recon, void *x, void *p, const void *r, const double *scal, int an, int ad, int bn, int bd, const DslashArgs<double> &A, cudaStream_t st);
+cudaError_t cg_update_pack(int recon, void *x, void *p, const void *r, const double *scal, int an, int ad, int bn, int bd, const DslashArgs<float> &A, cudaStream_t st);
+// x += alpha p ; p = r + beta p with device-resident scalars; in the fused halo mode the same launch sends the faces of the new p
+int cg_update(tmq_ctx *c, int prec, void *x, void *p, const void *r, int an, int ad, int bn, int bd);
 
 HaloArena halo_arena_layout(const Geom &g);
 inline size_t arena_flag_off(const HaloArena &L, int buf, int d, int dir) { return L.flag + sizeof(unsigned int) * (size_t)((buf * 4 + d) * 2 + dir); }

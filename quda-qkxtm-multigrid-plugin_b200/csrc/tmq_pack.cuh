@@ -61,31 +61,18 @@ __device__ __forceinline__ void pack_site(const DslashArgs<F> &A, int f, bool fw
 }
 
 
-// Fused path: the thread that has just stored output site `e` of this launch packs it as a face site of the NEXT application
-// (input parity = this launch's output parity, projector sign A.pk_dsign).  Slice 0 of a partitioned dimension goes backward
-// ((1 - s g) psi), slice L-1 goes forward (U^dag (1 + s g) psi, the link lives here).  The spinor is re-read from A.out: the
-// same thread stored it a few instructions ago, so the loads are served by the store queue / L2 and cost no HBM traffic.
+// Fused path: a thread that holds the complete spinor p of site (xh, y, z, t; cb index idx) of the field the NEXT application reads (site
+// parity A.parity, projector sign A.pk_dsign) packs it as a face site of every partitioned dimension it lies on the boundary of.  Slice 0
+// goes backward ((1 - s g) psi), slice L-1 goes forward (U^dag (1 + s g) psi, the link lives here).
 template <typename F, int RECON>
-__device__ __forceinline__ void pack_out(const DslashArgs<F> &A, const Enum &en, uint32_t e) {
+__device__ __forceinline__ void pack_spinor(const DslashArgs<F> &A, const Spinor<F> &p, int idx, int xh, int y, int z, int t) {
   const Geom &g = A.g;
-  const SiteCoord c = decode_site(g, en, A.parity, e);
-  bool any = false;
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    if (s >= A.pk.nslot) break;
-    const int mu = A.pk.dim[s], cm = mu == 3 ? c.t : c.z;
-    any = any || cm == 0 || cm == g.X[mu] - 1;
-  }
-  if (!any) return;
-  Spinor<F> p;
-#pragma unroll
-  for (int j = 0; j < 6; j++) unpack_vec(p, j, A.out[(size_t)j * g.Vh + c.idx]);
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     if (s >= A.pk.nslot) break;
     const int mu = A.pk.dim[s];
-    const int cm = mu == 3 ? c.t : c.z, L = g.X[mu], face = g.face[mu];
-    const int f = mu == 3 ? c.idx - cm * face : (c.t * g.X[1] + c.y) * g.Xh + c.xh;
+    const int cm = mu == 3 ? t : z, L = g.X[mu], face = g.face[mu];
+    const int f = mu == 3 ? idx - cm * face : (t * g.X[1] + y) * g.Xh + xh;
     if (cm == 0) {
       Half<F> h;
       if (mu == 3) project_any<F, 3>(h, p, A.pk_dsign); else project_any<F, 2>(h, p, A.pk_dsign);
@@ -96,11 +83,33 @@ __device__ __forceinline__ void pack_out(const DslashArgs<F> &A, const Enum &en,
       if (mu == 3) project_any<F, 3>(h, p, -A.pk_dsign); else project_any<F, 2>(h, p, -A.pk_dsign);
       Link<F> Lk;
       const F s12 = (mu == 3 && g.tb_last) ? (F)g.tb_sign : (F)1;
-      load_link<F, RECON>(Lk, A.gauge, A.parity, mu, c.idx, g.Vh, s12);
+      load_link<F, RECON>(Lk, A.gauge, A.parity, mu, idx, g.Vh, s12);
       su3_apply<F, true>(u, Lk, h);
       store_half(A.pk.dst[s][1], f, face, u);
     }
   }
+}
+template <typename F> __device__ __forceinline__ bool on_packed_boundary(const DslashArgs<F> &A, int z, int t) {
+  bool any = false;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    if (s >= A.pk.nslot) break;
+    const int mu = A.pk.dim[s], cm = mu == 3 ? t : z;
+    any = any || cm == 0 || cm == A.g.X[mu] - 1;
+  }
+  return any;
+}
+// the thread that has just stored output site `e` of a Dslash launch: the spinor is re-read from A.out (the same thread stored it a few
+// instructions ago, so the loads are served by the store queue / L2 and cost no HBM traffic)
+template <typename F, int RECON>
+__device__ __forceinline__ void pack_out(const DslashArgs<F> &A, const Enum &en, uint32_t e) {
+  const Geom &g = A.g;
+  const SiteCoord c = decode_site(g, en, A.parity, e);
+  if (!on_packed_boundary(A, c.z, c.t)) return;
+  Spinor<F> p;
+#pragma unroll
+  for (int j = 0; j < 6; j++) unpack_vec(p, j, A.out[(size_t)j * g.Vh + c.idx]);
+  pack_spinor<F, RECON>(A, p, c.idx, c.xh, c.y, c.z, c.t);
 }
 
 }  // namespace tmq

@@ -512,6 +512,19 @@ def lime_write_vector(fname, aos, localX, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0))
     _hck(load_host().tmq_lime_write_vector(fname.encode(), a.ctypes.data, prec, _i4(localX), _i4(grid), _i4(coord)))
 
 
+def lime_write_vector_header(fname, localX, grid, prec=8):
+    H = load_host()
+    H.tmq_lime_write_vector_header.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _hck(H.tmq_lime_write_vector_header(fname.encode(), prec, _i4(localX), _i4(grid)))
+
+
+def lime_write_vector_block(fname, aos, localX, grid, coord):
+    H = load_host()
+    H.tmq_lime_write_vector_block.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    a = np.ascontiguousarray(aos)
+    _hck(H.tmq_lime_write_vector_block(fname.encode(), a.ctypes.data, 8 if a.dtype == np.float64 else 4, _i4(localX), _i4(grid), _i4(coord)))
+
+
 def lime_read_vector(fname, localX, dtype=np.float64, grid=(1, 1, 1, 1), coord=(0, 0, 0, 0)):
     out = np.empty((int(np.prod(localX)), 4, 3, 2), dtype=dtype)
     _hck(load_host().tmq_lime_read_vector(fname.encode(), out.ctypes.data, out.dtype.itemsize, _i4(localX), _i4(grid), _i4(coord)))

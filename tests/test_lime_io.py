@@ -112,3 +112,54 @@ def test_errors(tmq, tmp_path):
     build_ildg(path, lu.random_su3_lex(X, seed=1), X, 0.1, 0.0)
     with pytest.raises(tmq.TmqError):
         tmq.lime_read_gauge(path, (4, 4, 4, 8))                       # wrong extents
+
+
+def _write_worker(rank, world, port, path, X, grid, q):
+    """one rank of QKXTM_Vector::write on a process grid (host/qudaQKXTM_tmq.cpp): rank 0 creates the file, ALL ranks meet at a barrier,
+    every rank writes its block, barrier -- the order the reference gets from its MPI_Bcast of the payload offset (lib/qudaQKXTM_Vector.cpp:625)"""
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import tmq as T
+        coord = lu.rank_coord(rank, grid)
+        psi = lu.gaussian_spinor_lex(X, seed=3, grid=grid, coord=coord)
+        if rank == 0:
+            T.lime_write_vector_header(path, X, grid)
+        dist.barrier()
+        T.lime_write_vector_block(path, psi, X, grid, coord)
+        dist.barrier()
+        q.put((rank, "ok"))
+    except Exception as e:          # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 1, 2), (1, 1, 2, 1)])
+def test_two_ranks_write_a_propagator_over_a_stale_file(tmq, tmp_path, grid):
+    """world_size-2 (gloo) run of the two-step writer over an EXISTING file of the same name with other content and size: the result must be
+    the complete new propagator (without the barrier a non-root rank could write into the old file, which rank 0 then truncates)"""
+    import socket
+    import torch.multiprocessing as mp
+    X = (4, 4, 4, 4)
+    G = tuple(X[d] * grid[d] for d in range(4))
+    path = str(tmp_path / "prop.lime")
+    tmq.lime_write_vector(path, lu.gaussian_spinor_lex((4, 4, 4, 6), seed=9), (4, 4, 4, 6))     # the stale file: another lattice
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_write_worker, args=(r, 2, port, path, X, grid, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: "ok", 1: "ok"}, res
+    want = lu.gaussian_spinor_lex(G, seed=3)
+    assert np.array_equal(tmq.lime_read_vector(path, G), want)
+    # a block written against a file whose payload does not match the lattice is refused, not silently accepted
+    tmq.lime_write_vector(path, lu.gaussian_spinor_lex((4, 4, 4, 6), seed=9), (4, 4, 4, 6))
+    with pytest.raises(tmq.TmqError, match="stale"):
+        tmq.lime_write_vector_block(path, want[: int(np.prod(X))], X, grid, (0, 0, 0, 0))
