@@ -402,7 +402,12 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
       }
     }
     A.hw.seq = seq;
-    TMQ_CUDA(halo_pack_p2p(c->recon, A, D, c->stream));
+    {
+      const int nwait = A.hw.n;
+      A.hw.n = 0;                    // the pack launch itself waits for nothing (its A.hw is only used after discarded faces, fused mode)
+      TMQ_CUDA(halo_pack_p2p(c->recon, A, D, c->stream));
+      A.hw.n = nwait;
+    }
     c->launches++;
     A.en = en_int; A.en_b[0] = en_t; A.en_b[1] = en_z;
     A.nblk[0] = nblocks(en_int); A.nblk[1] = nblocks(en_t); A.nblk[2] = nblocks(en_z);
