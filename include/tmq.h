@@ -58,6 +58,9 @@ int tmq_comm_init(tmq_ctx *, const char id128[128], int nranks, int rank);
  * (e.g. lib/qudaQKXTM_Vector.cpp:625, lib/qudaQKXTM_Contraction.cpp:1580-1584): call it after any phase in which ranks diverge
  * (file I/O by one rank), so that the bounded halo waits of the next Dslash never see that skew.  No-op on one rank.            */
 int tmq_barrier(tmq_ctx *);
+/* in-place sum of n host doubles over all ranks: the MPI_Reduce / MPI_Gather of the correlator writers
+ * (lib/qudaQKXTM_Contraction.cpp:869-875,1580-1584), staged through the device.  No-op on one rank.                             */
+int tmq_allreduce_host(tmq_ctx *, double *h, size_t n);
 /* force the ghost-zone (pack -> exchange -> interior/boundary) path in dimension d even when grid[d] = 1,
  * where the exchange wraps onto this rank: the reference's --partition mask (qkxtm/QKXTM_util.cpp:1717-1720).
  * Only z (part[2]) and t (part[3]) may be set.  Must be called before any field is created.              */

@@ -811,6 +811,19 @@ int tmq_comm_init(tmq_ctx *c, const char id128[128], int nranks, int rank) {
   TMQ_TRY(comm_init(c, id128, nranks, rank));
   return comm_setup_p2p(c);     // map the neighbours' ghost arenas (CUDA IPC); falls back to NCCL send/recv
 }
+// in-place sum of a host array over all ranks (staged through the device: NCCL all-reduce over NVLink)
+int tmq_allreduce_host(tmq_ctx *c, double *h, size_t n) {
+  TMQ_REQUIRE(c && h, "null argument");
+  if (c->nranks == 1 || n == 0) return 0;
+  TMQ_REQUIRE(n < ((size_t)1 << 31), "array too long");
+  TMQ_CUDA(cudaSetDevice(c->device));
+  TMQ_TRY(ensure_stage(c, n * sizeof(double)));
+  TMQ_CUDA(cudaMemcpyAsync(c->stage, h, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TMQ_TRY(comm_allreduce(c, (double *)c->stage, (int)n, c->stream));
+  TMQ_CUDA(cudaMemcpyAsync(h, c->stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TMQ_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
 int tmq_barrier(tmq_ctx *c) {
   TMQ_REQUIRE(c, "null context");
   TMQ_CUDA(cudaSetDevice(c->device));

@@ -41,9 +41,6 @@ struct Globals {
   double alphaGauss = 0;
   std::vector<int> moms;              // GK_moms [GK_Nmoms][3] (lib/qudaQKXTM_kernels.cu:75-76, createMomenta :98-116)
   std::vector<int> sourcePosition;    // GK_sourcePosition [Nsources][4]
-  // the complete (all time slices, reduced over ranks) result of the last contractMesons / contractBaryons / contractFixSink: libtmq hands
-  // it to every rank, so that the writers need no MPI_Gather over the time communicator (lib/qudaQKXTM_Contraction.cpp:1580-1584)
-  std::vector<double> glob_mesons, glob_baryons, glob_thrp;
   int op_matpc = -1;
   bool moms_overflow = false;         // init_qudaQKXTM saw more than MAX_NMOMENTA momenta
   quda::ColorSpinorField *work[3] = {nullptr, nullptr, nullptr};   // parity work fields of solve_device
@@ -850,6 +847,18 @@ template <typename Float> void QKXTM_Propagator3D<Float>::absorbVectorTimeSlice(
   TMQ_OK(tmq_qkxtm_column_copy(G.ctx, this->d_elem, V3, 0, vec.D_elem(), V, (long long)timeslice * V3, V3, (int)sizeof(Float), nu, c2, 1));
 }
 
+// The writers' gather over the time communicator (the reference: MPI_Gather of every rank's buffer, lib/qudaQKXTM_Contraction.cpp:1580-1584):
+// the CALLER's buffer [Lt][per_t] -- already summed over the ranks that share its time slices -- is placed at this rank's time offset of a
+// zero-padded global-T array and the arrays are summed over all ranks; only the ranks at z coordinate 0 contribute.
+template <typename Float> static std::vector<Float> gather_over_t(const Float *local, size_t per_t) {
+  const int Lt = G.localL[3], T = Lt * G.grid[3];
+  std::vector<double> g((size_t)T * per_t, 0.0);
+  if (G.coord[0] == 0 && G.coord[1] == 0 && G.coord[2] == 0)
+    for (size_t i = 0; i < (size_t)Lt * per_t; i++) g[(size_t)G.coord[3] * Lt * per_t + i] = (double)local[i];
+  TMQ_OK(tmq_allreduce_host(G.ctx, g.data(), g.size()));
+  return std::vector<Float>(g.begin(), g.end());
+}
+
 // ---- QKXTM_Contraction (mesons) -----------------------------------------------------------------------------------------------
 template <typename Float>
 void QKXTM_Contraction<Float>::contractMesons(QKXTM_Propagator<Float> &prop1, QKXTM_Propagator<Float> &prop2, void *corrMesons, int isource,
@@ -873,7 +882,6 @@ void QKXTM_Contraction<Float>::contractMesons(QKXTM_Propagator<Float> &prop1, QK
     std::vector<double> mom((size_t)gT * nm * 40);
     TMQ_OK(tmq_qkxtm_contract_mesons(G.ctx, prop1.D_elem(), prop2.D_elem(), (int)sizeof(Float), G.moms.data(), nm, &G.sourcePosition[(size_t)isource * 4],
                                      mom.data(), NULL));
-    G.glob_mesons = mom;
     for (int it = 0; it < Lt; it++)
       for (int im = 0; im < nm; im++)
         for (int ch = 0; ch < 20; ch++)
@@ -887,18 +895,10 @@ void QKXTM_Contraction<Float>::writeTwopMesons_ASCII(void *corrMesons, char *fil
   if (CorrSpace != MOMENTUM_SPACE) errorQuda("writeTwopMesons_ASCII: Supports writing only in momentum-space!");
   printfQuda("writeTwopMesons_ASCII: Will write in %s precision\n", sizeof(Float) == 4 ? "single" : "double");
   const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
-  // on a t split the complete correlator comes from the last contractMesons (every rank has it), rounded to Float like the caller's
+  // on a t split the caller's buffers are gathered over the time ranks (every rank calls this)
   std::vector<Float> gathered;
   const Float *c = (const Float *)corrMesons;
-  if (G.grid[3] != 1) {
-    if (G.glob_mesons.size() != (size_t)T * nm * 40) errorQuda("writeTwopMesons_ASCII: call contractMesons first");
-    gathered.resize((size_t)T * nm * 40);
-    for (int it = 0; it < T; it++)
-      for (int im = 0; im < nm; im++)
-        for (int ch = 0; ch < 20; ch++)
-          for (int ri = 0; ri < 2; ri++) gathered[(((size_t)it * nm + im) * 2 + ri) * 20 + ch] = (Float)G.glob_mesons[(((size_t)it * nm + im) * 20 + ch) * 2 + ri];
-    c = gathered.data();
-  }
+  if (G.grid[3] != 1) { gathered = gather_over_t(c, (size_t)nm * 40); c = gathered.data(); }
   const int *mv = qkxtm_moms();
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
@@ -930,7 +930,6 @@ void QKXTM_Contraction<Float>::contractBaryons(QKXTM_Propagator<Float> &prop1, Q
   std::vector<double> mom((size_t)gT * nm * 320 * 2);
   TMQ_OK(tmq_qkxtm_contract_baryons(G.ctx, prop1.D_elem(), prop2.D_elem(), (int)sizeof(Float), G.moms.data(), nm, &G.sourcePosition[(size_t)isource * 4],
                                     mom.data()));
-  G.glob_baryons = mom;
   for (int it = 0; it < Lt; it++)
     for (int im = 0; im < nm; im++)
       for (int ch = 0; ch < 320; ch++)
@@ -945,15 +944,7 @@ void QKXTM_Contraction<Float>::writeTwopBaryons_ASCII(void *corrBaryons, char *f
   const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
   std::vector<Float> gathered;
   const Float *c = (const Float *)corrBaryons;
-  if (G.grid[3] != 1) {
-    if (G.glob_baryons.size() != (size_t)T * nm * 640) errorQuda("writeTwopBaryons_ASCII: call contractBaryons first");
-    gathered.resize((size_t)T * nm * 640);
-    for (int it = 0; it < T; it++)
-      for (int im = 0; im < nm; im++)
-        for (int ch = 0; ch < 320; ch++)
-          for (int ri = 0; ri < 2; ri++) gathered[(((size_t)it * nm + im) * 2 + ri) * 320 + ch] = (Float)G.glob_baryons[(((size_t)it * nm + im) * 320 + ch) * 2 + ri];
-    c = gathered.data();
-  }
+  if (G.grid[3] != 1) { gathered = gather_over_t(c, (size_t)nm * 640); c = gathered.data(); }
   const int *mv = qkxtm_moms();
   bool root = true;
   for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
@@ -1004,7 +995,6 @@ void QKXTM_Contraction<Float>::contractFixSink(QKXTM_Propagator<Float> &seqProp,
                                  &G.sourcePosition[(size_t)isource * 4], mom.data()));
   Float *out = (Float *)corrThp_local;
   for (size_t i = 0; i < (size_t)Lt * nm * 32; i++) out[i] = (Float)mom[(size_t)G.coord[3] * Lt * nm * 32 + i];
-  G.glob_thrp = mom;
   if (corrThp_noether) {
     if (!gauge.D_elem()) errorQuda("contractFixSink: the Noether and one-derivative insertions need the gauge links on the device");
     std::vector<double> cn((size_t)Lt * nm * 4 * 2), co((size_t)Lt * nm * 64 * 2);
@@ -1028,18 +1018,14 @@ void QKXTM_Contraction<Float>::writeThrp_ASCII(void *corrThp_local, void *corrTh
   snprintf(fname_local, sizeof(fname_local), "%s.%s.%s.%s.SS.%02d.%02d.%02d.%02d.dat", filename_out, particle, flavour, "ultra_local", sp[0], sp[1], sp[2], sp[3]);
   snprintf(fname_noether, sizeof(fname_noether), "%s.%s.%s.%s.SS.%02d.%02d.%02d.%02d.dat", filename_out, particle, flavour, "noether", sp[0], sp[1], sp[2], sp[3]);
   snprintf(fname_oneD, sizeof(fname_oneD), "%s.%s.%s.%s.SS.%02d.%02d.%02d.%02d.dat", filename_out, particle, flavour, "oneD", sp[0], sp[1], sp[2], sp[3]);
-  bool root = true;
-  for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
-  if (!root) { comm_barrier(); return; }       // the writing rank joins when its file is complete (the reference has an MPI_Gather here)
   const int nm = qkxtm_Nmoms(), T = G.localL[3] * G.grid[3];
   const int *mv = qkxtm_moms();
   std::vector<Float> gathered;
   const Float *c = (const Float *)corrThp_local;
-  if (G.grid[3] != 1) {
-    if (G.glob_thrp.size() != (size_t)T * nm * 32) errorQuda("writeThrp_ASCII: call contractFixSink first");
-    gathered.assign(G.glob_thrp.begin(), G.glob_thrp.end());
-    c = gathered.data();
-  }
+  if (G.grid[3] != 1) { gathered = gather_over_t(c, (size_t)nm * 32); c = gathered.data(); }      // collective: before the root test
+  bool root = true;
+  for (int d = 0; d < 4; d++) root = root && G.coord[d] == 0;
+  if (!root) { comm_barrier(); return; }       // the writing rank joins when its file is complete (the reference has an MPI_Gather here)
   FILE *ptr_local = fopen(fname_local, "w");
   if (ptr_local == NULL) errorQuda("Error opening file for writing");
   for (int iop = 0; iop < 16; iop++)
