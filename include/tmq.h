@@ -69,6 +69,9 @@ int tmq_force_partition(tmq_ctx *, const int part[4]);
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
 enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3, TMQ_OPT_SMEAR_BLOCK_T = 4, TMQ_OPT_PACK_ASYNC = 5,
        TMQ_OPT_CONTRACT_SLICES = 6 /* > 0: time slices per pass of the baryon / derivative contractions (default: what fits 2 GiB) */,
+       TMQ_OPT_CG_LAG = 8 /* 1 (default): the fp64 CG's host loop runs one iteration ahead of the |r|^2 read-back, the stopping test is
+                             also taken on the device and launches enqueued past convergence exit at once -- same iterates, same iteration
+                             count as the synchronous loop (0) */,
        TMQ_OPT_HALO_TIMEOUT_MS = 7 /* wall-clock limit (ms, default 120000; env TMQ_HALO_TIMEOUT_MS) of a device-side wait for a neighbour's
                                       ghost face or all-reduce contribution; on expiry nothing is computed from stale ghosts, the device
                                       error scalar is raised and the enclosing call (tmq_sync, tmq_cg_mdagm, ...) fails */ };   /* TMQ_OPT_PREFETCH: accepted and ignored (the L2-prefetch experiment was removed: no gain) */

@@ -226,6 +226,8 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
   A.red_slot = s.red_slot; A.red_accum = 0;
   A.alpha_num = s.alpha_num; A.alpha_den = s.alpha_den;
   A.prefetch = c->opt_prefetch;
+  A.cg_iter = c->cg_iter_cur;
+  A.cg_local_stop = (c->cg_iter_cur > 0 && c->nranks == 1) ? 1 : 0;
   if (c->clover_on) {
     // site matrices of the OUTPUT parity (every site operator of the epilogues acts on the output site)
     const size_t off = (size_t)s.out_parity * 36 * c->g.Vh;
@@ -328,7 +330,7 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
     const HaloArena &L = c->arena_layout;
     bool sent_ahead = false, discard = false;
     if (c->prepacked_seq == seq) {
-      sent_ahead = c->prepacked_in == in && c->prepacked_dagger == s.dagger && c->prepacked_parity == s.out_parity && c->prepacked_prec == prec;
+      sent_ahead = s.accept_ahead && c->prepacked_in == in && c->prepacked_dagger == s.dagger && c->prepacked_parity == s.out_parity && c->prepacked_prec == prec;
       if (!sent_ahead) {
         // faces were sent ahead for an application that is not this one (the update of the LAST CG iteration sends the search direction
         // of an iteration that never runs): that sequence number is skipped on every rank alike.  Its flags were published by the
@@ -522,6 +524,7 @@ template <typename F> static int cg_update_fused(tmq_ctx *c, void *x, void *p, c
   const unsigned int next = c->halo_seq + 1;
   fill_pack_dst<F>(c, A.pk, next);
   A.pk_on = 1; A.pk_dsign = (F)1;
+  A.cg_iter = c->cg_iter_cur;
   TMQ_CUDA(cg_update_pack(c->recon, x, p, r, c->scal, an, ad, bn, bd, A, c->stream));
   c->launches++;
   c->prepacked_seq = next; c->prepacked_in = p; c->prepacked_dagger = 0; c->prepacked_parity = 1 - (c->matpc & 1); c->prepacked_prec = prec;
@@ -530,7 +533,7 @@ template <typename F> static int cg_update_fused(tmq_ctx *c, void *x, void *p, c
 int cg_update(tmq_ctx *c, int prec, void *x, void *p, const void *r, int an, int ad, int bn, int bd) {
   if (c->multi && c->p2p && c->opt_p2p == 3 && c->matpc < 2)
     return prec == 8 ? cg_update_fused<double>(c, x, p, r, an, ad, bn, bd) : cg_update_fused<float>(c, x, p, r, an, ad, bn, bd);
-  TMQ_CUDA(blas_cg_update(prec, x, p, r, (size_t)6 * c->g.Vh, c->scal, an, ad, bn, bd, c->stream));
+  TMQ_CUDA(blas_cg_update(prec, x, p, r, (size_t)6 * c->g.Vh, c->scal, an, ad, bn, bd, c->stream, c->cg_iter_cur));
   c->launches++;
   return 0;
 }
@@ -547,20 +550,20 @@ int op_matpc(tmq_ctx *c, int prec, void *out, const void *in, int dagger) {
   if (!asym && !dagger) {
     a.epi = EPI_TW; a.out_parity = q; a.t1 = tw_Ainv(c, 0); a.pack_next = 1; a.next_dagger = 0;
     TMQ_TRY(apply_hop(c, prec, t0, in, a));
-    b.epi = EPI_TW_XPAY; b.out_parity = p; b.t1 = tw_Ainv(c, 0); b.k = k2; b.x = in;
+    b.epi = EPI_TW_XPAY; b.out_parity = p; b.t1 = tw_Ainv(c, 0); b.k = k2; b.x = in; b.accept_ahead = 1;
     return apply_hop(c, prec, out, t0, b);
   }
   if (!asym && dagger) {
     TMQ_TRY(site_op(c, prec, t1, in, p, tw_Ainv(c, 1)));
     a.epi = EPI_TW; a.out_parity = q; a.dagger = 1; a.t1 = tw_Ainv(c, 1); a.pack_next = 1; a.next_dagger = 1;
     TMQ_TRY(apply_hop(c, prec, t0, t1, a));
-    b.epi = EPI_XPAY; b.out_parity = p; b.dagger = 1; b.k = k2; b.x = in;
+    b.epi = EPI_XPAY; b.out_parity = p; b.dagger = 1; b.k = k2; b.x = in; b.accept_ahead = 1;
     return apply_hop(c, prec, out, t0, b);
   }
   // asymmetric, either direction: t = A^-(dag) D(dag) in ; out = A(dag) in - k^2 D(dag) t
   a.epi = EPI_TW; a.out_parity = q; a.dagger = dagger; a.t1 = tw_Ainv(c, dagger); a.pack_next = 1; a.next_dagger = dagger;
   TMQ_TRY(apply_hop(c, prec, t0, in, a));
-  b.epi = EPI_TWX_XPAY; b.out_parity = p; b.dagger = dagger; b.tx = tw_A(c, dagger); b.k = k2; b.x = in;
+  b.epi = EPI_TWX_XPAY; b.out_parity = p; b.dagger = dagger; b.tx = tw_A(c, dagger); b.k = k2; b.x = in; b.accept_ahead = 1;
   return apply_hop(c, prec, out, t0, b);
 }
 
@@ -582,13 +585,14 @@ int op_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int pap_slot) {
   k1.epi = EPI_TW; k1.out_parity = q; k1.t1 = tw_Ainv(c, 0); k1.pack_next = 1; k1.next_dagger = 0;
   TMQ_TRY(apply_hop(c, prec, t0, in, k1));
   k2s.epi = EPI_MDAGM2; k2s.out_parity = p; k2s.t1 = tw_Ainv(c, 0); k2s.k = k2; k2s.x = in; k2s.t3 = tw_Ainv(c, 1);
-  k2s.red_slot = pap_slot; k2s.pack_next = 1; k2s.next_dagger = 1;
+  k2s.red_slot = pap_slot; k2s.pack_next = 1; k2s.next_dagger = 1; k2s.accept_ahead = 1;
   // twisted-clover: K2 also stores y = M in, and K4 forms y - k^2 D^dag u from it instead of applying A^dag to w
   void *ybuf = nullptr;
   if (c->clover_on) { TMQ_TRY(ensure_scratch(c, prec, 7)); ybuf = scr(c, prec, 6); k2s.out2 = ybuf; }
   TMQ_TRY(apply_hop(c, prec, t1, t0, k2s));
-  k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1); k3.pack_next = 1; k3.next_dagger = 1;
+  k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1); k3.pack_next = 1; k3.next_dagger = 1; k3.accept_ahead = 1;
   TMQ_TRY(apply_hop(c, prec, t0, t1, k3));
+  k4.accept_ahead = 1;
   k4.epi = EPI_TWX_XPAY; k4.out_parity = p; k4.dagger = 1; k4.tx = tw_A(c, 1); k4.k = k2; k4.x = t1;
   if (ybuf) { k4.x = ybuf; k4.cl_plain_x = 1; }
   return apply_hop(c, prec, out, t0, k4);
@@ -596,20 +600,22 @@ int op_mdagm(tmq_ctx *c, int prec, void *out, const void *in, int pap_slot) {
 
 // one fused CG iteration body on M_sym^dag M_sym (no host interaction): K1..K4.
 //   reads  r2_old from scal[r2_old], writes <p,Ap> to SC_PAP and the new |r|^2 to scal[r2_new]
-static int cg_fused_matvec(tmq_ctx *c, int prec, void *r, const void *p_, int r2_old, int r2_new) {
+static int cg_fused_matvec(tmq_ctx *c, int prec, void *r, const void *p_, int r2_old, int r2_new, bool first) {
   const int p = c->matpc & 1, q = 1 - p;
   const double k2 = -c->kappa * c->kappa;
   void *t0 = scr(c, prec, 0), *t1 = scr(c, prec, 1);
   HopSpec k1, k2s, k3, k4;
   k1.epi = EPI_TW; k1.out_parity = q; k1.t1 = tw_Ainv(c, 0); k1.pack_next = 1; k1.next_dagger = 0;
+  k1.accept_ahead = first ? 0 : 1;          // the update of the previous iteration sent the faces of the new search direction
   TMQ_TRY(apply_hop(c, prec, t0, p_, k1));
   k2s.epi = EPI_MDAGM2; k2s.out_parity = p; k2s.t1 = tw_Ainv(c, 0); k2s.k = k2; k2s.x = p_; k2s.t3 = tw_Ainv(c, 1);
-  k2s.red_slot = SC_PAP; k2s.pack_next = 1; k2s.next_dagger = 1;
+  k2s.red_slot = SC_PAP; k2s.pack_next = 1; k2s.next_dagger = 1; k2s.accept_ahead = 1;
   void *ybuf = nullptr;
   if (c->clover_on) { TMQ_TRY(ensure_scratch(c, prec, 7)); ybuf = scr(c, prec, 6); k2s.out2 = ybuf; }
   TMQ_TRY(apply_hop(c, prec, t1, t0, k2s));
-  k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1); k3.pack_next = 1; k3.next_dagger = 1;
+  k3.epi = EPI_TW; k3.out_parity = q; k3.dagger = 1; k3.t1 = tw_Ainv(c, 1); k3.pack_next = 1; k3.next_dagger = 1; k3.accept_ahead = 1;
   TMQ_TRY(apply_hop(c, prec, t0, t1, k3));
+  k4.accept_ahead = 1;
   k4.epi = EPI_CG4; k4.out_parity = p; k4.dagger = 1; k4.tx = tw_A(c, 1); k4.k = k2; k4.x = t1; k4.r = r;
   if (ybuf) { k4.x = ybuf; k4.cl_plain_x = 1; }
   k4.red_slot = r2_new; k4.alpha_num = r2_old; k4.alpha_den = SC_PAP;
@@ -689,6 +695,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   ok = ok && cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_r2, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev_r2b, cudaEventDisableTiming) == cudaSuccess;
   c->sms = 148;
   cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
   size_t nblk = (size_t)(g.Vh + 127) / 128 + 1;
@@ -790,6 +797,7 @@ int tmq_destroy(tmq_ctx *c) {
   if (c->ev_pack) cudaEventDestroy(c->ev_pack);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->ev_r2) cudaEventDestroy(c->ev_r2);
+  if (c->ev_r2b) cudaEventDestroy(c->ev_r2b);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   delete c;
@@ -847,6 +855,7 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
     case TMQ_OPT_PACK_ASYNC: c->opt_pack_async = value ? 1 : 0; return 0;
     case TMQ_OPT_CONTRACT_SLICES: c->opt_contract_slices = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_SMEAR_BLOCK_T: c->opt_smear_block_t = value < 0 ? 0 : value; return 0;
+    case TMQ_OPT_CG_LAG: c->opt_cg_lag = value ? 1 : 0; return 0;
     case TMQ_OPT_HALO_TIMEOUT_MS: c->opt_halo_timeout_ms = value > 0 ? value : 120000; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {
@@ -1266,10 +1275,55 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
   if (b2 == 0.0) { *iters = 0; *true_res = 0.0; return 0; }
   const auto tl0 = std::chrono::steady_clock::now();
   c->cg_reliable_updates = 0;
+  // The host needs |r|^2 only for the stopping test.  Waiting for it every iteration leaves the GPU idle for a launch latency per
+  // iteration -- nothing at 48^3x96 on one GPU, a tenth of the iteration on an 8-way shard.  So the host runs ONE ITERATION AHEAD: it
+  // enqueues iteration k+1, then reads |r|^2 of iteration k.  The test itself also runs on the device (the launch that completes the
+  // global |r|^2 sets SC_DONE); the launches of an iteration enqueued after convergence exit at once, so x, r, p and the iteration
+  // count are exactly those of the synchronous loop.  Not with NCCL all-reduces (their result is not tested on the device).
+  const bool lag = fused && c->opt_cg_lag && (c->nranks == 1 || (c->multi && c->p2p));
+  if (lag) {
+    c->h_scal[SC_STOP] = stop; c->h_scal[SC_DONE] = 0.0;
+    TMQ_CUDA(cudaMemcpyAsync(c->scal + SC_STOP, c->h_scal + SC_STOP, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    cudaEvent_t ev[2] = {c->ev_r2, c->ev_r2b};
+    int done = -1;
+    while (k < maxiter) {
+      const int so = SC_R2_0 + (k & 1), sn = SC_R2_0 + ((k + 1) & 1);
+      c->cg_iter_cur = k + 1;
+      int rc = cg_fused_matvec(c, prec, r, p, so, sn, k == 0);
+      if (!rc) rc = scal_to_host(c, sn, 1);
+      if (!rc && cudaEventRecord(ev[k & 1], c->stream) != cudaSuccess) rc = 1;
+      if (!rc) rc = cg_update(c, prec, x->d, p, r, so, SC_PAP, sn, so);
+      c->cg_iter_cur = 0;
+      if (rc) return rc;
+      if (k >= 1) {                       // |r|^2 of iteration k - 1, while iteration k runs
+        TMQ_CUDA(cudaEventSynchronize(ev[(k - 1) & 1]));
+        r2 = c->h_scal[so];
+        c->cg_hist.push_back(r2);
+        if (!(r2 == r2)) { set_error("CG broke down (NaN residual) at iteration %d", k); return 1; }
+        if (r2 <= stop) { done = k; break; }   // k iterations count; the device skipped iteration k + 1 (index k)
+      }
+      k++;
+    }
+    if (done < 0) {                       // maxiter reached: the last iteration's |r|^2 has not been read yet
+      if (k >= 1) {
+        TMQ_CUDA(cudaEventSynchronize(ev[(k - 1) & 1]));
+        r2 = c->h_scal[SC_R2_0 + (k & 1)];
+        c->cg_hist.push_back(r2);
+        if (!(r2 == r2)) { set_error("CG broke down (NaN residual) at iteration %d", k); return 1; }
+      }
+    } else k = done;
+    TMQ_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->multi) {
+      // launches that exited early published no arrival flags: forget the faces "sent ahead" and let every rank drain before the
+      // sequence numbers continue (the skipped ones are never waited for)
+      c->prepacked_seq = 0;
+      if (c->nranks > 1) TMQ_TRY(comm_barrier(c));
+    }
+  } else
   while (r2 > stop && k < maxiter) {
     const int so = SC_R2_0 + (k & 1), sn = SC_R2_0 + ((k + 1) & 1);
     if (fused) {
-      TMQ_TRY(cg_fused_matvec(c, prec, r, p, so, sn));
+      TMQ_TRY(cg_fused_matvec(c, prec, r, p, so, sn, k == 0));
     } else {
       // generic path (asymmetric preconditioning): Ap = M^dag M p ; <p,Ap> ; r -= alpha Ap ; |r|^2
       void *Ap = scr(c, prec, 2);
@@ -1331,11 +1385,13 @@ static int cg_mixed(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol, 
   const double stop = tol * tol * b2;
   double r2 = b2, rNorm = sqrt(r2), r0Norm = rNorm, maxrx = rNorm, maxrr = rNorm;
   int k = 0, cur = 0;   // scal[SC_R2_0 + cur] holds r2
+  bool fresh_p = true;  // the search direction was (re)built by something other than the fused update: its faces have not been sent ahead
   const auto tl0 = std::chrono::steady_clock::now();
   c->cg_reliable_updates = 0;
   while (r2 > stop && k < maxiter) {
     const int so = SC_R2_0 + cur, sn = SC_R2_0 + (1 - cur);
-    TMQ_TRY(cg_fused_matvec(c, 4, rS, pS, so, sn));
+    TMQ_TRY(cg_fused_matvec(c, 4, rS, pS, so, sn, fresh_p));
+    fresh_p = false;
     double sc[3];   // SC_R2_0, SC_R2_1, SC_PAP are adjacent
     TMQ_TRY(fetch_scal(c, SC_R2_0, 3, sc));
     const double r2n = sc[sn - SC_R2_0], pap = sc[SC_PAP - SC_R2_0];
@@ -1366,6 +1422,7 @@ static int cg_mixed(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol, 
       rNorm = sqrt(r2);
       r0Norm = rNorm; maxrr = rNorm; maxrx = rNorm;
       c->cg_reliable_updates++;
+      fresh_p = true;
     }
     cur = 1 - cur;
     k++;
@@ -1681,7 +1738,7 @@ int tmq_time_kernel(tmq_ctx *c, int kind, int prec, int reps, const tmq_spinor *
       case 3: return op_mdagm(c, prec, dst, src, SC_T3);
       default: {
         const int so = SC_R2_0 + (it & 1), sn = SC_R2_0 + ((it + 1) & 1);
-        TMQ_TRY(cg_fused_matvec(c, prec, r, p, so, sn));
+        TMQ_TRY(cg_fused_matvec(c, prec, r, p, so, sn, it == 0));   // it == 0: p was just (re)written by a copy
         TMQ_TRY(cg_update(c, prec, dst, p, r, so, SC_PAP, sn, so));
         return 0;
       }

@@ -129,8 +129,9 @@ template <typename F> struct OpAxpyZpbx {   // y += a x ; x = z + b x
   }
 };
 template <typename F> struct OpCgUpdate {   // x += alpha p ; p = r + beta p, scalars read from the device block
-  VecT<F> *x, *p; const VecT<F> *r; const double *scal; int an, ad, bn, bd;
+  VecT<F> *x, *p; const VecT<F> *r; const double *scal; int an, ad, bn, bd, cg_iter;
   __device__ void operator()(size_t i, double *) const {
+    if (cg_iteration_is_stale(scal, cg_iter)) return;
     const F alpha = (F)(scal[an] / scal[ad]), beta = (F)(scal[bn] / scal[bd]);
     VecT<F> xv = x[i], pv = p[i], rv = r[i];
     xv.a += alpha * pv.a; xv.b += alpha * pv.b; xv.c += alpha * pv.c; xv.d += alpha * pv.d;
@@ -213,9 +214,9 @@ cudaError_t blas_axpy_zpbx(int prec, double a, void *x, void *y, const void *z, 
                   run<0>(OpAxpyZpbx<float>{(float)a, (float)b, VS(x), VS(y), CVS(z)}, n, NORED, st));
 }
 cudaError_t blas_cg_update(int prec, void *x, void *p, const void *r, size_t n, const double *scal, int an, int ad,
-                           int bn, int bd, cudaStream_t st) {
-  return DISPATCH(prec, run<0>(OpCgUpdate<double>{VD(x), VD(p), CVD(r), scal, an, ad, bn, bd}, n, NORED, st),
-                  run<0>(OpCgUpdate<float>{VS(x), VS(p), CVS(r), scal, an, ad, bn, bd}, n, NORED, st));
+                           int bn, int bd, cudaStream_t st, int cg_iter) {
+  return DISPATCH(prec, run<0>(OpCgUpdate<double>{VD(x), VD(p), CVD(r), scal, an, ad, bn, bd, cg_iter}, n, NORED, st),
+                  run<0>(OpCgUpdate<float>{VS(x), VS(p), CVS(r), scal, an, ad, bn, bd, cg_iter}, n, NORED, st));
 }
 cudaError_t blas_xpy_mixed(void *y_d, const void *x_s, size_t n, cudaStream_t st) {
   return run<0>(OpXpyMixed{VD(y_d), CVS(x_s)}, n, NORED, st);

@@ -211,6 +211,8 @@ int comm_allreduce(tmq_ctx *c, double *d_ptr, int n, cudaStream_t st) {
     R.rank = c->comm->rank; R.nranks = c->comm->nranks; R.seq = ++c->red_seq;
     R.err = c->scal + SC_ERR;
     R.timeout_ns = (unsigned long long)c->opt_halo_timeout_ms * 1000000ull;
+    R.cg_iter = c->cg_iter_cur;
+    R.cg_stop = (c->cg_iter_cur > 0 && (R.slot == SC_R2_0 || R.slot == SC_R2_1) && n == 1) ? 1 : 0;
     for (int r = 0; r < R.nranks; r++) {
       R.mbox[r] = (double *)(c->rank_arena[r] + c->arena_layout.mbox);
       R.mflag[r] = (unsigned int *)(c->rank_arena[r] + c->arena_layout.mflag);

@@ -70,6 +70,7 @@ template <> struct MinBlocksClover<float> { static constexpr int v = 5; };
 template <typename F, int RECON, int EPI, bool MULTI, bool CLOVER = false>
 __global__ void __launch_bounds__(TMQ_DSLASH_BLOCK, (CLOVER ? MinBlocksClover<F>::v : MinBlocks<F, EPI, RECON>::v))
 dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
+  if (cg_iteration_is_stale(A.scal, A.cg_iter)) return;      // block-uniform
   uint32_t blk = blockIdx.x;
   const Enum *en = &A.en;
   bool boundary = MULTI && A.all_boundary;
@@ -117,7 +118,8 @@ dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
       }
     }
   }
-  if (EpiTraits<EPI>::RED != 0) block_reduce_finalize<1>(red, A.partials, A.ticket, A.scal, A.red_slot, A.red_accum != 0);
+  if (EpiTraits<EPI>::RED != 0)
+    block_reduce_finalize<1>(red, A.partials, A.ticket, A.scal, A.red_slot, A.red_accum != 0, (EPI == EPI_CG4 && A.cg_local_stop) ? A.cg_iter : 0);
 }
 
 template <typename F, int RECON, int EPI>

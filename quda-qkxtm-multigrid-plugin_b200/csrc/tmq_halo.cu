@@ -19,6 +19,7 @@ namespace tmq {
 template <typename F, int RECON, int MU>
 __global__ void __launch_bounds__(128) halo_pack_kernel(const __grid_constant__ DslashArgs<F> A, VecT<F> *send_bwd,
                                                         VecT<F> *send_fwd) {
+  if (cg_iteration_is_stale(A.scal, A.cg_iter)) return;
   const int f = blockIdx.x * 128 + threadIdx.x;
   if (f >= A.g.face[MU]) return;
   const bool fwd = blockIdx.y == 1;
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(128) halo_pack_kernel(const __grid_constant__ 
 template <typename F, int RECON>
 __global__ void __launch_bounds__(128) halo_pack_p2p_kernel(const __grid_constant__ DslashArgs<F> A,
                                                             const __grid_constant__ PackDst<F> D) {
+  if (cg_iteration_is_stale(A.scal, A.cg_iter)) return;
   const int slot = blockIdx.z;
   const int mu = D.dim[slot];
   const bool fwd = blockIdx.y == 1;
@@ -116,6 +118,7 @@ cudaError_t halo_pack_p2p(int recon, const DslashArgs<float> &A, const PackDst<f
 template <typename F, int RECON>
 __global__ void __launch_bounds__(128) cg_update_pack_kernel(VecT<F> *x, VecT<F> *p, const VecT<F> *__restrict__ r, const double *scal, int an, int ad,
                                                              int bn, int bd, const __grid_constant__ DslashArgs<F> A) {
+  if (cg_iteration_is_stale(scal, A.cg_iter)) return;
   const Geom &g = A.g;
   const int idx = blockIdx.x * 128 + threadIdx.x;
   if (idx < g.Vh) {
@@ -164,6 +167,7 @@ cudaError_t cg_update_pack(int recon, void *x, void *p, const void *r, const dou
 
 // ---- scalar all-reduce over peer memory -------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) p2p_allreduce_kernel(const __grid_constant__ P2PRed R) {
+  if (cg_iteration_is_stale(R.scal, R.cg_iter)) return;
   const int t = threadIdx.x;
   const int buf = (int)(R.seq & 1u);
   if (t < R.nranks) {
@@ -193,6 +197,8 @@ __global__ void __launch_bounds__(32) p2p_allreduce_kernel(const __grid_constant
     double s = 0.0;
     for (int r = 0; r < R.nranks; r++) s += src[r];      // fixed rank order: identical bits on every rank
     R.scal[R.slot + t] = s;
+    // the CG's stopping test on the global |r|^2: every rank has the same bits, so every rank takes the same decision
+    if (t == 0 && R.cg_stop && R.cg_iter > 0 && s <= R.scal[SC_STOP] && R.scal[SC_DONE] == 0.0) R.scal[SC_DONE] = (double)R.cg_iter;
   }
 }
 cudaError_t p2p_allreduce(const P2PRed &R, cudaStream_t st) {

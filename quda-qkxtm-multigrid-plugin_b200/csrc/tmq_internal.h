@@ -50,7 +50,9 @@ struct tmq_ctx {
   int device;
   cudaStream_t stream;       // compute stream
   cudaStream_t comm_stream;  // halo exchange stream
-  cudaEvent_t ev_a, ev_b, ev_pack, ev_halo, ev_r2;
+  cudaEvent_t ev_a, ev_b, ev_pack, ev_halo, ev_r2, ev_r2b;
+  int cg_iter_cur = 0;       // > 0 while tmq_cg_mdagm enqueues iteration cg_iter_cur of a solve whose stopping test lags by one iteration
+  int opt_cg_lag = 1;        // TMQ_OPT_CG_LAG
   tmq::Geom g;
   int grid[4], coord[4];
   int nranks, rank;
@@ -175,6 +177,9 @@ struct HopSpec {
   // fused halo mode: this application's output is the input of the NEXT application (with dagger next_dagger): its boundary CTAs pack
   // and send the faces themselves.  Only set inside chains of applications that this library issues back to back.
   int pack_next = 0, next_dagger = 0;
+  // the faces of THIS application may have been sent ahead by the launch issued immediately before it.  Pointer equality of the field
+  // is not enough (a work field is rewritten between solves), so only the chains set it, for the links they issue back to back.
+  int accept_ahead = 0;
 };
 inline double tw_a(const tmq_ctx *c) { return 2.0 * c->kappa * c->mu; }
 inline Tw tw_A(const tmq_ctx *c, int dag) { return {1.0, dag ? -tw_a(c) : tw_a(c), 0, dag}; }
@@ -225,7 +230,7 @@ cudaError_t blas_xmy_norm(int prec, const void *x, void *y, size_t n, const Blas
 cudaError_t blas_axpy_zpbx(int prec, double a, void *x, void *y, const void *z, double b, size_t n, cudaStream_t st);
 // CG update with device-resident scalars: alpha = s[an]/s[ad], beta = s[bn]/s[bd];  x += alpha p ; p = r + beta p
 cudaError_t blas_cg_update(int prec, void *x, void *p, const void *r, size_t n, const double *scal, int an, int ad,
-                           int bn, int bd, cudaStream_t st);
+                           int bn, int bd, cudaStream_t st, int cg_iter = 0);
 // mixed precision accumulate: y(double) += x(float)
 cudaError_t blas_xpy_mixed(void *y_d, const void *x_s, size_t n, cudaStream_t st);
 // site-local twist / gamma5 on a parity block: out = c (in + i a g5 in)

@@ -16,13 +16,21 @@ enum {
   SC_ONE = 8, SC_ZERO = 9,
   SC_ERR = 10,                // raised by a Dslash kernel whose halo wait timed out
   SC_BARRIER = 11,            // scratch of tmq_barrier's all-reduce
+  SC_STOP = 12,               // CG: tol^2 |b|^2, the device-side copy of the stopping threshold
+  SC_DONE = 13,               // CG: 0 while iterating, else the (1-based) iteration whose residual met SC_STOP: launches of later iterations exit at once
   SC_COUNT = 16
 };
 
 #if defined(__CUDACC__)
+// launches of a CG iteration that the host enqueued before it knew that an earlier iteration had converged
+__device__ __forceinline__ bool cg_iteration_is_stale(const double *scal, int cg_iter) {
+  if (cg_iter <= 0) return false;
+  const double d = *((const volatile double *)(scal + SC_DONE));
+  return d != 0.0 && (double)cg_iter > d;
+}
 template <int N>
 __device__ __forceinline__ void block_reduce_finalize(double (&v)[N], double *partials, unsigned int *ticket,
-                                                      double *scal, int slot0, bool accum = false) {
+                                                      double *scal, int slot0, bool accum = false, int cg_iter_done = 0) {
   __shared__ double sm[32 * N];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -71,7 +79,13 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[N], double *pa
       double s = (lane < nwarp) ? sm[lane * N + j] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-      if (lane == 0) scal[slot0 + j] = accum ? scal[slot0 + j] + s : s;
+      if (lane == 0) {
+        const double tot = accum ? scal[slot0 + j] + s : s;
+        scal[slot0 + j] = tot;
+        // the CG's stopping test on the device (single rank: this IS the global sum): later iterations that the host has
+        // already enqueued find SC_DONE set and exit
+        if (j == 0 && cg_iter_done > 0 && tot <= scal[SC_STOP] && scal[SC_DONE] == 0.0) scal[SC_DONE] = (double)cg_iter_done;
+      }
     }
   }
 }

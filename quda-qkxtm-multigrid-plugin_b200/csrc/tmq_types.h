@@ -106,6 +106,8 @@ struct P2PRed {
   unsigned int *mflag[TMQ_MAX_RANKS];  // mflag[r]: rank r's flags [2 buf][TMQ_MAX_RANKS]
   double *err;
   unsigned long long timeout_ns;       // wall-clock limit of the wait for the other ranks' contributions
+  int cg_iter;                         // as DslashArgs::cg_iter
+  int cg_stop;                         // 1: slot holds |r|^2 of CG iteration cg_iter: apply the stopping test to the global sum
 };
 
 template <typename F> struct Epi {
@@ -174,6 +176,9 @@ template <typename F> struct DslashArgs {
   int prefetch;            // unused (the L2-prefetch experiment was removed: no gain, and it cost the 4th resident CTA)
   // fused compute + halo exchange (TMQ_OPT_HALO_P2P = 3): the boundary CTAs of THIS launch pack the faces of its output for the NEXT
   // application and store them into the neighbours' ghost arenas; the last boundary CTA publishes pk.seq in the neighbours' flags
+  int cg_iter;             // > 0: this launch belongs to CG iteration cg_iter (1-based) of a solve whose host loop runs one iteration
+                           // ahead of the residual read-back; it exits at once when an earlier iteration has converged (SC_DONE)
+  int cg_local_stop;       // 1: the reduction of this launch is the global |r|^2 (single rank): apply the stopping test on the device
   int pk_on;
   F pk_dsign;              // projector sign of the next application (+1: D, -1: D^dagger)
   PackDst<F> pk;
