@@ -276,7 +276,7 @@ def make_context(tmq, dist, rank, local_rank, X, grid, coord, args, n):
         ctx.comm_init(bytes(uid.numpy().tobytes()), n, rank)
     if args.tile:
         ctx.set_tile(*args.tile)
-    ctx.set_option(tmq.OPT_HALO_P2P, {"fused": 3, "p2p": 2, "store": 1, "nccl": 0}[args.halo])
+    ctx.set_option(tmq.OPT_HALO_P2P, {"fusedce": 4, "fused": 3, "p2p": 2, "store": 1, "nccl": 0}[args.halo])
     if args.boundary_at is not None:
         ctx.set_option(3, args.boundary_at)
     if args.pack_async is not None:
@@ -285,7 +285,8 @@ def make_context(tmq, dist, rank, local_rank, X, grid, coord, args, n):
 
 
 HALO_NAMES = {0: "none", 1: "nccl send/recv", 2: "peer-memory stores + fused launch", 3: "copy-engine peer copies + fused launch",
-              4: "fused compute + halo exchange: boundary CTAs store the next application's faces into the neighbours' arenas"}
+              4: "fused compute + halo exchange: boundary CTAs store the next application's faces into the neighbours' arenas",
+              5: "producer's boundary CTAs pack the next application's faces locally, copy-engine peer copies + fused launch"}
 
 
 def e2e_through_the_plugin(args, n, rank, local_rank, GX, grid, dist):
@@ -297,6 +298,7 @@ def e2e_through_the_plugin(args, n, rank, local_rank, GX, grid, dist):
     env["TMQ_COMM_ID_FILE"] = "/tmp/tmq_bench_id_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid())
     env["TMQ_COMM_NONCE"] = "bench-%d-%s" % (os.getppid(), os.environ.get("TORCHELASTIC_RUN_ID", "-"))
     env["LOCAL_RANK"] = str(local_rank)
+    env["TMQ_HALO_P2P"] = str({"fusedce": 4, "fused": 3, "p2p": 2, "store": 1, "nccl": 0}[args.halo])     # the same ghost exchange as the device-resident legs
     env.pop("OMP_NUM_THREADS", None)                     # the host-side field generator may use the cores
     cmd = [drv, "--dim"] + [str(v) for v in X] + ["--gridsize"] + [str(v) for v in grid] + \
           ["--test", "e2e", "--tol", repr(args.tol), "--niter", str(args.maxiter), "--recon", str(args.recon), "--kappa", repr(KAPPA), "--mu", repr(MU),
@@ -501,8 +503,9 @@ def main():
     ap.add_argument("--tile", type=int, nargs=3, default=None)
     ap.add_argument("--boundary-at", type=int, default=None, help="%% of interior CTAs scheduled before the boundary CTAs")
     ap.add_argument("--pack-async", type=int, default=None, help="1: launch the face pack on the exchange stream (TMQ_OPT_PACK_ASYNC)")
-    ap.add_argument("--halo", default="p2p", choices=["fused", "p2p", "store", "nccl"],
-                    help="ghost exchange: copy-engine peer copies (p2p) or peer stores from the pack kernel (store), both with one fused Dslash launch; or ncclSend/Recv")
+    ap.add_argument("--halo", default="fusedce", choices=["fusedce", "fused", "p2p", "store", "nccl"],
+                    help="ghost exchange (TMQ_OPT_HALO_P2P): fusedce = the producing launch packs the next faces locally + copy-engine peer copies (default); "
+                         "p2p = pack launch + copy-engine peer copies; fused / store = peer stores by the producing launch / the pack launch; nccl = ncclSend/Recv")
     ap.add_argument("--tol", type=float, default=1e-9)
     ap.add_argument("--maxiter", type=int, default=5000)
     ap.add_argument("--sloppy-prec", type=int, default=8, choices=[8, 4])

@@ -80,13 +80,18 @@ int tmq_set_option(tmq_ctx *, int option, int value);
  * M^dag M, the CG iteration) the boundary CTAs of the launch that PRODUCES a field pack its faces for the next application and store
  * them straight into the neighbours' arenas over NVLink, then publish the arrival flags: one kernel per application, no pack launch,
  * no copy-engine transfer, no NCCL call.  Only the first application of a chain uses the stand-alone pack launch of mode 1.
- * tmq_halo_mode returns 4.  */
+ * tmq_halo_mode returns 4.
+ * TMQ_OPT_HALO_P2P = 4: fused PACK + copy-engine push.  As mode 2, but inside those chains the producing launch's boundary CTAs project
+ * the faces of their output into this rank's own send buffers (local stores: no peer store, no system-scope fence, nothing published);
+ * the next application only has the copy engines push the buffers and the arrival flags, so the stand-alone pack launch and its place
+ * on the critical path are gone while no SM ever waits on NVLink.  tmq_halo_mode returns 5.  This is the DEFAULT (measured fastest on 2
+ * and 8 GPUs); the environment variable TMQ_HALO_P2P = 0..4 sets the initial mode of every context.  */
 /* TMQ_OPT_HALO_P2P selects the ghost exchange.  0: ncclSend/ncclRecv on a separate stream + interior / boundary
  * launches.  1: the pack kernel stores the faces straight into the neighbours' ghost arenas over NVLink peer mappings
- * (CUDA IPC, set up by tmq_comm_init).  2 (default): faces are packed locally and pushed by the copy engines into the
- * neighbours' arenas, overlapping the Dslash.  In modes 1 and 2 the Dslash is ONE launch whose boundary CTAs wait on
+ * (CUDA IPC, set up by tmq_comm_init).  2: faces are packed locally and pushed by the copy engines into the
+ * neighbours' arenas, overlapping the Dslash.  In modes 1 to 4 the Dslash is ONE launch whose boundary CTAs wait on
  * arrival flags and the CG scalars are all-reduced through peer-memory mailboxes.  tmq_halo_mode returns 0 (not
- * sharded), 1 (NCCL), 2 (peer stores) or 3 (peer copies); modes 2/3 need every rank's arena to be mappable.       */
+ * sharded), 1 (NCCL), 2 (peer stores), 3 (peer copies), 4, 5 (see above); all but 1 need every rank's arena to be mappable.       */
 int tmq_halo_mode(tmq_ctx *);
 
 /* ---- gauge: replaces loadGaugeQuda / freeGaugeQuda (qkxtm/Calc_Loops.cpp:759,806) ----------------------

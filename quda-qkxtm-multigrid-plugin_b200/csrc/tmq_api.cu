@@ -198,6 +198,19 @@ template <typename F> static void fill_pack_dst(tmq_ctx *c, PackDst<F> &D, unsig
   }
 }
 
+// halo mode 4: the producer packs into THIS rank's send-buffer set (sq & 1); no flags, no ticket -- the copy engines publish
+template <typename F> static void fill_pack_local(tmq_ctx *c, PackDst<F> &D, unsigned int sq) {
+  const int pi = sizeof(F) == 8 ? 0 : 1;
+  memset(&D, 0, sizeof(D));
+  D.seq = sq;
+  for (int d = 2; d < 4; d++) {
+    if (!c->g.part[d]) continue;
+    const int sl = D.nslot++;
+    D.dim[sl] = d;
+    for (int dir = 0; dir < 2; dir++) D.dst[sl][dir] = (VecT<F> *)((sq & 1u) ? c->halo_send2[pi][d][dir] : c->halo_send[pi][d][dir]);
+  }
+}
+
 template <typename F>
 static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) {
   const int prec = (int)sizeof(F);
@@ -308,6 +321,68 @@ static int apply_hop_t(tmq_ctx *c, void *out, const void *in, const HopSpec &s) 
     }
     TMQ_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
     A.hw.seq = seq & (SEQ_TABLE - 1); A.hw.exact = 1;
+    A.en = en_int; A.en_b[0] = en_t; A.en_b[1] = en_z;
+    A.nblk[0] = nblocks(en_int); A.nblk[1] = nblocks(en_t); A.nblk[2] = nblocks(en_z);
+    A.npre = (int)((long long)A.nblk[0] * c->opt_pre_pct / 100);
+    TMQ_CUDA(launch_any<F>(c, s.epi, true, A, c->stream));
+    c->launches++;
+    if (has_red) TMQ_TRY(comm_allreduce(c, c->scal + s.red_slot, 1, c->stream));
+    return 0;
+  }
+
+  if (c->p2p && c->opt_p2p == 4) {
+    // ---- fused pack + copy-engine push.  As mode 2, but inside a chain of launches the stand-alone pack launch is gone: the boundary
+    //      CTAs of the launch that PRODUCES a field project the faces of their output for the next application into this rank's own
+    //      send buffers (plain local stores: no peer store, no system fence, nothing published), and the next application only has the
+    //      copy engines push those buffers and the arrival flags.  Nothing leaves this rank before the consuming application is issued,
+    //      so faces packed ahead for an application that never comes are simply dropped.
+    //      The compute stream never waits for the exchange stream.  Two sets of send buffers, set (N & 1) for application N, make that
+    //      safe: set (N+1)&1 is written by the boundary CTAs of kernel N only after they have seen the flags of application N from
+    //      every neighbour (or by a pack / update launch queued behind kernel N); a neighbour sends N only after ITS kernel N-1 has
+    //      completed, whose boundary CTAs waited for our faces of N-1 -- so our copies of N-1, the last readers of that set, are done.
+    //      (Launches that exit early after convergence of a lagged CG do not wait: cg_double drains both streams and all ranks then.)
+    const unsigned int seq = ++c->halo_seq;
+    const int buf = (int)(seq & 1u);
+    const HaloArena &L = c->arena_layout;
+    const bool sent_ahead = s.accept_ahead && c->prepacked_seq == seq && c->prepacked_in == in && c->prepacked_dagger == s.dagger &&
+                            c->prepacked_parity == s.out_parity && c->prepacked_prec == prec;
+    c->prepacked_seq = 0;
+    void *(*snd)[4][2] = buf ? c->halo_send2 : c->halo_send;
+    if (!sent_ahead) {
+      for (int d = 2; d < 4; d++)
+        if (g.part[d]) {
+          TMQ_CUDA(pack_any<F>(c, A, d, snd[pi][d][0], snd[pi][d][1], c->stream));
+          c->launches++;
+        }
+    }
+    const int dbg = c->opt_debug;       // timing experiments only (results are wrong): 1 = boundary CTAs do not wait, 2 = no copies
+    if (!(dbg & 2)) {
+      TMQ_CUDA(cudaEventRecord(c->ev_pack, c->stream));
+      TMQ_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+    }
+    for (int d = 2; d < 4; d++) {
+      if (!g.part[d]) continue;
+      const size_t nbytes = (size_t)3 * g.face[d] * vec_bytes(prec);
+      for (int dir = 0; dir < 2; dir++) {
+        char *peer = c->peer_arena[d][dir];
+        if (!(dbg & 2)) {
+        TMQ_CUDA(cudaMemcpyAsync(peer + L.recv[buf][pi][d][1 - dir], snd[pi][d][dir], nbytes, cudaMemcpyDeviceToDevice, c->comm_stream));
+        TMQ_CUDA(cudaMemcpyAsync(peer + arena_flag_off(L, buf, d, 1 - dir), c->seq_table + (seq & (SEQ_TABLE - 1)), sizeof(unsigned int),
+                                 cudaMemcpyDeviceToDevice, c->comm_stream));
+        }
+        A.ghost[d][dir] = (const VecT<F> *)(c->arena + L.recv[buf][pi][d][dir]);
+        A.hw.flag[A.hw.n++] = (const unsigned int *)(c->arena + arena_flag_off(L, buf, d, dir));
+      }
+    }
+    A.hw.seq = seq & (SEQ_TABLE - 1); A.hw.exact = 1;
+    if (dbg & 1) A.hw.n = 0;
+    if (s.pack_next && out != nullptr && s.epi != EPI_CG4) {
+      fill_pack_local<F>(c, A.pk, seq + 1);
+      A.pk_on = 2;
+      A.pk_dsign = s.next_dagger ? (F)-1 : (F)1;
+      c->prepacked_seq = seq + 1; c->prepacked_in = out; c->prepacked_dagger = s.next_dagger ? 1 : 0;
+      c->prepacked_parity = 1 - s.out_parity; c->prepacked_prec = prec;
+    }
     A.en = en_int; A.en_b[0] = en_t; A.en_b[1] = en_z;
     A.nblk[0] = nblocks(en_int); A.nblk[1] = nblocks(en_t); A.nblk[2] = nblocks(en_z);
     A.npre = (int)((long long)A.nblk[0] * c->opt_pre_pct / 100);
@@ -522,8 +597,14 @@ template <typename F> static int cg_update_fused(tmq_ctx *c, void *x, void *p, c
   A.gauge = gs.d;
   A.parity = c->matpc & 1;                           // p lives on the parity the preconditioned operator acts on
   const unsigned int next = c->halo_seq + 1;
-  fill_pack_dst<F>(c, A.pk, next);
-  A.pk_on = 1; A.pk_dsign = (F)1;
+  if (c->opt_p2p == 4) {
+    fill_pack_local<F>(c, A.pk, next);
+    A.pk_on = 2;
+  } else {
+    fill_pack_dst<F>(c, A.pk, next);
+    A.pk_on = 1;
+  }
+  A.pk_dsign = (F)1;
   A.cg_iter = c->cg_iter_cur;
   TMQ_CUDA(cg_update_pack(c->recon, x, p, r, c->scal, an, ad, bn, bd, A, c->stream));
   c->launches++;
@@ -531,7 +612,7 @@ template <typename F> static int cg_update_fused(tmq_ctx *c, void *x, void *p, c
   return 0;
 }
 int cg_update(tmq_ctx *c, int prec, void *x, void *p, const void *r, int an, int ad, int bn, int bd) {
-  if (c->multi && c->p2p && c->opt_p2p == 3 && c->matpc < 2)
+  if (c->multi && c->p2p && c->opt_p2p >= 3 && c->matpc < 2)
     return prec == 8 ? cg_update_fused<double>(c, x, p, r, an, ad, bn, bd) : cg_update_fused<float>(c, x, p, r, an, ad, bn, bd);
   TMQ_CUDA(blas_cg_update(prec, x, p, r, (size_t)6 * c->g.Vh, c->scal, an, ad, bn, bd, c->stream, c->cg_iter_cur));
   c->launches++;
@@ -659,6 +740,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->comm = nullptr; c->launches = 0; c->stage = nullptr; c->stage_bytes = 0;
   c->recon = 0; c->t_boundary = 1; c->kappa = 0; c->mu = 0; c->matpc = 0; c->op_set = false;
   memset(c->halo_send, 0, sizeof(c->halo_send));
+  memset(c->halo_send2, 0, sizeof(c->halo_send2));
   memset(c->halo_recv, 0, sizeof(c->halo_recv));
   Geom &g = c->g;
   memset(&g, 0, sizeof(g));
@@ -676,11 +758,12 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->tile[0] = 4; c->tile[1] = 4; c->tile[2] = 2;
   c->opt_prefetch = 0;
   c->opt_smear_block_t = 0;
-  c->opt_pack_async = 0;
+  c->opt_pack_async = 0; c->opt_debug = 0;
   c->opt_halo_timeout_ms = 120000;
   if (const char *e = getenv("TMQ_HALO_TIMEOUT_MS")) { const int v = atoi(e); if (v > 0) c->opt_halo_timeout_ms = v; }
+  if (const char *e = getenv("TMQ_HALO_P2P")) { const int v = atoi(e); if (v >= 0 && v <= 4) c->opt_p2p = v; }   // as TMQ_OPT_HALO_P2P
   c->opt_pre_pct = 50; c->red_seq = 0; memset(c->rank_arena, 0, sizeof(c->rank_arena));
-  c->opt_p2p = 2; c->p2p = false; c->seq_table = nullptr; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
+  c->opt_p2p = 4; c->p2p = false; c->seq_table = nullptr; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
   memset(c->peer_arena, 0, sizeof(c->peer_arena));
 
   bool ok = true;
@@ -745,6 +828,7 @@ int tmq_force_partition(tmq_ctx *c, const int part[4]) {
         if (!c->g.part[d] || c->halo_send[pi][d][dir]) continue;
         const size_t nbytes = (size_t)3 * c->g.face[d] * vec_bytes(pi == 0 ? 8 : 4);
         TMQ_CUDA(cudaMalloc(&c->halo_send[pi][d][dir], nbytes));
+        TMQ_CUDA(cudaMalloc(&c->halo_send2[pi][d][dir], nbytes));
         TMQ_CUDA(cudaMalloc(&c->halo_recv[pi][d][dir], nbytes));
       }
   // ghost arena of the peer-memory path; a partitioned dimension on a grid of extent 1 wraps onto this rank, so
@@ -780,6 +864,7 @@ int tmq_destroy(tmq_ctx *c) {
     for (int d = 0; d < 4; d++)
       for (int dir = 0; dir < 2; dir++) {
         if (c->halo_send[pi][d][dir]) cudaFree(c->halo_send[pi][d][dir]);
+        if (c->halo_send2[pi][d][dir]) cudaFree(c->halo_send2[pi][d][dir]);
         if (c->halo_recv[pi][d][dir]) cudaFree(c->halo_recv[pi][d][dir]);
       }
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -853,18 +938,20 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
   switch (option) {
     case TMQ_OPT_PREFETCH: c->opt_prefetch = value ? 1 : 0; return 0;
     case TMQ_OPT_PACK_ASYNC: c->opt_pack_async = value ? 1 : 0; return 0;
+    case 99: c->opt_debug = value; return 0;   // timing experiments (tools/shard_shape_study.py); results are wrong when set
     case TMQ_OPT_CONTRACT_SLICES: c->opt_contract_slices = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_SMEAR_BLOCK_T: c->opt_smear_block_t = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_CG_LAG: c->opt_cg_lag = value ? 1 : 0; return 0;
     case TMQ_OPT_HALO_TIMEOUT_MS: c->opt_halo_timeout_ms = value > 0 ? value : 120000; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {
-      c->opt_p2p = value < 0 ? 0 : (value > 3 ? 3 : value);
+      c->opt_p2p = value < 0 ? 0 : (value > 4 ? 4 : value);
       c->prepacked_seq = 0;
       bool all_mapped = c->multi;
       for (int d = 2; d < 4; d++)
         if (c->g.part[d]) all_mapped = all_mapped && c->peer_arena[d][0] && c->peer_arena[d][1];
       TMQ_CUDA(cudaStreamSynchronize(c->stream));
+      if (c->comm_stream) TMQ_CUDA(cudaStreamSynchronize(c->comm_stream));
       c->p2p = c->opt_p2p && all_mapped;
       return 0;
     }
@@ -1317,6 +1404,7 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
       // launches that exited early published no arrival flags: forget the faces "sent ahead" and let every rank drain before the
       // sequence numbers continue (the skipped ones are never waited for)
       c->prepacked_seq = 0;
+      if (c->comm_stream) TMQ_CUDA(cudaStreamSynchronize(c->comm_stream));
       if (c->nranks > 1) TMQ_TRY(comm_barrier(c));
     }
   } else

@@ -104,16 +104,18 @@ dslash_kernel(const __grid_constant__ DslashArgs<F> A) {
     // fused halo exchange: pack this launch's output faces for the next application into the neighbours' arenas (block-uniform branch)
     if (boundary && A.pk_on) {
       if (e < (uint32_t)en->nsites && ghosts_ok) pack_out<F, RECON>(A, *en, e);
-      __threadfence_system();            // this thread's peer stores are ordered before the ticket
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const unsigned int nb = (unsigned int)(A.nblk[1] + A.nblk[2]);
-        const unsigned int t = atomicInc(A.pk.ticket, nb - 1);
-        if (t == nb - 1) {
-          __threadfence_system();
-          for (int s = 0; s < A.pk.nslot; s++)
-            for (int d = 0; d < 2; d++)
-              asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.pk.flag[s][d]), "r"(A.pk.seq) : "memory");
+      if (A.pk_on == 1) {                  // peer stores (halo mode 3); mode 4 packs into local send buffers and the copy engines publish
+        __threadfence_system();            // this thread's peer stores are ordered before the ticket
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          const unsigned int nb = (unsigned int)(A.nblk[1] + A.nblk[2]);
+          const unsigned int t = atomicInc(A.pk.ticket, nb - 1);
+          if (t == nb - 1) {
+            __threadfence_system();
+            for (int s = 0; s < A.pk.nslot; s++)
+              for (int d = 0; d < 2; d++)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.pk.flag[s][d]), "r"(A.pk.seq) : "memory");
+          }
         }
       }
     }

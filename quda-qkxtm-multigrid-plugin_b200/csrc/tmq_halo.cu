@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(128) cg_update_pack_kernel(VecT<F> *x, VecT<F>
     const int t = idx / vol3, rem = idx - t * vol3, z = rem / plane, rem2 = rem - z * plane, y = rem2 / g.Xh, xh = rem2 - y * g.Xh;
     if (on_packed_boundary(A, z, t)) pack_spinor<F, RECON>(A, ps, idx, xh, y, z, t);
   }
+  if (A.pk_on == 2) return;              // halo mode 4: the faces went into this rank's own send buffers; the copy engines publish
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {

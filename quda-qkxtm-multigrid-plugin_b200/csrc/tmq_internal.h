@@ -82,6 +82,7 @@ struct tmq_ctx {
   double *h_scal_dev;        // the same memory as the device sees it (written by scal_to_host_kernel)
   // halo buffers per precision: [dim][dir] send / recv, vec[3][face]
   void *halo_send[2][4][2];
+  void *halo_send2[2][4][2];   // second set of send buffers (halo mode 4: the faces of application N+1 are packed while the copies of N still read)
   void *halo_recv[2][4][2];
   tmq::Comm *comm;
   long long launches;
@@ -103,6 +104,7 @@ struct tmq_ctx {
   // timing-kernel scratch (tmq_time_kernel)
   int sms;
   int opt_prefetch;
+  int opt_debug;             // timing experiments only (option 99)
   int opt_pack_async;        // copy-engine halo path: launch the face pack on the exchange stream, beside the Dslash
   int opt_smear_block_t;     // time slices per L2-resident block of the Gaussian smearing (0 = from the L2 size)
   // peer-memory halo path

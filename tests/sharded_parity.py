@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--lattice", type=int, nargs=4, default=[8, 8, 8, 16])
     ap.add_argument("--grid", type=int, nargs=4, default=[1, 1, 1, 2])
     ap.add_argument("--recon", type=int, default=12)
-    ap.add_argument("--p2p", type=int, default=2)
+    ap.add_argument("--p2p", type=int, default=4)
     ap.add_argument("--pack-async", type=int, default=0)
     ap.add_argument("--clover", type=int, default=1, help="also check the twisted-clover variant")
     ap.add_argument("--amin", type=float, default=0.2, help="lower edge of the Chebyshev window (just above the wanted eigenvalues)")

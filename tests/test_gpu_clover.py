@@ -151,7 +151,7 @@ def test_clover_on_the_ghost_zone_path(tmq, part):
     clov = orc.clover_compute(gauge, CSW * KAPPA)
     full = lu.spinor_eo_from_lex(lu.gaussian_spinor_lex(X, seed=101), X)
     even = np.ascontiguousarray(full[: orc.Vh])
-    for p2p in (2, 0):
+    for p2p in (4, 2, 0):
         c = tmq.Context(X)
         c.force_partition(part)
         c.set_option(tmq.OPT_HALO_P2P, p2p)

@@ -16,7 +16,7 @@ def test_hot_path_under_guarded_allocations():
     env = dict(os.environ, TMQ_GUARD_BYTES="4096")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_target.py"), "all", "4"], capture_output=True, text=True, env=env, timeout=1500)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert p.stdout.count("sanitize target:") == 13                      # plain + 4 modes x 3 partitions
+    assert p.stdout.count("sanitize target:") == 16                      # plain + 5 modes x 3 partitions
     assert "guard check: 0 corrupted allocations" in p.stdout and "TMQ_GUARD_BYTES=4096" in p.stdout
 
 

@@ -211,7 +211,7 @@ def test_mixed_precision_cg_reaches_fp64_residual(tmq, recon):
 @pytest.mark.parametrize("part", [(0, 0, 0, 1), (0, 0, 1, 0), (0, 0, 1, 1)])
 @pytest.mark.parametrize("recon", [12, 18])
 @pytest.mark.parametrize("prec", [8, 4])
-@pytest.mark.parametrize("p2p", [3, 2, 1, 0])
+@pytest.mark.parametrize("p2p", [4, 3, 2, 1, 0])
 def test_ghost_zone_path_equals_periodic_path(tmq, part, recon, prec, p2p):
     """--partition style self-exchange (qkxtm/QKXTM_util.cpp:1717-1720): pack -> exchange -> interior +
     boundary launches must reproduce the single-launch result and the oracle."""

@@ -1,6 +1,6 @@
 """The hot path on 8^3 x 16 -- hop, M^dag M, M_pc, fp64 and mixed CG, Chebyshev filter, prepare / reconstruct, the full operator, blas
 reductions, the containers' ghost exchange and plaquette -- plainly and with the ghost-zone path forced on one GPU in each halo mode
-(tmq_force_partition; mode 3 fused compute + peer stores, mode 2 copy-engine peer copies + flag waits, mode 1 peer stores + ticket,
+(tmq_force_partition; mode 4 fused pack + copy-engine push, mode 3 fused compute + peer stores, mode 2 copy-engine peer copies + flag waits, mode 1 peer stores + ticket,
 mode 0 NCCL-style staging), every result checked against the CPU oracle.
 
 Two uses: (1) the target of tools/sanitize.sh (compute-sanitizer memcheck / racecheck / synccheck / initcheck) where the tool is
@@ -85,7 +85,7 @@ if __name__ == "__main__":
     o = Oracle(X)
     gauge = tmq.gen_gauge(X, seed=137, t_boundary=-1)
     full = tmq.gen_spinor(X, "gaussian", seed=101)
-    for w in (["plain", "mode3", "mode2", "mode1", "mode0"] if what == "all" else [what]):
+    for w in (["plain", "mode4", "mode3", "mode2", "mode1", "mode0"] if what == "all" else [what]):
         if w == "plain":
             run(None, 0, iters, o, gauge, full)
         else:
