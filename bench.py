@@ -321,6 +321,10 @@ def e2e_through_the_plugin(args, n, rank, local_rank, GX, grid, dist):
             "columns": r["nsrc"], "secs": r["multi_secs"], "iterations": r["multi_iter"], "true_res": r["multi_true_res"],
             "solver_secs": r["multi_solver_secs"], "solver_ms_per_iter": r["multi_solver_secs"] / max(r["multi_iter"], 1) * 1e3,
             "h2d_bytes_total": int(field * r["nsrc"]), "d2h_bytes_total": int(field * r["nsrc"]),
+            "host_link": {"what": "pinned host <-> device copies of the same fields, all %d ranks at once, summed over the ranks (tmq_host_link_probe): "
+                                  "what the box gives the e2e legs; the pipelined leg moves h2d_bytes_total + d2h_bytes_total in `secs`" % n,
+                          "h2d_GBps": r.get("link_h2d_gbs"), "d2h_GBps": r.get("link_d2h_gbs"), "duplex_GBps": r.get("link_duplex_gbs"),
+                          "pipelined_leg_GBps": 2 * field * r["nsrc"] / r["multi_secs"] * 1e-9},
             "single_solve": {"what": "one invertQuda, fp64 (nothing to hide the 2 x %.2f GB of PCIe traffic behind)" % (field / 1e9), "value": gf(r["single_iter"], r["single_secs"]),
                              "secs": r["single_secs"], "iterations": r["single_iter"], "true_res": r["single_true_res"]},
             "single_solve_mixed": {"what": "one invertQuda, cuda_prec_sloppy = single, reliable_delta = 1e-4 (the reference drivers' setting)",

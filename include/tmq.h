@@ -69,9 +69,9 @@ int tmq_force_partition(tmq_ctx *, const int part[4]);
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
 enum { TMQ_OPT_PREFETCH = 1, TMQ_OPT_HALO_P2P = 2, TMQ_OPT_BOUNDARY_AT_PCT = 3, TMQ_OPT_SMEAR_BLOCK_T = 4, TMQ_OPT_PACK_ASYNC = 5,
        TMQ_OPT_CONTRACT_SLICES = 6 /* > 0: time slices per pass of the baryon / derivative contractions (default: what fits 2 GiB) */,
-       TMQ_OPT_CG_LAG = 8 /* 1 (default): the fp64 CG's host loop runs one iteration ahead of the |r|^2 read-back, the stopping test is
+       TMQ_OPT_CG_LAG = 8 /* L = 1 (default) .. 6: the fp64 CG's host loop runs L iterations ahead of the |r|^2 it reads, the stopping test is
                              also taken on the device and launches enqueued past convergence exit at once -- same iterates, same iteration
-                             count as the synchronous loop (0) */,
+                             count as the synchronous loop (0).  Environment: TMQ_CG_LAG */,
        TMQ_OPT_HALO_TIMEOUT_MS = 7 /* wall-clock limit (ms, default 120000; env TMQ_HALO_TIMEOUT_MS) of a device-side wait for a neighbour's
                                       ghost face or all-reduce contribution; on expiry nothing is computed from stale ghosts, the device
                                       error scalar is raised and the enclosing call (tmq_sync, tmq_cg_mdagm, ...) fails */ };   /* TMQ_OPT_PREFETCH: accepted and ignored (the L2-prefetch experiment was removed: no gain) */
@@ -312,6 +312,10 @@ int tmq_spinor_from_prefetch(tmq_spinor *dst_full, int slot, int host_order);   
 /* convert (times scale) into download slot `slot` on the compute stream, then copy to h_full on the download stream; returns at once */
 int tmq_spinor_to_host_async(double *h_full, const tmq_spinor *src_full, int slot, int host_order, double scale);
 int tmq_host_wait(tmq_ctx *);                                                     /* every outstanding upload / download is complete  */
+/* measurement aid: `reps` uploads of a full host field alone, `reps` downloads alone, then both at once, on the streams and staging
+ * slots of the pipeline above; secs[0..2] = wall time of the three phases on this rank (bench.py reports the host-link bandwidth the
+ * end-to-end numbers are bounded by, per GPU and with every rank of a node copying at once)                                          */
+int tmq_host_link_probe(tmq_ctx *, const double *h_src_full, double *h_dst_full, int reps, double secs[3]);
 int tmq_host_alloc_pinned(tmq_ctx *, void **ptr, size_t bytes);
 int tmq_host_free_pinned(tmq_ctx *, void *ptr);
 int tmq_host_register(tmq_ctx *, void *ptr, size_t bytes);                        /* page-lock a caller-owned buffer (idempotent)      */

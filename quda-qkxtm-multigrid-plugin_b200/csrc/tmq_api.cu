@@ -564,6 +564,12 @@ int scal_to_host(tmq_ctx *c, int slot, int n) {
   TMQ_CUDA(cudaGetLastError());
   return 0;
 }
+// one scalar into entry `ring` of the host ring behind the scalar block (the lagged CG reads |r|^2 of several iterations back)
+static int scal_to_host_ring(tmq_ctx *c, int slot, int ring) {
+  scal_to_host_kernel<<<1, 32, 0, c->stream>>>(c->h_scal_dev + SC_COUNT + ring, c->scal + slot, 1);
+  TMQ_CUDA(cudaGetLastError());
+  return 0;
+}
 int fetch_scal(tmq_ctx *c, int slot, int n, double *out) {
   TMQ_TRY(scal_to_host(c, slot, n));
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
@@ -761,6 +767,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->opt_pack_async = 0; c->opt_debug = 0;
   c->opt_halo_timeout_ms = 120000;
   if (const char *e = getenv("TMQ_HALO_TIMEOUT_MS")) { const int v = atoi(e); if (v > 0) c->opt_halo_timeout_ms = v; }
+  if (const char *e = getenv("TMQ_CG_LAG")) { const int v = atoi(e); if (v >= 0 && v <= 6) c->opt_cg_lag = v; }       // as TMQ_OPT_CG_LAG
   if (const char *e = getenv("TMQ_HALO_P2P")) { const int v = atoi(e); if (v >= 0 && v <= 4) c->opt_p2p = v; }   // as TMQ_OPT_HALO_P2P
   c->opt_pre_pct = 50; c->red_seq = 0; memset(c->rank_arena, 0, sizeof(c->rank_arena));
   c->opt_p2p = 4; c->p2p = false; c->seq_table = nullptr; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
@@ -778,7 +785,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   ok = ok && cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_r2, cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaEventCreateWithFlags(&c->ev_r2b, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 8; i++) ok = ok && cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming) == cudaSuccess;
   c->sms = 148;
   cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
   size_t nblk = (size_t)(g.Vh + 127) / 128 + 1;
@@ -789,7 +796,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   ok = ok && cudaMalloc(&c->ticket2, sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->seq_table, SEQ_TABLE * sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->scal, SC_COUNT * sizeof(double)) == cudaSuccess;
-  ok = ok && cudaHostAlloc((void **)&c->h_scal, SC_COUNT * sizeof(double), cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void **)&c->h_scal, (SC_COUNT + 8) * sizeof(double), cudaHostAllocMapped) == cudaSuccess;
   ok = ok && cudaHostGetDevicePointer((void **)&c->h_scal_dev, c->h_scal, 0) == cudaSuccess;
   if (ok) {
     double init[SC_COUNT];
@@ -882,7 +889,7 @@ int tmq_destroy(tmq_ctx *c) {
   if (c->ev_pack) cudaEventDestroy(c->ev_pack);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->ev_r2) cudaEventDestroy(c->ev_r2);
-  if (c->ev_r2b) cudaEventDestroy(c->ev_r2b);
+  for (int i = 0; i < 8; i++) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   delete c;
@@ -941,7 +948,7 @@ int tmq_set_option(tmq_ctx *c, int option, int value) {
     case 99: c->opt_debug = value; return 0;   // timing experiments (tools/shard_shape_study.py); results are wrong when set
     case TMQ_OPT_CONTRACT_SLICES: c->opt_contract_slices = value < 0 ? 0 : value; return 0;
     case TMQ_OPT_SMEAR_BLOCK_T: c->opt_smear_block_t = value < 0 ? 0 : value; return 0;
-    case TMQ_OPT_CG_LAG: c->opt_cg_lag = value ? 1 : 0; return 0;
+    case TMQ_OPT_CG_LAG: c->opt_cg_lag = value < 0 ? 0 : (value > 6 ? 6 : value); return 0;
     case TMQ_OPT_HALO_TIMEOUT_MS: c->opt_halo_timeout_ms = value > 0 ? value : 120000; return 0;
     case TMQ_OPT_BOUNDARY_AT_PCT: c->opt_pre_pct = value < 0 ? 0 : (value > 100 ? 100 : value); return 0;
     case TMQ_OPT_HALO_P2P: {
@@ -1225,6 +1232,23 @@ int tmq_host_wait(tmq_ctx *c) {
   TMQ_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
+int tmq_host_link_probe(tmq_ctx *c, const double *h_src, double *h_dst, int reps, double secs[3]) {
+  TMQ_REQUIRE(c && h_src && h_dst && secs && reps > 0, "bad argument");
+  TMQ_TRY(io_ensure(c));
+  TMQ_TRY(tmq_host_wait(c));
+  const size_t bytes = (size_t)2 * c->g.Vh * 24 * sizeof(double);
+  for (int phase = 0; phase < 3; phase++) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; r++) {
+      if (phase != 1) TMQ_CUDA(cudaMemcpyAsync(c->io_up[r & 1], h_src, bytes, cudaMemcpyHostToDevice, c->up_stream));
+      if (phase != 0) TMQ_CUDA(cudaMemcpyAsync(h_dst, c->io_down[r & 1], bytes, cudaMemcpyDeviceToHost, c->down_stream));
+    }
+    TMQ_CUDA(cudaStreamSynchronize(c->up_stream));
+    TMQ_CUDA(cudaStreamSynchronize(c->down_stream));
+    secs[phase] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return 0;
+}
 int tmq_host_alloc_pinned(tmq_ctx *c, void **ptr, size_t bytes) {
   TMQ_REQUIRE(c && ptr, "null argument");
   TMQ_CUDA(cudaSetDevice(c->device));
@@ -1371,34 +1395,41 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
   if (lag) {
     c->h_scal[SC_STOP] = stop; c->h_scal[SC_DONE] = 0.0;
     TMQ_CUDA(cudaMemcpyAsync(c->scal + SC_STOP, c->h_scal + SC_STOP, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    cudaEvent_t ev[2] = {c->ev_r2, c->ev_r2b};
-    int done = -1;
+    // the host runs L iterations ahead of the |r|^2 it reads (L = TMQ_OPT_CG_LAG): iteration k is enqueued, then the residual of
+    // iteration k - L is looked at.  The device takes the same test in the reduction itself, so nothing is computed past convergence.
+    const int L = c->opt_cg_lag < 1 ? 1 : (c->opt_cg_lag > 6 ? 6 : c->opt_cg_lag);
+    const double *ring = c->h_scal + SC_COUNT;
+    int done = -1, seen = 0;              // seen: iterations whose residual the host has read
+    auto look = [&](int j) -> int {       // residual after iteration j (0-based); 1 = converged, -1 = broke down
+      if (cudaEventSynchronize(c->ev_ring[j & 7]) != cudaSuccess) { set_error("cudaEventSynchronize failed"); return -1; }
+      r2 = ring[j & 7];
+      c->cg_hist.push_back(r2);
+      seen = j + 1;
+      if (!(r2 == r2)) { set_error("CG broke down (NaN residual) at iteration %d", j + 1); return -1; }
+      return r2 <= stop ? 1 : 0;
+    };
     while (k < maxiter) {
       const int so = SC_R2_0 + (k & 1), sn = SC_R2_0 + ((k + 1) & 1);
       c->cg_iter_cur = k + 1;
       int rc = cg_fused_matvec(c, prec, r, p, so, sn, k == 0);
-      if (!rc) rc = scal_to_host(c, sn, 1);
-      if (!rc && cudaEventRecord(ev[k & 1], c->stream) != cudaSuccess) rc = 1;
+      if (!rc) rc = scal_to_host_ring(c, sn, k & 7);
+      if (!rc && cudaEventRecord(c->ev_ring[k & 7], c->stream) != cudaSuccess) rc = 1;
       if (!rc) rc = cg_update(c, prec, x->d, p, r, so, SC_PAP, sn, so);
       c->cg_iter_cur = 0;
       if (rc) return rc;
-      if (k >= 1) {                       // |r|^2 of iteration k - 1, while iteration k runs
-        TMQ_CUDA(cudaEventSynchronize(ev[(k - 1) & 1]));
-        r2 = c->h_scal[so];
-        c->cg_hist.push_back(r2);
-        if (!(r2 == r2)) { set_error("CG broke down (NaN residual) at iteration %d", k); return 1; }
-        if (r2 <= stop) { done = k; break; }   // k iterations count; the device skipped iteration k + 1 (index k)
-      }
       k++;
-    }
-    if (done < 0) {                       // maxiter reached: the last iteration's |r|^2 has not been read yet
-      if (k >= 1) {
-        TMQ_CUDA(cudaEventSynchronize(ev[(k - 1) & 1]));
-        r2 = c->h_scal[SC_R2_0 + (k & 1)];
-        c->cg_hist.push_back(r2);
-        if (!(r2 == r2)) { set_error("CG broke down (NaN residual) at iteration %d", k); return 1; }
+      if (k > L) {
+        const int v = look(k - 1 - L);
+        if (v < 0) return 1;
+        if (v > 0) { done = seen; break; }      // `seen` iterations count; the device skipped the ones enqueued after them
       }
-    } else k = done;
+    }
+    while (done < 0 && seen < k) {              // maxiter reached: the residuals of the last L iterations have not been read yet
+      const int v = look(seen);
+      if (v < 0) return 1;
+      if (v > 0) done = seen;
+    }
+    if (done >= 0) k = done;
     TMQ_CUDA(cudaStreamSynchronize(c->stream));
     if (c->multi) {
       // launches that exited early published no arrival flags: forget the faces "sent ahead" and let every rank drain before the

@@ -50,9 +50,10 @@ struct tmq_ctx {
   int device;
   cudaStream_t stream;       // compute stream
   cudaStream_t comm_stream;  // halo exchange stream
-  cudaEvent_t ev_a, ev_b, ev_pack, ev_halo, ev_r2, ev_r2b;
+  cudaEvent_t ev_a, ev_b, ev_pack, ev_halo, ev_r2;
+  cudaEvent_t ev_ring[8];    // lagged CG: recorded behind the |r|^2 read-back of iteration k (entry k & 7)
   int cg_iter_cur = 0;       // > 0 while tmq_cg_mdagm enqueues iteration cg_iter_cur of a solve whose stopping test lags by one iteration
-  int opt_cg_lag = 1;        // TMQ_OPT_CG_LAG
+  int opt_cg_lag = 1;        // TMQ_OPT_CG_LAG: iterations the host loop runs ahead of the residual it reads (0: synchronous loop)
   tmq::Geom g;
   int grid[4], coord[4];
   int nranks, rank;

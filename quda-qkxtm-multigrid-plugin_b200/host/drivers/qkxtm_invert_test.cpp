@@ -250,10 +250,21 @@ int main(int argc, char **argv) {
     inv_param.cuda_prec_sloppy = sloppy_saved;
     // the last solution is returned (even-odd host order) so that the caller can check it
     result.assign(hx[(nsrc - 1) & 1], hx[(nsrc - 1) & 1] + (size_t)V * 24);
+    // the host link these numbers are bounded by, with every rank of the job copying at once: uploads alone, downloads alone, both
+    double link[3] = {0, 0, 0};
+    {
+      const int reps = 3;
+      double s3[3];
+      comm_barrier();
+      if (tmq_host_link_probe(qkxtm_context(), hb[0], hx[nsrc & 1], reps, s3)) { fprintf(stderr, "%s\n", tmq_last_error()); return 1; }
+      for (int i = 0; i < 3; i++) link[i] = (double)nbytes * reps * (i == 2 ? 2 : 1) / s3[i] * 1e-9;      // this rank's GB/s
+      if (tmq_allreduce_host(qkxtm_context(), link, 3)) { fprintf(stderr, "%s\n", tmq_last_error()); return 1; }   // summed over the ranks
+    }
     if (root)
       printf("RESULT_E2E {\"single_secs\": %.6f, \"single_iter\": %d, \"single_true_res\": %.6e, \"mixed_secs\": %.6f, \"mixed_iter\": %d, "
              "\"mixed_true_res\": %.6e, \"nsrc\": %d, \"multi_secs\": %.6f, \"multi_iter\": %d, \"multi_true_res\": %.6e, \"multi_solver_secs\": %.6f, "
-             "\"bytes_per_field\": %zu}\n", t_single, it_single, res_single, t_mixed, it_mixed, res_mixed, nsrc, t_multi, it_multi, res_multi, solver_secs_multi, nbytes);
+             "\"bytes_per_field\": %zu, \"link_h2d_gbs\": %.2f, \"link_d2h_gbs\": %.2f, \"link_duplex_gbs\": %.2f}\n", t_single, it_single, res_single, t_mixed, it_mixed,
+             res_mixed, nsrc, t_multi, it_multi, res_multi, solver_secs_multi, nbytes, link[0], link[1], link[2]);
     for (int k = 0; k < 2; k++) { tmq_host_free_pinned(qkxtm_context(), hb[k]); tmq_host_free_pinned(qkxtm_context(), hx[k]); }
   } else if (test == "calcloops") {
     // qkxtm/Calc_Loops.cpp main() (:585-791): arpackInfo, loopInfo, the operator of the eigensolver, then calc_loops.  The hook stands where

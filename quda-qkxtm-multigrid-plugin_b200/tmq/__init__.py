@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("TMQ_LIB_PATH") or os.path.join(os.path.dirname(_HERE)
 
 PREC_SINGLE, PREC_DOUBLE = 4, 8
 OPT_PREFETCH, OPT_HALO_P2P, OPT_BOUNDARY_AT_PCT, OPT_SMEAR_BLOCK_T = 1, 2, 3, 4
+OPT_PACK_ASYNC, OPT_CONTRACT_SLICES, OPT_HALO_TIMEOUT_MS, OPT_CG_LAG = 5, 6, 7, 8
 OPT_PACK_ASYNC, OPT_CONTRACT_SLICES = 5, 6
 PARITY, FULL = 1, 2
 MATPC_EVEN_EVEN, MATPC_ODD_ODD, MATPC_EVEN_EVEN_ASYM, MATPC_ODD_ODD_ASYM = 0, 1, 2, 3
@@ -31,7 +32,7 @@ tmq_caxpy tmq_cxpaypbz tmq_norm2 tmq_redot tmq_cdot tmq_axpy_norm tmq_xmy_norm t
 tmq_qkxtm_plaquette tmq_qkxtm_scale tmq_qkxtm_cast tmq_qkxtm_gamma5 tmq_qkxtm_absorb tmq_dev_malloc tmq_dev_free tmq_dev_memset
 tmq_h2d tmq_d2h tmq_time_kernel tmq_launch_count tmq_poly_mdagm tmq_eigset_alloc tmq_eigset_free tmq_eigset_size
 tmq_eigset_vector tmq_eigensolve tmq_deflate tmq_project tmq_qkxtm_gauss_smear tmq_timer_start tmq_timer_stop tmq_clover_load tmq_clover_free
-tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d tmq_barrier tmq_host_prefetch tmq_spinor_from_prefetch tmq_spinor_to_host_async tmq_host_wait tmq_host_alloc_pinned tmq_host_free_pinned tmq_host_register tmq_host_unregister tmq_cg_stats tmq_qkxtm_ghost_sites tmq_qkxtm_exchange_ghost tmq_guard_check tmq_allreduce_host""".split()
+tmq_qkxtm_conjugate tmq_qkxtm_gamma5_prop tmq_qkxtm_rotate_physical tmq_qkxtm_column_copy tmq_qkxtm_contract_mesons tmq_qkxtm_contract_baryons tmq_qkxtm_seq_source tmq_qkxtm_fixsink_local tmq_qkxtm_fixsink_derivative tmq_d2d tmq_barrier tmq_host_prefetch tmq_spinor_from_prefetch tmq_spinor_to_host_async tmq_host_wait tmq_host_alloc_pinned tmq_host_free_pinned tmq_host_register tmq_host_unregister tmq_cg_stats tmq_qkxtm_ghost_sites tmq_qkxtm_exchange_ghost tmq_guard_check tmq_allreduce_host tmq_host_link_probe""".split()
 
 
 class TmqError(RuntimeError):

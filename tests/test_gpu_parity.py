@@ -269,6 +269,40 @@ def test_ghost_zone_path_equals_periodic_path(tmq, part, recon, prec, p2p):
     c.close()
 
 
+@pytest.mark.parametrize("part", [None, (0, 0, 0, 1), (0, 0, 1, 1)])
+def test_cg_host_loop_ahead_of_the_residual_gives_the_same_iterates(tmq, part):
+    """TMQ_OPT_CG_LAG: the host enqueues L iterations ahead of the |r|^2 it reads and the device takes the stopping test itself; launches
+    enqueued past convergence exit at once.  Iteration count, residual history and solution must be those of the synchronous loop
+    (L = 0) bit for bit, also when maxiter cuts the solve short inside the look-ahead window."""
+    X = LATTICES[1]
+    s = get_setup(tmq, X, 12)
+    ref = None
+    for lag in (0, 1, 2, 3, 6):
+        c = tmq.Context(X)
+        if part is not None:
+            c.force_partition(part)
+        c.set_option(tmq.OPT_CG_LAG, lag)
+        c.load_gauge(s.gauge, t_boundary=-1, recon=12)
+        c.set_op(KAPPA, MU, tmq.MATPC_EVEN_EVEN)
+        b, x = c.spinor(), c.spinor()
+        b.set(s.even)
+        info = c.cg_mdagm(x, b, tol=1e-9, maxiter=5000)
+        hist = c.cg_history(info["iter"] + 1)                          # |b|^2, then |r|^2 after every iteration
+        x1 = x.get().copy()
+        cut = c.cg_mdagm(x, b, tol=1e-9, maxiter=info["iter"] - 2)      # stops on maxiter with unread residuals in flight
+        x2 = x.get().copy()
+        again = c.cg_mdagm(x, b, tol=1e-9, maxiter=5000)                # and the context is fit for the next solve
+        got = (info["iter"], info["true_res"], cut["iter"], cut["true_res"], again["iter"])
+        if ref is None:
+            ref = (got, x1, x2, hist)
+        else:
+            assert got == ref[0], (lag, got, ref[0])
+            assert np.array_equal(x1, ref[1]) and np.array_equal(x2, ref[2]) and np.array_equal(x.get(), ref[1]), lag
+            assert np.array_equal(hist, ref[3]), lag
+        assert cut["iter"] == info["iter"] - 2
+        c.close()
+
+
 def test_blas_against_numpy(tmq):
     X = LATTICES[1]
     s = get_setup(tmq, X, 18); c = s.ctx

@@ -8,7 +8,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 
 timeout 300 $TR --master-port 29518 tests/sharded_parity.py --lattice 8 8 16 32 --grid 1 1 2 4 --p2p 4 --eig 0 > $OUT/n8_${TAG}_parity_z2t4.log 2>&1; echo "parity TxZ rc=$?"
 grep -o "rank [0-9]/8[^;]*;[^;]*; failures: \[[^]]*\]" $OUT/n8_${TAG}_parity_z2t4.log | cut -c1-200
 timeout 600 $TR --master-port 29519 bench.py --gpus 8 --steps 20 --warmup 5 --halo fusedce --no-cpu > $OUT/n8_${TAG}_fusedce.json 2> $OUT/n8_${TAG}_fusedce.err; echo "fusedce rc=$?"
-timeout 500 $TR --master-port 29520 bench.py --gpus 8 --steps 20 --warmup 5 --halo p2p --no-cpu --no-e2e > $OUT/n8_${TAG}_p2p.json 2> $OUT/n8_${TAG}_p2p.err; echo "p2p rc=$?"
+timeout 500 $TR --master-port 29520 bench.py --gpus 8 --steps 20 --warmup 5 --halo p2p --no-cpu --no-e2e --scale64 0 > $OUT/n8_${TAG}_p2p.json 2> $OUT/n8_${TAG}_p2p.err; echo "p2p rc=$?"
 python - <<PY
 import json
 for h in ('fusedce','p2p'):
