@@ -767,10 +767,10 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
   c->opt_pack_async = 0; c->opt_debug = 0;
   c->opt_halo_timeout_ms = 120000;
   if (const char *e = getenv("TMQ_HALO_TIMEOUT_MS")) { const int v = atoi(e); if (v > 0) c->opt_halo_timeout_ms = v; }
-  if (const char *e = getenv("TMQ_CG_LAG")) { const int v = atoi(e); if (v >= 0 && v <= 6) c->opt_cg_lag = v; }       // as TMQ_OPT_CG_LAG
-  if (const char *e = getenv("TMQ_HALO_P2P")) { const int v = atoi(e); if (v >= 0 && v <= 4) c->opt_p2p = v; }   // as TMQ_OPT_HALO_P2P
   c->opt_pre_pct = 50; c->red_seq = 0; memset(c->rank_arena, 0, sizeof(c->rank_arena));
   c->opt_p2p = 4; c->p2p = false; c->seq_table = nullptr; c->arena = nullptr; c->halo_seq = 0; c->ticket2 = nullptr;
+  if (const char *e = getenv("TMQ_CG_LAG")) { const int v = atoi(e); if (v >= 0 && v <= 6) c->opt_cg_lag = v; }       // as TMQ_OPT_CG_LAG
+  if (const char *e = getenv("TMQ_HALO_P2P")) { const int v = atoi(e); if (v >= 0 && v <= 4) c->opt_p2p = v; }   // as TMQ_OPT_HALO_P2P
   memset(c->peer_arena, 0, sizeof(c->peer_arena));
 
   bool ok = true;
@@ -1391,7 +1391,8 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
   // enqueues iteration k+1, then reads |r|^2 of iteration k.  The test itself also runs on the device (the launch that completes the
   // global |r|^2 sets SC_DONE); the launches of an iteration enqueued after convergence exit at once, so x, r, p and the iteration
   // count are exactly those of the synchronous loop.  Not with NCCL all-reduces (their result is not tested on the device).
-  const bool lag = fused && c->opt_cg_lag && (c->nranks == 1 || (c->multi && c->p2p));
+  // (nor with the split interior / boundary launches of halo mode 0, whose first launch only holds a partial |r|^2)
+  const bool lag = fused && c->opt_cg_lag && ((!c->multi && c->nranks == 1) || (c->multi && c->p2p));
   if (lag) {
     c->h_scal[SC_STOP] = stop; c->h_scal[SC_DONE] = 0.0;
     TMQ_CUDA(cudaMemcpyAsync(c->scal + SC_STOP, c->h_scal + SC_STOP, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
