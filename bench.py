@@ -481,7 +481,7 @@ def run_native(args):
                 "run": {"local_lattice": list(X), "grid": list(grid), "halo": halo_mode, "recon": recon,
                         "step": "1 CG iteration = 4 Dslash launches + 1 fused update launch, no host sync (tmq_time_kernel kind 4)",
                         "timing": "CUDA events on libtmq's compute stream, max over ranks; wall %.3f s" % wall},
-                "solver_loop": {"what": "the same iteration inside tmq_cg_mdagm: its iteration loop with the per-iteration stopping test (host reads |r|^2), wall clock inside the library, max over ranks",
+                "solver_loop": {"what": "the same iteration inside tmq_cg_mdagm: its iteration loop with the stopping test (taken on the device; the host reads |r|^2 one iteration behind the launches), wall clock inside the library, max over ranks",
                                 "ms_per_iter": solver_ms, "iterations": loop["iter"], "value": FLOPS_ITER * Vh_glob / (solver_ms * 1e-3) * 1e-9},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
                 "gpu_launches_total": int(l1 - l0),
