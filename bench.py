@@ -320,6 +320,7 @@ def e2e_through_the_plugin(args, n, rank, local_rank, GX, grid, dist):
                     "iteration, bytes amortised per iteration" % (r["nsrc"], args.tol),
             "columns": r["nsrc"], "secs": r["multi_secs"], "iterations": r["multi_iter"], "true_res": r["multi_true_res"],
             "solver_secs": r["multi_solver_secs"], "solver_ms_per_iter": r["multi_solver_secs"] / max(r["multi_iter"], 1) * 1e3,
+            "halo": HALO_NAMES.get(r.get("halo_mode"), "?"), "last_column_cg_loop_secs": r.get("last_column_loop_secs"),
             "h2d_bytes_total": int(field * r["nsrc"]), "d2h_bytes_total": int(field * r["nsrc"]),
             "host_link": {"what": "pinned host <-> device copies of the same fields, all %d ranks at once, summed over the ranks (tmq_host_link_probe): "
                                   "what the box gives the e2e legs; the pipelined leg moves h2d_bytes_total + d2h_bytes_total in `secs`" % n,

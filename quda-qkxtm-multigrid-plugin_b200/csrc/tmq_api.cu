@@ -564,10 +564,13 @@ int scal_to_host(tmq_ctx *c, int slot, int n) {
   TMQ_CUDA(cudaGetLastError());
   return 0;
 }
-// one scalar into entry `ring` of the host ring behind the scalar block (the lagged CG reads |r|^2 of several iterations back)
+// The lagged CG's read-back of |r|^2 of one iteration: entry `ring` of the host ring behind the scalar block, and the event the host
+// waits on.  (Moving the store to a stream of its own was tried against the slow-down of the iteration next to bulk PCIe copies on
+// 8 GPUs and changed nothing, profiles/r2_e2e_n8.md; it stays on the compute stream.)
 static int scal_to_host_ring(tmq_ctx *c, int slot, int ring) {
   scal_to_host_kernel<<<1, 32, 0, c->stream>>>(c->h_scal_dev + SC_COUNT + ring, c->scal + slot, 1);
   TMQ_CUDA(cudaGetLastError());
+  TMQ_CUDA(cudaEventRecord(c->ev_ring[ring], c->stream));
   return 0;
 }
 int fetch_scal(tmq_ctx *c, int slot, int n, double *out) {
@@ -741,7 +744,7 @@ tmq_ctx *tmq_create(int device, const int localX[4], const int grid[4], const in
 
   tmq_ctx *c = new tmq_ctx();
   c->device = device;
-  c->stream = nullptr; c->comm_stream = nullptr;
+  c->stream = nullptr; c->comm_stream = nullptr; memset(c->ev_ring, 0, sizeof(c->ev_ring));
   c->partials = nullptr; c->ticket = nullptr; c->scal = nullptr; c->h_scal = nullptr;
   c->comm = nullptr; c->launches = 0; c->stage = nullptr; c->stage_bytes = 0;
   c->recon = 0; c->t_boundary = 1; c->kappa = 0; c->mu = 0; c->matpc = 0; c->op_set = false;
@@ -1414,7 +1417,6 @@ static int cg_double(tmq_ctx *c, tmq_spinor *x, const tmq_spinor *b, double tol,
       c->cg_iter_cur = k + 1;
       int rc = cg_fused_matvec(c, prec, r, p, so, sn, k == 0);
       if (!rc) rc = scal_to_host_ring(c, sn, k & 7);
-      if (!rc && cudaEventRecord(c->ev_ring[k & 7], c->stream) != cudaSuccess) rc = 1;
       if (!rc) rc = cg_update(c, prec, x->d, p, r, so, SC_PAP, sn, so);
       c->cg_iter_cur = 0;
       if (rc) return rc;

@@ -247,6 +247,10 @@ int main(int argc, char **argv) {
     const double t_multi = secs(t0, now());
     const int it_multi = inv_param.iter;
     const double res_multi = inv_param.true_res, solver_secs_multi = inv_param.secs;
+    double last_loop_secs = 0;                                                  // iteration loop of the last column's CG, and the ghost exchange in use
+    int last_reliable = 0;
+    tmq_cg_stats(qkxtm_context(), &last_loop_secs, &last_reliable);
+    const int halo_mode = tmq_halo_mode(qkxtm_context());
     inv_param.cuda_prec_sloppy = sloppy_saved;
     // the last solution is returned (even-odd host order) so that the caller can check it
     result.assign(hx[(nsrc - 1) & 1], hx[(nsrc - 1) & 1] + (size_t)V * 24);
@@ -263,8 +267,8 @@ int main(int argc, char **argv) {
     if (root)
       printf("RESULT_E2E {\"single_secs\": %.6f, \"single_iter\": %d, \"single_true_res\": %.6e, \"mixed_secs\": %.6f, \"mixed_iter\": %d, "
              "\"mixed_true_res\": %.6e, \"nsrc\": %d, \"multi_secs\": %.6f, \"multi_iter\": %d, \"multi_true_res\": %.6e, \"multi_solver_secs\": %.6f, "
-             "\"bytes_per_field\": %zu, \"link_h2d_gbs\": %.2f, \"link_d2h_gbs\": %.2f, \"link_duplex_gbs\": %.2f}\n", t_single, it_single, res_single, t_mixed, it_mixed,
-             res_mixed, nsrc, t_multi, it_multi, res_multi, solver_secs_multi, nbytes, link[0], link[1], link[2]);
+             "\"bytes_per_field\": %zu, \"link_h2d_gbs\": %.2f, \"link_d2h_gbs\": %.2f, \"link_duplex_gbs\": %.2f, \"halo_mode\": %d, \"last_column_loop_secs\": %.6f}\n", t_single, it_single, res_single, t_mixed, it_mixed,
+             res_mixed, nsrc, t_multi, it_multi, res_multi, solver_secs_multi, nbytes, link[0], link[1], link[2], halo_mode, last_loop_secs);
     for (int k = 0; k < 2; k++) { tmq_host_free_pinned(qkxtm_context(), hb[k]); tmq_host_free_pinned(qkxtm_context(), hx[k]); }
   } else if (test == "calcloops") {
     // qkxtm/Calc_Loops.cpp main() (:585-791): arpackInfo, loopInfo, the operator of the eigensolver, then calc_loops.  The hook stands where
