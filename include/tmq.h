@@ -63,7 +63,9 @@ int tmq_barrier(tmq_ctx *);
 int tmq_allreduce_host(tmq_ctx *, double *h, size_t n);
 /* force the ghost-zone (pack -> exchange -> interior/boundary) path in dimension d even when grid[d] = 1,
  * where the exchange wraps onto this rank: the reference's --partition mask (qkxtm/QKXTM_util.cpp:1717-1720).
- * Only z (part[2]) and t (part[3]) may be set.  Must be called before any field is created.              */
+ * Only z (part[2]) and t (part[3]) may be set.  Must be called before any field is created.  A test / debugging aid: do not keep the
+ * host pipeline (tmq_host_prefetch / tmq_spinor_to_host_async) busy next to a self-exchanged solve in the copy-engine halo modes --
+ * the same-device face copies can queue behind the bulk copies until the halo wait times out (profiles/r2_e2e_n8.md).       */
 int tmq_force_partition(tmq_ctx *, const int part[4]);
 /* tuning knobs (tile of the thread->site map); 0 keeps the default                                        */
 int tmq_set_tile(tmq_ctx *, int ty, int tz, int tt);
