@@ -265,6 +265,53 @@ def committed_traffic(prec, recon, X):
         return None, None
 
 
+def f_rows_leg(tmq, ctx, b_par, prec, recon, X, peak):
+    """SURVEY 8f rows on the resident lattice, each timed with CUDA events inside libtmq and set against its algorithmic bytes
+    (DESIGN.md section 4).  Never fatal: a failure is reported in the key instead of losing the bench line."""
+    out = {}
+    Vh = int(np.prod(X)) // 2
+    gbs = lambda bytes_per_site, sites, ms: bytes_per_site * sites / (ms * 1e-3) * 1e-9
+    try:   # f1: one degree of the Chebyshev-accelerated MdagM (4 Dslash launches, recurrence fused into the 4th)
+        ms, nl = ctx.time_kernel(5, prec, 10, b_par)
+        bps = (12 * 24 + 32 * recon) * prec
+        out["chebyshev_degree"] = {"ms": ms, "launches": nl, "bytes_per_site": bps, "GB/s": gbs(bps, Vh, ms), "frac_of_hbm_peak": gbs(bps, Vh, ms) / peak}
+    except Exception as e:
+        out["chebyshev_degree"] = {"error": str(e)[:200]}
+    try:   # f3: twisted-clover, hop + A^-1 and the fused CG iteration (site matrices: 72 complex per site and application)
+        ctx.clover_load(1.57551 * KAPPA)
+        ms1, _ = ctx.time_kernel(1, prec, 10, b_par)
+        ms4, _ = ctx.time_kernel(4, prec, 10, b_par)
+        cl = 72 * 2 * prec
+        b1 = (24 + 24 + 8 * recon) * prec + cl
+        b4 = (24 * 16 + 32 * recon) * prec + 3 * cl + 24 * prec
+        out["twisted_clover"] = {"hop+Ainv_ms": ms1, "hop+Ainv_bytes_per_site": b1, "hop+Ainv_frac_of_hbm_peak": gbs(b1, Vh, ms1) / peak,
+                                 "cg_iter_ms": ms4, "cg_iter_bytes_per_site": b4, "cg_iter_frac_of_hbm_peak": gbs(b4, Vh, ms4) / peak}
+        ctx.clover_free()
+    except Exception as e:
+        out["twisted_clover"] = {"error": str(e)[:200]}
+        try: ctx.clover_free()
+        except Exception: pass
+    try:   # f2: Gaussian smearing in the containers' layout, streaming order, fp64
+        V = 2 * Vh
+        nb_vec, nb_g = V * 24 * 8, V * 72 * 8
+        bufs = [ctx.dev_malloc(nb_vec), ctx.dev_malloc(nb_vec), ctx.dev_malloc(nb_g)]
+        try:
+            for pp, nn in zip(bufs, (nb_vec, nb_vec, nb_g)):
+                ctx.L.tmq_dev_memset(ctx.h, pp, 0x3c, nn)           # small normal numbers (timing only; parity is tests/test_gpu_smear.py)
+            ctx.qkxtm_gauss_smear(bufs[1], bufs[0], bufs[2], 8, 2, 0.25)
+            ctx.timer_start()
+            ctx.qkxtm_gauss_smear(bufs[1], bufs[0], bufs[2], 8, 20, 0.25)
+            ms = ctx.timer_stop() / 20
+            bps = (24 + 24 + 54) * 8
+            out["gauss_smearing_step"] = {"ms": ms, "bytes_per_site": bps, "GB/s": gbs(bps, V, ms), "frac_of_hbm_peak": gbs(bps, V, ms) / peak}
+        finally:
+            for pp in bufs:
+                ctx.dev_free(pp)
+    except Exception as e:
+        out["gauss_smearing_step"] = {"error": str(e)[:200]}
+    return out
+
+
 def make_context(tmq, dist, rank, local_rank, X, grid, coord, args, n):
     ctx = tmq.Context(X, grid=grid, coord=coord, device=local_rank)
     if n > 1:
@@ -450,6 +497,12 @@ def run_native(args):
                                 "frac_of_hbm_peak": bb * Vh_loc / (kern[kind] * 1e-3) * 1e-9 / peak}
     step_gbs = step_bytes_per_site(prec, recon) * Vh_loc / (ms_step * 1e-3) * 1e-9
 
+    # ---- the "next" rows of SURVEY 8f on the same resident lattice (N = 1 only; a few seconds): driver-visible numbers for the
+    #      Chebyshev filter, the twisted-clover iteration and the Gaussian smearing, each against its own algorithmic bytes
+    frows = None
+    if n == 1 and not args.no_frows:
+        frows = f_rows_leg(tmq, ctx, b_par, prec, recon, X, peak)
+
     # ---- CPU baseline on rank 0, N=1 only (bounded sample of the same workload)
     cpu = None
     if n == 1 and not args.no_cpu:
@@ -487,7 +540,7 @@ def run_native(args):
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
                 "gpu_launches_total": int(l1 - l0),
                 "step_hbm_gbs": step_gbs, "step_frac_of_hbm_peak": step_gbs / peak,
-                "kernels": kernels, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "scale64": s64}
+                "kernels": kernels, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "scale64": s64, "f_rows": frows}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -517,6 +570,7 @@ def main():
     ap.add_argument("--delta", type=float, default=1e-4, help="reliable_delta of the mixed-precision solve (the reference drivers set 1e-4, qkxtm/Calc_Loops.cpp:481)")
     ap.add_argument("--e2e-solves", type=int, default=2, help="repetitions of the single-solve legs of the e2e measurement")
     ap.add_argument("--e2e-columns", type=int, default=12, help="right-hand sides of the pipelined e2e leg (a propagator has 12 columns)")
+    ap.add_argument("--no-frows", action="store_true", help="skip the Chebyshev / clover / smearing timings (N = 1 only)")
     ap.add_argument("--scale64", type=int, default=1, help="also time 64^3x128 (BASELINE.json configs[4]) and emit its solution checksum")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
