@@ -15,6 +15,9 @@ One JSON line on stdout (rank 0).  Definitions (DESIGN.md section "Measurement")
   roofline the hop + A^-1 Dslash kernel (EPI_TW, half of all Dslash launches) timed alone with CUDA events:
            algorithmic bytes (24 + 24 + 8*12) * 8 = 1152 B per output parity site (fp64, recon 12)
   scale64  BASELINE.json configs[4], 64^3x128 sharded T then Z (T x Z at 8 GPUs): ms per fused CG iteration and the checksum of a solve
+  f_rows   N = 1: one Chebyshev degree, the twisted-clover hop + A^-1 and CG iteration, one Gaussian smearing step, each
+           timed with CUDA events inside libtmq and set against its algorithmic bytes
+  e2e.host_link  pinned host <-> device bandwidth with every rank of the job copying at once (what the box gives the e2e legs)
   cpu_baseline / --impl reference: the CPU oracle (oracle/, a port: the reference's own host code cannot be
            built here) running CG iterations of the same 48^3x96 workload on all host cores
 """
